@@ -222,7 +222,9 @@ def record_reeds_shepp(mods, n, seed):
             syaw = 0.0; gyaw = [0.0, math.pi / 2, math.pi, -math.pi / 2][(i // 10) % 4]
             gx, gy = sx + round(r), sy + [0.0, 1.0, -2.0][(i // 40) % 3]
         q[i] = [sx, sy, syaw, gx, gy, gyaw]
-        paths = rs.calc_all_paths(sx, sy, syaw, gx, gy, gyaw, maxc, 0.1)
+        # the env passes an np.float64 heading (vehicle.py:93) and float x/y/goal; the scalar type
+        # decides how builtin sum() accumulates word lengths (see oracle/c py_sum), so mimic it
+        paths = rs.calc_all_paths(float(sx), float(sy), np.float64(syaw), float(gx), float(gy), float(gyaw), maxc, 0.1)
         assert len(paths) <= MAXP
         npaths[i] = len(paths)
         for k, p in enumerate(paths):
@@ -260,12 +262,17 @@ def main():
     ap.add_argument("--episodes", type=int, default=3)
     ap.add_argument("--scenes", type=int, default=96)
     ap.add_argument("--follow-episodes", type=int, default=12)
+    ap.add_argument("--only", default=None, help="'rs' or 'tables': regenerate just that fixture")
     args = ap.parse_args()
     out = os.path.abspath(args.out)
     mods = _import_reference(args.ref)
     os.makedirs(out, exist_ok=True)
-    np.savez_compressed(os.path.join(out, "mask_table.npz"), **record_mask_table(mods))
-    np.savez_compressed(os.path.join(out, "reeds_shepp.npz"), **record_reeds_shepp(mods, 400, 7))
+    if args.only in (None, "tables"):
+        np.savez_compressed(os.path.join(out, "mask_table.npz"), **record_mask_table(mods))
+    if args.only in (None, "rs"):
+        np.savez_compressed(os.path.join(out, "reeds_shepp.npz"), **record_reeds_shepp(mods, 400, 7))
+    if args.only is not None:
+        return
     for level in ("Normal", "Complex", "Extrem"):
         np.savez_compressed(os.path.join(out, f"scenes_{level}.npz"), **record_scenes(mods, level, args.scenes, 42))
         ep = record_episodes(mods, level, args.episodes, 42)
