@@ -1,0 +1,194 @@
+"""BatchedParkingEnv — N independent parking scenes stepped on one B200 through the C ABI.
+
+Batched counterpart of the reference's single-env surface
+    CarParkingWrapper.reset / .step     src/env/env_wrapper.py:58-85
+    CarParking.reset / .step            src/env/car_parking_base.py:127-138, 235-299
+Observation keys, dtypes (float64) and layouts are the reference's, with a leading env axis:
+    obs['lidar'] (N,120)  obs['target'] (N,5)  obs['action_mask'] (N,42)  obs['img'] None
+`action_mask[:, j]`: j<21 forward, j>=21 backward, steer 0.75-0.075*(j%21)  (configs.py:108-115).
+
+PyTorch is used for device memory and streams only; all compute is in libhope_b200.so.  There
+is no CPU fallback: constructing the env without CUDA raises.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi, tables
+
+LEVELS = {"Normal": 0, "Complex": 1, "Extrem": 2}
+_NP = {C.c_double: np.float64, C.c_uint8: np.uint8, C.c_int32: np.int32}
+
+
+def generate_scenes(n, level="Normal", seed=42, nthreads=0):
+    """Host-side procedural scenes (parking_map_normal.py:40-494 semantics, own RNG streams).
+    level: 'Normal' | 'Complex' | 'Extrem' | 'mix' (i % 3 cycles the three, BASELINE cfg 3)."""
+    lib = capi.load_library()
+    if level == "mix":
+        parts = [generate_scenes((n - k + 2) // 3, lv, seed + 1000003 * k, nthreads) for k, lv in enumerate(LEVELS)]
+        out = {key: np.zeros((n,) + parts[0][key].shape[1:], dtype=parts[0][key].dtype) for key in parts[0]}
+        for k in range(3):
+            for key in out:
+                out[key][k::3] = parts[k][key]
+        return out
+    sc = dict(start=np.zeros((n, 3)), dest=np.zeros((n, 3)), bounds=np.zeros((n, 4)),
+              obs=np.zeros((n, capi.MAX_OBS, capi.MAX_VERTS, 2)), nverts=np.zeros((n, capi.MAX_OBS), dtype=np.int32),
+              case_id=np.zeros(n, dtype=np.int32))
+    capi.check(lib.hope_generate_scenes(n, LEVELS[level], seed, nthreads, sc["start"].ctypes.data, sc["dest"].ctypes.data,
+                                        sc["bounds"].ctypes.data, sc["obs"].ctypes.data, sc["nverts"].ctypes.data,
+                                        sc["case_id"].ctypes.data))
+    return sc
+
+
+class BatchedParkingEnv(object):
+    def __init__(self, n_envs, scenes=None, pool_size=None, level="Normal", seed=42, device=0, auto_reset=True,
+                 params=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise capi.HopeError("BatchedParkingEnv needs a CUDA device; there is no CPU path")
+        self.torch = torch
+        self.lib = capi.load_library()
+        self.n = int(n_envs)
+        self.device = torch.device("cuda", device)
+        if scenes is None:
+            pool_size = pool_size or 2 * self.n
+            scenes = generate_scenes(pool_size, level, seed)
+        self.scenes = scenes
+        self.pool_size = int(scenes["start"].shape[0])
+        self.params = capi.Params()
+        capi.check(self.lib.hope_default_params(C.byref(self.params)))
+        self.params.auto_reset = 1 if auto_reset else 0
+        for k, v in (params or {}).items():
+            setattr(self.params, k, v)
+        self.ctx = C.c_void_p()
+        capi.check(self.lib.hope_create(C.byref(self.ctx), device, self.n, self.pool_size, C.byref(self.params)), self.ctx)
+        tb = tables.host_tables()
+        capi.check(self.lib.hope_upload_tables(self.ctx, *[tb[k].ctypes.data for k in
+                                                            ("ray_a", "ray_b", "lidar_base", "mask_base", "dist_star", "w_lo", "w_hi")]), self.ctx)
+        self.set_scene_pool(scenes)
+        # device outputs (torch owns the memory; the library only sees raw pointers)
+        self.out = {}
+        self._out_struct = capi.Out()
+        for name, ct, shape in capi.OUT_FIELDS:
+            tdt = {C.c_double: torch.float64, C.c_uint8: torch.uint8, C.c_int32: torch.int32}[ct]
+            t = torch.zeros((self.n,) + shape, dtype=tdt, device=self.device)
+            self.out[name] = t
+            setattr(self._out_struct, name, t.data_ptr())
+        self._host = None
+
+    # ------------------------------------------------------------------------------------------
+    def set_scene_pool(self, scenes, first=0):
+        f8 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        s, d, b, o = f8(scenes["start"]), f8(scenes["dest"]), f8(scenes["bounds"]), f8(scenes["obs"])
+        nv = np.ascontiguousarray(scenes["nverts"], dtype=np.int32)
+        capi.check(self.lib.hope_set_scene_pool(self.ctx, first, s.shape[0], s.ctypes.data, d.ctypes.data, b.ctypes.data,
+                                                o.ctypes.data, nv.ctypes.data), self.ctx)
+
+    def _stream(self):
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def _obs(self):
+        return {"img": None, "lidar": self.out["lidar"], "target": self.out["target"], "action_mask": self.out["mask"]}
+
+    def _info(self):
+        o = self.out
+        return {"status": o["status"], "reward_info": o["reward_info"], "was_reset": o["was_reset"],
+                "path_to_dest": {"found": o["rs_found"], "nseg": o["rs_nseg"], "types": o["rs_types"],
+                                 "lengths": o["rs_lengths"], "L": o["rs_L"]}}
+
+    # ---- device-tensor API (what a GPU-resident rollout loop calls; asynchronous) ------------------
+    def reset(self, scene_ids=None):
+        ids = None
+        if scene_ids is not None:
+            ids = np.ascontiguousarray(scene_ids, dtype=np.int32)
+        capi.check(self.lib.hope_reset(self.ctx, ids.ctypes.data if ids is not None else None, C.byref(self._out_struct),
+                                       self._stream()), self.ctx)
+        return self._obs()
+
+    def step(self, actions, stages=capi.STAGE_ALL):
+        """actions: (N,2) float64 CUDA tensor in [-1,1] (steer, speed), as the policy emits them."""
+        t = self.torch
+        if not (isinstance(actions, t.Tensor) and actions.is_cuda and actions.dtype == t.float64 and actions.is_contiguous()
+                and tuple(actions.shape) == (self.n, 2)):
+            raise capi.HopeError("step() expects a contiguous float64 CUDA tensor of shape (n_envs, 2)")
+        capi.check(self.lib.hope_step(self.ctx, actions.data_ptr(), C.byref(self._out_struct), stages, self._stream()), self.ctx)
+        return self._obs(), self.out["reward"], self.out["done"], self._info()
+
+    def step_kinematics_collision(self, actions):
+        """BASELINE cfg 2: pose integration + collision (+ arrival) only."""
+        o = self.out
+        capi.check(self.lib.hope_step_kinematics_collision(self.ctx, actions.data_ptr(), o["pose"].data_ptr(),
+                                                           o["retreated"].data_ptr(), o["substeps"].data_ptr(), self._stream()), self.ctx)
+        return o["pose"], o["retreated"], o["substeps"]
+
+    # ---- host-buffer API (what the reference's host-side training loop would call; synchronous) ----
+    HOST_DEFAULT = ("lidar", "mask", "target", "reward", "done", "status", "reward_info", "rs_found", "rs_nseg",
+                    "rs_types", "rs_lengths")
+
+    def _host_buffers(self, names):
+        t = self.torch
+        if self._host is None:
+            self._host = {"action": t.zeros((self.n, 2), dtype=t.float64).pin_memory()}
+        st = capi.Out()
+        for name, ct, shape in capi.OUT_FIELDS:
+            if name not in names:
+                continue
+            if name not in self._host:
+                tdt = {C.c_double: t.float64, C.c_uint8: t.uint8, C.c_int32: t.int32}[ct]
+                self._host[name] = t.zeros((self.n,) + shape, dtype=tdt).pin_memory()
+            setattr(st, name, self._host[name].data_ptr())
+        return st
+
+    def step_host(self, actions, stages=capi.STAGE_ALL, outputs=HOST_DEFAULT):
+        """actions: (N,2) float64 numpy array on the host.  Copies it in, steps, copies `outputs`
+        back into pinned host buffers, synchronises.  Returns dict of numpy views."""
+        st = self._host_buffers(outputs)
+        self._host["action"].numpy()[...] = actions
+        capi.check(self.lib.hope_step_host(self.ctx, self._host["action"].data_ptr(), C.byref(st), stages), self.ctx)
+        return {k: self._host[k].numpy() for k in outputs}
+
+    def reset_host(self, scene_ids=None, outputs=HOST_DEFAULT):
+        st = self._host_buffers(outputs)
+        ids = None
+        if scene_ids is not None:
+            ids = np.ascontiguousarray(scene_ids, dtype=np.int32)
+        capi.check(self.lib.hope_reset_host(self.ctx, ids.ctypes.data if ids is not None else None, C.byref(st)), self.ctx)
+        return {k: self._host[k].numpy() for k in outputs}
+
+    def host_io_bytes(self, outputs=HOST_DEFAULT):
+        """(h2d, d2h) bytes one step_host call moves."""
+        d2h = 0
+        for name, ct, shape in capi.OUT_FIELDS:
+            if name in outputs:
+                d2h += self.n * int(np.prod(shape, dtype=np.int64)) * C.sizeof(ct)
+        return self.n * 2 * 8, d2h
+
+    # ---- state / diagnostics -------------------------------------------------------------------
+    def get_state(self):
+        pose = np.zeros((self.n, 3)); t = np.zeros(self.n, dtype=np.int32); acc = np.zeros(self.n); sid = np.zeros(self.n, dtype=np.int32)
+        capi.check(self.lib.hope_get_state(self.ctx, pose.ctypes.data, t.ctypes.data, acc.ctypes.data, sid.ctypes.data), self.ctx)
+        return dict(pose=pose, t=t, accum=acc, scene_id=sid)
+
+    def set_state(self, pose=None, t=None, accum=None):
+        p = np.ascontiguousarray(pose, dtype=np.float64) if pose is not None else None
+        tt = np.ascontiguousarray(t, dtype=np.int32) if t is not None else None
+        a = np.ascontiguousarray(accum, dtype=np.float64) if accum is not None else None
+        capi.check(self.lib.hope_set_state(self.ctx, p.ctypes.data if p is not None else None, tt.ctypes.data if tt is not None else None,
+                                           a.ctypes.data if a is not None else None), self.ctx)
+
+    def counters(self):
+        buf = (C.c_uint64 * 8)()
+        capi.check(self.lib.hope_get_counters(self.ctx, C.byref(buf)), self.ctx)
+        names = ("env_steps", "auto_resets", "exact_orient_fallbacks", "rs_capacity_overflows", "rs_zero_length_words", "kernel_launches")
+        return {k: int(buf[i]) for i, k in enumerate(names)}
+
+    def close(self):
+        if self.ctx:
+            self.lib.hope_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,92 @@
+"""ctypes binding of include/hope_b200.h (the C ABI of libhope_b200.so)."""
+import ctypes as C
+import os
+
+from . import build as _build
+
+MAX_OBS, MAX_VERTS, N_LIDAR, N_ACTION, N_MASK_ITER, N_UPSAMPLE, RS_MAX_SEG = 16, 4, 120, 42, 10, 1200, 5
+STAGE_ADVANCE, STAGE_OBSERVE, STAGE_RS, STAGE_ALL = 1, 2, 4, 7
+CONTINUE, ARRIVED, COLLIDED, OUTBOUND, OUTTIME = 1, 2, 3, 4, 5
+RS_S, RS_L, RS_R, RS_NONE = 0, 1, 2, 255
+
+
+class HopeError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("wheel_base", C.c_double), ("box_x", C.c_double * 4), ("box_y", C.c_double * 4),
+        ("valid_speed", C.c_double * 2), ("valid_steer", C.c_double * 2), ("num_step", C.c_int),
+        ("step_length", C.c_double), ("mini_iter", C.c_int), ("lidar_range", C.c_double),
+        ("tolerant_time", C.c_int), ("rs_max_dist", C.c_double), ("rs_step", C.c_double),
+        ("reward_weight", C.c_double * 5), ("reward_ratio", C.c_double), ("env_collide", C.c_int),
+        ("auto_reset", C.c_int)]
+
+
+# name -> (ctype, trailing shape); order must match struct hope_out
+OUT_FIELDS = [
+    ("pose", C.c_double, (3,)), ("lidar", C.c_double, (N_LIDAR,)), ("mask", C.c_double, (N_ACTION,)),
+    ("mask_steps", C.c_uint8, (N_ACTION,)), ("target", C.c_double, (5,)), ("reward", C.c_double, ()),
+    ("reward_info", C.c_double, (5,)), ("status", C.c_int32, ()), ("done", C.c_uint8, ()),
+    ("substeps", C.c_uint8, ()), ("retreated", C.c_uint8, ()), ("was_reset", C.c_uint8, ()),
+    ("rs_found", C.c_uint8, ()), ("rs_nseg", C.c_uint8, ()), ("rs_types", C.c_uint8, (RS_MAX_SEG,)),
+    ("rs_lengths", C.c_double, (RS_MAX_SEG,)), ("rs_L", C.c_double, ()), ("rs_ncand", C.c_uint8, ()),
+    ("rs_ntried", C.c_uint8, ())]
+
+
+class Out(C.Structure):
+    _fields_ = [(name, C.c_void_p) for name, _, _ in OUT_FIELDS]
+
+
+_LIB = None
+
+
+def load_library():
+    """Load (building if necessary) libhope_b200.so.  There is no fallback path: a missing
+    toolchain or library is an error."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.LIB
+    if _build.needs_build():
+        path = _build.build()
+    if not os.path.exists(path):
+        raise HopeError(f"{path} is missing; run `python -m hope_b200.build`")
+    lib = C.CDLL(path)
+    vp, i32, u64, dp, ip = C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p
+    sig = {
+        "hope_version": (C.c_int, []),
+        "hope_default_params": (C.c_int, [C.POINTER(Params)]),
+        "hope_create": (C.c_int, [C.POINTER(vp), i32, i32, i32, C.POINTER(Params)]),
+        "hope_destroy": (C.c_int, [vp]),
+        "hope_strerror": (C.c_char_p, [i32]),
+        "hope_last_cuda_error": (C.c_char_p, [vp]),
+        "hope_upload_tables": (C.c_int, [vp] + [dp] * 7),
+        "hope_set_scene_pool": (C.c_int, [vp, i32, i32, dp, dp, dp, dp, ip]),
+        "hope_generate_scenes": (C.c_int, [i32, i32, u64, i32, dp, dp, dp, dp, ip, ip]),
+        "hope_reset": (C.c_int, [vp, ip, C.POINTER(Out), vp]),
+        "hope_step": (C.c_int, [vp, dp, C.POINTER(Out), C.c_uint, vp]),
+        "hope_step_kinematics_collision": (C.c_int, [vp, dp, dp, vp, vp, vp]),
+        "hope_step_host": (C.c_int, [vp, dp, C.POINTER(Out), C.c_uint]),
+        "hope_reset_host": (C.c_int, [vp, ip, C.POINTER(Out)]),
+        "hope_get_state": (C.c_int, [vp, dp, ip, dp, ip]),
+        "hope_set_state": (C.c_int, [vp, dp, ip, dp]),
+        "hope_get_counters": (C.c_int, [vp, C.POINTER(u64 * 8)]),
+        "hope_n_envs": (C.c_int, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)  # AttributeError here means the library does not match the header
+        fn.restype, fn.argtypes = res, args
+    _LIB = lib
+    return lib
+
+
+def check(rc, ctx=None):
+    if rc == 0:
+        return
+    lib = load_library()
+    msg = lib.hope_strerror(rc).decode()
+    if ctx is not None and rc == -2:
+        msg += ": " + lib.hope_last_cuda_error(ctx).decode()
+    raise HopeError(f"hope_b200 error {rc}: {msg}")

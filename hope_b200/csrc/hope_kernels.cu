@@ -1,0 +1,1283 @@
+// hope_kernels.cu — the ParkingEnv step as sm_100a kernels over N independent scenes.
+//
+// Kernel            work item          reference code it replaces (src/...)
+// k_advance         thread / env       env/env_wrapper.py:37-50, env/vehicle.py:69-96,
+//                                      env/car_parking_base.py:153-233, 259-289
+// k_observe         warp / env         env/lidar_simulator.py:31-135, model/action_mask.py:166-196,
+//                                      env/car_parking_base.py:372-381
+// k_rs_enumerate    thread / env       env/reeds_shepp.py:57-449, 540-557; car_parking_base.py:431-444
+// k_rs_check        warp / env         env/reeds_shepp.py:452-537, 46-49; car_parking_base.py:452-534
+//
+// All arithmetic is float64 with FMA contraction off (see hope_device.cuh).  Data layout in HBM is
+// documented in DESIGN.md §3.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/hope_b200.h"
+#include "hope_device.cuh"
+
+namespace hope {
+
+constexpr int MAXO = HOPE_MAX_OBS;
+constexpr int MAXV = HOPE_MAX_VERTS;
+constexpr int MAXE = MAXO * MAXV;  // 64 edges
+constexpr int NRAY = HOPE_N_LIDAR;
+constexpr int NACT = HOPE_N_ACTION;
+constexpr int NITER = HOPE_N_MASK_ITER;
+constexpr int NUP = HOPE_N_UPSAMPLE;
+constexpr int META = 24;       // doubles of per-scene metadata
+constexpr int MAXW = 16;       // admitted Reeds-Shepp words kept per env
+constexpr int PD_CAP = 512;    // samples staged per block of a word in k_rs_check
+
+// per-scene metadata layout (doubles)
+enum { M_START = 0, M_DEST = 3, M_BOUNDS = 6, M_DBX = 10, M_DBY = 14, M_DAREA = 18, M_DNORM = 19, M_DAABB = 20 };
+
+struct Pool {
+    const double *obs;    // [P][16][4][2]
+    const uint8_t *nv;    // [P][16]
+    const double *aabb;   // [P][16][4] xmin xmax ymin ymax
+    const double *meta;   // [P][24]
+    const int *nobs;      // [P]
+    int size;
+};
+struct Tables {
+    const double *ray_a, *ray_b, *lidar_base, *mask_base;
+    const double *dist_star;  // [1200][42][10]
+    const double *pend;       // [1200][42]   max_k dist_star
+    const double *pmax;       // [1200]       max_{j,k} dist_star
+    const double *w_lo, *w_hi;
+    double maxc;
+};
+struct EnvState {
+    double *pose;     // [N][3]
+    int *t;           // [N]
+    double *accum;    // [N]
+    int *scene;       // [N]
+    uint8_t *pending; // [N] finished last step, takes its next scene on this one
+    uint8_t *gate;    // [N] RS gate of this step
+    unsigned long long *counters;  // [8]
+};
+struct RsWord {  // one admitted word, lengths in curvature-normalised units
+    double len[HOPE_RS_MAX_SEG];
+    double L;        // sum |len|, normalised
+    uint8_t types[HOPE_RS_MAX_SEG];
+    uint8_t n;
+    uint8_t pad[2];
+};
+struct RsScratch {
+    RsWord *words;     // [N][MAXW] in try order
+    uint8_t *ntry;     // [N]
+    uint8_t *ncand;    // [N]
+};
+
+__device__ __forceinline__ double4 ld_aabb(const double4 *p) {  // read-only path, two 128-bit loads
+    const double2 *q = reinterpret_cast<const double2 *>(p);
+    double2 lo = __ldg(q), hi = __ldg(q + 1);
+    return make_double4(lo.x, lo.y, hi.x, hi.y);
+}
+
+// =============================================================================================
+// k_advance: one thread per env.
+// =============================================================================================
+__device__ __forceinline__ bool box_collides(const double *bx, const double *by, const Pool &pool, int sid,
+                                             unsigned long long *fc) {
+    double vxmin = fmin(fmin(bx[0], bx[1]), fmin(bx[2], bx[3])), vxmax = fmax(fmax(bx[0], bx[1]), fmax(bx[2], bx[3]));
+    double vymin = fmin(fmin(by[0], by[1]), fmin(by[2], by[3])), vymax = fmax(fmax(by[0], by[1]), fmax(by[2], by[3]));
+    int no = pool.nobs[sid];
+    const double4 *aabb = reinterpret_cast<const double4 *>(pool.aabb) + (size_t)sid * MAXO;
+    for (int k = 0; k < no; ++k) {
+        double4 bb = ld_aabb(aabb + k);  // xmin xmax ymin ymax
+        if (vxmax < bb.x || bb.y < vxmin || vymax < bb.z || bb.w < vymin) continue;  // exact reject
+        int nv = pool.nv[(size_t)sid * MAXO + k];
+        const double2 *v = reinterpret_cast<const double2 *>(pool.obs) + ((size_t)sid * MAXO + k) * MAXV;
+        double2 p = __ldg(v);
+        for (int j = 0; j < nv; ++j) {
+            double2 q = __ldg(v + ((j + 1 == nv) ? 0 : j + 1));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                int i2 = (i + 1) & 3;
+                if (segments_touch(bx[i], by[i], bx[i2], by[i2], p.x, p.y, q.x, q.y, fc)) return true;
+            }
+            p = q;
+        }
+    }
+    return false;
+}
+
+__device__ __forceinline__ double angle_gap(double a1, double a2) {  // car_parking_base.py:203-206
+    double d = acos(cos(a1 - a2));
+    return d < HOPE_PI / 2 ? d : HOPE_PI - d;
+}
+
+__global__ void __launch_bounds__(128) k_advance(int n, Pool pool, EnvState st, const double *__restrict__ action,
+                                                 hope_params par, hope_out out, int reset_all) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long *fc = st.counters + 2;
+    int sid = st.scene[i];
+    bool pending = st.pending[i] != 0;
+    bool is_reset = reset_all || pending || action == nullptr;
+    if (pending && !reset_all) {  // auto-reset: next scene of the pool for this slot
+        sid = (sid + n) % pool.size;
+        st.scene[i] = sid;
+    }
+    const double *meta = pool.meta + (size_t)sid * META;
+    double x, y, h, accum;
+    int t;
+    if (reset_all || pending) {
+        x = meta[M_START]; y = meta[M_START + 1]; h = meta[M_START + 2];
+        accum = 0.0; t = 0;
+    } else {
+        x = st.pose[3 * i]; y = st.pose[3 * i + 1]; h = st.pose[3 * i + 2];
+        accum = st.accum[i]; t = st.t[i];
+    }
+    const double px0 = x, py0 = y, ph0 = h;
+    double dbx[4], dby[4], bx[4], by[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { dbx[k] = meta[M_DBX + k]; dby[k] = meta[M_DBY + k]; }
+    const double dest_area = meta[M_DAREA];
+    const double daxmin = meta[M_DAABB], daxmax = meta[M_DAABB + 1], daymin = meta[M_DAABB + 2], daymax = meta[M_DAABB + 3];
+
+    bool arrive = false;
+    int nsub = 0, nret = 0;
+    double c = cos(h), s = sin(h);
+    if (!is_reset) {
+        // env_wrapper.py:37-50: clip to [-1,1], a*(hi-lo)/2 + (hi+lo)/2 with float32-exact bounds
+        double a0 = fmin(fmax(action[2 * i], -1.0), 1.0), a1 = fmin(fmax(action[2 * i + 1], -1.0), 1.0);
+        double steer = a0 * ((par.valid_steer[1] - par.valid_steer[0]) / 2) + (par.valid_steer[1] + par.valid_steer[0]) / 2;
+        double speed = a1 * ((par.valid_speed[1] - par.valid_speed[0]) / 2) + (par.valid_speed[1] + par.valid_speed[0]) / 2;
+        // vehicle.py:83-84
+        double v = fmin(fmax(speed, par.valid_speed[0]), par.valid_speed[1]);
+        double phi = fmin(fmax(steer, par.valid_steer[0]), par.valid_steer[1]);
+        // vehicle.py:88-93, one mini-iteration: x += v cos(h) dt ; h += v tan(phi)/L dt   (dt = step_length/mini_iter)
+        const double dh = v * tan(phi) / par.wheel_base * par.step_length / par.mini_iter;
+        const double ds = v * par.step_length / par.mini_iter;
+        const int mi = par.mini_iter;
+        // closed form of the mini_iter explicit-Euler position sum: with h_k = h + k dh,
+        //   sum_k cos(h_k) = sin(mi dh/2)/sin(dh/2) * cos(h + (mi-1) dh/2)
+        const double ratio = (dh == 0.0) ? (double)mi : sin(0.5 * mi * dh) / sin(0.5 * dh);
+        for (int sub = 0; sub < par.num_step; ++sub) {  // car_parking_base.py:259-271
+            double kx = x, ky = y, kh = h, kc = c, ks = s;
+            double sm, cm;
+            sincos(h + 0.5 * (mi - 1) * dh, &sm, &cm);
+            x = x + ds * (ratio * cm);
+            y = y + ds * (ratio * sm);
+            for (int q = 0; q < mi; ++q) h += dh;  // heading accumulates by repeated addition in the reference
+            sincos(h, &s, &c);
+            ++nsub;
+            vehicle_box(x, y, c, s, par.box_x, par.box_y, bx, by);
+            double vxmin = fmin(fmin(bx[0], bx[1]), fmin(bx[2], bx[3])), vxmax = fmax(fmax(bx[0], bx[1]), fmax(bx[2], bx[3]));
+            double vymin = fmin(fmin(by[0], by[1]), fmin(by[2], by[3])), vymax = fmax(fmax(by[0], by[1]), fmax(by[2], by[3]));
+            if (!(vxmax < daxmin || daxmax < vxmin || vymax < daymin || daymax < vymin)) {
+                if (quad_clip_area(bx, by, dbx, dby) / dest_area > 0.95) { arrive = true; break; }  // :164-170
+            }
+            if (box_collides(bx, by, pool, sid, fc)) {  // :264-271 retreat one substep
+                x = kx; y = ky; h = kh; c = kc; s = ks;
+                ++nret;
+                break;
+            }
+        }
+    }
+    t += 1;
+    vehicle_box(x, y, c, s, par.box_x, par.box_y, bx, by);
+    double inter = 0.0;
+    {
+        double vxmin = fmin(fmin(bx[0], bx[1]), fmin(bx[2], bx[3])), vxmax = fmax(fmax(bx[0], bx[1]), fmax(bx[2], bx[3]));
+        double vymin = fmin(fmin(by[0], by[1]), fmin(by[2], by[3])), vymax = fmax(fmax(by[0], by[1]), fmax(by[2], by[3]));
+        if (!(vxmax < daxmin || daxmax < vxmin || vymax < daymin || daymax < vymin)) inter = quad_clip_area(bx, by, dbx, dby);
+    }
+    const double xmin = meta[M_BOUNDS], xmax = meta[M_BOUNDS + 1], ymin = meta[M_BOUNDS + 2], ymax = meta[M_BOUNDS + 3];
+    int status;  // car_parking_base.py:279-282, 175-184
+    if (arrive) status = HOPE_ARRIVED;
+    else if (box_collides(bx, by, pool, sid, fc)) status = HOPE_COLLIDED;
+    else if (x > xmax || x < xmin || y > ymax || y < ymin) status = HOPE_OUTBOUND;
+    else if (inter / dest_area > 0.95) status = HOPE_ARRIVED;
+    else if (t > par.tolerant_time) status = HOPE_OUTTIME;
+    else status = HOPE_CONTINUE;
+
+    const double dx = meta[M_DEST], dy = meta[M_DEST + 1], dhd = meta[M_DEST + 2];
+    double ri[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    const double dist_now = hypot(x - dx, y - dy);
+    if (status == HOPE_CONTINUE) {  // :186-227
+        ri[0] = -tanh((double)t / (10 * par.tolerant_time));
+        double dist_prev = hypot(px0 - dx, py0 - dy), norm = meta[M_DNORM];
+        ri[2] = dist_prev / norm - dist_now / norm;
+        ri[3] = angle_gap(ph0, dhd) / HOPE_PI - angle_gap(h, dhd) / HOPE_PI;
+        double u = inter / (2 * dest_area - inter);
+        if (u < accum) u = 0.0;
+        else { double p = accum; accum = u; u -= p; }
+        ri[4] = u;
+    }
+    double reward;  // env_wrapper.py:10-35
+    if (status == HOPE_CONTINUE) {
+        reward = 0.0;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) reward += par.reward_weight[k] * ri[k];
+    } else if (status == HOPE_OUTTIME) reward = -1.0;
+    else if (status == HOPE_ARRIVED) reward = 50.0;
+    else reward = -50.0;
+    reward *= par.reward_ratio;
+
+    st.pose[3 * i] = x; st.pose[3 * i + 1] = y; st.pose[3 * i + 2] = h;
+    st.accum[i] = accum; st.t[i] = t;
+    bool done = status != HOPE_CONTINUE;
+    st.pending[i] = (done && par.auto_reset) ? 1 : 0;
+    st.gate[i] = (t > 1 && status == HOPE_CONTINUE && dist_now < par.rs_max_dist) ? 1 : 0;  // :293-294
+
+    if (out.pose) { out.pose[3 * i] = x; out.pose[3 * i + 1] = y; out.pose[3 * i + 2] = h; }
+    if (out.status) out.status[i] = status;
+    if (out.done) out.done[i] = done;
+    if (out.reward) out.reward[i] = reward;
+    if (out.reward_info) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) out.reward_info[5 * i + k] = ri[k];
+    }
+    if (out.substeps) out.substeps[i] = (uint8_t)nsub;
+    if (out.retreated) out.retreated[i] = (uint8_t)nret;
+    if (out.was_reset) out.was_reset[i] = is_reset;
+    // whole-warp tallies -> one atomic per warp
+    const unsigned am = __activemask();
+    unsigned m_act = __ballot_sync(am, !is_reset);
+    unsigned m_rst = __ballot_sync(am, pending && !reset_all);
+    if ((threadIdx.x & 31) == (__ffs(am) - 1)) {
+        if (m_act) atomicAdd(st.counters + 0, (unsigned long long)__popc(m_act));
+        if (m_rst) atomicAdd(st.counters + 1, (unsigned long long)__popc(m_rst));
+    }
+}
+
+// =============================================================================================
+// k_observe: one warp per env.  LiDAR raycast -> action-mask sweep -> target representation.
+// =============================================================================================
+struct ObserveSmem {
+    double ex1[MAXE], ey1[MAXE], ex2[MAXE], ey2[MAXE];  // rotated edge end points (ego frame)
+    double ed[MAXE], ee[MAXE], ef[MAXE];                // line coefficients d x + e y + f = 0
+    double L[NRAY];                                     // clip(lidar)+mask_base
+    int steps[NACT + 2];
+    uint8_t quad[MAXE];                                 // which ray quadrants can accept this edge
+};
+
+__global__ void __launch_bounds__(256) k_observe(int n, Pool pool, EnvState st, Tables tb, hope_params par, hope_out out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int env = blockIdx.x * (blockDim.x >> 5) + warp_in_block;
+    if (env >= n) return;
+    ObserveSmem &sm = reinterpret_cast<ObserveSmem *>(smem_raw)[warp_in_block];
+    const int sid = st.scene[env];
+    const double x = st.pose[3 * env], y = st.pose[3 * env + 1], h = st.pose[3 * env + 2];
+
+    // ---- stage obstacle vertices, rotate into the ego frame (lidar_simulator.py:55-72) -------------
+    double a, b;
+    sincos(h, &b, &a);  // a = cos, b = sin
+    const double xoff = -x * a - y * b, yoff = x * b - y * a, mb = -b;
+    const double2 *verts = reinterpret_cast<const double2 *>(pool.obs) + (size_t)sid * MAXE;
+    const uint8_t *nvp = pool.nv + (size_t)sid * MAXO;
+    int n_edges = 0;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        int slot = half * 32 + lane, k = slot >> 2, j = slot & 3;
+        int nv = nvp[k];
+        bool valid = j < nv;
+        double2 p = __ldg(verts + slot);                                       // coalesced 128-bit loads
+        double2 q = __ldg(verts + (k << 2) + ((j + 1 >= nv) ? 0 : j + 1));
+        unsigned m = __ballot_sync(HOPE_FULL_MASK, valid);
+        if (valid) {
+            int e = n_edges + __popc(m & ((1u << lane) - 1));
+            double x1 = a * p.x + b * p.y + xoff, y1 = mb * p.x + a * p.y + yoff;
+            double x2 = a * q.x + b * q.y + xoff, y2 = mb * q.x + a * q.y + yoff;
+            sm.ex1[e] = x1; sm.ey1[e] = y1; sm.ex2[e] = x2; sm.ey2[e] = y2;
+            sm.ed[e] = y2 - y1; sm.ee[e] = x1 - x2; sm.ef[e] = y1 * x2 - x1 * y2;  // :104-106
+            double exmin = fmin(x1, x2), exmax = fmax(x1, x2), eymin = fmin(y1, y2), eymax = fmax(y1, y2);
+            // exact culls: a hit must lie inside the edge's bbox (:126-129), on the ray's side of the
+            // axes up to 1e-8 (:120-124), and nearer than lidar_range to survive the clip (:134)
+            bool xp = exmax >= -1e-8, xn = exmin <= 1e-8, yp = eymax >= -1e-8, yn = eymin <= 1e-8;
+            bool reach = !(exmin > par.lidar_range || exmax < -par.lidar_range || eymin > par.lidar_range || eymax < -par.lidar_range);
+            uint8_t qm = 0;
+            if (reach) qm = (uint8_t)((xp && yp ? 1 : 0) | (xn && yp ? 2 : 0) | (xn && yn ? 4 : 0) | (xp && yn ? 8 : 0));
+            sm.quad[e] = qm;
+        }
+        n_edges += __popc(m);
+    }
+    __syncwarp();
+
+    // ---- raycast: quadrant q handles rays 30q .. 30q+29, one per lane ---------------------------
+    const int per_quad = NRAY / 4;
+#pragma unroll 1
+    for (int q = 0; q < 4; ++q) {
+        const int ray = q * per_quad + lane;
+        const bool live = lane < per_quad;
+        const double A = live ? tb.ray_a[ray] : 0.0, B = live ? tb.ray_b[ray] : -1.0;
+        double best = par.lidar_range;
+        for (int e = 0; e < n_edges; ++e) {
+            if (!((sm.quad[e] >> q) & 1)) continue;  // warp-uniform
+            double d = sm.ed[e], ee = sm.ee[e], f = sm.ef[e];
+            double det = A * ee - B * d;              // :109
+            if (det == 0.0) continue;                 // parallel -> 100 -> clipped away (:131)
+            double rx = (B * f) / det, ry = (-(A * f)) / det;  // :112-113 with c = 0
+            bool ok;
+            if (q == 0) ok = !(rx < -1e-8) && !(ry < -1e-8);
+            else if (q == 1) ok = !(rx > 1e-8) && !(ry < -1e-8);
+            else if (q == 2) ok = !(rx > 1e-8) && !(ry > 1e-8);
+            else ok = !(rx < -1e-8) && !(ry > 1e-8);
+            double x1 = sm.ex1[e], x2 = sm.ex2[e], y1 = sm.ey1[e], y2 = sm.ey2[e];
+            ok = ok && !(rx > fmax(x1, x2)) && !(rx < fmin(x1, x2)) && !(ry > fmax(y1, y2)) && !(ry < fmin(y1, y2));
+            if (ok) best = fmin(best, sqrt(rx * rx + ry * ry));  // :133
+        }
+        if (live) {
+            double r = fmin(fmax(best, 0.0), par.lidar_range) - tb.lidar_base[ray];  // :134, :46
+            if (out.lidar) out.lidar[(size_t)env * NRAY + ray] = r;
+            sm.L[ray] = fmin(fmax(r, 0.0), 10.0) + tb.mask_base[ray];  // action_mask.py:170
+        }
+    }
+    __syncwarp();
+
+    // ---- action-mask sweep (action_mask.py:166-184) --------------------------------------------
+    // s_j = min over the 1200 upsampled rays of (first k with dist_star[rho][j][k] > d_rho).
+    // A ray can lower any s_j only if d_rho < max_{j,k} dist_star[rho] (pmax); an action only if
+    // d_rho < max_k dist_star[rho][j] (pend).  Both screens are exact comparisons of stored doubles,
+    // so the surviving compares give the same integers as the reference's full 1200x42x10 sweep.
+    int s0 = NITER, s1 = NITER;  // lane owns actions lane and lane+32
+    for (int base = 0; base < NUP; base += 32) {
+        int rho = base + lane;
+        bool in = rho < NUP;
+        int qd = in ? rho / 10 : 0, r = in ? rho - qd * 10 : 0;
+        int qn = (qd + 1 == NRAY) ? 0 : qd + 1;
+        double d = sm.L[qd] * tb.w_lo[r] + sm.L[qn] * tb.w_hi[r];  // action_mask.py:158-162
+        unsigned act = __ballot_sync(HOPE_FULL_MASK, in && d < __ldg(tb.pmax + (in ? rho : 0)));
+        while (act) {
+            int bsel = __ffs(act) - 1;
+            act &= act - 1;
+            double db = __shfl_sync(HOPE_FULL_MASK, d, bsel);
+            int rb = base + bsel;
+            const double *pe = tb.pend + (size_t)rb * NACT;
+            const double *ds = tb.dist_star + (size_t)rb * NACT * NITER;
+            if (s0 > 0 && db < __ldg(pe + lane)) {
+                const double *row = ds + lane * NITER;
+                int k = 0;
+                while (k < NITER && __ldg(row + k) <= db) ++k;
+                s0 = min(s0, k);
+            }
+            if (lane < NACT - 32 && s1 > 0 && db < __ldg(pe + 32 + lane)) {
+                const double *row = ds + (32 + lane) * NITER;
+                int k = 0;
+                while (k < NITER && __ldg(row + k) <= db) ++k;
+                s1 = min(s1, k);
+            }
+        }
+    }
+    sm.steps[lane] = s0;
+    if (lane < NACT - 32) sm.steps[32 + lane] = s1;
+    __syncwarp();
+    // post_process (action_mask.py:186-196): per half subtract 1 at both ends, 5-tap min, clip, /10
+    int mine[2] = {0, 0};
+    int total = 0;
+#pragma unroll
+    for (int rep = 0; rep < 2; ++rep) {
+        int j = rep * 32 + lane;
+        if (j < NACT) {
+            int half = j >= 21 ? 21 : 0, p = j - half, m = 1 << 30;
+#pragma unroll
+            for (int dt = -2; dt <= 2; ++dt) {
+                int u = p + dt;
+                if (u < 0 || u > 20) continue;  // 'reflect' border == truncated window for a min filter
+                int vv = sm.steps[half + u] - ((u == 0 || u == 20) ? 1 : 0);
+                m = min(m, vv);
+            }
+            m = max(0, min(m, NITER));
+            mine[rep] = m;
+            total += m;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(HOPE_FULL_MASK, total, o);
+#pragma unroll
+    for (int rep = 0; rep < 2; ++rep) {
+        int j = rep * 32 + lane;
+        if (j < NACT) {
+            if (out.mask) out.mask[(size_t)env * NACT + j] = total == 0 ? 0.01 : (double)mine[rep] / 10;  // :182-183
+            if (out.mask_steps) out.mask_steps[(size_t)env * NACT + j] = (uint8_t)mine[rep];
+        }
+    }
+    // ---- target representation (car_parking_base.py:372-381; element 4 repeats cos, sic) -----------
+    if (lane == 0 && out.target) {
+        const double *meta = pool.meta + (size_t)sid * META;
+        double ddx = meta[M_DEST] - x, ddy = meta[M_DEST + 1] - y;
+        double rel = atan2(ddy, ddx) - h, relh = meta[M_DEST + 2] - h;
+        double *tg = out.target + (size_t)env * 5;
+        tg[0] = sqrt(ddx * ddx + ddy * ddy);
+        tg[1] = cos(rel); tg[2] = sin(rel);
+        tg[3] = cos(relh); tg[4] = cos(relh);
+    }
+}
+
+// =============================================================================================
+// k_rs_enumerate: one thread per env.  46 candidate words -> admitted list -> heap pop order.
+// =============================================================================================
+struct Tuv { double t, u, v; };
+
+__device__ bool w_SLS(double x, double y, double phi, Tuv &o) {  // reeds_shepp.py:133-149
+    phi = rs_M(phi);
+    if (y != 0.0 && 0.0 < phi && phi < HOPE_PI * 0.99 && (y > 0.0 || y < 0.0)) {
+        double tp = tan(phi), th = tan(phi / 2.0);
+        double xd = -y / tp + x;
+        double dxx = x - xd;
+        double r = sqrt(dxx * dxx + y * y);
+        o.t = xd - th; o.u = phi; o.v = (y > 0.0 ? r : -r) - th;
+        return true;
+    }
+    return false;
+}
+__device__ bool w_LSL(double x, double y, double phi, Tuv &o) {  // :79-87
+    double s, c;
+    sincos(phi, &s, &c);
+    double ax = x - s, ay = y - 1.0 + c;
+    double t = atan2(ay, ax);
+    if (t >= 0.0) {
+        double v = rs_M(phi - t);
+        if (v >= 0.0) { o.t = t; o.u = hypot(ax, ay); o.v = v; return true; }
+    }
+    return false;
+}
+__device__ bool w_LSR(double x, double y, double phi, Tuv &o) {  // :90-103
+    double s, c;
+    sincos(phi, &s, &c);
+    double ax = x + s, ay = y - 1.0 - c;
+    double u1 = hypot(ax, ay), t1 = atan2(ay, ax);
+    u1 = u1 * u1;
+    if (u1 >= 4.0) {
+        double u = sqrt(u1 - 4.0), th = atan2(2.0, u), t = rs_M(t1 + th), v = rs_M(t - phi);
+        if (t >= 0.0 && v >= 0.0) { o.t = t; o.u = u; o.v = v; return true; }
+    }
+    return false;
+}
+__device__ bool w_LRL(double x, double y, double phi, Tuv &o) {  // :106-117
+    double s, c;
+    sincos(phi, &s, &c);
+    double ax = x - s, ay = y - 1.0 + c;
+    double u1 = hypot(ax, ay), t1 = atan2(ay, ax);
+    if (u1 <= 4.0) {
+        double u = -2.0 * asin(0.25 * u1), t = rs_M(t1 + 0.5 * u + HOPE_PI), v = rs_M(phi - t + u);
+        if (t >= 0.0 && u <= 0.0) { o.t = t; o.u = u; o.v = v; return true; }
+    }
+    return false;
+}
+__device__ void tau_omega(double u, double v, double xi, double eta, double phi, double &tau, double &omega) {  // :228-243
+    double delta = rs_M(u - v);
+    double su, cu, sd, cd;
+    sincos(u, &su, &cu);
+    sincos(delta, &sd, &cd);
+    double A = su - sd, B = cu - cd - 1.0;
+    double t1 = atan2(eta * A - xi * B, xi * A + eta * B);
+    double t2 = 2.0 * (cd - cos(v) - cu) + 3.0;
+    tau = t2 < 0 ? rs_M(t1 + HOPE_PI) : rs_M(t1);
+    omega = rs_M(tau - u + v - phi);
+}
+__device__ bool w_LRLRn(double x, double y, double phi, Tuv &o) {  // :246-257
+    double s, c;
+    sincos(phi, &s, &c);
+    double xi = x + s, eta = y - 1.0 - c, rho = 0.25 * (2.0 + sqrt(xi * xi + eta * eta));
+    if (rho <= 1.0) {
+        double u = acos(rho), t, v;
+        tau_omega(u, -u, xi, eta, phi, t, v);
+        if (t >= 0.0 && v <= 0.0) { o.t = t; o.u = u; o.v = v; return true; }
+    }
+    return false;
+}
+__device__ bool w_LRLRp(double x, double y, double phi, Tuv &o) {  // :260-272
+    double s, c;
+    sincos(phi, &s, &c);
+    double xi = x + s, eta = y - 1.0 - c, rho = (20.0 - xi * xi - eta * eta) / 16.0;
+    if (0.0 <= rho && rho <= 1.0) {
+        double u = -acos(rho);
+        if (u >= -0.5 * HOPE_PI) {
+            double t, v;
+            tau_omega(u, u, xi, eta, phi, t, v);
+            if (t >= 0.0 && v >= 0.0) { o.t = t; o.u = u; o.v = v; return true; }
+        }
+    }
+    return false;
+}
+__device__ bool w_LRSR(double x, double y, double phi, Tuv &o) {  // :311-323
+    double s, c;
+    sincos(phi, &s, &c);
+    double xi = x + s, eta = y - 1.0 - c;
+    double rho = hypot(-eta, xi), theta = atan2(xi, -eta);
+    if (rho >= 2.0) {
+        double t = theta, u = 2.0 - rho, v = rs_M(t + 0.5 * HOPE_PI - phi);
+        if (t >= 0.0 && u <= 0.0 && v <= 0.0) { o.t = t; o.u = u; o.v = v; return true; }
+    }
+    return false;
+}
+__device__ bool w_LRSL(double x, double y, double phi, Tuv &o) {  // :326-339
+    double s, c;
+    sincos(phi, &s, &c);
+    double xi = x - s, eta = y - 1.0 + c;
+    double rho = hypot(xi, eta), theta = atan2(eta, xi);
+    if (rho >= 2.0) {
+        double r = sqrt(rho * rho - 4.0), u = 2.0 - r, t = rs_M(theta + atan2(r, -2.0)), v = rs_M(phi - 0.5 * HOPE_PI - t);
+        if (t >= 0.0 && u <= 0.0 && v <= 0.0) { o.t = t; o.u = u; o.v = v; return true; }
+    }
+    return false;
+}
+__device__ bool w_LRSLR(double x, double y, double phi, Tuv &o) {  // :414-429
+    double s, c;
+    sincos(phi, &s, &c);
+    double xi = x + s, eta = y - 1.0 - c;
+    double rho = hypot(xi, eta);
+    if (rho >= 2.0) {
+        double u = 4.0 - sqrt(rho * rho - 4.0);
+        if (u <= 0.0) {
+            double t = rs_M(atan2((4.0 - u) * xi - 2.0 * eta, -2.0 * xi + (u - 4.0) * eta)), v = rs_M(t - phi);
+            if (t >= 0.0 && v >= 0.0) { o.t = t; o.u = u; o.v = v; return true; }
+        }
+    }
+    return false;
+}
+
+// Families in generate_path order (:549-555).  `lay` says where (t,u,v) land in the length vector.
+enum { LAY_TUV, LAY_VUT, LAY_T_U_mU_V, LAY_T_U_U_V, LAY_T_H_U_V, LAY_V_U_H_T, LAY_T_H_U_H_V };
+enum { F_LSL, F_LSR, F_LRL, F_LRLRn, F_LRLRp, F_LRSL, F_LRSR, F_LRSLR };
+struct Family { uint8_t fn, back, lay, n, ty[5]; };
+__constant__ Family c_families[11] = {
+    {F_LSL, 0, LAY_TUV, 3, {1, 0, 1, 255, 255}},        {F_LSR, 0, LAY_TUV, 3, {1, 0, 2, 255, 255}},
+    {F_LRL, 0, LAY_TUV, 3, {1, 2, 1, 255, 255}},        {F_LRL, 1, LAY_VUT, 3, {1, 2, 1, 255, 255}},
+    {F_LRLRn, 0, LAY_T_U_mU_V, 4, {1, 2, 1, 2, 255}},   {F_LRLRp, 0, LAY_T_U_U_V, 4, {1, 2, 1, 2, 255}},
+    {F_LRSL, 0, LAY_T_H_U_V, 4, {1, 2, 0, 1, 255}},     {F_LRSR, 0, LAY_T_H_U_V, 4, {1, 2, 0, 2, 255}},
+    {F_LRSL, 1, LAY_V_U_H_T, 4, {1, 0, 2, 1, 255}},     {F_LRSR, 1, LAY_V_U_H_T, 4, {2, 0, 2, 1, 255}},
+    {F_LRSLR, 0, LAY_T_H_U_H_V, 5, {1, 2, 0, 1, 2}},
+};
+
+struct WordList {
+    double len[MAXW][HOPE_RS_MAX_SEG];
+    double L[MAXW];
+    uint32_t ty[MAXW];  // 4 bits per segment, 0xF = unused
+    uint8_t n[MAXW];
+    int count;
+};
+// set_path (reeds_shepp.py:57-76).  Returns false if the capacity MAXW was hit.
+__device__ bool admit(WordList &w, int n, uint32_t ty, const double *len, unsigned long long *counters) {
+    for (int k = 0; k < w.count; ++k) {
+        if (w.ty[k] != ty) continue;
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) s = s + (w.len[k][i] - len[i]);
+        if (s <= 0.01) return true;  // near-duplicate of an earlier word of the same type
+    }
+    double L = 0.0;
+    for (int i = 0; i < n; ++i) L = L + fabs(len[i]);
+    if (L >= 1000.0) return true;
+    if (!(L >= 0.001)) { atomicAdd(counters + 4, 1ull); return true; }  // the reference asserts here (:73)
+    if (w.count == MAXW) { atomicAdd(counters + 3, 1ull); return false; }
+    int k = w.count++;
+    for (int i = 0; i < HOPE_RS_MAX_SEG; ++i) w.len[k][i] = i < n ? len[i] : 0.0;
+    w.L[k] = L; w.ty[k] = ty; w.n[k] = (uint8_t)n;
+    return true;
+}
+
+__global__ void __launch_bounds__(128) k_rs_enumerate(int n, Pool pool, EnvState st, Tables tb, RsScratch rs, hope_out out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // default outputs: no path (k_rs_check overwrites them for the env whose search succeeds)
+    if (out.rs_found) out.rs_found[i] = 0;
+    if (out.rs_nseg) out.rs_nseg[i] = 0;
+    if (out.rs_L) out.rs_L[i] = 0.0;
+    if (out.rs_ncand) out.rs_ncand[i] = 0;
+    if (out.rs_ntried) out.rs_ntried[i] = 0;
+    if (out.rs_types) for (int k = 0; k < 5; ++k) out.rs_types[5 * i + k] = HOPE_RS_NONE;
+    if (out.rs_lengths) for (int k = 0; k < 5; ++k) out.rs_lengths[5 * i + k] = 0.0;
+    if (!st.gate[i]) { rs.ntry[i] = 0; rs.ncand[i] = 0; return; }
+    const double *meta = pool.meta + (size_t)st.scene[i] * META;
+    const double sx = st.pose[3 * i], sy = st.pose[3 * i + 1], sh = st.pose[3 * i + 2];
+    // generate_path :540-547
+    double dx = meta[M_DEST] - sx, dy = meta[M_DEST + 1] - sy, phi = meta[M_DEST + 2] - sh;
+    double c, s;
+    sincos(sh, &s, &c);
+    const double x = (c * dx + s * dy) * tb.maxc, y = (-s * dx + c * dy) * tb.maxc;
+
+    WordList w;
+    w.count = 0;
+    Tuv o;
+    double len[5];
+    bool room = true;
+    // SCS :120-130
+    if (w_SLS(x, y, phi, o)) { len[0] = o.t; len[1] = o.u; len[2] = o.v; room &= admit(w, 3, 0xFF000u | 0x010u, len, st.counters); }
+    if (w_SLS(x, -y, -phi, o)) { len[0] = o.t; len[1] = o.u; len[2] = o.v; room &= admit(w, 3, 0xFF000u | 0x020u, len, st.counters); }
+    double sp, cp;
+    sincos(phi, &sp, &cp);
+    const double xb = x * cp + y * sp, yb = x * sp - y * cp;  // :206-207, :376-377
+    for (int f = 0; f < 11; ++f) {
+        const Family F = c_families[f];
+        const double X = F.back ? xb : x, Y = F.back ? yb : y;
+        for (int r = 0; r < 4; ++r) {
+            double ax = (r & 1) ? -X : X, ay = (r & 2) ? -Y : Y, ap = (r == 1 || r == 2) ? -phi : phi;
+            bool ok;
+            switch (F.fn) {
+            case F_LSL: ok = w_LSL(ax, ay, ap, o); break;
+            case F_LSR: ok = w_LSR(ax, ay, ap, o); break;
+            case F_LRL: ok = w_LRL(ax, ay, ap, o); break;
+            case F_LRLRn: ok = w_LRLRn(ax, ay, ap, o); break;
+            case F_LRLRp: ok = w_LRLRp(ax, ay, ap, o); break;
+            case F_LRSL: ok = w_LRSL(ax, ay, ap, o); break;
+            case F_LRSR: ok = w_LRSR(ax, ay, ap, o); break;
+            default: ok = w_LRSLR(ax, ay, ap, o); break;
+            }
+            if (!ok) continue;
+            const double H = -0.5 * HOPE_PI;
+            len[3] = len[4] = 0.0;
+            switch (F.lay) {
+            case LAY_TUV: len[0] = o.t; len[1] = o.u; len[2] = o.v; break;
+            case LAY_VUT: len[0] = o.v; len[1] = o.u; len[2] = o.t; break;
+            case LAY_T_U_mU_V: len[0] = o.t; len[1] = o.u; len[2] = -o.u; len[3] = o.v; break;
+            case LAY_T_U_U_V: len[0] = o.t; len[1] = o.u; len[2] = o.u; len[3] = o.v; break;
+            case LAY_T_H_U_V: len[0] = o.t; len[1] = H; len[2] = o.u; len[3] = o.v; break;
+            case LAY_V_U_H_T: len[0] = o.v; len[1] = o.u; len[2] = H; len[3] = o.t; break;
+            default: len[0] = o.t; len[1] = H; len[2] = o.u; len[3] = H; len[4] = o.v; break;
+            }
+            if (r & 1) for (int k = 0; k < F.n; ++k) len[k] = -len[k];
+            uint32_t ty = 0;
+            for (int k = 0; k < 5; ++k) {
+                uint32_t b = F.ty[k] == 255 ? 0xFu : F.ty[k];
+                if ((r & 2) && (b == 1 || b == 2)) b = 3 - b;  // reflected words swap L and R
+                ty |= b << (4 * k);
+            }
+            room &= admit(w, F.n, ty, len, st.counters);
+        }
+    }
+    (void)room;
+    // find_rs_path (car_parking_base.py:431-444): heapdict pop order (priority-only binary heap:
+    // sift-up stops at a strictly smaller parent, sift-down prefers left unless right is strictly
+    // smaller), cut at the first word with L > 1.6 L_min once more than two were popped.
+    int heap[MAXW], hn = 0;
+    double Ls[MAXW];
+    for (int k = 0; k < w.count; ++k) Ls[k] = w.L[k] / tb.maxc;  // reeds_shepp.py:52
+    for (int k = 0; k < w.count; ++k) {
+        int p = hn++;
+        heap[p] = k;
+        while (p > 0) {
+            int up = (p - 1) >> 1;
+            if (Ls[heap[up]] < Ls[heap[p]]) break;
+            int tmp = heap[up]; heap[up] = heap[p]; heap[p] = tmp;
+            p = up;
+        }
+    }
+    RsWord *dst = rs.words + (size_t)i * MAXW;
+    int ntry = 0, idx = 0;
+    double lmin = -1.0;
+    while (hn) {
+        ++idx;
+        int top = heap[0];
+        --hn;
+        if (hn) {
+            heap[0] = heap[hn];
+            int p = 0;
+            for (;;) {
+                int l = 2 * p + 1, r = 2 * p + 2, low = (l < hn && Ls[heap[l]] < Ls[heap[p]]) ? l : p;
+                if (r < hn && Ls[heap[r]] < Ls[heap[low]]) low = r;
+                if (low == p) break;
+                int tmp = heap[low]; heap[low] = heap[p]; heap[p] = tmp;
+                p = low;
+            }
+        }
+        if (lmin < 0) lmin = Ls[top];
+        if (Ls[top] > 1.6 * lmin && idx > 2) break;
+        RsWord ww;
+        for (int k = 0; k < 5; ++k) { ww.len[k] = w.len[top][k]; ww.types[k] = (uint8_t)((w.ty[top] >> (4 * k)) & 0xF); }
+        ww.L = w.L[top]; ww.n = w.n[top]; ww.pad[0] = ww.pad[1] = 0;
+        dst[ntry++] = ww;
+    }
+    rs.ntry[i] = (uint8_t)ntry;
+    rs.ncand[i] = (uint8_t)w.count;
+    if (out.rs_ncand) out.rs_ncand[i] = (uint8_t)w.count;
+}
+
+// =============================================================================================
+// k_rs_check: one warp per env.  Sample each word of the try list every rs_step metres and test
+// the swept vehicle boxes against map bounds and obstacle edges; the first clean word wins.
+// =============================================================================================
+struct CheckSmem {
+    double pd[PD_CAP];   // arc parameter of each staged sample (normalised units)
+    uint8_t seg[PD_CAP]; // segment index; 0xFE = path origin, 0xFF = final end point
+};
+
+__global__ void __launch_bounds__(256) k_rs_check(int n, Pool pool, EnvState st, Tables tb, RsScratch rs, hope_params par, hope_out out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int env = blockIdx.x * (blockDim.x >> 5) + warp_in_block;
+    if (env >= n) return;
+    const int ntry = rs.ntry[env];
+    if (ntry == 0) return;  // outputs already cleared by k_rs_enumerate (gate closed or no word)
+    CheckSmem &sm = reinterpret_cast<CheckSmem *>(smem_raw)[warp_in_block];
+    const int sid = st.scene[env];
+    const double q0x = st.pose[3 * env], q0y = st.pose[3 * env + 1], q0h = st.pose[3 * env + 2];
+    const double *meta = pool.meta + (size_t)sid * META;
+    const double xmin = meta[M_BOUNDS], xmax = meta[M_BOUNDS + 1], ymin = meta[M_BOUNDS + 2], ymax = meta[M_BOUNDS + 3];
+    const int nobs = pool.nobs[sid];
+    const double4 *aabb = reinterpret_cast<const double4 *>(pool.aabb) + (size_t)sid * MAXO;
+    const double2 *verts = reinterpret_cast<const double2 *>(pool.obs) + (size_t)sid * MAXE;
+    const uint8_t *nvp = pool.nv + (size_t)sid * MAXO;
+    double sg, cg;
+    sincos(-q0h, &sg, &cg);  // reeds_shepp.py:47-48
+    const double maxc = tb.maxc, step = par.rs_step * maxc;
+
+    int found = -1, tried = 0;
+    for (int wi = 0; wi < ntry && found < 0; ++wi) {
+        const RsWord w = rs.words[(size_t)env * MAXW + wi];
+        ++tried;
+        // walker state, identical in every lane (generate_local_course :452-507)
+        int seg = 0;
+        double ox = 0.0, oy = 0.0, oyaw = 0.0;       // origin of the current segment (local frame)
+        double so[HOPE_RS_MAX_SEG][3];               // per-segment origins for the sample phase
+        double d = w.len[0] > 0.0 ? step : -step;
+        double pd = d, ll = 0.0;
+        bool origin_pending = true, finished = false, bad = false, pending_bad = false;
+        so[0][0] = so[0][1] = so[0][2] = 0.0;
+        while (!finished && !bad) {
+            // ---- phase 1: stage up to PD_CAP samples (sequential float accumulation of pd) ---------
+            int cnt = 0;
+            if (origin_pending) { if (lane == 0) { sm.pd[0] = 0.0; sm.seg[0] = 0xFE; } cnt = 1; origin_pending = false; }
+            while (cnt < PD_CAP && !finished) {
+                double l = w.len[seg];
+                if (fabs(pd) <= fabs(l)) {  // :488-492
+                    if (lane == 0) { sm.pd[cnt] = pd; sm.seg[cnt] = (uint8_t)seg; }
+                    ++cnt;
+                    pd += d;
+                } else {
+                    ll = l - pd - d;  // :494
+                    if (seg + 1 == w.n) {  // the last segment's end point is the final sample (:496-498)
+                        if (lane == 0) { sm.pd[cnt] = l; sm.seg[cnt] = (uint8_t)(0x80 | seg); }
+                        ++cnt;
+                        finished = true;
+                    } else {
+                        // origin of the next segment = end point of this one (interpolate :510-537)
+                        int m = w.types[seg];
+                        if (m == HOPE_RS_S) {
+                            ox = ox + l / maxc * cos(oyaw);
+                            oy = oy + l / maxc * sin(oyaw);
+                        } else {
+                            double sl, cl, sy_, cy_;
+                            sincos(l, &sl, &cl);
+                            sincos(-oyaw, &sy_, &cy_);
+                            double ldx = sl / maxc, ldy = (1.0 - cl) / (m == HOPE_RS_L ? maxc : -maxc);
+                            double gdx = cy_ * ldx + sy_ * ldy, gdy = -sy_ * ldx + cy_ * ldy;
+                            ox = ox + gdx; oy = oy + gdy;
+                            oyaw = (m == HOPE_RS_L) ? oyaw + l : oyaw - l;
+                        }
+                        ++seg;
+                        so[seg][0] = ox; so[seg][1] = oy; so[seg][2] = oyaw;
+                        double ln = w.len[seg];
+                        d = ln > 0.0 ? step : -step;                          // :475-478
+                        pd = (w.len[seg - 1] * ln > 0) ? -d - ll : d - ll;    // :483-486
+                    }
+                }
+            }
+            __syncwarp();
+            // ---- phase 2: every lane evaluates samples lane, lane+32, ... of the staged block -------
+            for (int base = 0; base < cnt && !bad; base += 32) {
+                int k = base + lane;
+                bool have = k < cnt;
+                bool hit = false, nonzero = false;
+                if (have) {
+                    uint8_t sc = sm.seg[k];
+                    double lx, ly, lyaw;
+                    if (sc == 0xFE) { lx = 0.0; ly = 0.0; lyaw = 0.0; }
+                    else {
+                        int sgi = sc & 0x7F;
+                        double p = sm.pd[k];
+                        double bx0 = so[0][0], by0 = so[0][1], bw0 = so[0][2];
+#pragma unroll
+                        for (int q = 1; q < HOPE_RS_MAX_SEG; ++q) if (q == sgi) { bx0 = so[q][0]; by0 = so[q][1]; bw0 = so[q][2]; }
+                        int m = w.types[sgi];
+                        if (m == HOPE_RS_S) {
+                            lx = bx0 + p / maxc * cos(bw0);
+                            ly = by0 + p / maxc * sin(bw0);
+                            lyaw = bw0;
+                        } else {
+                            double sl, cl, sy_, cy_;
+                            sincos(p, &sl, &cl);
+                            sincos(-bw0, &sy_, &cy_);
+                            double ldx = sl / maxc, ldy = (1.0 - cl) / (m == HOPE_RS_L ? maxc : -maxc);
+                            double gdx = cy_ * ldx + sy_ * ldy, gdy = -sy_ * ldx + cy_ * ldy;
+                            lx = bx0 + gdx; ly = by0 + gdy;
+                            lyaw = (m == HOPE_RS_L) ? bw0 + p : bw0 - p;
+                        }
+                    }
+                    nonzero = lx != 0.0;  // trailing samples with x == 0.0 are dropped (:501-505)
+                    double gx = cg * lx + sg * ly + q0x, gy = -sg * lx + cg * ly + q0y;  // :47-48
+                    double gyaw = pi_2_pi(lyaw + q0h);                                   // :49
+                    if (gx < xmin || gx > xmax || gy < ymin || gy > ymax) hit = true;    // car_parking_base.py:462-464
+                    else {
+                        double cth, sth, bx[4], by[4];
+                        sincos(gyaw, &sth, &cth);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {  // :468-471
+                            bx[q] = cth * par.box_x[q] - sth * par.box_y[q] + gx;
+                            by[q] = sth * par.box_x[q] + cth * par.box_y[q] + gy;
+                        }
+                        double vxmin = fmin(fmin(bx[0], bx[1]), fmin(bx[2], bx[3])), vxmax = fmax(fmax(bx[0], bx[1]), fmax(bx[2], bx[3]));
+                        double vymin = fmin(fmin(by[0], by[1]), fmin(by[2], by[3])), vymax = fmax(fmax(by[0], by[1]), fmax(by[2], by[3]));
+                        for (int ob = 0; ob < nobs && !hit; ++ob) {
+                            double4 bb = ld_aabb(aabb + ob);
+                            // a hit needs rx inside both segments' x-ranges and ry inside both y-ranges (:518-526):
+                            // disjoint boxes cannot produce one, so this reject is exact
+                            if (vxmax < bb.x || bb.y < vxmin || vymax < bb.z || bb.w < vymin) continue;
+                            int nv = nvp[ob];
+                            double2 p1 = __ldg(verts + ob * MAXV);
+                            for (int j = 0; j < nv && !hit; ++j) {
+                                double2 p2 = __ldg(verts + ob * MAXV + ((j + 1 == nv) ? 0 : j + 1));
+                                double dd = p2.y - p1.y, ee = p1.x - p2.x, ff = p1.y * p2.x - p1.x * p2.y;  // :504-506
+                                double oxmax = fmax(p1.x, p2.x), oxmin = fmin(p1.x, p2.x), oymax = fmax(p1.y, p2.y), oymin = fmin(p1.y, p2.y);
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    int q2 = (q + 1) & 3;
+                                    double vx1 = bx[q], vy1 = by[q], vx2 = bx[q2], vy2 = by[q2];
+                                    double exmax = fmax(vx1, vx2), exmin = fmin(vx1, vx2), eymax = fmax(vy1, vy2), eymin = fmin(vy1, vy2);
+                                    if (exmax < oxmin || oxmax < exmin || eymax < oymin || oymax < eymin) continue;
+                                    double a = vy2 - vy1, b = vx1 - vx2, c = vy1 * vx2 - vx1 * vy2;  // :477-479
+                                    double det = a * ee - b * dd;                                    // :509
+                                    if (det == 0.0) continue;
+                                    double rx = (b * ff - c * ee) / det, ry = (c * dd - a * ff) / det;  // :512-513
+                                    bool okx = !(rx > oxmax) && !(rx < oxmin) && !(rx > exmax) && !(rx < exmin);
+                                    bool oky = !(ry > oymax) && !(ry < oymin) && !(ry > eymax) && !(ry < eymin);
+                                    if (okx && oky) hit = true;
+                                }
+                                p1 = p2;
+                            }
+                        }
+                    }
+                }
+                unsigned mh = __ballot_sync(HOPE_FULL_MASK, hit), mz = __ballot_sync(HOPE_FULL_MASK, nonzero);
+                if (mz) {
+                    if (pending_bad) bad = true;
+                    int top = 31 - __clz(mz);
+                    unsigned commit = (top == 31) ? 0xffffffffu : ((1u << (top + 1)) - 1);
+                    if (mh & commit) bad = true;
+                    pending_bad = (mh & ~commit) != 0;
+                } else if (mh) pending_bad = true;
+            }
+            __syncwarp();
+        }
+        if (!bad) found = wi;
+    }
+    if (lane == 0) {
+        if (out.rs_ntried) out.rs_ntried[env] = (uint8_t)tried;
+        if (found >= 0) {
+            const RsWord w = rs.words[(size_t)env * MAXW + found];
+            if (out.rs_found) out.rs_found[env] = 1;
+            if (out.rs_nseg) out.rs_nseg[env] = w.n;
+            if (out.rs_L) out.rs_L[env] = w.L / maxc;
+            for (int k = 0; k < 5; ++k) {
+                if (out.rs_types) out.rs_types[5 * env + k] = k < w.n ? w.types[k] : HOPE_RS_NONE;
+                if (out.rs_lengths) out.rs_lengths[5 * env + k] = k < w.n ? w.len[k] / maxc : 0.0;  // reeds_shepp.py:51
+            }
+        }
+    }
+}
+
+// small helpers -------------------------------------------------------------------------------
+__global__ void k_table_reduce(const double *__restrict__ dist_star, double *__restrict__ pend, double *__restrict__ pmax) {
+    // one block per upsampled ray: pend[rho][j] = max_k dist_star[rho][j][k], pmax[rho] = max_j pend
+    int rho = blockIdx.x, j = threadIdx.x;
+    __shared__ double sh[64];
+    double m = -1.0;
+    if (j < NACT) {
+        const double *row = dist_star + ((size_t)rho * NACT + j) * NITER;
+        m = row[0];
+        for (int k = 1; k < NITER; ++k) m = fmax(m, row[k]);
+        pend[(size_t)rho * NACT + j] = m;
+    }
+    sh[j] = m;
+    __syncthreads();
+    if (j == 0) {
+        double mm = sh[0];
+        for (int q = 1; q < NACT; ++q) mm = fmax(mm, sh[q]);
+        pmax[rho] = mm;
+    }
+}
+
+}  // namespace hope
+
+// =============================================================================================
+// Host side: context and C ABI
+// =============================================================================================
+using namespace hope;
+
+struct hope_ctx {
+    int device = 0, n = 0, pool = 0;
+    hope_params par;
+    // pool
+    double *d_obs = nullptr, *d_aabb = nullptr, *d_meta = nullptr;
+    uint8_t *d_nv = nullptr;
+    int *d_nobs = nullptr;
+    // tables
+    double *d_tab = nullptr;  // ray_a ray_b lidar_base mask_base w_lo w_hi | dist_star | pend | pmax
+    bool have_tables = false, have_scenes = false, have_reset = false;
+    double maxc = 0.0;
+    // state
+    double *d_pose = nullptr, *d_accum = nullptr;
+    int *d_t = nullptr, *d_scene = nullptr;
+    uint8_t *d_pending = nullptr, *d_gate = nullptr;
+    unsigned long long *d_counters = nullptr;
+    // RS scratch
+    RsWord *d_words = nullptr;
+    uint8_t *d_ntry = nullptr, *d_ncand = nullptr;
+    // host-API staging
+    double *d_action = nullptr;
+    void *d_stage = nullptr;
+    size_t stage_bytes = 0;
+    hope_out stage_out;
+    cudaStream_t own_stream = nullptr;
+    unsigned long long launches = 0;
+    std::string last_error;
+};
+
+namespace {
+
+int fail(hope_ctx *c, cudaError_t e, const char *what) {
+    if (c) c->last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return HOPE_ERR_CUDA;
+}
+#define CK(call)                                                   \
+    do {                                                           \
+        cudaError_t e_ = (call);                                   \
+        if (e_ != cudaSuccess) return fail(ctx, e_, #call);        \
+    } while (0)
+
+Pool make_pool(const hope_ctx *c) { return Pool{c->d_obs, c->d_nv, c->d_aabb, c->d_meta, c->d_nobs, c->pool}; }
+EnvState make_state(const hope_ctx *c) { return EnvState{c->d_pose, c->d_t, c->d_accum, c->d_scene, c->d_pending, c->d_gate, c->d_counters}; }
+Tables make_tables(const hope_ctx *c) {
+    const double *t = c->d_tab;
+    Tables tb;
+    tb.ray_a = t; tb.ray_b = t + 120; tb.lidar_base = t + 240; tb.mask_base = t + 360; tb.w_lo = t + 480; tb.w_hi = t + 496;
+    tb.dist_star = t + 512; tb.pend = tb.dist_star + (size_t)NUP * NACT * NITER; tb.pmax = tb.pend + (size_t)NUP * NACT;
+    tb.maxc = c->maxc;
+    return tb;
+}
+RsScratch make_rs(const hope_ctx *c) { return RsScratch{c->d_words, c->d_ntry, c->d_ncand}; }
+
+constexpr int ADV_THREADS = 128, OBS_THREADS = 256, ENUM_THREADS = 128, CHK_THREADS = 256;
+
+int launch_step(hope_ctx *ctx, const double *d_action, const hope_out &out, unsigned stages, int reset_all, cudaStream_t s) {
+    const int n = ctx->n;
+    Pool pool = make_pool(ctx);
+    EnvState st = make_state(ctx);
+    Tables tb = make_tables(ctx);
+    k_advance<<<(n + ADV_THREADS - 1) / ADV_THREADS, ADV_THREADS, 0, s>>>(n, pool, st, d_action, ctx->par, out, reset_all);
+    ctx->launches++;
+    if (stages & HOPE_STAGE_OBSERVE) {
+        const int wpb = OBS_THREADS / 32;
+        k_observe<<<(n + wpb - 1) / wpb, OBS_THREADS, wpb * sizeof(ObserveSmem), s>>>(n, pool, st, tb, ctx->par, out);
+        ctx->launches++;
+    }
+    if (stages & HOPE_STAGE_RS) {
+        RsScratch rs = make_rs(ctx);
+        k_rs_enumerate<<<(n + ENUM_THREADS - 1) / ENUM_THREADS, ENUM_THREADS, 0, s>>>(n, pool, st, tb, rs, out);
+        const int wpb = CHK_THREADS / 32;
+        k_rs_check<<<(n + wpb - 1) / wpb, CHK_THREADS, wpb * sizeof(CheckSmem), s>>>(n, pool, st, tb, rs, ctx->par, out);
+        ctx->launches += 2;
+    }
+    CK(cudaGetLastError());
+    return HOPE_OK;
+}
+
+struct OutField { size_t offset; size_t elem; int per_env; };
+#define OF(member, type, per) OutField{offsetof(hope_out, member), sizeof(type), per}
+const OutField kOutFields[] = {
+    OF(pose, double, 3), OF(lidar, double, NRAY), OF(mask, double, NACT), OF(mask_steps, uint8_t, NACT),
+    OF(target, double, 5), OF(reward, double, 1), OF(reward_info, double, 5), OF(status, int32_t, 1),
+    OF(done, uint8_t, 1), OF(substeps, uint8_t, 1), OF(retreated, uint8_t, 1), OF(was_reset, uint8_t, 1),
+    OF(rs_found, uint8_t, 1), OF(rs_nseg, uint8_t, 1), OF(rs_types, uint8_t, 5), OF(rs_lengths, double, 5),
+    OF(rs_L, double, 1), OF(rs_ncand, uint8_t, 1), OF(rs_ntried, uint8_t, 1)};
+constexpr int kNumOutFields = sizeof(kOutFields) / sizeof(kOutFields[0]);
+
+void *&field_ptr(hope_out &o, const OutField &f) { return *reinterpret_cast<void **>(reinterpret_cast<char *>(&o) + f.offset); }
+void *field_ptr_c(const hope_out &o, const OutField &f) { return *reinterpret_cast<void *const *>(reinterpret_cast<const char *>(&o) + f.offset); }
+
+int ensure_stage(hope_ctx *ctx) {
+    if (ctx->d_stage) return HOPE_OK;
+    size_t total = 0;
+    for (int k = 0; k < kNumOutFields; ++k) total += ((kOutFields[k].elem * kOutFields[k].per_env * ctx->n + 255) / 256) * 256;
+    CK(cudaMalloc(&ctx->d_stage, total));
+    CK(cudaMemset(ctx->d_stage, 0, total));
+    ctx->stage_bytes = total;
+    size_t off = 0;
+    for (int k = 0; k < kNumOutFields; ++k) {
+        field_ptr(ctx->stage_out, kOutFields[k]) = static_cast<char *>(ctx->d_stage) + off;
+        off += ((kOutFields[k].elem * kOutFields[k].per_env * ctx->n + 255) / 256) * 256;
+    }
+    CK(cudaMalloc(&ctx->d_action, sizeof(double) * 2 * ctx->n));
+    CK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    return HOPE_OK;
+}
+
+int copy_back(hope_ctx *ctx, const hope_host_out *h_out) {
+    for (int k = 0; k < kNumOutFields; ++k) {
+        void *dst = field_ptr_c(*h_out, kOutFields[k]);
+        if (!dst) continue;
+        CK(cudaMemcpyAsync(dst, field_ptr_c(ctx->stage_out, kOutFields[k]), kOutFields[k].elem * kOutFields[k].per_env * ctx->n,
+                           cudaMemcpyDeviceToHost, ctx->own_stream));
+    }
+    CK(cudaStreamSynchronize(ctx->own_stream));
+    return HOPE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hope_version(void) { return 100; }
+
+int hope_default_params(hope_params *p) {
+    if (!p) return HOPE_ERR_INVALID;
+    memset(p, 0, sizeof(*p));
+    p->wheel_base = 2.8;
+    const double front_hang = 0.96, rear_hang = 0.93, width = 1.94;
+    p->box_x[0] = -rear_hang; p->box_x[1] = front_hang + p->wheel_base; p->box_x[2] = front_hang + p->wheel_base; p->box_x[3] = -rear_hang;
+    p->box_y[0] = -width / 2; p->box_y[1] = -width / 2; p->box_y[2] = width / 2; p->box_y[3] = width / 2;
+    p->valid_speed[0] = -2.5; p->valid_speed[1] = 2.5;
+    p->valid_steer[0] = -0.75; p->valid_steer[1] = 0.75;
+    p->num_step = 10; p->step_length = 0.05; p->mini_iter = 20;
+    p->lidar_range = 10.0; p->tolerant_time = 200; p->rs_max_dist = 10.0; p->rs_step = 0.1;
+    p->reward_weight[0] = 1; p->reward_weight[1] = 0; p->reward_weight[2] = 5; p->reward_weight[3] = 0; p->reward_weight[4] = 10;
+    p->reward_ratio = 0.1; p->env_collide = 0; p->auto_reset = 1;
+    return HOPE_OK;
+}
+
+const char *hope_strerror(int status) {
+    switch (status) {
+    case HOPE_OK: return "ok";
+    case HOPE_ERR_INVALID: return "invalid argument";
+    case HOPE_ERR_CUDA: return "CUDA runtime error (see hope_last_cuda_error)";
+    case HOPE_ERR_NO_TABLES: return "tables not uploaded (hope_upload_tables)";
+    case HOPE_ERR_NO_SCENES: return "scene pool empty or envs not reset (hope_set_scene_pool / hope_reset)";
+    case HOPE_ERR_CAPACITY: return "scene exceeds HOPE_MAX_OBS / HOPE_MAX_VERTS";
+    default: return "unknown status";
+    }
+}
+
+const char *hope_last_cuda_error(const hope_ctx *ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+int hope_n_envs(const hope_ctx *ctx) { return ctx ? ctx->n : HOPE_ERR_INVALID; }
+
+int hope_create(hope_ctx **out, int device, int n_envs, int pool_size, const hope_params *p) {
+    if (!out || n_envs <= 0 || pool_size <= 0) return HOPE_ERR_INVALID;
+    hope_ctx *ctx = new (std::nothrow) hope_ctx();
+    if (!ctx) return HOPE_ERR_INVALID;
+    *out = ctx;
+    ctx->device = device; ctx->n = n_envs; ctx->pool = pool_size;
+    if (p) ctx->par = *p; else hope_default_params(&ctx->par);
+    if (ctx->par.env_collide) { ctx->last_error = "ENV_COLLIDE=True is not supported (reference default False, configs.py:79)"; return HOPE_ERR_INVALID; }
+    memset(&ctx->stage_out, 0, sizeof(ctx->stage_out));
+    ctx->maxc = tan(ctx->par.valid_steer[1]) / ctx->par.wheel_base;  // car_parking_base.py:422
+    CK(cudaSetDevice(device));
+    const size_t P = pool_size, N = n_envs;
+    CK(cudaMalloc(&ctx->d_obs, sizeof(double) * P * MAXE * 2));
+    CK(cudaMalloc(&ctx->d_aabb, sizeof(double) * P * MAXO * 4));
+    CK(cudaMalloc(&ctx->d_meta, sizeof(double) * P * META));
+    CK(cudaMalloc(&ctx->d_nv, P * MAXO));
+    CK(cudaMalloc(&ctx->d_nobs, sizeof(int) * P));
+    CK(cudaMemset(ctx->d_nv, 0, P * MAXO));
+    CK(cudaMemset(ctx->d_nobs, 0, sizeof(int) * P));
+    const size_t tab = 512 + (size_t)NUP * NACT * NITER + (size_t)NUP * NACT + NUP;
+    CK(cudaMalloc(&ctx->d_tab, sizeof(double) * tab));
+    CK(cudaMalloc(&ctx->d_pose, sizeof(double) * 3 * N));
+    CK(cudaMalloc(&ctx->d_accum, sizeof(double) * N));
+    CK(cudaMalloc(&ctx->d_t, sizeof(int) * N));
+    CK(cudaMalloc(&ctx->d_scene, sizeof(int) * N));
+    CK(cudaMalloc(&ctx->d_pending, N));
+    CK(cudaMalloc(&ctx->d_gate, N));
+    CK(cudaMalloc(&ctx->d_counters, sizeof(unsigned long long) * 8));
+    CK(cudaMemset(ctx->d_counters, 0, sizeof(unsigned long long) * 8));
+    CK(cudaMemset(ctx->d_pending, 0, N));
+    CK(cudaMemset(ctx->d_gate, 0, N));
+    CK(cudaMalloc(&ctx->d_words, sizeof(RsWord) * N * MAXW));
+    CK(cudaMalloc(&ctx->d_ntry, N));
+    CK(cudaMalloc(&ctx->d_ncand, N));
+    CK(cudaFuncSetAttribute(k_observe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((OBS_THREADS / 32) * sizeof(ObserveSmem))));
+    CK(cudaFuncSetAttribute(k_rs_check, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((CHK_THREADS / 32) * sizeof(CheckSmem))));
+    return HOPE_OK;
+}
+
+int hope_destroy(hope_ctx *ctx) {
+    if (!ctx) return HOPE_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    void *ptrs[] = {ctx->d_obs, ctx->d_aabb, ctx->d_meta, ctx->d_nv, ctx->d_nobs, ctx->d_tab, ctx->d_pose, ctx->d_accum, ctx->d_t,
+                    ctx->d_scene, ctx->d_pending, ctx->d_gate, ctx->d_counters, ctx->d_words, ctx->d_ntry, ctx->d_ncand,
+                    ctx->d_action, ctx->d_stage};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return HOPE_OK;
+}
+
+int hope_upload_tables(hope_ctx *ctx, const double *ray_a, const double *ray_b, const double *lidar_base, const double *mask_base,
+                       const double *dist_star, const double *w_lo, const double *w_hi) {
+    if (!ctx || !ray_a || !ray_b || !lidar_base || !mask_base || !dist_star || !w_lo || !w_hi) return HOPE_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    std::vector<double> head(512, 0.0);
+    memcpy(&head[0], ray_a, 120 * 8); memcpy(&head[120], ray_b, 120 * 8); memcpy(&head[240], lidar_base, 120 * 8);
+    memcpy(&head[360], mask_base, 120 * 8); memcpy(&head[480], w_lo, 80); memcpy(&head[496], w_hi, 80);
+    CK(cudaMemcpy(ctx->d_tab, head.data(), 512 * 8, cudaMemcpyHostToDevice));
+    double *ds = ctx->d_tab + 512;
+    CK(cudaMemcpy(ds, dist_star, sizeof(double) * NUP * NACT * NITER, cudaMemcpyHostToDevice));
+    double *pend = ds + (size_t)NUP * NACT * NITER, *pmax = pend + (size_t)NUP * NACT;
+    k_table_reduce<<<NUP, 64>>>(ds, pend, pmax);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    ctx->have_tables = true;
+    return HOPE_OK;
+}
+
+int hope_set_scene_pool(hope_ctx *ctx, int first, int n, const double *start, const double *dest, const double *bounds,
+                        const double *obs_xy, const int32_t *nverts) {
+    if (!ctx || first < 0 || n <= 0 || first + n > ctx->pool || !start || !dest || !bounds || !obs_xy || !nverts) return HOPE_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    std::vector<double> meta((size_t)n * META), aabb((size_t)n * MAXO * 4, 0.0), obs((size_t)n * MAXE * 2, 0.0);
+    std::vector<uint8_t> nv((size_t)n * MAXO, 0);
+    std::vector<int> nobs(n, 0);
+    const hope_params &par = ctx->par;
+    for (int i = 0; i < n; ++i) {
+        double *m = &meta[(size_t)i * META];
+        for (int k = 0; k < 3; ++k) { m[M_START + k] = start[3 * i + k]; m[M_DEST + k] = dest[3 * i + k]; }
+        for (int k = 0; k < 4; ++k) m[M_BOUNDS + k] = bounds[4 * i + k];
+        // dest box (State.create_box, vehicle.py:32-36) and its shoelace area, on the host libm
+        double c = cos(dest[3 * i + 2]), s = sin(dest[3 * i + 2]), ms = -s;
+        double bx[4], by[4];
+        for (int k = 0; k < 4; ++k) {
+            bx[k] = c * par.box_x[k] + ms * par.box_y[k] + dest[3 * i];
+            by[k] = s * par.box_x[k] + c * par.box_y[k] + dest[3 * i + 1];
+            m[M_DBX + k] = bx[k]; m[M_DBY + k] = by[k];
+        }
+        double sa = 0.0;
+        for (int k = 0; k < 4; ++k) { int j = (k + 1) & 3; sa += bx[k] * by[j] - bx[j] * by[k]; }
+        m[M_DAREA] = fabs(sa) * 0.5;
+        m[M_DNORM] = fmax(hypot(dest[3 * i] - start[3 * i], dest[3 * i + 1] - start[3 * i + 1]), 10.0);  // car_parking_base.py:211
+        m[M_DAABB] = fmin(fmin(bx[0], bx[1]), fmin(bx[2], bx[3])); m[M_DAABB + 1] = fmax(fmax(bx[0], bx[1]), fmax(bx[2], bx[3]));
+        m[M_DAABB + 2] = fmin(fmin(by[0], by[1]), fmin(by[2], by[3])); m[M_DAABB + 3] = fmax(fmax(by[0], by[1]), fmax(by[2], by[3]));
+        // obstacles: compact non-empty rings to the front
+        int no = 0;
+        for (int k = 0; k < MAXO; ++k) {
+            int v = nverts[(size_t)i * MAXO + k];
+            if (v == 0) continue;
+            if (v < 3 || v > MAXV) return HOPE_ERR_CAPACITY;
+            const double *src = obs_xy + ((size_t)i * MAXO + k) * MAXV * 2;
+            double *dst = &obs[((size_t)i * MAXO + no) * MAXV * 2];
+            double xmn = src[0], xmx = src[0], ymn = src[1], ymx = src[1];
+            for (int j = 0; j < v; ++j) {
+                dst[2 * j] = src[2 * j]; dst[2 * j + 1] = src[2 * j + 1];
+                xmn = fmin(xmn, src[2 * j]); xmx = fmax(xmx, src[2 * j]); ymn = fmin(ymn, src[2 * j + 1]); ymx = fmax(ymx, src[2 * j + 1]);
+            }
+            double *bb = &aabb[((size_t)i * MAXO + no) * 4];
+            bb[0] = xmn; bb[1] = xmx; bb[2] = ymn; bb[3] = ymx;
+            nv[(size_t)i * MAXO + no] = (uint8_t)v;
+            ++no;
+        }
+        nobs[i] = no;
+    }
+    CK(cudaMemcpy(ctx->d_meta + (size_t)first * META, meta.data(), meta.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_aabb + (size_t)first * MAXO * 4, aabb.data(), aabb.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_obs + (size_t)first * MAXE * 2, obs.data(), obs.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_nv + (size_t)first * MAXO, nv.data(), nv.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_nobs + first, nobs.data(), nobs.size() * sizeof(int), cudaMemcpyHostToDevice));
+    ctx->have_scenes = true;
+    return HOPE_OK;
+}
+
+int hope_reset(hope_ctx *ctx, const int32_t *h_scene_ids, const hope_out *d_out, void *stream) {
+    if (!ctx || !d_out) return HOPE_ERR_INVALID;
+    if (!ctx->have_tables) return HOPE_ERR_NO_TABLES;
+    if (!ctx->have_scenes) return HOPE_ERR_NO_SCENES;
+    CK(cudaSetDevice(ctx->device));
+    std::vector<int> ids(ctx->n);
+    for (int i = 0; i < ctx->n; ++i) {
+        ids[i] = h_scene_ids ? h_scene_ids[i] : i % ctx->pool;
+        if (ids[i] < 0 || ids[i] >= ctx->pool) return HOPE_ERR_INVALID;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CK(cudaMemcpyAsync(ctx->d_scene, ids.data(), sizeof(int) * ctx->n, cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));  // ids is a local buffer
+    ctx->have_reset = true;
+    // the reset step computes the observation; RS is gated off by t > 1 (car_parking_base.py:293)
+    return launch_step(ctx, nullptr, *d_out, HOPE_STAGE_ADVANCE | HOPE_STAGE_OBSERVE | HOPE_STAGE_RS, 1, s);
+}
+
+int hope_step(hope_ctx *ctx, const double *d_action, const hope_out *d_out, unsigned stages, void *stream) {
+    if (!ctx || !d_action || !d_out) return HOPE_ERR_INVALID;
+    if (!ctx->have_tables) return HOPE_ERR_NO_TABLES;
+    if (!ctx->have_reset) return HOPE_ERR_NO_SCENES;
+    CK(cudaSetDevice(ctx->device));
+    return launch_step(ctx, d_action, *d_out, stages | HOPE_STAGE_ADVANCE, 0, static_cast<cudaStream_t>(stream));
+}
+
+int hope_step_kinematics_collision(hope_ctx *ctx, const double *d_action, double *d_pose, uint8_t *d_collided, uint8_t *d_substeps,
+                                   void *stream) {
+    if (!ctx || !d_action) return HOPE_ERR_INVALID;
+    if (!ctx->have_reset) return HOPE_ERR_NO_SCENES;
+    CK(cudaSetDevice(ctx->device));
+    hope_out o;
+    memset(&o, 0, sizeof(o));
+    o.pose = d_pose; o.retreated = d_collided; o.substeps = d_substeps;
+    return launch_step(ctx, d_action, o, HOPE_STAGE_ADVANCE, 0, static_cast<cudaStream_t>(stream));
+}
+
+int hope_step_host(hope_ctx *ctx, const double *h_action, const hope_host_out *h_out, unsigned stages) {
+    if (!ctx || !h_action || !h_out) return HOPE_ERR_INVALID;
+    if (!ctx->have_tables) return HOPE_ERR_NO_TABLES;
+    if (!ctx->have_reset) return HOPE_ERR_NO_SCENES;
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_stage(ctx);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->d_action, h_action, sizeof(double) * 2 * ctx->n, cudaMemcpyHostToDevice, ctx->own_stream));
+    rc = launch_step(ctx, ctx->d_action, ctx->stage_out, stages | HOPE_STAGE_ADVANCE, 0, ctx->own_stream);
+    if (rc) return rc;
+    return copy_back(ctx, h_out);
+}
+
+int hope_reset_host(hope_ctx *ctx, const int32_t *h_scene_ids, const hope_host_out *h_out) {
+    if (!ctx || !h_out) return HOPE_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_stage(ctx);
+    if (rc) return rc;
+    rc = hope_reset(ctx, h_scene_ids, &ctx->stage_out, ctx->own_stream);
+    if (rc) return rc;
+    return copy_back(ctx, h_out);
+}
+
+int hope_get_state(hope_ctx *ctx, double *h_pose, int32_t *h_t, double *h_accum, int32_t *h_scene_id) {
+    if (!ctx) return HOPE_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    if (h_pose) CK(cudaMemcpy(h_pose, ctx->d_pose, sizeof(double) * 3 * ctx->n, cudaMemcpyDeviceToHost));
+    if (h_t) CK(cudaMemcpy(h_t, ctx->d_t, sizeof(int) * ctx->n, cudaMemcpyDeviceToHost));
+    if (h_accum) CK(cudaMemcpy(h_accum, ctx->d_accum, sizeof(double) * ctx->n, cudaMemcpyDeviceToHost));
+    if (h_scene_id) CK(cudaMemcpy(h_scene_id, ctx->d_scene, sizeof(int) * ctx->n, cudaMemcpyDeviceToHost));
+    return HOPE_OK;
+}
+
+int hope_set_state(hope_ctx *ctx, const double *h_pose, const int32_t *h_t, const double *h_accum) {
+    if (!ctx) return HOPE_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    if (h_pose) CK(cudaMemcpy(ctx->d_pose, h_pose, sizeof(double) * 3 * ctx->n, cudaMemcpyHostToDevice));
+    if (h_t) CK(cudaMemcpy(ctx->d_t, h_t, sizeof(int) * ctx->n, cudaMemcpyHostToDevice));
+    if (h_accum) CK(cudaMemcpy(ctx->d_accum, h_accum, sizeof(double) * ctx->n, cudaMemcpyHostToDevice));
+    CK(cudaMemset(ctx->d_pending, 0, ctx->n));
+    return HOPE_OK;
+}
+
+int hope_get_counters(hope_ctx *ctx, uint64_t h_counters[8]) {
+    if (!ctx || !h_counters) return HOPE_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    unsigned long long tmp[8];
+    CK(cudaMemcpy(tmp, ctx->d_counters, sizeof(tmp), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 8; ++k) h_counters[k] = tmp[k];
+    h_counters[5] = ctx->launches;
+    return HOPE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,160 @@
+/* hope_b200.h — C ABI of the B200-native batched ParkingEnv step.
+ *
+ * The reference (jiamiya/HOPE) has no FFI: its boundary is the Python class surface
+ *   CarParkingWrapper.reset / .step          src/env/env_wrapper.py:58-85
+ *   CarParking.reset / .step                 src/env/car_parking_base.py:127-138, 235-299
+ * This header is what a binding for that path would call (see INTEGRATION.md for the ctypes
+ * stub).  Plain pointers and sizes only; no torch / CUDA types (a stream is passed as void*).
+ *
+ * Conventions
+ *   - every function returns HOPE_OK (0) or a negative hope_status; nothing throws;
+ *   - "d_" parameters are DEVICE pointers owned by the caller (e.g. torch tensors),
+ *     "h_" parameters are HOST pointers; all floating point data is float64 like the reference;
+ *   - step functions are asynchronous on `stream` (a cudaStream_t, NULL = default stream);
+ *   - one context per GPU; a context is not thread-safe.
+ *
+ * Scene capacity: HOPE_MAX_OBS obstacle rings of up to HOPE_MAX_VERTS vertices.
+ */
+#ifndef HOPE_B200_H
+#define HOPE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HOPE_MAX_OBS 16
+#define HOPE_MAX_VERTS 4
+#define HOPE_N_LIDAR 120     /* configs.py:96  LIDAR_NUM */
+#define HOPE_N_ACTION 42     /* configs.py:115 N_DISCRETE_ACTION */
+#define HOPE_N_MASK_ITER 10  /* action_mask.py:9 n_iter */
+#define HOPE_N_UPSAMPLE 1200 /* LIDAR_NUM * up_sample_rate, action_mask.py:18 */
+#define HOPE_RS_MAX_SEG 5
+
+typedef enum {
+    HOPE_OK = 0,
+    HOPE_ERR_INVALID = -1,     /* bad argument */
+    HOPE_ERR_CUDA = -2,        /* a CUDA runtime call failed (hope_last_cuda_error) */
+    HOPE_ERR_NO_TABLES = -3,   /* hope_upload_tables not called yet */
+    HOPE_ERR_NO_SCENES = -4,   /* hope_set_scene_pool / hope_reset not called yet */
+    HOPE_ERR_CAPACITY = -5     /* scene exceeds HOPE_MAX_OBS / HOPE_MAX_VERTS */
+} hope_status;
+
+/* vehicle.py:13-18 */
+enum { HOPE_CONTINUE = 1, HOPE_ARRIVED = 2, HOPE_COLLIDED = 3, HOPE_OUTBOUND = 4, HOPE_OUTTIME = 5 };
+/* Reeds-Shepp segment codes in rs_types (reeds_shepp.py ctypes 'S','L','R'); 255 = unused slot */
+enum { HOPE_RS_S = 0, HOPE_RS_L = 1, HOPE_RS_R = 2, HOPE_RS_NONE = 255 };
+
+/* stages of one env step (bit mask) */
+enum {
+    HOPE_STAGE_ADVANCE = 1,  /* kinematics + collision + arrival + status + reward (always runs) */
+    HOPE_STAGE_OBSERVE = 2,  /* LiDAR raycast + action-mask sweep + target representation */
+    HOPE_STAGE_RS = 4,       /* Reeds-Shepp search (car_parking_base.py:293-297 gate) */
+    HOPE_STAGE_ALL = 7
+};
+
+/* Mirrors the constants of src/configs.py the path reads. */
+typedef struct hope_params {
+    double wheel_base;        /* configs.py:13  WHEEL_BASE 2.8 */
+    double box_x[4], box_y[4];/* configs.py:20-24 VehicleBox corners rb, rf, lf, lb */
+    double valid_speed[2];    /* configs.py:32 */
+    double valid_steer[2];    /* configs.py:33 */
+    int num_step;             /* configs.py:37  NUM_STEP 10 */
+    double step_length;       /* configs.py:38  STEP_LENGTH 0.05 */
+    int mini_iter;            /* vehicle.py:66  20 */
+    double lidar_range;       /* configs.py:95  10 */
+    int tolerant_time;        /* configs.py:98  200 */
+    double rs_max_dist;       /* configs.py:104 10 */
+    double rs_step;           /* car_parking_base.py:424 sampling interval 0.1 m */
+    double reward_weight[5];  /* configs.py:181-187 time, rs_dist, dist, angle, box_union */
+    double reward_ratio;      /* configs.py:180 0.1 */
+    int env_collide;          /* configs.py:79  0 */
+    int auto_reset;           /* 1: an env that finished takes its next pool scene on the following step */
+} hope_params;
+
+/* Per-step outputs; DEVICE pointers, row-major [n_envs][...].  A NULL member is skipped. */
+typedef struct hope_out {
+    double *pose;         /* [n][3] x, y, heading after the step */
+    double *lidar;        /* [n][120]  lidar_simulator.py:31-46 (range minus own-box offset) */
+    double *mask;         /* [n][42]   action_mask.py:166-184 (steps/10, or all 0.01) */
+    uint8_t *mask_steps;  /* [n][42]   integer collision-free steps 0..10 after the min filter */
+    double *target;       /* [n][5]    car_parking_base.py:372-381 */
+    double *reward;       /* [n]       env_wrapper.py:10-35 shaped scalar */
+    double *reward_info;  /* [n][5]    car_parking_base.py:285-289 */
+    int32_t *status;      /* [n]       HOPE_CONTINUE.. */
+    uint8_t *done;        /* [n]       status != CONTINUE */
+    uint8_t *substeps;    /* [n]       Vehicle.step calls made (0..10) */
+    uint8_t *retreated;   /* [n]       1 if the loop ended in a collision retreat */
+    uint8_t *was_reset;   /* [n]       1 if this step was an auto-reset (no motion, t = 1) */
+    uint8_t *rs_found;    /* [n]       info['path_to_dest'] is not None */
+    uint8_t *rs_nseg;     /* [n] */
+    uint8_t *rs_types;    /* [n][5] */
+    double *rs_lengths;   /* [n][5]    signed metres (PATH.lengths) */
+    double *rs_L;         /* [n]       PATH.L */
+    uint8_t *rs_ncand;    /* [n]       admissible words (diagnostic) */
+    uint8_t *rs_ntried;   /* [n]       words sampled and checked (diagnostic) */
+} hope_out;
+
+/* Host mirror of hope_out for hope_step_host (same shapes, HOST pointers, NULL = skip). */
+typedef hope_out hope_host_out;
+
+typedef struct hope_ctx hope_ctx;
+
+int hope_default_params(hope_params *p);
+int hope_create(hope_ctx **out, int device, int n_envs, int pool_size, const hope_params *p);
+int hope_destroy(hope_ctx *ctx);
+const char *hope_strerror(int status);
+const char *hope_last_cuda_error(const hope_ctx *ctx);
+
+/* Scene-independent tables, HOST pointers (built by the host layer with the reference's numpy
+ * expressions; model/action_mask.py:9-163, env/lidar_simulator.py:14-53, 86-88):
+ *   ray_a[120]=sin(theta_i)  ray_b[120]=-cos(theta_i)  lidar_base[120]  mask_base[120]
+ *   dist_star[1200][42][10]  w_lo[10]=1-r/10  w_hi[10]=r/10 */
+int hope_upload_tables(hope_ctx *ctx, const double *h_ray_a, const double *h_ray_b, const double *h_lidar_base,
+                       const double *h_mask_base, const double *h_dist_star, const double *h_w_lo,
+                       const double *h_w_hi);
+
+/* Scene pool, HOST pointers: scenes [first, first+n) of the pool.
+ *   start[n][3] dest[n][3] bounds[n][4]=(xmin,xmax,ymin,ymax) obs_xy[n][16][4][2] nverts[n][16]
+ * (ParkingMapNormal fields, parking_map_normal.py:460-494). */
+int hope_set_scene_pool(hope_ctx *ctx, int first, int n, const double *h_start, const double *h_dest,
+                        const double *h_bounds, const double *h_obs_xy, const int32_t *h_nverts);
+
+/* Procedural scenes on the host (bay / parallel cases, parking_map_normal.py:40-457), own RNG
+ * stream per scene (seed + index): level 0 Normal, 1 Complex, 2 Extrem.  Fills HOST arrays. */
+int hope_generate_scenes(int n, int level, uint64_t seed, int nthreads, double *h_start, double *h_dest,
+                         double *h_bounds, double *h_obs_xy, int32_t *h_nverts, int32_t *h_case_id);
+
+/* env.reset for every env: env i takes pool scene h_scene_ids[i] (NULL: scene i % pool),
+ * pose = start, t = 0, accum = 0, then the reset step (no action, t becomes 1; RS skipped). */
+int hope_reset(hope_ctx *ctx, const int32_t *h_scene_ids, const hope_out *d_out, void *stream);
+
+/* One CarParkingWrapper.step for every env.  d_action[n][2]: policy output in [-1,1]^2
+ * (env_wrapper.py:37-50 rescale happens on the device). */
+int hope_step(hope_ctx *ctx, const double *d_action, const hope_out *d_out, unsigned stages, void *stream);
+
+/* BASELINE cfg 2: kinematics + collision (+ arrival) only. */
+int hope_step_kinematics_collision(hope_ctx *ctx, const double *d_action, double *d_pose, uint8_t *d_collided,
+                                   uint8_t *d_substeps, void *stream);
+
+/* Same step with HOST buffers: copies h_action in, runs, copies the non-NULL outputs back,
+ * synchronises.  This is the end-to-end entry point a host-only caller (the reference's
+ * training loop) would use. */
+int hope_step_host(hope_ctx *ctx, const double *h_action, const hope_host_out *h_out, unsigned stages);
+int hope_reset_host(hope_ctx *ctx, const int32_t *h_scene_ids, const hope_host_out *h_out);
+
+/* State access (device -> host copies; synchronous). */
+int hope_get_state(hope_ctx *ctx, double *h_pose, int32_t *h_t, double *h_accum, int32_t *h_scene_id);
+int hope_set_state(hope_ctx *ctx, const double *h_pose, const int32_t *h_t, const double *h_accum);
+/* counters since creation: [0] env steps with an action, [1] auto-resets, [2] exact-orientation
+ * fallbacks taken, [3] RS word-capacity overflows, [4] RS zero-length words (reference asserts),
+ * [5] kernels launched by this context */
+int hope_get_counters(hope_ctx *ctx, uint64_t h_counters[8]);
+int hope_n_envs(const hope_ctx *ctx);
+int hope_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HOPE_B200_H */

@@ -1,0 +1,259 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI
+(hope_b200.capi -> libhope_b200.so); the oracle is only the checker.
+
+Bars (BASELINE.json north_star): collision booleans, status and action-mask step indices
+bit-exact; ego pose within 1e-5 (we assert 1e-9); float observations 1e-9.  Reeds-Shepp: word
+lengths 1e-9 when both sides pick the same word; found/not-found must agree except on
+equal-length ties, which the reference itself resolves by rounding noise.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+from hope_b200 import capi  # noqa: E402
+from hope_b200.batched_env import BatchedParkingEnv, generate_scenes  # noqa: E402
+from oracle import parking_oracle as po  # noqa: E402
+
+LEVELS = ("Normal", "Complex", "Extrem")
+POSE_TOL = 1e-9      # spec: 1e-5
+FLOAT_TOL = 1e-9
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+class Tally(object):
+    def __init__(self):
+        self.n = 0
+        self.maxdiff = {}
+        self.mismatch = {}
+
+    def diff(self, key, a, b, mask=None):
+        d = np.abs(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64))
+        if mask is not None:
+            d = d[mask]
+        if d.size:
+            self.maxdiff[key] = max(self.maxdiff.get(key, 0.0), float(d.max()))
+
+    def exact(self, key, a, b, mask=None):
+        ne = np.asarray(a) != np.asarray(b)
+        if ne.ndim > 1:
+            ne = ne.reshape(ne.shape[0], -1).any(axis=1)
+        if mask is not None:
+            ne = ne & mask
+        self.mismatch[key] = self.mismatch.get(key, 0) + int(ne.sum())
+        return ne
+
+    def report(self, title):
+        print(f"\n[{title}] env-steps compared: {self.n}")
+        print("  max |diff|:", {k: float(f"{v:.3g}") for k, v in self.maxdiff.items()})
+        print("  mismatches:", self.mismatch)
+
+
+def compare_step(tl, out, ref, ref_pose, live):
+    """out: dict of numpy arrays from the CUDA path; ref: OracleEnv.out; live: bool mask of envs to compare."""
+    tl.n += int(live.sum())
+    tl.diff("pose", out["pose"], ref_pose, live)
+    tl.exact("status", out["status"], ref["status"], live)
+    tl.exact("substeps", out["substeps"], ref["substeps"], live)
+    tl.exact("retreated(collision)", out["retreated"], ref["retreated"], live)
+    tl.diff("lidar", out["lidar"], ref["lidar"], live)
+    tl.exact("mask_steps", out["mask_steps"], ref["mask_steps"], live)
+    tl.diff("mask", out["mask"], ref["mask"], live)
+    tl.diff("target", out["target"], ref["target"], live)
+    tl.diff("reward", out["reward"], ref["reward"], live)
+    tl.diff("reward_info", out["reward_info"], ref["reward_info"], live)
+    tl.exact("rs_ncand", out["rs_ncand"], ref["rs_ncand"], live)
+    nf = tl.exact("rs_found", out["rs_found"], ref["rs_found"], live)
+    both = live & (out["rs_found"] == 1) & (ref["rs_found"] == 1)
+    same_word = both & ~(out["rs_types"] != ref["rs_types"]).any(axis=1)
+    tl.mismatch["rs_word_differs"] = tl.mismatch.get("rs_word_differs", 0) + int((both & ~same_word).sum())
+    tl.mismatch["rs_both_found"] = tl.mismatch.get("rs_both_found", 0) + int(both.sum())
+    tl.diff("rs_lengths(same word)", out["rs_lengths"], ref["rs_len"], same_word)
+    tl.diff("rs_L(same word)", out["rs_L"], ref["rs_L"], same_word)
+    return nf
+
+
+def gather(env):
+    torch.cuda.synchronize()
+    return {k: _np(v) for k, v in env.out.items()}
+
+
+def assert_bars(tl, rs_found_slack=0):
+    for k in ("status", "substeps", "retreated(collision)", "mask_steps", "rs_ncand"):
+        assert tl.mismatch[k] == 0, (k, tl.mismatch)
+    assert tl.maxdiff["pose"] <= POSE_TOL, tl.maxdiff
+    for k in ("lidar", "mask", "target", "reward", "reward_info"):
+        assert tl.maxdiff[k] <= FLOAT_TOL, (k, tl.maxdiff)
+    for k in ("rs_lengths(same word)", "rs_L(same word)"):
+        if k in tl.maxdiff:
+            assert tl.maxdiff[k] <= FLOAT_TOL, (k, tl.maxdiff)
+    assert tl.mismatch["rs_found"] <= rs_found_slack, tl.mismatch
+
+
+def test_library_reports_version_and_params():
+    lib = capi.load_library()
+    assert lib.hope_version() >= 100
+    p = capi.Params()
+    capi.check(lib.hope_default_params(p))
+    assert p.num_step == 10 and p.mini_iter == 20 and abs(p.box_x[1] - 3.76) < 1e-12
+
+
+@pytest.mark.parametrize("stem", ["episodes", "episodes_follow"])
+@pytest.mark.parametrize("level", LEVELS)
+def test_golden_episodes_through_cuda(golden_dir, level, stem):
+    """The traces recorded from the unmodified reference, replayed through the CUDA path: one env
+    per recorded episode, recorded float64 actions, free-running (no state correction)."""
+    g = np.load(os.path.join(golden_dir, f"{stem}_{level}.npz"))
+    n_ep = len(g["scene_start"])
+    scenes = dict(start=g["scene_start"], dest=g["scene_dest"], bounds=g["scene_bounds"], obs=g["scene_obs"], nverts=g["scene_nverts"])
+    env = BatchedParkingEnv(n_ep, scenes=scenes, auto_reset=False)
+    env.reset()
+    out = gather(env)
+    assert np.abs(out["lidar"] - g["scene_reset_lidar"]).max() <= FLOAT_TOL
+    assert np.array_equal(out["mask"], g["scene_reset_mask"])
+    assert np.abs(out["target"] - g["scene_reset_target"]).max() <= FLOAT_TOL
+    idx = [np.where(g["ep"] == e)[0] for e in range(n_ep)]
+    tl = Tally()
+    for k in range(max(len(i) for i in idx)):
+        live = np.array([k < len(i) for i in idx])
+        rows = np.array([i[k] if k < len(i) else i[-1] for i in idx])
+        act = np.where(live[:, None], g["action"][rows], 0.0)
+        env.step(torch.as_tensor(act, device=env.device).contiguous())
+        out = gather(env)
+        ref = dict(status=g["status"][rows], substeps=g["substeps"][rows], retreated=g["retreated"][rows], lidar=g["lidar"][rows],
+                   mask=g["mask"][rows], mask_steps=np.rint(g["mask"][rows] * 10).astype(np.uint8), target=g["target"][rows],
+                   reward=g["reward"][rows], reward_info=g["reward_info"][rows], rs_ncand=g["rs_ncand"][rows],
+                   rs_found=g["rs_found"][rows], rs_types=g["rs_types"][rows], rs_len=g["rs_lengths"][rows], rs_L=g["rs_L"][rows])
+        allz = (g["mask"][rows] == 0.01).all(axis=1)
+        ref["mask_steps"][allz] = 0
+        compare_step(tl, out, ref, g["pose"][rows], live)
+    tl.report(f"golden {stem}_{level} via CUDA")
+    assert_bars(tl, rs_found_slack=max(2, tl.n // 200))
+    env.close()
+
+
+def _lockstep(n, level, steps, seed, stages, cfg2=False):
+    sc = generate_scenes(n, level, seed)
+    env = BatchedParkingEnv(n, scenes=sc, auto_reset=False)
+    orc = po.OracleEnv(sc["start"], sc["dest"], sc["bounds"], sc["obs"], sc["nverts"])
+    env.reset()
+    ref = orc.reset_step(stages=1)
+    out = gather(env)
+    assert np.abs(out["lidar"] - ref["lidar"]).max() <= FLOAT_TOL
+    assert np.array_equal(out["mask_steps"], ref["mask_steps"].astype(np.uint8))
+    rng = np.random.default_rng(10_000 + seed)
+    tl = Tally()
+    live = np.ones(n, dtype=bool)
+    for _ in range(steps):
+        act = rng.uniform(-1.0, 1.0, size=(n, 2))
+        a_dev = torch.as_tensor(act, device=env.device).contiguous()
+        if cfg2:
+            env.step_kinematics_collision(a_dev)
+        else:
+            env.step(a_dev, stages=stages)
+        ref = orc.step(act, stages=(1 if stages & capi.STAGE_OBSERVE else 0) | (2 if stages & capi.STAGE_RS else 0))
+        out = gather(env)
+        if cfg2:
+            tl.n += int(live.sum())
+            tl.diff("pose", out["pose"], orc.pose, live)
+            tl.exact("retreated(collision)", out["retreated"], ref["retreated"], live)
+            tl.exact("substeps", out["substeps"], ref["substeps"], live)
+        else:
+            compare_step(tl, out, {**ref, "mask_steps": ref["mask_steps"].astype(np.uint8)}, orc.pose, live)
+        live &= ref["status"] == 1  # the oracle env has no auto-reset: stop comparing finished episodes
+    return tl, env
+
+
+def test_cfg2_kinematics_collision_4096():
+    """BASELINE cfg 2: 4 096 scenes, kinematics + ring collision, vs the oracle."""
+    tl, env = _lockstep(4096, "Normal", 64, 42, capi.STAGE_ADVANCE, cfg2=True)
+    tl.report("cfg2 4096 scenes x 64 steps")
+    assert tl.mismatch["retreated(collision)"] == 0 and tl.mismatch["substeps"] == 0, tl.mismatch
+    assert tl.maxdiff["pose"] <= POSE_TOL
+    assert env.counters()["kernel_launches"] > 0
+    env.close()
+
+
+def test_full_step_mixed_levels_vs_oracle():
+    """BASELINE cfg 3 at a size the oracle finishes in seconds: all stages, levels cycled."""
+    tl, env = _lockstep(3072, "mix", 48, 7, capi.STAGE_ALL)
+    tl.report("full step 3072 mixed scenes x 48 steps")
+    assert_bars(tl, rs_found_slack=max(2, tl.n // 500))
+    c = env.counters()
+    print("  counters:", c)
+    assert c["rs_capacity_overflows"] == 0 and c["rs_zero_length_words"] == 0
+    env.close()
+
+
+def test_host_buffer_api_matches_device_api():
+    sc = generate_scenes(512, "Complex", 3)
+    a = BatchedParkingEnv(512, scenes=sc, auto_reset=False)
+    b = BatchedParkingEnv(512, scenes=sc, auto_reset=False)
+    a.reset(); b.reset_host()
+    rng = np.random.default_rng(5)
+    for _ in range(5):
+        act = rng.uniform(-1, 1, size=(512, 2))
+        a.step(torch.as_tensor(act, device=a.device).contiguous())
+        h = b.step_host(act)
+        d = gather(a)
+        for k in ("lidar", "mask", "target", "reward", "status", "rs_found", "rs_lengths"):
+            assert np.array_equal(d[k], h[k]), k
+    a.close(); b.close()
+
+
+def test_auto_reset_takes_next_pool_scene():
+    n = 256
+    sc = generate_scenes(2 * n, "Normal", 11)
+    env = BatchedParkingEnv(n, scenes=sc, auto_reset=True)
+    env.reset()
+    # drive everybody out of bounds: full speed straight ahead
+    act = torch.zeros((n, 2), dtype=torch.float64, device=env.device); act[:, 1] = 1.0
+    seen_done = np.zeros(n, dtype=bool)
+    for _ in range(60):
+        env.step(act)
+        o = gather(env)
+        st = env.get_state()
+        was = o["was_reset"].astype(bool)
+        # an env that was done on the previous step is reset on this one: t == 1, pose == new scene start
+        assert (was == seen_done).all()
+        assert (st["t"][was] == 1).all()
+        assert np.array_equal(st["pose"][was], sc["start"][st["scene_id"][was]])
+        assert ((st["scene_id"][was] % n) == np.arange(n)[was]).all()
+        seen_done = o["done"].astype(bool)
+    assert env.counters()["auto_resets"] > 0
+    env.close()
+
+
+def test_edge_cases_empty_and_ragged_scenes():
+    """No obstacles at all, a single triangle, and a full 16-ring scene share one batch."""
+    base = generate_scenes(3, "Extrem", 5)
+    sc = {k: v.copy() for k, v in base.items()}
+    sc["nverts"][0, :] = 0                       # empty scene: lidar saturates, mask is all 1
+    sc["nverts"][1, :] = 0; sc["nverts"][1, 0] = 3  # one triangle
+    env = BatchedParkingEnv(3, scenes=sc, auto_reset=False)
+    orc = po.OracleEnv(sc["start"], sc["dest"], sc["bounds"], sc["obs"], sc["nverts"])
+    env.reset(); ref = orc.reset_step()
+    out = gather(env)
+    assert np.abs(out["lidar"] - ref["lidar"]).max() <= FLOAT_TOL
+    assert np.array_equal(out["mask_steps"], ref["mask_steps"].astype(np.uint8))
+    tb = po.mask_tables()
+    assert np.abs(out["lidar"][0] - (10.0 - tb["lidar_base"])).max() <= FLOAT_TOL
+    rng = np.random.default_rng(1)
+    tl = Tally()
+    for _ in range(20):
+        act = rng.uniform(-1, 1, size=(3, 2))
+        env.step(torch.as_tensor(act, device=env.device).contiguous())
+        ref = orc.step(act)
+        compare_step(tl, gather(env), {**ref, "mask_steps": ref["mask_steps"].astype(np.uint8)}, orc.pose, ref["status"] >= 1)
+    tl.report("edge cases")
+    assert_bars(tl, rs_found_slack=1)
+    env.close()
