@@ -182,6 +182,17 @@ class BatchedParkingEnv(object):
         names = ("env_steps", "auto_resets", "exact_orient_fallbacks", "rs_capacity_overflows", "rs_zero_length_words", "kernel_launches")
         return {k: int(buf[i]) for i, k in enumerate(names)}
 
+    KERNELS = ("k_advance", "k_observe", "k_rs_enumerate", "k_rs_check")
+
+    def profile(self, on=True):
+        capi.check(self.lib.hope_profile_enable(self.ctx, 1 if on else 0), self.ctx)
+
+    def profile_read(self):
+        """{kernel: (total_ms, launches)} measured with CUDA events on the launch stream."""
+        ms = (C.c_double * 4)(); cnt = (C.c_uint64 * 4)()
+        capi.check(self.lib.hope_profile_read(self.ctx, C.byref(ms), C.byref(cnt)), self.ctx)
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.KERNELS)}
+
     def close(self):
         if self.ctx:
             self.lib.hope_destroy(self.ctx)

@@ -932,6 +932,8 @@ struct hope_ctx {
     hope_out stage_out;
     cudaStream_t own_stream = nullptr;
     unsigned long long launches = 0;
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_events[4];  // begin/end pairs per kernel
     std::string last_error;
 };
 
@@ -961,23 +963,39 @@ RsScratch make_rs(const hope_ctx *c) { return RsScratch{c->d_words, c->d_ntry, c
 
 constexpr int ADV_THREADS = 128, OBS_THREADS = 256, ENUM_THREADS = 128, CHK_THREADS = 256;
 
+void prof_mark(hope_ctx *ctx, int which, cudaStream_t s) {
+    if (!ctx->profile) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, s);
+    ctx->prof_events[which].push_back(e);
+}
+
 int launch_step(hope_ctx *ctx, const double *d_action, const hope_out &out, unsigned stages, int reset_all, cudaStream_t s) {
     const int n = ctx->n;
     Pool pool = make_pool(ctx);
     EnvState st = make_state(ctx);
     Tables tb = make_tables(ctx);
+    prof_mark(ctx, 0, s);
     k_advance<<<(n + ADV_THREADS - 1) / ADV_THREADS, ADV_THREADS, 0, s>>>(n, pool, st, d_action, ctx->par, out, reset_all);
+    prof_mark(ctx, 0, s);
     ctx->launches++;
     if (stages & HOPE_STAGE_OBSERVE) {
         const int wpb = OBS_THREADS / 32;
+        prof_mark(ctx, 1, s);
         k_observe<<<(n + wpb - 1) / wpb, OBS_THREADS, wpb * sizeof(ObserveSmem), s>>>(n, pool, st, tb, ctx->par, out);
+        prof_mark(ctx, 1, s);
         ctx->launches++;
     }
     if (stages & HOPE_STAGE_RS) {
         RsScratch rs = make_rs(ctx);
+        prof_mark(ctx, 2, s);
         k_rs_enumerate<<<(n + ENUM_THREADS - 1) / ENUM_THREADS, ENUM_THREADS, 0, s>>>(n, pool, st, tb, rs, out);
+        prof_mark(ctx, 2, s);
         const int wpb = CHK_THREADS / 32;
+        prof_mark(ctx, 3, s);
         k_rs_check<<<(n + wpb - 1) / wpb, CHK_THREADS, wpb * sizeof(CheckSmem), s>>>(n, pool, st, tb, rs, ctx->par, out);
+        prof_mark(ctx, 3, s);
         ctx->launches += 2;
     }
     CK(cudaGetLastError());
@@ -1266,6 +1284,31 @@ int hope_set_state(hope_ctx *ctx, const double *h_pose, const int32_t *h_t, cons
     if (h_t) CK(cudaMemcpy(ctx->d_t, h_t, sizeof(int) * ctx->n, cudaMemcpyHostToDevice));
     if (h_accum) CK(cudaMemcpy(ctx->d_accum, h_accum, sizeof(double) * ctx->n, cudaMemcpyHostToDevice));
     CK(cudaMemset(ctx->d_pending, 0, ctx->n));
+    return HOPE_OK;
+}
+
+int hope_profile_enable(hope_ctx *ctx, int on) {
+    if (!ctx) return HOPE_ERR_INVALID;
+    ctx->profile = on != 0;
+    return HOPE_OK;
+}
+
+int hope_profile_read(hope_ctx *ctx, double h_ms[4], uint64_t h_launches[4]) {
+    if (!ctx || !h_ms || !h_launches) return HOPE_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    for (int k = 0; k < 4; ++k) {
+        auto &ev = ctx->prof_events[k];
+        double total = 0.0;
+        for (size_t i = 0; i + 1 < ev.size(); i += 2) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ev[i], ev[i + 1]) == cudaSuccess) total += ms;
+        }
+        h_ms[k] = total;
+        h_launches[k] = ev.size() / 2;
+        for (cudaEvent_t e : ev) cudaEventDestroy(e);
+        ev.clear();
+    }
     return HOPE_OK;
 }
 

@@ -151,6 +151,12 @@ int hope_set_state(hope_ctx *ctx, const double *h_pose, const int32_t *h_t, cons
  * fallbacks taken, [3] RS word-capacity overflows, [4] RS zero-length words (reference asserts),
  * [5] kernels launched by this context */
 int hope_get_counters(hope_ctx *ctx, uint64_t h_counters[8]);
+/* Per-kernel device timing: when enabled every kernel launch of a step is bracketed by CUDA
+ * events on the launch stream.  hope_profile_read synchronises, returns the accumulated
+ * milliseconds and launch counts per kernel [0] advance [1] observe [2] rs_enumerate
+ * [3] rs_check since the last read, and clears them. */
+int hope_profile_enable(hope_ctx *ctx, int on);
+int hope_profile_read(hope_ctx *ctx, double h_ms[4], uint64_t h_launches[4]);
 int hope_n_envs(const hope_ctx *ctx);
 int hope_version(void);
 
