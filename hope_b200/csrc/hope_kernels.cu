@@ -34,7 +34,6 @@ constexpr int NITER = HOPE_N_MASK_ITER;
 constexpr int NUP = HOPE_N_UPSAMPLE;
 constexpr int META = 24;       // doubles of per-scene metadata
 constexpr int MAXW = 16;       // admitted Reeds-Shepp words kept per env
-constexpr int PD_CAP = 512;    // samples staged per block of a word in k_rs_check
 
 // per-scene metadata layout (doubles)
 enum { M_START = 0, M_DEST = 3, M_BOUNDS = 6, M_DBX = 10, M_DBY = 14, M_DAREA = 18, M_DNORM = 19, M_DAABB = 20 };
@@ -698,13 +697,186 @@ __global__ void __launch_bounds__(128) k_rs_enumerate(int n, Pool pool, EnvState
 // =============================================================================================
 // k_rs_check: one warp per env.  Sample each word of the try list every rs_step metres and test
 // the swept vehicle boxes against map bounds and obstacle edges; the first clean word wins.
+//
+// The sample positions of a word come from a float accumulation (`pd += d`, reeds_shepp.py:488-492)
+// that has to be replayed add by add to reproduce the reference's sample set.  Replaying it in
+// one lane per sample step would serialise the warp, so the work is split:
+//   walk phase    lane w replays the chain of word w of the current batch (up to RS_WB words side by
+//                 side) and saves its state every RS_STRIDE samples;
+//   sample phase  for one word at a time, lane j resumes from saved state j and evaluates its own
+//                 RS_STRIDE consecutive samples (pose, swept box, bounds, obstacle edges).
 // =============================================================================================
-struct CheckSmem {
-    double pd[PD_CAP];   // arc parameter of each staged sample (normalised units)
-    uint8_t seg[PD_CAP]; // segment index; 0xFE = path origin, 0xFF = final end point
+constexpr int RS_WB = 8;                        // words walked side by side
+constexpr int RS_STRIDE = 8;                    // samples per lane in one chunk
+constexpr int RS_CHUNK = 32 * RS_STRIDE;        // samples covered by one set of saved states
+constexpr uint8_t RS_ORIGIN = 0xFE, RS_END = 0x80, RS_DONE = 0xFF;
+
+struct WordSlot {
+    double len[HOPE_RS_MAX_SEG];                // normalised signed segment lengths
+    double org[HOPE_RS_MAX_SEG][5];             // per segment: ox, oy, oyaw, cos(oyaw), sin(oyaw) (local frame)
+    double st_pd[32];                           // saved walker state at sample RS_STRIDE*j of the chunk
+    double end_lx;                              // local x of the final end point (trailing-zero rule)
+    uint8_t st_code[32];
+    uint32_t types;                             // 4 bits per segment
+    int n;                                      // segments
+    int total;                                  // samples in the word if the walk reached the end, else -1
+    uint8_t resume_code; double resume_pd;      // walker state at the start of the next chunk
+};
+struct CheckSmem { WordSlot slot[RS_WB]; };
+
+// One step of generate_local_course's sample sequence (:452-507).  (code, pd) is the sample just
+// emitted; on return it is the next one.  code: RS_ORIGIN = path start, seg index = loop sample of
+// that segment at arc parameter pd, RS_END|seg = the final end point, RS_DONE = no more samples.
+__device__ __forceinline__ void walker_next(const WordSlot &w, double step, uint8_t &code, double &pd) {
+    int seg;
+    double d;
+    if (code == RS_ORIGIN) {
+        seg = 0;
+        d = w.len[0] > 0.0 ? step : -step;
+        pd = d - 0.0;                                   // pd = d - ll with ll = 0.0 (:471-472, :486)
+    } else if (code & RS_END) {
+        code = RS_DONE;
+        return;
+    } else {
+        seg = code;
+        d = w.len[seg] > 0.0 ? step : -step;
+        pd += d;                                        // :492
+    }
+    for (;;) {
+        double l = w.len[seg];
+        if (fabs(pd) <= fabs(l)) { code = (uint8_t)seg; return; }   // :488
+        if (seg + 1 == w.n) { code = (uint8_t)(RS_END | seg); pd = l; return; }  // :496-498
+        double ll = l - pd - d;                         // :494
+        double ln = w.len[seg + 1];
+        d = ln > 0.0 ? step : -step;                    // :475-478
+        pd = (l * ln > 0) ? -d - ll : d - ll;           // :483-486
+        ++seg;
+    }
+}
+
+// interpolate (:510-537) from a segment origin; returns the local-frame pose of the sample.
+__device__ __forceinline__ void rs_interp(double p, int m, double maxc, const double *org, double &lx, double &ly, double &lyaw) {
+    if (m == HOPE_RS_S) {
+        lx = org[0] + p / maxc * org[3];
+        ly = org[1] + p / maxc * org[4];
+        lyaw = org[2];
+    } else {
+        double sl, cl;
+        sincos(p, &sl, &cl);
+        double ldx = sl / maxc, ldy = (1.0 - cl) / (m == HOPE_RS_L ? maxc : -maxc);
+        double cy_ = org[3], sy_ = -org[4];             // cos(-oyaw), sin(-oyaw)
+        double gdx = cy_ * ldx + sy_ * ldy, gdy = -sy_ * ldx + cy_ * ldy;
+        lx = org[0] + gdx; ly = org[1] + gdy;
+        lyaw = (m == HOPE_RS_L) ? org[2] + p : org[2] - p;
+    }
+}
+
+// Evaluate the up-to RS_STRIDE samples lane `lane` owns in the current chunk of word slot `s`.
+// Returns true (warp-uniform) if any sample leaves the map or touches an obstacle edge.
+struct CheckEnv {
+    double q0x, q0y, q0h, cg, sg, xmin, xmax, ymin, ymax, maxc, step;
+    const double4 *aabb; const double2 *verts; const uint8_t *nvp; int nobs;
 };
 
-__global__ void __launch_bounds__(256) k_rs_check(int n, Pool pool, EnvState st, Tables tb, RsScratch rs, hope_params par, hope_out out) {
+__device__ __forceinline__ bool sample_hits(const CheckEnv &E, const hope_params &par, double lx, double ly, double lyaw) {
+    double gx = E.cg * lx + E.sg * ly + E.q0x, gy = -E.sg * lx + E.cg * ly + E.q0y;  // reeds_shepp.py:47-48
+    double gyaw = pi_2_pi(lyaw + E.q0h);                                             // :49
+    if (gx < E.xmin || gx > E.xmax || gy < E.ymin || gy > E.ymax) return true;       // car_parking_base.py:462-464
+    double cth, sth, bx[4], by[4];
+    sincos(gyaw, &sth, &cth);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {  // :468-471
+        bx[q] = cth * par.box_x[q] - sth * par.box_y[q] + gx;
+        by[q] = sth * par.box_x[q] + cth * par.box_y[q] + gy;
+    }
+    const double vxmin = fmin(fmin(bx[0], bx[1]), fmin(bx[2], bx[3])), vxmax = fmax(fmax(bx[0], bx[1]), fmax(bx[2], bx[3]));
+    const double vymin = fmin(fmin(by[0], by[1]), fmin(by[2], by[3])), vymax = fmax(fmax(by[0], by[1]), fmax(by[2], by[3]));
+    for (int ob = 0; ob < E.nobs; ++ob) {
+        double4 bb = ld_aabb(E.aabb + ob);
+        // a hit needs rx inside both segments' x-ranges and ry inside both y-ranges (:518-526): disjoint
+        // boxes cannot produce one, so these rejects are exact
+        if (vxmax < bb.x || bb.y < vxmin || vymax < bb.z || bb.w < vymin) continue;
+        const int nv = E.nvp[ob];
+        double2 p1 = __ldg(E.verts + ob * MAXV);
+        for (int j = 0; j < nv; ++j) {
+            double2 p2 = __ldg(E.verts + ob * MAXV + ((j + 1 == nv) ? 0 : j + 1));
+            const double oxmax = fmax(p1.x, p2.x), oxmin = fmin(p1.x, p2.x), oymax = fmax(p1.y, p2.y), oymin = fmin(p1.y, p2.y);
+            if (!(vxmax < oxmin || oxmax < vxmin || vymax < oymin || oymax < vymin)) {
+                const double dd = p2.y - p1.y, ee = p1.x - p2.x, ff = p1.y * p2.x - p1.x * p2.y;  // :504-506
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int q2 = (q + 1) & 3;
+                    const double vx1 = bx[q], vy1 = by[q], vx2 = bx[q2], vy2 = by[q2];
+                    const double exmax = fmax(vx1, vx2), exmin = fmin(vx1, vx2), eymax = fmax(vy1, vy2), eymin = fmin(vy1, vy2);
+                    if (exmax < oxmin || oxmax < exmin || eymax < oymin || oymax < eymin) continue;
+                    const double a = vy2 - vy1, b = vx1 - vx2, c = vy1 * vx2 - vx1 * vy2;  // :477-479
+                    const double det = a * ee - b * dd;                                    // :509
+                    if (det == 0.0) continue;
+                    const double rx = (b * ff - c * ee) / det, ry = (c * dd - a * ff) / det;  // :512-513
+                    const bool okx = !(rx > oxmax) && !(rx < oxmin) && !(rx > exmax) && !(rx < exmin);
+                    const bool oky = !(ry > oymax) && !(ry < oymin) && !(ry > eymax) && !(ry < eymin);
+                    if (okx && oky) return true;
+                }
+            }
+            p1 = p2;
+        }
+    }
+    return false;
+}
+
+__device__ bool chunk_is_bad(const WordSlot &s, const CheckEnv &E, const hope_params &par, int lane) {
+    uint8_t code = s.st_code[lane];
+    double pd = s.st_pd[lane];
+    // Trailing samples whose local x is exactly 0.0 are dropped by the reference (:501-505).  That can
+    // only remove anything if the final end point itself has x == 0.0 (zero_tail), a degenerate goal.
+    const bool zero_tail = s.end_lx == 0.0;
+    unsigned zero_hits = 0, nonzero_bits = 0;
+    for (int r = 0; r < RS_STRIDE; ++r) {
+        bool hit = false;
+        if (code != RS_DONE) {
+            double lx = 0.0, ly = 0.0, lyaw = 0.0;
+            if (code != RS_ORIGIN) {
+                const int sgi = code & 0x7F;
+                rs_interp(pd, (int)((s.types >> (4 * sgi)) & 0xF), E.maxc, s.org[sgi], lx, ly, lyaw);
+            }
+            hit = sample_hits(E, par, lx, ly, lyaw);
+            if (zero_tail) {
+                if (lx != 0.0) nonzero_bits |= 1u << r;
+                else if (hit) { zero_hits |= 1u << r; hit = false; }
+            }
+            walker_next(s, E.step, code, pd);
+        }
+        if (__any_sync(HOPE_FULL_MASK, hit)) return true;
+    }
+    if (zero_tail) {  // lanes own consecutive sample ranges: scan from the last sample backwards
+        bool nz_after = false, bad = false;
+        for (int l2 = 31; l2 >= 0; --l2) {
+            const unsigned nzb = __shfl_sync(HOPE_FULL_MASK, nonzero_bits, l2), zhb = __shfl_sync(HOPE_FULL_MASK, zero_hits, l2);
+            for (int r = RS_STRIDE - 1; r >= 0; --r) {
+                if (((zhb >> r) & 1) && nz_after) bad = true;
+                if ((nzb >> r) & 1) nz_after = true;
+            }
+        }
+        return bad;
+    }
+    return false;
+}
+
+// lane-private: replay up to RS_CHUNK samples of this slot's chain, saving a state every RS_STRIDE
+__device__ void walk_chunk(WordSlot &s, double step, int chunk_base) {
+    uint8_t code = s.resume_code;
+    double pd = s.resume_pd;
+    int k = 0;
+    for (; k < RS_CHUNK && code != RS_DONE; ++k) {
+        if ((k & (RS_STRIDE - 1)) == 0) { s.st_code[k / RS_STRIDE] = code; s.st_pd[k / RS_STRIDE] = pd; }
+        walker_next(s, step, code, pd);
+    }
+    for (int j = (k + RS_STRIDE - 1) / RS_STRIDE; j < 32; ++j) s.st_code[j] = RS_DONE;
+    s.resume_code = code; s.resume_pd = pd;
+    s.total = (code == RS_DONE) ? chunk_base + k : -1;
+}
+
+__global__ void __launch_bounds__(128, 4) k_rs_check(int n, Pool pool, EnvState st, Tables tb, RsScratch rs, hope_params par, hope_out out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int env = blockIdx.x * (blockDim.x >> 5) + warp_in_block;
@@ -713,155 +885,57 @@ __global__ void __launch_bounds__(256) k_rs_check(int n, Pool pool, EnvState st,
     if (ntry == 0) return;  // outputs already cleared by k_rs_enumerate (gate closed or no word)
     CheckSmem &sm = reinterpret_cast<CheckSmem *>(smem_raw)[warp_in_block];
     const int sid = st.scene[env];
-    const double q0x = st.pose[3 * env], q0y = st.pose[3 * env + 1], q0h = st.pose[3 * env + 2];
     const double *meta = pool.meta + (size_t)sid * META;
-    const double xmin = meta[M_BOUNDS], xmax = meta[M_BOUNDS + 1], ymin = meta[M_BOUNDS + 2], ymax = meta[M_BOUNDS + 3];
-    const int nobs = pool.nobs[sid];
-    const double4 *aabb = reinterpret_cast<const double4 *>(pool.aabb) + (size_t)sid * MAXO;
-    const double2 *verts = reinterpret_cast<const double2 *>(pool.obs) + (size_t)sid * MAXE;
-    const uint8_t *nvp = pool.nv + (size_t)sid * MAXO;
-    double sg, cg;
-    sincos(-q0h, &sg, &cg);  // reeds_shepp.py:47-48
-    const double maxc = tb.maxc, step = par.rs_step * maxc;
+    CheckEnv E;
+    E.q0x = st.pose[3 * env]; E.q0y = st.pose[3 * env + 1]; E.q0h = st.pose[3 * env + 2];
+    sincos(-E.q0h, &E.sg, &E.cg);  // reeds_shepp.py:47-48
+    E.xmin = meta[M_BOUNDS]; E.xmax = meta[M_BOUNDS + 1]; E.ymin = meta[M_BOUNDS + 2]; E.ymax = meta[M_BOUNDS + 3];
+    E.maxc = tb.maxc; E.step = par.rs_step * tb.maxc;
+    E.nobs = pool.nobs[sid];
+    E.aabb = reinterpret_cast<const double4 *>(pool.aabb) + (size_t)sid * MAXO;
+    E.verts = reinterpret_cast<const double2 *>(pool.obs) + (size_t)sid * MAXE;
+    E.nvp = pool.nv + (size_t)sid * MAXO;
 
     int found = -1, tried = 0;
-    for (int wi = 0; wi < ntry && found < 0; ++wi) {
-        const RsWord w = rs.words[(size_t)env * MAXW + wi];
-        ++tried;
-        // walker state, identical in every lane (generate_local_course :452-507)
-        int seg = 0;
-        double ox = 0.0, oy = 0.0, oyaw = 0.0;       // origin of the current segment (local frame)
-        double so[HOPE_RS_MAX_SEG][3];               // per-segment origins for the sample phase
-        double d = w.len[0] > 0.0 ? step : -step;
-        double pd = d, ll = 0.0;
-        bool origin_pending = true, finished = false, bad = false, pending_bad = false;
-        so[0][0] = so[0][1] = so[0][2] = 0.0;
-        while (!finished && !bad) {
-            // ---- phase 1: stage up to PD_CAP samples (sequential float accumulation of pd) ---------
-            int cnt = 0;
-            if (origin_pending) { if (lane == 0) { sm.pd[0] = 0.0; sm.seg[0] = 0xFE; } cnt = 1; origin_pending = false; }
-            while (cnt < PD_CAP && !finished) {
-                double l = w.len[seg];
-                if (fabs(pd) <= fabs(l)) {  // :488-492
-                    if (lane == 0) { sm.pd[cnt] = pd; sm.seg[cnt] = (uint8_t)seg; }
-                    ++cnt;
-                    pd += d;
-                } else {
-                    ll = l - pd - d;  // :494
-                    if (seg + 1 == w.n) {  // the last segment's end point is the final sample (:496-498)
-                        if (lane == 0) { sm.pd[cnt] = l; sm.seg[cnt] = (uint8_t)(0x80 | seg); }
-                        ++cnt;
-                        finished = true;
-                    } else {
-                        // origin of the next segment = end point of this one (interpolate :510-537)
-                        int m = w.types[seg];
-                        if (m == HOPE_RS_S) {
-                            ox = ox + l / maxc * cos(oyaw);
-                            oy = oy + l / maxc * sin(oyaw);
-                        } else {
-                            double sl, cl, sy_, cy_;
-                            sincos(l, &sl, &cl);
-                            sincos(-oyaw, &sy_, &cy_);
-                            double ldx = sl / maxc, ldy = (1.0 - cl) / (m == HOPE_RS_L ? maxc : -maxc);
-                            double gdx = cy_ * ldx + sy_ * ldy, gdy = -sy_ * ldx + cy_ * ldy;
-                            ox = ox + gdx; oy = oy + gdy;
-                            oyaw = (m == HOPE_RS_L) ? oyaw + l : oyaw - l;
-                        }
-                        ++seg;
-                        so[seg][0] = ox; so[seg][1] = oy; so[seg][2] = oyaw;
-                        double ln = w.len[seg];
-                        d = ln > 0.0 ? step : -step;                          // :475-478
-                        pd = (w.len[seg - 1] * ln > 0) ? -d - ll : d - ll;    // :483-486
-                    }
-                }
+    for (int batch = 0; batch < ntry && found < 0; batch += RS_WB) {
+        const int nb = min(RS_WB, ntry - batch);
+        // ---- lane w = word (batch + w): lengths, segment origins, first chunk of the chain ------------
+        if (lane < nb) {
+            const RsWord w = rs.words[(size_t)env * MAXW + batch + lane];
+            WordSlot &s = sm.slot[lane];
+            uint32_t ty = 0;
+            for (int k = 0; k < HOPE_RS_MAX_SEG; ++k) { s.len[k] = w.len[k]; ty |= (uint32_t)(w.types[k] & 0xF) << (4 * k); }
+            s.types = ty; s.n = w.n;
+            double org[5] = {0.0, 0.0, 0.0, 1.0, 0.0};
+            for (int k = 0; k < w.n; ++k) {
+                for (int q = 0; q < 5; ++q) s.org[k][q] = org[q];
+                double ex, ey, eyaw;
+                rs_interp(w.len[k], w.types[k], E.maxc, org, ex, ey, eyaw);  // end of segment k = origin of k+1
+                org[0] = ex; org[1] = ey;
+                if (eyaw != org[2]) { org[2] = eyaw; sincos(eyaw, &org[4], &org[3]); }
             }
-            __syncwarp();
-            // ---- phase 2: every lane evaluates samples lane, lane+32, ... of the staged block -------
-            for (int base = 0; base < cnt && !bad; base += 32) {
-                int k = base + lane;
-                bool have = k < cnt;
-                bool hit = false, nonzero = false;
-                if (have) {
-                    uint8_t sc = sm.seg[k];
-                    double lx, ly, lyaw;
-                    if (sc == 0xFE) { lx = 0.0; ly = 0.0; lyaw = 0.0; }
-                    else {
-                        int sgi = sc & 0x7F;
-                        double p = sm.pd[k];
-                        double bx0 = so[0][0], by0 = so[0][1], bw0 = so[0][2];
-#pragma unroll
-                        for (int q = 1; q < HOPE_RS_MAX_SEG; ++q) if (q == sgi) { bx0 = so[q][0]; by0 = so[q][1]; bw0 = so[q][2]; }
-                        int m = w.types[sgi];
-                        if (m == HOPE_RS_S) {
-                            lx = bx0 + p / maxc * cos(bw0);
-                            ly = by0 + p / maxc * sin(bw0);
-                            lyaw = bw0;
-                        } else {
-                            double sl, cl, sy_, cy_;
-                            sincos(p, &sl, &cl);
-                            sincos(-bw0, &sy_, &cy_);
-                            double ldx = sl / maxc, ldy = (1.0 - cl) / (m == HOPE_RS_L ? maxc : -maxc);
-                            double gdx = cy_ * ldx + sy_ * ldy, gdy = -sy_ * ldx + cy_ * ldy;
-                            lx = bx0 + gdx; ly = by0 + gdy;
-                            lyaw = (m == HOPE_RS_L) ? bw0 + p : bw0 - p;
-                        }
-                    }
-                    nonzero = lx != 0.0;  // trailing samples with x == 0.0 are dropped (:501-505)
-                    double gx = cg * lx + sg * ly + q0x, gy = -sg * lx + cg * ly + q0y;  // :47-48
-                    double gyaw = pi_2_pi(lyaw + q0h);                                   // :49
-                    if (gx < xmin || gx > xmax || gy < ymin || gy > ymax) hit = true;    // car_parking_base.py:462-464
-                    else {
-                        double cth, sth, bx[4], by[4];
-                        sincos(gyaw, &sth, &cth);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {  // :468-471
-                            bx[q] = cth * par.box_x[q] - sth * par.box_y[q] + gx;
-                            by[q] = sth * par.box_x[q] + cth * par.box_y[q] + gy;
-                        }
-                        double vxmin = fmin(fmin(bx[0], bx[1]), fmin(bx[2], bx[3])), vxmax = fmax(fmax(bx[0], bx[1]), fmax(bx[2], bx[3]));
-                        double vymin = fmin(fmin(by[0], by[1]), fmin(by[2], by[3])), vymax = fmax(fmax(by[0], by[1]), fmax(by[2], by[3]));
-                        for (int ob = 0; ob < nobs && !hit; ++ob) {
-                            double4 bb = ld_aabb(aabb + ob);
-                            // a hit needs rx inside both segments' x-ranges and ry inside both y-ranges (:518-526):
-                            // disjoint boxes cannot produce one, so this reject is exact
-                            if (vxmax < bb.x || bb.y < vxmin || vymax < bb.z || bb.w < vymin) continue;
-                            int nv = nvp[ob];
-                            double2 p1 = __ldg(verts + ob * MAXV);
-                            for (int j = 0; j < nv && !hit; ++j) {
-                                double2 p2 = __ldg(verts + ob * MAXV + ((j + 1 == nv) ? 0 : j + 1));
-                                double dd = p2.y - p1.y, ee = p1.x - p2.x, ff = p1.y * p2.x - p1.x * p2.y;  // :504-506
-                                double oxmax = fmax(p1.x, p2.x), oxmin = fmin(p1.x, p2.x), oymax = fmax(p1.y, p2.y), oymin = fmin(p1.y, p2.y);
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    int q2 = (q + 1) & 3;
-                                    double vx1 = bx[q], vy1 = by[q], vx2 = bx[q2], vy2 = by[q2];
-                                    double exmax = fmax(vx1, vx2), exmin = fmin(vx1, vx2), eymax = fmax(vy1, vy2), eymin = fmin(vy1, vy2);
-                                    if (exmax < oxmin || oxmax < exmin || eymax < oymin || oymax < eymin) continue;
-                                    double a = vy2 - vy1, b = vx1 - vx2, c = vy1 * vx2 - vx1 * vy2;  // :477-479
-                                    double det = a * ee - b * dd;                                    // :509
-                                    if (det == 0.0) continue;
-                                    double rx = (b * ff - c * ee) / det, ry = (c * dd - a * ff) / det;  // :512-513
-                                    bool okx = !(rx > oxmax) && !(rx < oxmin) && !(rx > exmax) && !(rx < exmin);
-                                    bool oky = !(ry > oymax) && !(ry < oymin) && !(ry > eymax) && !(ry < eymin);
-                                    if (okx && oky) hit = true;
-                                }
-                                p1 = p2;
-                            }
-                        }
-                    }
-                }
-                unsigned mh = __ballot_sync(HOPE_FULL_MASK, hit), mz = __ballot_sync(HOPE_FULL_MASK, nonzero);
-                if (mz) {
-                    if (pending_bad) bad = true;
-                    int top = 31 - __clz(mz);
-                    unsigned commit = (top == 31) ? 0xffffffffu : ((1u << (top + 1)) - 1);
-                    if (mh & commit) bad = true;
-                    pending_bad = (mh & ~commit) != 0;
-                } else if (mh) pending_bad = true;
-            }
-            __syncwarp();
+            s.end_lx = org[0];
+            s.resume_code = RS_ORIGIN; s.resume_pd = 0.0;
+            walk_chunk(s, E.step, 0);
         }
-        if (!bad) found = wi;
+        __syncwarp();
+        // ---- words in try order; the whole warp samples one word at a time ----------------------------
+        for (int wl = 0; wl < nb && found < 0; ++wl) {
+            WordSlot &s = sm.slot[wl];
+            ++tried;
+            bool bad = false;
+            int chunk_base = 0;
+            for (;;) {
+                bad = chunk_is_bad(s, E, par, lane);
+                if (bad || s.total >= 0) break;
+                chunk_base += RS_CHUNK;  // a word longer than one chunk: its owner lane walks on
+                __syncwarp();
+                if (lane == wl) walk_chunk(s, E.step, chunk_base);
+                __syncwarp();
+            }
+            if (!bad) found = batch + wl;
+        }
+        __syncwarp();
     }
     if (lane == 0) {
         if (out.rs_ntried) out.rs_ntried[env] = (uint8_t)tried;
@@ -869,10 +943,10 @@ __global__ void __launch_bounds__(256) k_rs_check(int n, Pool pool, EnvState st,
             const RsWord w = rs.words[(size_t)env * MAXW + found];
             if (out.rs_found) out.rs_found[env] = 1;
             if (out.rs_nseg) out.rs_nseg[env] = w.n;
-            if (out.rs_L) out.rs_L[env] = w.L / maxc;
+            if (out.rs_L) out.rs_L[env] = w.L / E.maxc;
             for (int k = 0; k < 5; ++k) {
                 if (out.rs_types) out.rs_types[5 * env + k] = k < w.n ? w.types[k] : HOPE_RS_NONE;
-                if (out.rs_lengths) out.rs_lengths[5 * env + k] = k < w.n ? w.len[k] / maxc : 0.0;  // reeds_shepp.py:51
+                if (out.rs_lengths) out.rs_lengths[5 * env + k] = k < w.n ? w.len[k] / E.maxc : 0.0;  // reeds_shepp.py:51
             }
         }
     }
@@ -961,7 +1035,7 @@ Tables make_tables(const hope_ctx *c) {
 }
 RsScratch make_rs(const hope_ctx *c) { return RsScratch{c->d_words, c->d_ntry, c->d_ncand}; }
 
-constexpr int ADV_THREADS = 128, OBS_THREADS = 256, ENUM_THREADS = 128, CHK_THREADS = 256;
+constexpr int ADV_THREADS = 128, OBS_THREADS = 256, ENUM_THREADS = 128, CHK_THREADS = 128;
 
 void prof_mark(hope_ctx *ctx, int which, cudaStream_t s) {
     if (!ctx->profile) return;
