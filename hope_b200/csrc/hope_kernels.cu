@@ -49,13 +49,14 @@ struct Pool {
 struct Tables {
     const double *ray_a, *ray_b, *lidar_base, *mask_base;
     const double *dist_star;  // [1200][42][10]
-    const double *pend;       // [1200][42]   max_k dist_star
+    const double *pmaxk;      // [1200][10][42] running max over k of dist_star, action index contiguous
     const double *pmax;       // [1200]       max_{j,k} dist_star
     const double *w_lo, *w_hi;
     double maxc;
 };
 struct EnvState {
     double *pose;     // [N][3]
+    double *cs;       // [N][2] cos, sin of the heading (k_advance -> k_observe)
     int *t;           // [N]
     double *accum;    // [N]
     int *scene;       // [N]
@@ -83,31 +84,69 @@ __device__ __forceinline__ double4 ld_aabb(const double4 *p) {  // read-only pat
 }
 
 // =============================================================================================
-// k_advance: one thread per env.
+// k_advance: one thread per env for the sequential part (pose integration, status, reward); the
+// ring-vs-ring collision tests of a warp's 32 envs are pooled and spread over all 32 lanes.
 // =============================================================================================
-__device__ __forceinline__ bool box_collides(const double *bx, const double *by, const Pool &pool, int sid,
-                                             unsigned long long *fc) {
-    double vxmin = fmin(fmin(bx[0], bx[1]), fmin(bx[2], bx[3])), vxmax = fmax(fmax(bx[0], bx[1]), fmax(bx[2], bx[3]));
-    double vymin = fmin(fmin(by[0], by[1]), fmin(by[2], by[3])), vymax = fmax(fmax(by[0], by[1]), fmax(by[2], by[3]));
-    int no = pool.nobs[sid];
-    const double4 *aabb = reinterpret_cast<const double4 *>(pool.aabb) + (size_t)sid * MAXO;
-    for (int k = 0; k < no; ++k) {
-        double4 bb = ld_aabb(aabb + k);  // xmin xmax ymin ymax
-        if (vxmax < bb.x || bb.y < vxmin || vymax < bb.z || bb.w < vymin) continue;  // exact reject
-        int nv = pool.nv[(size_t)sid * MAXO + k];
-        const double2 *v = reinterpret_cast<const double2 *>(pool.obs) + ((size_t)sid * MAXO + k) * MAXV;
-        double2 p = __ldg(v);
-        for (int j = 0; j < nv; ++j) {
-            double2 q = __ldg(v + ((j + 1 == nv) ? 0 : j + 1));
+struct AdvanceSmem {           // per warp
+    double bx[32][4], by[32][4];   // current vehicle box of each lane's env
+    int sid[32];
+    uint16_t queue[32 * MAXO];     // (lane << 4) | obstacle of every vehicle-AABB / obstacle-AABB overlap
+};
+
+// Per-lane result: does lane's vehicle ring touch any obstacle ring of its scene
+// (car_parking_base.py:153-158)?  `check` selects the lanes that ask.  Phase 1: every asking lane
+// walks its obstacle AABBs (exact reject) and enqueues the overlaps.  Phase 2: the warp drains the
+// queue two items at a time, 16 lanes per item = 4 vehicle edges x up to 4 obstacle edges, one
+// robust segment-pair test per lane.
+__device__ __forceinline__ unsigned warp_collisions(bool check, const double *bx, const double *by, int sid, int nobs,
+                                                    const Pool &pool, AdvanceSmem &sm, int lane, unsigned long long *fc) {
+    if (!__any_sync(HOPE_FULL_MASK, check)) return 0u;
+    __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                int i2 = (i + 1) & 3;
-                if (segments_touch(bx[i], by[i], bx[i2], by[i2], p.x, p.y, q.x, q.y, fc)) return true;
-            }
-            p = q;
+    for (int i = 0; i < 4; ++i) { sm.bx[lane][i] = bx[i]; sm.by[lane][i] = by[i]; }
+    sm.sid[lane] = sid;
+    const double vxmin = fmin(fmin(bx[0], bx[1]), fmin(bx[2], bx[3])), vxmax = fmax(fmax(bx[0], bx[1]), fmax(bx[2], bx[3]));
+    const double vymin = fmin(fmin(by[0], by[1]), fmin(by[2], by[3])), vymax = fmax(fmax(by[0], by[1]), fmax(by[2], by[3]));
+    int maxn = check ? nobs : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxn = max(maxn, __shfl_xor_sync(HOPE_FULL_MASK, maxn, o));
+    const double4 *aabb = reinterpret_cast<const double4 *>(pool.aabb) + (size_t)sid * MAXO;
+    int qn = 0;
+    for (int k = 0; k < maxn; ++k) {
+        bool over = false;
+        if (check && k < nobs) {
+            double4 bb = ld_aabb(aabb + k);  // xmin xmax ymin ymax
+            over = !(vxmax < bb.x || bb.y < vxmin || vymax < bb.z || bb.w < vymin);  // disjoint boxes: exact reject
         }
+        unsigned m = __ballot_sync(HOPE_FULL_MASK, over);
+        if (over) sm.queue[qn + __popc(m & ((1u << lane) - 1))] = (uint16_t)((lane << 4) | k);
+        qn += __popc(m);
     }
-    return false;
+    __syncwarp();
+    unsigned collided = 0;
+    const int half = lane >> 4, pair = lane & 15, vi = pair & 3, oj = pair >> 2;
+    for (int base = 0; base < qn; base += 2) {
+        const int item = base + half;
+        bool hit = false;
+        if (item < qn) {
+            const int code = sm.queue[item], owner = code >> 4, k = code & 15;
+            if (!((collided >> owner) & 1)) {
+                const int osid = sm.sid[owner];
+                const int nv = pool.nv[(size_t)osid * MAXO + k];
+                if (oj < nv) {
+                    const double2 *v = reinterpret_cast<const double2 *>(pool.obs) + ((size_t)osid * MAXO + k) * MAXV;
+                    const double2 p = __ldg(v + oj), q = __ldg(v + ((oj + 1 == nv) ? 0 : oj + 1));
+                    const int vi2 = (vi + 1) & 3;
+                    hit = segments_touch(sm.bx[owner][vi], sm.by[owner][vi], sm.bx[owner][vi2], sm.by[owner][vi2], p.x, p.y, q.x, q.y, fc);
+                }
+            }
+        }
+        const unsigned m = __ballot_sync(HOPE_FULL_MASK, hit);
+        if (m & 0xffffu) collided |= 1u << (sm.queue[base] >> 4);
+        if ((m >> 16) && base + 1 < qn) collided |= 1u << (sm.queue[base + 1] >> 4);
+    }
+    __syncwarp();
+    return collided;
 }
 
 __device__ __forceinline__ double angle_gap(double a1, double a2) {  // car_parking_base.py:203-206
@@ -117,17 +156,22 @@ __device__ __forceinline__ double angle_gap(double a1, double a2) {  // car_park
 
 __global__ void __launch_bounds__(128) k_advance(int n, Pool pool, EnvState st, const double *__restrict__ action,
                                                  hope_params par, hope_out out, int reset_all) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    __shared__ AdvanceSmem smem[4];
+    const int lane = threadIdx.x & 31;
+    AdvanceSmem &sm = smem[threadIdx.x >> 5];
+    const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = gi < n;
+    const int i = valid ? gi : n - 1;  // tail lanes shadow the last env (no stores) so warp collectives stay full
     unsigned long long *fc = st.counters + 2;
     int sid = st.scene[i];
-    bool pending = st.pending[i] != 0;
-    bool is_reset = reset_all || pending || action == nullptr;
+    const bool pending = st.pending[i] != 0;
+    const bool is_reset = reset_all || pending || action == nullptr;
     if (pending && !reset_all) {  // auto-reset: next scene of the pool for this slot
         sid = (sid + n) % pool.size;
-        st.scene[i] = sid;
+        if (valid) st.scene[i] = sid;
     }
     const double *meta = pool.meta + (size_t)sid * META;
+    const int nobs = pool.nobs[sid];
     double x, y, h, accum;
     int t;
     if (reset_all || pending) {
@@ -143,45 +187,56 @@ __global__ void __launch_bounds__(128) k_advance(int n, Pool pool, EnvState st, 
     for (int k = 0; k < 4; ++k) { dbx[k] = meta[M_DBX + k]; dby[k] = meta[M_DBY + k]; }
     const double dest_area = meta[M_DAREA];
     const double daxmin = meta[M_DAABB], daxmax = meta[M_DAABB + 1], daymin = meta[M_DAABB + 2], daymax = meta[M_DAABB + 3];
+    // centre of the vehicle box in its own frame (mean of the two diagonal corners)
+    const double ccx = 0.5 * (par.box_x[0] + par.box_x[2]), ccy = 0.5 * (par.box_y[0] + par.box_y[2]);
 
     bool arrive = false;
     int nsub = 0, nret = 0;
-    double c = cos(h), s = sin(h);
-    if (!is_reset) {
+    double c, s;
+    sincos(h, &s, &c);
+    double v = 0.0, dh = 0.0, ds = 0.0, ratio = 0.0;
+    const int mi = par.mini_iter;
+    bool moving = !is_reset;
+    if (moving) {
         // env_wrapper.py:37-50: clip to [-1,1], a*(hi-lo)/2 + (hi+lo)/2 with float32-exact bounds
         double a0 = fmin(fmax(action[2 * i], -1.0), 1.0), a1 = fmin(fmax(action[2 * i + 1], -1.0), 1.0);
         double steer = a0 * ((par.valid_steer[1] - par.valid_steer[0]) / 2) + (par.valid_steer[1] + par.valid_steer[0]) / 2;
         double speed = a1 * ((par.valid_speed[1] - par.valid_speed[0]) / 2) + (par.valid_speed[1] + par.valid_speed[0]) / 2;
         // vehicle.py:83-84
-        double v = fmin(fmax(speed, par.valid_speed[0]), par.valid_speed[1]);
+        v = fmin(fmax(speed, par.valid_speed[0]), par.valid_speed[1]);
         double phi = fmin(fmax(steer, par.valid_steer[0]), par.valid_steer[1]);
         // vehicle.py:88-93, one mini-iteration: x += v cos(h) dt ; h += v tan(phi)/L dt   (dt = step_length/mini_iter)
-        const double dh = v * tan(phi) / par.wheel_base * par.step_length / par.mini_iter;
-        const double ds = v * par.step_length / par.mini_iter;
-        const int mi = par.mini_iter;
+        dh = v * tan(phi) / par.wheel_base * par.step_length / par.mini_iter;
+        ds = v * par.step_length / par.mini_iter;
         // closed form of the mini_iter explicit-Euler position sum: with h_k = h + k dh,
         //   sum_k cos(h_k) = sin(mi dh/2)/sin(dh/2) * cos(h + (mi-1) dh/2)
-        const double ratio = (dh == 0.0) ? (double)mi : sin(0.5 * mi * dh) / sin(0.5 * dh);
-        for (int sub = 0; sub < par.num_step; ++sub) {  // car_parking_base.py:259-271
-            double kx = x, ky = y, kh = h, kc = c, ks = s;
-            double sm, cm;
-            sincos(h + 0.5 * (mi - 1) * dh, &sm, &cm);
-            x = x + ds * (ratio * cm);
-            y = y + ds * (ratio * sm);
+        ratio = (dh == 0.0) ? (double)mi : sin(0.5 * mi * dh) / sin(0.5 * dh);
+    }
+    for (int sub = 0; sub < par.num_step; ++sub) {  // car_parking_base.py:259-271, lock-step across the warp
+        if (!__any_sync(HOPE_FULL_MASK, moving)) break;
+        double kx = x, ky = y, kh = h, kc = c, ks = s;
+        if (moving) {
+            double sm_, cm_;
+            sincos(h + 0.5 * (mi - 1) * dh, &sm_, &cm_);
+            x = x + ds * (ratio * cm_);
+            y = y + ds * (ratio * sm_);
             for (int q = 0; q < mi; ++q) h += dh;  // heading accumulates by repeated addition in the reference
             sincos(h, &s, &c);
             ++nsub;
             vehicle_box(x, y, c, s, par.box_x, par.box_y, bx, by);
-            double vxmin = fmin(fmin(bx[0], bx[1]), fmin(bx[2], bx[3])), vxmax = fmax(fmax(bx[0], bx[1]), fmax(bx[2], bx[3]));
-            double vymin = fmin(fmin(by[0], by[1]), fmin(by[2], by[3])), vymax = fmax(fmax(by[0], by[1]), fmax(by[2], by[3]));
-            if (!(vxmax < daxmin || daxmax < vxmin || vymax < daymin || daymax < vymin)) {
-                if (quad_clip_area(bx, by, dbx, dby) / dest_area > 0.95) { arrive = true; break; }  // :164-170
+            // arrival (:164-170) needs 95 % of the slot covered; a convex, centrally symmetric box whose centre
+            // lies outside the slot covers at most half of it, so the centre-in-slot-AABB test (with slack) is a
+            // safe necessary condition before paying for the polygon clip
+            double cx = c * ccx - s * ccy + x, cy = s * ccx + c * ccy + y;
+            if (cx >= daxmin - 1e-6 && cx <= daxmax + 1e-6 && cy >= daymin - 1e-6 && cy <= daymax + 1e-6) {
+                if (quad_clip_area(bx, by, dbx, dby) / dest_area > 0.95) { arrive = true; moving = false; }
             }
-            if (box_collides(bx, by, pool, sid, fc)) {  // :264-271 retreat one substep
-                x = kx; y = ky; h = kh; c = kc; s = ks;
-                ++nret;
-                break;
-            }
+        }
+        unsigned hitmask = warp_collisions(moving, bx, by, sid, nobs, pool, sm, lane, fc);
+        if (moving && ((hitmask >> lane) & 1)) {  // :264-271 retreat one substep
+            x = kx; y = ky; h = kh; c = kc; s = ks;
+            ++nret;
+            moving = false;
         }
     }
     t += 1;
@@ -193,9 +248,10 @@ __global__ void __launch_bounds__(128) k_advance(int n, Pool pool, EnvState st, 
         if (!(vxmax < daxmin || daxmax < vxmin || vymax < daymin || daymax < vymin)) inter = quad_clip_area(bx, by, dbx, dby);
     }
     const double xmin = meta[M_BOUNDS], xmax = meta[M_BOUNDS + 1], ymin = meta[M_BOUNDS + 2], ymax = meta[M_BOUNDS + 3];
+    const unsigned final_hits = warp_collisions(!arrive, bx, by, sid, nobs, pool, sm, lane, fc);
     int status;  // car_parking_base.py:279-282, 175-184
     if (arrive) status = HOPE_ARRIVED;
-    else if (box_collides(bx, by, pool, sid, fc)) status = HOPE_COLLIDED;
+    else if ((final_hits >> lane) & 1) status = HOPE_COLLIDED;
     else if (x > xmax || x < xmin || y > ymax || y < ymin) status = HOPE_OUTBOUND;
     else if (inter / dest_area > 0.95) status = HOPE_ARRIVED;
     else if (t > par.tolerant_time) status = HOPE_OUTTIME;
@@ -224,28 +280,39 @@ __global__ void __launch_bounds__(128) k_advance(int n, Pool pool, EnvState st, 
     else reward = -50.0;
     reward *= par.reward_ratio;
 
-    st.pose[3 * i] = x; st.pose[3 * i + 1] = y; st.pose[3 * i + 2] = h;
-    st.accum[i] = accum; st.t[i] = t;
-    bool done = status != HOPE_CONTINUE;
-    st.pending[i] = (done && par.auto_reset) ? 1 : 0;
-    st.gate[i] = (t > 1 && status == HOPE_CONTINUE && dist_now < par.rs_max_dist) ? 1 : 0;  // :293-294
-
-    if (out.pose) { out.pose[3 * i] = x; out.pose[3 * i + 1] = y; out.pose[3 * i + 2] = h; }
-    if (out.status) out.status[i] = status;
-    if (out.done) out.done[i] = done;
-    if (out.reward) out.reward[i] = reward;
-    if (out.reward_info) {
+    const bool done = status != HOPE_CONTINUE;
+    if (valid) {
+        st.pose[3 * i] = x; st.pose[3 * i + 1] = y; st.pose[3 * i + 2] = h;
+        st.cs[2 * i] = c; st.cs[2 * i + 1] = s;
+        st.accum[i] = accum; st.t[i] = t;
+        st.pending[i] = (done && par.auto_reset) ? 1 : 0;
+        st.gate[i] = (t > 1 && status == HOPE_CONTINUE && dist_now < par.rs_max_dist) ? 1 : 0;  // :293-294
+        if (out.pose) { out.pose[3 * i] = x; out.pose[3 * i + 1] = y; out.pose[3 * i + 2] = h; }
+        if (out.status) out.status[i] = status;
+        if (out.done) out.done[i] = done;
+        if (out.reward) out.reward[i] = reward;
+        if (out.reward_info) {
 #pragma unroll
-        for (int k = 0; k < 5; ++k) out.reward_info[5 * i + k] = ri[k];
+            for (int k = 0; k < 5; ++k) out.reward_info[5 * i + k] = ri[k];
+        }
+        if (out.substeps) out.substeps[i] = (uint8_t)nsub;
+        if (out.retreated) out.retreated[i] = (uint8_t)nret;
+        if (out.was_reset) out.was_reset[i] = is_reset;
+        if (out.target) {  // car_parking_base.py:372-381; element 4 repeats cos (sic)
+            double ddx = dx - x, ddy = dy - y;
+            double rel = atan2(ddy, ddx) - h, relh = dhd - h;
+            double *tg = out.target + (size_t)i * 5;
+            double sr, cr;
+            sincos(rel, &sr, &cr);
+            tg[0] = sqrt(ddx * ddx + ddy * ddy);
+            tg[1] = cr; tg[2] = sr;
+            tg[3] = cos(relh); tg[4] = tg[3];
+        }
     }
-    if (out.substeps) out.substeps[i] = (uint8_t)nsub;
-    if (out.retreated) out.retreated[i] = (uint8_t)nret;
-    if (out.was_reset) out.was_reset[i] = is_reset;
     // whole-warp tallies -> one atomic per warp
-    const unsigned am = __activemask();
-    unsigned m_act = __ballot_sync(am, !is_reset);
-    unsigned m_rst = __ballot_sync(am, pending && !reset_all);
-    if ((threadIdx.x & 31) == (__ffs(am) - 1)) {
+    const unsigned m_act = __ballot_sync(HOPE_FULL_MASK, valid && !is_reset);
+    const unsigned m_rst = __ballot_sync(HOPE_FULL_MASK, valid && pending && !reset_all);
+    if (lane == 0) {
         if (m_act) atomicAdd(st.counters + 0, (unsigned long long)__popc(m_act));
         if (m_rst) atomicAdd(st.counters + 1, (unsigned long long)__popc(m_rst));
     }
@@ -255,12 +322,22 @@ __global__ void __launch_bounds__(128) k_advance(int n, Pool pool, EnvState st, 
 // k_observe: one warp per env.  LiDAR raycast -> action-mask sweep -> target representation.
 // =============================================================================================
 struct ObserveSmem {
-    double ex1[MAXE], ey1[MAXE], ex2[MAXE], ey2[MAXE];  // rotated edge end points (ego frame)
-    double ed[MAXE], ee[MAXE], ef[MAXE];                // line coefficients d x + e y + f = 0
-    double L[NRAY];                                     // clip(lidar)+mask_base
+    double ed[MAXE], ee[MAXE], ef[MAXE];                         // line coefficients d x + e y + f = 0 (ego frame)
+    double exmin[MAXE], exmax[MAXE], eymin[MAXE], eymax[MAXE];   // edge bounding box
+    double L[NRAY];                                              // clip(lidar)+mask_base
     int steps[NACT + 2];
-    uint8_t quad[MAXE];                                 // which ray quadrants can accept this edge
+    uint8_t quad[MAXE];                                          // which ray quadrants can accept this edge
 };
+
+// n1/den and n2/den, each correctly rounded (== IEEE division), sharing one reciprocal: with r = RN(1/den)
+// and q = RN(n r), the residual n - den q is exact in an FMA and q + r (n - den q) rounds to RN(n/den)
+// (Markstein).  Used where the reference divides two numerators by the same determinant.
+__device__ __forceinline__ void div_pair(double n1, double n2, double den, double &q1, double &q2) {
+    const double r = __drcp_rn(den);
+    const double a = __dmul_rn(n1, r), b = __dmul_rn(n2, r);
+    q1 = __fma_rn(__fma_rn(-den, a, n1), r, a);
+    q2 = __fma_rn(__fma_rn(-den, b, n2), r, b);
+}
 
 __global__ void __launch_bounds__(256) k_observe(int n, Pool pool, EnvState st, Tables tb, hope_params par, hope_out out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -269,11 +346,10 @@ __global__ void __launch_bounds__(256) k_observe(int n, Pool pool, EnvState st, 
     if (env >= n) return;
     ObserveSmem &sm = reinterpret_cast<ObserveSmem *>(smem_raw)[warp_in_block];
     const int sid = st.scene[env];
-    const double x = st.pose[3 * env], y = st.pose[3 * env + 1], h = st.pose[3 * env + 2];
+    const double x = st.pose[3 * env], y = st.pose[3 * env + 1];
 
     // ---- stage obstacle vertices, rotate into the ego frame (lidar_simulator.py:55-72) -------------
-    double a, b;
-    sincos(h, &b, &a);  // a = cos, b = sin
+    const double a = st.cs[2 * env], b = st.cs[2 * env + 1];  // cos, sin of the heading (from k_advance)
     const double xoff = -x * a - y * b, yoff = x * b - y * a, mb = -b;
     const double2 *verts = reinterpret_cast<const double2 *>(pool.obs) + (size_t)sid * MAXE;
     const uint8_t *nvp = pool.nv + (size_t)sid * MAXO;
@@ -290,9 +366,9 @@ __global__ void __launch_bounds__(256) k_observe(int n, Pool pool, EnvState st, 
             int e = n_edges + __popc(m & ((1u << lane) - 1));
             double x1 = a * p.x + b * p.y + xoff, y1 = mb * p.x + a * p.y + yoff;
             double x2 = a * q.x + b * q.y + xoff, y2 = mb * q.x + a * q.y + yoff;
-            sm.ex1[e] = x1; sm.ey1[e] = y1; sm.ex2[e] = x2; sm.ey2[e] = y2;
             sm.ed[e] = y2 - y1; sm.ee[e] = x1 - x2; sm.ef[e] = y1 * x2 - x1 * y2;  // :104-106
             double exmin = fmin(x1, x2), exmax = fmax(x1, x2), eymin = fmin(y1, y2), eymax = fmax(y1, y2);
+            sm.exmin[e] = exmin; sm.exmax[e] = exmax; sm.eymin[e] = eymin; sm.eymax[e] = eymax;
             // exact culls: a hit must lie inside the edge's bbox (:126-129), on the ray's side of the
             // axes up to 1e-8 (:120-124), and nearer than lidar_range to survive the clip (:134)
             bool xp = exmax >= -1e-8, xn = exmin <= 1e-8, yp = eymax >= -1e-8, yn = eymin <= 1e-8;
@@ -312,24 +388,22 @@ __global__ void __launch_bounds__(256) k_observe(int n, Pool pool, EnvState st, 
         const int ray = q * per_quad + lane;
         const bool live = lane < per_quad;
         const double A = live ? tb.ray_a[ray] : 0.0, B = live ? tb.ray_b[ray] : -1.0;
-        double best = par.lidar_range;
+        // sign conventions of the quadrant (:120-124): reject rx < -1e-8 (sx=+1) or rx > 1e-8 (sx=-1), same for ry
+        const double sx = (q == 0 || q == 3) ? 1.0 : -1.0, sy = (q < 2) ? 1.0 : -1.0;
+        double best2 = INFINITY;  // min over edges of rx^2 + ry^2; sqrt is monotone, so one sqrt at the end is exact
         for (int e = 0; e < n_edges; ++e) {
             if (!((sm.quad[e] >> q) & 1)) continue;  // warp-uniform
-            double d = sm.ed[e], ee = sm.ee[e], f = sm.ef[e];
-            double det = A * ee - B * d;              // :109
+            const double d = sm.ed[e], ee = sm.ee[e], f = sm.ef[e];
+            const double det = A * ee - B * d;        // :109
             if (det == 0.0) continue;                 // parallel -> 100 -> clipped away (:131)
-            double rx = (B * f) / det, ry = (-(A * f)) / det;  // :112-113 with c = 0
-            bool ok;
-            if (q == 0) ok = !(rx < -1e-8) && !(ry < -1e-8);
-            else if (q == 1) ok = !(rx > 1e-8) && !(ry < -1e-8);
-            else if (q == 2) ok = !(rx > 1e-8) && !(ry > 1e-8);
-            else ok = !(rx < -1e-8) && !(ry > 1e-8);
-            double x1 = sm.ex1[e], x2 = sm.ex2[e], y1 = sm.ey1[e], y2 = sm.ey2[e];
-            ok = ok && !(rx > fmax(x1, x2)) && !(rx < fmin(x1, x2)) && !(ry > fmax(y1, y2)) && !(ry < fmin(y1, y2));
-            if (ok) best = fmin(best, sqrt(rx * rx + ry * ry));  // :133
+            double rx, ry;
+            div_pair(B * f, -(A * f), det, rx, ry);   // :112-113 with c = 0
+            const bool ok = !(sx * rx < -1e-8) && !(sy * ry < -1e-8) &&
+                            !(rx > sm.exmax[e]) && !(rx < sm.exmin[e]) && !(ry > sm.eymax[e]) && !(ry < sm.eymin[e]);  // :126-129
+            if (ok) best2 = fmin(best2, rx * rx + ry * ry);  // :133
         }
         if (live) {
-            double r = fmin(fmax(best, 0.0), par.lidar_range) - tb.lidar_base[ray];  // :134, :46
+            double r = fmin(fmax(sqrt(best2), 0.0), par.lidar_range) - tb.lidar_base[ray];  // :133-134, :46
             if (out.lidar) out.lidar[(size_t)env * NRAY + ray] = r;
             sm.L[ray] = fmin(fmax(r, 0.0), 10.0) + tb.mask_base[ray];  // action_mask.py:170
         }
@@ -337,11 +411,12 @@ __global__ void __launch_bounds__(256) k_observe(int n, Pool pool, EnvState st, 
     __syncwarp();
 
     // ---- action-mask sweep (action_mask.py:166-184) --------------------------------------------
-    // s_j = min over the 1200 upsampled rays of (first k with dist_star[rho][j][k] > d_rho).
-    // A ray can lower any s_j only if d_rho < max_{j,k} dist_star[rho] (pmax); an action only if
-    // d_rho < max_k dist_star[rho][j] (pend).  Both screens are exact comparisons of stored doubles,
-    // so the surviving compares give the same integers as the reference's full 1200x42x10 sweep.
+    // s_j = min over the 1200 upsampled rays of (first k with dist_star[rho][j][k] > d_rho).  With the
+    // running maximum P[rho][k][j] = max_{k'<=k} dist_star[rho][j][k'] (same first exceedance), a ray can
+    // lower any s_j only if d_rho < P[rho][9][.] somewhere, i.e. d_rho < pmax[rho].  All screens compare
+    // stored doubles exactly, so the integers equal the reference's full 1200x42x10 sweep.
     int s0 = NITER, s1 = NITER;  // lane owns actions lane and lane+32
+    const bool has2 = lane < NACT - 32;
     for (int base = 0; base < NUP; base += 32) {
         int rho = base + lane;
         bool in = rho < NUP;
@@ -352,26 +427,21 @@ __global__ void __launch_bounds__(256) k_observe(int n, Pool pool, EnvState st, 
         while (act) {
             int bsel = __ffs(act) - 1;
             act &= act - 1;
-            double db = __shfl_sync(HOPE_FULL_MASK, d, bsel);
-            int rb = base + bsel;
-            const double *pe = tb.pend + (size_t)rb * NACT;
-            const double *ds = tb.dist_star + (size_t)rb * NACT * NITER;
-            if (s0 > 0 && db < __ldg(pe + lane)) {
-                const double *row = ds + lane * NITER;
-                int k = 0;
-                while (k < NITER && __ldg(row + k) <= db) ++k;
-                s0 = min(s0, k);
+            const double db = __shfl_sync(HOPE_FULL_MASK, d, bsel);
+            const double *P = tb.pmaxk + (size_t)(base + bsel) * NITER * NACT;  // [k][j], j contiguous
+            // lanes whose running maximum never exceeds db are unaffected by this ray
+            bool open0 = s0 > 0 && db < __ldg(P + (NITER - 1) * NACT + lane);
+            bool open1 = has2 && s1 > 0 && db < __ldg(P + (NITER - 1) * NACT + 32 + lane);
+            for (int k = 0; k < NITER - 1 && __any_sync(HOPE_FULL_MASK, open0 || open1); ++k) {
+                if (open0 && (k >= s0 || db < __ldg(P + k * NACT + lane))) { s0 = min(s0, k); open0 = false; }
+                if (open1 && (k >= s1 || db < __ldg(P + k * NACT + 32 + lane))) { s1 = min(s1, k); open1 = false; }
             }
-            if (lane < NACT - 32 && s1 > 0 && db < __ldg(pe + 32 + lane)) {
-                const double *row = ds + (32 + lane) * NITER;
-                int k = 0;
-                while (k < NITER && __ldg(row + k) <= db) ++k;
-                s1 = min(s1, k);
-            }
+            if (open0) s0 = min(s0, NITER - 1);
+            if (open1) s1 = min(s1, NITER - 1);
         }
     }
     sm.steps[lane] = s0;
-    if (lane < NACT - 32) sm.steps[32 + lane] = s1;
+    if (has2) sm.steps[32 + lane] = s1;
     __syncwarp();
     // post_process (action_mask.py:186-196): per half subtract 1 at both ends, 5-tap min, clip, /10
     int mine[2] = {0, 0};
@@ -402,16 +472,6 @@ __global__ void __launch_bounds__(256) k_observe(int n, Pool pool, EnvState st, 
             if (out.mask) out.mask[(size_t)env * NACT + j] = total == 0 ? 0.01 : (double)mine[rep] / 10;  // :182-183
             if (out.mask_steps) out.mask_steps[(size_t)env * NACT + j] = (uint8_t)mine[rep];
         }
-    }
-    // ---- target representation (car_parking_base.py:372-381; element 4 repeats cos, sic) -----------
-    if (lane == 0 && out.target) {
-        const double *meta = pool.meta + (size_t)sid * META;
-        double ddx = meta[M_DEST] - x, ddy = meta[M_DEST + 1] - y;
-        double rel = atan2(ddy, ddx) - h, relh = meta[M_DEST + 2] - h;
-        double *tg = out.target + (size_t)env * 5;
-        tg[0] = sqrt(ddx * ddx + ddy * ddy);
-        tg[1] = cos(rel); tg[2] = sin(rel);
-        tg[3] = cos(relh); tg[4] = cos(relh);
     }
 }
 
@@ -812,7 +872,8 @@ __device__ __forceinline__ bool sample_hits(const CheckEnv &E, const hope_params
                     const double a = vy2 - vy1, b = vx1 - vx2, c = vy1 * vx2 - vx1 * vy2;  // :477-479
                     const double det = a * ee - b * dd;                                    // :509
                     if (det == 0.0) continue;
-                    const double rx = (b * ff - c * ee) / det, ry = (c * dd - a * ff) / det;  // :512-513
+                    double rx, ry;
+                    div_pair(b * ff - c * ee, c * dd - a * ff, det, rx, ry);               // :512-513
                     const bool okx = !(rx > oxmax) && !(rx < oxmin) && !(rx > exmax) && !(rx < exmin);
                     const bool oky = !(ry > oymax) && !(ry < oymin) && !(ry > eymax) && !(ry < eymin);
                     if (okx && oky) return true;
@@ -953,16 +1014,17 @@ __global__ void __launch_bounds__(128, 4) k_rs_check(int n, Pool pool, EnvState 
 }
 
 // small helpers -------------------------------------------------------------------------------
-__global__ void k_table_reduce(const double *__restrict__ dist_star, double *__restrict__ pend, double *__restrict__ pmax) {
-    // one block per upsampled ray: pend[rho][j] = max_k dist_star[rho][j][k], pmax[rho] = max_j pend
+__global__ void k_table_reduce(const double *__restrict__ dist_star, double *__restrict__ pmaxk, double *__restrict__ pmax) {
+    // one block per upsampled ray: pmaxk[rho][k][j] = max_{k'<=k} dist_star[rho][j][k'], pmax[rho] = max_j pmaxk[rho][9][j]
     int rho = blockIdx.x, j = threadIdx.x;
     __shared__ double sh[64];
     double m = -1.0;
     if (j < NACT) {
         const double *row = dist_star + ((size_t)rho * NACT + j) * NITER;
-        m = row[0];
-        for (int k = 1; k < NITER; ++k) m = fmax(m, row[k]);
-        pend[(size_t)rho * NACT + j] = m;
+        for (int k = 0; k < NITER; ++k) {
+            m = k == 0 ? row[0] : fmax(m, row[k]);
+            pmaxk[((size_t)rho * NITER + k) * NACT + j] = m;
+        }
     }
     sh[j] = m;
     __syncthreads();
@@ -992,7 +1054,7 @@ struct hope_ctx {
     bool have_tables = false, have_scenes = false, have_reset = false;
     double maxc = 0.0;
     // state
-    double *d_pose = nullptr, *d_accum = nullptr;
+    double *d_pose = nullptr, *d_accum = nullptr, *d_cs = nullptr;
     int *d_t = nullptr, *d_scene = nullptr;
     uint8_t *d_pending = nullptr, *d_gate = nullptr;
     unsigned long long *d_counters = nullptr;
@@ -1024,12 +1086,12 @@ int fail(hope_ctx *c, cudaError_t e, const char *what) {
     } while (0)
 
 Pool make_pool(const hope_ctx *c) { return Pool{c->d_obs, c->d_nv, c->d_aabb, c->d_meta, c->d_nobs, c->pool}; }
-EnvState make_state(const hope_ctx *c) { return EnvState{c->d_pose, c->d_t, c->d_accum, c->d_scene, c->d_pending, c->d_gate, c->d_counters}; }
+EnvState make_state(const hope_ctx *c) { return EnvState{c->d_pose, c->d_cs, c->d_t, c->d_accum, c->d_scene, c->d_pending, c->d_gate, c->d_counters}; }
 Tables make_tables(const hope_ctx *c) {
     const double *t = c->d_tab;
     Tables tb;
     tb.ray_a = t; tb.ray_b = t + 120; tb.lidar_base = t + 240; tb.mask_base = t + 360; tb.w_lo = t + 480; tb.w_hi = t + 496;
-    tb.dist_star = t + 512; tb.pend = tb.dist_star + (size_t)NUP * NACT * NITER; tb.pmax = tb.pend + (size_t)NUP * NACT;
+    tb.dist_star = t + 512; tb.pmaxk = tb.dist_star + (size_t)NUP * NACT * NITER; tb.pmax = tb.pmaxk + (size_t)NUP * NACT * NITER;
     tb.maxc = c->maxc;
     return tb;
 }
@@ -1173,10 +1235,11 @@ int hope_create(hope_ctx **out, int device, int n_envs, int pool_size, const hop
     CK(cudaMalloc(&ctx->d_nobs, sizeof(int) * P));
     CK(cudaMemset(ctx->d_nv, 0, P * MAXO));
     CK(cudaMemset(ctx->d_nobs, 0, sizeof(int) * P));
-    const size_t tab = 512 + (size_t)NUP * NACT * NITER + (size_t)NUP * NACT + NUP;
+    const size_t tab = 512 + 2 * (size_t)NUP * NACT * NITER + NUP;
     CK(cudaMalloc(&ctx->d_tab, sizeof(double) * tab));
     CK(cudaMalloc(&ctx->d_pose, sizeof(double) * 3 * N));
     CK(cudaMalloc(&ctx->d_accum, sizeof(double) * N));
+    CK(cudaMalloc(&ctx->d_cs, sizeof(double) * 2 * N));
     CK(cudaMalloc(&ctx->d_t, sizeof(int) * N));
     CK(cudaMalloc(&ctx->d_scene, sizeof(int) * N));
     CK(cudaMalloc(&ctx->d_pending, N));
@@ -1197,7 +1260,7 @@ int hope_destroy(hope_ctx *ctx) {
     if (!ctx) return HOPE_ERR_INVALID;
     cudaSetDevice(ctx->device);
     void *ptrs[] = {ctx->d_obs, ctx->d_aabb, ctx->d_meta, ctx->d_nv, ctx->d_nobs, ctx->d_tab, ctx->d_pose, ctx->d_accum, ctx->d_t,
-                    ctx->d_scene, ctx->d_pending, ctx->d_gate, ctx->d_counters, ctx->d_words, ctx->d_ntry, ctx->d_ncand,
+                    ctx->d_scene, ctx->d_pending, ctx->d_gate, ctx->d_counters, ctx->d_words, ctx->d_ntry, ctx->d_ncand, ctx->d_cs,
                     ctx->d_action, ctx->d_stage};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -1215,8 +1278,8 @@ int hope_upload_tables(hope_ctx *ctx, const double *ray_a, const double *ray_b, 
     CK(cudaMemcpy(ctx->d_tab, head.data(), 512 * 8, cudaMemcpyHostToDevice));
     double *ds = ctx->d_tab + 512;
     CK(cudaMemcpy(ds, dist_star, sizeof(double) * NUP * NACT * NITER, cudaMemcpyHostToDevice));
-    double *pend = ds + (size_t)NUP * NACT * NITER, *pmax = pend + (size_t)NUP * NACT;
-    k_table_reduce<<<NUP, 64>>>(ds, pend, pmax);
+    double *pmaxk = ds + (size_t)NUP * NACT * NITER, *pmax = pmaxk + (size_t)NUP * NACT * NITER;
+    k_table_reduce<<<NUP, 64>>>(ds, pmaxk, pmax);
     ctx->launches++;
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
