@@ -339,7 +339,7 @@ __device__ __forceinline__ void div_pair(double n1, double n2, double den, doubl
     q2 = __fma_rn(__fma_rn(-den, b, n2), r, b);
 }
 
-__global__ void __launch_bounds__(256) k_observe(int n, Pool pool, EnvState st, Tables tb, hope_params par, hope_out out) {
+__global__ void __launch_bounds__(64) k_observe(int n, Pool pool, EnvState st, Tables tb, hope_params par, hope_out out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int env = blockIdx.x * (blockDim.x >> 5) + warp_in_block;
@@ -429,15 +429,19 @@ __global__ void __launch_bounds__(256) k_observe(int n, Pool pool, EnvState st, 
             act &= act - 1;
             const double db = __shfl_sync(HOPE_FULL_MASK, d, bsel);
             const double *P = tb.pmaxk + (size_t)(base + bsel) * NITER * NACT;  // [k][j], j contiguous
-            // lanes whose running maximum never exceeds db are unaffected by this ray
-            bool open0 = s0 > 0 && db < __ldg(P + (NITER - 1) * NACT + lane);
-            bool open1 = has2 && s1 > 0 && db < __ldg(P + (NITER - 1) * NACT + 32 + lane);
-            for (int k = 0; k < NITER - 1 && __any_sync(HOPE_FULL_MASK, open0 || open1); ++k) {
-                if (open0 && (k >= s0 || db < __ldg(P + k * NACT + lane))) { s0 = min(s0, k); open0 = false; }
-                if (open1 && (k >= s1 || db < __ldg(P + k * NACT + 32 + lane))) { s1 = min(s1, k); open1 = false; }
+            // every lane fetches the running maxima of its action(s) below its current bound in one batch of
+            // independent, coalesced loads (row k is 42 contiguous doubles), then finds the first exceedance
+            double v0[NITER], v1[NITER];
+#pragma unroll
+            for (int k = 0; k < NITER; ++k) {
+                v0[k] = (k < s0) ? __ldg(P + k * NACT + lane) : INFINITY;
+                v1[k] = (has2 && k < s1) ? __ldg(P + k * NACT + 32 + lane) : INFINITY;
             }
-            if (open0) s0 = min(s0, NITER - 1);
-            if (open1) s1 = min(s1, NITER - 1);
+#pragma unroll
+            for (int k = NITER - 1; k >= 0; --k) {
+                if (db < v0[k]) s0 = min(s0, k);
+                if (db < v1[k]) s1 = min(s1, k);
+            }
         }
     }
     sm.steps[lane] = s0;
@@ -937,7 +941,7 @@ __device__ void walk_chunk(WordSlot &s, double step, int chunk_base) {
     s.total = (code == RS_DONE) ? chunk_base + k : -1;
 }
 
-__global__ void __launch_bounds__(128, 4) k_rs_check(int n, Pool pool, EnvState st, Tables tb, RsScratch rs, hope_params par, hope_out out) {
+__global__ void __launch_bounds__(64, 8) k_rs_check(int n, Pool pool, EnvState st, Tables tb, RsScratch rs, hope_params par, hope_out out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int env = blockIdx.x * (blockDim.x >> 5) + warp_in_block;
@@ -1097,7 +1101,7 @@ Tables make_tables(const hope_ctx *c) {
 }
 RsScratch make_rs(const hope_ctx *c) { return RsScratch{c->d_words, c->d_ntry, c->d_ncand}; }
 
-constexpr int ADV_THREADS = 128, OBS_THREADS = 256, ENUM_THREADS = 128, CHK_THREADS = 128;
+constexpr int ADV_THREADS = 128, OBS_THREADS = 64, ENUM_THREADS = 128, CHK_THREADS = 64;
 
 void prof_mark(hope_ctx *ctx, int which, cudaStream_t s) {
     if (!ctx->profile) return;
