@@ -1071,6 +1071,8 @@ struct hope_ctx {
     size_t stage_bytes = 0;
     hope_out stage_out;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t aux_stream = nullptr;        // k_observe runs here, concurrently with the Reeds-Shepp kernels
+    cudaEvent_t ev_advanced = nullptr, ev_observed = nullptr;
     unsigned long long launches = 0;
     bool profile = false;
     std::vector<cudaEvent_t> prof_events[4];  // begin/end pairs per kernel
@@ -1111,7 +1113,14 @@ void prof_mark(hope_ctx *ctx, int which, cudaStream_t s) {
     ctx->prof_events[which].push_back(e);
 }
 
-int launch_step(hope_ctx *ctx, const double *d_action, const hope_out &out, unsigned stages, int reset_all, cudaStream_t s) {
+int copy_fields(hope_ctx *ctx, const hope_host_out *h_out, int observe, cudaStream_t s);
+
+// Kernel order of one step.  k_observe and the Reeds-Shepp pair both depend only on k_advance, so when
+// both stages are requested k_observe goes to the context's auxiliary stream and overlaps the RS kernels;
+// the caller's stream waits for it before hope_step returns control of the stream.  With `early_out`
+// (host API) the observation buffers are copied to the host right behind k_observe, under the RS kernels.
+int launch_step(hope_ctx *ctx, const double *d_action, const hope_out &out, unsigned stages, int reset_all, cudaStream_t s,
+                const hope_host_out *early_out = nullptr) {
     const int n = ctx->n;
     Pool pool = make_pool(ctx);
     EnvState st = make_state(ctx);
@@ -1120,12 +1129,20 @@ int launch_step(hope_ctx *ctx, const double *d_action, const hope_out &out, unsi
     k_advance<<<(n + ADV_THREADS - 1) / ADV_THREADS, ADV_THREADS, 0, s>>>(n, pool, st, d_action, ctx->par, out, reset_all);
     prof_mark(ctx, 0, s);
     ctx->launches++;
+    const bool fork = (stages & HOPE_STAGE_OBSERVE) && (stages & HOPE_STAGE_RS);
+    cudaStream_t so = fork ? ctx->aux_stream : s;
     if (stages & HOPE_STAGE_OBSERVE) {
+        if (fork) {
+            CK(cudaEventRecord(ctx->ev_advanced, s));
+            CK(cudaStreamWaitEvent(so, ctx->ev_advanced, 0));
+        }
         const int wpb = OBS_THREADS / 32;
-        prof_mark(ctx, 1, s);
-        k_observe<<<(n + wpb - 1) / wpb, OBS_THREADS, wpb * sizeof(ObserveSmem), s>>>(n, pool, st, tb, ctx->par, out);
-        prof_mark(ctx, 1, s);
+        prof_mark(ctx, 1, so);
+        k_observe<<<(n + wpb - 1) / wpb, OBS_THREADS, wpb * sizeof(ObserveSmem), so>>>(n, pool, st, tb, ctx->par, out);
+        prof_mark(ctx, 1, so);
         ctx->launches++;
+        if (early_out) { int rc = copy_fields(ctx, early_out, 1, so); if (rc) return rc; }
+        if (fork) CK(cudaEventRecord(ctx->ev_observed, so));
     }
     if (stages & HOPE_STAGE_RS) {
         RsScratch rs = make_rs(ctx);
@@ -1138,14 +1155,16 @@ int launch_step(hope_ctx *ctx, const double *d_action, const hope_out &out, unsi
         prof_mark(ctx, 3, s);
         ctx->launches += 2;
     }
+    if (fork) CK(cudaStreamWaitEvent(s, ctx->ev_observed, 0));
     CK(cudaGetLastError());
     return HOPE_OK;
 }
 
-struct OutField { size_t offset; size_t elem; int per_env; };
-#define OF(member, type, per) OutField{offsetof(hope_out, member), sizeof(type), per}
+struct OutField { size_t offset; size_t elem; int per_env; int observe; };  // observe = 1: produced by k_observe
+#define OF(member, type, per) OutField{offsetof(hope_out, member), sizeof(type), per, 0}
+#define OFO(member, type, per) OutField{offsetof(hope_out, member), sizeof(type), per, 1}
 const OutField kOutFields[] = {
-    OF(pose, double, 3), OF(lidar, double, NRAY), OF(mask, double, NACT), OF(mask_steps, uint8_t, NACT),
+    OF(pose, double, 3), OFO(lidar, double, NRAY), OFO(mask, double, NACT), OFO(mask_steps, uint8_t, NACT),
     OF(target, double, 5), OF(reward, double, 1), OF(reward_info, double, 5), OF(status, int32_t, 1),
     OF(done, uint8_t, 1), OF(substeps, uint8_t, 1), OF(retreated, uint8_t, 1), OF(was_reset, uint8_t, 1),
     OF(rs_found, uint8_t, 1), OF(rs_nseg, uint8_t, 1), OF(rs_types, uint8_t, 5), OF(rs_lengths, double, 5),
@@ -1172,14 +1191,14 @@ int ensure_stage(hope_ctx *ctx) {
     return HOPE_OK;
 }
 
-int copy_back(hope_ctx *ctx, const hope_host_out *h_out) {
+// observe: 1 = only k_observe's outputs, 0 = only the others, -1 = all
+int copy_fields(hope_ctx *ctx, const hope_host_out *h_out, int observe, cudaStream_t s) {
     for (int k = 0; k < kNumOutFields; ++k) {
         void *dst = field_ptr_c(*h_out, kOutFields[k]);
-        if (!dst) continue;
+        if (!dst || (observe >= 0 && kOutFields[k].observe != observe)) continue;
         CK(cudaMemcpyAsync(dst, field_ptr_c(ctx->stage_out, kOutFields[k]), kOutFields[k].elem * kOutFields[k].per_env * ctx->n,
-                           cudaMemcpyDeviceToHost, ctx->own_stream));
+                           cudaMemcpyDeviceToHost, s));
     }
-    CK(cudaStreamSynchronize(ctx->own_stream));
     return HOPE_OK;
 }
 
@@ -1255,6 +1274,9 @@ int hope_create(hope_ctx **out, int device, int n_envs, int pool_size, const hop
     CK(cudaMalloc(&ctx->d_words, sizeof(RsWord) * N * MAXW));
     CK(cudaMalloc(&ctx->d_ntry, N));
     CK(cudaMalloc(&ctx->d_ncand, N));
+    CK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->ev_advanced, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_observed, cudaEventDisableTiming));
     CK(cudaFuncSetAttribute(k_observe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((OBS_THREADS / 32) * sizeof(ObserveSmem))));
     CK(cudaFuncSetAttribute(k_rs_check, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((CHK_THREADS / 32) * sizeof(CheckSmem))));
     return HOPE_OK;
@@ -1268,6 +1290,9 @@ int hope_destroy(hope_ctx *ctx) {
                     ctx->d_action, ctx->d_stage};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    if (ctx->ev_advanced) cudaEventDestroy(ctx->ev_advanced);
+    if (ctx->ev_observed) cudaEventDestroy(ctx->ev_observed);
     delete ctx;
     return HOPE_OK;
 }
@@ -1391,9 +1416,15 @@ int hope_step_host(hope_ctx *ctx, const double *h_action, const hope_host_out *h
     int rc = ensure_stage(ctx);
     if (rc) return rc;
     CK(cudaMemcpyAsync(ctx->d_action, h_action, sizeof(double) * 2 * ctx->n, cudaMemcpyHostToDevice, ctx->own_stream));
-    rc = launch_step(ctx, ctx->d_action, ctx->stage_out, stages | HOPE_STAGE_ADVANCE, 0, ctx->own_stream);
+    stages |= HOPE_STAGE_ADVANCE;
+    const bool fork = (stages & HOPE_STAGE_OBSERVE) && (stages & HOPE_STAGE_RS);
+    // with both stages on, the observation buffers leave for the host behind k_observe while the RS kernels run
+    rc = launch_step(ctx, ctx->d_action, ctx->stage_out, stages, 0, ctx->own_stream, fork ? h_out : nullptr);
     if (rc) return rc;
-    return copy_back(ctx, h_out);
+    rc = copy_fields(ctx, h_out, fork ? 0 : -1, ctx->own_stream);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->own_stream));
+    return HOPE_OK;
 }
 
 int hope_reset_host(hope_ctx *ctx, const int32_t *h_scene_ids, const hope_host_out *h_out) {
@@ -1403,7 +1434,10 @@ int hope_reset_host(hope_ctx *ctx, const int32_t *h_scene_ids, const hope_host_o
     if (rc) return rc;
     rc = hope_reset(ctx, h_scene_ids, &ctx->stage_out, ctx->own_stream);
     if (rc) return rc;
-    return copy_back(ctx, h_out);
+    rc = copy_fields(ctx, h_out, -1, ctx->own_stream);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->own_stream));
+    return HOPE_OK;
 }
 
 int hope_get_state(hope_ctx *ctx, double *h_pose, int32_t *h_t, double *h_accum, int32_t *h_scene_id) {
