@@ -140,7 +140,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="scenes per GPU (default: the BASELINE cfg-3 size)")
@@ -194,12 +194,17 @@ def main():
     for k in range(W):
         env.step(actions[k])
     barrier()
-    c0 = env.counters()
-    env.profile(True)
-    env.profile_read()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        t_wait = time.time()
+        while not sampler.lines and time.time() - t_wait < 3.0:  # let nvidia-smi deliver its first line,
+            env.step(actions[0])                                  # keeping the GPU busy (untimed, uncounted)
+        sampler.lines.clear()
+    barrier()
+    c0 = env.counters()
+    env.profile(True)
+    env.profile_read()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -213,6 +218,7 @@ def main():
     env.profile(False)
     c1 = env.counters()
     steps_local = c1["env_steps"] - c0["env_steps"]  # env-steps with an action (auto-reset steps excluded)
+    assert 0 < steps_local <= n * K, (steps_local, n, K)
     launches = c1["kernel_launches"] - c0["kernel_launches"]
     ms = max_over_ranks(ms_local)
     total_steps = sum_over_ranks(float(steps_local))

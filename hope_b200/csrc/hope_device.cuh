@@ -14,6 +14,11 @@
 
 namespace hope {
 
+// min / max of finite doubles as one compare + select (fmin/fmax carry NaN handling that costs twice
+// as many instructions in SASS; no operand here is ever NaN)
+__device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
+__device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
+
 // ---------------------------------------------------------------------------------------------
 // Exact orientation sign.  Ring-vs-ring `intersects` (car_parking_base.py:153-158) is a robust
 // predicate in GEOS; a float64 determinant alone can flip it for near-degenerate contacts.
@@ -55,13 +60,13 @@ __device__ __forceinline__ int orient(double ax, double ay, double bx, double by
     return orient_exact(ax, ay, bx, by, cx, cy, fallback_counter);
 }
 __device__ __forceinline__ bool within(double px, double py, double ax, double ay, double bx, double by) {
-    return fmin(ax, bx) <= px && px <= fmax(ax, bx) && fmin(ay, by) <= py && py <= fmax(ay, by);
+    return dmin(ax, bx) <= px && px <= dmax(ax, bx) && dmin(ay, by) <= py && py <= dmax(ay, by);
 }
 // Closed segments share a point (proper crossing, touch or collinear overlap).
 __device__ __forceinline__ bool segments_touch(double p1x, double p1y, double p2x, double p2y, double q1x, double q1y,
                                                double q2x, double q2y, unsigned long long *fc) {
-    if (fmax(p1x, p2x) < fmin(q1x, q2x) || fmax(q1x, q2x) < fmin(p1x, p2x)) return false;
-    if (fmax(p1y, p2y) < fmin(q1y, q2y) || fmax(q1y, q2y) < fmin(p1y, p2y)) return false;
+    if (dmax(p1x, p2x) < dmin(q1x, q2x) || dmax(q1x, q2x) < dmin(p1x, p2x)) return false;
+    if (dmax(p1y, p2y) < dmin(q1y, q2y) || dmax(q1y, q2y) < dmin(p1y, p2y)) return false;
     int o1 = orient(p1x, p1y, p2x, p2y, q1x, q1y, fc), o2 = orient(p1x, p1y, p2x, p2y, q2x, q2y, fc);
     int o3 = orient(q1x, q1y, q2x, q2y, p1x, p1y, fc), o4 = orient(q1x, q1y, q2x, q2y, p2x, p2y, fc);
     if (o1 * o2 < 0 && o3 * o4 < 0) return true;

@@ -105,8 +105,8 @@ __device__ __forceinline__ unsigned warp_collisions(bool check, const double *bx
 #pragma unroll
     for (int i = 0; i < 4; ++i) { sm.bx[lane][i] = bx[i]; sm.by[lane][i] = by[i]; }
     sm.sid[lane] = sid;
-    const double vxmin = fmin(fmin(bx[0], bx[1]), fmin(bx[2], bx[3])), vxmax = fmax(fmax(bx[0], bx[1]), fmax(bx[2], bx[3]));
-    const double vymin = fmin(fmin(by[0], by[1]), fmin(by[2], by[3])), vymax = fmax(fmax(by[0], by[1]), fmax(by[2], by[3]));
+    const double vxmin = dmin(dmin(bx[0], bx[1]), dmin(bx[2], bx[3])), vxmax = dmax(dmax(bx[0], bx[1]), dmax(bx[2], bx[3]));
+    const double vymin = dmin(dmin(by[0], by[1]), dmin(by[2], by[3])), vymax = dmax(dmax(by[0], by[1]), dmax(by[2], by[3]));
     int maxn = check ? nobs : 0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) maxn = max(maxn, __shfl_xor_sync(HOPE_FULL_MASK, maxn, o));
@@ -199,12 +199,12 @@ __global__ void __launch_bounds__(128) k_advance(int n, Pool pool, EnvState st, 
     bool moving = !is_reset;
     if (moving) {
         // env_wrapper.py:37-50: clip to [-1,1], a*(hi-lo)/2 + (hi+lo)/2 with float32-exact bounds
-        double a0 = fmin(fmax(action[2 * i], -1.0), 1.0), a1 = fmin(fmax(action[2 * i + 1], -1.0), 1.0);
+        double a0 = dmin(dmax(action[2 * i], -1.0), 1.0), a1 = dmin(dmax(action[2 * i + 1], -1.0), 1.0);
         double steer = a0 * ((par.valid_steer[1] - par.valid_steer[0]) / 2) + (par.valid_steer[1] + par.valid_steer[0]) / 2;
         double speed = a1 * ((par.valid_speed[1] - par.valid_speed[0]) / 2) + (par.valid_speed[1] + par.valid_speed[0]) / 2;
         // vehicle.py:83-84
-        v = fmin(fmax(speed, par.valid_speed[0]), par.valid_speed[1]);
-        double phi = fmin(fmax(steer, par.valid_steer[0]), par.valid_steer[1]);
+        v = dmin(dmax(speed, par.valid_speed[0]), par.valid_speed[1]);
+        double phi = dmin(dmax(steer, par.valid_steer[0]), par.valid_steer[1]);
         // vehicle.py:88-93, one mini-iteration: x += v cos(h) dt ; h += v tan(phi)/L dt   (dt = step_length/mini_iter)
         dh = v * tan(phi) / par.wheel_base * par.step_length / par.mini_iter;
         ds = v * par.step_length / par.mini_iter;
@@ -243,8 +243,8 @@ __global__ void __launch_bounds__(128) k_advance(int n, Pool pool, EnvState st, 
     vehicle_box(x, y, c, s, par.box_x, par.box_y, bx, by);
     double inter = 0.0;
     {
-        double vxmin = fmin(fmin(bx[0], bx[1]), fmin(bx[2], bx[3])), vxmax = fmax(fmax(bx[0], bx[1]), fmax(bx[2], bx[3]));
-        double vymin = fmin(fmin(by[0], by[1]), fmin(by[2], by[3])), vymax = fmax(fmax(by[0], by[1]), fmax(by[2], by[3]));
+        double vxmin = dmin(dmin(bx[0], bx[1]), dmin(bx[2], bx[3])), vxmax = dmax(dmax(bx[0], bx[1]), dmax(bx[2], bx[3]));
+        double vymin = dmin(dmin(by[0], by[1]), dmin(by[2], by[3])), vymax = dmax(dmax(by[0], by[1]), dmax(by[2], by[3]));
         if (!(vxmax < daxmin || daxmax < vxmin || vymax < daymin || daymax < vymin)) inter = quad_clip_area(bx, by, dbx, dby);
     }
     const double xmin = meta[M_BOUNDS], xmax = meta[M_BOUNDS + 1], ymin = meta[M_BOUNDS + 2], ymax = meta[M_BOUNDS + 3];
@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(64) k_observe(int n, Pool pool, EnvState st, T
             double x1 = a * p.x + b * p.y + xoff, y1 = mb * p.x + a * p.y + yoff;
             double x2 = a * q.x + b * q.y + xoff, y2 = mb * q.x + a * q.y + yoff;
             sm.ed[e] = y2 - y1; sm.ee[e] = x1 - x2; sm.ef[e] = y1 * x2 - x1 * y2;  // :104-106
-            double exmin = fmin(x1, x2), exmax = fmax(x1, x2), eymin = fmin(y1, y2), eymax = fmax(y1, y2);
+            double exmin = dmin(x1, x2), exmax = dmax(x1, x2), eymin = dmin(y1, y2), eymax = dmax(y1, y2);
             sm.exmin[e] = exmin; sm.exmax[e] = exmax; sm.eymin[e] = eymin; sm.eymax[e] = eymax;
             // exact culls: a hit must lie inside the edge's bbox (:126-129), on the ray's side of the
             // axes up to 1e-8 (:120-124), and nearer than lidar_range to survive the clip (:134)
@@ -400,12 +400,12 @@ __global__ void __launch_bounds__(64) k_observe(int n, Pool pool, EnvState st, T
             div_pair(B * f, -(A * f), det, rx, ry);   // :112-113 with c = 0
             const bool ok = !(sx * rx < -1e-8) && !(sy * ry < -1e-8) &&
                             !(rx > sm.exmax[e]) && !(rx < sm.exmin[e]) && !(ry > sm.eymax[e]) && !(ry < sm.eymin[e]);  // :126-129
-            if (ok) best2 = fmin(best2, rx * rx + ry * ry);  // :133
+            if (ok) best2 = dmin(best2, rx * rx + ry * ry);  // :133
         }
         if (live) {
-            double r = fmin(fmax(sqrt(best2), 0.0), par.lidar_range) - tb.lidar_base[ray];  // :133-134, :46
+            double r = dmin(dmax(sqrt(best2), 0.0), par.lidar_range) - tb.lidar_base[ray];  // :133-134, :46
             if (out.lidar) out.lidar[(size_t)env * NRAY + ray] = r;
-            sm.L[ray] = fmin(fmax(r, 0.0), 10.0) + tb.mask_base[ray];  // action_mask.py:170
+            sm.L[ray] = dmin(dmax(r, 0.0), 10.0) + tb.mask_base[ray];  // action_mask.py:170
         }
     }
     __syncwarp();
@@ -853,8 +853,8 @@ __device__ __forceinline__ bool sample_hits(const CheckEnv &E, const hope_params
         bx[q] = cth * par.box_x[q] - sth * par.box_y[q] + gx;
         by[q] = sth * par.box_x[q] + cth * par.box_y[q] + gy;
     }
-    const double vxmin = fmin(fmin(bx[0], bx[1]), fmin(bx[2], bx[3])), vxmax = fmax(fmax(bx[0], bx[1]), fmax(bx[2], bx[3]));
-    const double vymin = fmin(fmin(by[0], by[1]), fmin(by[2], by[3])), vymax = fmax(fmax(by[0], by[1]), fmax(by[2], by[3]));
+    const double vxmin = dmin(dmin(bx[0], bx[1]), dmin(bx[2], bx[3])), vxmax = dmax(dmax(bx[0], bx[1]), dmax(bx[2], bx[3]));
+    const double vymin = dmin(dmin(by[0], by[1]), dmin(by[2], by[3])), vymax = dmax(dmax(by[0], by[1]), dmax(by[2], by[3]));
     for (int ob = 0; ob < E.nobs; ++ob) {
         double4 bb = ld_aabb(E.aabb + ob);
         // a hit needs rx inside both segments' x-ranges and ry inside both y-ranges (:518-526): disjoint
@@ -864,14 +864,14 @@ __device__ __forceinline__ bool sample_hits(const CheckEnv &E, const hope_params
         double2 p1 = __ldg(E.verts + ob * MAXV);
         for (int j = 0; j < nv; ++j) {
             double2 p2 = __ldg(E.verts + ob * MAXV + ((j + 1 == nv) ? 0 : j + 1));
-            const double oxmax = fmax(p1.x, p2.x), oxmin = fmin(p1.x, p2.x), oymax = fmax(p1.y, p2.y), oymin = fmin(p1.y, p2.y);
+            const double oxmax = dmax(p1.x, p2.x), oxmin = dmin(p1.x, p2.x), oymax = dmax(p1.y, p2.y), oymin = dmin(p1.y, p2.y);
             if (!(vxmax < oxmin || oxmax < vxmin || vymax < oymin || oymax < vymin)) {
                 const double dd = p2.y - p1.y, ee = p1.x - p2.x, ff = p1.y * p2.x - p1.x * p2.y;  // :504-506
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int q2 = (q + 1) & 3;
                     const double vx1 = bx[q], vy1 = by[q], vx2 = bx[q2], vy2 = by[q2];
-                    const double exmax = fmax(vx1, vx2), exmin = fmin(vx1, vx2), eymax = fmax(vy1, vy2), eymin = fmin(vy1, vy2);
+                    const double exmax = dmax(vx1, vx2), exmin = dmin(vx1, vx2), eymax = dmax(vy1, vy2), eymin = dmin(vy1, vy2);
                     if (exmax < oxmin || oxmax < exmin || eymax < oymin || oymax < eymin) continue;
                     const double a = vy2 - vy1, b = vx1 - vx2, c = vy1 * vx2 - vx1 * vy2;  // :477-479
                     const double det = a * ee - b * dd;                                    // :509
@@ -927,14 +927,33 @@ __device__ bool chunk_is_bad(const WordSlot &s, const CheckEnv &E, const hope_pa
     return false;
 }
 
-// lane-private: replay up to RS_CHUNK samples of this slot's chain, saving a state every RS_STRIDE
+// lane-private: replay up to RS_CHUNK samples of this slot's chain, saving a state every RS_STRIDE.
+// Inside a segment the step is the bare `pd += d; |pd| <= |l|` of the reference; everything else
+// (origin, segment changes, end point) goes through walker_next.
 __device__ void walk_chunk(WordSlot &s, double step, int chunk_base) {
     uint8_t code = s.resume_code;
     double pd = s.resume_pd;
-    int k = 0;
-    for (; k < RS_CHUNK && code != RS_DONE; ++k) {
-        if ((k & (RS_STRIDE - 1)) == 0) { s.st_code[k / RS_STRIDE] = code; s.st_pd[k / RS_STRIDE] = pd; }
-        walker_next(s, step, code, pd);
+    int k = 0, cur = -1;
+    double d = 0.0, al = 0.0;
+    if (code < HOPE_RS_MAX_SEG) { cur = code; const double l = s.len[code]; al = fabs(l); d = l > 0.0 ? step : -step; }
+    while (k < RS_CHUNK && code != RS_DONE) {
+        s.st_code[k / RS_STRIDE] = code; s.st_pd[k / RS_STRIDE] = pd;
+        int i = 0;
+        while (i < RS_STRIDE && code != RS_DONE) {
+            if (code == cur) {
+                while (i < RS_STRIDE) {
+                    const double nx = pd + d;           // reeds_shepp.py:492
+                    if (!(fabs(nx) <= al)) break;       // :488
+                    pd = nx; ++i;
+                }
+                if (i == RS_STRIDE) break;
+            }
+            walker_next(s, step, code, pd);
+            ++i;
+            if (code < HOPE_RS_MAX_SEG) { cur = code; const double l = s.len[code]; al = fabs(l); d = l > 0.0 ? step : -step; }
+            else cur = -1;
+        }
+        k += i;
     }
     for (int j = (k + RS_STRIDE - 1) / RS_STRIDE; j < 32; ++j) s.st_code[j] = RS_DONE;
     s.resume_code = code; s.resume_pd = pd;
@@ -1026,7 +1045,7 @@ __global__ void k_table_reduce(const double *__restrict__ dist_star, double *__r
     if (j < NACT) {
         const double *row = dist_star + ((size_t)rho * NACT + j) * NITER;
         for (int k = 0; k < NITER; ++k) {
-            m = k == 0 ? row[0] : fmax(m, row[k]);
+            m = k == 0 ? row[0] : dmax(m, row[k]);
             pmaxk[((size_t)rho * NITER + k) * NACT + j] = m;
         }
     }
@@ -1034,7 +1053,7 @@ __global__ void k_table_reduce(const double *__restrict__ dist_star, double *__r
     __syncthreads();
     if (j == 0) {
         double mm = sh[0];
-        for (int q = 1; q < NACT; ++q) mm = fmax(mm, sh[q]);
+        for (int q = 1; q < NACT; ++q) mm = dmax(mm, sh[q]);
         pmax[rho] = mm;
     }
 }
