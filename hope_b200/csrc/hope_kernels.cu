@@ -71,10 +71,16 @@ struct RsWord {  // one admitted word, lengths in curvature-normalised units
     uint8_t n;
     uint8_t pad[2];
 };
+struct WordSlot;
 struct RsScratch {
-    RsWord *words;     // [N][MAXW] in try order
-    uint8_t *ntry;     // [N]
-    uint8_t *ncand;    // [N]
+    RsWord *words;       // [N][MAXW] in try order
+    uint8_t *ntry;       // [N]
+    uint8_t *ncand;      // [N]
+    int *item_base;      // [N]   first work item of env i (its ntry items are consecutive, in try order)
+    int *items;          // [N*MAXW] work item -> (env << 4) | try slot
+    uint8_t *item_bad;   // [N*MAXW] 1 = the word leaves the map or touches an obstacle
+    WordSlot *slots;     // [N*MAXW] per-item sampling plan written by k_rs_walk
+    int *n_items;        // [1]   items of this step (reset by the host before k_rs_enumerate)
 };
 
 __device__ __forceinline__ double4 ld_aabb(const double4 *p) {  // read-only path, two 128-bit loads
@@ -642,10 +648,8 @@ __device__ bool admit(WordList &w, int n, uint32_t ty, const double *len, unsign
     return true;
 }
 
-__global__ void __launch_bounds__(128) k_rs_enumerate(int n, Pool pool, EnvState st, Tables tb, RsScratch rs, hope_out out) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    // default outputs: no path (k_rs_check overwrites them for the env whose search succeeds)
+__device__ int enumerate_env(int i, const Pool &pool, const EnvState &st, const Tables &tb, const RsScratch &rs, const hope_out &out) {
+    // default outputs: no path (k_rs_select overwrites them for the env whose search succeeds)
     if (out.rs_found) out.rs_found[i] = 0;
     if (out.rs_nseg) out.rs_nseg[i] = 0;
     if (out.rs_L) out.rs_L[i] = 0.0;
@@ -653,7 +657,7 @@ __global__ void __launch_bounds__(128) k_rs_enumerate(int n, Pool pool, EnvState
     if (out.rs_ntried) out.rs_ntried[i] = 0;
     if (out.rs_types) for (int k = 0; k < 5; ++k) out.rs_types[5 * i + k] = HOPE_RS_NONE;
     if (out.rs_lengths) for (int k = 0; k < 5; ++k) out.rs_lengths[5 * i + k] = 0.0;
-    if (!st.gate[i]) { rs.ntry[i] = 0; rs.ncand[i] = 0; return; }
+    if (!st.gate[i]) { rs.ntry[i] = 0; rs.ncand[i] = 0; return 0; }
     const double *meta = pool.meta + (size_t)st.scene[i] * META;
     const double sx = st.pose[3 * i], sy = st.pose[3 * i + 1], sh = st.pose[3 * i + 2];
     // generate_path :540-547
@@ -756,62 +760,84 @@ __global__ void __launch_bounds__(128) k_rs_enumerate(int n, Pool pool, EnvState
     rs.ntry[i] = (uint8_t)ntry;
     rs.ncand[i] = (uint8_t)w.count;
     if (out.rs_ncand) out.rs_ncand[i] = (uint8_t)w.count;
+    return ntry;
+}
+
+__global__ void __launch_bounds__(128) k_rs_enumerate(int n, Pool pool, EnvState st, Tables tb, RsScratch rs, hope_out out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    const int ntry = i < n ? enumerate_env(i, pool, st, tb, rs, out) : 0;
+    // every tried word becomes one work item of k_rs_walk / k_rs_check: warp-level prefix sum, one atomic per warp
+    int incl = ntry;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(HOPE_FULL_MASK, incl, o); if (lane >= o) incl += v; }
+    const int warp_total = __shfl_sync(HOPE_FULL_MASK, incl, 31);
+    int warp_base = 0;
+    if (lane == 31 && warp_total) warp_base = atomicAdd(rs.n_items, warp_total);
+    warp_base = __shfl_sync(HOPE_FULL_MASK, warp_base, 31);
+    if (i < n) {
+        const int base = warp_base + incl - ntry;
+        rs.item_base[i] = base;
+        for (int k = 0; k < ntry; ++k) rs.items[base + k] = (i << 4) | k;
+    }
 }
 
 // =============================================================================================
-// k_rs_check: one warp per env.  Sample each word of the try list every rs_step metres and test
-// the swept vehicle boxes against map bounds and obstacle edges; the first clean word wins.
+// Reeds-Shepp feasibility: k_rs_walk (thread / tried word) -> k_rs_check (warp / tried word)
+// -> k_rs_select (thread / env).
+//
+// Sample each tried word every rs_step metres and test the swept vehicle boxes against map bounds
+// and obstacle edges; the first clean word in try order wins (car_parking_base.py:436-450).
 //
 // The sample positions of a word come from a float accumulation (`pd += d`, reeds_shepp.py:488-492)
-// that has to be replayed add by add to reproduce the reference's sample set.  Replaying it in
-// one lane per sample step would serialise the warp, so the work is split:
-//   walk phase    lane w replays the chain of word w of the current batch (up to RS_WB words side by
-//                 side) and saves its state every RS_STRIDE samples;
-//   sample phase  for one word at a time, lane j resumes from saved state j and evaluates its own
-//                 RS_STRIDE consecutive samples (pose, swept box, bounds, obstacle edges).
+// that has to be replayed add by add to reproduce the reference's sample set.  k_rs_walk replays it
+// once per word, one word per THREAD (so 32 words advance per warp instruction), and saves a resume
+// state every RS_STRIDE samples; k_rs_check gives every word a WARP in which lane j resumes from
+// saved state j and evaluates its own RS_STRIDE consecutive samples.  All tried words of an env are
+// checked independently (under random actions 93 % of searches fail, i.e. every word is needed
+// anyway); k_rs_select then takes the first clean one.
 // =============================================================================================
-constexpr int RS_WB = 8;                        // words walked side by side
 constexpr int RS_STRIDE = 8;                    // samples per lane in one chunk
 constexpr int RS_CHUNK = 32 * RS_STRIDE;        // samples covered by one set of saved states
 constexpr uint8_t RS_ORIGIN = 0xFE, RS_END = 0x80, RS_DONE = 0xFF;
 
-struct WordSlot {
+struct WordSlot {                               // 552 bytes, the sampling plan of one tried word
     double len[HOPE_RS_MAX_SEG];                // normalised signed segment lengths
     double org[HOPE_RS_MAX_SEG][5];             // per segment: ox, oy, oyaw, cos(oyaw), sin(oyaw) (local frame)
     double st_pd[32];                           // saved walker state at sample RS_STRIDE*j of the chunk
     double end_lx;                              // local x of the final end point (trailing-zero rule)
+    double resume_pd;                           // walker state at the start of the next chunk
     uint8_t st_code[32];
     uint32_t types;                             // 4 bits per segment
     int n;                                      // segments
     int total;                                  // samples in the word if the walk reached the end, else -1
-    uint8_t resume_code; double resume_pd;      // walker state at the start of the next chunk
+    uint8_t resume_code, pad[3];
 };
-struct CheckSmem { WordSlot slot[RS_WB]; };
+static_assert(sizeof(WordSlot) % 8 == 0, "WordSlot is copied as 64-bit words");
 
 // One step of generate_local_course's sample sequence (:452-507).  (code, pd) is the sample just
 // emitted; on return it is the next one.  code: RS_ORIGIN = path start, seg index = loop sample of
 // that segment at arc parameter pd, RS_END|seg = the final end point, RS_DONE = no more samples.
-__device__ __forceinline__ void walker_next(const WordSlot &w, double step, uint8_t &code, double &pd) {
+__device__ __forceinline__ void walker_next(const double *len, int nseg, double step, uint8_t &code, double &pd) {
     int seg;
     double d;
     if (code == RS_ORIGIN) {
         seg = 0;
-        d = w.len[0] > 0.0 ? step : -step;
+        d = len[0] > 0.0 ? step : -step;
         pd = d - 0.0;                                   // pd = d - ll with ll = 0.0 (:471-472, :486)
     } else if (code & RS_END) {
         code = RS_DONE;
         return;
     } else {
         seg = code;
-        d = w.len[seg] > 0.0 ? step : -step;
+        d = len[seg] > 0.0 ? step : -step;
         pd += d;                                        // :492
     }
     for (;;) {
-        double l = w.len[seg];
+        double l = len[seg];
         if (fabs(pd) <= fabs(l)) { code = (uint8_t)seg; return; }   // :488
-        if (seg + 1 == w.n) { code = (uint8_t)(RS_END | seg); pd = l; return; }  // :496-498
+        if (seg + 1 == nseg) { code = (uint8_t)(RS_END | seg); pd = l; return; }  // :496-498
         double ll = l - pd - d;                         // :494
-        double ln = w.len[seg + 1];
+        double ln = len[seg + 1];
         d = ln > 0.0 ? step : -step;                    // :475-478
         pd = (l * ln > 0) ? -d - ll : d - ll;           // :483-486
         ++seg;
@@ -835,13 +861,73 @@ __device__ __forceinline__ void rs_interp(double p, int m, double maxc, const do
     }
 }
 
-// Evaluate the up-to RS_STRIDE samples lane `lane` owns in the current chunk of word slot `s`.
-// Returns true (warp-uniform) if any sample leaves the map or touches an obstacle edge.
+// Replay up to RS_CHUNK samples of a word's chain from its resume state, saving a state every
+// RS_STRIDE.  Inside a segment the step is the bare `pd += d; |pd| <= |l|` of the reference;
+// everything else (origin, segment changes, end point) goes through walker_next.
+__device__ void walk_chunk(WordSlot &s, const double *len, double step, int chunk_base) {
+    uint8_t code = s.resume_code;
+    double pd = s.resume_pd;
+    const int nseg = s.n;
+    int k = 0, cur = -1;
+    double d = 0.0, al = 0.0;
+    if (code < HOPE_RS_MAX_SEG) { cur = code; const double l = len[code]; al = fabs(l); d = l > 0.0 ? step : -step; }
+    while (k < RS_CHUNK && code != RS_DONE) {
+        s.st_code[k / RS_STRIDE] = code; s.st_pd[k / RS_STRIDE] = pd;
+        int i = 0;
+        while (i < RS_STRIDE && code != RS_DONE) {
+            if (code == cur) {
+                while (i < RS_STRIDE) {
+                    const double nx = pd + d;           // reeds_shepp.py:492
+                    if (!(fabs(nx) <= al)) break;       // :488
+                    pd = nx; ++i;
+                }
+                if (i == RS_STRIDE) break;
+            }
+            walker_next(len, nseg, step, code, pd);
+            ++i;
+            if (code < HOPE_RS_MAX_SEG) { cur = code; const double l = len[code]; al = fabs(l); d = l > 0.0 ? step : -step; }
+            else cur = -1;
+        }
+        k += i;
+    }
+    for (int j = (k + RS_STRIDE - 1) / RS_STRIDE; j < 32; ++j) s.st_code[j] = RS_DONE;
+    s.resume_code = code; s.resume_pd = pd;
+    s.total = (code == RS_DONE) ? chunk_base + k : -1;
+}
+
+__global__ void __launch_bounds__(128) k_rs_walk(RsScratch rs, Tables tb, hope_params par) {
+    const int n_items = *rs.n_items;
+    const double maxc = tb.maxc, step = par.rs_step * maxc;
+    for (int item = blockIdx.x * blockDim.x + threadIdx.x; item < n_items; item += gridDim.x * blockDim.x) {
+        const int code = rs.items[item], env = code >> 4, slot = code & 15;
+        const RsWord w = rs.words[(size_t)env * MAXW + slot];
+        WordSlot &s = rs.slots[item];
+        double len[HOPE_RS_MAX_SEG];
+        uint32_t ty = 0;
+#pragma unroll
+        for (int k = 0; k < HOPE_RS_MAX_SEG; ++k) { len[k] = w.len[k]; s.len[k] = w.len[k]; ty |= (uint32_t)(w.types[k] & 0xF) << (4 * k); }
+        s.types = ty; s.n = w.n;
+        double org[5] = {0.0, 0.0, 0.0, 1.0, 0.0};
+        for (int k = 0; k < w.n; ++k) {
+#pragma unroll
+            for (int q = 0; q < 5; ++q) s.org[k][q] = org[q];
+            double ex, ey, eyaw;
+            rs_interp(len[k], (int)((ty >> (4 * k)) & 0xF), maxc, org, ex, ey, eyaw);  // end of segment k = origin of k+1
+            org[0] = ex; org[1] = ey;
+            if (eyaw != org[2]) { org[2] = eyaw; sincos(eyaw, &org[4], &org[3]); }
+        }
+        s.end_lx = org[0];
+        s.resume_code = RS_ORIGIN; s.resume_pd = 0.0;
+        walk_chunk(s, len, step, 0);
+    }
+}
+
 struct CheckEnv {
     double q0x, q0y, q0h, cg, sg, xmin, xmax, ymin, ymax, maxc, step;
     const double4 *aabb; const double2 *verts; const uint8_t *nvp; int nobs;
 };
 
+// Does the vehicle box at local-frame pose (lx, ly, lyaw) leave the map or touch an obstacle edge?
 __device__ __forceinline__ bool sample_hits(const CheckEnv &E, const hope_params &par, double lx, double ly, double lyaw) {
     double gx = E.cg * lx + E.sg * ly + E.q0x, gy = -E.sg * lx + E.cg * ly + E.q0y;  // reeds_shepp.py:47-48
     double gyaw = pi_2_pi(lyaw + E.q0h);                                             // :49
@@ -864,22 +950,24 @@ __device__ __forceinline__ bool sample_hits(const CheckEnv &E, const hope_params
         double2 p1 = __ldg(E.verts + ob * MAXV);
         for (int j = 0; j < nv; ++j) {
             double2 p2 = __ldg(E.verts + ob * MAXV + ((j + 1 == nv) ? 0 : j + 1));
-            const double oxmax = dmax(p1.x, p2.x), oxmin = dmin(p1.x, p2.x), oymax = dmax(p1.y, p2.y), oymin = dmin(p1.y, p2.y);
-            if (!(vxmax < oxmin || oxmax < vxmin || vymax < oymin || oymax < vymin)) {
+            // obstacle edge box vs vehicle box, tested corner-wise (no min/max needed to reject)
+            if (!((p1.x < vxmin && p2.x < vxmin) || (p1.x > vxmax && p2.x > vxmax) ||
+                  (p1.y < vymin && p2.y < vymin) || (p1.y > vymax && p2.y > vymax))) {
+                const double oxmax = dmax(p1.x, p2.x), oxmin = dmin(p1.x, p2.x), oymax = dmax(p1.y, p2.y), oymin = dmin(p1.y, p2.y);
                 const double dd = p2.y - p1.y, ee = p1.x - p2.x, ff = p1.y * p2.x - p1.x * p2.y;  // :504-506
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int q2 = (q + 1) & 3;
                     const double vx1 = bx[q], vy1 = by[q], vx2 = bx[q2], vy2 = by[q2];
-                    const double exmax = dmax(vx1, vx2), exmin = dmin(vx1, vx2), eymax = dmax(vy1, vy2), eymin = dmin(vy1, vy2);
-                    if (exmax < oxmin || oxmax < exmin || eymax < oymin || oymax < eymin) continue;
+                    if ((vx1 < oxmin && vx2 < oxmin) || (vx1 > oxmax && vx2 > oxmax) ||
+                        (vy1 < oymin && vy2 < oymin) || (vy1 > oymax && vy2 > oymax)) continue;
                     const double a = vy2 - vy1, b = vx1 - vx2, c = vy1 * vx2 - vx1 * vy2;  // :477-479
                     const double det = a * ee - b * dd;                                    // :509
                     if (det == 0.0) continue;
                     double rx, ry;
                     div_pair(b * ff - c * ee, c * dd - a * ff, det, rx, ry);               // :512-513
-                    const bool okx = !(rx > oxmax) && !(rx < oxmin) && !(rx > exmax) && !(rx < exmin);
-                    const bool oky = !(ry > oymax) && !(ry < oymin) && !(ry > eymax) && !(ry < eymin);
+                    const bool okx = !(rx > oxmax) && !(rx < oxmin) && !(rx > dmax(vx1, vx2)) && !(rx < dmin(vx1, vx2));
+                    const bool oky = !(ry > oymax) && !(ry < oymin) && !(ry > dmax(vy1, vy2)) && !(ry < dmin(vy1, vy2));
                     if (okx && oky) return true;
                 }
             }
@@ -889,6 +977,8 @@ __device__ __forceinline__ bool sample_hits(const CheckEnv &E, const hope_params
     return false;
 }
 
+// Evaluate the up-to RS_STRIDE samples each lane owns in the current chunk of word slot `s`.
+// Returns true (warp-uniform) if any sample leaves the map or touches an obstacle edge.
 __device__ bool chunk_is_bad(const WordSlot &s, const CheckEnv &E, const hope_params &par, int lane) {
     uint8_t code = s.st_code[lane];
     double pd = s.st_pd[lane];
@@ -909,7 +999,7 @@ __device__ bool chunk_is_bad(const WordSlot &s, const CheckEnv &E, const hope_pa
                 if (lx != 0.0) nonzero_bits |= 1u << r;
                 else if (hit) { zero_hits |= 1u << r; hit = false; }
             }
-            walker_next(s, E.step, code, pd);
+            walker_next(s.len, s.n, E.step, code, pd);
         }
         if (__any_sync(HOPE_FULL_MASK, hit)) return true;
     }
@@ -927,111 +1017,67 @@ __device__ bool chunk_is_bad(const WordSlot &s, const CheckEnv &E, const hope_pa
     return false;
 }
 
-// lane-private: replay up to RS_CHUNK samples of this slot's chain, saving a state every RS_STRIDE.
-// Inside a segment the step is the bare `pd += d; |pd| <= |l|` of the reference; everything else
-// (origin, segment changes, end point) goes through walker_next.
-__device__ void walk_chunk(WordSlot &s, double step, int chunk_base) {
-    uint8_t code = s.resume_code;
-    double pd = s.resume_pd;
-    int k = 0, cur = -1;
-    double d = 0.0, al = 0.0;
-    if (code < HOPE_RS_MAX_SEG) { cur = code; const double l = s.len[code]; al = fabs(l); d = l > 0.0 ? step : -step; }
-    while (k < RS_CHUNK && code != RS_DONE) {
-        s.st_code[k / RS_STRIDE] = code; s.st_pd[k / RS_STRIDE] = pd;
-        int i = 0;
-        while (i < RS_STRIDE && code != RS_DONE) {
-            if (code == cur) {
-                while (i < RS_STRIDE) {
-                    const double nx = pd + d;           // reeds_shepp.py:492
-                    if (!(fabs(nx) <= al)) break;       // :488
-                    pd = nx; ++i;
-                }
-                if (i == RS_STRIDE) break;
-            }
-            walker_next(s, step, code, pd);
-            ++i;
-            if (code < HOPE_RS_MAX_SEG) { cur = code; const double l = s.len[code]; al = fabs(l); d = l > 0.0 ? step : -step; }
-            else cur = -1;
+constexpr int CHK_WARPS = 4;  // warps per block of k_rs_check
+
+__global__ void __launch_bounds__(CHK_WARPS * 32, 4) k_rs_check(Pool pool, EnvState st, Tables tb, RsScratch rs, hope_params par) {
+    __shared__ WordSlot smem[CHK_WARPS];
+    const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_items = *rs.n_items;
+    const int warps_total = gridDim.x * CHK_WARPS;
+    WordSlot &s = smem[warp_in_block];
+    for (int item = blockIdx.x * CHK_WARPS + warp_in_block; item < n_items; item += warps_total) {
+        const int env = rs.items[item] >> 4;
+        {   // stage the word's plan: coalesced 64-bit copies
+            const unsigned long long *src = reinterpret_cast<const unsigned long long *>(rs.slots + item);
+            unsigned long long *dst = reinterpret_cast<unsigned long long *>(&s);
+            for (int q = lane; q < (int)(sizeof(WordSlot) / 8); q += 32) dst[q] = src[q];
         }
-        k += i;
+        const int sid = st.scene[env];
+        const double *meta = pool.meta + (size_t)sid * META;
+        CheckEnv E;
+        E.q0x = st.pose[3 * env]; E.q0y = st.pose[3 * env + 1]; E.q0h = st.pose[3 * env + 2];
+        E.cg = st.cs[2 * env]; E.sg = -st.cs[2 * env + 1];  // cos(-h), sin(-h)  (reeds_shepp.py:47-48)
+        E.xmin = meta[M_BOUNDS]; E.xmax = meta[M_BOUNDS + 1]; E.ymin = meta[M_BOUNDS + 2]; E.ymax = meta[M_BOUNDS + 3];
+        E.maxc = tb.maxc; E.step = par.rs_step * tb.maxc;
+        E.nobs = pool.nobs[sid];
+        E.aabb = reinterpret_cast<const double4 *>(pool.aabb) + (size_t)sid * MAXO;
+        E.verts = reinterpret_cast<const double2 *>(pool.obs) + (size_t)sid * MAXE;
+        E.nvp = pool.nv + (size_t)sid * MAXO;
+        __syncwarp();
+        bool bad = false;
+        int chunk_base = 0;
+        for (;;) {
+            bad = chunk_is_bad(s, E, par, lane);
+            if (bad || s.total >= 0) break;
+            chunk_base += RS_CHUNK;  // a word longer than one chunk (rare): lane 0 walks on
+            __syncwarp();
+            if (lane == 0) walk_chunk(s, s.len, E.step, chunk_base);
+            __syncwarp();
+        }
+        if (lane == 0) rs.item_bad[item] = bad ? 1 : 0;
+        __syncwarp();
     }
-    for (int j = (k + RS_STRIDE - 1) / RS_STRIDE; j < 32; ++j) s.st_code[j] = RS_DONE;
-    s.resume_code = code; s.resume_pd = pd;
-    s.total = (code == RS_DONE) ? chunk_base + k : -1;
 }
 
-__global__ void __launch_bounds__(64, 8) k_rs_check(int n, Pool pool, EnvState st, Tables tb, RsScratch rs, hope_params par, hope_out out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int env = blockIdx.x * (blockDim.x >> 5) + warp_in_block;
-    if (env >= n) return;
-    const int ntry = rs.ntry[env];
-    if (ntry == 0) return;  // outputs already cleared by k_rs_enumerate (gate closed or no word)
-    CheckSmem &sm = reinterpret_cast<CheckSmem *>(smem_raw)[warp_in_block];
-    const int sid = st.scene[env];
-    const double *meta = pool.meta + (size_t)sid * META;
-    CheckEnv E;
-    E.q0x = st.pose[3 * env]; E.q0y = st.pose[3 * env + 1]; E.q0h = st.pose[3 * env + 2];
-    sincos(-E.q0h, &E.sg, &E.cg);  // reeds_shepp.py:47-48
-    E.xmin = meta[M_BOUNDS]; E.xmax = meta[M_BOUNDS + 1]; E.ymin = meta[M_BOUNDS + 2]; E.ymax = meta[M_BOUNDS + 3];
-    E.maxc = tb.maxc; E.step = par.rs_step * tb.maxc;
-    E.nobs = pool.nobs[sid];
-    E.aabb = reinterpret_cast<const double4 *>(pool.aabb) + (size_t)sid * MAXO;
-    E.verts = reinterpret_cast<const double2 *>(pool.obs) + (size_t)sid * MAXE;
-    E.nvp = pool.nv + (size_t)sid * MAXO;
-
-    int found = -1, tried = 0;
-    for (int batch = 0; batch < ntry && found < 0; batch += RS_WB) {
-        const int nb = min(RS_WB, ntry - batch);
-        // ---- lane w = word (batch + w): lengths, segment origins, first chunk of the chain ------------
-        if (lane < nb) {
-            const RsWord w = rs.words[(size_t)env * MAXW + batch + lane];
-            WordSlot &s = sm.slot[lane];
-            uint32_t ty = 0;
-            for (int k = 0; k < HOPE_RS_MAX_SEG; ++k) { s.len[k] = w.len[k]; ty |= (uint32_t)(w.types[k] & 0xF) << (4 * k); }
-            s.types = ty; s.n = w.n;
-            double org[5] = {0.0, 0.0, 0.0, 1.0, 0.0};
-            for (int k = 0; k < w.n; ++k) {
-                for (int q = 0; q < 5; ++q) s.org[k][q] = org[q];
-                double ex, ey, eyaw;
-                rs_interp(w.len[k], w.types[k], E.maxc, org, ex, ey, eyaw);  // end of segment k = origin of k+1
-                org[0] = ex; org[1] = ey;
-                if (eyaw != org[2]) { org[2] = eyaw; sincos(eyaw, &org[4], &org[3]); }
-            }
-            s.end_lx = org[0];
-            s.resume_code = RS_ORIGIN; s.resume_pd = 0.0;
-            walk_chunk(s, E.step, 0);
-        }
-        __syncwarp();
-        // ---- words in try order; the whole warp samples one word at a time ----------------------------
-        for (int wl = 0; wl < nb && found < 0; ++wl) {
-            WordSlot &s = sm.slot[wl];
-            ++tried;
-            bool bad = false;
-            int chunk_base = 0;
-            for (;;) {
-                bad = chunk_is_bad(s, E, par, lane);
-                if (bad || s.total >= 0) break;
-                chunk_base += RS_CHUNK;  // a word longer than one chunk: its owner lane walks on
-                __syncwarp();
-                if (lane == wl) walk_chunk(s, E.step, chunk_base);
-                __syncwarp();
-            }
-            if (!bad) found = batch + wl;
-        }
-        __syncwarp();
-    }
-    if (lane == 0) {
-        if (out.rs_ntried) out.rs_ntried[env] = (uint8_t)tried;
-        if (found >= 0) {
-            const RsWord w = rs.words[(size_t)env * MAXW + found];
-            if (out.rs_found) out.rs_found[env] = 1;
-            if (out.rs_nseg) out.rs_nseg[env] = w.n;
-            if (out.rs_L) out.rs_L[env] = w.L / E.maxc;
-            for (int k = 0; k < 5; ++k) {
-                if (out.rs_types) out.rs_types[5 * env + k] = k < w.n ? w.types[k] : HOPE_RS_NONE;
-                if (out.rs_lengths) out.rs_lengths[5 * env + k] = k < w.n ? w.len[k] / E.maxc : 0.0;  // reeds_shepp.py:51
-            }
+__global__ void __launch_bounds__(128) k_rs_select(int n, Tables tb, RsScratch rs, hope_out out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int ntry = rs.ntry[i];
+    if (ntry == 0) return;  // outputs already cleared by k_rs_enumerate
+    const int base = rs.item_base[i];
+    int found = -1;
+    for (int k = 0; k < ntry; ++k)
+        if (!rs.item_bad[base + k]) { found = k; break; }
+    // words the reference would have sampled: everything up to and including the winner (car_parking_base.py:438-449)
+    if (out.rs_ntried) out.rs_ntried[i] = (uint8_t)(found >= 0 ? found + 1 : ntry);
+    if (found >= 0) {
+        const RsWord w = rs.words[(size_t)i * MAXW + found];
+        if (out.rs_found) out.rs_found[i] = 1;
+        if (out.rs_nseg) out.rs_nseg[i] = w.n;
+        if (out.rs_L) out.rs_L[i] = w.L / tb.maxc;
+        for (int k = 0; k < 5; ++k) {
+            if (out.rs_types) out.rs_types[5 * i + k] = k < w.n ? w.types[k] : HOPE_RS_NONE;
+            if (out.rs_lengths) out.rs_lengths[5 * i + k] = k < w.n ? w.len[k] / tb.maxc : 0.0;  // reeds_shepp.py:51
         }
     }
 }
@@ -1083,7 +1129,10 @@ struct hope_ctx {
     unsigned long long *d_counters = nullptr;
     // RS scratch
     RsWord *d_words = nullptr;
-    uint8_t *d_ntry = nullptr, *d_ncand = nullptr;
+    uint8_t *d_ntry = nullptr, *d_ncand = nullptr, *d_item_bad = nullptr;
+    int *d_item_base = nullptr, *d_items = nullptr, *d_n_items = nullptr;
+    WordSlot *d_slots = nullptr;
+    int sm_count = 148, walk_blocks = 148 * 4, check_blocks = 148 * 4;
     // host-API staging
     double *d_action = nullptr;
     void *d_stage = nullptr;
@@ -1120,9 +1169,11 @@ Tables make_tables(const hope_ctx *c) {
     tb.maxc = c->maxc;
     return tb;
 }
-RsScratch make_rs(const hope_ctx *c) { return RsScratch{c->d_words, c->d_ntry, c->d_ncand}; }
+RsScratch make_rs(const hope_ctx *c) {
+    return RsScratch{c->d_words, c->d_ntry, c->d_ncand, c->d_item_base, c->d_items, c->d_item_bad, c->d_slots, c->d_n_items};
+}
 
-constexpr int ADV_THREADS = 128, OBS_THREADS = 64, ENUM_THREADS = 128, CHK_THREADS = 64;
+constexpr int ADV_THREADS = 128, OBS_THREADS = 64, ENUM_THREADS = 128;
 
 void prof_mark(hope_ctx *ctx, int which, cudaStream_t s) {
     if (!ctx->profile) return;
@@ -1166,13 +1217,16 @@ int launch_step(hope_ctx *ctx, const double *d_action, const hope_out &out, unsi
     if (stages & HOPE_STAGE_RS) {
         RsScratch rs = make_rs(ctx);
         prof_mark(ctx, 2, s);
+        CK(cudaMemsetAsync(ctx->d_n_items, 0, sizeof(int), s));
         k_rs_enumerate<<<(n + ENUM_THREADS - 1) / ENUM_THREADS, ENUM_THREADS, 0, s>>>(n, pool, st, tb, rs, out);
         prof_mark(ctx, 2, s);
-        const int wpb = CHK_THREADS / 32;
         prof_mark(ctx, 3, s);
-        k_rs_check<<<(n + wpb - 1) / wpb, CHK_THREADS, wpb * sizeof(CheckSmem), s>>>(n, pool, st, tb, rs, ctx->par, out);
+        // persistent grids: the item count only exists on the device, so both kernels stride over it
+        k_rs_walk<<<ctx->walk_blocks, 128, 0, s>>>(rs, tb, ctx->par);
+        k_rs_check<<<ctx->check_blocks, CHK_WARPS * 32, 0, s>>>(pool, st, tb, rs, ctx->par);
+        k_rs_select<<<(n + 127) / 128, 128, 0, s>>>(n, tb, rs, out);
         prof_mark(ctx, 3, s);
-        ctx->launches += 2;
+        ctx->launches += 4;
     }
     if (fork) CK(cudaStreamWaitEvent(s, ctx->ev_observed, 0));
     CK(cudaGetLastError());
@@ -1293,11 +1347,24 @@ int hope_create(hope_ctx **out, int device, int n_envs, int pool_size, const hop
     CK(cudaMalloc(&ctx->d_words, sizeof(RsWord) * N * MAXW));
     CK(cudaMalloc(&ctx->d_ntry, N));
     CK(cudaMalloc(&ctx->d_ncand, N));
+    CK(cudaMalloc(&ctx->d_item_base, sizeof(int) * N));
+    CK(cudaMalloc(&ctx->d_items, sizeof(int) * N * MAXW));
+    CK(cudaMalloc(&ctx->d_item_bad, N * MAXW));
+    CK(cudaMalloc(&ctx->d_slots, sizeof(WordSlot) * N * MAXW));
+    CK(cudaMalloc(&ctx->d_n_items, sizeof(int)));
+    CK(cudaMemset(ctx->d_n_items, 0, sizeof(int)));
+    { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) ctx->sm_count = v; }
+    {   // persistent grids = exactly the number of co-resident blocks (multiples of the SM count)
+        int nb = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_rs_walk, 128, 0));
+        ctx->walk_blocks = ctx->sm_count * (nb > 0 ? nb : 1);
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_rs_check, CHK_WARPS * 32, 0));
+        ctx->check_blocks = ctx->sm_count * (nb > 0 ? nb : 1);
+    }
     CK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ctx->ev_advanced, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_observed, cudaEventDisableTiming));
     CK(cudaFuncSetAttribute(k_observe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((OBS_THREADS / 32) * sizeof(ObserveSmem))));
-    CK(cudaFuncSetAttribute(k_rs_check, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((CHK_THREADS / 32) * sizeof(CheckSmem))));
     return HOPE_OK;
 }
 
@@ -1305,7 +1372,7 @@ int hope_destroy(hope_ctx *ctx) {
     if (!ctx) return HOPE_ERR_INVALID;
     cudaSetDevice(ctx->device);
     void *ptrs[] = {ctx->d_obs, ctx->d_aabb, ctx->d_meta, ctx->d_nv, ctx->d_nobs, ctx->d_tab, ctx->d_pose, ctx->d_accum, ctx->d_t,
-                    ctx->d_scene, ctx->d_pending, ctx->d_gate, ctx->d_counters, ctx->d_words, ctx->d_ntry, ctx->d_ncand, ctx->d_cs,
+                    ctx->d_scene, ctx->d_pending, ctx->d_gate, ctx->d_counters, ctx->d_words, ctx->d_ntry, ctx->d_ncand, ctx->d_cs, ctx->d_item_base, ctx->d_items, ctx->d_item_bad, ctx->d_slots, ctx->d_n_items,
                     ctx->d_action, ctx->d_stage};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
