@@ -44,6 +44,22 @@ ALGO_BYTES = {
 CPU_SAMPLE_ENVS, CPU_SAMPLE_STEPS = 4096, 8
 
 
+def scene_seed(rank):
+    """scene id -> GPU: rank r generates its own pool of the global synthetic scene set."""
+    return 42 + 7919 * rank
+
+
+def reduce_scalar(x, op, world, device):
+    """max / sum of a python float over ranks (the only collectives of the env path)."""
+    if world == 1:
+        return x
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM)
+    return float(t.item())
+
+
 def _dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
@@ -165,7 +181,7 @@ def main():
     dev = torch.device("cuda", local_rank)
 
     # scene id -> GPU: rank r owns scenes [r*2n, (r+1)*2n) of the global synthetic pool
-    scenes = generate_scenes(2 * n, "mix", 42 + 7919 * rank)
+    scenes = generate_scenes(2 * n, "mix", scene_seed(rank))
     env = BatchedParkingEnv(n, scenes=scenes, device=local_rank, auto_reset=True)
     env.reset()
     gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
@@ -177,18 +193,10 @@ def main():
         torch.cuda.synchronize()
 
     def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return reduce_scalar(x, "max", world, dev)
 
     def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        return reduce_scalar(x, "sum", world, dev)
 
     # ---- device-resident timing ----------------------------------------------------------------
     for k in range(W):

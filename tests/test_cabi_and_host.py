@@ -1,0 +1,131 @@
+"""CPU tests of the product's host side: the C ABI library loads and exports every symbol the
+header declares (no compute calls without a GPU), struct layouts match, the host scene generator
+and the constant tables behave, and the product never imports the oracle."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header():
+    return open(os.path.join(ROOT, "include", "hope_b200.h")).read()
+
+
+def test_library_exports_every_declared_symbol():
+    from hope_b200 import capi
+    lib = capi.load_library()
+    declared = set(re.findall(r"\b(hope_[a-z_0-9]+)\s*\(", _header()))
+    assert len(declared) >= 18
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/hope_b200.h but not exported"
+    assert lib.hope_version() >= 100
+    assert lib.hope_strerror(0) == b"ok" and b"invalid" in lib.hope_strerror(-1)
+
+
+def test_ctypes_structs_match_the_header():
+    from hope_b200 import capi
+    h = _header()
+    out_body = h[h.index("typedef struct hope_out {"):h.index("} hope_out;")]
+    members = re.findall(r"\*(\w+);", out_body)
+    assert members == [name for name, _, _ in capi.OUT_FIELDS]
+    assert C.sizeof(capi.Out) == 8 * len(members)
+    p = capi.Params()
+    capi.check(capi.load_library().hope_default_params(C.byref(p)))
+    # configs.py:13-38, 95-104, 180-187
+    assert (p.wheel_base, p.num_step, p.step_length, p.mini_iter) == (2.8, 10, 0.05, 20)
+    assert list(p.box_x) == [-0.93, 0.96 + 2.8, 0.96 + 2.8, -0.93] and list(p.box_y) == [-0.97, -0.97, 0.97, 0.97]
+    assert list(p.reward_weight) == [1, 0, 5, 0, 10] and p.reward_ratio == 0.1
+    assert (p.lidar_range, p.tolerant_time, p.rs_max_dist, p.env_collide, p.auto_reset) == (10.0, 200, 10.0, 0, 1)
+
+
+def test_invalid_arguments_are_reported_not_crashed():
+    from hope_b200 import capi
+    lib = capi.load_library()
+    assert lib.hope_create(None, 0, 16, 16, None) == -1
+    ctx = C.c_void_p()
+    assert lib.hope_create(C.byref(ctx), 0, 0, 16, None) == -1
+    assert lib.hope_destroy(None) == -1
+    assert lib.hope_generate_scenes(0, 0, 1, 1, None, None, None, None, None, None) == -1
+    with pytest.raises(capi.HopeError):
+        capi.check(-3)
+
+
+def test_env_refuses_to_run_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from hope_b200 import capi
+    from hope_b200.batched_env import BatchedParkingEnv
+    with pytest.raises(capi.HopeError):
+        BatchedParkingEnv(8)
+
+
+@pytest.mark.parametrize("level", ["Normal", "Complex", "Extrem"])
+def test_generated_scenes_are_valid_and_deterministic(level):
+    """parking_map_normal.py:40-494 semantics: start/dest boxes touch nothing, gaps in budget,
+    bounds = floor/ceil of the poses -/+ 10; same seed -> same scenes for any thread count."""
+    from hope_b200.batched_env import generate_scenes
+    from oracle import geom
+    n = 200
+    a = generate_scenes(n, level, 123, nthreads=1)
+    b = generate_scenes(n, level, 123, nthreads=5)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    box = np.array([(-0.93, -0.97), (3.76, -0.97), (3.76, 0.97), (-0.93, 0.97)])
+
+    def ring(pose):
+        c, s = np.cos(pose[2]), np.sin(pose[2])
+        pts = [(c * x - s * y + pose[0], s * x + c * y + pose[1]) for x, y in box]
+        return pts + [pts[0]]
+
+    nobs = (a["nverts"] > 0).sum(axis=1)
+    assert 3 <= nobs.min() and nobs.max() <= 16
+    if level == "Extrem":
+        assert (a["case_id"] == 1).all()
+    else:
+        assert 0.3 < (a["case_id"] == 0).mean() < 0.7
+    for i in range(n):
+        srt, dst = ring(a["start"][i]), ring(a["dest"][i])
+        assert not geom.rings_intersect(srt, dst)
+        for k in range(16):
+            nv = a["nverts"][i, k]
+            if nv == 0:
+                continue
+            ob = [tuple(p) for p in a["obs"][i, k, :nv]]
+            ob.append(ob[0])
+            assert not geom.rings_intersect(srt, ob), (i, k)
+            assert not geom.rings_intersect(dst, ob), (i, k)
+        lo = np.minimum(a["start"][i, :2], a["dest"][i, :2]); hi = np.maximum(a["start"][i, :2], a["dest"][i, :2])
+        assert np.array_equal(a["bounds"][i], [np.floor(lo[0] - 10), np.ceil(hi[0] + 10), np.floor(lo[1] - 10), np.ceil(hi[1] + 10)])
+
+
+def test_product_tables_equal_reference_tables_bit_for_bit(golden_dir):
+    import hashlib
+    from hope_b200 import tables
+    g = np.load(os.path.join(golden_dir, "mask_table.npz"))
+    t = tables.host_tables()
+    assert np.array_equal(t["mask_base"], g["vehicle_lidar_base"])
+    assert np.array_equal(t["lidar_base"], g["vehicle_boundary"])
+    assert np.array_equal(tables.discrete_actions(), g["discrete_actions"])
+    assert hashlib.sha256(t["dist_star"].tobytes()).digest() == g["dist_star_sha256"].tobytes()
+    theta = np.array([i * np.pi / 120 * 2 for i in range(120)])
+    assert np.array_equal(t["ray_a"], np.sin(theta)) and np.array_equal(t["ray_b"], -np.cos(theta))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "hope_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert "parking_oracle" not in src, f
+    code = "import sys; import hope_b200, hope_b200.batched_env, hope_b200.tables; print(any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules))"
+    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, check=True).stdout.strip()
+    assert out == "False"
