@@ -153,6 +153,38 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_rollout(args, rank, local_rank, world, dev):
+    """BASELINE cfg 4: PPO acting loop, 65 536 envs x K steps: state norm -> transformer policy (bf16 autocast,
+    tensor-core GEMMs through stock PyTorch) -> masked discrete sampling -> RS plan hand-off -> env step."""
+    import torch
+    from hope_b200 import rollout
+    from hope_b200.batched_env import BatchedParkingEnv, generate_scenes
+    n, K, W = args.envs, args.steps, max(3, args.warmup)
+    env = BatchedParkingEnv(n, scenes=generate_scenes(2 * n, "mix", scene_seed(rank)), device=local_rank, auto_reset=True)
+    actor = rollout.ReferenceShapedActor().to(dev)
+    eng = rollout.RolloutEngine(env, actor, seed=rank)
+    eng.collect(W)
+    torch.cuda.synchronize()
+    c0 = env.counters()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    eng.collect(K)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = reduce_scalar(e0.elapsed_time(e1), "max", world, dev)
+    c1 = env.counters()
+    steps = reduce_scalar(float(c1["env_steps"] - c0["env_steps"]), "sum", world, dev)
+    if rank == 0:
+        print(json.dumps({
+            "metric": "env-steps/sec", "value": steps / (ms * 1e-3), "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 env / bf16 policy",
+            "data": "synthetic", "gpu_launches": c1["kernel_launches"] - c0["kernel_launches"],
+            "config": {"workload": "cfg4: PPO rollout, 65536 envs/GPU, transformer policy forward + masked sampling + RS plan hand-off + full env step",
+                       "envs_per_gpu": n, "policy": "ReferenceShapedActor (MultiObsEmbedding shapes, 3 modalities), random init",
+                       "policy_params": sum(p.numel() for p in actor.parameters())}}))
+    env.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -161,6 +193,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="scenes per GPU (default: the BASELINE cfg-3 size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="step", choices=["step", "rollout"],
+                    help="step: BASELINE cfg 3 (default, the headline metric); rollout: cfg 4, PPO acting loop with the transformer policy")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -179,6 +213,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n, K, W = args.envs, args.steps, max(3, args.warmup)
     dev = torch.device("cuda", local_rank)
+    if args.config == "rollout":
+        return run_rollout(args, rank, local_rank, world, dev)
 
     # scene id -> GPU: rank r owns scenes [r*2n, (r+1)*2n) of the global synthetic pool
     scenes = generate_scenes(2 * n, "mix", scene_seed(rank))

@@ -182,6 +182,21 @@ class BatchedParkingEnv(object):
         names = ("env_steps", "auto_resets", "exact_orient_fallbacks", "rs_capacity_overflows", "rs_zero_length_words", "kernel_launches")
         return {k: int(buf[i]) for i, k in enumerate(names)}
 
+    # ---- batched RsPlanner hand-off (parking_agent.py:2-47) ----------------------------------------
+    def planner_actions(self, policy_actions, step_ratio=1.25):
+        """Replace the policy's action by the RS plan's next open-loop action where a plan is being
+        executed.  Uses the outputs of the previous step; returns (actions, executing) device tensors."""
+        t = self.torch
+        if not hasattr(self, "_plan_action"):
+            self._plan_action = t.zeros((self.n, 2), dtype=t.float64, device=self.device)
+            self._plan_exec = t.zeros(self.n, dtype=t.uint8, device=self.device)
+        capi.check(self.lib.hope_planner_actions(self.ctx, policy_actions.data_ptr(), C.byref(self._out_struct), self._plan_action.data_ptr(),
+                                                 self._plan_exec.data_ptr(), float(step_ratio), self._stream()), self.ctx)
+        return self._plan_action, self._plan_exec
+
+    def planner_reset(self):
+        capi.check(self.lib.hope_planner_reset(self.ctx, self._stream()), self.ctx)
+
     KERNELS = ("k_advance", "k_observe", "k_rs_enumerate", "k_rs_check")
 
     def profile(self, on=True):

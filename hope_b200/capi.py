@@ -74,6 +74,8 @@ def load_library():
         "hope_set_state": (C.c_int, [vp, dp, ip, dp]),
         "hope_get_counters": (C.c_int, [vp, C.POINTER(u64 * 8)]),
         "hope_n_envs": (C.c_int, [vp]),
+        "hope_planner_actions": (C.c_int, [vp, dp, C.POINTER(Out), dp, vp, C.c_double, vp]),
+        "hope_planner_reset": (C.c_int, [vp, vp]),
         "hope_profile_enable": (C.c_int, [vp, i32]),
         "hope_profile_read": (C.c_int, [vp, C.POINTER(C.c_double * 4), C.POINTER(u64 * 4)]),
     }

@@ -1082,6 +1082,78 @@ __global__ void __launch_bounds__(128) k_rs_select(int n, Tables tb, RsScratch r
     }
 }
 
+// =============================================================================================
+// k_planner: one thread per env.  RsPlanner.set_rs_path / get_action evaluated lazily.
+// =============================================================================================
+struct PlanState {
+    double *rem;       // [N][5] remaining signed length of each segment in policy units (length / step_ratio)
+    uint8_t *types;    // [N][5]
+    uint8_t *big;      // [N]    bit k: segment k started with |a| > 1 (its remainder rule differs, parking_agent.py:26-37)
+    uint8_t *n;        // [N]    segments
+    uint8_t *seg;      // [N]    current segment
+    uint8_t *active;   // [N]    planner.route is not None
+};
+
+// next action of the filtered list, or false when the list is exhausted.  `commit` = pop it.
+__device__ __forceinline__ bool plan_next(double *rem, const uint8_t *types, unsigned big, int n, int &seg, bool commit, double &steer, double &speed) {
+    double local[HOPE_RS_MAX_SEG];
+    if (!commit) for (int k = 0; k < HOPE_RS_MAX_SEG; ++k) local[k] = rem[k];
+    double *r = commit ? rem : local;
+    while (seg < n) {
+        const double a = r[seg];
+        const int t = types[seg];
+        steer = t == HOPE_RS_L ? 1.0 : (t == HOPE_RS_R ? -1.0 : 0.0);  // action_type {'L':1,'S':0,'R':-1}
+        if (!((big >> seg) & 1)) {  // |a| <= 1 from the start: one action if 1e-3 < |a| < 1, else nothing (|a| == 1 is dropped, sic)
+            ++seg;
+            if (fabs(a) < 1.0 && fabs(a) > 1e-3) { speed = a; return true; }
+        } else if (a > 1.0) { r[seg] = a - 1.0; speed = 1.0; return true; }
+        else if (a < -1.0) { r[seg] = a + 1.0; speed = -1.0; return true; }
+        else {  // remainder of a long segment
+            ++seg;
+            if (fabs(a) > 1e-3) { speed = a; return true; }
+        }
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(128) k_planner(int n, PlanState ps, const double *__restrict__ policy_action, hope_out last,
+                                                 double *__restrict__ action_out, uint8_t *__restrict__ executing, double step_ratio) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bool active = ps.active[i] != 0;
+    const bool ended = (last.done && last.done[i]) || (last.was_reset && last.was_reset[i]);
+    if (ended) active = false;  // ParkingAgent.reset at the start of the next episode (parking_agent.py:60-62)
+    else if (!active && last.rs_found && last.rs_found[i]) {  // set_planner_path: only when no route is being executed (:64-68)
+        const int nseg = last.rs_nseg[i];
+        unsigned big = 0;
+        for (int k = 0; k < HOPE_RS_MAX_SEG; ++k) {
+            const double a = k < nseg ? last.rs_lengths[5 * i + k] / step_ratio : 0.0;  // :16-17
+            ps.rem[5 * i + k] = a;
+            ps.types[5 * i + k] = k < nseg ? last.rs_types[5 * i + k] : HOPE_RS_NONE;
+            if (fabs(a) > 1.0) big |= 1u << k;
+        }
+        ps.big[i] = (uint8_t)big; ps.n[i] = (uint8_t)nseg; ps.seg[i] = 0;
+        active = true;
+    }
+    double steer = policy_action[2 * i], speed = policy_action[2 * i + 1];
+    bool from_plan = false;
+    if (active) {
+        int seg = ps.seg[i];
+        double ps_steer, ps_speed;
+        if (plan_next(ps.rem + 5 * i, ps.types + 5 * i, ps.big[i], ps.n[i], seg, true, ps_steer, ps_speed)) {
+            steer = ps_steer; speed = ps_speed; from_plan = true;
+            int peek = seg;
+            double d0, d1;
+            // RsPlanner.get_action: the route is dropped as soon as its last action is popped (:42-46)
+            if (!plan_next(ps.rem + 5 * i, ps.types + 5 * i, ps.big[i], ps.n[i], peek, false, d0, d1)) active = false;
+        } else active = false;  // empty filtered list (the reference would raise IndexError on pop)
+        ps.seg[i] = (uint8_t)seg;
+    }
+    ps.active[i] = active ? 1 : 0;
+    action_out[2 * i] = steer; action_out[2 * i + 1] = speed;
+    if (executing) executing[i] = from_plan ? 1 : 0;
+}
+
 // small helpers -------------------------------------------------------------------------------
 __global__ void k_table_reduce(const double *__restrict__ dist_star, double *__restrict__ pmaxk, double *__restrict__ pmax) {
     // one block per upsampled ray: pmaxk[rho][k][j] = max_{k'<=k} dist_star[rho][j][k'], pmax[rho] = max_j pmaxk[rho][9][j]
@@ -1132,6 +1204,8 @@ struct hope_ctx {
     uint8_t *d_ntry = nullptr, *d_ncand = nullptr, *d_item_bad = nullptr;
     int *d_item_base = nullptr, *d_items = nullptr, *d_n_items = nullptr;
     WordSlot *d_slots = nullptr;
+    double *d_plan_rem = nullptr;
+    uint8_t *d_plan_u8 = nullptr;  // types[N][5] | big[N] | n[N] | seg[N] | active[N]
     int sm_count = 148, walk_blocks = 148 * 4, check_blocks = 148 * 4;
     // host-API staging
     double *d_action = nullptr;
@@ -1352,6 +1426,9 @@ int hope_create(hope_ctx **out, int device, int n_envs, int pool_size, const hop
     CK(cudaMalloc(&ctx->d_item_bad, N * MAXW));
     CK(cudaMalloc(&ctx->d_slots, sizeof(WordSlot) * N * MAXW));
     CK(cudaMalloc(&ctx->d_n_items, sizeof(int)));
+    CK(cudaMalloc(&ctx->d_plan_rem, sizeof(double) * 5 * N));
+    CK(cudaMalloc(&ctx->d_plan_u8, 9 * N));
+    CK(cudaMemset(ctx->d_plan_u8, 0, 9 * N));
     CK(cudaMemset(ctx->d_n_items, 0, sizeof(int)));
     { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) ctx->sm_count = v; }
     {   // persistent grids = exactly the number of co-resident blocks (multiples of the SM count)
@@ -1372,7 +1449,7 @@ int hope_destroy(hope_ctx *ctx) {
     if (!ctx) return HOPE_ERR_INVALID;
     cudaSetDevice(ctx->device);
     void *ptrs[] = {ctx->d_obs, ctx->d_aabb, ctx->d_meta, ctx->d_nv, ctx->d_nobs, ctx->d_tab, ctx->d_pose, ctx->d_accum, ctx->d_t,
-                    ctx->d_scene, ctx->d_pending, ctx->d_gate, ctx->d_counters, ctx->d_words, ctx->d_ntry, ctx->d_ncand, ctx->d_cs, ctx->d_item_base, ctx->d_items, ctx->d_item_bad, ctx->d_slots, ctx->d_n_items,
+                    ctx->d_scene, ctx->d_pending, ctx->d_gate, ctx->d_counters, ctx->d_words, ctx->d_ntry, ctx->d_ncand, ctx->d_cs, ctx->d_item_base, ctx->d_items, ctx->d_item_bad, ctx->d_slots, ctx->d_n_items, ctx->d_plan_rem, ctx->d_plan_u8,
                     ctx->d_action, ctx->d_stage};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -1545,6 +1622,27 @@ int hope_set_state(hope_ctx *ctx, const double *h_pose, const int32_t *h_t, cons
     if (h_t) CK(cudaMemcpy(ctx->d_t, h_t, sizeof(int) * ctx->n, cudaMemcpyHostToDevice));
     if (h_accum) CK(cudaMemcpy(ctx->d_accum, h_accum, sizeof(double) * ctx->n, cudaMemcpyHostToDevice));
     CK(cudaMemset(ctx->d_pending, 0, ctx->n));
+    return HOPE_OK;
+}
+
+int hope_planner_actions(hope_ctx *ctx, const double *d_policy_action, const hope_out *d_last_out, double *d_action_out,
+                         uint8_t *d_executing, double step_ratio, void *stream) {
+    if (!ctx || !d_policy_action || !d_last_out || !d_action_out || !(step_ratio > 0)) return HOPE_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    const size_t N = ctx->n;
+    uint8_t *u = ctx->d_plan_u8;
+    PlanState ps{ctx->d_plan_rem, u, u + 5 * N, u + 6 * N, u + 7 * N, u + 8 * N};
+    k_planner<<<(ctx->n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(ctx->n, ps, d_policy_action, *d_last_out, d_action_out,
+                                                                                     d_executing, step_ratio);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return HOPE_OK;
+}
+
+int hope_planner_reset(hope_ctx *ctx, void *stream) {
+    if (!ctx) return HOPE_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemsetAsync(ctx->d_plan_u8, 0, 9 * (size_t)ctx->n, static_cast<cudaStream_t>(stream)));
     return HOPE_OK;
 }
 

@@ -144,6 +144,17 @@ int hope_step_kinematics_collision(hope_ctx *ctx, const double *d_action, double
 int hope_step_host(hope_ctx *ctx, const double *h_action, const hope_host_out *h_out, unsigned stages);
 int hope_reset_host(hope_ctx *ctx, const int32_t *h_scene_ids, const hope_host_out *h_out);
 
+/* Batched RsPlanner + ParkingAgent hand-off (model/agent/parking_agent.py:2-47, 64-70, 93-110;
+ * train_HOPE_sac.py:194-213).  Call once per rollout step BEFORE hope_step, with the outputs of the
+ * previous step: an env whose last step ended (done / was_reset) drops its plan; an env without a plan
+ * whose last step found a path (rs_found) takes it; an env with a plan gets the plan's next open-loop
+ * action ([steer in {+1,0,-1}, signed length / step_ratio split into pieces of at most 1]) instead of
+ * the policy's.  d_action_out[n][2] is what to pass to hope_step; d_executing[n] = 1 where it came from
+ * the plan.  step_ratio = step_len * n_step * VALID_SPEED[1] = 1.25 (train_HOPE_sac.py:164). */
+int hope_planner_actions(hope_ctx *ctx, const double *d_policy_action, const hope_out *d_last_out, double *d_action_out,
+                         uint8_t *d_executing, double step_ratio, void *stream);
+int hope_planner_reset(hope_ctx *ctx, void *stream);
+
 /* State access (device -> host copies; synchronous). */
 int hope_get_state(hope_ctx *ctx, double *h_pose, int32_t *h_t, double *h_accum, int32_t *h_scene_id);
 int hope_set_state(hope_ctx *ctx, const double *h_pose, const int32_t *h_t, const double *h_accum);
