@@ -15,7 +15,6 @@ import math
 
 import torch
 from torch import nn
-import torch.nn.functional as F
 
 from . import tables
 
@@ -92,7 +91,9 @@ class ReferenceShapedActor(nn.Module):
         x = torch.stack([self.embed_lidar(obs["lidar"]), self.embed_tgt(obs["target"]), self.embed_am(obs["action_mask"])], dim=1)
         b, n, _ = x.shape
         q, k, v = self.to_qkv(self.norm1(x)).view(b, n, 3, self.heads, self.dim_head).permute(2, 0, 3, 1, 4)
-        a = F.scaled_dot_product_attention(q, k, v)
+        # 3 tokens per env: explicit softmax(q k^T / sqrt(d)) v like attention.py:33-46 (the fused SDPA back ends
+        # reject a 65 536 x 8-head batch of 3-token sequences)
+        a = torch.matmul(torch.softmax(torch.matmul(q, k.transpose(-1, -2)) * (self.dim_head ** -0.5), dim=-1), v)
         x = self.to_out(a.transpose(1, 2).reshape(b, n, self.heads * self.dim_head)) + x
         x = self.ff(self.norm2(x)) + x
         return torch.tanh(self.head(x.reshape(b, n * x.shape[-1])))
