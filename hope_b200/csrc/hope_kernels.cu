@@ -51,6 +51,7 @@ struct Tables {
     const double *dist_star;  // [1200][42][10]
     const double *pmaxk;      // [1200][10][42] running max over k of dist_star, action index contiguous
     const double *pmax;       // [1200]       max_{j,k} dist_star
+    const double *gpmax;      // [120]        max of pmax over the 10 upsampled rays of a beam
     const double *w_lo, *w_hi;
     double maxc;
 };
@@ -423,30 +424,54 @@ __global__ void __launch_bounds__(64) k_observe(int n, Pool pool, EnvState st, T
     // stored doubles exactly, so the integers equal the reference's full 1200x42x10 sweep.
     int s0 = NITER, s1 = NITER;  // lane owns actions lane and lane+32
     const bool has2 = lane < NACT - 32;
-    for (int base = 0; base < NUP; base += 32) {
-        int rho = base + lane;
-        bool in = rho < NUP;
-        int qd = in ? rho / 10 : 0, r = in ? rho - qd * 10 : 0;
-        int qn = (qd + 1 == NRAY) ? 0 : qd + 1;
-        double d = sm.L[qd] * tb.w_lo[r] + sm.L[qn] * tb.w_hi[r];  // action_mask.py:158-162
-        unsigned act = __ballot_sync(HOPE_FULL_MASK, in && d < __ldg(tb.pmax + (in ? rho : 0)));
-        while (act) {
-            int bsel = __ffs(act) - 1;
-            act &= act - 1;
-            const double db = __shfl_sync(HOPE_FULL_MASK, d, bsel);
-            const double *P = tb.pmaxk + (size_t)(base + bsel) * NITER * NACT;  // [k][j], j contiguous
-            // every lane fetches the running maxima of its action(s) below its current bound in one batch of
-            // independent, coalesced loads (row k is 42 contiguous doubles), then finds the first exceedance
-            double v0[NITER], v1[NITER];
+    // Screen 1, per lidar beam q: the 10 upsampled rays 10q..10q+9 interpolate L[q] and L[q+1] with weights that
+    // sum to 1 within one rounding, so each d is >= min(L[q], L[q+1]) (1 - 5e-16).  If that minimum, shrunk by
+    // 1e-15, still reaches gpmax[q] = max of pmax over the group, none of the 10 rays can lower any action.
+    unsigned gmask[4];
 #pragma unroll
-            for (int k = 0; k < NITER; ++k) {
-                v0[k] = (k < s0) ? __ldg(P + k * NACT + lane) : INFINITY;
-                v1[k] = (has2 && k < s1) ? __ldg(P + k * NACT + 32 + lane) : INFINITY;
-            }
+    for (int w = 0; w < 4; ++w) {
+        const int q = w * 32 + lane;
+        bool on = false;
+        if (q < NRAY) {
+            const double m = dmin(sm.L[q], sm.L[(q + 1 == NRAY) ? 0 : q + 1]);
+            on = m * (1.0 - 1e-15) < __ldg(tb.gpmax + q);
+        }
+        gmask[w] = __ballot_sync(HOPE_FULL_MASK, on);
+    }
+    // Screen 2, per upsampled ray of an active beam (three beams = 30 lanes per pass): d_rho < pmax[rho]
 #pragma unroll
-            for (int k = NITER - 1; k >= 0; --k) {
-                if (db < v0[k]) s0 = min(s0, k);
-                if (db < v1[k]) s1 = min(s1, k);
+    for (int w = 0; w < 4; ++w) {
+        unsigned gm = gmask[w];
+        while (gm) {
+            int g[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { g[c] = gm ? (w * 32 + __ffs(gm) - 1) : -1; gm &= gm - 1; }
+            const int sub = lane / 10, r = lane - sub * 10;
+            const int qd = sub < 3 ? g[sub] : -1;
+            const bool in = qd >= 0;
+            const int rho = in ? qd * 10 + r : 0;
+            const int qn = (qd + 1 == NRAY) ? 0 : qd + 1;
+            const double d = in ? sm.L[qd] * tb.w_lo[r] + sm.L[qn] * tb.w_hi[r] : 0.0;  // action_mask.py:158-162
+            unsigned act = __ballot_sync(HOPE_FULL_MASK, in && d < __ldg(tb.pmax + rho));
+            while (act) {
+                const int bsel = __ffs(act) - 1;
+                act &= act - 1;
+                const double db = __shfl_sync(HOPE_FULL_MASK, d, bsel);
+                const int rb = __shfl_sync(HOPE_FULL_MASK, rho, bsel);
+                const double *P = tb.pmaxk + (size_t)rb * NITER * NACT;  // [k][j], j contiguous
+                // every lane fetches the running maxima of its action(s) below its current bound in one batch of
+                // independent, coalesced loads (row k is 42 contiguous doubles), then finds the first exceedance
+                double v0[NITER], v1[NITER];
+#pragma unroll
+                for (int k = 0; k < NITER; ++k) {
+                    v0[k] = (k < s0) ? __ldg(P + k * NACT + lane) : INFINITY;
+                    v1[k] = (has2 && k < s1) ? __ldg(P + k * NACT + 32 + lane) : INFINITY;
+                }
+#pragma unroll
+                for (int k = NITER - 1; k >= 0; --k) {
+                    if (db < v0[k]) s0 = min(s0, k);
+                    if (db < v1[k]) s1 = min(s1, k);
+                }
             }
         }
     }
@@ -1176,6 +1201,14 @@ __global__ void k_table_reduce(const double *__restrict__ dist_star, double *__r
     }
 }
 
+__global__ void k_table_group(const double *__restrict__ pmax, double *__restrict__ gpmax) {
+    int q = threadIdx.x;
+    if (q >= NRAY) return;
+    double m = pmax[q * 10];
+    for (int r = 1; r < 10; ++r) m = fmax(m, pmax[q * 10 + r]);
+    gpmax[q] = m;
+}
+
 }  // namespace hope
 
 // =============================================================================================
@@ -1239,7 +1272,7 @@ Tables make_tables(const hope_ctx *c) {
     const double *t = c->d_tab;
     Tables tb;
     tb.ray_a = t; tb.ray_b = t + 120; tb.lidar_base = t + 240; tb.mask_base = t + 360; tb.w_lo = t + 480; tb.w_hi = t + 496;
-    tb.dist_star = t + 512; tb.pmaxk = tb.dist_star + (size_t)NUP * NACT * NITER; tb.pmax = tb.pmaxk + (size_t)NUP * NACT * NITER;
+    tb.dist_star = t + 512; tb.pmaxk = tb.dist_star + (size_t)NUP * NACT * NITER; tb.pmax = tb.pmaxk + (size_t)NUP * NACT * NITER; tb.gpmax = tb.pmax + NUP;
     tb.maxc = c->maxc;
     return tb;
 }
@@ -1405,7 +1438,7 @@ int hope_create(hope_ctx **out, int device, int n_envs, int pool_size, const hop
     CK(cudaMalloc(&ctx->d_nobs, sizeof(int) * P));
     CK(cudaMemset(ctx->d_nv, 0, P * MAXO));
     CK(cudaMemset(ctx->d_nobs, 0, sizeof(int) * P));
-    const size_t tab = 512 + 2 * (size_t)NUP * NACT * NITER + NUP;
+    const size_t tab = 512 + 2 * (size_t)NUP * NACT * NITER + NUP + NRAY;
     CK(cudaMalloc(&ctx->d_tab, sizeof(double) * tab));
     CK(cudaMalloc(&ctx->d_pose, sizeof(double) * 3 * N));
     CK(cudaMalloc(&ctx->d_accum, sizeof(double) * N));
@@ -1472,6 +1505,7 @@ int hope_upload_tables(hope_ctx *ctx, const double *ray_a, const double *ray_b, 
     CK(cudaMemcpy(ds, dist_star, sizeof(double) * NUP * NACT * NITER, cudaMemcpyHostToDevice));
     double *pmaxk = ds + (size_t)NUP * NACT * NITER, *pmax = pmaxk + (size_t)NUP * NACT * NITER;
     k_table_reduce<<<NUP, 64>>>(ds, pmaxk, pmax);
+    k_table_group<<<1, 128>>>(pmax, pmax + NUP);
     ctx->launches++;
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
