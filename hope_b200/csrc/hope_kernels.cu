@@ -162,7 +162,7 @@ __device__ __forceinline__ double angle_gap(double a1, double a2) {  // car_park
 }
 
 __global__ void __launch_bounds__(128) k_advance(int n, Pool pool, EnvState st, const double *__restrict__ action,
-                                                 hope_params par, hope_out out, int reset_all) {
+                                                 hope_params par, hope_out out, int reset_all, int reset_stride) {
     __shared__ AdvanceSmem smem[4];
     const int lane = threadIdx.x & 31;
     AdvanceSmem &sm = smem[threadIdx.x >> 5];
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(128) k_advance(int n, Pool pool, EnvState st, 
     const bool pending = st.pending[i] != 0;
     const bool is_reset = reset_all || pending || action == nullptr;
     if (pending && !reset_all) {  // auto-reset: next scene of the pool for this slot
-        sid = (sid + n) % pool.size;
+        sid = (sid + reset_stride) % pool.size;  // env slot i cycles through scenes i, i+N, i+2N, ... of the pool
         if (valid) st.scene[i] = sid;
     }
     const double *meta = pool.meta + (size_t)sid * META;
@@ -1246,8 +1246,12 @@ struct hope_ctx {
     size_t stage_bytes = 0;
     hope_out stage_out;
     cudaStream_t own_stream = nullptr;
-    cudaStream_t aux_stream = nullptr;        // k_observe runs here, concurrently with the Reeds-Shepp kernels
-    cudaEvent_t ev_advanced = nullptr, ev_observed = nullptr;
+    // a "lane" = the stream pair one env range is stepped on: k_observe goes to `aux`, concurrently with the
+    // Reeds-Shepp kernels on `main`.  Lane 0's main stream is replaced by the caller's in the device API; the
+    // host API pipelines env ranges over all lanes so one range's D2H copies hide under the next one's kernels.
+    static constexpr int MAX_LANES = 4;
+    struct Lane { cudaStream_t main = nullptr, aux = nullptr; cudaEvent_t ev_advanced = nullptr, ev_observed = nullptr; } lanes[MAX_LANES];
+    int host_chunks = 4;
     unsigned long long launches = 0;
     bool profile = false;
     std::vector<cudaEvent_t> prof_events[4];  // begin/end pairs per kernel
@@ -1267,7 +1271,6 @@ int fail(hope_ctx *c, cudaError_t e, const char *what) {
     } while (0)
 
 Pool make_pool(const hope_ctx *c) { return Pool{c->d_obs, c->d_nv, c->d_aabb, c->d_meta, c->d_nobs, c->pool}; }
-EnvState make_state(const hope_ctx *c) { return EnvState{c->d_pose, c->d_cs, c->d_t, c->d_accum, c->d_scene, c->d_pending, c->d_gate, c->d_counters}; }
 Tables make_tables(const hope_ctx *c) {
     const double *t = c->d_tab;
     Tables tb;
@@ -1276,10 +1279,6 @@ Tables make_tables(const hope_ctx *c) {
     tb.maxc = c->maxc;
     return tb;
 }
-RsScratch make_rs(const hope_ctx *c) {
-    return RsScratch{c->d_words, c->d_ntry, c->d_ncand, c->d_item_base, c->d_items, c->d_item_bad, c->d_slots, c->d_n_items};
-}
-
 constexpr int ADV_THREADS = 128, OBS_THREADS = 64, ENUM_THREADS = 128;
 
 void prof_mark(hope_ctx *ctx, int which, cudaStream_t s) {
@@ -1290,56 +1289,10 @@ void prof_mark(hope_ctx *ctx, int which, cudaStream_t s) {
     ctx->prof_events[which].push_back(e);
 }
 
-int copy_fields(hope_ctx *ctx, const hope_host_out *h_out, int observe, cudaStream_t s);
-
 // Kernel order of one step.  k_observe and the Reeds-Shepp pair both depend only on k_advance, so when
 // both stages are requested k_observe goes to the context's auxiliary stream and overlaps the RS kernels;
 // the caller's stream waits for it before hope_step returns control of the stream.  With `early_out`
 // (host API) the observation buffers are copied to the host right behind k_observe, under the RS kernels.
-int launch_step(hope_ctx *ctx, const double *d_action, const hope_out &out, unsigned stages, int reset_all, cudaStream_t s,
-                const hope_host_out *early_out = nullptr) {
-    const int n = ctx->n;
-    Pool pool = make_pool(ctx);
-    EnvState st = make_state(ctx);
-    Tables tb = make_tables(ctx);
-    prof_mark(ctx, 0, s);
-    k_advance<<<(n + ADV_THREADS - 1) / ADV_THREADS, ADV_THREADS, 0, s>>>(n, pool, st, d_action, ctx->par, out, reset_all);
-    prof_mark(ctx, 0, s);
-    ctx->launches++;
-    const bool fork = (stages & HOPE_STAGE_OBSERVE) && (stages & HOPE_STAGE_RS);
-    cudaStream_t so = fork ? ctx->aux_stream : s;
-    if (stages & HOPE_STAGE_OBSERVE) {
-        if (fork) {
-            CK(cudaEventRecord(ctx->ev_advanced, s));
-            CK(cudaStreamWaitEvent(so, ctx->ev_advanced, 0));
-        }
-        const int wpb = OBS_THREADS / 32;
-        prof_mark(ctx, 1, so);
-        k_observe<<<(n + wpb - 1) / wpb, OBS_THREADS, wpb * sizeof(ObserveSmem), so>>>(n, pool, st, tb, ctx->par, out);
-        prof_mark(ctx, 1, so);
-        ctx->launches++;
-        if (early_out) { int rc = copy_fields(ctx, early_out, 1, so); if (rc) return rc; }
-        if (fork) CK(cudaEventRecord(ctx->ev_observed, so));
-    }
-    if (stages & HOPE_STAGE_RS) {
-        RsScratch rs = make_rs(ctx);
-        prof_mark(ctx, 2, s);
-        CK(cudaMemsetAsync(ctx->d_n_items, 0, sizeof(int), s));
-        k_rs_enumerate<<<(n + ENUM_THREADS - 1) / ENUM_THREADS, ENUM_THREADS, 0, s>>>(n, pool, st, tb, rs, out);
-        prof_mark(ctx, 2, s);
-        prof_mark(ctx, 3, s);
-        // persistent grids: the item count only exists on the device, so both kernels stride over it
-        k_rs_walk<<<ctx->walk_blocks, 128, 0, s>>>(rs, tb, ctx->par);
-        k_rs_check<<<ctx->check_blocks, CHK_WARPS * 32, 0, s>>>(pool, st, tb, rs, ctx->par);
-        k_rs_select<<<(n + 127) / 128, 128, 0, s>>>(n, tb, rs, out);
-        prof_mark(ctx, 3, s);
-        ctx->launches += 4;
-    }
-    if (fork) CK(cudaStreamWaitEvent(s, ctx->ev_observed, 0));
-    CK(cudaGetLastError());
-    return HOPE_OK;
-}
-
 struct OutField { size_t offset; size_t elem; int per_env; int observe; };  // observe = 1: produced by k_observe
 #define OF(member, type, per) OutField{offsetof(hope_out, member), sizeof(type), per, 0}
 #define OFO(member, type, per) OutField{offsetof(hope_out, member), sizeof(type), per, 1}
@@ -1353,6 +1306,85 @@ constexpr int kNumOutFields = sizeof(kOutFields) / sizeof(kOutFields[0]);
 
 void *&field_ptr(hope_out &o, const OutField &f) { return *reinterpret_cast<void **>(reinterpret_cast<char *>(&o) + f.offset); }
 void *field_ptr_c(const hope_out &o, const OutField &f) { return *reinterpret_cast<void *const *>(reinterpret_cast<const char *>(&o) + f.offset); }
+
+hope_out offset_out(const hope_out &o, size_t lo) {  // the same arrays, starting at env `lo`
+    hope_out r = o;
+    for (int k = 0; k < kNumOutFields; ++k) {
+        void *p = field_ptr_c(o, kOutFields[k]);
+        if (p) field_ptr(r, kOutFields[k]) = static_cast<char *>(p) + lo * kOutFields[k].per_env * kOutFields[k].elem;
+    }
+    return r;
+}
+
+// observe: 1 = only k_observe's outputs, 0 = only the others, -1 = all; envs [lo, lo+cnt)
+int copy_fields(hope_ctx *ctx, const hope_host_out *h_out, int observe, cudaStream_t s, size_t lo, size_t cnt) {
+    for (int k = 0; k < kNumOutFields; ++k) {
+        void *dst = field_ptr_c(*h_out, kOutFields[k]);
+        if (!dst || (observe >= 0 && kOutFields[k].observe != observe)) continue;
+        const size_t row = kOutFields[k].elem * kOutFields[k].per_env;
+        CK(cudaMemcpyAsync(static_cast<char *>(dst) + lo * row, static_cast<const char *>(field_ptr_c(ctx->stage_out, kOutFields[k])) + lo * row,
+                           row * cnt, cudaMemcpyDeviceToHost, s));
+    }
+    return HOPE_OK;
+}
+
+// Kernel order of one step over envs [lo, lo+cnt).  k_observe and the Reeds-Shepp kernels both depend only on
+// k_advance, so when both stages are requested k_observe goes to the lane's auxiliary stream and overlaps the RS
+// kernels; the main stream waits for it at the end.  With `early_out` (host API) the observation buffers are
+// copied to the host right behind k_observe, under the RS kernels.
+int launch_range(hope_ctx *ctx, const double *d_action, const hope_out &out_all, unsigned stages, int reset_all, cudaStream_t s,
+                 int lane_id, int chunk_id, int lo, int cnt, const hope_host_out *early_out = nullptr) {
+    const int n = cnt;
+    hope_ctx::Lane &lane = ctx->lanes[lane_id];
+    Pool pool = make_pool(ctx);
+    Tables tb = make_tables(ctx);
+    EnvState st{ctx->d_pose + 3 * (size_t)lo, ctx->d_cs + 2 * (size_t)lo, ctx->d_t + lo, ctx->d_accum + lo, ctx->d_scene + lo,
+                ctx->d_pending + lo, ctx->d_gate + lo, ctx->d_counters};
+    const hope_out out = offset_out(out_all, lo);
+    const double *act = d_action ? d_action + 2 * (size_t)lo : nullptr;
+    prof_mark(ctx, 0, s);
+    k_advance<<<(n + ADV_THREADS - 1) / ADV_THREADS, ADV_THREADS, 0, s>>>(n, pool, st, act, ctx->par, out, reset_all, ctx->n);
+    prof_mark(ctx, 0, s);
+    ctx->launches++;
+    const bool fork = (stages & HOPE_STAGE_OBSERVE) && (stages & HOPE_STAGE_RS);
+    cudaStream_t so = fork ? lane.aux : s;
+    if (stages & HOPE_STAGE_OBSERVE) {
+        if (fork) {
+            CK(cudaEventRecord(lane.ev_advanced, s));
+            CK(cudaStreamWaitEvent(so, lane.ev_advanced, 0));
+        }
+        const int wpb = OBS_THREADS / 32;
+        prof_mark(ctx, 1, so);
+        k_observe<<<(n + wpb - 1) / wpb, OBS_THREADS, wpb * sizeof(ObserveSmem), so>>>(n, pool, st, tb, ctx->par, out);
+        prof_mark(ctx, 1, so);
+        ctx->launches++;
+        if (early_out) { int rc = copy_fields(ctx, early_out, 1, so, lo, cnt); if (rc) return rc; }
+        if (fork) CK(cudaEventRecord(lane.ev_observed, so));
+    }
+    if (stages & HOPE_STAGE_RS) {
+        const size_t wo = (size_t)lo * MAXW;
+        RsScratch rs{ctx->d_words + wo, ctx->d_ntry + lo, ctx->d_ncand + lo, ctx->d_item_base + lo, ctx->d_items + wo,
+                     ctx->d_item_bad + wo, ctx->d_slots + wo, ctx->d_n_items + chunk_id};
+        prof_mark(ctx, 2, s);
+        CK(cudaMemsetAsync(rs.n_items, 0, sizeof(int), s));
+        k_rs_enumerate<<<(n + ENUM_THREADS - 1) / ENUM_THREADS, ENUM_THREADS, 0, s>>>(n, pool, st, tb, rs, out);
+        prof_mark(ctx, 2, s);
+        prof_mark(ctx, 3, s);
+        // persistent grids: the item count only exists on the device, so both kernels stride over it
+        k_rs_walk<<<ctx->walk_blocks, 128, 0, s>>>(rs, tb, ctx->par);
+        k_rs_check<<<ctx->check_blocks, CHK_WARPS * 32, 0, s>>>(pool, st, tb, rs, ctx->par);
+        k_rs_select<<<(n + 127) / 128, 128, 0, s>>>(n, tb, rs, out);
+        prof_mark(ctx, 3, s);
+        ctx->launches += 4;
+    }
+    if (fork) CK(cudaStreamWaitEvent(s, lane.ev_observed, 0));
+    CK(cudaGetLastError());
+    return HOPE_OK;
+}
+
+int launch_step(hope_ctx *ctx, const double *d_action, const hope_out &out, unsigned stages, int reset_all, cudaStream_t s) {
+    return launch_range(ctx, d_action, out, stages, reset_all, s, 0, 0, 0, ctx->n);
+}
 
 int ensure_stage(hope_ctx *ctx) {
     if (ctx->d_stage) return HOPE_OK;
@@ -1368,17 +1400,6 @@ int ensure_stage(hope_ctx *ctx) {
     }
     CK(cudaMalloc(&ctx->d_action, sizeof(double) * 2 * ctx->n));
     CK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
-    return HOPE_OK;
-}
-
-// observe: 1 = only k_observe's outputs, 0 = only the others, -1 = all
-int copy_fields(hope_ctx *ctx, const hope_host_out *h_out, int observe, cudaStream_t s) {
-    for (int k = 0; k < kNumOutFields; ++k) {
-        void *dst = field_ptr_c(*h_out, kOutFields[k]);
-        if (!dst || (observe >= 0 && kOutFields[k].observe != observe)) continue;
-        CK(cudaMemcpyAsync(dst, field_ptr_c(ctx->stage_out, kOutFields[k]), kOutFields[k].elem * kOutFields[k].per_env * ctx->n,
-                           cudaMemcpyDeviceToHost, s));
-    }
     return HOPE_OK;
 }
 
@@ -1458,11 +1479,11 @@ int hope_create(hope_ctx **out, int device, int n_envs, int pool_size, const hop
     CK(cudaMalloc(&ctx->d_items, sizeof(int) * N * MAXW));
     CK(cudaMalloc(&ctx->d_item_bad, N * MAXW));
     CK(cudaMalloc(&ctx->d_slots, sizeof(WordSlot) * N * MAXW));
-    CK(cudaMalloc(&ctx->d_n_items, sizeof(int)));
+    CK(cudaMalloc(&ctx->d_n_items, sizeof(int) * 64));
     CK(cudaMalloc(&ctx->d_plan_rem, sizeof(double) * 5 * N));
     CK(cudaMalloc(&ctx->d_plan_u8, 9 * N));
     CK(cudaMemset(ctx->d_plan_u8, 0, 9 * N));
-    CK(cudaMemset(ctx->d_n_items, 0, sizeof(int)));
+    CK(cudaMemset(ctx->d_n_items, 0, sizeof(int) * 64));
     { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) ctx->sm_count = v; }
     {   // persistent grids = exactly the number of co-resident blocks (multiples of the SM count)
         int nb = 0;
@@ -1471,9 +1492,13 @@ int hope_create(hope_ctx **out, int device, int n_envs, int pool_size, const hop
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_rs_check, CHK_WARPS * 32, 0));
         ctx->check_blocks = ctx->sm_count * (nb > 0 ? nb : 1);
     }
-    CK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&ctx->ev_advanced, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&ctx->ev_observed, cudaEventDisableTiming));
+    for (auto &ln : ctx->lanes) {
+        CK(cudaStreamCreateWithFlags(&ln.main, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ln.aux, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ln.ev_advanced, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ln.ev_observed, cudaEventDisableTiming));
+    }
+    if (const char *e = getenv("HOPE_B200_HOST_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->host_chunks = v; }
     CK(cudaFuncSetAttribute(k_observe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((OBS_THREADS / 32) * sizeof(ObserveSmem))));
     return HOPE_OK;
 }
@@ -1486,9 +1511,12 @@ int hope_destroy(hope_ctx *ctx) {
                     ctx->d_action, ctx->d_stage};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
-    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
-    if (ctx->ev_advanced) cudaEventDestroy(ctx->ev_advanced);
-    if (ctx->ev_observed) cudaEventDestroy(ctx->ev_observed);
+    for (auto &ln : ctx->lanes) {
+        if (ln.main) cudaStreamDestroy(ln.main);
+        if (ln.aux) cudaStreamDestroy(ln.aux);
+        if (ln.ev_advanced) cudaEventDestroy(ln.ev_advanced);
+        if (ln.ev_observed) cudaEventDestroy(ln.ev_observed);
+    }
     delete ctx;
     return HOPE_OK;
 }
@@ -1612,15 +1640,27 @@ int hope_step_host(hope_ctx *ctx, const double *h_action, const hope_host_out *h
     CK(cudaSetDevice(ctx->device));
     int rc = ensure_stage(ctx);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(ctx->d_action, h_action, sizeof(double) * 2 * ctx->n, cudaMemcpyHostToDevice, ctx->own_stream));
     stages |= HOPE_STAGE_ADVANCE;
     const bool fork = (stages & HOPE_STAGE_OBSERVE) && (stages & HOPE_STAGE_RS);
-    // with both stages on, the observation buffers leave for the host behind k_observe while the RS kernels run
-    rc = launch_step(ctx, ctx->d_action, ctx->stage_out, stages, 0, ctx->own_stream, fork ? h_out : nullptr);
-    if (rc) return rc;
-    rc = copy_fields(ctx, h_out, fork ? 0 : -1, ctx->own_stream);
-    if (rc) return rc;
-    CK(cudaStreamSynchronize(ctx->own_stream));
+    // Software pipeline over env ranges: range c runs on lane c % MAX_LANES (its own stream pair), so its D2H
+    // copies travel while the next range's kernels execute.  Envs are independent, so the split changes nothing.
+    const int n = ctx->n;
+    int chunks = ctx->host_chunks;
+    if (n < 4096 * chunks) chunks = n / 4096 > 0 ? n / 4096 : 1;
+    const int per = ((n + chunks - 1) / chunks + 127) / 128 * 128;
+    int used = 0;
+    for (int c = 0, lo = 0; lo < n; ++c, lo += per) {
+        const int cnt = (lo + per <= n) ? per : n - lo;
+        const int li = c % hope_ctx::MAX_LANES;
+        cudaStream_t s = ctx->lanes[li].main;
+        CK(cudaMemcpyAsync(ctx->d_action + 2 * (size_t)lo, h_action + 2 * (size_t)lo, sizeof(double) * 2 * cnt, cudaMemcpyHostToDevice, s));
+        rc = launch_range(ctx, ctx->d_action, ctx->stage_out, stages, 0, s, li, c, lo, cnt, fork ? h_out : nullptr);
+        if (rc) return rc;
+        rc = copy_fields(ctx, h_out, fork ? 0 : -1, s, lo, cnt);
+        if (rc) return rc;
+        used = c + 1;
+    }
+    for (int li = 0; li < hope_ctx::MAX_LANES && li < used; ++li) CK(cudaStreamSynchronize(ctx->lanes[li].main));
     return HOPE_OK;
 }
 
@@ -1631,7 +1671,7 @@ int hope_reset_host(hope_ctx *ctx, const int32_t *h_scene_ids, const hope_host_o
     if (rc) return rc;
     rc = hope_reset(ctx, h_scene_ids, &ctx->stage_out, ctx->own_stream);
     if (rc) return rc;
-    rc = copy_fields(ctx, h_out, -1, ctx->own_stream);
+    rc = copy_fields(ctx, h_out, -1, ctx->own_stream, 0, ctx->n);
     if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->own_stream));
     return HOPE_OK;

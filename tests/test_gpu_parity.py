@@ -194,19 +194,25 @@ def test_full_step_mixed_levels_vs_oracle():
     env.close()
 
 
-def test_host_buffer_api_matches_device_api():
-    sc = generate_scenes(512, "Complex", 3)
-    a = BatchedParkingEnv(512, scenes=sc, auto_reset=False)
-    b = BatchedParkingEnv(512, scenes=sc, auto_reset=False)
+@pytest.mark.parametrize("n", [512, 20000])
+def test_host_buffer_api_matches_device_api(n):
+    """hope_step_host pipelines env ranges over several stream pairs (4 ranges at n = 20 000); the result must be
+    the same arrays the one-launch device path produces."""
+    sc = generate_scenes(n, "Complex", 3)
+    a = BatchedParkingEnv(n, scenes=sc, auto_reset=True)
+    b = BatchedParkingEnv(n, scenes=sc, auto_reset=True)
     a.reset(); b.reset_host()
     rng = np.random.default_rng(5)
     for _ in range(5):
-        act = rng.uniform(-1, 1, size=(512, 2))
+        act = rng.uniform(-1, 1, size=(n, 2))
         a.step(torch.as_tensor(act, device=a.device).contiguous())
         h = b.step_host(act)
         d = gather(a)
-        for k in ("lidar", "mask", "target", "reward", "status", "rs_found", "rs_lengths"):
+        for k in ("lidar", "mask", "target", "reward", "status", "done", "reward_info", "rs_found", "rs_nseg", "rs_types", "rs_lengths"):
             assert np.array_equal(d[k], h[k]), k
+    sa, sb = a.get_state(), b.get_state()
+    for k in sa:
+        assert np.array_equal(sa[k], sb[k]), k
     a.close(); b.close()
 
 
