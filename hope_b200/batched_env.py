@@ -42,7 +42,10 @@ def generate_scenes(n, level="Normal", seed=42, nthreads=0):
 
 class BatchedParkingEnv(object):
     def __init__(self, n_envs, scenes=None, pool_size=None, level="Normal", seed=42, device=0, auto_reset=True,
-                 params=None):
+                 params=None, device_scenes=False):
+        """scenes: dict of host arrays (start/dest/bounds/obs/nverts) to upload as the pool; None -> generate
+        `pool_size` (default 2 n) scenes of `level` on the host, or with device_scenes=True on the GPU
+        (then finished envs also get a fresh device-generated scene instead of cycling the pool)."""
         import torch
         if not torch.cuda.is_available():
             raise capi.HopeError("BatchedParkingEnv needs a CUDA device; there is no CPU path")
@@ -50,14 +53,18 @@ class BatchedParkingEnv(object):
         self.lib = capi.load_library()
         self.n = int(n_envs)
         self.device = torch.device("cuda", device)
-        if scenes is None:
+        if scenes is None and not device_scenes:
             pool_size = pool_size or 2 * self.n
             scenes = generate_scenes(pool_size, level, seed)
         self.scenes = scenes
-        self.pool_size = int(scenes["start"].shape[0])
+        self.pool_size = int(scenes["start"].shape[0]) if scenes is not None else int(pool_size or self.n)
         self.params = capi.Params()
         capi.check(self.lib.hope_default_params(C.byref(self.params)))
         self.params.auto_reset = 1 if auto_reset else 0
+        if device_scenes:
+            self.params.regen_on_reset = 1
+            self.params.regen_level = -1 if level == "mix" else LEVELS[level]
+            self.params.regen_seed = seed
         for k, v in (params or {}).items():
             setattr(self.params, k, v)
         self.ctx = C.c_void_p()
@@ -65,7 +72,10 @@ class BatchedParkingEnv(object):
         tb = tables.host_tables()
         capi.check(self.lib.hope_upload_tables(self.ctx, *[tb[k].ctypes.data for k in
                                                             ("ray_a", "ray_b", "lidar_base", "mask_base", "dist_star", "w_lo", "w_hi")]), self.ctx)
-        self.set_scene_pool(scenes)
+        if scenes is not None:
+            self.set_scene_pool(scenes)
+        else:
+            self.generate_pool_on_device(0, self.pool_size, level, seed)
         # device outputs (torch owns the memory; the library only sees raw pointers)
         self.out = {}
         self._out_struct = capi.Out()
@@ -83,6 +93,20 @@ class BatchedParkingEnv(object):
         nv = np.ascontiguousarray(scenes["nverts"], dtype=np.int32)
         capi.check(self.lib.hope_set_scene_pool(self.ctx, first, s.shape[0], s.ctypes.data, d.ctypes.data, b.ctypes.data,
                                                 o.ctypes.data, nv.ctypes.data), self.ctx)
+
+    def generate_pool_on_device(self, first, n, level="mix", seed=42):
+        """hope_generate_scene_pool_device: fill pool slots [first, first+n) with scenes generated by GPU threads."""
+        lv = -1 if level == "mix" else LEVELS[level]
+        capi.check(self.lib.hope_generate_scene_pool_device(self.ctx, first, n, lv, seed, self._stream()), self.ctx)
+
+    def get_scene_pool(self, first=0, n=None):
+        """Read pool scenes back to the host (e.g. to hand device-generated scenes to a checker)."""
+        n = self.pool_size - first if n is None else n
+        sc = dict(start=np.zeros((n, 3)), dest=np.zeros((n, 3)), bounds=np.zeros((n, 4)),
+                  obs=np.zeros((n, capi.MAX_OBS, capi.MAX_VERTS, 2)), nverts=np.zeros((n, capi.MAX_OBS), dtype=np.int32))
+        capi.check(self.lib.hope_get_scene_pool(self.ctx, first, n, sc["start"].ctypes.data, sc["dest"].ctypes.data, sc["bounds"].ctypes.data,
+                                                sc["obs"].ctypes.data, sc["nverts"].ctypes.data), self.ctx)
+        return sc
 
     def _stream(self):
         return self.torch.cuda.current_stream(self.device).cuda_stream
@@ -179,7 +203,8 @@ class BatchedParkingEnv(object):
     def counters(self):
         buf = (C.c_uint64 * 8)()
         capi.check(self.lib.hope_get_counters(self.ctx, C.byref(buf)), self.ctx)
-        names = ("env_steps", "auto_resets", "exact_orient_fallbacks", "rs_capacity_overflows", "rs_zero_length_words", "kernel_launches")
+        names = ("env_steps", "auto_resets", "exact_orient_fallbacks", "rs_capacity_overflows", "rs_zero_length_words", "kernel_launches",
+                 "device_scenes_generated")
         return {k: int(buf[i]) for i, k in enumerate(names)}
 
     # ---- batched RsPlanner hand-off (parking_agent.py:2-47) ----------------------------------------

@@ -7,8 +7,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhope_b200.so")
-SOURCES = ["hope_kernels.cu", "scene_gen.cpp"]
-DEPS = SOURCES + ["hope_device.cuh", os.path.join("..", "..", "include", "hope_b200.h")]
+SOURCES = ["hope_kernels.cu", "scene_gen.cu"]
+DEPS = SOURCES + ["hope_device.cuh", "scene_gen.h", os.path.join("..", "..", "include", "hope_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false",  # the reference rounds every product and sum separately (numpy / CPython float64)

@@ -21,7 +21,7 @@ class Params(C.Structure):
         ("step_length", C.c_double), ("mini_iter", C.c_int), ("lidar_range", C.c_double),
         ("tolerant_time", C.c_int), ("rs_max_dist", C.c_double), ("rs_step", C.c_double),
         ("reward_weight", C.c_double * 5), ("reward_ratio", C.c_double), ("env_collide", C.c_int),
-        ("auto_reset", C.c_int)]
+        ("auto_reset", C.c_int), ("regen_on_reset", C.c_int), ("regen_level", C.c_int), ("regen_seed", C.c_uint64)]
 
 
 # name -> (ctype, trailing shape); order must match struct hope_out
@@ -65,6 +65,8 @@ def load_library():
         "hope_upload_tables": (C.c_int, [vp] + [dp] * 7),
         "hope_set_scene_pool": (C.c_int, [vp, i32, i32, dp, dp, dp, dp, ip]),
         "hope_generate_scenes": (C.c_int, [i32, i32, u64, i32, dp, dp, dp, dp, ip, ip]),
+        "hope_generate_scene_pool_device": (C.c_int, [vp, i32, i32, i32, u64, vp]),
+        "hope_get_scene_pool": (C.c_int, [vp, i32, i32, dp, dp, dp, dp, ip]),
         "hope_reset": (C.c_int, [vp, ip, C.POINTER(Out), vp]),
         "hope_step": (C.c_int, [vp, dp, C.POINTER(Out), C.c_uint, vp]),
         "hope_step_kinematics_collision": (C.c_int, [vp, dp, dp, vp, vp, vp]),

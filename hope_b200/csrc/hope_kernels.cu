@@ -22,6 +22,7 @@
 
 #include "../../include/hope_b200.h"
 #include "hope_device.cuh"
+#include "scene_gen.h"
 
 namespace hope {
 
@@ -1179,6 +1180,28 @@ __global__ void __launch_bounds__(128) k_planner(int n, PlanState ps, const doub
     if (executing) executing[i] = from_plan ? 1 : 0;
 }
 
+// envs that finished last step -> dense list of their pool slots (regen_on_reset); bumps the slot's episode counter
+__global__ void __launch_bounds__(128) k_list_pending(int n, const uint8_t *__restrict__ pending, const int *__restrict__ scene,
+                                                      unsigned *__restrict__ episode, int *__restrict__ slots, int *__restrict__ count,
+                                                      unsigned long long *__restrict__ counters) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    const bool p = i < n && pending[i] != 0;
+    const unsigned m = __ballot_sync(HOPE_FULL_MASK, p);
+    int base = 0;
+    if (lane == 0 && m) { base = atomicAdd(count, __popc(m)); atomicAdd(counters + 6, (unsigned long long)__popc(m)); }
+    base = __shfl_sync(HOPE_FULL_MASK, base, 0);
+    if (p) {
+        const int slot = scene[i];
+        episode[slot] += 1;
+        slots[base + __popc(m & ((1u << lane) - 1))] = slot;
+    }
+}
+// pad the rest of the list with -1 so the generator kernel can be launched over all n entries
+__global__ void k_pad_slots(int n, int *__restrict__ slots, const int *__restrict__ count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && i >= *count) slots[i] = -1;
+}
+
 // small helpers -------------------------------------------------------------------------------
 __global__ void k_table_reduce(const double *__restrict__ dist_star, double *__restrict__ pmaxk, double *__restrict__ pmax) {
     // one block per upsampled ray: pmaxk[rho][k][j] = max_{k'<=k} dist_star[rho][j][k'], pmax[rho] = max_j pmaxk[rho][9][j]
@@ -1237,6 +1260,8 @@ struct hope_ctx {
     uint8_t *d_ntry = nullptr, *d_ncand = nullptr, *d_item_bad = nullptr;
     int *d_item_base = nullptr, *d_items = nullptr, *d_n_items = nullptr;
     WordSlot *d_slots = nullptr;
+    int *d_regen_slots = nullptr, *d_regen_count = nullptr, *d_gen_status = nullptr;
+    unsigned *d_episode = nullptr;
     double *d_plan_rem = nullptr;
     uint8_t *d_plan_u8 = nullptr;  // types[N][5] | big[N] | n[N] | seg[N] | active[N]
     int sm_count = 148, walk_blocks = 148 * 4, check_blocks = 148 * 4;
@@ -1342,8 +1367,18 @@ int launch_range(hope_ctx *ctx, const double *d_action, const hope_out &out_all,
                 ctx->d_pending + lo, ctx->d_gate + lo, ctx->d_counters};
     const hope_out out = offset_out(out_all, lo);
     const double *act = d_action ? d_action + 2 * (size_t)lo : nullptr;
+    const bool regen = ctx->par.regen_on_reset && ctx->par.auto_reset && !reset_all;
+    if (regen) {  // fresh scenes for the envs that finished last step, generated in place on the device
+        int *slots = ctx->d_regen_slots + lo, *count = ctx->d_n_items + 32 + chunk_id % 32;
+        CK(cudaMemsetAsync(count, 0, sizeof(int), s));
+        k_list_pending<<<(n + 127) / 128, 128, 0, s>>>(n, st.pending, st.scene, ctx->d_episode, slots, count, ctx->d_counters);
+        k_pad_slots<<<(n + 127) / 128, 128, 0, s>>>(n, slots, count);
+        if (hope_scene::launch_generate(n, 0, ctx->par.regen_level, ctx->par.regen_seed, slots, ctx->d_episode, ctx->par, ctx->d_obs, ctx->d_nv,
+                                        ctx->d_aabb, ctx->d_meta, ctx->d_nobs, ctx->d_gen_status, s) != HOPE_OK) return HOPE_ERR_CUDA;
+        ctx->launches += 3;
+    }
     prof_mark(ctx, 0, s);
-    k_advance<<<(n + ADV_THREADS - 1) / ADV_THREADS, ADV_THREADS, 0, s>>>(n, pool, st, act, ctx->par, out, reset_all, ctx->n);
+    k_advance<<<(n + ADV_THREADS - 1) / ADV_THREADS, ADV_THREADS, 0, s>>>(n, pool, st, act, ctx->par, out, reset_all, regen ? 0 : ctx->n);
     prof_mark(ctx, 0, s);
     ctx->launches++;
     const bool fork = (stages & HOPE_STAGE_OBSERVE) && (stages & HOPE_STAGE_RS);
@@ -1422,6 +1457,7 @@ int hope_default_params(hope_params *p) {
     p->lidar_range = 10.0; p->tolerant_time = 200; p->rs_max_dist = 10.0; p->rs_step = 0.1;
     p->reward_weight[0] = 1; p->reward_weight[1] = 0; p->reward_weight[2] = 5; p->reward_weight[3] = 0; p->reward_weight[4] = 10;
     p->reward_ratio = 0.1; p->env_collide = 0; p->auto_reset = 1;
+    p->regen_on_reset = 0; p->regen_level = -1; p->regen_seed = 20240529;
     return HOPE_OK;
 }
 
@@ -1447,6 +1483,7 @@ int hope_create(hope_ctx **out, int device, int n_envs, int pool_size, const hop
     *out = ctx;
     ctx->device = device; ctx->n = n_envs; ctx->pool = pool_size;
     if (p) ctx->par = *p; else hope_default_params(&ctx->par);
+    if (ctx->par.regen_on_reset && pool_size < n_envs) { ctx->last_error = "regen_on_reset needs pool_size >= n_envs (env i owns slot i)"; return HOPE_ERR_INVALID; }
     if (ctx->par.env_collide) { ctx->last_error = "ENV_COLLIDE=True is not supported (reference default False, configs.py:79)"; return HOPE_ERR_INVALID; }
     memset(&ctx->stage_out, 0, sizeof(ctx->stage_out));
     ctx->maxc = tan(ctx->par.valid_steer[1]) / ctx->par.wheel_base;  // car_parking_base.py:422
@@ -1480,6 +1517,12 @@ int hope_create(hope_ctx **out, int device, int n_envs, int pool_size, const hop
     CK(cudaMalloc(&ctx->d_item_bad, N * MAXW));
     CK(cudaMalloc(&ctx->d_slots, sizeof(WordSlot) * N * MAXW));
     CK(cudaMalloc(&ctx->d_n_items, sizeof(int) * 64));
+    CK(cudaMalloc(&ctx->d_regen_slots, sizeof(int) * N));
+    CK(cudaMalloc(&ctx->d_regen_count, sizeof(int)));
+    CK(cudaMalloc(&ctx->d_gen_status, sizeof(int)));
+    CK(cudaMemset(ctx->d_gen_status, 0, sizeof(int)));
+    CK(cudaMalloc(&ctx->d_episode, sizeof(unsigned) * P));
+    CK(cudaMemset(ctx->d_episode, 0, sizeof(unsigned) * P));
     CK(cudaMalloc(&ctx->d_plan_rem, sizeof(double) * 5 * N));
     CK(cudaMalloc(&ctx->d_plan_u8, 9 * N));
     CK(cudaMemset(ctx->d_plan_u8, 0, 9 * N));
@@ -1507,7 +1550,7 @@ int hope_destroy(hope_ctx *ctx) {
     if (!ctx) return HOPE_ERR_INVALID;
     cudaSetDevice(ctx->device);
     void *ptrs[] = {ctx->d_obs, ctx->d_aabb, ctx->d_meta, ctx->d_nv, ctx->d_nobs, ctx->d_tab, ctx->d_pose, ctx->d_accum, ctx->d_t,
-                    ctx->d_scene, ctx->d_pending, ctx->d_gate, ctx->d_counters, ctx->d_words, ctx->d_ntry, ctx->d_ncand, ctx->d_cs, ctx->d_item_base, ctx->d_items, ctx->d_item_bad, ctx->d_slots, ctx->d_n_items, ctx->d_plan_rem, ctx->d_plan_u8,
+                    ctx->d_scene, ctx->d_pending, ctx->d_gate, ctx->d_counters, ctx->d_words, ctx->d_ntry, ctx->d_ncand, ctx->d_cs, ctx->d_item_base, ctx->d_items, ctx->d_item_bad, ctx->d_slots, ctx->d_n_items, ctx->d_plan_rem, ctx->d_plan_u8, ctx->d_regen_slots, ctx->d_regen_count, ctx->d_gen_status, ctx->d_episode,
                     ctx->d_action, ctx->d_stage};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -1593,6 +1636,37 @@ int hope_set_scene_pool(hope_ctx *ctx, int first, int n, const double *start, co
     CK(cudaMemcpy(ctx->d_nv + (size_t)first * MAXO, nv.data(), nv.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_nobs + first, nobs.data(), nobs.size() * sizeof(int), cudaMemcpyHostToDevice));
     ctx->have_scenes = true;
+    return HOPE_OK;
+}
+
+int hope_generate_scene_pool_device(hope_ctx *ctx, int first, int n, int level, uint64_t seed, void *stream) {
+    if (!ctx || first < 0 || n <= 0 || first + n > ctx->pool || level < -1 || level > 2) return HOPE_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (hope_scene::launch_generate(n, first, level, seed, nullptr, nullptr, ctx->par, ctx->d_obs, ctx->d_nv, ctx->d_aabb, ctx->d_meta, ctx->d_nobs,
+                                    ctx->d_gen_status, stream) != HOPE_OK) return fail(ctx, cudaGetLastError(), "k_generate_scenes");
+    ctx->launches++;
+    ctx->have_scenes = true;
+    return HOPE_OK;
+}
+
+int hope_get_scene_pool(hope_ctx *ctx, int first, int n, double *h_start, double *h_dest, double *h_bounds, double *h_obs_xy, int32_t *h_nverts) {
+    if (!ctx || first < 0 || n <= 0 || first + n > ctx->pool) return HOPE_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    int gs = 0;
+    CK(cudaMemcpy(&gs, ctx->d_gen_status, sizeof(int), cudaMemcpyDeviceToHost));
+    if (gs != 0) return gs;  // a device generator thread gave up (HOPE_ERR_INVALID) or overflowed HOPE_MAX_OBS
+    std::vector<double> meta((size_t)n * META);
+    std::vector<uint8_t> nv((size_t)n * MAXO);
+    CK(cudaMemcpy(meta.data(), ctx->d_meta + (size_t)first * META, meta.size() * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(nv.data(), ctx->d_nv + (size_t)first * MAXO, nv.size(), cudaMemcpyDeviceToHost));
+    if (h_obs_xy) CK(cudaMemcpy(h_obs_xy, ctx->d_obs + (size_t)first * MAXE * 2, sizeof(double) * n * MAXE * 2, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) {
+        const double *m = &meta[(size_t)i * META];
+        for (int k = 0; k < 3; ++k) { if (h_start) h_start[3 * i + k] = m[M_START + k]; if (h_dest) h_dest[3 * i + k] = m[M_DEST + k]; }
+        for (int k = 0; k < 4; ++k) if (h_bounds) h_bounds[4 * i + k] = m[M_BOUNDS + k];
+        for (int k = 0; k < MAXO; ++k) if (h_nverts) h_nverts[(size_t)i * MAXO + k] = nv[(size_t)i * MAXO + k];
+    }
     return HOPE_OK;
 }
 

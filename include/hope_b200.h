@@ -71,6 +71,11 @@ typedef struct hope_params {
     double reward_ratio;      /* configs.py:180 0.1 */
     int env_collide;          /* configs.py:79  0 */
     int auto_reset;           /* 1: an env that finished takes its next pool scene on the following step */
+    int regen_on_reset;       /* 1 (needs pool_size >= n_envs): env i owns pool slot i and, when it finishes, a fresh
+                                 scene is generated ON THE DEVICE into that slot (scope row f4) instead of cycling
+                                 through a pre-generated pool */
+    int regen_level;          /* level of regenerated scenes: 0 Normal, 1 Complex, 2 Extrem, -1 = slot % 3 */
+    uint64_t regen_seed;      /* stream seed of regenerated scenes */
 } hope_params;
 
 /* Per-step outputs; DEVICE pointers, row-major [n_envs][...].  A NULL member is skipped. */
@@ -126,6 +131,13 @@ int hope_set_scene_pool(hope_ctx *ctx, int first, int n, const double *h_start, 
 int hope_generate_scenes(int n, int level, uint64_t seed, int nthreads, double *h_start, double *h_dest,
                          double *h_bounds, double *h_obs_xy, int32_t *h_nverts, int32_t *h_case_id);
 
+/* Same generator, run on the device (one thread per scene) straight into pool slots [first, first+n);
+ * level -1 cycles the three levels by slot % 3.  Asynchronous on `stream`. */
+int hope_generate_scene_pool_device(hope_ctx *ctx, int first, int n, int level, uint64_t seed, void *stream);
+/* Read pool scenes back to HOST arrays (shapes as in hope_set_scene_pool; synchronous). */
+int hope_get_scene_pool(hope_ctx *ctx, int first, int n, double *h_start, double *h_dest, double *h_bounds, double *h_obs_xy,
+                        int32_t *h_nverts);
+
 /* env.reset for every env: env i takes pool scene h_scene_ids[i] (NULL: scene i % pool),
  * pose = start, t = 0, accum = 0, then the reset step (no action, t becomes 1; RS skipped). */
 int hope_reset(hope_ctx *ctx, const int32_t *h_scene_ids, const hope_out *d_out, void *stream);
@@ -160,7 +172,7 @@ int hope_get_state(hope_ctx *ctx, double *h_pose, int32_t *h_t, double *h_accum,
 int hope_set_state(hope_ctx *ctx, const double *h_pose, const int32_t *h_t, const double *h_accum);
 /* counters since creation: [0] env steps with an action, [1] auto-resets, [2] exact-orientation
  * fallbacks taken, [3] RS word-capacity overflows, [4] RS zero-length words (reference asserts),
- * [5] kernels launched by this context */
+ * [5] kernels launched by this context, [6] scenes generated on the device */
 int hope_get_counters(hope_ctx *ctx, uint64_t h_counters[8]);
 /* Per-kernel device timing: when enabled every kernel launch of a step is bracketed by CUDA
  * events on the launch stream.  hope_profile_read synchronises, returns the accumulated

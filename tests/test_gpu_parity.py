@@ -263,3 +263,69 @@ def test_edge_cases_empty_and_ragged_scenes():
     tl.report("edge cases")
     assert_bars(tl, rs_found_slack=1)
     env.close()
+
+
+def test_device_generated_scenes_are_valid_and_step_like_the_oracle():
+    """Scope row f4: scenes generated by GPU threads (k_generate_scenes), read back and handed to the oracle."""
+    from oracle import geom
+    n = 3072
+    env = BatchedParkingEnv(n, pool_size=n, level="mix", seed=77, auto_reset=False, device_scenes=True)
+    sc = env.get_scene_pool()
+    nobs = (sc["nverts"] > 0).sum(axis=1)
+    assert nobs.min() >= 3 and nobs.max() <= 16
+    box = np.array([(-0.93, -0.97), (3.76, -0.97), (3.76, 0.97), (-0.93, 0.97)])
+
+    def ring(pose):
+        c, s = np.cos(pose[2]), np.sin(pose[2])
+        pts = [(c * x - s * y + pose[0], s * x + c * y + pose[1]) for x, y in box]
+        return pts + [pts[0]]
+
+    for i in range(0, n, 13):
+        srt, dst = ring(sc["start"][i]), ring(sc["dest"][i])
+        assert not geom.rings_intersect(srt, dst)
+        for k in range(16):
+            nv = sc["nverts"][i, k]
+            if nv:
+                ob = [tuple(p) for p in sc["obs"][i, k, :nv]]; ob.append(ob[0])
+                assert not geom.rings_intersect(srt, ob) and not geom.rings_intersect(dst, ob)
+    orc = po.OracleEnv(sc["start"], sc["dest"], sc["bounds"], sc["obs"], sc["nverts"])
+    env.reset(); ref = orc.reset_step(stages=1)
+    out = gather(env)
+    assert np.abs(out["lidar"] - ref["lidar"]).max() <= FLOAT_TOL
+    rng = np.random.default_rng(4)
+    tl = Tally(); live = np.ones(n, dtype=bool)
+    for _ in range(16):
+        act = rng.uniform(-1, 1, size=(n, 2))
+        env.step(torch.as_tensor(act, device=env.device).contiguous())
+        ref = orc.step(act)
+        compare_step(tl, gather(env), {**ref, "mask_steps": ref["mask_steps"].astype(np.uint8)}, orc.pose, live)
+        live &= ref["status"] == 1
+    tl.report("device-generated scenes, 3072 x 16 steps")
+    assert_bars(tl, rs_found_slack=2)
+    env.close()
+
+
+def test_regeneration_on_reset_stays_on_the_device():
+    n = 1024
+    env = BatchedParkingEnv(n, pool_size=n, level="Normal", seed=5, auto_reset=True, device_scenes=True)
+    env.reset()
+    before = env.get_scene_pool()
+    act = torch.zeros((n, 2), dtype=torch.float64, device=env.device); act[:, 1] = 1.0  # straight ahead until out of bounds
+    resets = np.zeros(n, dtype=int)
+    for _ in range(70):
+        env.step(act)
+        o = gather(env)
+        was = o["was_reset"].astype(bool)
+        resets += was
+        if was.any():
+            st = env.get_state()
+            now = env.get_scene_pool()
+            assert (st["scene_id"] == np.arange(n)).all()            # env i keeps slot i
+            assert np.array_equal(st["pose"][was], now["start"][was])  # and starts at the fresh scene's start
+            assert (o["status"][was] == 1).all() and np.isfinite(o["lidar"][was]).all()
+    after = env.get_scene_pool()
+    changed = (before["start"] != after["start"]).any(axis=1)
+    assert (resets > 0).sum() > n // 2
+    assert np.array_equal(changed, resets > 0)
+    assert env.counters()["device_scenes_generated"] == resets.sum()
+    env.close()
