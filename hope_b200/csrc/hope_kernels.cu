@@ -953,11 +953,15 @@ struct CheckEnv {
     const double4 *aabb; const double2 *verts; const uint8_t *nvp; int nobs;
 };
 
-// Does the vehicle box at local-frame pose (lx, ly, lyaw) leave the map or touch an obstacle edge?
-__device__ __forceinline__ bool sample_hits(const CheckEnv &E, const hope_params &par, double lx, double ly, double lyaw) {
+// Does ANY lane's vehicle box at local-frame pose (lx, ly, lyaw) leave the map or touch an obstacle edge?
+// Called by the whole warp (lanes without a sample pass valid = false); returns a warp-uniform verdict and
+// (with `early`) stops at the first obstacle for which some lane reports a hit, since one bad sample condemns the word.
+// `mine` is set for the lanes that hit (only consulted by the degenerate trailing-zero rule).
+__device__ __forceinline__ bool warp_samples_hit(const CheckEnv &E, const hope_params &par, bool valid, bool early, double lx, double ly, double lyaw, bool &mine) {
     double gx = E.cg * lx + E.sg * ly + E.q0x, gy = -E.sg * lx + E.cg * ly + E.q0y;  // reeds_shepp.py:47-48
     double gyaw = pi_2_pi(lyaw + E.q0h);                                             // :49
-    if (gx < E.xmin || gx > E.xmax || gy < E.ymin || gy > E.ymax) return true;       // car_parking_base.py:462-464
+    mine = valid && (gx < E.xmin || gx > E.xmax || gy < E.ymin || gy > E.ymax);      // car_parking_base.py:462-464
+    if (early && __any_sync(HOPE_FULL_MASK, mine)) return true;
     double cth, sth, bx[4], by[4];
     sincos(gyaw, &sth, &cth);
 #pragma unroll
@@ -967,40 +971,42 @@ __device__ __forceinline__ bool sample_hits(const CheckEnv &E, const hope_params
     }
     const double vxmin = dmin(dmin(bx[0], bx[1]), dmin(bx[2], bx[3])), vxmax = dmax(dmax(bx[0], bx[1]), dmax(bx[2], bx[3]));
     const double vymin = dmin(dmin(by[0], by[1]), dmin(by[2], by[3])), vymax = dmax(dmax(by[0], by[1]), dmax(by[2], by[3]));
-    for (int ob = 0; ob < E.nobs; ++ob) {
+    for (int ob = 0; ob < E.nobs; ++ob) {  // same trip count in every lane
         double4 bb = ld_aabb(E.aabb + ob);
         // a hit needs rx inside both segments' x-ranges and ry inside both y-ranges (:518-526): disjoint
         // boxes cannot produce one, so these rejects are exact
-        if (vxmax < bb.x || bb.y < vxmin || vymax < bb.z || bb.w < vymin) continue;
-        const int nv = E.nvp[ob];
-        double2 p1 = __ldg(E.verts + ob * MAXV);
-        for (int j = 0; j < nv; ++j) {
-            double2 p2 = __ldg(E.verts + ob * MAXV + ((j + 1 == nv) ? 0 : j + 1));
-            // obstacle edge box vs vehicle box, tested corner-wise (no min/max needed to reject)
-            if (!((p1.x < vxmin && p2.x < vxmin) || (p1.x > vxmax && p2.x > vxmax) ||
-                  (p1.y < vymin && p2.y < vymin) || (p1.y > vymax && p2.y > vymax))) {
-                const double oxmax = dmax(p1.x, p2.x), oxmin = dmin(p1.x, p2.x), oymax = dmax(p1.y, p2.y), oymin = dmin(p1.y, p2.y);
-                const double dd = p2.y - p1.y, ee = p1.x - p2.x, ff = p1.y * p2.x - p1.x * p2.y;  // :504-506
+        if (valid && !mine && !(vxmax < bb.x || bb.y < vxmin || vymax < bb.z || bb.w < vymin)) {
+            const int nv = E.nvp[ob];
+            double2 p1 = __ldg(E.verts + ob * MAXV);
+            for (int j = 0; j < nv && !mine; ++j) {
+                double2 p2 = __ldg(E.verts + ob * MAXV + ((j + 1 == nv) ? 0 : j + 1));
+                // obstacle edge box vs vehicle box, tested corner-wise (no min/max needed to reject)
+                if (!((p1.x < vxmin && p2.x < vxmin) || (p1.x > vxmax && p2.x > vxmax) ||
+                      (p1.y < vymin && p2.y < vymin) || (p1.y > vymax && p2.y > vymax))) {
+                    const double oxmax = dmax(p1.x, p2.x), oxmin = dmin(p1.x, p2.x), oymax = dmax(p1.y, p2.y), oymin = dmin(p1.y, p2.y);
+                    const double dd = p2.y - p1.y, ee = p1.x - p2.x, ff = p1.y * p2.x - p1.x * p2.y;  // :504-506
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int q2 = (q + 1) & 3;
-                    const double vx1 = bx[q], vy1 = by[q], vx2 = bx[q2], vy2 = by[q2];
-                    if ((vx1 < oxmin && vx2 < oxmin) || (vx1 > oxmax && vx2 > oxmax) ||
-                        (vy1 < oymin && vy2 < oymin) || (vy1 > oymax && vy2 > oymax)) continue;
-                    const double a = vy2 - vy1, b = vx1 - vx2, c = vy1 * vx2 - vx1 * vy2;  // :477-479
-                    const double det = a * ee - b * dd;                                    // :509
-                    if (det == 0.0) continue;
-                    double rx, ry;
-                    div_pair(b * ff - c * ee, c * dd - a * ff, det, rx, ry);               // :512-513
-                    const bool okx = !(rx > oxmax) && !(rx < oxmin) && !(rx > dmax(vx1, vx2)) && !(rx < dmin(vx1, vx2));
-                    const bool oky = !(ry > oymax) && !(ry < oymin) && !(ry > dmax(vy1, vy2)) && !(ry < dmin(vy1, vy2));
-                    if (okx && oky) return true;
+                    for (int q = 0; q < 4; ++q) {
+                        const int q2 = (q + 1) & 3;
+                        const double vx1 = bx[q], vy1 = by[q], vx2 = bx[q2], vy2 = by[q2];
+                        if ((vx1 < oxmin && vx2 < oxmin) || (vx1 > oxmax && vx2 > oxmax) ||
+                            (vy1 < oymin && vy2 < oymin) || (vy1 > oymax && vy2 > oymax)) continue;
+                        const double a = vy2 - vy1, b = vx1 - vx2, c = vy1 * vx2 - vx1 * vy2;  // :477-479
+                        const double det = a * ee - b * dd;                                    // :509
+                        if (det == 0.0) continue;
+                        double rx, ry;
+                        div_pair(b * ff - c * ee, c * dd - a * ff, det, rx, ry);               // :512-513
+                        const bool okx = !(rx > oxmax) && !(rx < oxmin) && !(rx > dmax(vx1, vx2)) && !(rx < dmin(vx1, vx2));
+                        const bool oky = !(ry > oymax) && !(ry < oymin) && !(ry > dmax(vy1, vy2)) && !(ry < dmin(vy1, vy2));
+                        if (okx && oky) mine = true;
+                    }
                 }
+                p1 = p2;
             }
-            p1 = p2;
         }
+        if (early && __any_sync(HOPE_FULL_MASK, mine)) return true;
     }
-    return false;
+    return __any_sync(HOPE_FULL_MASK, mine);
 }
 
 // Evaluate the up-to RS_STRIDE samples each lane owns in the current chunk of word slot `s`.
@@ -1013,21 +1019,22 @@ __device__ bool chunk_is_bad(const WordSlot &s, const CheckEnv &E, const hope_pa
     const bool zero_tail = s.end_lx == 0.0;
     unsigned zero_hits = 0, nonzero_bits = 0;
     for (int r = 0; r < RS_STRIDE; ++r) {
-        bool hit = false;
-        if (code != RS_DONE) {
-            double lx = 0.0, ly = 0.0, lyaw = 0.0;
-            if (code != RS_ORIGIN) {
-                const int sgi = code & 0x7F;
-                rs_interp(pd, (int)((s.types >> (4 * sgi)) & 0xF), E.maxc, s.org[sgi], lx, ly, lyaw);
-            }
-            hit = sample_hits(E, par, lx, ly, lyaw);
-            if (zero_tail) {
-                if (lx != 0.0) nonzero_bits |= 1u << r;
-                else if (hit) { zero_hits |= 1u << r; hit = false; }
-            }
-            walker_next(s.len, s.n, E.step, code, pd);
+        const bool valid = code != RS_DONE;
+        if (!__any_sync(HOPE_FULL_MASK, valid)) break;
+        double lx = 0.0, ly = 0.0, lyaw = 0.0;
+        if (valid && code != RS_ORIGIN) {
+            const int sgi = code & 0x7F;
+            rs_interp(pd, (int)((s.types >> (4 * sgi)) & 0xF), E.maxc, s.org[sgi], lx, ly, lyaw);
         }
-        if (__any_sync(HOPE_FULL_MASK, hit)) return true;
+        bool mine;
+        const bool any_hit = warp_samples_hit(E, par, valid, !zero_tail, lx, ly, lyaw, mine);
+        if (!zero_tail) { if (any_hit) return true; }
+        else if (valid) {  // degenerate goal: a hit on an x == 0.0 sample only counts if a later sample has x != 0.0
+            if (lx != 0.0) { nonzero_bits |= 1u << r; }
+            else if (mine) { zero_hits |= 1u << r; mine = false; }
+        }
+        if (zero_tail && __any_sync(HOPE_FULL_MASK, valid && mine)) return true;
+        if (valid) walker_next(s.len, s.n, E.step, code, pd);
     }
     if (zero_tail) {  // lanes own consecutive sample ranges: scan from the last sample backwards
         bool nz_after = false, bad = false;
