@@ -10,6 +10,7 @@
 //
 // All arithmetic is float64 with FMA contraction off (see hope_device.cuh).  Data layout in HBM is
 // documented in DESIGN.md §3.
+#include <cuda_pipeline.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -335,6 +336,8 @@ struct ObserveSmem {
     double L[NRAY];                                              // clip(lidar)+mask_base
     int steps[NACT + 2];
     uint8_t quad[MAXE];                                          // which ray quadrants can accept this edge
+    uint8_t qlist[4][MAXE];                                      // per quadrant: the edges that can be hit from it
+    uint8_t qcount[4];
 };
 
 // n1/den and n2/den, each correctly rounded (== IEEE division), sharing one reciprocal: with r = RN(1/den)
@@ -388,6 +391,21 @@ __global__ void __launch_bounds__(64) k_observe(int n, Pool pool, EnvState st, T
         n_edges += __popc(m);
     }
     __syncwarp();
+    // per-quadrant edge lists, so the ray loop below only visits edges that can be hit from its quadrant
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        int cnt = 0;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int e = half * 32 + lane;
+            const bool on = e < n_edges && ((sm.quad[e] >> q) & 1);
+            const unsigned m = __ballot_sync(HOPE_FULL_MASK, on);
+            if (on) sm.qlist[q][cnt + __popc(m & ((1u << lane) - 1))] = (uint8_t)e;
+            cnt += __popc(m);
+        }
+        if (lane == 0) sm.qcount[q] = (uint8_t)cnt;
+    }
+    __syncwarp();
 
     // ---- raycast: quadrant q handles rays 30q .. 30q+29, one per lane ---------------------------
     const int per_quad = NRAY / 4;
@@ -399,8 +417,9 @@ __global__ void __launch_bounds__(64) k_observe(int n, Pool pool, EnvState st, T
         // sign conventions of the quadrant (:120-124): reject rx < -1e-8 (sx=+1) or rx > 1e-8 (sx=-1), same for ry
         const double sx = (q == 0 || q == 3) ? 1.0 : -1.0, sy = (q < 2) ? 1.0 : -1.0;
         double best2 = INFINITY;  // min over edges of rx^2 + ry^2; sqrt is monotone, so one sqrt at the end is exact
-        for (int e = 0; e < n_edges; ++e) {
-            if (!((sm.quad[e] >> q) & 1)) continue;  // warp-uniform
+        const int qn_edges = sm.qcount[q];
+        for (int t = 0; t < qn_edges; ++t) {
+            const int e = sm.qlist[q][t];            // warp-uniform
             const double d = sm.ed[e], ee = sm.ee[e], f = sm.ef[e];
             const double det = A * ee - B * d;        // :109
             if (det == 0.0) continue;                 // parallel -> 100 -> clipped away (:131)
@@ -826,7 +845,7 @@ constexpr int RS_STRIDE = 8;                    // samples per lane in one chunk
 constexpr int RS_CHUNK = 32 * RS_STRIDE;        // samples covered by one set of saved states
 constexpr uint8_t RS_ORIGIN = 0xFE, RS_END = 0x80, RS_DONE = 0xFF;
 
-struct WordSlot {                               // 552 bytes, the sampling plan of one tried word
+struct __align__(16) WordSlot {                 // 560 bytes, the sampling plan of one tried word
     double len[HOPE_RS_MAX_SEG];                // normalised signed segment lengths
     double org[HOPE_RS_MAX_SEG][5];             // per segment: ox, oy, oyaw, cos(oyaw), sin(oyaw) (local frame)
     double st_pd[32];                           // saved walker state at sample RS_STRIDE*j of the chunk
@@ -838,7 +857,7 @@ struct WordSlot {                               // 552 bytes, the sampling plan 
     int total;                                  // samples in the word if the walk reached the end, else -1
     uint8_t resume_code, pad[3];
 };
-static_assert(sizeof(WordSlot) % 8 == 0, "WordSlot is copied as 64-bit words");
+static_assert(sizeof(WordSlot) % 16 == 0, "WordSlot is staged with 16-byte asynchronous copies");
 
 // One step of generate_local_course's sample sequence (:452-507).  (code, pd) is the sample just
 // emitted; on return it is the next one.  code: RS_ORIGIN = path start, seg index = loop sample of
@@ -1052,19 +1071,25 @@ __device__ bool chunk_is_bad(const WordSlot &s, const CheckEnv &E, const hope_pa
 
 constexpr int CHK_WARPS = 4;  // warps per block of k_rs_check
 
+// asynchronous global -> shared copy of one WordSlot by a warp (LDGSTS, 16 bytes per lane per pass)
+__device__ __forceinline__ void stage_slot_async(WordSlot *dst, const WordSlot *src, int lane) {
+    const char *g = reinterpret_cast<const char *>(src);
+    char *sh = reinterpret_cast<char *>(dst);
+    for (int q = lane * 16; q < (int)sizeof(WordSlot); q += 32 * 16) __pipeline_memcpy_async(sh + q, g + q, 16);
+    __pipeline_commit();
+}
+
 __global__ void __launch_bounds__(CHK_WARPS * 32, 4) k_rs_check(Pool pool, EnvState st, Tables tb, RsScratch rs, hope_params par) {
-    __shared__ WordSlot smem[CHK_WARPS];
+    __shared__ WordSlot smem[CHK_WARPS][2];  // double buffer: the next word's plan streams in while this one is sampled
     const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_items = *rs.n_items;
     const int warps_total = gridDim.x * CHK_WARPS;
-    WordSlot &s = smem[warp_in_block];
-    for (int item = blockIdx.x * CHK_WARPS + warp_in_block; item < n_items; item += warps_total) {
+    int item = blockIdx.x * CHK_WARPS + warp_in_block, buf = 0;
+    if (item < n_items) stage_slot_async(&smem[warp_in_block][0], rs.slots + item, lane);
+    for (; item < n_items; item += warps_total, buf ^= 1) {
         const int env = rs.items[item] >> 4;
-        {   // stage the word's plan: coalesced 64-bit copies
-            const unsigned long long *src = reinterpret_cast<const unsigned long long *>(rs.slots + item);
-            unsigned long long *dst = reinterpret_cast<unsigned long long *>(&s);
-            for (int q = lane; q < (int)(sizeof(WordSlot) / 8); q += 32) dst[q] = src[q];
-        }
+        const int next = item + warps_total;
+        if (next < n_items) stage_slot_async(&smem[warp_in_block][buf ^ 1], rs.slots + next, lane);
         const int sid = st.scene[env];
         const double *meta = pool.meta + (size_t)sid * META;
         CheckEnv E;
@@ -1076,7 +1101,9 @@ __global__ void __launch_bounds__(CHK_WARPS * 32, 4) k_rs_check(Pool pool, EnvSt
         E.aabb = reinterpret_cast<const double4 *>(pool.aabb) + (size_t)sid * MAXO;
         E.verts = reinterpret_cast<const double2 *>(pool.obs) + (size_t)sid * MAXE;
         E.nvp = pool.nv + (size_t)sid * MAXO;
+        if (next < n_items) __pipeline_wait_prior(1); else __pipeline_wait_prior(0);  // this word's plan has landed
         __syncwarp();
+        WordSlot &s = smem[warp_in_block][buf];
         bool bad = false;
         int chunk_base = 0;
         for (;;) {
