@@ -185,6 +185,45 @@ def run_rollout(args, rank, local_rank, world, dev):
     env.close()
 
 
+def run_sac(args, rank, local_rank, world, dev):
+    """BASELINE cfg 5: 65 536 envs per GPU, SAC-style acting + replay + one update every 8 env steps, gradients of
+    actor + twin critics reduced with a single NCCL all-reduce that overlaps the following rollout steps."""
+    import torch
+    from hope_b200 import learner
+    from hope_b200.batched_env import BatchedParkingEnv, generate_scenes
+    n, K, W = args.envs, args.steps, max(3, args.warmup)
+    env = BatchedParkingEnv(n, scenes=generate_scenes(2 * n, "mix", scene_seed(rank)), device=local_rank, auto_reset=True)
+    loop = learner.SacRollout(env, world=world, seed=0)
+    loop.run(max(W, 2 * loop.update_every))
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    c0, u0 = env.counters(), loop.updates
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    loop.run(K)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = reduce_scalar(e0.elapsed_time(e1), "max", world, dev)
+    c1 = env.counters()
+    steps = reduce_scalar(float(c1["env_steps"] - c0["env_steps"]), "sum", world, dev)
+    # replicas must stay identical: same init, same averaged gradients
+    w = torch.cat([p.detach().reshape(-1).float() for p in loop.learner.actor.parameters()])
+    spread = reduce_scalar(float(w.double().sum()), "max", world, dev) - (-reduce_scalar(-float(w.double().sum()), "max", world, dev))
+    if rank == 0:
+        print(json.dumps({
+            "metric": "env-steps/sec", "value": steps / (ms * 1e-3), "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 env / bf16 nets",
+            "data": "synthetic", "gpu_launches": c1["kernel_launches"] - c0["kernel_launches"],
+            "config": {"workload": "cfg5: SAC rollout + device replay + update every 8 env steps (batch 8192/GPU), one flat NCCL gradient all-reduce per update",
+                       "envs_per_gpu": n, "updates": loop.updates - u0, "allreduce_floats": loop.learner.reducer.numel,
+                       "replica_weight_spread": spread}}))
+    env.close()
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -193,7 +232,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="scenes per GPU (default: the BASELINE cfg-3 size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--config", default="step", choices=["step", "rollout"],
+    ap.add_argument("--config", default="step", choices=["step", "rollout", "sac"],
                     help="step: BASELINE cfg 3 (default, the headline metric); rollout: cfg 4, PPO acting loop with the transformer policy")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -215,6 +254,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if args.config == "rollout":
         return run_rollout(args, rank, local_rank, world, dev)
+    if args.config == "sac":
+        return run_sac(args, rank, local_rank, world, dev)
 
     # scene id -> GPU: rank r owns scenes [r*2n, (r+1)*2n) of the global synthetic pool
     scenes = generate_scenes(2 * n, "mix", scene_seed(rank))
