@@ -60,6 +60,30 @@ def reduce_scalar(x, op, world, device):
     return float(t.item())
 
 
+def pin_to_gpu_numa(local_rank):
+    """Bind this rank's host threads (and therefore its pinned staging buffers, first-touch) to the CPUs
+    that are local to its GPU's PCIe root: with 8 ranks the D2H streams otherwise cross sockets."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-"); cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return spec
+    except Exception:
+        pass
+    return None
+
+
 def _dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
@@ -247,6 +271,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the product has no CPU path); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
+    numa = pin_to_gpu_numa(local_rank) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -344,7 +369,8 @@ def main():
                        "l2": "per-step working set (scene pool 2N x 1.7 KB + outputs N x 1.5 KB = 320 MB) exceeds the 126 MB L2; no explicit flush",
                        "counted": "env-steps with an action; auto-reset steps excluded"},
             "e2e": {"value": e2e_steps / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "hope_step_host (pinned host buffers, synchronous)", "ms_per_step": 1e3 * e2e_s / K},
+                    "api": "hope_step_host (pinned host buffers, synchronous)", "ms_per_step": 1e3 * e2e_s / K,
+                    "host_cpus_rank0": numa},
             "gpu_launches": launches,
             "clocks": clocks,
             "kernels_ms_per_launch": {k: (v[0] / v[1] if v[1] else None) for k, v in prof.items()},
