@@ -348,6 +348,14 @@ def main():
     c3 = env.counters()
     e2e_steps = sum_over_ranks(float(c3["env_steps"] - c2["env_steps"]))
     h2d, d2h = env.host_io_bytes()
+    # context for the e2e number: what a plain pinned D2H copy of the lidar buffer achieves on this box
+    pin = torch.empty_like(env.out["lidar"], device="cpu").pin_memory()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    for _ in range(5):
+        pin.copy_(env.out["lidar"], non_blocking=True)
+    torch.cuda.synchronize()
+    pcie_gbs = 5 * pin.numel() * 8 / (time.perf_counter() - t1) / 1e9
 
     if rank == 0:
         dom = max(prof, key=lambda k: prof[k][0])
@@ -370,6 +378,7 @@ def main():
                        "counted": "env-steps with an action; auto-reset steps excluded"},
             "e2e": {"value": e2e_steps / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "hope_step_host (pinned host buffers, synchronous)", "ms_per_step": 1e3 * e2e_s / K,
+                    "plain_d2h_copy_gbs": pcie_gbs,
                     "host_cpus_rank0": numa},
             "gpu_launches": launches,
             "clocks": clocks,

@@ -1311,6 +1311,21 @@ struct hope_ctx {
     static constexpr int MAX_LANES = 4;
     struct Lane { cudaStream_t main = nullptr, aux = nullptr; cudaEvent_t ev_advanced = nullptr, ev_observed = nullptr; } lanes[MAX_LANES];
     int host_chunks = 4;
+    // hope_step_host replays a captured CUDA graph of the whole pipelined step while the caller keeps passing the
+    // same buffers (one launch instead of ~120 driver calls per step)
+    bool host_graph_enabled = true;
+    // Optional (HOPE_B200_ZERO_COPY=1): outputs whose host buffer is pinned + mapped (cudaHostAlloc / cudaHostRegister,
+    // e.g. torch pin_memory) are written by the kernels directly over PCIe instead of staged in HBM and copied:
+    // bit k = field k of kOutFields.  3.3 ms vs 2.7 ms per 65 536-env step on B200, so staged copies stay the default.
+    bool zero_copy_enabled = false;  // measured slower than staged copies on B200 (small PCIe write TLPs): opt-in
+    unsigned zero_copy_mask = 0;
+    hope_out step_out;   // what the kernels of the current host step write to (stage_out with mapped pointers patched in)
+    cudaGraphExec_t host_graph = nullptr;
+    const double *hg_action = nullptr;
+    hope_out hg_out;
+    unsigned hg_stages = 0;
+    unsigned long long hg_launches = 0;
+    cudaEvent_t ev_fork = nullptr, ev_join[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
     unsigned long long launches = 0;
     bool profile = false;
     std::vector<cudaEvent_t> prof_events[4];  // begin/end pairs per kernel
@@ -1380,6 +1395,7 @@ int copy_fields(hope_ctx *ctx, const hope_host_out *h_out, int observe, cudaStre
     for (int k = 0; k < kNumOutFields; ++k) {
         void *dst = field_ptr_c(*h_out, kOutFields[k]);
         if (!dst || (observe >= 0 && kOutFields[k].observe != observe)) continue;
+        if ((ctx->zero_copy_mask >> k) & 1) continue;  // the kernels wrote this array straight into the caller's mapped buffer
         const size_t row = kOutFields[k].elem * kOutFields[k].per_env;
         CK(cudaMemcpyAsync(static_cast<char *>(dst) + lo * row, static_cast<const char *>(field_ptr_c(ctx->stage_out, kOutFields[k])) + lo * row,
                            row * cnt, cudaMemcpyDeviceToHost, s));
@@ -1575,6 +1591,12 @@ int hope_create(hope_ctx **out, int device, int n_envs, int pool_size, const hop
         CK(cudaEventCreateWithFlags(&ln.ev_advanced, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ln.ev_observed, cudaEventDisableTiming));
     }
+    CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    for (int li = 0; li < hope_ctx::MAX_LANES; ++li) CK(cudaEventCreateWithFlags(&ctx->ev_join[li], cudaEventDisableTiming));
+    memset(&ctx->hg_out, 0, sizeof(ctx->hg_out));
+    if (const char *e = getenv("HOPE_B200_HOST_GRAPH")) ctx->host_graph_enabled = atoi(e) != 0;
+    if (const char *e = getenv("HOPE_B200_ZERO_COPY")) ctx->zero_copy_enabled = atoi(e) != 0;
+    memset(&ctx->step_out, 0, sizeof(ctx->step_out));
     if (const char *e = getenv("HOPE_B200_HOST_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->host_chunks = v; }
     CK(cudaFuncSetAttribute(k_observe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((OBS_THREADS / 32) * sizeof(ObserveSmem))));
     return HOPE_OK;
@@ -1588,6 +1610,9 @@ int hope_destroy(hope_ctx *ctx) {
                     ctx->d_action, ctx->d_stage};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->host_graph) cudaGraphExecDestroy(ctx->host_graph);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    for (auto e : ctx->ev_join) if (e) cudaEventDestroy(e);
     for (auto &ln : ctx->lanes) {
         if (ln.main) cudaStreamDestroy(ln.main);
         if (ln.aux) cudaStreamDestroy(ln.aux);
@@ -1741,6 +1766,51 @@ int hope_step_kinematics_collision(hope_ctx *ctx, const double *d_action, double
     return launch_step(ctx, d_action, o, HOPE_STAGE_ADVANCE, 0, static_cast<cudaStream_t>(stream));
 }
 
+// enqueue one pipelined host step (see hope_step_host) on the context's lanes; lane 0's main stream is the origin:
+// the other lanes fork from it and join back, which also makes the whole thing capturable as one CUDA graph
+static void plan_zero_copy(hope_ctx *ctx, const hope_host_out *h_out) {
+    ctx->step_out = ctx->stage_out;
+    ctx->zero_copy_mask = 0;
+    if (!ctx->zero_copy_enabled) return;
+    for (int k = 0; k < kNumOutFields; ++k) {
+        void *h = field_ptr_c(*h_out, kOutFields[k]);
+        if (!h) continue;
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, h) != cudaSuccess) { (void)cudaGetLastError(); continue; }
+        if (at.type == cudaMemoryTypeHost && at.devicePointer) {
+            field_ptr(ctx->step_out, kOutFields[k]) = at.devicePointer;
+            ctx->zero_copy_mask |= 1u << k;
+        }
+    }
+}
+
+static int enqueue_host_step(hope_ctx *ctx, const double *h_action, const hope_host_out *h_out, unsigned stages) {
+    const bool fork = (stages & HOPE_STAGE_OBSERVE) && (stages & HOPE_STAGE_RS);
+    const int n = ctx->n;
+    int chunks = ctx->host_chunks;
+    if (n < 4096 * chunks) chunks = n / 4096 > 0 ? n / 4096 : 1;
+    const int per = ((n + chunks - 1) / chunks + 127) / 128 * 128;
+    cudaStream_t s0 = ctx->lanes[0].main;
+    CK(cudaEventRecord(ctx->ev_fork, s0));
+    for (int li = 1; li < hope_ctx::MAX_LANES; ++li) CK(cudaStreamWaitEvent(ctx->lanes[li].main, ctx->ev_fork, 0));
+    int rc;
+    for (int c = 0, lo = 0; lo < n; ++c, lo += per) {
+        const int cnt = (lo + per <= n) ? per : n - lo;
+        const int li = c % hope_ctx::MAX_LANES;
+        cudaStream_t s = ctx->lanes[li].main;
+        CK(cudaMemcpyAsync(ctx->d_action + 2 * (size_t)lo, h_action + 2 * (size_t)lo, sizeof(double) * 2 * cnt, cudaMemcpyHostToDevice, s));
+        rc = launch_range(ctx, ctx->d_action, ctx->step_out, stages, 0, s, li, c, lo, cnt, fork ? h_out : nullptr);
+        if (rc) return rc;
+        rc = copy_fields(ctx, h_out, fork ? 0 : -1, s, lo, cnt);
+        if (rc) return rc;
+    }
+    for (int li = 1; li < hope_ctx::MAX_LANES; ++li) {  // every forked lane joins, used or not
+        CK(cudaEventRecord(ctx->ev_join[li], ctx->lanes[li].main));
+        CK(cudaStreamWaitEvent(s0, ctx->ev_join[li], 0));
+    }
+    return HOPE_OK;
+}
+
 int hope_step_host(hope_ctx *ctx, const double *h_action, const hope_host_out *h_out, unsigned stages) {
     if (!ctx || !h_action || !h_out) return HOPE_ERR_INVALID;
     if (!ctx->have_tables) return HOPE_ERR_NO_TABLES;
@@ -1749,26 +1819,42 @@ int hope_step_host(hope_ctx *ctx, const double *h_action, const hope_host_out *h
     int rc = ensure_stage(ctx);
     if (rc) return rc;
     stages |= HOPE_STAGE_ADVANCE;
-    const bool fork = (stages & HOPE_STAGE_OBSERVE) && (stages & HOPE_STAGE_RS);
     // Software pipeline over env ranges: range c runs on lane c % MAX_LANES (its own stream pair), so its D2H
     // copies travel while the next range's kernels execute.  Envs are independent, so the split changes nothing.
-    const int n = ctx->n;
-    int chunks = ctx->host_chunks;
-    if (n < 4096 * chunks) chunks = n / 4096 > 0 ? n / 4096 : 1;
-    const int per = ((n + chunks - 1) / chunks + 127) / 128 * 128;
-    int used = 0;
-    for (int c = 0, lo = 0; lo < n; ++c, lo += per) {
-        const int cnt = (lo + per <= n) ? per : n - lo;
-        const int li = c % hope_ctx::MAX_LANES;
-        cudaStream_t s = ctx->lanes[li].main;
-        CK(cudaMemcpyAsync(ctx->d_action + 2 * (size_t)lo, h_action + 2 * (size_t)lo, sizeof(double) * 2 * cnt, cudaMemcpyHostToDevice, s));
-        rc = launch_range(ctx, ctx->d_action, ctx->stage_out, stages, 0, s, li, c, lo, cnt, fork ? h_out : nullptr);
-        if (rc) return rc;
-        rc = copy_fields(ctx, h_out, fork ? 0 : -1, s, lo, cnt);
-        if (rc) return rc;
-        used = c + 1;
+    cudaStream_t s0 = ctx->lanes[0].main;
+    if (ctx->host_graph_enabled && !ctx->profile) {
+        const bool same = ctx->host_graph && ctx->hg_action == h_action && ctx->hg_stages == stages &&
+                          memcmp(&ctx->hg_out, h_out, sizeof(hope_out)) == 0;
+        if (!same) {
+            if (ctx->host_graph) { cudaGraphExecDestroy(ctx->host_graph); ctx->host_graph = nullptr; }
+            plan_zero_copy(ctx, h_out);
+            const unsigned long long before = ctx->launches;
+            cudaGraph_t g = nullptr;
+            CK(cudaStreamBeginCapture(s0, cudaStreamCaptureModeThreadLocal));
+            rc = enqueue_host_step(ctx, h_action, h_out, stages);
+            cudaError_t ce = cudaStreamEndCapture(s0, &g);
+            if (rc == HOPE_OK && ce == cudaSuccess && g && cudaGraphInstantiate(&ctx->host_graph, g, 0) == cudaSuccess) {
+                ctx->hg_action = h_action; ctx->hg_out = *h_out; ctx->hg_stages = stages;
+                ctx->hg_launches = ctx->launches - before;
+                ctx->launches = before;  // nothing ran yet: the capture only recorded the launches
+            } else {
+                ctx->host_graph = nullptr; ctx->host_graph_enabled = false;  // fall back to direct enqueue for good
+                ctx->launches = before;
+                (void)cudaGetLastError();
+            }
+            if (g) cudaGraphDestroy(g);
+        }
+        if (ctx->host_graph) {
+            CK(cudaGraphLaunch(ctx->host_graph, s0));
+            ctx->launches += ctx->hg_launches;
+            CK(cudaStreamSynchronize(s0));
+            return HOPE_OK;
+        }
     }
-    for (int li = 0; li < hope_ctx::MAX_LANES && li < used; ++li) CK(cudaStreamSynchronize(ctx->lanes[li].main));
+    plan_zero_copy(ctx, h_out);
+    rc = enqueue_host_step(ctx, h_action, h_out, stages);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(s0));
     return HOPE_OK;
 }
 
@@ -1779,7 +1865,10 @@ int hope_reset_host(hope_ctx *ctx, const int32_t *h_scene_ids, const hope_host_o
     if (rc) return rc;
     rc = hope_reset(ctx, h_scene_ids, &ctx->stage_out, ctx->own_stream);
     if (rc) return rc;
+    const unsigned keep_mask = ctx->zero_copy_mask;
+    ctx->zero_copy_mask = 0;  // the reset step always goes through the staging buffers
     rc = copy_fields(ctx, h_out, -1, ctx->own_stream, 0, ctx->n);
+    ctx->zero_copy_mask = keep_mask;
     if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->own_stream));
     return HOPE_OK;
