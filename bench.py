@@ -39,7 +39,9 @@ ALGO_BYTES = {
     "k_advance": 516,              # pose 24 r/w + action 16 + vertices 390 + n_obs 4 + dest/bounds 56 + flags 2
     "k_observe": 1378 + 62 + 336 + 40,  # raycast (pose, vertices, lidar 960 out) + table share + mask f64 + target; lidar not re-read (fused)
     "k_rs_enumerate": 24 + 24 + 16,     # pose + dest + gate/state in; word list stays on chip-side scratch
-    "k_rs_check": 24 + 56 + 394 + 47,   # pose, dest/bounds, vertices in; RS result out
+    "k_rs_walk": 0.75 * 2.9 * (56 + 560),   # per gated env-step: ~2.9 tried words, 56 B word in + 560 B sampling plan out
+    "k_rs_check": 24 + 56 + 394 + 0.75 * 2.9 * 560,   # pose, dest/bounds, vertices + the sampling plans read back
+    "k_rs_select": 47,                   # RS result out
 }
 CPU_SAMPLE_ENVS, CPU_SAMPLE_STEPS = 4096, 8
 
@@ -370,6 +372,13 @@ def main():
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get(dom)
+        import ctypes
+        fp64 = ctypes.c_double(0.0)
+        capi.check(capi.load_library().hope_fp64_peak_tflops(local_rank, ctypes.byref(fp64)))
+        pipe = None
+        ppath = os.path.join(ROOT, "profiles", "fp64_pipe_pct.json")
+        if os.path.exists(ppath):
+            pipe = json.load(open(ppath)).get(dom)
         line = {
             "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -385,7 +394,8 @@ def main():
             "kernels_ms_per_launch": {k: (v[0] / v[1] if v[1] else None) for k, v in prof.items()},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "algorithmic_bytes_per_env_step": ALGO_BYTES[dom], "peak_source": peak_src,
-                         "note": "float64 ALU/latency-bound path: HBM fraction is small by construction (SURVEY.md §8d)"},
+                         "note": "float64 ALU/latency-bound path: HBM fraction is small by construction (SURVEY.md §8d)",
+                         "fp64_fma_peak_tflops_measured": fp64.value, "fp64_pipe_active_pct_ncu": pipe},
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1

@@ -222,14 +222,14 @@ class BatchedParkingEnv(object):
     def planner_reset(self):
         capi.check(self.lib.hope_planner_reset(self.ctx, self._stream()), self.ctx)
 
-    KERNELS = ("k_advance", "k_observe", "k_rs_enumerate", "k_rs_check")
+    KERNELS = ("k_advance", "k_observe", "k_rs_enumerate", "k_rs_walk", "k_rs_check", "k_rs_select")
 
     def profile(self, on=True):
         capi.check(self.lib.hope_profile_enable(self.ctx, 1 if on else 0), self.ctx)
 
     def profile_read(self):
         """{kernel: (total_ms, launches)} measured with CUDA events on the launch stream."""
-        ms = (C.c_double * 4)(); cnt = (C.c_uint64 * 4)()
+        ms = (C.c_double * 8)(); cnt = (C.c_uint64 * 8)()
         capi.check(self.lib.hope_profile_read(self.ctx, C.byref(ms), C.byref(cnt)), self.ctx)
         return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.KERNELS)}
 

@@ -33,7 +33,8 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    extra = os.environ.get("HOPE_B200_NVCC_DEFS", "").split()  # tuning experiments, e.g. "-DHOPE_CHK_MINBLOCKS=5"
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     env = dict(os.environ)
     env.pop("CC", None); env.pop("CXX", None)  # this image exports a gcc wrapper that lacks libgomp specs
     res = subprocess.run(cmd, capture_output=True, text=True, env=env)

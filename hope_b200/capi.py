@@ -78,8 +78,9 @@ def load_library():
         "hope_n_envs": (C.c_int, [vp]),
         "hope_planner_actions": (C.c_int, [vp, dp, C.POINTER(Out), dp, vp, C.c_double, vp]),
         "hope_planner_reset": (C.c_int, [vp, vp]),
+        "hope_fp64_peak_tflops": (C.c_int, [i32, C.POINTER(C.c_double)]),
         "hope_profile_enable": (C.c_int, [vp, i32]),
-        "hope_profile_read": (C.c_int, [vp, C.POINTER(C.c_double * 4), C.POINTER(u64 * 4)]),
+        "hope_profile_read": (C.c_int, [vp, C.POINTER(C.c_double * 8), C.POINTER(u64 * 8)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError here means the library does not match the header

@@ -1069,7 +1069,13 @@ __device__ bool chunk_is_bad(const WordSlot &s, const CheckEnv &E, const hope_pa
     return false;
 }
 
-constexpr int CHK_WARPS = 4;  // warps per block of k_rs_check
+#ifndef HOPE_CHK_WARPS
+#define HOPE_CHK_WARPS 4
+#endif
+#ifndef HOPE_CHK_MINBLOCKS
+#define HOPE_CHK_MINBLOCKS 4
+#endif
+constexpr int CHK_WARPS = HOPE_CHK_WARPS;  // warps per block of k_rs_check
 
 // asynchronous global -> shared copy of one WordSlot by a warp (LDGSTS, 16 bytes per lane per pass)
 __device__ __forceinline__ void stage_slot_async(WordSlot *dst, const WordSlot *src, int lane) {
@@ -1079,7 +1085,7 @@ __device__ __forceinline__ void stage_slot_async(WordSlot *dst, const WordSlot *
     __pipeline_commit();
 }
 
-__global__ void __launch_bounds__(CHK_WARPS * 32, 4) k_rs_check(Pool pool, EnvState st, Tables tb, RsScratch rs, hope_params par) {
+__global__ void __launch_bounds__(CHK_WARPS * 32, HOPE_CHK_MINBLOCKS) k_rs_check(Pool pool, EnvState st, Tables tb, RsScratch rs, hope_params par) {
     __shared__ WordSlot smem[CHK_WARPS][2];  // double buffer: the next word's plan streams in while this one is sampled
     const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_items = *rs.n_items;
@@ -1258,6 +1264,16 @@ __global__ void k_table_reduce(const double *__restrict__ dist_star, double *__r
     }
 }
 
+// float64 FMA throughput probe: 8 independent chains per thread so the pipe, not the latency, is measured
+__global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = __fma_rn(x0, a, b); x1 = __fma_rn(x1, a, b); x2 = __fma_rn(x2, a, b); x3 = __fma_rn(x3, a, b);
+        x4 = __fma_rn(x4, a, b); x5 = __fma_rn(x5, a, b); x6 = __fma_rn(x6, a, b); x7 = __fma_rn(x7, a, b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
 __global__ void k_table_group(const double *__restrict__ pmax, double *__restrict__ gpmax) {
     int q = threadIdx.x;
     if (q >= NRAY) return;
@@ -1328,7 +1344,7 @@ struct hope_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
     unsigned long long launches = 0;
     bool profile = false;
-    std::vector<cudaEvent_t> prof_events[4];  // begin/end pairs per kernel
+    std::vector<cudaEvent_t> prof_events[8];  // begin/end pairs per kernel
     std::string last_error;
 };
 
@@ -1454,12 +1470,16 @@ int launch_range(hope_ctx *ctx, const double *d_action, const hope_out &out_all,
         CK(cudaMemsetAsync(rs.n_items, 0, sizeof(int), s));
         k_rs_enumerate<<<(n + ENUM_THREADS - 1) / ENUM_THREADS, ENUM_THREADS, 0, s>>>(n, pool, st, tb, rs, out);
         prof_mark(ctx, 2, s);
-        prof_mark(ctx, 3, s);
         // persistent grids: the item count only exists on the device, so both kernels stride over it
-        k_rs_walk<<<ctx->walk_blocks, 128, 0, s>>>(rs, tb, ctx->par);
-        k_rs_check<<<ctx->check_blocks, CHK_WARPS * 32, 0, s>>>(pool, st, tb, rs, ctx->par);
-        k_rs_select<<<(n + 127) / 128, 128, 0, s>>>(n, tb, rs, out);
         prof_mark(ctx, 3, s);
+        k_rs_walk<<<ctx->walk_blocks, 128, 0, s>>>(rs, tb, ctx->par);
+        prof_mark(ctx, 3, s);
+        prof_mark(ctx, 4, s);
+        k_rs_check<<<ctx->check_blocks, CHK_WARPS * 32, 0, s>>>(pool, st, tb, rs, ctx->par);
+        prof_mark(ctx, 4, s);
+        prof_mark(ctx, 5, s);
+        k_rs_select<<<(n + 127) / 128, 128, 0, s>>>(n, tb, rs, out);
+        prof_mark(ctx, 5, s);
         ctx->launches += 4;
     }
     if (fork) CK(cudaStreamWaitEvent(s, lane.ev_observed, 0));
@@ -1917,17 +1937,45 @@ int hope_planner_reset(hope_ctx *ctx, void *stream) {
     return HOPE_OK;
 }
 
+int hope_fp64_peak_tflops(int device, double *tflops) {
+    if (!tflops) return HOPE_ERR_INVALID;
+    hope_ctx *ctx = nullptr;
+    CK(cudaSetDevice(device));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const int blocks = sms * 8, threads = 256, iters = 20000;
+    double *buf = nullptr;
+    CK(cudaMalloc(&buf, sizeof(double) * blocks * threads));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    k_fp64_peak<<<blocks, threads>>>(buf, 2000, 0.999999, 1e-9);  // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        CK(cudaEventRecord(e0));
+        k_fp64_peak<<<blocks, threads>>>(buf, iters, 0.999999, 1e-9);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best) best = ms;
+    }
+    CK(cudaGetLastError());
+    *tflops = 2.0 * 8.0 * (double)iters * blocks * threads / (best * 1e-3) / 1e12;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf);
+    return HOPE_OK;
+}
+
 int hope_profile_enable(hope_ctx *ctx, int on) {
     if (!ctx) return HOPE_ERR_INVALID;
     ctx->profile = on != 0;
     return HOPE_OK;
 }
 
-int hope_profile_read(hope_ctx *ctx, double h_ms[4], uint64_t h_launches[4]) {
+int hope_profile_read(hope_ctx *ctx, double h_ms[8], uint64_t h_launches[8]) {
     if (!ctx || !h_ms || !h_launches) return HOPE_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     CK(cudaDeviceSynchronize());
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 8; ++k) {
         auto &ev = ctx->prof_events[k];
         double total = 0.0;
         for (size_t i = 0; i + 1 < ev.size(); i += 2) {

@@ -176,10 +176,13 @@ int hope_set_state(hope_ctx *ctx, const double *h_pose, const int32_t *h_t, cons
 int hope_get_counters(hope_ctx *ctx, uint64_t h_counters[8]);
 /* Per-kernel device timing: when enabled every kernel launch of a step is bracketed by CUDA
  * events on the launch stream.  hope_profile_read synchronises, returns the accumulated
- * milliseconds and launch counts per kernel [0] advance [1] observe [2] rs_enumerate
- * [3] rs_check since the last read, and clears them. */
+ * milliseconds and launch counts per kernel [0] advance [1] observe [2] rs_enumerate [3] rs_walk
+ * [4] rs_check [5] rs_select ([6],[7] reserved) since the last read, and clears them. */
 int hope_profile_enable(hope_ctx *ctx, int on);
-int hope_profile_read(hope_ctx *ctx, double h_ms[4], uint64_t h_launches[4]);
+int hope_profile_read(hope_ctx *ctx, double h_ms[8], uint64_t h_launches[8]);
+/* Micro-benchmark for the roofline's compute axis: sustained float64 FMA rate of the device (8 independent DFMA
+ * chains per thread, SMs x 8 blocks x 256 threads), in TFLOP/s counting an FMA as 2.  Synchronous, ~20 ms. */
+int hope_fp64_peak_tflops(int device, double *tflops);
 int hope_n_envs(const hope_ctx *ctx);
 int hope_version(void);
 
