@@ -20,19 +20,19 @@ LEVELS = {"Normal": 0, "Complex": 1, "Extrem": 2}
 _NP = {C.c_double: np.float64, C.c_uint8: np.uint8, C.c_int32: np.int32}
 
 
-def generate_scenes(n, level="Normal", seed=42, nthreads=0):
+def generate_scenes(n, level="Normal", seed=42, nthreads=0, max_obs=16):
     """Host-side procedural scenes (parking_map_normal.py:40-494 semantics, own RNG streams).
     level: 'Normal' | 'Complex' | 'Extrem' | 'mix' (i % 3 cycles the three, BASELINE cfg 3)."""
-    lib = capi.load_library()
+    lib = capi.load_library(max_obs)
     if level == "mix":
-        parts = [generate_scenes((n - k + 2) // 3, lv, seed + 1000003 * k, nthreads) for k, lv in enumerate(LEVELS)]
+        parts = [generate_scenes((n - k + 2) // 3, lv, seed + 1000003 * k, nthreads, max_obs) for k, lv in enumerate(LEVELS)]
         out = {key: np.zeros((n,) + parts[0][key].shape[1:], dtype=parts[0][key].dtype) for key in parts[0]}
         for k in range(3):
             for key in out:
                 out[key][k::3] = parts[k][key]
         return out
     sc = dict(start=np.zeros((n, 3)), dest=np.zeros((n, 3)), bounds=np.zeros((n, 4)),
-              obs=np.zeros((n, capi.MAX_OBS, capi.MAX_VERTS, 2)), nverts=np.zeros((n, capi.MAX_OBS), dtype=np.int32),
+              obs=np.zeros((n, max_obs, capi.MAX_VERTS, 2)), nverts=np.zeros((n, max_obs), dtype=np.int32),
               case_id=np.zeros(n, dtype=np.int32))
     capi.check(lib.hope_generate_scenes(n, LEVELS[level], seed, nthreads, sc["start"].ctypes.data, sc["dest"].ctypes.data,
                                         sc["bounds"].ctypes.data, sc["obs"].ctypes.data, sc["nverts"].ctypes.data,
@@ -42,7 +42,7 @@ def generate_scenes(n, level="Normal", seed=42, nthreads=0):
 
 class BatchedParkingEnv(object):
     def __init__(self, n_envs, scenes=None, pool_size=None, level="Normal", seed=42, device=0, auto_reset=True,
-                 params=None, device_scenes=False):
+                 params=None, device_scenes=False, max_obs=None):
         """scenes: dict of host arrays (start/dest/bounds/obs/nverts) to upload as the pool; None -> generate
         `pool_size` (default 2 n) scenes of `level` on the host, or with device_scenes=True on the GPU
         (then finished envs also get a fresh device-generated scene instead of cycling the pool)."""
@@ -50,12 +50,15 @@ class BatchedParkingEnv(object):
         if not torch.cuda.is_available():
             raise capi.HopeError("BatchedParkingEnv needs a CUDA device; there is no CPU path")
         self.torch = torch
-        self.lib = capi.load_library()
+        if max_obs is None:  # scenes decide: anything wider than the default block needs the 128-ring build
+            max_obs = int(scenes["nverts"].shape[1]) if scenes is not None else 16
+        self.max_obs = max_obs
+        self.lib = capi.load_library(max_obs)
         self.n = int(n_envs)
         self.device = torch.device("cuda", device)
         if scenes is None and not device_scenes:
             pool_size = pool_size or 2 * self.n
-            scenes = generate_scenes(pool_size, level, seed)
+            scenes = generate_scenes(pool_size, level, seed, max_obs=max_obs)
         self.scenes = scenes
         self.pool_size = int(scenes["start"].shape[0]) if scenes is not None else int(pool_size or self.n)
         self.params = capi.Params()
@@ -91,6 +94,8 @@ class BatchedParkingEnv(object):
         f8 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
         s, d, b, o = f8(scenes["start"]), f8(scenes["dest"]), f8(scenes["bounds"]), f8(scenes["obs"])
         nv = np.ascontiguousarray(scenes["nverts"], dtype=np.int32)
+        if nv.shape[1] != self.max_obs or o.shape[1] != self.max_obs:
+            raise capi.HopeError(f"scene arrays hold {nv.shape[1]} rings per scene, this env was built for {self.max_obs}")
         capi.check(self.lib.hope_set_scene_pool(self.ctx, first, s.shape[0], s.ctypes.data, d.ctypes.data, b.ctypes.data,
                                                 o.ctypes.data, nv.ctypes.data), self.ctx)
 
@@ -103,7 +108,7 @@ class BatchedParkingEnv(object):
         """Read pool scenes back to the host (e.g. to hand device-generated scenes to a checker)."""
         n = self.pool_size - first if n is None else n
         sc = dict(start=np.zeros((n, 3)), dest=np.zeros((n, 3)), bounds=np.zeros((n, 4)),
-                  obs=np.zeros((n, capi.MAX_OBS, capi.MAX_VERTS, 2)), nverts=np.zeros((n, capi.MAX_OBS), dtype=np.int32))
+                  obs=np.zeros((n, self.max_obs, capi.MAX_VERTS, 2)), nverts=np.zeros((n, self.max_obs), dtype=np.int32))
         capi.check(self.lib.hope_get_scene_pool(self.ctx, first, n, sc["start"].ctypes.data, sc["dest"].ctypes.data, sc["bounds"].ctypes.data,
                                                 sc["obs"].ctypes.data, sc["nverts"].ctypes.data), self.ctx)
         return sc

@@ -7,6 +7,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhope_b200.so")
+# second build of the same sources with 128 obstacle rings per scene (Dragon Lake Parking scenes, scope row f3)
+VARIANTS = {16: LIB, 128: os.path.join(HERE, "libhope_b200_obs128.so")}
 SOURCES = ["hope_kernels.cu", "scene_gen.cu"]
 DEPS = SOURCES + ["hope_device.cuh", "scene_gen.h", os.path.join("..", "..", "include", "hope_b200.h")]
 NVCC_FLAGS = [
@@ -23,27 +25,36 @@ def nvcc_path():
     return cand
 
 
-def needs_build():
-    if not os.path.exists(LIB):
+def needs_build(max_obs=16):
+    lib = VARIANTS[max_obs]
+    if not os.path.exists(lib):
         return True
-    t = os.path.getmtime(LIB)
+    t = os.path.getmtime(lib)
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
-        return LIB
+def _command(max_obs, verbose):
     extra = os.environ.get("HOPE_B200_NVCC_DEFS", "").split()  # tuning experiments, e.g. "-DHOPE_CHK_MINBLOCKS=5"
-    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    if max_obs != 16:
+        extra = extra + [f"-DHOPE_MAX_OBS={max_obs}"]
+    return [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", VARIANTS[max_obs]] + \
+        [os.path.join(CSRC, s) for s in SOURCES]
+
+
+def build(force=False, verbose=False, variants=(16,)):
+    """Build the requested capacity variants (concurrently); returns the path of the first."""
+    todo = [v for v in variants if force or needs_build(v)]
     env = dict(os.environ)
     env.pop("CC", None); env.pop("CXX", None)  # this image exports a gcc wrapper that lacks libgomp specs
-    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
-    if verbose or res.returncode:
-        sys.stderr.write(res.stdout + res.stderr)
-    if res.returncode:
-        raise RuntimeError("nvcc failed building libhope_b200.so")
-    return LIB
+    procs = [(v, subprocess.Popen(_command(v, verbose), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)) for v in todo]
+    for v, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode:
+            sys.stderr.write(out)
+        if p.returncode:
+            raise RuntimeError(f"nvcc failed building {os.path.basename(VARIANTS[v])}")
+    return VARIANTS[variants[0]]
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variants=(16, 128) if "--all" in sys.argv else (16,)))

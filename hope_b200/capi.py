@@ -39,20 +39,21 @@ class Out(C.Structure):
     _fields_ = [(name, C.c_void_p) for name, _, _ in OUT_FIELDS]
 
 
-_LIB = None
+_LIBS = {}
 
 
-def load_library():
-    """Load (building if necessary) libhope_b200.so.  There is no fallback path: a missing
-    toolchain or library is an error."""
-    global _LIB
-    if _LIB is not None:
-        return _LIB
-    path = _build.LIB
-    if _build.needs_build():
-        path = _build.build()
+def load_library(max_obs=16):
+    """Load (building if necessary) libhope_b200.so, or its 128-obstacle build for max_obs=128.  There is no
+    fallback path: a missing toolchain or library is an error."""
+    if max_obs in _LIBS:
+        return _LIBS[max_obs]
+    if max_obs not in _build.VARIANTS:
+        raise HopeError(f"no build with {max_obs} obstacle rings per scene (have {sorted(_build.VARIANTS)})")
+    path = _build.VARIANTS[max_obs]
+    if _build.needs_build(max_obs):
+        path = _build.build(variants=(max_obs,))
     if not os.path.exists(path):
-        raise HopeError(f"{path} is missing; run `python -m hope_b200.build`")
+        raise HopeError(f"{path} is missing; run `python -m hope_b200.build --all`")
     lib = C.CDLL(path)
     vp, i32, u64, dp, ip = C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p
     sig = {
@@ -76,6 +77,7 @@ def load_library():
         "hope_set_state": (C.c_int, [vp, dp, ip, dp]),
         "hope_get_counters": (C.c_int, [vp, C.POINTER(u64 * 8)]),
         "hope_n_envs": (C.c_int, [vp]),
+        "hope_max_obs": (C.c_int, []),
         "hope_planner_actions": (C.c_int, [vp, dp, C.POINTER(Out), dp, vp, C.c_double, vp]),
         "hope_planner_reset": (C.c_int, [vp, vp]),
         "hope_fp64_peak_tflops": (C.c_int, [i32, C.POINTER(C.c_double)]),
@@ -85,7 +87,9 @@ def load_library():
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError here means the library does not match the header
         fn.restype, fn.argtypes = res, args
-    _LIB = lib
+    if lib.hope_max_obs() != max_obs:
+        raise HopeError(f"{path} was built for {lib.hope_max_obs()} obstacle rings, expected {max_obs}")
+    _LIBS[max_obs] = lib
     return lib
 
 

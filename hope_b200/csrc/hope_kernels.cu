@@ -29,7 +29,8 @@ namespace hope {
 
 constexpr int MAXO = HOPE_MAX_OBS;
 constexpr int MAXV = HOPE_MAX_VERTS;
-constexpr int MAXE = MAXO * MAXV;  // 64 edges
+constexpr int MAXE = MAXO * MAXV;  // 64 edges (512 in the obs128 build)
+static_assert(MAXO <= 256 && MAXE % 32 == 0, "obstacle indices are packed into 8 bits, edges staged 32 at a time");
 constexpr int NRAY = HOPE_N_LIDAR;
 constexpr int NACT = HOPE_N_ACTION;
 constexpr int NITER = HOPE_N_MASK_ITER;
@@ -99,7 +100,7 @@ __device__ __forceinline__ double4 ld_aabb(const double4 *p) {  // read-only pat
 struct AdvanceSmem {           // per warp
     double bx[32][4], by[32][4];   // current vehicle box of each lane's env
     int sid[32];
-    uint16_t queue[32 * MAXO];     // (lane << 4) | obstacle of every vehicle-AABB / obstacle-AABB overlap
+    uint16_t queue[32 * MAXO];     // (lane << 8) | obstacle of every vehicle-AABB / obstacle-AABB overlap
 };
 
 // Per-lane result: does lane's vehicle ring touch any obstacle ring of its scene
@@ -128,7 +129,7 @@ __device__ __forceinline__ unsigned warp_collisions(bool check, const double *bx
             over = !(vxmax < bb.x || bb.y < vxmin || vymax < bb.z || bb.w < vymin);  // disjoint boxes: exact reject
         }
         unsigned m = __ballot_sync(HOPE_FULL_MASK, over);
-        if (over) sm.queue[qn + __popc(m & ((1u << lane) - 1))] = (uint16_t)((lane << 4) | k);
+        if (over) sm.queue[qn + __popc(m & ((1u << lane) - 1))] = (uint16_t)((lane << 8) | k);
         qn += __popc(m);
     }
     __syncwarp();
@@ -138,7 +139,7 @@ __device__ __forceinline__ unsigned warp_collisions(bool check, const double *bx
         const int item = base + half;
         bool hit = false;
         if (item < qn) {
-            const int code = sm.queue[item], owner = code >> 4, k = code & 15;
+            const int code = sm.queue[item], owner = code >> 8, k = code & 255;
             if (!((collided >> owner) & 1)) {
                 const int osid = sm.sid[owner];
                 const int nv = pool.nv[(size_t)osid * MAXO + k];
@@ -151,8 +152,8 @@ __device__ __forceinline__ unsigned warp_collisions(bool check, const double *bx
             }
         }
         const unsigned m = __ballot_sync(HOPE_FULL_MASK, hit);
-        if (m & 0xffffu) collided |= 1u << (sm.queue[base] >> 4);
-        if ((m >> 16) && base + 1 < qn) collided |= 1u << (sm.queue[base + 1] >> 4);
+        if (m & 0xffffu) collided |= 1u << (sm.queue[base] >> 8);
+        if ((m >> 16) && base + 1 < qn) collided |= 1u << (sm.queue[base + 1] >> 8);
     }
     __syncwarp();
     return collided;
@@ -336,8 +337,8 @@ struct ObserveSmem {
     double L[NRAY];                                              // clip(lidar)+mask_base
     int steps[NACT + 2];
     uint8_t quad[MAXE];                                          // which ray quadrants can accept this edge
-    uint8_t qlist[4][MAXE];                                      // per quadrant: the edges that can be hit from it
-    uint8_t qcount[4];
+    uint16_t qlist[4][MAXE];                                     // per quadrant: the edges that can be hit from it
+    uint16_t qcount[4];
 };
 
 // n1/den and n2/den, each correctly rounded (== IEEE division), sharing one reciprocal: with r = RN(1/den)
@@ -365,8 +366,8 @@ __global__ void __launch_bounds__(64) k_observe(int n, Pool pool, EnvState st, T
     const double2 *verts = reinterpret_cast<const double2 *>(pool.obs) + (size_t)sid * MAXE;
     const uint8_t *nvp = pool.nv + (size_t)sid * MAXO;
     int n_edges = 0;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
+    const int n_slots = pool.nobs[sid] * MAXV;  // rings are compacted to the front of the scene block
+    for (int half = 0; half * 32 < n_slots; ++half) {
         int slot = half * 32 + lane, k = slot >> 2, j = slot & 3;
         int nv = nvp[k];
         bool valid = j < nv;
@@ -395,15 +396,15 @@ __global__ void __launch_bounds__(64) k_observe(int n, Pool pool, EnvState st, T
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         int cnt = 0;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        for (int half = 0; half < MAXE / 32; ++half) {
             const int e = half * 32 + lane;
+            if (half * 32 >= n_edges) break;
             const bool on = e < n_edges && ((sm.quad[e] >> q) & 1);
             const unsigned m = __ballot_sync(HOPE_FULL_MASK, on);
-            if (on) sm.qlist[q][cnt + __popc(m & ((1u << lane) - 1))] = (uint8_t)e;
+            if (on) sm.qlist[q][cnt + __popc(m & ((1u << lane) - 1))] = (uint16_t)e;
             cnt += __popc(m);
         }
-        if (lane == 0) sm.qcount[q] = (uint8_t)cnt;
+        if (lane == 0) sm.qcount[q] = (uint16_t)cnt;
     }
     __syncwarp();
 
@@ -1513,6 +1514,7 @@ int ensure_stage(hope_ctx *ctx) {
 extern "C" {
 
 int hope_version(void) { return 100; }
+int hope_max_obs(void) { return HOPE_MAX_OBS; }
 
 int hope_default_params(hope_params *p) {
     if (!p) return HOPE_ERR_INVALID;

@@ -24,7 +24,11 @@
 extern "C" {
 #endif
 
-#define HOPE_MAX_OBS 16
+#ifndef HOPE_MAX_OBS
+#define HOPE_MAX_OBS 16      /* obstacle rings per scene.  The library is also built with -DHOPE_MAX_OBS=128
+                                (libhope_b200_obs128.so) for the Dragon Lake Parking scenes (37-125 rings, row f3);
+                                hope_max_obs() reports the capacity of the loaded build */
+#endif
 #define HOPE_MAX_VERTS 4
 #define HOPE_N_LIDAR 120     /* configs.py:96  LIDAR_NUM */
 #define HOPE_N_ACTION 42     /* configs.py:115 N_DISCRETE_ACTION */
@@ -184,6 +188,7 @@ int hope_profile_read(hope_ctx *ctx, double h_ms[8], uint64_t h_launches[8]);
  * chains per thread, SMs x 8 blocks x 256 threads), in TFLOP/s counting an FMA as 2.  Synchronous, ~20 ms. */
 int hope_fp64_peak_tflops(int device, double *tflops);
 int hope_n_envs(const hope_ctx *ctx);
+int hope_max_obs(void);
 int hope_version(void);
 
 #ifdef __cplusplus

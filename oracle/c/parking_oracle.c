@@ -28,7 +28,9 @@
 #include <omp.h>
 #endif
 
-#define MAX_OBS 16
+#ifndef MAX_OBS
+#define MAX_OBS 16 /* -DMAX_OBS=128 builds the variant for Dragon Lake Parking scenes */
+#endif
 #define MAX_V 4
 #define N_RAY 120
 #define N_UP 1200
@@ -801,3 +803,4 @@ int orc_orient(double ax, double ay, double bx, double by, double cx, double cy)
 int orc_seg_hit(const double *p) { return seg_hit(p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7]); }
 double orc_clip_area(const double *sx, const double *sy, const double *cx, const double *cy) { return clip_area(sx, sy, cx, cy); }
 int orc_sizeof_io(void) { return (int)sizeof(orc_io); }
+int orc_max_obs(void) { return MAX_OBS; }

@@ -24,6 +24,7 @@ from . import geom
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_build", "libparking_oracle.so")
+LIB_PATHS = {16: LIB_PATH, 128: os.path.join(HERE, "_build", "libparking_oracle_obs128.so")}
 
 MAX_OBS, MAX_V, N_RAY, N_UP, N_ACT, N_ITER = 16, 4, 120, 1200, 42, 10
 WHEEL_BASE, LIDAR_RANGE = 2.8, 10.0
@@ -33,7 +34,7 @@ MAXC = math.tan(0.75) / WHEEL_BASE  # car_parking_base.py:422
 
 def build(force=False):
     src = os.path.join(HERE, "c", "parking_oracle.c")
-    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
+    if force or any(not os.path.exists(p) or os.path.getmtime(p) < os.path.getmtime(src) for p in LIB_PATHS.values()):
         subprocess.check_call(["make", "-C", HERE, "-s"])
     return LIB_PATH
 
@@ -163,14 +164,14 @@ class _IO(C.Structure):
     _fields_ = [(k, C.POINTER(t)) for k, t in _IO_FIELDS]
 
 
-_LIB = None
+_LIBS = {}
 
 
-def lib():
-    global _LIB
-    if _LIB is None:
+def lib(max_obs=16):
+    if max_obs not in _LIBS:
         build()
-        _LIB = C.CDLL(LIB_PATH)
+        _LIB = C.CDLL(LIB_PATHS[max_obs])
+        assert _LIB.orc_max_obs() == max_obs
         _LIB.orc_step.restype = C.c_int
         _LIB.orc_step.argtypes = [C.c_int, C.POINTER(_IO), C.c_void_p, C.c_void_p, C.POINTER(_Tables), C.c_int, C.c_int]
         _LIB.orc_rs_all_paths.restype = C.c_int
@@ -179,7 +180,8 @@ def lib():
         _LIB.orc_seg_hit.restype = C.c_int
         _LIB.orc_clip_area.restype = C.c_double
         assert _LIB.orc_sizeof_io() == C.sizeof(_IO)
-    return _LIB
+        _LIBS[max_obs] = _LIB
+    return _LIBS[max_obs]
 
 
 def _ptr(a, t):
@@ -198,6 +200,7 @@ class OracleEnv(object):
 
     def __init__(self, start, dest, bounds, obs, nverts, tables=None, nthreads=0):
         self.n = n = start.shape[0]
+        MAX_OBS = int(np.asarray(nverts).shape[1])  # 16, or 128 for Dragon Lake Parking scenes
         f8 = lambda a, s: np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape((n,) + s))
         self.start, self.dest, self.bounds = f8(start, (3,)), f8(dest, (3,)), f8(bounds, (4,))
         self.obs = f8(obs, (MAX_OBS, MAX_V, 2))
@@ -217,7 +220,7 @@ class OracleEnv(object):
         arrs = dict(start=self.start, dest=self.dest, bounds=self.bounds, obs=self.obs, nverts=self.nverts,
                     pose=self.pose, accum=self.accum, t=self.t, **self.out)
         self._io = _IO(*[_ptr(arrs[k], t) for k, t in _IO_FIELDS])
-        self._lib = lib()
+        self._lib = lib(MAX_OBS)
 
     def reset_state(self, idx=None):
         idx = slice(None) if idx is None else idx
