@@ -211,6 +211,47 @@ def run_rollout(args, rank, local_rank, world, dev):
     env.close()
 
 
+def run_dlp(args, rank, local_rank, world, dev):
+    """Row f3: full step on Dragon Lake Parking scenes (31-119 obstacle rings, 128-ring build of the library).
+    Scenes: the 16 fixture cases of tests/golden/dlp_cases.npz, each prepared with different random starts."""
+    import torch
+    from hope_b200 import dlp
+    from hope_b200.batched_env import BatchedParkingEnv
+    n = args.envs if args.envs != ENVS_PER_GPU else 16384
+    K, W = args.steps, max(3, args.warmup)
+    cases = dlp.cases_from_fixture(np.load(os.path.join(ROOT, "tests", "golden", "dlp_cases.npz")))
+    sc = dlp.prepare_scenes(cases, np.arange(2 * n) % len(cases), seed=scene_seed(rank))
+    env = BatchedParkingEnv(n, scenes=sc, device=local_rank, auto_reset=True)
+    env.reset()
+    gen = torch.Generator(device=dev); gen.manual_seed(7 + rank)
+    actions = torch.rand((K + W, n, 2), dtype=torch.float64, device=dev, generator=gen) * 2 - 1
+    for k in range(W):
+        env.step(actions[k])
+    torch.cuda.synchronize()
+    c0 = env.counters()
+    env.profile(True); env.profile_read()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(W, W + K):
+        env.step(actions[k])
+    e1.record()
+    torch.cuda.synchronize()
+    prof = env.profile_read()
+    ms = reduce_scalar(e0.elapsed_time(e1), "max", world, dev)
+    c1 = env.counters()
+    steps = reduce_scalar(float(c1["env_steps"] - c0["env_steps"]), "sum", world, dev)
+    if rank == 0:
+        nobs = (sc["nverts"] > 0).sum(axis=1)
+        print(json.dumps({
+            "metric": "env-steps/sec", "value": steps / (ms * 1e-3), "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "dlp fixture cases",
+            "gpu_launches": c1["kernel_launches"] - c0["kernel_launches"],
+            "kernels_ms_per_launch": {k: (v[0] / v[1] if v[1] else None) for k, v in prof.items()},
+            "config": {"workload": "row f3: full step on Dragon Lake Parking scenes, 128-ring build", "envs_per_gpu": n,
+                       "obstacle_rings_per_scene": {"min": int(nobs.min()), "mean": float(nobs.mean()), "max": int(nobs.max())}}}))
+    env.close()
+
+
 def run_sac(args, rank, local_rank, world, dev):
     """BASELINE cfg 5: 65 536 envs per GPU, SAC-style acting + replay + one update every 8 env steps, gradients of
     actor + twin critics reduced with a single NCCL all-reduce that overlaps the following rollout steps."""
@@ -258,7 +299,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="scenes per GPU (default: the BASELINE cfg-3 size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--config", default="step", choices=["step", "rollout", "sac"],
+    ap.add_argument("--config", default="step", choices=["step", "rollout", "sac", "dlp"],
                     help="step: BASELINE cfg 3 (default, the headline metric); rollout: cfg 4, PPO acting loop with the transformer policy")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -283,6 +324,8 @@ def main():
         return run_rollout(args, rank, local_rank, world, dev)
     if args.config == "sac":
         return run_sac(args, rank, local_rank, world, dev)
+    if args.config == "dlp":
+        return run_dlp(args, rank, local_rank, world, dev)
 
     # scene id -> GPU: rank r owns scenes [r*2n, (r+1)*2n) of the global synthetic pool
     scenes = generate_scenes(2 * n, "mix", scene_seed(rank))
