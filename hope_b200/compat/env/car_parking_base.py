@@ -99,14 +99,16 @@ class CarParking(object):
         self._device = device
         self._seed = int(np.random.SeedSequence(seed).generate_state(1)[0]) if seed is None else int(seed)
         self._episode = 0
+        self._backends = {}      # obstacle capacity (16 | 128) -> BatchedParkingEnv
         self._backend = None
+        self._dlp_cases = None
         self._pending_scene = None
 
     # ---- scene handling ---------------------------------------------------------------------------
+    DLP_PATH = "../data/dlp.data"  # ParkingMapDLP.default['path'] (parking_map_dlp.py:15-17), relative to src/
+
     def set_level(self, level=None):
         self.level = "Normal" if level is None else level
-        if self.level == "dlp":
-            raise NotImplementedError("DLP scenes are scope row f3")
         self.map = _Map(self.level)
 
     def load_scene(self, scene):
@@ -116,6 +118,15 @@ class CarParking(object):
     def _next_scene(self, case_id):
         if self._pending_scene is not None:
             sc, self._pending_scene = self._pending_scene, None
+            return sc
+        if self.level == "dlp":  # ParkingMapDLP.reset (parking_map_dlp.py:38-86) through the shapely-free reader
+            from hope_b200 import dlp
+            if self._dlp_cases is None:
+                self._dlp_cases = dlp.read_dlp(self.DLP_PATH)
+            self._episode += 1
+            rng = np.random.default_rng(self._seed + self._episode)
+            cid = int(rng.integers(0, len(self._dlp_cases))) if case_id is None else int(case_id) % len(self._dlp_cases)
+            sc = dlp.prepare_scenes(self._dlp_cases, [cid], seed=self._seed + self._episode)
             return sc
         for _ in range(64):  # hope_generate_scenes draws bay/parallel itself; honour an explicit case_id
             self._episode += 1
@@ -131,10 +142,12 @@ class CarParking(object):
         sc = self._next_scene(case_id)
         self.map.map_level = self.level
         self.map.load(sc)
-        if self._backend is None:
-            self._backend = BatchedParkingEnv(1, scenes=sc, device=self._device, auto_reset=False)
+        cap = int(np.asarray(sc["nverts"]).shape[1])
+        if cap not in self._backends:
+            self._backends[cap] = BatchedParkingEnv(1, scenes=sc, device=self._device, auto_reset=False)
         else:
-            self._backend.set_scene_pool(sc)
+            self._backends[cap].set_scene_pool(sc)
+        self._backend = self._backends[cap]
         self.t = 1.0
         out = self._backend.reset_host(outputs=self._OUT)
         self.vehicle.initial_state = self.map.start
@@ -177,6 +190,6 @@ class CarParking(object):
         return None
 
     def close(self):
-        if self._backend is not None:
-            self._backend.close()
-            self._backend = None
+        for b in self._backends.values():
+            b.close()
+        self._backends, self._backend = {}, None

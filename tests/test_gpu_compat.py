@@ -84,3 +84,20 @@ def test_replays_a_recorded_reference_episode(compat_env, golden_dir, level):
                     assert np.abs(np.array(p.lengths) - g["rs_lengths"][i][:len(want)]).max() < 1e-9
     assert n_found > 0
     env.close()
+
+
+def test_facade_switches_to_dlp_scenes(compat_env, golden_dir):
+    """eval_mix_scene.py drives `env.reset(case_id, None, 'dlp')`; the facade reads the cases itself."""
+    from hope_b200 import dlp
+    CarParking, CarParkingWrapper, Status, _ = compat_env
+    raw = CarParking(render_mode="rgb_array", verbose=False, use_img_observation=False)
+    raw._dlp_cases = dlp.cases_from_fixture(np.load(os.path.join(golden_dir, "dlp_cases.npz")))  # instead of ../data/dlp.data
+    env = CarParkingWrapper(raw)
+    obs = env.reset(3, None, "dlp")
+    assert env.map.map_level == "dlp" and len(env.map.obstacles) > 16
+    assert obs["lidar"].shape == (120,) and (obs["lidar"] < 9.9).any()
+    obs, reward, done, info = env.step(np.array([0.0, 0.5]))
+    assert np.isfinite(obs["lidar"]).all() and isinstance(info["status"], Status)
+    obs = env.reset(None, None, "Normal")   # and back to the 16-ring backend
+    assert len(env.map.obstacles) <= 16
+    env.close()
