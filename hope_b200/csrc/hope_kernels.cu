@@ -480,19 +480,21 @@ __global__ void __launch_bounds__(64) k_observe(int n, Pool pool, EnvState st, T
                 const double db = __shfl_sync(HOPE_FULL_MASK, d, bsel);
                 const int rb = __shfl_sync(HOPE_FULL_MASK, rho, bsel);
                 const double *P = tb.pmaxk + (size_t)rb * NITER * NACT;  // [k][j], j contiguous
-                // every lane fetches the running maxima of its action(s) below its current bound in one batch of
-                // independent, coalesced loads (row k is 42 contiguous doubles), then finds the first exceedance
+                // every lane fetches the 10 running maxima of its action(s) in one batch of independent, coalesced,
+                // unconditional loads (row k is 42 contiguous doubles; lanes without a second action re-read column
+                // 32), then takes the first exceedance; rows at or above the current bound cannot lower it
+                const double *P0 = P + lane, *P1 = P + 32 + (has2 ? lane : 0);
                 double v0[NITER], v1[NITER];
 #pragma unroll
-                for (int k = 0; k < NITER; ++k) {
-                    v0[k] = (k < s0) ? __ldg(P + k * NACT + lane) : INFINITY;
-                    v1[k] = (has2 && k < s1) ? __ldg(P + k * NACT + 32 + lane) : INFINITY;
-                }
+                for (int k = 0; k < NITER; ++k) { v0[k] = __ldg(P0 + k * NACT); v1[k] = __ldg(P1 + k * NACT); }
+                int f0 = NITER, f1 = NITER;
 #pragma unroll
                 for (int k = NITER - 1; k >= 0; --k) {
-                    if (db < v0[k]) s0 = min(s0, k);
-                    if (db < v1[k]) s1 = min(s1, k);
+                    if (db < v0[k]) f0 = k;
+                    if (db < v1[k]) f1 = k;
                 }
+                s0 = min(s0, f0);
+                if (has2) s1 = min(s1, f1);
             }
         }
     }
