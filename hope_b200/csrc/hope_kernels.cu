@@ -1330,6 +1330,8 @@ struct hope_ctx {
     static constexpr int MAX_LANES = 4;
     struct Lane { cudaStream_t main = nullptr, aux = nullptr; cudaEvent_t ev_advanced = nullptr, ev_observed = nullptr; } lanes[MAX_LANES];
     int host_chunks = 4;
+    int device_chunks = 1;  // hope_step: env ranges stepped on separate lanes so one range's latency-bound kernels
+                            // (advance, enumerate, walk) run under another range's issue-bound ones (observe, check)
     // hope_step_host replays a captured CUDA graph of the whole pipelined step while the caller keeps passing the
     // same buffers (one launch instead of ~120 driver calls per step)
     bool host_graph_enabled = true;
@@ -1621,6 +1623,7 @@ int hope_create(hope_ctx **out, int device, int n_envs, int pool_size, const hop
     if (const char *e = getenv("HOPE_B200_HOST_GRAPH")) ctx->host_graph_enabled = atoi(e) != 0;
     if (const char *e = getenv("HOPE_B200_ZERO_COPY")) ctx->zero_copy_enabled = atoi(e) != 0;
     memset(&ctx->step_out, 0, sizeof(ctx->step_out));
+    if (const char *e = getenv("HOPE_B200_DEVICE_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= 16) ctx->device_chunks = v; }
     if (const char *e = getenv("HOPE_B200_HOST_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->host_chunks = v; }
     CK(cudaFuncSetAttribute(k_observe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((OBS_THREADS / 32) * sizeof(ObserveSmem))));
     return HOPE_OK;
@@ -1776,7 +1779,27 @@ int hope_step(hope_ctx *ctx, const double *d_action, const hope_out *d_out, unsi
     if (!ctx->have_tables) return HOPE_ERR_NO_TABLES;
     if (!ctx->have_reset) return HOPE_ERR_NO_SCENES;
     CK(cudaSetDevice(ctx->device));
-    return launch_step(ctx, d_action, *d_out, stages | HOPE_STAGE_ADVANCE, 0, static_cast<cudaStream_t>(stream));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    stages |= HOPE_STAGE_ADVANCE;
+    const int n = ctx->n;
+    int chunks = ctx->device_chunks;
+    if (n < 8192 * chunks) chunks = n / 8192 > 0 ? n / 8192 : 1;
+    if (chunks <= 1) return launch_step(ctx, d_action, *d_out, stages, 0, s);
+    // fork the lanes from the caller's stream, one env range per lane (round robin), join back
+    const int per = ((n + chunks - 1) / chunks + 127) / 128 * 128;
+    CK(cudaEventRecord(ctx->ev_fork, s));
+    for (int li = 0; li < hope_ctx::MAX_LANES; ++li) CK(cudaStreamWaitEvent(ctx->lanes[li].main, ctx->ev_fork, 0));
+    for (int c = 0, lo = 0; lo < n; ++c, lo += per) {
+        const int cnt = (lo + per <= n) ? per : n - lo;
+        const int li = c % hope_ctx::MAX_LANES;
+        int rc = launch_range(ctx, d_action, *d_out, stages, 0, ctx->lanes[li].main, li, c, lo, cnt);
+        if (rc) return rc;
+    }
+    for (int li = 0; li < hope_ctx::MAX_LANES; ++li) {
+        CK(cudaEventRecord(ctx->ev_join[li], ctx->lanes[li].main));
+        CK(cudaStreamWaitEvent(s, ctx->ev_join[li], 0));
+    }
+    return HOPE_OK;
 }
 
 int hope_step_kinematics_collision(hope_ctx *ctx, const double *d_action, double *d_pose, uint8_t *d_collided, uint8_t *d_substeps,
