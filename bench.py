@@ -252,6 +252,40 @@ def run_dlp(args, rank, local_rank, world, dev):
     env.close()
 
 
+def run_cfg2(args, rank, local_rank, world, dev):
+    """BASELINE cfg 2: 4 096 parallel scenes (level Normal), kinematics + ring collision (+ arrival) only."""
+    import torch
+    from hope_b200.batched_env import BatchedParkingEnv, generate_scenes
+    n = args.envs if args.envs != ENVS_PER_GPU else 4096
+    K, W = args.steps, max(3, args.warmup)
+    env = BatchedParkingEnv(n, scenes=generate_scenes(2 * n, "Normal", scene_seed(rank)), device=local_rank, auto_reset=True)
+    env.reset()
+    gen = torch.Generator(device=dev); gen.manual_seed(3 + rank)
+    actions = torch.rand((K + W, n, 2), dtype=torch.float64, device=dev, generator=gen) * 2 - 1
+    for k in range(W):
+        env.step_kinematics_collision(actions[k])
+    torch.cuda.synchronize()
+    c0 = env.counters()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(W, W + K):
+        env.step_kinematics_collision(actions[k])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = reduce_scalar(e0.elapsed_time(e1), "max", world, dev)
+    c1 = env.counters()
+    steps = reduce_scalar(float(c1["env_steps"] - c0["env_steps"]), "sum", world, dev)
+    if rank == 0:
+        print(json.dumps({
+            "metric": "env-steps/sec", "value": steps / (ms * 1e-3), "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "gpu_launches": c1["kernel_launches"] - c0["kernel_launches"],
+            "roofline": {"bound": "hbm", "kernel": "k_advance", "achieved": ALGO_BYTES["k_advance"] * n / (ms / K * 1e-3) / 1e9, "unit": "GB/s",
+                         "note": "launch-latency bound at 4 096 scenes (one 32-block kernel per step)"},
+            "config": {"workload": "cfg2: kinematics + ring collision (+ arrival) only, level Normal", "envs_per_gpu": n}}))
+    env.close()
+
+
 def run_sac(args, rank, local_rank, world, dev):
     """BASELINE cfg 5: 65 536 envs per GPU, SAC-style acting + replay + one update every 8 env steps, gradients of
     actor + twin critics reduced with a single NCCL all-reduce that overlaps the following rollout steps."""
@@ -299,7 +333,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="scenes per GPU (default: the BASELINE cfg-3 size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--config", default="step", choices=["step", "rollout", "sac", "dlp"],
+    ap.add_argument("--config", default="step", choices=["step", "rollout", "sac", "dlp", "cfg2"],
                     help="step: BASELINE cfg 3 (default, the headline metric); rollout: cfg 4, PPO acting loop with the transformer policy")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -326,6 +360,8 @@ def main():
         return run_sac(args, rank, local_rank, world, dev)
     if args.config == "dlp":
         return run_dlp(args, rank, local_rank, world, dev)
+    if args.config == "cfg2":
+        return run_cfg2(args, rank, local_rank, world, dev)
 
     # scene id -> GPU: rank r owns scenes [r*2n, (r+1)*2n) of the global synthetic pool
     scenes = generate_scenes(2 * n, "mix", scene_seed(rank))
