@@ -550,36 +550,48 @@ __device__ bool w_SLS(double x, double y, double phi, Tuv &o) {  // reeds_shepp.
     }
     return false;
 }
-__device__ bool w_LSL(double x, double y, double phi, Tuv &o) {  // :79-87
-    double s, c;
-    sincos(phi, &s, &c);
-    double ax = x - s, ay = y - 1.0 + c;
-    double t = atan2(ay, ax);
+// One "frame" = one reflection (x, y, phi) -> (+-x, +-y, +-phi) of the normalised goal.  Every word formula
+// starts from one of two points, A = (x - sin phi, y - 1 + cos phi) or B = (x + sin phi, y - 1 - cos phi), in polar
+// form; the reference recomputes sin/cos/hypot/atan2 inside each of its 44 calls, here each frame does it once.
+// sin(-phi) = -sin(phi) and cos(-phi) = cos(phi) hold exactly for the libdevice routines, and hypot is symmetric
+// in its arguments and their signs, so the shared values are the ones each formula would have computed.
+struct Frame {
+    double x, y, phi;
+    double xi, eta;         // B
+    double rA, tA;          // |A|, atan2(A.y, A.x)
+    double rB, tB, tB2;     // |B|, atan2(B.y, B.x), atan2(B.x, -B.y)
+};
+__device__ __forceinline__ void make_frame(Frame &F, double x, double y, double phi, double s, double c, bool forward) {
+    F.x = x; F.y = y; F.phi = phi;
+    const double ax = x - s, ay = y - 1.0 + c;
+    F.xi = x + s; F.eta = y - 1.0 - c;
+    F.rA = hypot(ax, ay); F.tA = atan2(ay, ax);
+    F.rB = hypot(F.xi, F.eta);
+    F.tB2 = atan2(F.xi, -F.eta);
+    F.tB = forward ? atan2(F.eta, F.xi) : 0.0;  // only LSR needs it, and LSR has no "backwards" variant
+}
+__device__ bool w_LSL(const Frame &F, Tuv &o) {  // :79-87
+    const double t = F.tA;
     if (t >= 0.0) {
-        double v = rs_M(phi - t);
-        if (v >= 0.0) { o.t = t; o.u = hypot(ax, ay); o.v = v; return true; }
+        double v = rs_M(F.phi - t);
+        if (v >= 0.0) { o.t = t; o.u = F.rA; o.v = v; return true; }
     }
     return false;
 }
-__device__ bool w_LSR(double x, double y, double phi, Tuv &o) {  // :90-103
-    double s, c;
-    sincos(phi, &s, &c);
-    double ax = x + s, ay = y - 1.0 - c;
-    double u1 = hypot(ax, ay), t1 = atan2(ay, ax);
+__device__ bool w_LSR(const Frame &F, Tuv &o) {  // :90-103
+    double u1 = F.rB;
+    const double t1 = F.tB;
     u1 = u1 * u1;
     if (u1 >= 4.0) {
-        double u = sqrt(u1 - 4.0), th = atan2(2.0, u), t = rs_M(t1 + th), v = rs_M(t - phi);
+        double u = sqrt(u1 - 4.0), th = atan2(2.0, u), t = rs_M(t1 + th), v = rs_M(t - F.phi);
         if (t >= 0.0 && v >= 0.0) { o.t = t; o.u = u; o.v = v; return true; }
     }
     return false;
 }
-__device__ bool w_LRL(double x, double y, double phi, Tuv &o) {  // :106-117
-    double s, c;
-    sincos(phi, &s, &c);
-    double ax = x - s, ay = y - 1.0 + c;
-    double u1 = hypot(ax, ay), t1 = atan2(ay, ax);
+__device__ bool w_LRL(const Frame &F, Tuv &o) {  // :106-117
+    const double u1 = F.rA, t1 = F.tA;
     if (u1 <= 4.0) {
-        double u = -2.0 * asin(0.25 * u1), t = rs_M(t1 + 0.5 * u + HOPE_PI), v = rs_M(phi - t + u);
+        double u = -2.0 * asin(0.25 * u1), t = rs_M(t1 + 0.5 * u + HOPE_PI), v = rs_M(F.phi - t + u);
         if (t >= 0.0 && u <= 0.0) { o.t = t; o.u = u; o.v = v; return true; }
     }
     return false;
@@ -595,62 +607,49 @@ __device__ void tau_omega(double u, double v, double xi, double eta, double phi,
     tau = t2 < 0 ? rs_M(t1 + HOPE_PI) : rs_M(t1);
     omega = rs_M(tau - u + v - phi);
 }
-__device__ bool w_LRLRn(double x, double y, double phi, Tuv &o) {  // :246-257
-    double s, c;
-    sincos(phi, &s, &c);
-    double xi = x + s, eta = y - 1.0 - c, rho = 0.25 * (2.0 + sqrt(xi * xi + eta * eta));
+__device__ bool w_LRLRn(const Frame &F, Tuv &o) {  // :246-257
+    const double xi = F.xi, eta = F.eta, rho = 0.25 * (2.0 + sqrt(xi * xi + eta * eta));
     if (rho <= 1.0) {
         double u = acos(rho), t, v;
-        tau_omega(u, -u, xi, eta, phi, t, v);
+        tau_omega(u, -u, xi, eta, F.phi, t, v);
         if (t >= 0.0 && v <= 0.0) { o.t = t; o.u = u; o.v = v; return true; }
     }
     return false;
 }
-__device__ bool w_LRLRp(double x, double y, double phi, Tuv &o) {  // :260-272
-    double s, c;
-    sincos(phi, &s, &c);
-    double xi = x + s, eta = y - 1.0 - c, rho = (20.0 - xi * xi - eta * eta) / 16.0;
+__device__ bool w_LRLRp(const Frame &F, Tuv &o) {  // :260-272
+    const double xi = F.xi, eta = F.eta, rho = (20.0 - xi * xi - eta * eta) / 16.0;
     if (0.0 <= rho && rho <= 1.0) {
         double u = -acos(rho);
         if (u >= -0.5 * HOPE_PI) {
             double t, v;
-            tau_omega(u, u, xi, eta, phi, t, v);
+            tau_omega(u, u, xi, eta, F.phi, t, v);
             if (t >= 0.0 && v >= 0.0) { o.t = t; o.u = u; o.v = v; return true; }
         }
     }
     return false;
 }
-__device__ bool w_LRSR(double x, double y, double phi, Tuv &o) {  // :311-323
-    double s, c;
-    sincos(phi, &s, &c);
-    double xi = x + s, eta = y - 1.0 - c;
-    double rho = hypot(-eta, xi), theta = atan2(xi, -eta);
+__device__ bool w_LRSR(const Frame &F, Tuv &o) {  // :311-323  R(-eta, xi)
+    const double rho = F.rB, theta = F.tB2;
     if (rho >= 2.0) {
-        double t = theta, u = 2.0 - rho, v = rs_M(t + 0.5 * HOPE_PI - phi);
+        double t = theta, u = 2.0 - rho, v = rs_M(t + 0.5 * HOPE_PI - F.phi);
         if (t >= 0.0 && u <= 0.0 && v <= 0.0) { o.t = t; o.u = u; o.v = v; return true; }
     }
     return false;
 }
-__device__ bool w_LRSL(double x, double y, double phi, Tuv &o) {  // :326-339
-    double s, c;
-    sincos(phi, &s, &c);
-    double xi = x - s, eta = y - 1.0 + c;
-    double rho = hypot(xi, eta), theta = atan2(eta, xi);
+__device__ bool w_LRSL(const Frame &F, Tuv &o) {  // :326-339
+    const double rho = F.rA, theta = F.tA;
     if (rho >= 2.0) {
-        double r = sqrt(rho * rho - 4.0), u = 2.0 - r, t = rs_M(theta + atan2(r, -2.0)), v = rs_M(phi - 0.5 * HOPE_PI - t);
+        double r = sqrt(rho * rho - 4.0), u = 2.0 - r, t = rs_M(theta + atan2(r, -2.0)), v = rs_M(F.phi - 0.5 * HOPE_PI - t);
         if (t >= 0.0 && u <= 0.0 && v <= 0.0) { o.t = t; o.u = u; o.v = v; return true; }
     }
     return false;
 }
-__device__ bool w_LRSLR(double x, double y, double phi, Tuv &o) {  // :414-429
-    double s, c;
-    sincos(phi, &s, &c);
-    double xi = x + s, eta = y - 1.0 - c;
-    double rho = hypot(xi, eta);
+__device__ bool w_LRSLR(const Frame &F, Tuv &o) {  // :414-429
+    const double xi = F.xi, eta = F.eta, rho = F.rB;
     if (rho >= 2.0) {
         double u = 4.0 - sqrt(rho * rho - 4.0);
         if (u <= 0.0) {
-            double t = rs_M(atan2((4.0 - u) * xi - 2.0 * eta, -2.0 * xi + (u - 4.0) * eta)), v = rs_M(t - phi);
+            double t = rs_M(atan2((4.0 - u) * xi - 2.0 * eta, -2.0 * xi + (u - 4.0) * eta)), v = rs_M(t - F.phi);
             if (t >= 0.0 && v >= 0.0) { o.t = t; o.u = u; o.v = v; return true; }
         }
     }
@@ -725,21 +724,31 @@ __device__ int enumerate_env(int i, const Pool &pool, const EnvState &st, const 
     double sp, cp;
     sincos(phi, &sp, &cp);
     const double xb = x * cp + y * sp, yb = x * sp - y * cp;  // :206-207, :376-377
+    // the four reflections (x,y,phi) (-x,y,-phi) (x,-y,-phi) (-x,-y,phi) of the goal and of the "backwards" goal
+    Frame frames[8];
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+        const double X = b ? xb : x, Y = b ? yb : y;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const bool neg = (r == 1 || r == 2);
+            make_frame(frames[4 * b + r], (r & 1) ? -X : X, (r & 2) ? -Y : Y, neg ? -phi : phi, neg ? -sp : sp, cp, b == 0);
+        }
+    }
     for (int f = 0; f < 11; ++f) {
         const Family F = c_families[f];
-        const double X = F.back ? xb : x, Y = F.back ? yb : y;
         for (int r = 0; r < 4; ++r) {
-            double ax = (r & 1) ? -X : X, ay = (r & 2) ? -Y : Y, ap = (r == 1 || r == 2) ? -phi : phi;
+            const Frame &fr = frames[4 * F.back + r];
             bool ok;
             switch (F.fn) {
-            case F_LSL: ok = w_LSL(ax, ay, ap, o); break;
-            case F_LSR: ok = w_LSR(ax, ay, ap, o); break;
-            case F_LRL: ok = w_LRL(ax, ay, ap, o); break;
-            case F_LRLRn: ok = w_LRLRn(ax, ay, ap, o); break;
-            case F_LRLRp: ok = w_LRLRp(ax, ay, ap, o); break;
-            case F_LRSL: ok = w_LRSL(ax, ay, ap, o); break;
-            case F_LRSR: ok = w_LRSR(ax, ay, ap, o); break;
-            default: ok = w_LRSLR(ax, ay, ap, o); break;
+            case F_LSL: ok = w_LSL(fr, o); break;
+            case F_LSR: ok = w_LSR(fr, o); break;
+            case F_LRL: ok = w_LRL(fr, o); break;
+            case F_LRLRn: ok = w_LRLRn(fr, o); break;
+            case F_LRLRp: ok = w_LRLRp(fr, o); break;
+            case F_LRSL: ok = w_LRSL(fr, o); break;
+            case F_LRSR: ok = w_LRSR(fr, o); break;
+            default: ok = w_LRSLR(fr, o); break;
             }
             if (!ok) continue;
             const double H = -0.5 * HOPE_PI;
