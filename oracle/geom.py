@@ -186,3 +186,22 @@ def segment_ring_intersection_points(p0, p1, ring):
                 if _on_segment_box(*c, *q0, *q1):
                     pts.append(c)
     return pts
+
+
+def ring_centroid(ring):
+    """Centroid of a lineal geometry (`LinearRing.centroid`, car_parking_base.py:328): GEOS
+    `Centroid::addLineSegments` — length-weighted mean of the segment mid-points, accumulated in ring
+    order; zero-length segments skipped; length = sqrt(dx*dx + dy*dy)."""
+    total = 0.0
+    sx = 0.0
+    sy = 0.0
+    for i in range(len(ring) - 1):
+        (x0, y0), (x1, y1) = ring[i], ring[i + 1]
+        dx, dy = x0 - x1, y0 - y1
+        seg = math.sqrt(dx * dx + dy * dy)
+        if seg == 0.0:
+            continue
+        total += seg
+        sx += seg * ((x0 + x1) / 2)
+        sy += seg * ((y0 + y1) / 2)
+    return sx / total, sy / total

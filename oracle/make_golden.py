@@ -15,6 +15,9 @@ Fixtures written (all float64 unless noted):
                          executed (covers ARRIVED, the box-union reward and long RS hand-offs)
   scenes_<Level>.npz     reference-generated scenes (parking_map_normal.py:460-494)
   reeds_shepp.npz        calc_all_paths known answers (reeds_shepp.py:35-54)
+  images_<Level>.npz     CarParkingWrapper with use_img_observation=True: per step the uint8 image
+                         (obs['img'] * 255, exact), pose, trajectory length, substep counters; pygame is the
+                         software restatement oracle/softraster.py (unpinned), cv2 is the real one
   mask_table.npz         ActionMask constants: vehicle_lidar_base, sha256 + strided sample of
                          dist_star (action_mask.py:114-143), LidarSimlator.vehicle_boundary
 
@@ -184,6 +187,62 @@ def record_episodes(mods, level, n_episodes, seed, steps_per_episode=200, follow
     return out
 
 
+def record_images(mods, level, n_episodes, seed, steps_per_episode=40):
+    """Image observation of the unmodified reference (car_parking_base.py:301-350, observation_processor.py)."""
+    cpb, wrap, vehicle, rs, pmn, configs = mods
+    raw = cpb.CarParking(render_mode="rgb_array", fps=100, verbose=False,
+                         use_lidar_observation=True, use_img_observation=True, use_action_mask=True)
+    env = wrap.CarParkingWrapper(raw)
+    counters = {"substeps": 0, "retreats": 0}
+    veh = raw.vehicle
+    orig_step, orig_retreat = veh.step, veh.retreat
+
+    def step_spy(action, step_time=configs.NUM_STEP):
+        counters["substeps"] += 1
+        return orig_step(action, step_time)
+
+    def retreat_spy(prev):
+        counters["retreats"] += 1
+        return orig_retreat(prev)
+
+    veh.step, veh.retreat = step_spy, retreat_spy
+
+    def u8(img):
+        q = np.rint(img * 255.0)
+        assert np.array_equal(q / 255.0, img)
+        return q.astype(np.uint8)
+
+    rec = {k: [] for k in ("ep", "action", "pose", "img", "traj_len", "substeps", "retreated", "done")}
+    scn = {k: [] for k in ("start", "dest", "bounds", "obs", "nverts", "reset_img")}
+    for ep in range(n_episodes):
+        np.random.seed(seed + ep)
+        obs0 = env.reset(None, None, level)
+        s, d, b, o, nv = scene_arrays(raw.map)
+        scn["start"].append(s); scn["dest"].append(d); scn["bounds"].append(b)
+        scn["obs"].append(o); scn["nverts"].append(nv); scn["reset_img"].append(u8(obs0["img"]))
+        rng = np.random.default_rng(seed + 1000 * (ep + 1))
+        drift = rng.uniform(-1.0, 1.0, size=2)
+        for k in range(steps_per_episode):
+            a = rng.uniform(-1.0, 1.0, size=2)
+            if ep % 2 == 1:  # every other episode keeps a persistent bias so the vehicle travels and turns
+                a = np.clip(0.6 * drift + 0.4 * a, -1.0, 1.0)
+                if k % 15 == 14:
+                    drift = rng.uniform(-1.0, 1.0, size=2)
+            counters["substeps"] = 0; counters["retreats"] = 0
+            obs, reward, done, info = env.step(a)
+            st = raw.vehicle.state
+            rec["ep"].append(ep); rec["action"].append(a)
+            rec["pose"].append([st.loc.x, st.loc.y, st.heading])
+            rec["img"].append(u8(obs["img"])); rec["traj_len"].append(len(raw.vehicle.trajectory))
+            rec["substeps"].append(counters["substeps"]); rec["retreated"].append(counters["retreats"])
+            rec["done"].append(done)
+            if done:
+                break
+    out = {k: np.asarray(v) for k, v in rec.items()}
+    out.update({"scene_" + k: np.asarray(v) for k, v in scn.items()})
+    return out
+
+
 def record_scenes(mods, level, n, seed):
     cpb, wrap, vehicle, rs, pmn, configs = mods
     m = pmn.ParkingMapNormal(level)
@@ -262,7 +321,8 @@ def main():
     ap.add_argument("--episodes", type=int, default=3)
     ap.add_argument("--scenes", type=int, default=96)
     ap.add_argument("--follow-episodes", type=int, default=12)
-    ap.add_argument("--only", default=None, help="'rs' or 'tables': regenerate just that fixture")
+    ap.add_argument("--only", default=None, help="'rs', 'tables' or 'images': regenerate just that fixture")
+    ap.add_argument("--image-episodes", type=int, default=4)
     args = ap.parse_args()
     out = os.path.abspath(args.out)
     mods = _import_reference(args.ref)
@@ -271,6 +331,11 @@ def main():
         np.savez_compressed(os.path.join(out, "mask_table.npz"), **record_mask_table(mods))
     if args.only in (None, "rs"):
         np.savez_compressed(os.path.join(out, "reeds_shepp.npz"), **record_reeds_shepp(mods, 400, 7))
+    if args.only in (None, "images"):
+        for level in ("Normal", "Complex", "Extrem"):
+            im = record_images(mods, level, args.image_episodes, 777)
+            np.savez_compressed(os.path.join(out, f"images_{level}.npz"), **im)
+            print(level, "image steps", len(im["traj_len"]), "max traj", int(im["traj_len"].max()))
     if args.only is not None:
         return
     for level in ("Normal", "Complex", "Extrem"):

@@ -1,14 +1,16 @@
-"""pygame stand-in: drawing, display and clock are no-ops (image modality out of scope)."""
+"""pygame stand-in (TEST INFRASTRUCTURE ONLY): the software surface of oracle/softraster.py behind the
+module layout the reference touches (`car_parking_base.py:301-350, 383-411`), so the UNMODIFIED
+reference renders its image observation here.  Display and clock are no-ops."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import softraster as _sr  # oracle/softraster.py
+
 SHOWN = 0
 HIDDEN = 1
-
-
-class Surface(object):
-    def __init__(self, size=(0, 0)):
-        self.size = size
-
-    def fill(self, color):
-        pass
+Surface = _sr.Surface
+Rect = _sr.Rect
 
 
 class _Display(object):
@@ -27,7 +29,17 @@ class _Display(object):
 
 class _Draw(object):
     def polygon(self, surface, color, points, width=0):
-        pass
+        _sr.polygon(surface, color, points, width)
+
+
+class _Transform(object):
+    def rotate(self, surface, angle):
+        return _sr.rotate(surface, angle)
+
+
+class _Image(object):
+    def tostring(self, surface, fmt):
+        return _sr.tostring(surface, fmt)
 
 
 class _Clock(object):
@@ -41,6 +53,8 @@ class _Time(object):
 
 display = _Display()
 draw = _Draw()
+transform = _Transform()
+image = _Image()
 time = _Time()
 
 

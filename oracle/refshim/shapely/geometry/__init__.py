@@ -72,6 +72,10 @@ class LineString(BaseGeometry):
     def intersects(self, other):
         return _g.rings_intersect(self._coords, other._coords)
 
+    @property
+    def centroid(self):
+        return Point(_g.ring_centroid(self._coords))
+
     def distance(self, other):
         if isinstance(other, Point):
             return _g.point_ring_distance(other.x, other.y, self._coords)
