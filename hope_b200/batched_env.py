@@ -4,7 +4,9 @@ Batched counterpart of the reference's single-env surface
     CarParkingWrapper.reset / .step     src/env/env_wrapper.py:58-85
     CarParking.reset / .step            src/env/car_parking_base.py:127-138, 235-299
 Observation keys, dtypes (float64) and layouts are the reference's, with a leading env axis:
-    obs['lidar'] (N,120)  obs['target'] (N,5)  obs['action_mask'] (N,42)  obs['img'] None
+    obs['lidar'] (N,120)  obs['target'] (N,5)  obs['action_mask'] (N,42)
+    obs['img'] None, or with use_img_observation=True the (N,3,64,64) uint8 image whose /255.0 is the reference's
+    float64 image (car_parking_base.py:301-350, observation_processor.py:13-23; 12 KB instead of 96 KB per env)
 `action_mask[:, j]`: j<21 forward, j>=21 backward, steer 0.75-0.075*(j%21)  (configs.py:108-115).
 
 PyTorch is used for device memory and streams only; all compute is in libhope_b200.so.  There
@@ -42,7 +44,7 @@ def generate_scenes(n, level="Normal", seed=42, nthreads=0, max_obs=16):
 
 class BatchedParkingEnv(object):
     def __init__(self, n_envs, scenes=None, pool_size=None, level="Normal", seed=42, device=0, auto_reset=True,
-                 params=None, device_scenes=False, max_obs=None):
+                 params=None, device_scenes=False, max_obs=None, use_img_observation=False):
         """scenes: dict of host arrays (start/dest/bounds/obs/nverts) to upload as the pool; None -> generate
         `pool_size` (default 2 n) scenes of `level` on the host, or with device_scenes=True on the GPU
         (then finished envs also get a fresh device-generated scene instead of cycling the pool)."""
@@ -82,7 +84,11 @@ class BatchedParkingEnv(object):
         # device outputs (torch owns the memory; the library only sees raw pointers)
         self.out = {}
         self._out_struct = capi.Out()
+        self.use_img = bool(use_img_observation)
+        self.default_stages = capi.STAGE_ALL | (capi.STAGE_IMAGE if self.use_img else 0)
         for name, ct, shape in capi.OUT_FIELDS:
+            if name == "img" and not self.use_img:
+                continue  # NULL pointer: the library skips the image stage
             tdt = {C.c_double: torch.float64, C.c_uint8: torch.uint8, C.c_int32: torch.int32}[ct]
             t = torch.zeros((self.n,) + shape, dtype=tdt, device=self.device)
             self.out[name] = t
@@ -117,7 +123,7 @@ class BatchedParkingEnv(object):
         return self.torch.cuda.current_stream(self.device).cuda_stream
 
     def _obs(self):
-        return {"img": None, "lidar": self.out["lidar"], "target": self.out["target"], "action_mask": self.out["mask"]}
+        return {"img": self.out.get("img"), "lidar": self.out["lidar"], "target": self.out["target"], "action_mask": self.out["mask"]}
 
     def _info(self):
         o = self.out
@@ -134,9 +140,10 @@ class BatchedParkingEnv(object):
                                        self._stream()), self.ctx)
         return self._obs()
 
-    def step(self, actions, stages=capi.STAGE_ALL):
+    def step(self, actions, stages=None):
         """actions: (N,2) float64 CUDA tensor in [-1,1] (steer, speed), as the policy emits them."""
         t = self.torch
+        stages = self.default_stages if stages is None else stages
         if not (isinstance(actions, t.Tensor) and actions.is_cuda and actions.dtype == t.float64 and actions.is_contiguous()
                 and tuple(actions.shape) == (self.n, 2)):
             raise capi.HopeError("step() expects a contiguous float64 CUDA tensor of shape (n_envs, 2)")
@@ -168,10 +175,11 @@ class BatchedParkingEnv(object):
             setattr(st, name, self._host[name].data_ptr())
         return st
 
-    def step_host(self, actions, stages=capi.STAGE_ALL, outputs=HOST_DEFAULT):
+    def step_host(self, actions, stages=None, outputs=HOST_DEFAULT):
         """actions: (N,2) float64 numpy array on the host.  Copies it in, steps, copies `outputs`
         back into pinned host buffers, synchronises.  Returns dict of numpy views."""
         st = self._host_buffers(outputs)
+        stages = (capi.STAGE_ALL | (capi.STAGE_IMAGE if "img" in outputs else 0)) if stages is None else stages
         self._host["action"].numpy()[...] = actions
         capi.check(self.lib.hope_step_host(self.ctx, self._host["action"].data_ptr(), C.byref(st), stages), self.ctx)
         return {k: self._host[k].numpy() for k in outputs}
@@ -227,7 +235,14 @@ class BatchedParkingEnv(object):
     def planner_reset(self):
         capi.check(self.lib.hope_planner_reset(self.ctx, self._stream()), self.ctx)
 
-    KERNELS = ("k_advance", "k_observe", "k_rs_enumerate", "k_rs_walk", "k_rs_check", "k_rs_select")
+    KERNELS = ("k_advance", "k_observe", "k_rs_enumerate", "k_rs_walk", "k_rs_check", "k_rs_select", "k_render")
+
+    def set_palette(self, rgb):
+        """hope_set_palette: (25,3) uint8 colours in painter's order (configs.py:26-30, 80-88)."""
+        a = np.ascontiguousarray(rgb, dtype=np.uint8)
+        if a.shape != (capi.N_COLOR, 3):
+            raise capi.HopeError("palette must be (25, 3) uint8")
+        capi.check(self.lib.hope_set_palette(self.ctx, a.ctypes.data), self.ctx)
 
     def profile(self, on=True):
         capi.check(self.lib.hope_profile_enable(self.ctx, 1 if on else 0), self.ctx)

@@ -5,7 +5,8 @@ import os
 from . import build as _build
 
 MAX_OBS, MAX_VERTS, N_LIDAR, N_ACTION, N_MASK_ITER, N_UPSAMPLE, RS_MAX_SEG = 16, 4, 120, 42, 10, 1200, 5
-STAGE_ADVANCE, STAGE_OBSERVE, STAGE_RS, STAGE_ALL = 1, 2, 4, 7
+STAGE_ADVANCE, STAGE_OBSERVE, STAGE_RS, STAGE_ALL, STAGE_IMAGE = 1, 2, 4, 7, 8
+IMG_C, IMG_HW, N_COLOR = 3, 64, 25
 CONTINUE, ARRIVED, COLLIDED, OUTBOUND, OUTTIME = 1, 2, 3, 4, 5
 RS_S, RS_L, RS_R, RS_NONE = 0, 1, 2, 255
 
@@ -32,7 +33,7 @@ OUT_FIELDS = [
     ("substeps", C.c_uint8, ()), ("retreated", C.c_uint8, ()), ("was_reset", C.c_uint8, ()),
     ("rs_found", C.c_uint8, ()), ("rs_nseg", C.c_uint8, ()), ("rs_types", C.c_uint8, (RS_MAX_SEG,)),
     ("rs_lengths", C.c_double, (RS_MAX_SEG,)), ("rs_L", C.c_double, ()), ("rs_ncand", C.c_uint8, ()),
-    ("rs_ntried", C.c_uint8, ())]
+    ("rs_ntried", C.c_uint8, ()), ("img", C.c_uint8, (IMG_C, IMG_HW, IMG_HW))]
 
 
 class Out(C.Structure):
@@ -64,6 +65,7 @@ def load_library(max_obs=16):
         "hope_strerror": (C.c_char_p, [i32]),
         "hope_last_cuda_error": (C.c_char_p, [vp]),
         "hope_upload_tables": (C.c_int, [vp] + [dp] * 7),
+        "hope_set_palette": (C.c_int, [vp, vp]),
         "hope_set_scene_pool": (C.c_int, [vp, i32, i32, dp, dp, dp, dp, ip]),
         "hope_generate_scenes": (C.c_int, [i32, i32, u64, i32, dp, dp, dp, dp, ip, ip]),
         "hope_generate_scene_pool_device": (C.c_int, [vp, i32, i32, i32, u64, vp]),

@@ -67,6 +67,8 @@ struct EnvState {
     uint8_t *pending; // [N] finished last step, takes its next scene on this one
     uint8_t *gate;    // [N] RS gate of this step
     unsigned long long *counters;  // [8]
+    double *traj;     // [N][20][3] ring buffer: tail of Vehicle.trajectory (vehicle.py:121-157), read by k_render
+    int *traj_n;      // [N] len(Vehicle.trajectory); entry j of the list lives in slot j % 20
 };
 struct RsWord {  // one admitted word, lengths in curvature-normalised units
     double len[HOPE_RS_MAX_SEG];
@@ -297,6 +299,18 @@ __global__ void __launch_bounds__(128) k_advance(int n, Pool pool, EnvState st, 
         st.accum[i] = accum; st.t[i] = t;
         st.pending[i] = (done && par.auto_reset) ? 1 : 0;
         st.gate[i] = (t > 1 && status == HOPE_CONTINUE && dist_now < par.rs_max_dist) ? 1 : 0;  // :293-294
+        // Vehicle.trajectory: reset -> [start]; a step keeps exactly one new state (car_parking_base.py:273-275
+        // prunes the substeps) unless the very first substep collided and was popped again (vehicle.py:157)
+        if (reset_all || pending) {
+            double *tj = st.traj + (size_t)i * 60;
+            tj[0] = x; tj[1] = y; tj[2] = h;
+            st.traj_n[i] = 1;
+        } else if (nsub - nret >= 1) {
+            const int tn = st.traj_n[i];
+            double *tj = st.traj + ((size_t)i * 20 + tn % 20) * 3;
+            tj[0] = x; tj[1] = y; tj[2] = h;
+            st.traj_n[i] = tn + 1;
+        }
         if (out.pose) { out.pose[3 * i] = x; out.pose[3 * i + 1] = y; out.pose[3 * i + 2] = h; }
         if (out.status) out.status[i] = status;
         if (out.done) out.done[i] = done;
@@ -536,6 +550,8 @@ __global__ void __launch_bounds__(64) k_observe(int n, Pool pool, EnvState st, T
 // =============================================================================================
 // k_rs_enumerate: one thread per env.  46 candidate words -> admitted list -> heap pop order.
 // =============================================================================================
+#include "render.cuh"
+
 struct Tuv { double t, u, v; };
 
 __device__ bool w_SLS(double x, double y, double phi, Tuv &o) {  // reeds_shepp.py:133-149
@@ -1324,6 +1340,10 @@ struct hope_ctx {
     WordSlot *d_slots = nullptr;
     int *d_regen_slots = nullptr, *d_regen_count = nullptr, *d_gen_status = nullptr;
     unsigned *d_episode = nullptr;
+    double *d_traj = nullptr;
+    int *d_traj_n = nullptr;
+    render::Palette palette;
+    int render_blocks = 148;
     double *d_plan_rem = nullptr;
     uint8_t *d_plan_u8 = nullptr;  // types[N][5] | big[N] | n[N] | seg[N] | active[N]
     int sm_count = 148, walk_blocks = 148 * 4, check_blocks = 148 * 4;
@@ -1405,7 +1425,7 @@ const OutField kOutFields[] = {
     OF(target, double, 5), OF(reward, double, 1), OF(reward_info, double, 5), OF(status, int32_t, 1),
     OF(done, uint8_t, 1), OF(substeps, uint8_t, 1), OF(retreated, uint8_t, 1), OF(was_reset, uint8_t, 1),
     OF(rs_found, uint8_t, 1), OF(rs_nseg, uint8_t, 1), OF(rs_types, uint8_t, 5), OF(rs_lengths, double, 5),
-    OF(rs_L, double, 1), OF(rs_ncand, uint8_t, 1), OF(rs_ntried, uint8_t, 1)};
+    OF(rs_L, double, 1), OF(rs_ncand, uint8_t, 1), OF(rs_ntried, uint8_t, 1), OFO(img, uint8_t, HOPE_IMG_C * HOPE_IMG_HW * HOPE_IMG_HW)};
 constexpr int kNumOutFields = sizeof(kOutFields) / sizeof(kOutFields[0]);
 
 void *&field_ptr(hope_out &o, const OutField &f) { return *reinterpret_cast<void **>(reinterpret_cast<char *>(&o) + f.offset); }
@@ -1444,7 +1464,7 @@ int launch_range(hope_ctx *ctx, const double *d_action, const hope_out &out_all,
     Pool pool = make_pool(ctx);
     Tables tb = make_tables(ctx);
     EnvState st{ctx->d_pose + 3 * (size_t)lo, ctx->d_cs + 2 * (size_t)lo, ctx->d_t + lo, ctx->d_accum + lo, ctx->d_scene + lo,
-                ctx->d_pending + lo, ctx->d_gate + lo, ctx->d_counters};
+                ctx->d_pending + lo, ctx->d_gate + lo, ctx->d_counters, ctx->d_traj + 60 * (size_t)lo, ctx->d_traj_n + lo};
     const hope_out out = offset_out(out_all, lo);
     const double *act = d_action ? d_action + 2 * (size_t)lo : nullptr;
     const bool regen = ctx->par.regen_on_reset && ctx->par.auto_reset && !reset_all;
@@ -1461,18 +1481,29 @@ int launch_range(hope_ctx *ctx, const double *d_action, const hope_out &out_all,
     k_advance<<<(n + ADV_THREADS - 1) / ADV_THREADS, ADV_THREADS, 0, s>>>(n, pool, st, act, ctx->par, out, reset_all, regen ? 0 : ctx->n);
     prof_mark(ctx, 0, s);
     ctx->launches++;
-    const bool fork = (stages & HOPE_STAGE_OBSERVE) && (stages & HOPE_STAGE_RS);
+    const bool image = (stages & HOPE_STAGE_IMAGE) && out.img;
+    const bool side = (stages & HOPE_STAGE_OBSERVE) || image;  // work that only depends on k_advance, besides RS
+    const bool fork = side && (stages & HOPE_STAGE_RS);
     cudaStream_t so = fork ? lane.aux : s;
-    if (stages & HOPE_STAGE_OBSERVE) {
+    if (side) {
         if (fork) {
             CK(cudaEventRecord(lane.ev_advanced, s));
             CK(cudaStreamWaitEvent(so, lane.ev_advanced, 0));
         }
-        const int wpb = OBS_THREADS / 32;
-        prof_mark(ctx, 1, so);
-        k_observe<<<(n + wpb - 1) / wpb, OBS_THREADS, wpb * sizeof(ObserveSmem), so>>>(n, pool, st, tb, ctx->par, out);
-        prof_mark(ctx, 1, so);
-        ctx->launches++;
+        if (stages & HOPE_STAGE_OBSERVE) {
+            const int wpb = OBS_THREADS / 32;
+            prof_mark(ctx, 1, so);
+            k_observe<<<(n + wpb - 1) / wpb, OBS_THREADS, wpb * sizeof(ObserveSmem), so>>>(n, pool, st, tb, ctx->par, out);
+            prof_mark(ctx, 1, so);
+            ctx->launches++;
+        }
+        if (image) {
+            prof_mark(ctx, 6, so);
+            k_render<<<n < ctx->render_blocks ? n : ctx->render_blocks, render::THREADS, sizeof(render::Smem), so>>>(
+                n, pool, st, st.traj, st.traj_n, ctx->par, ctx->palette, out.img);
+            prof_mark(ctx, 6, so);
+            ctx->launches++;
+        }
         if (early_out) { int rc = copy_fields(ctx, early_out, 1, so, lo, cnt); if (rc) return rc; }
         if (fork) CK(cudaEventRecord(lane.ev_observed, so));
     }
@@ -1608,6 +1639,10 @@ int hope_create(hope_ctx **out, int device, int n_envs, int pool_size, const hop
     CK(cudaMemset(ctx->d_gen_status, 0, sizeof(int)));
     CK(cudaMalloc(&ctx->d_episode, sizeof(unsigned) * P));
     CK(cudaMemset(ctx->d_episode, 0, sizeof(unsigned) * P));
+    CK(cudaMalloc(&ctx->d_traj, sizeof(double) * 60 * N));
+    CK(cudaMalloc(&ctx->d_traj_n, sizeof(int) * N));
+    CK(cudaMemset(ctx->d_traj, 0, sizeof(double) * 60 * N));
+    CK(cudaMemset(ctx->d_traj_n, 0, sizeof(int) * N));
     CK(cudaMalloc(&ctx->d_plan_rem, sizeof(double) * 5 * N));
     CK(cudaMalloc(&ctx->d_plan_u8, 9 * N));
     CK(cudaMemset(ctx->d_plan_u8, 0, 9 * N));
@@ -1635,6 +1670,18 @@ int hope_create(hope_ctx **out, int device, int n_envs, int pool_size, const hop
     if (const char *e = getenv("HOPE_B200_DEVICE_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= 16) ctx->device_chunks = v; }
     if (const char *e = getenv("HOPE_B200_HOST_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->host_chunks = v; }
     CK(cudaFuncSetAttribute(k_observe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((OBS_THREADS / 32) * sizeof(ObserveSmem))));
+    CK(cudaFuncSetAttribute(k_render, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(render::Smem)));
+    ctx->render_blocks = ctx->sm_count;  // persistent: one 1024-thread CTA (150 KB of shared memory) per SM
+    {   // configs.py:26-30, 80-88; TRAJ_COLORS = np.linspace(LOW, HIGH, 20, endpoint=True, dtype=np.uint8)
+        uint8_t rgb[HOPE_N_COLOR][3] = {{255, 255, 255}, {150, 150, 150}, {100, 149, 237}, {69, 139, 0}, {30, 144, 255}};
+        const double low[3] = {10, 10, 10}, high[3] = {10, 10, 200};
+        for (int k = 0; k < 20; ++k)
+            for (int c = 0; c < 3; ++c) {
+                const double step = (high[c] - low[c]) / 19;
+                rgb[5 + k][c] = (uint8_t)(k == 19 ? high[c] : low[c] + k * step);
+            }
+        hope_set_palette(ctx, &rgb[0][0]);
+    }
     return HOPE_OK;
 }
 
@@ -1643,7 +1690,7 @@ int hope_destroy(hope_ctx *ctx) {
     cudaSetDevice(ctx->device);
     void *ptrs[] = {ctx->d_obs, ctx->d_aabb, ctx->d_meta, ctx->d_nv, ctx->d_nobs, ctx->d_tab, ctx->d_pose, ctx->d_accum, ctx->d_t,
                     ctx->d_scene, ctx->d_pending, ctx->d_gate, ctx->d_counters, ctx->d_words, ctx->d_ntry, ctx->d_ncand, ctx->d_cs, ctx->d_item_base, ctx->d_items, ctx->d_item_bad, ctx->d_slots, ctx->d_n_items, ctx->d_plan_rem, ctx->d_plan_u8, ctx->d_regen_slots, ctx->d_regen_count, ctx->d_gen_status, ctx->d_episode,
-                    ctx->d_action, ctx->d_stage};
+                    ctx->d_action, ctx->d_stage, ctx->d_traj, ctx->d_traj_n};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->host_graph) cudaGraphExecDestroy(ctx->host_graph);
@@ -1656,6 +1703,18 @@ int hope_destroy(hope_ctx *ctx) {
         if (ln.ev_observed) cudaEventDestroy(ln.ev_observed);
     }
     delete ctx;
+    return HOPE_OK;
+}
+
+int hope_set_palette(hope_ctx *ctx, const uint8_t *h_rgb) {
+    if (!ctx || !h_rgb) return HOPE_ERR_INVALID;
+    const uint8_t *bg = h_rgb;
+    for (int k = 0; k < HOPE_N_COLOR; ++k) {
+        const uint8_t *c = h_rgb + 3 * k;
+        const bool white = c[0] == bg[0] && c[1] == bg[1] && c[2] == bg[2];  // change_bg_color: BG_COLOR pixels become black
+        ctx->palette.rg[k] = white ? 0u : ((uint32_t)c[0] | ((uint32_t)c[1] << 16));
+        ctx->palette.b[k] = white ? 0u : (uint32_t)c[2];
+    }
     return HOPE_OK;
 }
 
@@ -1780,7 +1839,7 @@ int hope_reset(hope_ctx *ctx, const int32_t *h_scene_ids, const hope_out *d_out,
     CK(cudaStreamSynchronize(s));  // ids is a local buffer
     ctx->have_reset = true;
     // the reset step computes the observation; RS is gated off by t > 1 (car_parking_base.py:293)
-    return launch_step(ctx, nullptr, *d_out, HOPE_STAGE_ADVANCE | HOPE_STAGE_OBSERVE | HOPE_STAGE_RS, 1, s);
+    return launch_step(ctx, nullptr, *d_out, HOPE_STAGE_ADVANCE | HOPE_STAGE_OBSERVE | HOPE_STAGE_RS | HOPE_STAGE_IMAGE, 1, s);
 }
 
 int hope_step(hope_ctx *ctx, const double *d_action, const hope_out *d_out, unsigned stages, void *stream) {
@@ -1841,7 +1900,8 @@ static void plan_zero_copy(hope_ctx *ctx, const hope_host_out *h_out) {
 }
 
 static int enqueue_host_step(hope_ctx *ctx, const double *h_action, const hope_host_out *h_out, unsigned stages) {
-    const bool fork = (stages & HOPE_STAGE_OBSERVE) && (stages & HOPE_STAGE_RS);
+    if (!h_out->img) stages &= ~(unsigned)HOPE_STAGE_IMAGE;  // nobody reads the staged image
+    const bool fork = (stages & (HOPE_STAGE_OBSERVE | HOPE_STAGE_IMAGE)) && (stages & HOPE_STAGE_RS);
     const int n = ctx->n;
     int chunks = ctx->host_chunks;
     if (n < 4096 * chunks) chunks = n / 4096 > 0 ? n / 4096 : 1;

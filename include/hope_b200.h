@@ -55,8 +55,13 @@ enum {
     HOPE_STAGE_ADVANCE = 1,  /* kinematics + collision + arrival + status + reward (always runs) */
     HOPE_STAGE_OBSERVE = 2,  /* LiDAR raycast + action-mask sweep + target representation */
     HOPE_STAGE_RS = 4,       /* Reeds-Shepp search (car_parking_base.py:293-297 gate) */
-    HOPE_STAGE_ALL = 7
+    HOPE_STAGE_ALL = 7,      /* the lidar + action-mask + Reeds-Shepp step (use_img_observation=False) */
+    HOPE_STAGE_IMAGE = 8     /* ego-centric image observation into hope_out.img (car_parking_base.py:301-350,
+                                observation_processor.py:6-23); needs a non-NULL img pointer */
 };
+#define HOPE_IMG_C 3         /* observation_processor.py:9  n_channels */
+#define HOPE_IMG_HW 64       /* configs.py:89-90 OBS_W, OBS_H = 256, observation_processor.py:8 downsample_rate 4 */
+#define HOPE_N_COLOR 25      /* palette entries: background, obstacle, start, dest, vehicle, 20 trajectory colours */
 
 /* Mirrors the constants of src/configs.py the path reads. */
 typedef struct hope_params {
@@ -103,6 +108,9 @@ typedef struct hope_out {
     double *rs_L;         /* [n]       PATH.L */
     uint8_t *rs_ncand;    /* [n]       admissible words (diagnostic) */
     uint8_t *rs_ntried;   /* [n]       words sampled and checked (diagnostic) */
+    uint8_t *img;         /* [n][3][64][64]  image observation after Obs_Processor.process_img and the wrapper's
+                                       HWC -> CHW transpose, as the uint8 value cv2.resize produced: the reference's
+                                       float64 obs['img'] is exactly img / 255.0 (env_wrapper.py:52-55) */
 } hope_out;
 
 /* Host mirror of hope_out for hope_step_host (same shapes, HOST pointers, NULL = skip). */
@@ -123,6 +131,12 @@ const char *hope_last_cuda_error(const hope_ctx *ctx);
 int hope_upload_tables(hope_ctx *ctx, const double *h_ray_a, const double *h_ray_b, const double *h_lidar_base,
                        const double *h_mask_base, const double *h_dist_star, const double *h_w_lo,
                        const double *h_w_hi);
+
+/* Colours of the image observation (configs.py:26-30, 80-88), HOST pointer rgb[25][3] in painter's order:
+ * [0] BG_COLOR [1] OBSTACLE_COLOR [2] START_COLOR [3] DEST_COLOR [4] vehicle colour COLOR_POOL[0]
+ * [5..24] TRAJ_COLORS[0..19].  A palette entry equal to BG_COLOR reads as black in the observation
+ * (Obs_Processor.change_bg_color).  hope_create installs the reference's defaults. */
+int hope_set_palette(hope_ctx *ctx, const uint8_t *h_rgb);
 
 /* Scene pool, HOST pointers: scenes [first, first+n) of the pool.
  *   start[n][3] dest[n][3] bounds[n][4]=(xmin,xmax,ymin,ymax) obs_xy[n][16][4][2] nverts[n][16]
@@ -181,7 +195,7 @@ int hope_get_counters(hope_ctx *ctx, uint64_t h_counters[8]);
 /* Per-kernel device timing: when enabled every kernel launch of a step is bracketed by CUDA
  * events on the launch stream.  hope_profile_read synchronises, returns the accumulated
  * milliseconds and launch counts per kernel [0] advance [1] observe [2] rs_enumerate [3] rs_walk
- * [4] rs_check [5] rs_select ([6],[7] reserved) since the last read, and clears them. */
+ * [4] rs_check [5] rs_select [6] render ([7] reserved) since the last read, and clears them. */
 int hope_profile_enable(hope_ctx *ctx, int on);
 int hope_profile_read(hope_ctx *ctx, double h_ms[8], uint64_t h_launches[8]);
 /* Micro-benchmark for the roofline's compute axis: sustained float64 FMA rate of the device (8 independent DFMA

@@ -99,7 +99,7 @@ def crop_observation(surf, mat, pose):
     capture = sr.rotate(surf, np.rad2deg(angle))
     rot = sr.Surface((WIN_W, WIN_H))
     rot.blit(capture, capture.get_rect(center=old_center))
-    cx, cy = _g.ring_centroid(to_screen(create_box(x, y, heading), mat))
+    (cx, cy), = to_screen([_g.ring_centroid(create_box(x, y, heading))], mat)
     dx = (cx - old_center[0]) * np.cos(angle) + (cy - old_center[1]) * np.sin(angle)
     dy = -(cx - old_center[0]) * np.sin(angle) + (cy - old_center[1]) * np.cos(angle)
     obs = sr.Surface((WIN_W, WIN_H))

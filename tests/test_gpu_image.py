@@ -1,0 +1,155 @@
+"""GPU parity of the image observation: k_render through the C ABI against
+(1) the uint8 images recorded from the unmodified reference (tests/golden/images_*.npz) and
+(2) oracle/image_oracle.py on generated and Dragon-Lake scenes.  Bar: bit-exact bytes (integer work).
+
+What is pinned: the reference's own rendering glue and the real cv2.resize; the pygame raster rules are a
+restatement (oracle/softraster.py), so parity with a real pygame build is unpinned."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+from hope_b200 import capi  # noqa: E402
+from hope_b200.batched_env import BatchedParkingEnv, generate_scenes  # noqa: E402
+from oracle import image_oracle as io  # noqa: E402
+
+LEVELS = ("Normal", "Complex", "Extrem")
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _mismatch(a, b):
+    return int((a != b).any(axis=(1, 2, 3)).sum()), int((a != b).sum())
+
+
+@pytest.mark.parametrize("level", LEVELS)
+def test_golden_images_through_cuda(golden_dir, level):
+    g = np.load(os.path.join(golden_dir, f"images_{level}.npz"))
+    n_ep = len(g["scene_start"])
+    scenes = dict(start=g["scene_start"], dest=g["scene_dest"], bounds=g["scene_bounds"], obs=g["scene_obs"], nverts=g["scene_nverts"])
+    env = BatchedParkingEnv(n_ep, scenes=scenes, auto_reset=False, use_img_observation=True)
+    obs = env.reset()
+    assert obs["img"].shape == (n_ep, 3, 64, 64) and obs["img"].dtype == torch.uint8
+    assert np.array_equal(_np(obs["img"]), g["scene_reset_img"]), "reset images"
+    idx = [np.where(g["ep"] == e)[0] for e in range(n_ep)]
+    checked = 0
+    for k in range(max(len(i) for i in idx)):
+        live = np.array([k < len(i) for i in idx])
+        rows = np.array([i[k] if k < len(i) else i[-1] for i in idx])
+        act = np.where(live[:, None], g["action"][rows], 0.0)
+        obs, _, _, _ = env.step(torch.as_tensor(act, device=env.device).contiguous())
+        img = _np(obs["img"])
+        assert np.array_equal(_np(env.out["substeps"])[live], g["substeps"][rows][live])
+        assert np.array_equal(img[live], g["img"][rows][live]), f"step {k}: {_mismatch(img[live], g['img'][rows][live])}"
+        checked += int(live.sum())
+    assert checked == len(g["ep"])
+    env.close()
+
+
+def _oracle_images(sc, book, ids):
+    out = []
+    for i in ids:
+        rings = io.scene_rings(sc["obs"][i], sc["nverts"][i])
+        out.append(io.render_observation(sc["start"][i], sc["dest"][i], sc["bounds"][i], rings, book.traj[i]))
+    return np.stack(out)
+
+
+def _lockstep_images(env, sc, n, steps, seed, check_every=3):
+    """Steps the CUDA env with persistent, drifting actions; the oracle renders from the CUDA env's own pose and
+    substep counters (so this isolates the rasteriser), a rotating subset of envs each step."""
+    book = io.TrajectoryBook(n)
+    obs = env.reset()
+    for i in range(n):
+        book.reset(i, sc["start"][i])
+    ids = list(range(0, n, 4))
+    assert np.array_equal(_np(obs["img"])[ids], _oracle_images(sc, book, ids)), "reset images"
+    rng = np.random.default_rng(seed)
+    drift = rng.uniform(-1, 1, size=(n, 2))
+    live = np.ones(n, dtype=bool)
+    compared = 0
+    for k in range(steps):
+        if k % 12 == 11:
+            drift = rng.uniform(-1, 1, size=(n, 2))
+        act = np.clip(0.7 * drift + 0.3 * rng.uniform(-1, 1, size=(n, 2)), -1, 1)
+        obs, _, done, _ = env.step(torch.as_tensor(act, device=env.device).contiguous())
+        pose, sub, ret = _np(env.out["pose"]), _np(env.out["substeps"]), _np(env.out["retreated"])
+        for i in range(n):
+            if live[i]:
+                book.step(i, pose[i], sub[i], ret[i])
+        ids = [i for i in range(k % check_every, n, check_every) if live[i]]
+        if ids:
+            got, want = _np(obs["img"])[ids], _oracle_images(sc, book, ids)
+            assert np.array_equal(got, want), f"step {k}: (images, bytes) differing = {_mismatch(got, want)}"
+            compared += len(ids)
+        live &= _np(done) == 0
+    return compared, book
+
+
+def test_render_matches_the_oracle_on_generated_scenes():
+    n = 48
+    sc = generate_scenes(n, "mix", 31)
+    env = BatchedParkingEnv(n, scenes=sc, auto_reset=False, use_img_observation=True)
+    compared, book = _lockstep_images(env, sc, n, 45, 5)
+    assert compared >= 300
+    assert max(len(t) for t in book.traj) > io.TRAJ_RENDER_LEN
+    env.close()
+
+
+def test_quarter_turn_headings_take_the_rotate90_path():
+    n = 8
+    sc = generate_scenes(n, "Normal", 77)
+    env = BatchedParkingEnv(n, scenes=sc, auto_reset=False, use_img_observation=True)
+    env.reset()
+    book = io.TrajectoryBook(n)
+    pose = sc["start"].copy()
+    heads = [0.0, np.pi / 2, np.pi, -np.pi / 2, 3 * np.pi / 2, 2 * np.pi, 1e-9, -np.pi]
+    for i in range(n):
+        book.reset(i, sc["start"][i])
+        pose[i, 2] = heads[i]
+    env.set_state(pose=pose)
+    zero = torch.zeros((n, 2), dtype=torch.float64, device=env.device)  # speed 0: the pose stays where it was put
+    obs, _, _, _ = env.step(zero)
+    got_pose = _np(env.out["pose"])
+    assert np.array_equal(got_pose[:, 2], pose[:, 2])
+    for i in range(n):
+        book.step(i, got_pose[i], _np(env.out["substeps"])[i], _np(env.out["retreated"])[i])
+    assert np.array_equal(_np(obs["img"]), _oracle_images(sc, book, range(n)))
+    env.close()
+
+
+def test_image_stage_is_optional_and_does_not_disturb_the_other_outputs():
+    n = 64
+    sc = generate_scenes(n, "mix", 9)
+    a = BatchedParkingEnv(n, scenes=sc, auto_reset=False, use_img_observation=True)
+    b = BatchedParkingEnv(n, scenes=sc, auto_reset=False)
+    assert b.reset()["img"] is None
+    a.reset()
+    rng = np.random.default_rng(3)
+    for _ in range(6):
+        act = torch.as_tensor(rng.uniform(-1, 1, size=(n, 2)), device=a.device).contiguous()
+        a.step(act); b.step(act)
+    for key in ("pose", "lidar", "mask_steps", "status", "rs_found", "reward"):
+        assert torch.equal(a.out[key], b.out[key]), key
+    host = a.step_host(rng.uniform(-1, 1, size=(n, 2)), outputs=("img", "status"))
+    assert host["img"].shape == (n, 3, 64, 64) and host["img"].any()
+    a.close(); b.close()
+
+
+def test_render_on_dragon_lake_scenes_128_ring_build(golden_dir):
+    from hope_b200 import dlp
+    cases = dlp.cases_from_fixture(np.load(os.path.join(golden_dir, "dlp_cases.npz")))
+    n = 12
+    sc = dlp.prepare_scenes(cases, np.arange(n) % 16, seed=5)
+    env = BatchedParkingEnv(n, scenes=sc, auto_reset=False, use_img_observation=True)
+    assert env.max_obs == 128
+    compared, _ = _lockstep_images(env, sc, n, 8, 2, check_every=2)
+    assert compared >= 30
+    env.close()
