@@ -67,7 +67,7 @@ struct EnvState {
     uint8_t *pending; // [N] finished last step, takes its next scene on this one
     uint8_t *gate;    // [N] RS gate of this step
     unsigned long long *counters;  // [8]
-    double *traj;     // [N][20][3] ring buffer: tail of Vehicle.trajectory (vehicle.py:121-157), read by k_render
+    double *traj;     // [N][20][4] ring buffer (x, y, cos h, sin h): tail of Vehicle.trajectory (vehicle.py:121-157), read by k_render
     int *traj_n;      // [N] len(Vehicle.trajectory); entry j of the list lives in slot j % 20
 };
 struct RsWord {  // one admitted word, lengths in curvature-normalised units
@@ -302,13 +302,13 @@ __global__ void __launch_bounds__(128) k_advance(int n, Pool pool, EnvState st, 
         // Vehicle.trajectory: reset -> [start]; a step keeps exactly one new state (car_parking_base.py:273-275
         // prunes the substeps) unless the very first substep collided and was popped again (vehicle.py:157)
         if (reset_all || pending) {
-            double *tj = st.traj + (size_t)i * 60;
-            tj[0] = x; tj[1] = y; tj[2] = h;
+            double2 *tj = reinterpret_cast<double2 *>(st.traj) + (size_t)i * 40;
+            tj[0] = make_double2(x, y); tj[1] = make_double2(c, s);
             st.traj_n[i] = 1;
         } else if (nsub - nret >= 1) {
             const int tn = st.traj_n[i];
-            double *tj = st.traj + ((size_t)i * 20 + tn % 20) * 3;
-            tj[0] = x; tj[1] = y; tj[2] = h;
+            double2 *tj = reinterpret_cast<double2 *>(st.traj) + ((size_t)i * 20 + tn % 20) * 2;
+            tj[0] = make_double2(x, y); tj[1] = make_double2(c, s);
             st.traj_n[i] = tn + 1;
         }
         if (out.pose) { out.pose[3 * i] = x; out.pose[3 * i + 1] = y; out.pose[3 * i + 2] = h; }
@@ -1343,7 +1343,7 @@ struct hope_ctx {
     double *d_traj = nullptr;
     int *d_traj_n = nullptr;
     render::Palette palette;
-    int render_blocks = 148;
+    render::Camera *d_cams = nullptr;
     double *d_plan_rem = nullptr;
     uint8_t *d_plan_u8 = nullptr;  // types[N][5] | big[N] | n[N] | seg[N] | active[N]
     int sm_count = 148, walk_blocks = 148 * 4, check_blocks = 148 * 4;
@@ -1464,7 +1464,7 @@ int launch_range(hope_ctx *ctx, const double *d_action, const hope_out &out_all,
     Pool pool = make_pool(ctx);
     Tables tb = make_tables(ctx);
     EnvState st{ctx->d_pose + 3 * (size_t)lo, ctx->d_cs + 2 * (size_t)lo, ctx->d_t + lo, ctx->d_accum + lo, ctx->d_scene + lo,
-                ctx->d_pending + lo, ctx->d_gate + lo, ctx->d_counters, ctx->d_traj + 60 * (size_t)lo, ctx->d_traj_n + lo};
+                ctx->d_pending + lo, ctx->d_gate + lo, ctx->d_counters, ctx->d_traj + 80 * (size_t)lo, ctx->d_traj_n + lo};
     const hope_out out = offset_out(out_all, lo);
     const double *act = d_action ? d_action + 2 * (size_t)lo : nullptr;
     const bool regen = ctx->par.regen_on_reset && ctx->par.auto_reset && !reset_all;
@@ -1499,8 +1499,10 @@ int launch_range(hope_ctx *ctx, const double *d_action, const hope_out &out_all,
         }
         if (image) {
             prof_mark(ctx, 6, so);
-            k_render<<<n < ctx->render_blocks ? n : ctx->render_blocks, render::THREADS, sizeof(render::Smem), so>>>(
-                n, pool, st, st.traj, st.traj_n, ctx->par, ctx->palette, out.img);
+            render::Camera *cams = ctx->d_cams + lo;
+            k_render_camera<<<(n + 127) / 128, 128, 0, so>>>(n, pool, st, ctx->par, cams);
+            k_render<<<4 * n, render::THREADS, sizeof(render::Smem), so>>>(n, pool, st, cams, ctx->par, ctx->palette, out.img);
+            ctx->launches++;
             prof_mark(ctx, 6, so);
             ctx->launches++;
         }
@@ -1639,9 +1641,10 @@ int hope_create(hope_ctx **out, int device, int n_envs, int pool_size, const hop
     CK(cudaMemset(ctx->d_gen_status, 0, sizeof(int)));
     CK(cudaMalloc(&ctx->d_episode, sizeof(unsigned) * P));
     CK(cudaMemset(ctx->d_episode, 0, sizeof(unsigned) * P));
-    CK(cudaMalloc(&ctx->d_traj, sizeof(double) * 60 * N));
+    CK(cudaMalloc(&ctx->d_traj, sizeof(double) * 80 * N));
+    CK(cudaMalloc(&ctx->d_cams, sizeof(render::Camera) * N));
     CK(cudaMalloc(&ctx->d_traj_n, sizeof(int) * N));
-    CK(cudaMemset(ctx->d_traj, 0, sizeof(double) * 60 * N));
+    CK(cudaMemset(ctx->d_traj, 0, sizeof(double) * 80 * N));
     CK(cudaMemset(ctx->d_traj_n, 0, sizeof(int) * N));
     CK(cudaMalloc(&ctx->d_plan_rem, sizeof(double) * 5 * N));
     CK(cudaMalloc(&ctx->d_plan_u8, 9 * N));
@@ -1671,7 +1674,6 @@ int hope_create(hope_ctx **out, int device, int n_envs, int pool_size, const hop
     if (const char *e = getenv("HOPE_B200_HOST_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->host_chunks = v; }
     CK(cudaFuncSetAttribute(k_observe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((OBS_THREADS / 32) * sizeof(ObserveSmem))));
     CK(cudaFuncSetAttribute(k_render, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(render::Smem)));
-    ctx->render_blocks = ctx->sm_count;  // persistent: one 1024-thread CTA (150 KB of shared memory) per SM
     {   // configs.py:26-30, 80-88; TRAJ_COLORS = np.linspace(LOW, HIGH, 20, endpoint=True, dtype=np.uint8)
         uint8_t rgb[HOPE_N_COLOR][3] = {{255, 255, 255}, {150, 150, 150}, {100, 149, 237}, {69, 139, 0}, {30, 144, 255}};
         const double low[3] = {10, 10, 10}, high[3] = {10, 10, 200};
@@ -1690,7 +1692,7 @@ int hope_destroy(hope_ctx *ctx) {
     cudaSetDevice(ctx->device);
     void *ptrs[] = {ctx->d_obs, ctx->d_aabb, ctx->d_meta, ctx->d_nv, ctx->d_nobs, ctx->d_tab, ctx->d_pose, ctx->d_accum, ctx->d_t,
                     ctx->d_scene, ctx->d_pending, ctx->d_gate, ctx->d_counters, ctx->d_words, ctx->d_ntry, ctx->d_ncand, ctx->d_cs, ctx->d_item_base, ctx->d_items, ctx->d_item_bad, ctx->d_slots, ctx->d_n_items, ctx->d_plan_rem, ctx->d_plan_u8, ctx->d_regen_slots, ctx->d_regen_count, ctx->d_gen_status, ctx->d_episode,
-                    ctx->d_action, ctx->d_stage, ctx->d_traj, ctx->d_traj_n};
+                    ctx->d_action, ctx->d_stage, ctx->d_traj, ctx->d_traj_n, ctx->d_cams};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->host_graph) cudaGraphExecDestroy(ctx->host_graph);

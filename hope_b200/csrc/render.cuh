@@ -9,15 +9,20 @@
 //   process_img           white -> black, cv2.resize to 64 x 64 (INTER_LINEAR), / 255
 // cv2's 4x INTER_LINEAR reads only source pixels 4i+1 and 4i+2 of every axis, so an output pixel is the rounded
 // mean of 4 crop pixels, and each crop pixel is ONE screen pixel through two integer shifts and the 16.16
-// fixed-point rotation.  One CTA per env (persistent grid, one CTA per SM):
-//   1. camera: the composed integer map crop pixel -> screen pixel, and the screen window the 128 x 128 sample
-//      lattice can touch (<= 360 x 360 pixels) — kept as one byte per pixel in shared memory;
-//   2. paint: one warp per shape, one lane per scan line, pygame's scan conversion restated literally
-//      (draw_fillpoly, draw_line); the painter's order becomes a per-byte MAX of the colour index (later shapes
-//      have larger indices), applied with __vmaxu4 + shared-memory CAS so all shapes paint concurrently;
-//   3. gather: each thread resolves output pixels = 4 window bytes -> palette -> (sum + 2) >> 2, staged in shared
-//      memory and written with 128-bit stores as uint8 [3][64][64] (the reference's float64 image is this / 255).
-// HBM traffic per env-step: 12 288 B written + ~1.6 KB read (scene ring vertices, trajectory ring buffer).
+// fixed-point rotation.
+//   k_render_camera (thread / env): the composed integer map crop pixel -> screen pixel (Camera, 96 B per env).
+//   k_render (CTA / quadrant of an env's image, 256 threads, ~45 KB of shared memory, 5 CTAs per SM):
+//   1. set-up: the screen window the quadrant's 64 x 64 sample lattice can touch (<= 180 x 180 pixels) is kept as
+//      one byte per pixel (the colour index) in shared memory; one thread per shape turns its ring into integer
+//      screen vertices and a scan-conversion record (edges in draw_fillpoly's visiting order); the start-box
+//      outline (draw_line, Bresenham) becomes 5 segment records whose pixel run on any row has a closed form;
+//   2. paint: one thread OWNS one window row and replays the painter's order over the shapes that cross it —
+//      pygame's scan conversion restated literally, plain (non-atomic) word stores, no inter-thread ordering;
+//      each warp first ballots the shapes that touch its 32-row band;
+//   3. gather: each thread resolves output pixels = 4 window bytes -> palette -> (sum + 2) >> 2 and stores them as
+//      uint8 [3][64][64], a warp writing one 32-byte sector per channel (the reference's float64 image is this / 255).
+// HBM traffic per env-step: 12 288 B written + ~1.3 KB read (scene ring vertices, trajectory ring buffer; the other
+// three quadrants hit L2).
 #pragma once
 
 namespace render {
@@ -27,11 +32,15 @@ constexpr int OBS = 256;          // configs.py:89-90 OBS_W, OBS_H
 constexpr int IMG = 64;           // OBS / downsample_rate (observation_processor.py:8)
 constexpr int KSCALE = 12;        // configs.py:103 K
 constexpr int TRAJ = 20;          // configs.py:86 TRAJ_RENDER_LEN
-constexpr int PITCH = 368;        // window bytes per row: 253 * sqrt(2) + 1 pixels + alignment to 4
-constexpr int ROWS = 364;
-constexpr int THREADS = 1024;
+constexpr int QUAD = 32;          // output pixels per quadrant side (4 quadrants of the 64 x 64 image)
+constexpr int PITCHW = 47;        // window words per row (188 pixels >= 125 sqrt(2) + 2 + alignment); odd, so the rows
+                                  // owned by adjacent lanes start in different banks
+constexpr int PITCH = PITCHW * 4;
+constexpr int ROWS = 180;
+constexpr int THREADS = 256;
 constexpr int MAXSHAPES = MAXO + 3 + TRAJ;
 constexpr int NCOLOR = 5 + TRAJ;  // 0 background, 1 obstacle, 2 start outline, 3 dest, 4 vehicle, 5.. trajectory old -> new
+static_assert(THREADS >= ROWS + 1 && MAXSHAPES <= THREADS - 2 - NCOLOR, "row owners + the probe thread; shape threads, palette threads and the camera thread are disjoint");
 
 struct Palette { uint32_t rg[NCOLOR], b[NCOLOR]; };  // R | G << 16 and B: 16-bit lanes so four samples add without carry
 
@@ -42,117 +51,36 @@ struct Camera {
     int rx0, ry0;          // crop -> "rotate" surface offset (the 500 x 500 blit target)
     int nx, ny;            // capture size
     int a0, a1, a2, b0, b1, b2;
-    int wx0, wy0, wx1, wy1;  // screen window (inclusive), wx0 aligned to 4
+    int wx0, wy0, wx1, wy1;  // screen window of one quadrant (inclusive), wx0 aligned to 4; filled in by k_render
     double kbx, kby;       // coord_transform_matrix offsets
+    int ulo, uhi, vlo, vhi;  // crop pixels that land on the rotated screen copy at all (the rest reads as background)
+};
+// a Camera in shared memory, plus what k_render derives for its quadrant
+struct QuadCamera : Camera { int fast; };  // 1: every sample of the quadrant maps inside the screen (no per-sample checks)
+static_assert(sizeof(Camera) == 96, "one Camera per env in HBM");
+
+struct Edge { short ylo, yhi, xlo, dx; int dy; float rdy; };  // non-horizontal edge, lower end first: x(y) = xlo + (y - ylo) dx / dy
+
+struct Shape {   // one ring prepared for draw_fillpoly
+    short miny, maxy, minx, maxx;
+    short color, ne, nh, outline;      // outline = 1: the width-1 start box (runs in Smem::orun), 0: filled
+    Edge e[4];                         // in the order draw_fillpoly visits them (decides floor / ceil)
+    short hy[4], hxa[4], hxb[4];       // horizontal edges strictly between miny and maxy (incl. the closing zero-length edge)
 };
 
-struct Shape {
-    int px[5], py[5];
-    int n;       // points (a closed ring repeats its first point, like shapely's coords)
-    int color;   // palette index
-    int outline; // 1: width=1 polygon (lines), 0: filled
-};
+// One segment of the width-1 start box (draw.c draw_line).  kind 0: horizontal run or single point, 1: vertical,
+// 2: x-major Bresenham, 3: y-major Bresenham (dx <= dy)
+struct Seg { short ylo, yhi, x1, y1, xa, xb, dx, dy, sx, sy, err0, kind; float rdy; };
 
 struct Smem {
-    Camera cam;
+    QuadCamera cam;
     Shape shapes[MAXSHAPES];
     int nshapes;
-    unsigned probe;                     // colour index painted on screen pixel (0, 0): rotate()'s background
-    alignas(16) unsigned char stage[3 * IMG * IMG]; // output staging
-    alignas(16) uint32_t win[ROWS * PITCH / 4];
+    uint32_t probe;                     // screen pixel (0, 0) in byte 0: rotate()'s background colour index
+    Seg seg[5];
+    uint2 pal[NCOLOR];                  // (R | G << 16, B)
+    alignas(16) uint32_t win[ROWS * PITCHW + 3];
 };
-
-// per-byte max of `val` into a shared-memory word
-__device__ __forceinline__ void smem_max4(uint32_t *w, uint32_t val) {
-    uint32_t old = *w;
-    while (true) {
-        const uint32_t nw = __vmaxu4(old, val);
-        if (nw == old) return;
-        const uint32_t prev = atomicCAS(w, old, nw);
-        if (prev == old) return;
-        old = prev;
-    }
-}
-
-// drawhorzlineclip restricted to the window (+ the (0,0) probe)
-__device__ __forceinline__ void hline(Smem &sm, int color, int x1, int y, int x2) {
-    if (x2 < x1) { const int t = x1; x1 = x2; x2 = t; }
-    if (y < 0 || y >= WIN) return;
-    x1 = max(x1, 0); x2 = min(x2, WIN - 1);
-    if (x2 < x1) return;
-    const Camera &c = sm.cam;
-    if (y == 0 && x1 == 0) atomicMax(&sm.probe, (unsigned)color);
-    if (y < c.wy0 || y > c.wy1) return;
-    x1 = max(x1, c.wx0); x2 = min(x2, c.wx1);
-    if (x2 < x1) return;
-    const int a = x1 - c.wx0, b = x2 - c.wx0;
-    uint32_t *row = sm.win + (y - c.wy0) * (PITCH / 4);
-    const uint32_t fill = (uint32_t)color * 0x01010101u;
-    for (int w = a >> 2; w <= (b >> 2); ++w) {
-        const int lo = max(a - 4 * w, 0), hi = min(b - 4 * w, 3);  // byte range inside the word
-        const uint32_t mask = (0xffffffffu >> (8 * (3 - hi))) & (0xffffffffu << (8 * lo));
-        smem_max4(row + w, fill & mask);
-    }
-}
-
-__device__ __forceinline__ void pixel(Smem &sm, int color, int x, int y) { hline(sm, color, x, y, x); }
-
-// draw.c draw_fillpoly, scan line y (one lane); miny/maxy over the shape's points
-__device__ __forceinline__ void fill_row(Smem &sm, const Shape &s, int y, int miny, int maxy) {
-    if (miny == maxy) {  // one pixel high: a single run from min x to max x
-        int mn = s.px[0], mx = s.px[0];
-        for (int i = 1; i < s.n; ++i) { mn = min(mn, s.px[i]); mx = max(mx, s.px[i]); }
-        hline(sm, s.color, mn, y, mx);
-        return;
-    }
-    int xs[6];
-    int cnt = 0;
-    for (int i = 0; i < s.n; ++i) {
-        const int ip = i ? i - 1 : s.n - 1;
-        int y1 = s.py[ip], y2 = s.py[i], x1, x2;
-        if (y1 < y2) { x1 = s.px[ip]; x2 = s.px[i]; }
-        else if (y1 > y2) { y2 = s.py[ip]; y1 = s.py[i]; x2 = s.px[ip]; x1 = s.px[i]; }
-        else continue;
-        if ((y >= y1 && y < y2) || (y == maxy && y2 == maxy)) {
-            float q = __fdiv_rn((float)((y - y1) * (x2 - x1)), (float)(y2 - y1));
-            q = (cnt & 1) ? ceilf(q) : floorf(q);
-            if (cnt < 6) xs[cnt] = (int)q + x1;
-            ++cnt;
-        }
-    }
-    cnt = min(cnt, 6);
-    for (int i = 1; i < cnt; ++i) {  // qsort of a handful of ints
-        const int v = xs[i];
-        int j = i - 1;
-        while (j >= 0 && xs[j] > v) { xs[j + 1] = xs[j]; --j; }
-        xs[j + 1] = v;
-    }
-    for (int i = 0; i + 1 < cnt; i += 2) hline(sm, s.color, xs[i], y, xs[i + 1]);
-    for (int i = 0; i < s.n; ++i) {  // horizontal edges strictly between miny and maxy
-        const int ip = i ? i - 1 : s.n - 1;
-        if (s.py[i] == y && miny < y && s.py[ip] == y && y < maxy) hline(sm, s.color, s.px[i], y, s.px[ip]);
-    }
-}
-
-// draw.c draw_line (one lane walks one segment)
-__device__ void line(Smem &sm, int color, int x1, int y1, int x2, int y2) {
-    if (y1 == y2) { hline(sm, color, x1, y1, x2); return; }
-    if (x1 == x2) {
-        const int lo = min(y1, y2), hi = max(y1, y2);
-        for (int y = max(lo, 0); y <= min(hi, WIN - 1); ++y) pixel(sm, color, x1, y);
-        return;
-    }
-    const int dx = abs(x2 - x1), sx = x1 < x2 ? 1 : -1;
-    const int dy = abs(y2 - y1), sy = y1 < y2 ? 1 : -1;
-    int err = (dx > dy ? dx : -dy) / 2;
-    for (int guard = 0; guard < 8 * WIN && (x1 != x2 || y1 != y2); ++guard) {
-        pixel(sm, color, x1, y1);
-        const int e2 = err;
-        if (e2 > -dx) { err -= dy; x1 += sx; }
-        if (e2 < dy) { err += dx; y1 += sy; }
-    }
-    pixel(sm, color, x2, y2);
-}
 
 // _coord_transform + pygame's (int) conversion of one world point
 __device__ __forceinline__ void to_screen(const Camera &c, double x, double y, int &ix, int &iy) {
@@ -160,193 +88,384 @@ __device__ __forceinline__ void to_screen(const Camera &c, double x, double y, i
     iy = (int)((double)KSCALE * y + c.kby);
 }
 
-__device__ __forceinline__ void ring_shape(Shape &s, const Camera &c, const double *bx, const double *by, int nv, int color, int outline) {
-    for (int k = 0; k < nv; ++k) to_screen(c, bx[k], by[k], s.px[k], s.py[k]);
-    s.px[nv] = s.px[0]; s.py[nv] = s.py[0];
-    s.n = nv + 1; s.color = color; s.outline = outline;
+// ring (nv world vertices) -> Shape.  pygame receives shapely's closed coordinate list: nv + 1 points, last = first.
+__device__ void ring_shape(Shape &S, const Camera &c, const double *bx, const double *by, int nv, int color, int outline) {
+    int px[5], py[5];
+    int mny = 0x7fff, mxy = -0x8000, mnx = 0x7fff, mxx = -0x8000;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (k < nv) {
+            to_screen(c, bx[k], by[k], px[k], py[k]);
+            mny = min(mny, py[k]); mxy = max(mxy, py[k]); mnx = min(mnx, px[k]); mxx = max(mxx, px[k]);
+        }
+    }
+#pragma unroll
+    for (int k = 1; k < 5; ++k) if (k == nv) { px[k] = px[0]; py[k] = py[0]; }
+    const int n = nv + 1;
+    S.miny = (short)mny; S.maxy = (short)mxy; S.minx = (short)mnx; S.maxx = (short)mxx;
+    S.color = (short)color; S.outline = (short)outline;
+    int ne = 0, nh = 0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {  // draw_fillpoly's edge loop: (p[i-1], p[i]) with p[-1] = p[n-1]
+        if (i < n) {
+            const int ip = i ? i - 1 : n - 1;
+            const int y1 = py[ip], y2 = py[i];
+            if (y1 != y2) {
+                const bool up = y1 < y2;
+                Edge E;
+                E.ylo = (short)(up ? y1 : y2); E.yhi = (short)(up ? y2 : y1);
+                E.xlo = (short)(up ? px[ip] : px[i]);
+                E.dx = (short)(up ? px[i] - px[ip] : px[ip] - px[i]);
+                E.dy = (int)E.yhi - (int)E.ylo; E.rdy = __frcp_rn((float)E.dy);
+                if (ne < 4) S.e[ne] = E;
+                ++ne;
+            } else if (mny < y2 && y2 < mxy) {
+                if (nh < 4) { S.hy[nh] = (short)y2; S.hxa[nh] = (short)px[i]; S.hxb[nh] = (short)px[ip]; }
+                ++nh;
+            }
+        }
+    }
+    S.ne = (short)min(ne, 4); S.nh = (short)min(nh, 4);
 }
+
+// draw.c draw_line, one segment (x1, y1) -> (x2, y2).  The walk
+//     err = (dx > dy ? dx : -dy) / 2;  loop: plot; e2 = err; if (e2 > -dx) { err -= dy; x += sx; } if (e2 < dy) { err += dx; y += sy; }
+// advances x every iteration when dx > dy, with the i-th pixel on row offset ceil((i dy - err0) / dx); otherwise it
+// advances y every iteration, with row offset j at column offset ceil((j dx + err0) / dy).  So the pixels of row offset k
+// are i in (((k-1) dx + err0) / dy, (k dx + err0) / dy] (x-major) or the single column above (y-major) — checked
+// exhaustively against the literal walk for |dx|, |dy| <= 40 (oracle/softraster.py line_pixels).
+__device__ void make_seg(Seg &g, int x1, int y1, int x2, int y2) {
+    g.ylo = (short)min(y1, y2); g.yhi = (short)max(y1, y2);
+    g.x1 = (short)x1; g.y1 = (short)y1;
+    g.xa = (short)min(x1, x2); g.xb = (short)max(x1, x2);
+    const int dx = abs(x2 - x1), dy = abs(y2 - y1);
+    g.dx = (short)dx; g.dy = (short)dy;
+    g.sx = (short)(x1 < x2 ? 1 : -1); g.sy = (short)(y1 < y2 ? 1 : -1);
+    g.kind = (short)(y1 == y2 ? 0 : (x1 == x2 ? 1 : (dx > dy ? 2 : 3)));
+    g.err0 = (short)(dx > dy ? dx / 2 : -(dy / 2));
+    g.rdy = dy ? __frcp_rn((float)dy) : 0.0f;
+}
+
+// inclusive run [x1, x2] of screen row `row` (byte offset of screen x is x - base), clipped to [cx0, cx1]; the
+// calling thread owns the row
+__device__ __forceinline__ void span(uint32_t *row, int base, int cx0, int cx1, int x1, int x2, uint32_t fill) {
+    int a = max(min(x1, x2), cx0) - base, b = min(max(x1, x2), cx1) - base;
+    if (b < a) return;
+    const int wa = a >> 2, wb = b >> 2;
+    const uint32_t ma = 0xffffffffu << (8 * (a & 3)), mb = 0xffffffffu >> (8 * (3 - (b & 3)));
+    if (wa == wb) {
+        const uint32_t m = ma & mb;
+        row[wa] = (row[wa] & ~m) | (fill & m);
+        return;
+    }
+    row[wa] = (row[wa] & ~ma) | (fill & ma);
+    for (int w = wa + 1; w < wb; ++w) row[w] = fill;
+    row[wb] = (row[wb] & ~mb) | (fill & mb);
+}
+
+// exact floor / ceil of num / dy (dy > 0, |num| < 2^22): the reference's float division followed by floor / ceil
+// is exact on these magnitudes, so integer arithmetic reproduces it
+__device__ __forceinline__ int div_round(int num, int dy, float rdy, bool up) {
+    int t = __float2int_rd(__int2float_rn(num) * rdy);
+    int r = num - t * dy;
+    if (r < 0) { --t; r += dy; } else if (r >= dy) { ++t; r -= dy; }
+    return t + ((up && r != 0) ? 1 : 0);
+}
+
+// What one shape paints on screen row y (owned by the calling thread).
+__device__ void paint_shape_row(const Smem &sm, const Shape &S, int y, uint32_t *row, int base, int cx0, int cx1) {
+    {
+        if (y < S.miny || y > S.maxy) return;
+        const uint32_t fill = (uint32_t)S.color * 0x01010101u;
+        if (S.outline) {  // lines(closed=True): 5 segments of the closed coordinate list
+            for (int k = 0; k < 5; ++k) {
+                const Seg g = sm.seg[k];
+                if (y < g.ylo || y > g.yhi) continue;
+                int xa = g.xa, xb = g.xb;  // kind 0
+                if (g.kind == 1) { xa = xb = g.x1; }
+                else if (g.kind >= 2) {
+                    const int k_ = (y - g.y1) * g.sy;  // row offset along the walk, 0 .. dy
+                    if (g.kind == 2) {
+                        const int ilo = max(div_round((k_ - 1) * g.dx + g.err0, g.dy, g.rdy, false) + 1, 0);
+                        const int ihi = min(div_round(k_ * g.dx + g.err0, g.dy, g.rdy, false), (int)g.dx);
+                        xa = g.x1 + g.sx * ilo; xb = g.x1 + g.sx * ihi;
+                    } else {
+                        xa = xb = g.x1 + g.sx * div_round(k_ * g.dx + g.err0, g.dy, g.rdy, true);
+                    }
+                }
+                span(row, base, cx0, cx1, xa, xb, fill);
+            }
+            return;
+        }
+        if (S.miny == S.maxy) { span(row, base, cx0, cx1, S.minx, S.maxx, fill); return; }  // one pixel high
+        int x0 = 0, x1 = 0, x2 = 0, x3 = 0, cnt = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (e < S.ne) {
+                const Edge E = S.e[e];
+                if ((y >= E.ylo && y < E.yhi) || (y == S.maxy && E.yhi == S.maxy)) {
+                    const int v = E.xlo + div_round((y - E.ylo) * E.dx, E.dy, E.rdy, cnt & 1);  // floor, ceil, floor, ceil
+                    if (cnt == 0) x0 = v; else if (cnt == 1) x1 = v; else if (cnt == 2) x2 = v; else x3 = v;
+                    ++cnt;
+                }
+            }
+        }
+        if (cnt == 2 || cnt == 3) {
+            if (cnt == 3) {  // sorted, the first two form the pair (the third has no partner)
+                const int lo = min(x0, min(x1, x2)), hi = max(x0, max(x1, x2));
+                const int mid = x0 + x1 + x2 - lo - hi;
+                x0 = lo; x1 = mid;
+            }
+            span(row, base, cx0, cx1, x0, x1, fill);
+        } else if (cnt == 4) {
+            int a = min(x0, x1), b = max(x0, x1), c = min(x2, x3), d = max(x2, x3);
+            const int s0 = min(a, c), s3 = max(b, d), m1 = max(a, c), m2 = min(b, d);
+            span(row, base, cx0, cx1, s0, min(m1, m2), fill);
+            span(row, base, cx0, cx1, max(m1, m2), s3, fill);
+        }
+        for (int k = 0; k < S.nh; ++k)
+            if (S.hy[k] == y) span(row, base, cx0, cx1, S.hxa[k], S.hxb[k], fill);
+    }
+}
+
+static_assert(MAXO != 16 || sizeof(Smem) <= 44 * 1024, "5 CTAs per SM (227 KB, 1 KB reserved per CTA)");
 
 }  // namespace render
 
-// traj: [N][20][3] ring buffer of Vehicle.trajectory's tail, traj_n: [N] its length (see k_advance)
-__global__ void __launch_bounds__(render::THREADS, 1)
-k_render(int n, Pool pool, EnvState st, const double *__restrict__ traj, const int *__restrict__ traj_n, hope_params par,
-         render::Palette pal, uint8_t *__restrict__ img) {
+// One thread per env: the camera of this step (see Camera).
+__global__ void __launch_bounds__(128) k_render_camera(int n, Pool pool, EnvState st, hope_params par, render::Camera *__restrict__ cams) {
+    using namespace render;
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= n) return;
+    const double *meta = pool.meta + (size_t)st.scene[env] * META;
+    const double x = st.pose[3 * env], y = st.pose[3 * env + 1], h = st.pose[3 * env + 2];
+    const double ch = st.cs[2 * env], sh = st.cs[2 * env + 1];
+    Camera c;
+    c.kbx = 0.5 * (WIN - KSCALE * (meta[M_BOUNDS + 1] + meta[M_BOUNDS]));  // car_parking_base.py:143-144
+    c.kby = 0.5 * (WIN - KSCALE * (meta[M_BOUNDS + 3] + meta[M_BOUNDS + 2]));
+    // centroid of the vehicle ring (GEOS lineal centroid, see oracle/geom.py), then _coord_transform (:328)
+    double qx[5], qy[5];
+    vehicle_box(x, y, ch, sh, par.box_x, par.box_y, qx, qy);
+    qx[4] = qx[0]; qy[4] = qy[0];
+    double tot = 0.0, sx = 0.0, sy = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double ddx = qx[k] - qx[k + 1], ddy = qy[k] - qy[k + 1];
+        const double seg = sqrt(ddx * ddx + ddy * ddy);
+        if (seg == 0.0) continue;
+        tot += seg;
+        sx += seg * ((qx[k] + qx[k + 1]) / 2);
+        sy += seg * ((qy[k] + qy[k + 1]) / 2);
+    }
+    const double vcx = KSCALE * (sx / tot) + c.kbx, vcy = KSCALE * (sy / tot) + c.kby;
+    const double ddx = (vcx - WIN / 2) * ch + (vcy - WIN / 2) * sh;   // :329-332
+    const double ddy = -(vcx - WIN / 2) * sh + (vcy - WIN / 2) * ch;
+    const int ox = (int)(-ddx), oy = (int)(-ddy);
+    // pygame.transform.rotate: the angle is a C float of the degrees
+    const float angle = (float)(h * (180.0 / HOPE_PI));
+    if (fmod((double)angle, 90.0) == 0.0) {  // rotate90 path: exact quarter turns of the 500 x 500 screen
+        int q = ((int)angle / 90) % 4;
+        if (q < 0) q += 4;
+        c.nx = WIN; c.ny = WIN;
+        const int one = 1 << 16, last = (WIN - 1) << 16;
+        if (q == 0) { c.a0 = 0; c.a1 = one; c.a2 = 0; c.b0 = 0; c.b1 = 0; c.b2 = one; }
+        else if (q == 1) { c.a0 = last; c.a1 = 0; c.a2 = -one; c.b0 = 0; c.b1 = one; c.b2 = 0; }
+        else if (q == 2) { c.a0 = last; c.a1 = -one; c.a2 = 0; c.b0 = last; c.b1 = 0; c.b2 = -one; }
+        else { c.a0 = 0; c.a1 = 0; c.a2 = one; c.b0 = last; c.b1 = -one; c.b2 = 0; }
+    } else {
+        const double rad = (double)angle * .01745329251994329;
+        double sa, ca;
+        sincos(rad, &sa, &ca);
+        const double cx = ca * WIN, cy = ca * WIN, sxx = sa * WIN, syy = sa * WIN;
+        c.nx = (int)fmax(fmax(fmax(fabs(cx + syy), fabs(cx - syy)), fabs(-cx + syy)), fabs(-cx - syy));
+        c.ny = (int)fmax(fmax(fmax(fabs(sxx + cy), fabs(sxx - cy)), fabs(-sxx + cy)), fabs(-sxx - cy));
+        const int cyc = c.ny / 2, xd = (WIN - c.nx) << 15, yd = (WIN - c.ny) << 15;
+        const int isin = (int)(sa * 65536), icos = (int)(ca * 65536);
+        const int ax = (c.nx << 15) - (int)(ca * ((c.nx - 1) << 15));
+        const int ay = (c.ny << 15) - (int)(sa * ((c.nx - 1) << 15));
+        c.a0 = ax + isin * cyc + xd; c.a1 = icos; c.a2 = -isin;
+        c.b0 = ay - icos * cyc + yd; c.b1 = isin; c.b2 = icos;
+    }
+    // crop pixel (u, v) = observation pixel (122 + u, 122 + v) = rotate-surface pixel shifted by the blit
+    // offset = capture pixel shifted by the centred blit (Rect.center setter: x = cx - w / 2)
+    const int crop0 = (WIN - OBS) / 2;
+    c.rx0 = crop0 - ox; c.ry0 = crop0 - oy;
+    c.cx0 = c.rx0 - (WIN / 2 - (c.nx >> 1)); c.cy0 = c.ry0 - (WIN / 2 - (c.ny >> 1));
+    c.wx0 = c.wy0 = c.wx1 = c.wy1 = 0; c.ulo = c.uhi = c.vlo = c.vhi = 0;
+    cams[env] = c;
+}
+
+// traj: [N][20][4] ring buffer (x, y, cos h, sin h) of Vehicle.trajectory's tail, traj_n: [N] its length (see k_advance)
+__global__ void __launch_bounds__(render::THREADS, 5)
+k_render(int n, Pool pool, EnvState st, const render::Camera *__restrict__ cams, hope_params par, render::Palette pal,
+         uint8_t *__restrict__ img) {
     using namespace render;
     extern __shared__ __align__(16) unsigned char render_smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(render_smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = THREADS / 32;
-
-    for (int env = blockIdx.x; env < n; env += gridDim.x) {
-        const int sid = st.scene[env];
-        const double *meta = pool.meta + (size_t)sid * META;
-        const double x = st.pose[3 * env], y = st.pose[3 * env + 1], h = st.pose[3 * env + 2];
-        const double ch = st.cs[2 * env], sh = st.cs[2 * env + 1];
-        const int tn = traj_n[env];
-        // ---------------------------------------------------------------- 1. camera (one thread)
-        if (tid == 0) {
-            Camera c;
-            c.kbx = 0.5 * (WIN - KSCALE * (meta[M_BOUNDS + 1] + meta[M_BOUNDS]));  // car_parking_base.py:143-144
-            c.kby = 0.5 * (WIN - KSCALE * (meta[M_BOUNDS + 3] + meta[M_BOUNDS + 2]));
-            // centroid of the vehicle ring (GEOS lineal centroid, see oracle/geom.py), then _coord_transform (:328)
-            double qx[5], qy[5];
-            vehicle_box(x, y, ch, sh, par.box_x, par.box_y, qx, qy);
-            qx[4] = qx[0]; qy[4] = qy[0];
-            double tot = 0.0, sx = 0.0, sy = 0.0;
-            for (int k = 0; k < 4; ++k) {
-                const double ddx = qx[k] - qx[k + 1], ddy = qy[k] - qy[k + 1];
-                const double seg = sqrt(ddx * ddx + ddy * ddy);
-                if (seg == 0.0) continue;
-                tot += seg;
-                sx += seg * ((qx[k] + qx[k + 1]) / 2);
-                sy += seg * ((qy[k] + qy[k + 1]) / 2);
-            }
-            const double vcx = KSCALE * (sx / tot) + c.kbx, vcy = KSCALE * (sy / tot) + c.kby;
-            const double ddx = (vcx - WIN / 2) * ch + (vcy - WIN / 2) * sh;   // :329-332
-            const double ddy = -(vcx - WIN / 2) * sh + (vcy - WIN / 2) * ch;
-            const int ox = (int)(-ddx), oy = (int)(-ddy);
-            // pygame.transform.rotate: the angle is a C float of the degrees
-            const float angle = (float)(h * (180.0 / HOPE_PI));
-            if (fmod((double)angle, 90.0) == 0.0) {  // rotate90 path: exact quarter turns of the 500 x 500 screen
-                int q = ((int)angle / 90) % 4;
-                if (q < 0) q += 4;
-                c.nx = WIN; c.ny = WIN;
-                const int one = 1 << 16, last = (WIN - 1) << 16;
-                if (q == 0) { c.a0 = 0; c.a1 = one; c.a2 = 0; c.b0 = 0; c.b1 = 0; c.b2 = one; }
-                else if (q == 1) { c.a0 = last; c.a1 = 0; c.a2 = -one; c.b0 = 0; c.b1 = one; c.b2 = 0; }
-                else if (q == 2) { c.a0 = last; c.a1 = -one; c.a2 = 0; c.b0 = last; c.b1 = 0; c.b2 = -one; }
-                else { c.a0 = 0; c.a1 = 0; c.a2 = one; c.b0 = last; c.b1 = -one; c.b2 = 0; }
-            } else {
-                const double rad = (double)angle * .01745329251994329;
-                const double sa = sin(rad), ca = cos(rad);
-                const double cx = ca * WIN, cy = ca * WIN, sxx = sa * WIN, syy = sa * WIN;
-                c.nx = (int)fmax(fmax(fmax(fabs(cx + syy), fabs(cx - syy)), fabs(-cx + syy)), fabs(-cx - syy));
-                c.ny = (int)fmax(fmax(fmax(fabs(sxx + cy), fabs(sxx - cy)), fabs(-sxx + cy)), fabs(-sxx - cy));
-                const int cyc = c.ny / 2, xd = (WIN - c.nx) << 15, yd = (WIN - c.ny) << 15;
-                const int isin = (int)(sa * 65536), icos = (int)(ca * 65536);
-                const int ax = (c.nx << 15) - (int)(ca * ((c.nx - 1) << 15));
-                const int ay = (c.ny << 15) - (int)(sa * ((c.nx - 1) << 15));
-                c.a0 = ax + isin * cyc + xd; c.a1 = icos; c.a2 = -isin;
-                c.b0 = ay - icos * cyc + yd; c.b1 = isin; c.b2 = icos;
-            }
-            // crop pixel (u, v) = observation pixel (122 + u, 122 + v) = rotate-surface pixel shifted by the blit
-            // offset = capture pixel shifted by the centred blit (Rect.center setter: x = cx - w / 2)
-            const int crop0 = (WIN - OBS) / 2;
-            c.rx0 = crop0 - ox; c.ry0 = crop0 - oy;
-            c.cx0 = c.rx0 - (WIN / 2 - (c.nx >> 1)); c.cy0 = c.ry0 - (WIN / 2 - (c.ny >> 1));
-            // screen window touched by the sample lattice u, v in {4i+1, 4i+2}: the map is affine, so the
-            // corners bound it
-            int fx0 = 0x7fffffff, fx1 = -0x7fffffff - 1, fy0 = 0x7fffffff, fy1 = -0x7fffffff - 1;
-            for (int k = 0; k < 4; ++k) {
-                const int xc = ((k & 1) ? OBS - 2 : 1) + c.cx0, yc = ((k & 2) ? OBS - 2 : 1) + c.cy0;
-                const int fx = c.a0 + c.a1 * xc + c.a2 * yc, fy = c.b0 + c.b1 * xc + c.b2 * yc;
-                fx0 = min(fx0, fx); fx1 = max(fx1, fx); fy0 = min(fy0, fy); fy1 = max(fy1, fy);
-            }
-            c.wx0 = max(fx0 >> 16, 0) & ~3; c.wx1 = min(min(fx1 >> 16, WIN - 1), c.wx0 + PITCH - 1);
-            c.wy0 = max(fy0 >> 16, 0); c.wy1 = min(min(fy1 >> 16, WIN - 1), c.wy0 + ROWS - 1);
-            sm.cam = c;
-            sm.probe = 0u;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int env = blockIdx.x >> 2, quad = blockIdx.x & 3;
+    const int u0 = (quad & 1) * (OBS / 2), v0 = (quad >> 1) * (OBS / 2);  // crop origin of this quadrant
+    const int sid = st.scene[env];
+    const double *meta = pool.meta + (size_t)sid * META;
+    // ---------------------------------------------------------------- 1. set-up, one phase: camera + window (one
+    // otherwise idle thread), shapes (one thread each; they only need the two screen offsets), window clear (all)
+    if (tid == THREADS - 2) {
+        QuadCamera c;
+        static_cast<Camera &>(c) = cams[env];
+        // screen window touched by the sample lattice u, v in {4i+1, 4i+2} of this quadrant: the map is affine, so
+        // the corners bound it
+        int fx0 = 0x7fffffff, fx1 = -0x7fffffff - 1, fy0 = 0x7fffffff, fy1 = -0x7fffffff - 1;
+        for (int k = 0; k < 4; ++k) {
+            const int xc = u0 + ((k & 1) ? OBS / 2 - 2 : 1) + c.cx0, yc = v0 + ((k & 2) ? OBS / 2 - 2 : 1) + c.cy0;
+            const int fx = c.a0 + c.a1 * xc + c.a2 * yc, fy = c.b0 + c.b1 * xc + c.b2 * yc;
+            fx0 = min(fx0, fx); fx1 = max(fx1, fx); fy0 = min(fy0, fy); fy1 = max(fy1, fy);
         }
-        __syncthreads();
-        const Camera &cam = sm.cam;
-        // ---------------------------------------------------------------- shapes + clear the window
-        {
-            const int nobs = pool.nobs[sid];
-            const int ntraj = tn > 1 ? min(tn, TRAJ) : 0;
-            const int total = nobs + 3 + ntraj;
-            if (tid == 0) sm.nshapes = total;
-            for (int s = tid; s < total; s += THREADS) {
-                Shape &S = sm.shapes[s];
-                double bx[4], by[4];
-                if (s < nobs) {  // :303-305 obstacles
-                    const int nv = pool.nv[(size_t)sid * MAXO + s];
-                    const double2 *v = reinterpret_cast<const double2 *>(pool.obs) + ((size_t)sid * MAXO + s) * MAXV;
-                    for (int k = 0; k < nv; ++k) { const double2 p = __ldg(v + k); bx[k] = p.x; by[k] = p.y; }
-                    ring_shape(S, cam, bx, by, nv, 1, 0);
-                } else if (s == nobs) {  // :307-308 start box, width = 1
-                    double ss, cc;
-                    sincos(meta[M_START + 2], &ss, &cc);
-                    vehicle_box(meta[M_START], meta[M_START + 1], cc, ss, par.box_x, par.box_y, bx, by);
-                    ring_shape(S, cam, bx, by, 4, 2, 1);
-                } else if (s == nobs + 1) {  // :309-310 dest box
-                    for (int k = 0; k < 4; ++k) { bx[k] = meta[M_DBX + k]; by[k] = meta[M_DBY + k]; }
-                    ring_shape(S, cam, bx, by, 4, 3, 0);
-                } else if (s == nobs + 2) {  // :312-313 vehicle
-                    vehicle_box(x, y, ch, sh, par.box_x, par.box_y, bx, by);
-                    ring_shape(S, cam, bx, by, 4, 4, 0);
-                } else {  // :315-319 trajectory[-(ntraj - i)], colour TRAJ_COLORS[-(ntraj - i)]
-                    const int i = s - (nobs + 3), back = ntraj - i;  // back = 1: newest
-                    const double *p = traj + ((size_t)env * TRAJ + (tn - back) % TRAJ) * 3;
-                    double ss, cc;
-                    sincos(p[2], &ss, &cc);
-                    vehicle_box(p[0], p[1], cc, ss, par.box_x, par.box_y, bx, by);
-                    ring_shape(S, cam, bx, by, 4, 5 + TRAJ - back, 0);
+        c.wx0 = min(max(fx0 >> 16, 0), WIN - 1) & ~3; c.wx1 = min(min(max(fx1 >> 16, 0), WIN - 1), c.wx0 + PITCH - 1);
+        c.wy0 = min(max(fy0 >> 16, 0), WIN - 1); c.wy1 = min(min(max(fy1 >> 16, 0), WIN - 1), c.wy0 + ROWS - 1);
+        // crop pixels inside the 500 x 500 blit target AND inside the rotated copy (both axis-aligned in u, v)
+        c.ulo = max(-c.rx0, -c.cx0); c.uhi = min(WIN - 1 - c.rx0, c.nx - 1 - c.cx0);
+        c.vlo = max(-c.ry0, -c.cy0); c.vhi = min(WIN - 1 - c.ry0, c.ny - 1 - c.cy0);
+        const int fmax_ = (WIN << 16) - 1;
+        c.fast = (u0 + 1 >= c.ulo && u0 + OBS / 2 - 2 <= c.uhi && v0 + 1 >= c.vlo && v0 + OBS / 2 - 2 <= c.vhi &&
+                  fx0 >= 0 && fy0 >= 0 && fx1 <= fmax_ && fy1 <= fmax_) ? 1 : 0;
+        sm.cam = c;
+        sm.probe = 0u;
+    }
+    if (tid >= THREADS - 2 - NCOLOR && tid < THREADS - 2) sm.pal[tid - (THREADS - 2 - NCOLOR)] = make_uint2(pal.rg[tid - (THREADS - 2 - NCOLOR)], pal.b[tid - (THREADS - 2 - NCOLOR)]);
+    {
+        const int nobs = pool.nobs[sid];
+        const int tn = st.traj_n[env];
+        const int ntraj = tn > 1 ? min(tn, TRAJ) : 0;
+        const int total = nobs + 3 + ntraj;
+        if (tid == 0) sm.nshapes = total;
+        if (tid < total) {
+            const int s = tid;
+            Shape &S = sm.shapes[s];
+            double bx[4], by[4];
+            Camera cam;  // only the screen offsets are read here
+            cam.kbx = cams[env].kbx; cam.kby = cams[env].kby;
+            if (s < nobs) {  // :303-305 obstacles
+                const int nv = pool.nv[(size_t)sid * MAXO + s];
+                const double2 *v = reinterpret_cast<const double2 *>(pool.obs) + ((size_t)sid * MAXO + s) * MAXV;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) if (k < nv) { const double2 p = __ldg(v + k); bx[k] = p.x; by[k] = p.y; }
+                ring_shape(S, cam, bx, by, nv, 1, 0);
+            } else if (s == nobs) {  // :307-308 start box, width = 1: lines(closed=True) over the 5 coordinates
+                double ss, cc;
+                sincos(meta[M_START + 2], &ss, &cc);
+                vehicle_box(meta[M_START], meta[M_START + 1], cc, ss, par.box_x, par.box_y, bx, by);
+                ring_shape(S, cam, bx, by, 4, 2, 1);
+                int px[4], py[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) to_screen(cam, bx[q], by[q], px[q], py[q]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) make_seg(sm.seg[k], px[k], py[k], px[(k + 1) & 3], py[(k + 1) & 3]);
+                make_seg(sm.seg[4], px[0], py[0], px[0], py[0]);  // (p4 = p0) -> p0: a single pixel
+            } else if (s == nobs + 1) {  // :309-310 dest box
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { bx[k] = meta[M_DBX + k]; by[k] = meta[M_DBY + k]; }
+                ring_shape(S, cam, bx, by, 4, 3, 0);
+            } else if (s == nobs + 2) {  // :312-313 vehicle
+                const double x = st.pose[3 * env], y = st.pose[3 * env + 1], c = st.cs[2 * env], sn = st.cs[2 * env + 1];
+                vehicle_box(x, y, c, sn, par.box_x, par.box_y, bx, by);
+                ring_shape(S, cam, bx, by, 4, 4, 0);
+                if (ntraj > 0) {  // the newest trajectory box is painted later over the very same pixels: skip this one
+                    const double2 *p = reinterpret_cast<const double2 *>(st.traj) + ((size_t)env * TRAJ + (tn - 1) % TRAJ) * 2;
+                    const double2 xy = p[0], cs = p[1];
+                    if (xy.x == x && xy.y == y && cs.x == c && cs.y == sn) { S.miny = 1; S.maxy = 0; }
+                }
+            } else {  // :315-319 trajectory[-(ntraj - i)], colour TRAJ_COLORS[-(ntraj - i)]
+                const int i = s - (nobs + 3), back = ntraj - i;  // back = 1: newest
+                const double2 *p = reinterpret_cast<const double2 *>(st.traj) + ((size_t)env * TRAJ + (tn - back) % TRAJ) * 2;
+                const double2 xy = p[0], cs = p[1];
+                vehicle_box(xy.x, xy.y, cs.x, cs.y, par.box_x, par.box_y, bx, by);
+                ring_shape(S, cam, bx, by, 4, 5 + TRAJ - back, 0);
+            }
+        }
+        uint4 *w4 = reinterpret_cast<uint4 *>(sm.win);  // the whole window: its extent is being computed concurrently
+        for (int k = tid; k < (ROWS * PITCHW + 3) / 4; k += THREADS) w4[k] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+    const QuadCamera &cam = sm.cam;
+    // ---------------------------------------------------------------- 2. paint: one thread owns one window row
+    {
+        const int nrows = cam.wy1 - cam.wy0 + 1;
+        // the last thread owns screen pixel (0, 0) instead (rotate()'s background colour), as a 1-pixel "row"
+        const bool probe = tid == THREADS - 1;
+        const int y = tid < nrows ? cam.wy0 + tid : (probe ? 0 : -1);
+        uint32_t *row = probe ? &sm.probe : sm.win + tid * PITCHW;
+        const int base = probe ? 0 : cam.wx0, cx1 = probe ? 0 : cam.wx1;
+        const int band_lo = __reduce_min_sync(HOPE_FULL_MASK, y >= 0 ? y : 0x7fffffff);
+        const int band_hi = __reduce_max_sync(HOPE_FULL_MASK, y);
+        if (band_hi >= 0) {
+            const int ns = sm.nshapes;
+            for (int sb = 0; sb < ns; sb += 32) {  // shapes that touch this warp's band of rows, in the painter's order
+                const int s = sb + lane;
+                unsigned m = __ballot_sync(HOPE_FULL_MASK, s < ns && sm.shapes[s].maxy >= band_lo && sm.shapes[s].miny <= band_hi);
+                while (m) {
+                    const int hit = sb + __ffs(m) - 1;
+                    m &= m - 1;
+                    if (y >= 0) paint_shape_row(sm, sm.shapes[hit], y, row, base, base, cx1);
                 }
             }
-            const int words = (cam.wy1 - cam.wy0 + 1) * (PITCH / 4);
-            uint4 *w4 = reinterpret_cast<uint4 *>(sm.win);
-            for (int k = tid; k < (words + 3) / 4; k += THREADS) w4[k] = make_uint4(0u, 0u, 0u, 0u);
         }
-        __syncthreads();
-        // ---------------------------------------------------------------- 2. paint: warp per shape, lane per scan line
-        for (int s = warp; s < sm.nshapes; s += nwarps) {
-            const Shape &S = sm.shapes[s];
-            if (S.outline) {
-                // lines(closed=True): segments (p0,p1) .. (p[n-2],p[n-1]) then (p[n-1], p0)
-                if (lane < S.n) {
-                    const int a = lane, b = (lane + 1 == S.n) ? 0 : lane + 1;
-                    line(sm, S.color, S.px[a], S.py[a], S.px[b], S.py[b]);
-                }
-                continue;
-            }
-            int miny = S.py[0], maxy = S.py[0];
-            for (int k = 1; k < S.n; ++k) { miny = min(miny, S.py[k]); maxy = max(maxy, S.py[k]); }
-            // only rows that can matter: the window, plus row 0 for the background probe
-            const int lo = max(miny, cam.wy0), hi = min(maxy, cam.wy1);
-            for (int yy = lo + lane; yy <= hi; yy += 32) fill_row(sm, S, yy, miny, maxy);
-            if (lane == 0 && miny <= 0 && maxy >= 0 && cam.wy0 > 0) fill_row(sm, S, 0, miny, maxy);
-        }
-        __syncthreads();
-        // ---------------------------------------------------------------- 3. gather 64 x 64 x (2 x 2 samples)
-        {
-            const unsigned bgidx = sm.probe;
-            const unsigned char *win8 = reinterpret_cast<const unsigned char *>(sm.win);
-            const int xmaxv = (WIN << 16) - 1;
-            for (int p = tid; p < IMG * IMG; p += THREADS) {
-                const int i = p & (IMG - 1), j = p >> 6;  // output column, row
+    }
+    __syncthreads();
+    // ---------------------------------------------------------------- 3. gather 32 x 32 x (2 x 2 samples)
+    {
+        const unsigned char *win8 = reinterpret_cast<const unsigned char *>(sm.win);
+        const int a0 = cam.a0, a1 = cam.a1, a2 = cam.a2, b0 = cam.b0, b1 = cam.b1, b2 = cam.b2;
+        const int woff = cam.wy0 * PITCH + cam.wx0;
+        const int i = tid & (QUAD - 1);
+        const int ub = u0 + 4 * i + 1, xc = ub + cam.cx0;
+        uint8_t *out = img + (size_t)env * 3 * IMG * IMG + (quad >> 1) * QUAD * IMG + (quad & 1) * QUAD + i;
+        if (cam.fast) {
+#pragma unroll
+            for (int r = 0; r < QUAD * QUAD / THREADS; ++r) {
+                const int j = (tid >> 5) + r * (THREADS / QUAD);
+                const int yc = v0 + 4 * j + 1 + cam.cy0;
+                const int fxb = a0 + a1 * xc + a2 * yc, fyb = b0 + b1 * xc + b2 * yc;
                 uint32_t srg = 0u, sb = 0u;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const int u = 4 * i + 1 + (k & 1), v = 4 * j + 1 + (k >> 1);
-                    unsigned idx = 0u;  // background: white -> black, and the untouched (black) blit target
-                    const int xr = u + cam.rx0, yr = v + cam.ry0;
-                    const int xc = u + cam.cx0, yc = v + cam.cy0;
-                    if ((unsigned)xr < (unsigned)WIN && (unsigned)yr < (unsigned)WIN && (unsigned)xc < (unsigned)cam.nx &&
-                        (unsigned)yc < (unsigned)cam.ny) {
-                        const int fx = cam.a0 + cam.a1 * xc + cam.a2 * yc, fy = cam.b0 + cam.b1 * xc + cam.b2 * yc;
-                        if (fx < 0 || fy < 0 || fx > xmaxv || fy > xmaxv) idx = bgidx;
-                        else {
-                            const int sx = fx >> 16, sy = fy >> 16;
-                            if (sx >= cam.wx0 && sx <= cam.wx1 && sy >= cam.wy0 && sy <= cam.wy1)
-                                idx = win8[(sy - cam.wy0) * PITCH + (sx - cam.wx0)];
-                        }
-                    }
-                    srg += pal.rg[idx]; sb += pal.b[idx];
+                    const int fx = fxb + ((k & 1) ? a1 : 0) + ((k >> 1) ? a2 : 0), fy = fyb + ((k & 1) ? b1 : 0) + ((k >> 1) ? b2 : 0);
+                    const uint2 c = sm.pal[win8[(fy >> 16) * PITCH + (fx >> 16) - woff]];
+                    srg += c.x; sb += c.y;
                 }
                 srg = ((srg + 0x00020002u) >> 2) & 0x00ff00ffu;  // (a + b + c + d + 2) >> 2 per 16-bit lane
                 sb = (sb + 2u) >> 2;
-                sm.stage[p] = (unsigned char)(srg & 0xffu);
-                sm.stage[IMG * IMG + p] = (unsigned char)(srg >> 16);
-                sm.stage[2 * IMG * IMG + p] = (unsigned char)sb;
+                uint8_t *o = out + j * IMG;  // a warp writes 32 consecutive bytes per channel: one full sector each
+                o[0] = (uint8_t)(srg & 0xffu); o[IMG * IMG] = (uint8_t)(srg >> 16); o[2 * IMG * IMG] = (uint8_t)sb;
+            }
+        } else {
+            const unsigned bgidx = sm.probe & 0xffu;
+            const unsigned xmaxv = (WIN << 16) - 1;
+            const int ulo = cam.ulo, uhi = cam.uhi, vlo = cam.vlo, vhi = cam.vhi;
+            for (int r = 0; r < QUAD * QUAD / THREADS; ++r) {
+                const int j = (tid >> 5) + r * (THREADS / QUAD);
+                const int vb = v0 + 4 * j + 1, yc = vb + cam.cy0;
+                const int fxb = a0 + a1 * xc + a2 * yc, fyb = b0 + b1 * xc + b2 * yc;
+                uint32_t srg = 0u, sb = 0u;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int u = ub + (k & 1), v = vb + (k >> 1);
+                    unsigned idx = 0u;  // background: white -> black, and the untouched (black) blit target
+                    if (u >= ulo && u <= uhi && v >= vlo && v <= vhi) {
+                        const int fx = fxb + ((k & 1) ? a1 : 0) + ((k >> 1) ? a2 : 0), fy = fyb + ((k & 1) ? b1 : 0) + ((k >> 1) ? b2 : 0);
+                        if ((unsigned)fx > xmaxv || (unsigned)fy > xmaxv) idx = bgidx;  // negative wraps to a huge unsigned
+                        else {
+                            const unsigned off = (unsigned)((fy >> 16) * PITCH + (fx >> 16) - woff);
+                            if (off < (unsigned)(ROWS * PITCH)) idx = win8[off];
+                        }
+                    }
+                    const uint2 c = sm.pal[idx];
+                    srg += c.x; sb += c.y;
+                }
+                srg = ((srg + 0x00020002u) >> 2) & 0x00ff00ffu;
+                sb = (sb + 2u) >> 2;
+                uint8_t *o = out + j * IMG;
+                o[0] = (uint8_t)(srg & 0xffu); o[IMG * IMG] = (uint8_t)(srg >> 16); o[2 * IMG * IMG] = (uint8_t)sb;
             }
         }
-        __syncthreads();
-        {
-            const uint4 *src = reinterpret_cast<const uint4 *>(sm.stage);
-            uint4 *dst = reinterpret_cast<uint4 *>(img + (size_t)env * 3 * IMG * IMG);
-            for (int k = tid; k < 3 * IMG * IMG / 16; k += THREADS) dst[k] = src[k];
-        }
-        // the next iteration's first barrier orders these reads before the staging area is rewritten; the camera is
-        // rewritten by thread 0 only after it passed the barrier above, when every thread is done with phase 3
     }
 }
