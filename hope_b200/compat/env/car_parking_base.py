@@ -1,11 +1,12 @@
 """CarParking facade (car_parking_base.py:39-541 surface) over one env of the CUDA backend.
 
 Same constructor, attributes and return values as the reference class for the lidar / target /
-action-mask modalities.  Differences, all by construction of the backend:
+action-mask / image modalities.  Differences, all by construction of the backend:
   * scenes come from hope_generate_scenes (same distributions as parking_map_normal.py, own RNG),
     or from `load_scene()`; the global numpy RNG is not consumed;
   * no pygame window, no clock.tick (the reference sleeps to <= fps steps/s, :409);
-  * the image modality is row f1 of the scope table: `use_img_observation=True` raises.
+  * the image (scope row f1) is rendered by k_render as uint8 and divided by 255.0 here, which is exactly
+    what Obs_Processor.process_img returns (observation_processor.py:13-17); there is no pygame surface.
 """
 from collections import OrderedDict
 
@@ -78,12 +79,9 @@ class CarParking(object):
 
     def __init__(self, render_mode=None, fps=100, verbose=True, use_lidar_observation=True, use_img_observation=True,
                  use_action_mask=True, device=0, seed=None):
-        if use_img_observation:
-            raise NotImplementedError("the image modality (pygame raster, car_parking_base.py:301-350) is not part of the CUDA "
-                                      "backend yet (scope row f1); construct with use_img_observation=False")
         self.verbose, self.fps = verbose, fps
         self.render_mode = "human" if render_mode is None else render_mode
-        self.use_lidar_observation, self.use_img_observation, self.use_action_mask = use_lidar_observation, False, use_action_mask
+        self.use_lidar_observation, self.use_img_observation, self.use_action_mask = use_lidar_observation, bool(use_img_observation), use_action_mask
         self.level = "Normal"
         self.t = 0.0
         self.vehicle = Vehicle()
@@ -93,6 +91,9 @@ class CarParking(object):
         self.observation_space = {}
         if use_action_mask:
             self.observation_space["action_mask"] = Box(0, 1, shape=(N_DISCRETE_ACTION,), dtype=np.float64)
+        if use_img_observation:  # car_parking_base.py:93-98: (OBS_W // 4, OBS_H // 4, 3) uint8
+            self.observation_space["img"] = Box(0, 255, shape=(64, 64, 3), dtype=np.uint8)
+            self.raw_img_shape = (256, 256, 3)
         if use_lidar_observation:
             self.observation_space["lidar"] = Box(np.zeros(LIDAR_NUM), np.ones(LIDAR_NUM) * LIDAR_RANGE, shape=(LIDAR_NUM,), dtype=np.float64)
         self.observation_space["target"] = Box(np.array([0, -1, -1, -1, -1]), np.array([MAX_DIST_TO_DEST, 1, 1, 1, 1]), shape=(5,), dtype=np.float64)
@@ -144,12 +145,13 @@ class CarParking(object):
         self.map.load(sc)
         cap = int(np.asarray(sc["nverts"]).shape[1])
         if cap not in self._backends:
-            self._backends[cap] = BatchedParkingEnv(1, scenes=sc, device=self._device, auto_reset=False)
+            self._backends[cap] = BatchedParkingEnv(1, scenes=sc, device=self._device, auto_reset=False,
+                                                    use_img_observation=self.use_img_observation)
         else:
             self._backends[cap].set_scene_pool(sc)
         self._backend = self._backends[cap]
         self.t = 1.0
-        out = self._backend.reset_host(outputs=self._OUT)
+        out = self._backend.reset_host(outputs=self._outputs())
         self.vehicle.initial_state = self.map.start
         return self._unpack(out)[0]
 
@@ -163,12 +165,17 @@ class CarParking(object):
 
     def _step_unit(self, unit_action):
         """policy-scale action in [-1,1]^2 (what CarParkingWrapper.step receives), no round trip through physical units"""
-        out = self._backend.step_host(np.asarray(unit_action, dtype=np.float64).reshape(1, 2), outputs=self._OUT)
+        out = self._backend.step_host(np.asarray(unit_action, dtype=np.float64).reshape(1, 2), outputs=self._outputs())
         self.t += 1
         return self._unpack(out)
 
+    def _outputs(self):
+        return self._OUT + (("img",) if self.use_img_observation else ())
+
     def _unpack(self, out):
         obs = {"img": None, "lidar": None, "target": out["target"][0].copy(), "action_mask": None}
+        if self.use_img_observation:  # (64, 64, 3) float64 like process_img; the wrapper transposes to (3, 64, 64)
+            obs["img"] = out["img"][0].transpose(1, 2, 0) / 255.0
         if self.use_lidar_observation:
             obs["lidar"] = out["lidar"][0].copy()
         if self.use_action_mask:

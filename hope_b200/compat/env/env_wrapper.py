@@ -12,6 +12,15 @@ class CarParkingWrapper(object):
             raise NotImplementedError("custom action/reward/observation functions would have to run on the device")
         self.env = env
         self.observation_shape = {k: self.env.observation_space[k].shape for k in self.env.observation_space}
+        if "img" in self.observation_shape:  # env_wrapper.py:68-71
+            w, h, c = self.observation_shape["img"]
+            self.observation_shape["img"] = (c, w, h)
+
+    @staticmethod
+    def _rescale(obs):  # observation_rescale, env_wrapper.py:52-55
+        if obs["img"] is not None:
+            obs["img"] = obs["img"].transpose((2, 0, 1))
+        return obs
 
     def __getattr__(self, name):
         if name.startswith("_"):
@@ -24,7 +33,7 @@ class CarParkingWrapper(object):
         # action_rescale (env_wrapper.py:37-50: clip, scale to steer/speed units) runs on the device
         obs, reward_info, status, info = self.env._step_unit(np.asarray(action, dtype=np.float64))
         info["status"] = status
-        return obs, self.env._shaped_reward, status != Status.CONTINUE, info
+        return self._rescale(obs), self.env._shaped_reward, status != Status.CONTINUE, info
 
     def reset(self, *args):
-        return self.env.reset(*args)
+        return self._rescale(self.env.reset(*args))

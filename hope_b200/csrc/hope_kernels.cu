@@ -1349,7 +1349,7 @@ struct hope_ctx {
     int sm_count = 148, walk_blocks = 148 * 4, check_blocks = 148 * 4;
     // host-API staging
     double *d_action = nullptr;
-    void *d_stage = nullptr;
+    void *d_stage = nullptr, *d_stage_img = nullptr;
     size_t stage_bytes = 0;
     hope_out stage_out;
     cudaStream_t own_stream = nullptr;
@@ -1538,15 +1538,23 @@ int launch_step(hope_ctx *ctx, const double *d_action, const hope_out &out, unsi
     return launch_range(ctx, d_action, out, stages, reset_all, s, 0, 0, 0, ctx->n);
 }
 
-int ensure_stage(hope_ctx *ctx) {
+// staging buffers of the host API; the image (12 KB per env) only when a caller asks for it
+int ensure_stage(hope_ctx *ctx, bool want_img) {
+    if (want_img && !ctx->d_stage_img) {
+        CK(cudaMalloc(&ctx->d_stage_img, (size_t)ctx->n * HOPE_IMG_C * HOPE_IMG_HW * HOPE_IMG_HW));
+        ctx->stage_out.img = static_cast<uint8_t *>(ctx->d_stage_img);
+    }
     if (ctx->d_stage) return HOPE_OK;
+    const size_t img_offset = offsetof(hope_out, img);
     size_t total = 0;
-    for (int k = 0; k < kNumOutFields; ++k) total += ((kOutFields[k].elem * kOutFields[k].per_env * ctx->n + 255) / 256) * 256;
+    for (int k = 0; k < kNumOutFields; ++k)
+        if (kOutFields[k].offset != img_offset) total += ((kOutFields[k].elem * kOutFields[k].per_env * ctx->n + 255) / 256) * 256;
     CK(cudaMalloc(&ctx->d_stage, total));
     CK(cudaMemset(ctx->d_stage, 0, total));
     ctx->stage_bytes = total;
     size_t off = 0;
     for (int k = 0; k < kNumOutFields; ++k) {
+        if (kOutFields[k].offset == img_offset) continue;
         field_ptr(ctx->stage_out, kOutFields[k]) = static_cast<char *>(ctx->d_stage) + off;
         off += ((kOutFields[k].elem * kOutFields[k].per_env * ctx->n + 255) / 256) * 256;
     }
@@ -1692,7 +1700,7 @@ int hope_destroy(hope_ctx *ctx) {
     cudaSetDevice(ctx->device);
     void *ptrs[] = {ctx->d_obs, ctx->d_aabb, ctx->d_meta, ctx->d_nv, ctx->d_nobs, ctx->d_tab, ctx->d_pose, ctx->d_accum, ctx->d_t,
                     ctx->d_scene, ctx->d_pending, ctx->d_gate, ctx->d_counters, ctx->d_words, ctx->d_ntry, ctx->d_ncand, ctx->d_cs, ctx->d_item_base, ctx->d_items, ctx->d_item_bad, ctx->d_slots, ctx->d_n_items, ctx->d_plan_rem, ctx->d_plan_u8, ctx->d_regen_slots, ctx->d_regen_count, ctx->d_gen_status, ctx->d_episode,
-                    ctx->d_action, ctx->d_stage, ctx->d_traj, ctx->d_traj_n, ctx->d_cams};
+                    ctx->d_action, ctx->d_stage, ctx->d_stage_img, ctx->d_traj, ctx->d_traj_n, ctx->d_cams};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->host_graph) cudaGraphExecDestroy(ctx->host_graph);
@@ -1934,7 +1942,7 @@ int hope_step_host(hope_ctx *ctx, const double *h_action, const hope_host_out *h
     if (!ctx->have_tables) return HOPE_ERR_NO_TABLES;
     if (!ctx->have_reset) return HOPE_ERR_NO_SCENES;
     CK(cudaSetDevice(ctx->device));
-    int rc = ensure_stage(ctx);
+    int rc = ensure_stage(ctx, h_out->img != nullptr);
     if (rc) return rc;
     stages |= HOPE_STAGE_ADVANCE;
     // Software pipeline over env ranges: range c runs on lane c % MAX_LANES (its own stream pair), so its D2H
@@ -1979,9 +1987,11 @@ int hope_step_host(hope_ctx *ctx, const double *h_action, const hope_host_out *h
 int hope_reset_host(hope_ctx *ctx, const int32_t *h_scene_ids, const hope_host_out *h_out) {
     if (!ctx || !h_out) return HOPE_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
-    int rc = ensure_stage(ctx);
+    int rc = ensure_stage(ctx, h_out->img != nullptr);
     if (rc) return rc;
-    rc = hope_reset(ctx, h_scene_ids, &ctx->stage_out, ctx->own_stream);
+    hope_out reset_out = ctx->stage_out;
+    if (!h_out->img) reset_out.img = nullptr;  // nobody reads the staged image: skip the render
+    rc = hope_reset(ctx, h_scene_ids, &reset_out, ctx->own_stream);
     if (rc) return rc;
     const unsigned keep_mask = ctx->zero_copy_mask;
     ctx->zero_copy_mask = 0;  // the reset step always goes through the staging buffers

@@ -31,8 +31,6 @@ def compat_env():
 
 def test_surface_matches_what_the_scripts_touch(compat_env):
     CarParking, CarParkingWrapper, Status, VALID_SPEED = compat_env
-    with pytest.raises(NotImplementedError):
-        CarParking(fps=100, verbose=False)  # USE_IMG default: image modality is row f1
     raw = CarParking(fps=100, verbose=False, render_mode="rgb_array", use_img_observation=False)
     env = CarParkingWrapper(raw)
     assert env.observation_shape == {"action_mask": (42,), "lidar": (120,), "target": (5,)}
@@ -100,4 +98,29 @@ def test_facade_switches_to_dlp_scenes(compat_env, golden_dir):
     assert np.isfinite(obs["lidar"]).all() and isinstance(info["status"], Status)
     obs = env.reset(None, None, "Normal")   # and back to the 16-ring backend
     assert len(env.map.obstacles) <= 16
+    env.close()
+
+
+def test_image_modality_through_the_facade(compat_env, golden_dir):
+    """USE_IMG defaults to True in the reference (configs.py:100): the facade returns the float64 (3, 64, 64)
+    image of env_wrapper.py:52-55; replay of an episode recorded from the unmodified reference."""
+    CarParking, CarParkingWrapper, Status, _ = compat_env
+    g = np.load(os.path.join(golden_dir, "images_Normal.npz"))
+    raw = CarParking(fps=100, verbose=False, render_mode="rgb_array")  # image on by default
+    env = CarParkingWrapper(raw)
+    assert env.observation_shape == {"action_mask": (42,), "img": (3, 64, 64), "lidar": (120,), "target": (5,)}
+    assert raw.observation_space["img"].shape == (64, 64, 3)
+    ep = 1
+    rows = np.where(g["ep"] == ep)[0]
+    raw.load_scene(dict(start=g["scene_start"][ep:ep + 1], dest=g["scene_dest"][ep:ep + 1], bounds=g["scene_bounds"][ep:ep + 1],
+                        obs=g["scene_obs"][ep:ep + 1], nverts=g["scene_nverts"][ep:ep + 1]))
+    obs = env.reset()
+    assert obs["img"].shape == (3, 64, 64) and obs["img"].dtype == np.float64
+    assert np.array_equal(obs["img"], g["scene_reset_img"][ep] / 255.0)
+    for k in rows:
+        obs, reward, done, info = env.step(g["action"][k])
+        assert np.array_equal(obs["img"], g["img"][k] / 255.0), f"step {k}"
+        assert 0.0 <= obs["img"].min() and obs["img"].max() <= 1.0
+        if done:
+            break
     env.close()
