@@ -153,3 +153,31 @@ def test_render_on_dragon_lake_scenes_128_ring_build(golden_dir):
     compared, _ = _lockstep_images(env, sc, n, 8, 2, check_every=2)
     assert compared >= 30
     env.close()
+
+
+def test_full_size_65536_images_placement_invariance_and_oracle_subset():
+    """BASELINE cfg-3 size with the image on: 256 distinct scenes tiled over 65 536 envs with identical actions per
+    tile -> every copy must produce the identical image (size-independent property), and a few envs are checked
+    against the oracle."""
+    n, period = 65536, 256
+    base = generate_scenes(period, "mix", 404)
+    sc = {k: np.concatenate([v] * (n // period)) for k, v in base.items()}
+    env = BatchedParkingEnv(n, scenes=sc, auto_reset=False, use_img_observation=True)
+    book = io.TrajectoryBook(period)
+    obs = env.reset()
+    for i in range(period):
+        book.reset(i, base["start"][i])
+    rng = np.random.default_rng(8)
+    drift = rng.uniform(-1, 1, size=(period, 2))
+    for k in range(6):
+        act = np.clip(0.7 * drift + 0.3 * rng.uniform(-1, 1, size=(period, 2)), -1, 1)
+        obs, _, _, _ = env.step(torch.as_tensor(np.tile(act, (n // period, 1)), device=env.device).contiguous())
+        pose, sub, ret = _np(env.out["pose"][:period]), _np(env.out["substeps"][:period]), _np(env.out["retreated"][:period])
+        for i in range(period):
+            book.step(i, pose[i], sub[i], ret[i])
+    img = obs["img"].view(n // period, period, 3, 64, 64)
+    assert bool((img == img[0:1]).all()), "copies of one scene rendered differently"
+    assert int(img[0].any(dim=(1, 2, 3)).sum()) == period  # nothing is blank
+    ids = list(range(0, period, 16))
+    assert np.array_equal(_np(img[-1])[ids], _oracle_images(base, book, ids))
+    env.close()
