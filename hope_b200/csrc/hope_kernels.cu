@@ -1358,7 +1358,12 @@ struct hope_ctx {
     // host API pipelines env ranges over all lanes so one range's D2H copies hide under the next one's kernels.
     static constexpr int MAX_LANES = 4;
     struct Lane { cudaStream_t main = nullptr, aux = nullptr; cudaEvent_t ev_advanced = nullptr, ev_observed = nullptr; } lanes[MAX_LANES];
-    int host_chunks = 4;
+    int host_chunks = 3;   // measured on B200 at 65 536 envs: 2 -> 2.60 ms, 3 -> 2.53, 4 -> 2.63, 6 -> 2.97, 8 -> 3.30 per host step
+    bool host_rs_after_observe = true;
+    bool in_host_step = false;
+    int host_debug = 0;  // HOPE_B200_HOST_DEBUG: 1 = enqueue no copies, 2 = enqueue no kernels (timing experiments only)
+    static constexpr int MAX_CHUNK_EVENTS = 64;
+    cudaEvent_t ev_chunk[MAX_CHUNK_EVENTS] = {};
     int device_chunks = 1;  // hope_step: env ranges stepped on separate lanes so one range's latency-bound kernels
                             // (advance, enumerate, walk) run under another range's issue-bound ones (observe, check)
     // hope_step_host replays a captured CUDA graph of the whole pipelined step while the caller keeps passing the
@@ -1442,6 +1447,7 @@ hope_out offset_out(const hope_out &o, size_t lo) {  // the same arrays, startin
 
 // observe: 1 = only k_observe's outputs, 0 = only the others, -1 = all; envs [lo, lo+cnt)
 int copy_fields(hope_ctx *ctx, const hope_host_out *h_out, int observe, cudaStream_t s, size_t lo, size_t cnt) {
+    if (ctx->host_debug == 1 && ctx->in_host_step) return HOPE_OK;
     for (int k = 0; k < kNumOutFields; ++k) {
         void *dst = field_ptr_c(*h_out, kOutFields[k]);
         if (!dst || (observe >= 0 && kOutFields[k].observe != observe)) continue;
@@ -1458,8 +1464,9 @@ int copy_fields(hope_ctx *ctx, const hope_host_out *h_out, int observe, cudaStre
 // kernels; the main stream waits for it at the end.  With `early_out` (host API) the observation buffers are
 // copied to the host right behind k_observe, under the RS kernels.
 int launch_range(hope_ctx *ctx, const double *d_action, const hope_out &out_all, unsigned stages, int reset_all, cudaStream_t s,
-                 int lane_id, int chunk_id, int lo, int cnt, const hope_host_out *early_out = nullptr) {
+                 int lane_id, int chunk_id, int lo, int cnt, const hope_host_out *early_out = nullptr, bool do_advance = true) {
     const int n = cnt;
+    if (ctx->host_debug == 2 && ctx->in_host_step) return HOPE_OK;
     hope_ctx::Lane &lane = ctx->lanes[lane_id];
     Pool pool = make_pool(ctx);
     Tables tb = make_tables(ctx);
@@ -1468,7 +1475,7 @@ int launch_range(hope_ctx *ctx, const double *d_action, const hope_out &out_all,
     const hope_out out = offset_out(out_all, lo);
     const double *act = d_action ? d_action + 2 * (size_t)lo : nullptr;
     const bool regen = ctx->par.regen_on_reset && ctx->par.auto_reset && !reset_all;
-    if (regen) {  // fresh scenes for the envs that finished last step, generated in place on the device
+    if (regen && do_advance) {  // fresh scenes for the envs that finished last step, generated in place on the device
         int *slots = ctx->d_regen_slots + lo, *count = ctx->d_n_items + 32 + chunk_id % 32;
         CK(cudaMemsetAsync(count, 0, sizeof(int), s));
         k_list_pending<<<(n + 127) / 128, 128, 0, s>>>(n, st.pending, st.scene, ctx->d_episode, slots, count, ctx->d_counters);
@@ -1477,10 +1484,12 @@ int launch_range(hope_ctx *ctx, const double *d_action, const hope_out &out_all,
                                         ctx->d_aabb, ctx->d_meta, ctx->d_nobs, ctx->d_gen_status, s) != HOPE_OK) return HOPE_ERR_CUDA;
         ctx->launches += 3;
     }
-    prof_mark(ctx, 0, s);
-    k_advance<<<(n + ADV_THREADS - 1) / ADV_THREADS, ADV_THREADS, 0, s>>>(n, pool, st, act, ctx->par, out, reset_all, regen ? 0 : ctx->n);
-    prof_mark(ctx, 0, s);
-    ctx->launches++;
+    if (do_advance) {
+        prof_mark(ctx, 0, s);
+        k_advance<<<(n + ADV_THREADS - 1) / ADV_THREADS, ADV_THREADS, 0, s>>>(n, pool, st, act, ctx->par, out, reset_all, regen ? 0 : ctx->n);
+        prof_mark(ctx, 0, s);
+        ctx->launches++;
+    }
     const bool image = (stages & HOPE_STAGE_IMAGE) && out.img;
     const bool side = (stages & HOPE_STAGE_OBSERVE) || image;  // work that only depends on k_advance, besides RS
     const bool fork = side && (stages & HOPE_STAGE_RS);
@@ -1668,17 +1677,28 @@ int hope_create(hope_ctx **out, int device, int n_envs, int pool_size, const hop
     }
     for (auto &ln : ctx->lanes) {
         CK(cudaStreamCreateWithFlags(&ln.main, cudaStreamNonBlocking));
-        CK(cudaStreamCreateWithFlags(&ln.aux, cudaStreamNonBlocking));
+        {   // the auxiliary stream carries k_observe, whose outputs are 90 % of the bytes the host API copies back:
+            // give it the higher priority so its blocks are scheduled ahead of the Reeds-Shepp kernels and the
+            // device-to-host copies start as early as possible (HOPE_B200_AUX_PRIORITY=0 turns this off)
+            int lo_p = 0, hi_p = 0;
+            CK(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+            const char *e = getenv("HOPE_B200_AUX_PRIORITY");
+            const bool prio = e ? atoi(e) != 0 : true;
+            CK(cudaStreamCreateWithPriority(&ln.aux, cudaStreamNonBlocking, prio ? hi_p : lo_p));
+        }
         CK(cudaEventCreateWithFlags(&ln.ev_advanced, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ln.ev_observed, cudaEventDisableTiming));
     }
     CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     for (int li = 0; li < hope_ctx::MAX_LANES; ++li) CK(cudaEventCreateWithFlags(&ctx->ev_join[li], cudaEventDisableTiming));
+    for (auto &e : ctx->ev_chunk) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     memset(&ctx->hg_out, 0, sizeof(ctx->hg_out));
     if (const char *e = getenv("HOPE_B200_HOST_GRAPH")) ctx->host_graph_enabled = atoi(e) != 0;
     if (const char *e = getenv("HOPE_B200_ZERO_COPY")) ctx->zero_copy_enabled = atoi(e) != 0;
     memset(&ctx->step_out, 0, sizeof(ctx->step_out));
     if (const char *e = getenv("HOPE_B200_DEVICE_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= 16) ctx->device_chunks = v; }
+    if (const char *e = getenv("HOPE_B200_HOST_DEBUG")) ctx->host_debug = atoi(e);
+    if (const char *e = getenv("HOPE_B200_HOST_RS_AFTER")) ctx->host_rs_after_observe = atoi(e) != 0;
     if (const char *e = getenv("HOPE_B200_HOST_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->host_chunks = v; }
     CK(cudaFuncSetAttribute(k_observe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((OBS_THREADS / 32) * sizeof(ObserveSmem))));
     CK(cudaFuncSetAttribute(k_render, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(render::Smem)));
@@ -1706,6 +1726,7 @@ int hope_destroy(hope_ctx *ctx) {
     if (ctx->host_graph) cudaGraphExecDestroy(ctx->host_graph);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     for (auto e : ctx->ev_join) if (e) cudaEventDestroy(e);
+    for (auto e : ctx->ev_chunk) if (e) cudaEventDestroy(e);
     for (auto &ln : ctx->lanes) {
         if (ln.main) cudaStreamDestroy(ln.main);
         if (ln.aux) cudaStreamDestroy(ln.aux);
@@ -1909,30 +1930,56 @@ static void plan_zero_copy(hope_ctx *ctx, const hope_host_out *h_out) {
     }
 }
 
+// One host step, ordered so that the device-to-host copies start as early as possible and never wait for the
+// Reeds-Shepp kernels: k_observe's outputs (lidar + mask) are 90 % of the bytes.
+//   s0     : H2D(actions), k_advance over all envs, then the Reeds-Shepp kernels over all envs, then their small outputs
+//   s_obs  : (high priority) k_observe [+ k_render] env range by env range, in order
+//   s_copy : the observation buffers of a range, as soon as that range's k_observe is done
+// s0 is the origin; the other two fork from it and join back, so the whole step is capturable as one CUDA graph.
+// (Letting every range run advance -> observe -> RS on its own stream pair finishes all ranges at about the same
+// time: the first copy then starts ~0.9 ms into the step whatever the number of ranges.)
 static int enqueue_host_step(hope_ctx *ctx, const double *h_action, const hope_host_out *h_out, unsigned stages) {
     if (!h_out->img) stages &= ~(unsigned)HOPE_STAGE_IMAGE;  // nobody reads the staged image
-    const bool fork = (stages & (HOPE_STAGE_OBSERVE | HOPE_STAGE_IMAGE)) && (stages & HOPE_STAGE_RS);
+    const unsigned side = stages & (HOPE_STAGE_OBSERVE | HOPE_STAGE_IMAGE);
     const int n = ctx->n;
-    int chunks = ctx->host_chunks;
-    if (n < 4096 * chunks) chunks = n / 4096 > 0 ? n / 4096 : 1;
-    const int per = ((n + chunks - 1) / chunks + 127) / 128 * 128;
-    cudaStream_t s0 = ctx->lanes[0].main;
-    CK(cudaEventRecord(ctx->ev_fork, s0));
-    for (int li = 1; li < hope_ctx::MAX_LANES; ++li) CK(cudaStreamWaitEvent(ctx->lanes[li].main, ctx->ev_fork, 0));
-    int rc;
-    for (int c = 0, lo = 0; lo < n; ++c, lo += per) {
-        const int cnt = (lo + per <= n) ? per : n - lo;
-        const int li = c % hope_ctx::MAX_LANES;
-        cudaStream_t s = ctx->lanes[li].main;
-        CK(cudaMemcpyAsync(ctx->d_action + 2 * (size_t)lo, h_action + 2 * (size_t)lo, sizeof(double) * 2 * cnt, cudaMemcpyHostToDevice, s));
-        rc = launch_range(ctx, ctx->d_action, ctx->step_out, stages, 0, s, li, c, lo, cnt, fork ? h_out : nullptr);
-        if (rc) return rc;
-        rc = copy_fields(ctx, h_out, fork ? 0 : -1, s, lo, cnt);
+    struct Scope { hope_ctx *c; ~Scope() { c->in_host_step = false; } } scope{ctx};
+    ctx->in_host_step = true;
+    cudaStream_t s0 = ctx->lanes[0].main, s_obs = ctx->lanes[0].aux, s_copy = ctx->lanes[1].main;
+    CK(cudaMemcpyAsync(ctx->d_action, h_action, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, s0));
+    int rc = launch_range(ctx, ctx->d_action, ctx->step_out, HOPE_STAGE_ADVANCE, 0, s0, 0, 0, 0, n);
+    if (rc) return rc;
+    int last_chunk = 0;
+    if (side) {
+        CK(cudaEventRecord(ctx->ev_fork, s0));
+        CK(cudaStreamWaitEvent(s_obs, ctx->ev_fork, 0));
+        CK(cudaStreamWaitEvent(s_copy, ctx->ev_fork, 0));
+        int chunks = ctx->host_chunks;
+        if (n < 4096 * chunks) chunks = n / 4096 > 0 ? n / 4096 : 1;
+        const int per = ((n + chunks - 1) / chunks + 127) / 128 * 128;
+        for (int c = 0, lo = 0; lo < n; ++c, lo += per) {
+            const int cnt = (lo + per <= n) ? per : n - lo;
+            rc = launch_range(ctx, ctx->d_action, ctx->step_out, side, 0, s_obs, 0, c, lo, cnt, nullptr, false);
+            if (rc) return rc;
+            last_chunk = c;
+            cudaEvent_t ev = ctx->ev_chunk[c % hope_ctx::MAX_CHUNK_EVENTS];
+            CK(cudaEventRecord(ev, s_obs));
+            CK(cudaStreamWaitEvent(s_copy, ev, 0));
+            rc = copy_fields(ctx, h_out, 1, s_copy, lo, cnt);
+            if (rc) return rc;
+        }
+    }
+    if (stages & HOPE_STAGE_RS) {
+        // the persistent Reeds-Shepp grids would occupy every SM and starve the (later launched) k_observe ranges
+        // whatever the stream priorities, so they start behind the last range and run under the copies instead
+        if (side && ctx->host_rs_after_observe) CK(cudaStreamWaitEvent(s0, ctx->ev_chunk[(last_chunk) % hope_ctx::MAX_CHUNK_EVENTS], 0));
+        rc = launch_range(ctx, ctx->d_action, ctx->step_out, HOPE_STAGE_RS, 0, s0, 0, 0, 0, n, nullptr, false);
         if (rc) return rc;
     }
-    for (int li = 1; li < hope_ctx::MAX_LANES; ++li) {  // every forked lane joins, used or not
-        CK(cudaEventRecord(ctx->ev_join[li], ctx->lanes[li].main));
-        CK(cudaStreamWaitEvent(s0, ctx->ev_join[li], 0));
+    rc = copy_fields(ctx, h_out, side ? 0 : -1, s0, 0, n);
+    if (rc) return rc;
+    if (side) {  // s_obs joins through the last range's event, s_copy joins here
+        CK(cudaEventRecord(ctx->ev_join[1], s_copy));
+        CK(cudaStreamWaitEvent(s0, ctx->ev_join[1], 0));
     }
     return HOPE_OK;
 }
@@ -1945,8 +1992,9 @@ int hope_step_host(hope_ctx *ctx, const double *h_action, const hope_host_out *h
     int rc = ensure_stage(ctx, h_out->img != nullptr);
     if (rc) return rc;
     stages |= HOPE_STAGE_ADVANCE;
-    // Software pipeline over env ranges: range c runs on lane c % MAX_LANES (its own stream pair), so its D2H
-    // copies travel while the next range's kernels execute.  Envs are independent, so the split changes nothing.
+    // Software pipeline (see enqueue_host_step): k_observe runs env range by env range and each range's observation
+    // buffers start their D2H copy behind it, under the Reeds-Shepp kernels.  Envs are independent, so the split
+    // changes nothing.
     cudaStream_t s0 = ctx->lanes[0].main;
     if (ctx->host_graph_enabled && !ctx->profile) {
         const bool same = ctx->host_graph && ctx->hg_action == h_action && ctx->hg_stages == stages &&
