@@ -37,6 +37,7 @@ constexpr int NITER = HOPE_N_MASK_ITER;
 constexpr int NUP = HOPE_N_UPSAMPLE;
 constexpr int META = 24;       // doubles of per-scene metadata
 constexpr int MAXW = 16;       // admitted Reeds-Shepp words kept per env
+constexpr int ADV_THREADS = 64;
 
 // per-scene metadata layout (doubles)
 enum { M_START = 0, M_DEST = 3, M_BOUNDS = 6, M_DBX = 10, M_DBY = 14, M_DAREA = 18, M_DNORM = 19, M_DAABB = 20 };
@@ -166,9 +167,14 @@ __device__ __forceinline__ double angle_gap(double a1, double a2) {  // car_park
     return d < HOPE_PI / 2 ? d : HOPE_PI - d;
 }
 
-__global__ void __launch_bounds__(128) k_advance(int n, Pool pool, EnvState st, const double *__restrict__ action,
-                                                 hope_params par, hope_out out, int reset_all, int reset_stride) {
-    __shared__ AdvanceSmem smem[4];
+// MINB = resident 64-thread blocks per SM the register allocation is sized for.  168 registers (6 blocks) is the
+// unconstrained optimum, but 65 536 envs are 1.15 waves of that; capped at 128 registers (8 blocks, a few spills) the
+// whole batch is one wave.  Small batches keep the unconstrained build.  64-thread blocks: 1 024 blocks spread over
+// 148 SMs within 1 % (512 blocks of 128 leave SMs with 3 or 4).
+template <int MINB>
+__global__ void __launch_bounds__(ADV_THREADS, MINB) k_advance(int n, Pool pool, EnvState st, const double *__restrict__ action,
+                                                       hope_params par, hope_out out, int reset_all, int reset_stride) {
+    __shared__ AdvanceSmem smem[ADV_THREADS / 32];
     const int lane = threadIdx.x & 31;
     AdvanceSmem &sm = smem[threadIdx.x >> 5];
     const int gi = blockIdx.x * blockDim.x + threadIdx.x;
@@ -836,7 +842,7 @@ __device__ int enumerate_env(int i, const Pool &pool, const EnvState &st, const 
     return ntry;
 }
 
-__global__ void __launch_bounds__(128) k_rs_enumerate(int n, Pool pool, EnvState st, Tables tb, RsScratch rs, hope_out out) {
+__global__ void __launch_bounds__(64) k_rs_enumerate(int n, Pool pool, EnvState st, Tables tb, RsScratch rs, hope_out out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
     const int ntry = i < n ? enumerate_env(i, pool, st, tb, rs, out) : 0;
     // every tried word becomes one work item of k_rs_walk / k_rs_check: warp-level prefix sum, one atomic per warp
@@ -1408,7 +1414,7 @@ Tables make_tables(const hope_ctx *c) {
     tb.maxc = c->maxc;
     return tb;
 }
-constexpr int ADV_THREADS = 128, OBS_THREADS = 64, ENUM_THREADS = 128;
+constexpr int OBS_THREADS = 64, ENUM_THREADS = 64;
 
 void prof_mark(hope_ctx *ctx, int which, cudaStream_t s) {
     if (!ctx->profile) return;
@@ -1486,7 +1492,11 @@ int launch_range(hope_ctx *ctx, const double *d_action, const hope_out &out_all,
     }
     if (do_advance) {
         prof_mark(ctx, 0, s);
-        k_advance<<<(n + ADV_THREADS - 1) / ADV_THREADS, ADV_THREADS, 0, s>>>(n, pool, st, act, ctx->par, out, reset_all, regen ? 0 : ctx->n);
+        const int adv_blocks = (n + ADV_THREADS - 1) / ADV_THREADS;
+        if (adv_blocks > 6 * ctx->sm_count)  // more than one wave at 6 blocks per SM
+            k_advance<8><<<adv_blocks, ADV_THREADS, 0, s>>>(n, pool, st, act, ctx->par, out, reset_all, regen ? 0 : ctx->n);
+        else
+            k_advance<6><<<adv_blocks, ADV_THREADS, 0, s>>>(n, pool, st, act, ctx->par, out, reset_all, regen ? 0 : ctx->n);
         prof_mark(ctx, 0, s);
         ctx->launches++;
     }
