@@ -500,6 +500,11 @@ __global__ void __launch_bounds__(64) k_observe(int n, Pool pool, EnvState st, T
                 const double db = __shfl_sync(HOPE_FULL_MASK, d, bsel);
                 const int rb = __shfl_sync(HOPE_FULL_MASK, rho, bsel);
                 const double *P = tb.pmaxk + (size_t)rb * NITER * NACT;  // [k][j], j contiguous
+                // the running maximum is monotone in k, so this ray lowers action j below its current bound s only if
+                // d < P[s-1][j]: one load per action decides; most rays after the nearest obstacles lower nothing
+                const bool need0 = s0 > 0 && db < __ldg(P + (s0 - 1) * NACT + lane);
+                const bool need1 = has2 && s1 > 0 && db < __ldg(P + (s1 - 1) * NACT + 32 + lane);
+                if (!__any_sync(HOPE_FULL_MASK, need0 || need1)) continue;
                 // every lane fetches the 10 running maxima of its action(s) in one batch of independent, coalesced,
                 // unconditional loads (row k is 42 contiguous doubles; lanes without a second action re-read column
                 // 32), then takes the first exceedance; rows at or above the current bound cannot lower it
