@@ -1529,7 +1529,7 @@ int launch_range(hope_ctx *ctx, const double *d_action, const hope_out &out_all,
             prof_mark(ctx, 6, so);
             render::Camera *cams = ctx->d_cams + lo;
             k_render_camera<<<(n + 127) / 128, 128, 0, so>>>(n, pool, st, ctx->par, cams);
-            k_render<<<4 * n, render::THREADS, sizeof(render::Smem), so>>>(n, pool, st, cams, ctx->par, ctx->palette, out.img);
+            k_render<<<n, render::THREADS, sizeof(render::Smem), so>>>(n, pool, st, cams, ctx->par, ctx->palette, out.img);
             ctx->launches++;
             prof_mark(ctx, 6, so);
             ctx->launches++;
@@ -1561,7 +1561,7 @@ int launch_range(hope_ctx *ctx, const double *d_action, const hope_out &out_all,
         prof_mark(ctx, 6, s);
         render::Camera *cams = ctx->d_cams + lo;
         k_render_camera<<<(n + 127) / 128, 128, 0, s>>>(n, pool, st, ctx->par, cams);
-        k_render<<<4 * n, render::THREADS, sizeof(render::Smem), s>>>(n, pool, st, cams, ctx->par, ctx->palette, out.img);
+        k_render<<<n, render::THREADS, sizeof(render::Smem), s>>>(n, pool, st, cams, ctx->par, ctx->palette, out.img);
         prof_mark(ctx, 6, s);
         ctx->launches += 2;
     }
