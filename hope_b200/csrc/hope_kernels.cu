@@ -1373,6 +1373,7 @@ struct hope_ctx {
     bool host_rs_after_observe = true;
     bool in_host_step = false;
     bool render_after_rs = false;
+    bool image_ok = true;  // false: the vehicle box is too large for k_render's per-box span table
     int host_debug = 0;  // HOPE_B200_HOST_DEBUG: 1 = enqueue no copies, 2 = enqueue no kernels (timing experiments only)
     static constexpr int MAX_CHUNK_EVENTS = 64;
     cudaEvent_t ev_chunk[MAX_CHUNK_EVENTS] = {};
@@ -1507,6 +1508,10 @@ int launch_range(hope_ctx *ctx, const double *d_action, const hope_out &out_all,
         ctx->launches++;
     }
     const bool image = (stages & HOPE_STAGE_IMAGE) && out.img;
+    if (image && !ctx->image_ok) {
+        ctx->last_error = "image observation: the vehicle box spans more screen rows than k_render's span table holds (render::DROWS)";
+        return HOPE_ERR_CAPACITY;
+    }
     // optional (HOPE_B200_RENDER_AFTER_RS=1): k_render behind the Reeds-Shepp kernels on the main stream instead of
     // next to them on the auxiliary one; measured equal within 2 % (11.0 vs 10.8 ms per 65 536-env step), so off
     const bool image_last = image && (stages & HOPE_STAGE_RS) && !ctx->in_host_step && ctx->render_after_rs;
@@ -1730,6 +1735,12 @@ int hope_create(hope_ctx **out, int device, int n_envs, int pool_size, const hop
     if (const char *e = getenv("HOPE_B200_HOST_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->host_chunks = v; }
     CK(cudaFuncSetAttribute(k_observe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((OBS_THREADS / 32) * sizeof(ObserveSmem))));
     CK(cudaFuncSetAttribute(k_render, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(render::Smem)));
+    {   // a vehicle-sized box covers at most diagonal * K + 2 screen rows after truncation
+        double diag = 0.0;
+        for (int a = 0; a < 4; ++a)
+            for (int b = a + 1; b < 4; ++b) diag = fmax(diag, hypot(ctx->par.box_x[a] - ctx->par.box_x[b], ctx->par.box_y[a] - ctx->par.box_y[b]));
+        ctx->image_ok = diag * render::KSCALE + 2.0 <= render::DROWS;
+    }
     {   // configs.py:26-30, 80-88; TRAJ_COLORS = np.linspace(LOW, HIGH, 20, endpoint=True, dtype=np.uint8)
         uint8_t rgb[HOPE_N_COLOR][3] = {{255, 255, 255}, {150, 150, 150}, {100, 149, 237}, {69, 139, 0}, {30, 144, 255}};
         const double low[3] = {10, 10, 10}, high[3] = {10, 10, 200};
