@@ -352,8 +352,12 @@ __global__ void __launch_bounds__(ADV_THREADS, MINB) k_advance(int n, Pool pool,
 // k_observe: one warp per env.  LiDAR raycast -> action-mask sweep -> target representation.
 // =============================================================================================
 struct ObserveSmem {
-    double ed[MAXE], ee[MAXE], ef[MAXE];                         // line coefficients d x + e y + f = 0 (ego frame)
-    double exmin[MAXE], exmax[MAXE], eymin[MAXE], eymax[MAXE];   // edge bounding box
+    // per edge, packed for 128-bit broadcast loads in the ray loop: line coefficients d x + e y + f = 0 (ego frame)
+    // and the edge bounding box
+    double2 de[MAXE];      // d, e
+    double2 fxn[MAXE];     // f, xmin
+    double2 xym[MAXE];     // xmax, ymin
+    double eymax[MAXE];
     double L[NRAY];                                              // clip(lidar)+mask_base
     int steps[NACT + 2];
     uint8_t quad[MAXE];                                          // which ray quadrants can accept this edge
@@ -398,9 +402,10 @@ __global__ void __launch_bounds__(64) k_observe(int n, Pool pool, EnvState st, T
             int e = n_edges + __popc(m & ((1u << lane) - 1));
             double x1 = a * p.x + b * p.y + xoff, y1 = mb * p.x + a * p.y + yoff;
             double x2 = a * q.x + b * q.y + xoff, y2 = mb * q.x + a * q.y + yoff;
-            sm.ed[e] = y2 - y1; sm.ee[e] = x1 - x2; sm.ef[e] = y1 * x2 - x1 * y2;  // :104-106
             double exmin = dmin(x1, x2), exmax = dmax(x1, x2), eymin = dmin(y1, y2), eymax = dmax(y1, y2);
-            sm.exmin[e] = exmin; sm.exmax[e] = exmax; sm.eymin[e] = eymin; sm.eymax[e] = eymax;
+            sm.de[e] = make_double2(y2 - y1, x1 - x2);                   // :104-106
+            sm.fxn[e] = make_double2(y1 * x2 - x1 * y2, exmin);
+            sm.xym[e] = make_double2(exmax, eymin); sm.eymax[e] = eymax;
             // exact culls: a hit must lie inside the edge's bbox (:126-129), on the ray's side of the
             // axes up to 1e-8 (:120-124), and nearer than lidar_range to survive the clip (:134)
             bool xp = exmax >= -1e-8, xn = exmin <= 1e-8, yp = eymax >= -1e-8, yn = eymin <= 1e-8;
@@ -441,13 +446,14 @@ __global__ void __launch_bounds__(64) k_observe(int n, Pool pool, EnvState st, T
         const int qn_edges = sm.qcount[q];
         for (int t = 0; t < qn_edges; ++t) {
             const int e = sm.qlist[q][t];            // warp-uniform
-            const double d = sm.ed[e], ee = sm.ee[e], f = sm.ef[e];
+            const double2 de = sm.de[e], fxn = sm.fxn[e], xym = sm.xym[e];
+            const double d = de.x, ee = de.y, f = fxn.x;
             const double det = A * ee - B * d;        // :109
             if (det == 0.0) continue;                 // parallel -> 100 -> clipped away (:131)
             double rx, ry;
             div_pair(B * f, -(A * f), det, rx, ry);   // :112-113 with c = 0
             const bool ok = !(sx * rx < -1e-8) && !(sy * ry < -1e-8) &&
-                            !(rx > sm.exmax[e]) && !(rx < sm.exmin[e]) && !(ry > sm.eymax[e]) && !(ry < sm.eymin[e]);  // :126-129
+                            !(rx > xym.x) && !(rx < fxn.y) && !(ry > sm.eymax[e]) && !(ry < xym.y);  // :126-129
             if (ok) best2 = dmin(best2, rx * rx + ry * ry);  // :133
         }
         if (live) {
@@ -1706,6 +1712,9 @@ int hope_create(hope_ctx **out, int device, int n_envs, int pool_size, const hop
         ctx->walk_blocks = ctx->sm_count * (nb > 0 ? nb : 1);
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_rs_check, CHK_WARPS * 32, 0));
         ctx->check_blocks = ctx->sm_count * (nb > 0 ? nb : 1);
+        // tuning experiments: fewer resident Reeds-Shepp blocks per SM leave registers for k_observe's blocks
+        if (const char *e = getenv("HOPE_B200_CHECK_BPS")) { int v = atoi(e); if (v >= 1 && v <= 8) ctx->check_blocks = ctx->sm_count * v; }
+        if (const char *e = getenv("HOPE_B200_WALK_BPS")) { int v = atoi(e); if (v >= 1 && v <= 16) ctx->walk_blocks = ctx->sm_count * v; }
     }
     for (auto &ln : ctx->lanes) {
         CK(cudaStreamCreateWithFlags(&ln.main, cudaStreamNonBlocking));
