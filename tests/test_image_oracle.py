@@ -86,3 +86,43 @@ def test_rotate_quarter_turns_and_general_angle():
     assert g.w > 50 and g.h > 50
     assert np.array_equal(g.arr[g.h // 2, g.w // 2], s.arr[25, 25]) or np.array_equal(g.arr[g.h // 2, g.w // 2], s.arr[24, 24]) \
         or np.array_equal(g.arr[g.h // 2, g.w // 2], s.arr[24, 25]) or np.array_equal(g.arr[g.h // 2, g.w // 2], s.arr[25, 24])
+
+
+def _bresenham_run_on_row(x1, y1, x2, y2, y):
+    """The closed form k_render uses for the pixels a draw_line walk leaves on row y (render.cuh make_seg /
+    paint_shape_row): x-major lines put pixel i on row offset ceil((i dy - err0) / dx), y-major lines put row offset j
+    at column offset ceil((j dx + err0) / dy), with err0 = (dx > dy ? dx : -dy) / 2 truncated like C."""
+    if y < min(y1, y2) or y > max(y1, y2):
+        return None
+    if y1 == y2:
+        return (min(x1, x2), max(x1, x2))
+    if x1 == x2:
+        return (x1, x1)
+    dx, dy = abs(x2 - x1), abs(y2 - y1)
+    sx, sy = (1 if x1 < x2 else -1), (1 if y1 < y2 else -1)
+    k = (y - y1) * sy
+    if dx > dy:
+        err0 = dx // 2
+        ilo = max(((k - 1) * dx + err0) // dy + 1, 0)
+        ihi = min((k * dx + err0) // dy, dx)
+        a, b = x1 + sx * ilo, x1 + sx * ihi
+        return (min(a, b), max(a, b))
+    err0 = -(dy // 2)
+    m = -((-(k * dx + err0)) // dy)  # ceil
+    return (x1 + sx * m, x1 + sx * m)
+
+
+def test_closed_form_bresenham_rows_equal_the_literal_walk():
+    checked = 0
+    for dxs in range(-33, 34):
+        for dys in range(-33, 34):
+            x1, y1 = 70, 70
+            x2, y2 = x1 + dxs, y1 + dys
+            rows = {}
+            for x, y in sr.line_pixels(x1, y1, x2, y2):
+                lo, hi = rows.get(y, (x, x))
+                rows[y] = (min(lo, x), max(hi, x))
+            for y in range(min(y1, y2) - 1, max(y1, y2) + 2):
+                assert _bresenham_run_on_row(x1, y1, x2, y2, y) == rows.get(y), (dxs, dys, y)
+                checked += 1
+    assert checked > 80000
