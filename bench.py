@@ -447,7 +447,7 @@ def main():
         sampler.lines.clear()
     barrier()
     c0 = env.counters()
-    env.profile(os.environ.get("HOPE_BENCH_NO_KERNEL_EVENTS", "0") != "1")  # per-kernel CUDA events inside the timed region
+    env.profile(True)  # per-kernel CUDA events inside the timed region
     env.profile_read()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
