@@ -514,7 +514,7 @@ def main():
                        "l2": "per-step working set (scene pool 2N x 1.7 KB + outputs N x 1.5 KB = 320 MB) exceeds the 126 MB L2; no explicit flush",
                        "counted": "env-steps with an action; auto-reset steps excluded"},
             "e2e": {"value": e2e_steps / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "hope_step_host (pinned host buffers, synchronous)", "ms_per_step": 1e3 * e2e_s / K,
+                    "api": "hope_step_host (pinned host buffers, synchronous; the float64 mask crosses PCIe as uint8 step counts and is expanded by 6 host threads inside the call)", "host_bytes_delivered_per_step": int(env.n * 1436), "ms_per_step": 1e3 * e2e_s / K,
                     "plain_d2h_copy_gbs": pcie_gbs,
                     "host_cpus_rank0": numa},
             "gpu_launches": launches,

@@ -193,11 +193,15 @@ class BatchedParkingEnv(object):
         return {k: self._host[k].numpy() for k in outputs}
 
     def host_io_bytes(self, outputs=HOST_DEFAULT):
-        """(h2d, d2h) bytes one step_host call moves."""
+        """(h2d, d2h) bytes one step_host call moves over PCIe.  The float64 action mask travels as its 42 uint8
+        step counts and is expanded by host threads inside hope_step_host (unless HOPE_B200_HOST_MASK_EXPAND=0)."""
+        import os
+        narrow_mask = os.environ.get("HOPE_B200_HOST_MASK_EXPAND", "1") != "0"
         d2h = 0
         for name, ct, shape in capi.OUT_FIELDS:
             if name in outputs:
-                d2h += self.n * int(np.prod(shape, dtype=np.int64)) * C.sizeof(ct)
+                size = C.sizeof(C.c_uint8) if (name == "mask" and narrow_mask) else C.sizeof(ct)
+                d2h += self.n * int(np.prod(shape, dtype=np.int64)) * size
         return self.n * 2 * 8, d2h
 
     # ---- state / diagnostics -------------------------------------------------------------------

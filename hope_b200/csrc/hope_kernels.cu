@@ -17,8 +17,12 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/hope_b200.h"
@@ -1319,6 +1323,8 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters, doubl
     out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
 }
 
+__global__ void k_bump_seq(unsigned long long *seq) { *seq += 1ull; }
+
 __global__ void k_table_group(const double *__restrict__ pmax, double *__restrict__ gpmax) {
     int q = threadIdx.x;
     if (q >= NRAY) return;
@@ -1333,6 +1339,47 @@ __global__ void k_table_group(const double *__restrict__ pmax, double *__restric
 // Host side: context and C ABI
 // =============================================================================================
 using namespace hope;
+
+// A few persistent host threads for the one piece of host-side work in hope_step_host (expanding the uint8
+// action-mask steps into the float64 mask while the remaining copies are still travelling).
+struct HostPool {
+    std::vector<std::thread> workers;
+    std::mutex m;
+    std::condition_variable cv, done_cv;
+    std::function<void(int, int)> job;  // (part, nparts)
+    int generation = 0, pending = 0;
+    bool stop = false;
+    void start(int n) {
+        for (int w = 0; w < n; ++w)
+            workers.emplace_back([this, w, n] {
+                int seen = 0;
+                for (;;) {
+                    std::function<void(int, int)> f;
+                    {
+                        std::unique_lock<std::mutex> lk(m);
+                        cv.wait(lk, [&] { return stop || generation != seen; });
+                        if (stop) return;
+                        seen = generation;
+                        f = job;
+                    }
+                    f(w, n);
+                    std::lock_guard<std::mutex> lk(m);
+                    if (--pending == 0) done_cv.notify_one();
+                }
+            });
+    }
+    void run(const std::function<void(int, int)> &f) {
+        std::unique_lock<std::mutex> lk(m);
+        job = f; pending = (int)workers.size(); ++generation;
+        cv.notify_all();
+        done_cv.wait(lk, [&] { return pending == 0; });
+    }
+    ~HostPool() {
+        { std::lock_guard<std::mutex> lk(m); stop = true; }
+        cv.notify_all();
+        for (auto &t : workers) t.join();
+    }
+};
 
 struct hope_ctx {
     int device = 0, n = 0, pool = 0;
@@ -1380,6 +1427,20 @@ struct hope_ctx {
     bool in_host_step = false;
     bool render_after_rs = false;
     bool image_ok = true;  // false: the vehicle box is too large for k_render's per-box span table
+    // Narrow wire format of the host API: the float64 action mask (336 B per env, 23 % of the bytes a step returns) is
+    // a function of its 42 uint8 step counts (k_observe: steps / 10, or 0.01 everywhere when all are 0), so the
+    // counts travel and a few host threads expand them into the caller's float64 buffer while the lidar copies are
+    // still in flight.  HOPE_B200_HOST_MASK_EXPAND=0 copies the float64 mask instead.
+    bool host_mask_expand = true, expanding = false;
+    uint8_t *h_mask_steps = nullptr;   // pinned [N][42]
+    HostPool *host_pool = nullptr;
+    int hm_chunks = 0, hm_per = 0;
+    // "range c's step counts have landed": a device sequence number, bumped once per host step, is copied into
+    // pinned host memory right behind each range's step counts (same stream, so in order); the host spins on it.
+    // (An event recorded inside a replayed graph cannot be used for this: until the node runs it still reports the
+    // previous launch's completed record.)
+    unsigned long long *d_seq = nullptr, host_seq = 0;
+    volatile unsigned long long *h_seq = nullptr;  // pinned [MAX_CHUNK_EVENTS]
     int host_debug = 0;  // HOPE_B200_HOST_DEBUG: 1 = enqueue no copies, 2 = enqueue no kernels (timing experiments only)
     static constexpr int MAX_CHUNK_EVENTS = 64;
     cudaEvent_t ev_chunk[MAX_CHUNK_EVENTS] = {};
@@ -1471,6 +1532,7 @@ int copy_fields(hope_ctx *ctx, const hope_host_out *h_out, int observe, cudaStre
         void *dst = field_ptr_c(*h_out, kOutFields[k]);
         if (!dst || (observe >= 0 && kOutFields[k].observe != observe)) continue;
         if ((ctx->zero_copy_mask >> k) & 1) continue;  // the kernels wrote this array straight into the caller's mapped buffer
+        if (ctx->expanding && ctx->in_host_step && kOutFields[k].offset == offsetof(hope_out, mask)) continue;  // rebuilt on the host
         const size_t row = kOutFields[k].elem * kOutFields[k].per_env;
         CK(cudaMemcpyAsync(static_cast<char *>(dst) + lo * row, static_cast<const char *>(field_ptr_c(ctx->stage_out, kOutFields[k])) + lo * row,
                            row * cnt, cudaMemcpyDeviceToHost, s));
@@ -1739,6 +1801,7 @@ int hope_create(hope_ctx **out, int device, int n_envs, int pool_size, const hop
     memset(&ctx->step_out, 0, sizeof(ctx->step_out));
     if (const char *e = getenv("HOPE_B200_DEVICE_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= 16) ctx->device_chunks = v; }
     if (const char *e = getenv("HOPE_B200_RENDER_AFTER_RS")) ctx->render_after_rs = atoi(e) != 0;
+    if (const char *e = getenv("HOPE_B200_HOST_MASK_EXPAND")) ctx->host_mask_expand = atoi(e) != 0;
     if (const char *e = getenv("HOPE_B200_HOST_DEBUG")) ctx->host_debug = atoi(e);
     if (const char *e = getenv("HOPE_B200_HOST_RS_AFTER")) ctx->host_rs_after_observe = atoi(e) != 0;
     if (const char *e = getenv("HOPE_B200_HOST_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->host_chunks = v; }
@@ -1775,6 +1838,10 @@ int hope_destroy(hope_ctx *ctx) {
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     for (auto e : ctx->ev_join) if (e) cudaEventDestroy(e);
     for (auto e : ctx->ev_chunk) if (e) cudaEventDestroy(e);
+    if (ctx->h_mask_steps) cudaFreeHost(ctx->h_mask_steps);
+    if (ctx->h_seq) cudaFreeHost(const_cast<unsigned long long *>(ctx->h_seq));
+    if (ctx->d_seq) cudaFree(ctx->d_seq);
+    delete ctx->host_pool;
     for (auto &ln : ctx->lanes) {
         if (ln.main) cudaStreamDestroy(ln.main);
         if (ln.aux) cudaStreamDestroy(ln.aux);
@@ -1978,6 +2045,77 @@ static void plan_zero_copy(hope_ctx *ctx, const hope_host_out *h_out) {
     }
 }
 
+// Decide whether this host step returns the action mask through its uint8 step counts (see hope_ctx::host_mask_expand).
+static int plan_mask_expand(hope_ctx *ctx, const hope_host_out *h_out, unsigned stages) {
+    const int mask_field = 2;  // index of `mask` in kOutFields
+    ctx->expanding = ctx->host_mask_expand && h_out->mask && (stages & HOPE_STAGE_OBSERVE) && !((ctx->zero_copy_mask >> mask_field) & 1);
+    if (!ctx->expanding) return HOPE_OK;
+    if (!ctx->h_mask_steps) {
+        CK(cudaMallocHost(&ctx->h_mask_steps, (size_t)ctx->n * NACT));
+        unsigned long long *hs = nullptr;
+        CK(cudaMallocHost(&hs, sizeof(unsigned long long) * hope_ctx::MAX_CHUNK_EVENTS));
+        memset(hs, 0, sizeof(unsigned long long) * hope_ctx::MAX_CHUNK_EVENTS);
+        ctx->h_seq = hs;
+        CK(cudaMalloc(&ctx->d_seq, sizeof(unsigned long long)));
+        CK(cudaMemset(ctx->d_seq, 0, sizeof(unsigned long long)));
+        CK(cudaDeviceSynchronize());  // the step runs on non-blocking streams, which do not order after the memset
+        ctx->host_seq = 0;
+    }
+    if (!ctx->host_pool) {
+        ctx->host_pool = new (std::nothrow) HostPool();
+        if (!ctx->host_pool) return HOPE_ERR_INVALID;
+        int nt = 6;
+        if (const char *e = getenv("HOPE_B200_HOST_THREADS")) { int v = atoi(e); if (v >= 1 && v <= 64) nt = v; }
+        ctx->host_pool->start(nt);
+    }
+    ctx->step_out.mask = nullptr;  // k_observe does not write the float64 mask at all
+    return HOPE_OK;
+}
+
+// action_mask.py:182-183 on the host: mask = steps / 10, or 0.01 everywhere when every step count of the env is 0
+// (the same expression k_observe evaluates; steps / 10 through a table of the 11 possible quotients).
+static void expand_mask_range(const uint8_t *steps, double *mask, size_t lo, size_t hi) {
+    double lut[NITER + 1];
+    for (int k = 0; k <= NITER; ++k) lut[k] = (double)k / 10;
+    for (size_t i = lo; i < hi; ++i) {
+        const uint8_t *sp = steps + i * NACT;
+        double *mp = mask + i * NACT;
+        unsigned total = 0;
+        for (int j = 0; j < NACT; ++j) total += sp[j];
+        if (total == 0) { for (int j = 0; j < NACT; ++j) mp[j] = 0.01; }
+        else { for (int j = 0; j < NACT; ++j) mp[j] = lut[sp[j] <= NITER ? sp[j] : NITER]; }
+    }
+}
+
+// After the step has been launched: expand each env range's mask as soon as its step counts have landed, then wait
+// for everything else.
+static int finish_host_step(hope_ctx *ctx, const hope_host_out *h_out, cudaStream_t s0) {
+    if (ctx->expanding) {
+        double *mask = h_out->mask;
+        const unsigned long long expected = ++ctx->host_seq;  // k_bump_seq ran (or will run) once more on the device
+        for (int c = 0; c < ctx->hm_chunks; ++c) {
+            volatile unsigned long long *flag = ctx->h_seq + c % hope_ctx::MAX_CHUNK_EVENTS;
+            for (unsigned spins = 0; *flag != expected; ++spins) {
+                if ((spins & 0xfff) == 0xfff) {  // the step died or finished without delivering: do not spin forever
+                    cudaError_t q = cudaStreamQuery(s0);
+                    if (q != cudaErrorNotReady) {
+                        if (q != cudaSuccess) return fail(ctx, q, "hope_step_host");
+                        if (*flag != expected) { ctx->last_error = "hope_step_host: mask step counts did not arrive"; return HOPE_ERR_CUDA; }
+                    }
+                }
+            }
+            const size_t lo = (size_t)c * ctx->hm_per, hi = (lo + ctx->hm_per < (size_t)ctx->n) ? lo + ctx->hm_per : (size_t)ctx->n;
+            const uint8_t *steps = ctx->h_mask_steps;
+            ctx->host_pool->run([=](int part, int nparts) {
+                const size_t span = (hi - lo + nparts - 1) / nparts, a = lo + span * part, b = a + span < hi ? a + span : hi;
+                if (a < b) expand_mask_range(steps, mask, a, b);
+            });
+        }
+    }
+    CK(cudaStreamSynchronize(s0));
+    return HOPE_OK;
+}
+
 // One host step, ordered so that the device-to-host copies start as early as possible and never wait for the
 // Reeds-Shepp kernels: k_observe's outputs (lidar + mask) are 90 % of the bytes.
 //   s0     : H2D(actions), k_advance over all envs, then the Reeds-Shepp kernels over all envs, then their small outputs
@@ -1994,6 +2132,7 @@ static int enqueue_host_step(hope_ctx *ctx, const double *h_action, const hope_h
     ctx->in_host_step = true;
     cudaStream_t s0 = ctx->lanes[0].main, s_obs = ctx->lanes[0].aux, s_copy = ctx->lanes[1].main;
     CK(cudaMemcpyAsync(ctx->d_action, h_action, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, s0));
+    if (ctx->expanding) { k_bump_seq<<<1, 1, 0, s0>>>(ctx->d_seq); ctx->launches++; }
     int rc = launch_range(ctx, ctx->d_action, ctx->step_out, HOPE_STAGE_ADVANCE, 0, s0, 0, 0, 0, n);
     if (rc) return rc;
     int last_chunk = 0;
@@ -2004,6 +2143,7 @@ static int enqueue_host_step(hope_ctx *ctx, const double *h_action, const hope_h
         int chunks = ctx->host_chunks;
         if (n < 4096 * chunks) chunks = n / 4096 > 0 ? n / 4096 : 1;
         const int per = ((n + chunks - 1) / chunks + 127) / 128 * 128;
+        ctx->hm_per = per; ctx->hm_chunks = (n + per - 1) / per;
         for (int c = 0, lo = 0; lo < n; ++c, lo += per) {
             const int cnt = (lo + per <= n) ? per : n - lo;
             rc = launch_range(ctx, ctx->d_action, ctx->step_out, side, 0, s_obs, 0, c, lo, cnt, nullptr, false);
@@ -2012,6 +2152,12 @@ static int enqueue_host_step(hope_ctx *ctx, const double *h_action, const hope_h
             cudaEvent_t ev = ctx->ev_chunk[c % hope_ctx::MAX_CHUNK_EVENTS];
             CK(cudaEventRecord(ev, s_obs));
             CK(cudaStreamWaitEvent(s_copy, ev, 0));
+            if (ctx->expanding) {  // the step counts first, so the host can start expanding this range right away
+                CK(cudaMemcpyAsync(ctx->h_mask_steps + (size_t)lo * NACT, ctx->stage_out.mask_steps + (size_t)lo * NACT, (size_t)cnt * NACT,
+                                   cudaMemcpyDeviceToHost, s_copy));
+                CK(cudaMemcpyAsync(const_cast<unsigned long long *>(ctx->h_seq) + c % hope_ctx::MAX_CHUNK_EVENTS, ctx->d_seq, sizeof(unsigned long long),
+                                   cudaMemcpyDeviceToHost, s_copy));
+            }
             rc = copy_fields(ctx, h_out, 1, s_copy, lo, cnt);
             if (rc) return rc;
         }
@@ -2050,6 +2196,8 @@ int hope_step_host(hope_ctx *ctx, const double *h_action, const hope_host_out *h
         if (!same) {
             if (ctx->host_graph) { cudaGraphExecDestroy(ctx->host_graph); ctx->host_graph = nullptr; }
             plan_zero_copy(ctx, h_out);
+            rc = plan_mask_expand(ctx, h_out, stages);
+            if (rc) return rc;
             const unsigned long long before = ctx->launches;
             cudaGraph_t g = nullptr;
             CK(cudaStreamBeginCapture(s0, cudaStreamCaptureModeThreadLocal));
@@ -2069,15 +2217,15 @@ int hope_step_host(hope_ctx *ctx, const double *h_action, const hope_host_out *h
         if (ctx->host_graph) {
             CK(cudaGraphLaunch(ctx->host_graph, s0));
             ctx->launches += ctx->hg_launches;
-            CK(cudaStreamSynchronize(s0));
-            return HOPE_OK;
+            return finish_host_step(ctx, h_out, s0);
         }
     }
     plan_zero_copy(ctx, h_out);
+    rc = plan_mask_expand(ctx, h_out, stages);
+    if (rc) return rc;
     rc = enqueue_host_step(ctx, h_action, h_out, stages);
     if (rc) return rc;
-    CK(cudaStreamSynchronize(s0));
-    return HOPE_OK;
+    return finish_host_step(ctx, h_out, s0);
 }
 
 int hope_reset_host(hope_ctx *ctx, const int32_t *h_scene_ids, const hope_host_out *h_out) {
