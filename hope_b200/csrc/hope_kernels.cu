@@ -1422,7 +1422,8 @@ struct hope_ctx {
     // host API pipelines env ranges over all lanes so one range's D2H copies hide under the next one's kernels.
     static constexpr int MAX_LANES = 4;
     struct Lane { cudaStream_t main = nullptr, aux = nullptr; cudaEvent_t ev_advanced = nullptr, ev_observed = nullptr; } lanes[MAX_LANES];
-    int host_chunks = 3;   // measured on B200 at 65 536 envs: 2 -> 2.60 ms, 3 -> 2.53, 4 -> 2.63, 6 -> 2.97, 8 -> 3.30 per host step
+    int host_chunks = 2;   // measured on B200 at 65 536 envs with the narrow mask format: 2 -> 2.18 ms, 3 -> 2.21, 4 -> 2.35 per
+                           // host step (with the float64 mask copied: 2 -> 2.60, 3 -> 2.53, 4 -> 2.63, 8 -> 3.30)
     bool host_rs_after_observe = true;
     bool in_host_step = false;
     bool render_after_rs = false;
