@@ -2179,6 +2179,12 @@ static int enqueue_host_step(hope_ctx *ctx, const double *h_action, const hope_h
     return HOPE_OK;
 }
 
+int hope_expand_mask(const uint8_t *h_steps, double *h_mask, int n) {
+    if (!h_steps || !h_mask || n < 0) return HOPE_ERR_INVALID;
+    expand_mask_range(h_steps, h_mask, 0, (size_t)n);
+    return HOPE_OK;
+}
+
 int hope_step_host(hope_ctx *ctx, const double *h_action, const hope_host_out *h_out, unsigned stages) {
     if (!ctx || !h_action || !h_out) return HOPE_ERR_INVALID;
     if (!ctx->have_tables) return HOPE_ERR_NO_TABLES;

@@ -174,6 +174,11 @@ int hope_step_kinematics_collision(hope_ctx *ctx, const double *d_action, double
 int hope_step_host(hope_ctx *ctx, const double *h_action, const hope_host_out *h_out, unsigned stages);
 int hope_reset_host(hope_ctx *ctx, const int32_t *h_scene_ids, const hope_host_out *h_out);
 
+/* Host-side half of the narrow wire format of hope_step_host: the float64 action mask of n envs from their uint8
+ * step counts, exactly as action_mask.py:182-183 / k_observe compute it (steps / 10, or 0.01 for all 42 actions of an
+ * env whose counts are all 0).  HOST pointers h_steps[n][42], h_mask[n][42]; pure host code, no CUDA call. */
+int hope_expand_mask(const uint8_t *h_steps, double *h_mask, int n);
+
 /* Batched RsPlanner + ParkingAgent hand-off (model/agent/parking_agent.py:2-47, 64-70, 93-110;
  * train_HOPE_sac.py:194-213).  Call once per rollout step BEFORE hope_step, with the outputs of the
  * previous step: an env whose last step ended (done / was_reset) drops its plan; an env without a plan

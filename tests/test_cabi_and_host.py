@@ -129,3 +129,20 @@ def test_product_never_imports_the_oracle():
     code = "import sys; import hope_b200, hope_b200.batched_env, hope_b200.tables; print(any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules))"
     out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, check=True).stdout.strip()
     assert out == "False"
+
+
+def test_host_mask_expansion_equals_the_reference_formula():
+    """hope_step_host ships the action mask as uint8 step counts and rebuilds the float64 mask on the host
+    (hope_expand_mask); action_mask.py:182-183: steps / 10, or 0.01 everywhere when the env has no free step."""
+    from hope_b200 import capi
+    lib = capi.load_library()
+    rng = np.random.default_rng(3)
+    steps = rng.integers(0, 11, size=(4096, 42), dtype=np.uint8)
+    steps[::7] = 0                      # blocked envs: every action has 0 free steps
+    steps[1::7, :] = np.minimum(steps[1::7, :], 1)
+    mask = np.full((4096, 42), -1.0)
+    capi.check(lib.hope_expand_mask(steps.ctypes.data, mask.ctypes.data, 4096))
+    want = steps.astype(np.float64) / 10
+    want[steps.sum(axis=1) == 0] = 0.01
+    assert np.array_equal(mask, want)
+    assert lib.hope_expand_mask(None, mask.ctypes.data, 1) == -1

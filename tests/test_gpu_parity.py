@@ -196,8 +196,9 @@ def test_full_step_mixed_levels_vs_oracle():
 
 @pytest.mark.parametrize("n", [512, 20000])
 def test_host_buffer_api_matches_device_api(n):
-    """hope_step_host pipelines env ranges over several stream pairs (4 ranges at n = 20 000); the result must be
-    the same arrays the one-launch device path produces."""
+    """hope_step_host steps k_observe env range by env range (2 ranges at n = 20 000), copies each range behind it and
+    rebuilds the float64 mask from its step counts on the host; the result must be the same arrays the one-launch
+    device path produces."""
     sc = generate_scenes(n, "Complex", 3)
     a = BatchedParkingEnv(n, scenes=sc, auto_reset=True)
     b = BatchedParkingEnv(n, scenes=sc, auto_reset=True)
