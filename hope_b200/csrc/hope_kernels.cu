@@ -1444,7 +1444,8 @@ struct hope_ctx {
     volatile unsigned long long *h_seq = nullptr;  // pinned [MAX_CHUNK_EVENTS]
     int host_debug = 0;  // HOPE_B200_HOST_DEBUG: 1 = enqueue no copies, 2 = enqueue no kernels (timing experiments only)
     static constexpr int MAX_CHUNK_EVENTS = 64;
-    cudaEvent_t ev_chunk[MAX_CHUNK_EVENTS] = {};
+    cudaEvent_t ev_chunk[MAX_CHUNK_EVENTS] = {}, ev_adv[MAX_CHUNK_EVENTS] = {};
+    bool host_split_advance = true;
     int device_chunks = 1;  // hope_step: env ranges stepped on separate lanes so one range's latency-bound kernels
                             // (advance, enumerate, walk) run under another range's issue-bound ones (observe, check)
     // hope_step_host replays a captured CUDA graph of the whole pipelined step while the caller keeps passing the
@@ -1796,6 +1797,8 @@ int hope_create(hope_ctx **out, int device, int n_envs, int pool_size, const hop
     CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     for (int li = 0; li < hope_ctx::MAX_LANES; ++li) CK(cudaEventCreateWithFlags(&ctx->ev_join[li], cudaEventDisableTiming));
     for (auto &e : ctx->ev_chunk) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto &e : ctx->ev_adv) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    if (const char *e = getenv("HOPE_B200_HOST_SPLIT_ADVANCE")) ctx->host_split_advance = atoi(e) != 0;
     memset(&ctx->hg_out, 0, sizeof(ctx->hg_out));
     if (const char *e = getenv("HOPE_B200_HOST_GRAPH")) ctx->host_graph_enabled = atoi(e) != 0;
     if (const char *e = getenv("HOPE_B200_ZERO_COPY")) ctx->zero_copy_enabled = atoi(e) != 0;
@@ -1839,6 +1842,7 @@ int hope_destroy(hope_ctx *ctx) {
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     for (auto e : ctx->ev_join) if (e) cudaEventDestroy(e);
     for (auto e : ctx->ev_chunk) if (e) cudaEventDestroy(e);
+    for (auto e : ctx->ev_adv) if (e) cudaEventDestroy(e);
     if (ctx->h_mask_steps) cudaFreeHost(ctx->h_mask_steps);
     if (ctx->h_seq) cudaFreeHost(const_cast<unsigned long long *>(ctx->h_seq));
     if (ctx->d_seq) cudaFree(ctx->d_seq);
@@ -2134,19 +2138,31 @@ static int enqueue_host_step(hope_ctx *ctx, const double *h_action, const hope_h
     cudaStream_t s0 = ctx->lanes[0].main, s_obs = ctx->lanes[0].aux, s_copy = ctx->lanes[1].main;
     CK(cudaMemcpyAsync(ctx->d_action, h_action, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, s0));
     if (ctx->expanding) { k_bump_seq<<<1, 1, 0, s0>>>(ctx->d_seq); ctx->launches++; }
-    int rc = launch_range(ctx, ctx->d_action, ctx->step_out, HOPE_STAGE_ADVANCE, 0, s0, 0, 0, 0, n);
-    if (rc) return rc;
+    int rc;
+    int chunks = ctx->host_chunks;
+    if (n < 4096 * chunks) chunks = n / 4096 > 0 ? n / 4096 : 1;
+    const int per = ((n + chunks - 1) / chunks + 127) / 128 * 128;
+    const bool split_advance = side && ctx->host_split_advance;  // k_advance per range too: the first range's k_observe starts earlier
+    if (!split_advance) {
+        rc = launch_range(ctx, ctx->d_action, ctx->step_out, HOPE_STAGE_ADVANCE, 0, s0, 0, 0, 0, n);
+        if (rc) return rc;
+    }
     int last_chunk = 0;
     if (side) {
-        CK(cudaEventRecord(ctx->ev_fork, s0));
-        CK(cudaStreamWaitEvent(s_obs, ctx->ev_fork, 0));
-        CK(cudaStreamWaitEvent(s_copy, ctx->ev_fork, 0));
-        int chunks = ctx->host_chunks;
-        if (n < 4096 * chunks) chunks = n / 4096 > 0 ? n / 4096 : 1;
-        const int per = ((n + chunks - 1) / chunks + 127) / 128 * 128;
+        if (!split_advance) {
+            CK(cudaEventRecord(ctx->ev_fork, s0));
+            CK(cudaStreamWaitEvent(s_obs, ctx->ev_fork, 0));
+        }
         ctx->hm_per = per; ctx->hm_chunks = (n + per - 1) / per;
         for (int c = 0, lo = 0; lo < n; ++c, lo += per) {
             const int cnt = (lo + per <= n) ? per : n - lo;
+            if (split_advance) {
+                rc = launch_range(ctx, ctx->d_action, ctx->step_out, HOPE_STAGE_ADVANCE, 0, s0, 0, c, lo, cnt);
+                if (rc) return rc;
+                cudaEvent_t ea = ctx->ev_adv[c % hope_ctx::MAX_CHUNK_EVENTS];
+                CK(cudaEventRecord(ea, s0));
+                CK(cudaStreamWaitEvent(s_obs, ea, 0));
+            }
             rc = launch_range(ctx, ctx->d_action, ctx->step_out, side, 0, s_obs, 0, c, lo, cnt, nullptr, false);
             if (rc) return rc;
             last_chunk = c;
