@@ -101,6 +101,6 @@ def check(rc, ctx=None):
         return
     lib = load_library()
     msg = lib.hope_strerror(rc).decode()
-    if ctx is not None and rc == -2:
+    if ctx is not None and rc in (-2, -5) and lib.hope_last_cuda_error(ctx):
         msg += ": " + lib.hope_last_cuda_error(ctx).decode()
     raise HopeError(f"hope_b200 error {rc}: {msg}")

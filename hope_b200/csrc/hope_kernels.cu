@@ -1678,7 +1678,7 @@ int ensure_stage(hope_ctx *ctx, bool want_img) {
 
 extern "C" {
 
-int hope_version(void) { return 100; }
+int hope_version(void) { return 110; }  // 110: hope_out.img, HOPE_STAGE_IMAGE, hope_set_palette, hope_expand_mask
 int hope_max_obs(void) { return HOPE_MAX_OBS; }
 
 int hope_default_params(hope_params *p) {
@@ -1705,7 +1705,7 @@ const char *hope_strerror(int status) {
     case HOPE_ERR_CUDA: return "CUDA runtime error (see hope_last_cuda_error)";
     case HOPE_ERR_NO_TABLES: return "tables not uploaded (hope_upload_tables)";
     case HOPE_ERR_NO_SCENES: return "scene pool empty or envs not reset (hope_set_scene_pool / hope_reset)";
-    case HOPE_ERR_CAPACITY: return "scene exceeds HOPE_MAX_OBS / HOPE_MAX_VERTS";
+    case HOPE_ERR_CAPACITY: return "capacity exceeded: a scene's HOPE_MAX_OBS / HOPE_MAX_VERTS, or the image stage's span table (hope_last_cuda_error)";
     default: return "unknown status";
     }
 }

@@ -42,7 +42,8 @@ typedef enum {
     HOPE_ERR_CUDA = -2,        /* a CUDA runtime call failed (hope_last_cuda_error) */
     HOPE_ERR_NO_TABLES = -3,   /* hope_upload_tables not called yet */
     HOPE_ERR_NO_SCENES = -4,   /* hope_set_scene_pool / hope_reset not called yet */
-    HOPE_ERR_CAPACITY = -5     /* scene exceeds HOPE_MAX_OBS / HOPE_MAX_VERTS */
+    HOPE_ERR_CAPACITY = -5     /* scene exceeds HOPE_MAX_OBS / HOPE_MAX_VERTS, or the vehicle box is too large for the
+                                  image stage's per-box span table */
 } hope_status;
 
 /* vehicle.py:13-18 */

@@ -181,3 +181,22 @@ def test_full_size_65536_images_placement_invariance_and_oracle_subset():
     ids = list(range(0, period, 16))
     assert np.array_equal(_np(img[-1])[ids], _oracle_images(base, book, ids))
     env.close()
+
+
+def test_palette_override_and_capacity_guard():
+    """hope_set_palette replaces configs.py's colours (painter's order); a vehicle box too large for k_render's
+    per-box span table is refused instead of rendered wrongly."""
+    n = 16
+    sc = generate_scenes(n, "Normal", 12)
+    env = BatchedParkingEnv(n, scenes=sc, auto_reset=False, use_img_observation=True)
+    pal = np.full((capi.N_COLOR, 3), 50, dtype=np.uint8)
+    pal[0] = (255, 255, 255)  # background stays white -> black
+    env.set_palette(pal)
+    img = _np(env.reset()["img"])
+    assert img.max() == 50 and set(np.unique(img)) <= {0, 13, 25, 38, 50}   # (k * 50 + 2) >> 2 for k covered samples of 4
+    env.close()
+    big = BatchedParkingEnv(n, scenes=sc, auto_reset=False, use_img_observation=True,
+                            params={"box_x": (-3.0, 9.0, 9.0, -3.0)})
+    with pytest.raises(capi.HopeError, match="(?i)capacity|span table|exceeds"):
+        big.reset()
+    big.close()
