@@ -279,6 +279,8 @@ static_assert(MAXO != 16 || sizeof(Smem) <= 44400, "5 CTAs per SM (227 KB, 1 KB 
 
 }  // namespace render
 
+#ifndef HOPE_RENDER_HOST_TEST  // tests/render_host_harness.cpp compiles the scan-conversion helpers above with g++
+
 // One thread per env: the camera of this step (see Camera).
 __global__ void __launch_bounds__(128) k_render_camera(int n, Pool pool, EnvState st, hope_params par, render::Camera *__restrict__ cams) {
     using namespace render;
@@ -567,3 +569,5 @@ k_render(int n, Pool pool, EnvState st, const render::Camera *__restrict__ cams,
         __syncthreads();  // the window is cleared and repainted for the next quadrant
     }
 }
+
+#endif  // HOPE_RENDER_HOST_TEST
