@@ -75,13 +75,7 @@ struct EnvState {
     double *traj;     // [N][20][4] ring buffer (x, y, cos h, sin h): tail of Vehicle.trajectory (vehicle.py:121-157), read by k_render
     int *traj_n;      // [N] len(Vehicle.trajectory); entry j of the list lives in slot j % 20
 };
-struct RsWord {  // one admitted word, lengths in curvature-normalised units
-    double len[HOPE_RS_MAX_SEG];
-    double L;        // sum |len|, normalised
-    uint8_t types[HOPE_RS_MAX_SEG];
-    uint8_t n;
-    uint8_t pad[2];
-};
+struct RsWord;   // rs_words.cuh
 struct WordSlot;
 struct RsScratch {
     RsWord *words;       // [N][MAXW] in try order
@@ -668,129 +662,14 @@ __global__ void __launch_bounds__(64) k_rs_enumerate(int n, Pool pool, EnvState 
 // checked independently (under random actions 93 % of searches fail, i.e. every word is needed
 // anyway); k_rs_select then takes the first clean one.
 // =============================================================================================
-constexpr int RS_STRIDE = 8;                    // samples per lane in one chunk
-constexpr int RS_CHUNK = 32 * RS_STRIDE;        // samples covered by one set of saved states
-constexpr uint8_t RS_ORIGIN = 0xFE, RS_END = 0x80, RS_DONE = 0xFF;
-
-struct __align__(16) WordSlot {                 // 560 bytes, the sampling plan of one tried word
-    double len[HOPE_RS_MAX_SEG];                // normalised signed segment lengths
-    double org[HOPE_RS_MAX_SEG][5];             // per segment: ox, oy, oyaw, cos(oyaw), sin(oyaw) (local frame)
-    double st_pd[32];                           // saved walker state at sample RS_STRIDE*j of the chunk
-    double end_lx;                              // local x of the final end point (trailing-zero rule)
-    double resume_pd;                           // walker state at the start of the next chunk
-    uint8_t st_code[32];
-    uint32_t types;                             // 4 bits per segment
-    int n;                                      // segments
-    int total;                                  // samples in the word if the walk reached the end, else -1
-    uint8_t resume_code, pad[3];
-};
-static_assert(sizeof(WordSlot) % 16 == 0, "WordSlot is staged with 16-byte asynchronous copies");
-
-// One step of generate_local_course's sample sequence (:452-507).  (code, pd) is the sample just
-// emitted; on return it is the next one.  code: RS_ORIGIN = path start, seg index = loop sample of
-// that segment at arc parameter pd, RS_END|seg = the final end point, RS_DONE = no more samples.
-__device__ __forceinline__ void walker_next(const double *len, int nseg, double step, uint8_t &code, double &pd) {
-    int seg;
-    double d;
-    if (code == RS_ORIGIN) {
-        seg = 0;
-        d = len[0] > 0.0 ? step : -step;
-        pd = d - 0.0;                                   // pd = d - ll with ll = 0.0 (:471-472, :486)
-    } else if (code & RS_END) {
-        code = RS_DONE;
-        return;
-    } else {
-        seg = code;
-        d = len[seg] > 0.0 ? step : -step;
-        pd += d;                                        // :492
-    }
-    for (;;) {
-        double l = len[seg];
-        if (fabs(pd) <= fabs(l)) { code = (uint8_t)seg; return; }   // :488
-        if (seg + 1 == nseg) { code = (uint8_t)(RS_END | seg); pd = l; return; }  // :496-498
-        double ll = l - pd - d;                         // :494
-        double ln = len[seg + 1];
-        d = ln > 0.0 ? step : -step;                    // :475-478
-        pd = (l * ln > 0) ? -d - ll : d - ll;           // :483-486
-        ++seg;
-    }
-}
-
-// interpolate (:510-537) from a segment origin; returns the local-frame pose of the sample.
-__device__ __forceinline__ void rs_interp(double p, int m, double maxc, const double *org, double &lx, double &ly, double &lyaw) {
-    if (m == HOPE_RS_S) {
-        lx = org[0] + p / maxc * org[3];
-        ly = org[1] + p / maxc * org[4];
-        lyaw = org[2];
-    } else {
-        double sl, cl;
-        sincos(p, &sl, &cl);
-        double ldx = sl / maxc, ldy = (1.0 - cl) / (m == HOPE_RS_L ? maxc : -maxc);
-        double cy_ = org[3], sy_ = -org[4];             // cos(-oyaw), sin(-oyaw)
-        double gdx = cy_ * ldx + sy_ * ldy, gdy = -sy_ * ldx + cy_ * ldy;
-        lx = org[0] + gdx; ly = org[1] + gdy;
-        lyaw = (m == HOPE_RS_L) ? org[2] + p : org[2] - p;
-    }
-}
-
-// Replay up to RS_CHUNK samples of a word's chain from its resume state, saving a state every
-// RS_STRIDE.  Inside a segment the step is the bare `pd += d; |pd| <= |l|` of the reference;
-// everything else (origin, segment changes, end point) goes through walker_next.
-__device__ void walk_chunk(WordSlot &s, const double *len, double step, int chunk_base) {
-    uint8_t code = s.resume_code;
-    double pd = s.resume_pd;
-    const int nseg = s.n;
-    int k = 0, cur = -1;
-    double d = 0.0, al = 0.0;
-    if (code < HOPE_RS_MAX_SEG) { cur = code; const double l = len[code]; al = fabs(l); d = l > 0.0 ? step : -step; }
-    while (k < RS_CHUNK && code != RS_DONE) {
-        s.st_code[k / RS_STRIDE] = code; s.st_pd[k / RS_STRIDE] = pd;
-        int i = 0;
-        while (i < RS_STRIDE && code != RS_DONE) {
-            if (code == cur) {
-                while (i < RS_STRIDE) {
-                    const double nx = pd + d;           // reeds_shepp.py:492
-                    if (!(fabs(nx) <= al)) break;       // :488
-                    pd = nx; ++i;
-                }
-                if (i == RS_STRIDE) break;
-            }
-            walker_next(len, nseg, step, code, pd);
-            ++i;
-            if (code < HOPE_RS_MAX_SEG) { cur = code; const double l = len[code]; al = fabs(l); d = l > 0.0 ? step : -step; }
-            else cur = -1;
-        }
-        k += i;
-    }
-    for (int j = (k + RS_STRIDE - 1) / RS_STRIDE; j < 32; ++j) s.st_code[j] = RS_DONE;
-    s.resume_code = code; s.resume_pd = pd;
-    s.total = (code == RS_DONE) ? chunk_base + k : -1;
-}
+#include "rs_walk.cuh"
 
 __global__ void __launch_bounds__(128) k_rs_walk(RsScratch rs, Tables tb, hope_params par) {
     const int n_items = *rs.n_items;
     const double maxc = tb.maxc, step = par.rs_step * maxc;
     for (int item = blockIdx.x * blockDim.x + threadIdx.x; item < n_items; item += gridDim.x * blockDim.x) {
         const int code = rs.items[item], env = code >> 4, slot = code & 15;
-        const RsWord w = rs.words[(size_t)env * MAXW + slot];
-        WordSlot &s = rs.slots[item];
-        double len[HOPE_RS_MAX_SEG];
-        uint32_t ty = 0;
-#pragma unroll
-        for (int k = 0; k < HOPE_RS_MAX_SEG; ++k) { len[k] = w.len[k]; s.len[k] = w.len[k]; ty |= (uint32_t)(w.types[k] & 0xF) << (4 * k); }
-        s.types = ty; s.n = w.n;
-        double org[5] = {0.0, 0.0, 0.0, 1.0, 0.0};
-        for (int k = 0; k < w.n; ++k) {
-#pragma unroll
-            for (int q = 0; q < 5; ++q) s.org[k][q] = org[q];
-            double ex, ey, eyaw;
-            rs_interp(len[k], (int)((ty >> (4 * k)) & 0xF), maxc, org, ex, ey, eyaw);  // end of segment k = origin of k+1
-            org[0] = ex; org[1] = ey;
-            if (eyaw != org[2]) { org[2] = eyaw; sincos(eyaw, &org[4], &org[3]); }
-        }
-        s.end_lx = org[0];
-        s.resume_code = RS_ORIGIN; s.resume_pd = 0.0;
-        walk_chunk(s, len, step, 0);
+        plan_word(rs.slots[item], rs.words[(size_t)env * MAXW + slot], maxc, step);
     }
 }
 
@@ -804,8 +683,8 @@ struct CheckEnv {
 // (with `early`) stops at the first obstacle for which some lane reports a hit, since one bad sample condemns the word.
 // `mine` is set for the lanes that hit (only consulted by the degenerate trailing-zero rule).
 __device__ __forceinline__ bool warp_samples_hit(const CheckEnv &E, const hope_params &par, bool valid, bool early, double lx, double ly, double lyaw, bool &mine) {
-    double gx = E.cg * lx + E.sg * ly + E.q0x, gy = -E.sg * lx + E.cg * ly + E.q0y;  // reeds_shepp.py:47-48
-    double gyaw = pi_2_pi(lyaw + E.q0h);                                             // :49
+    double gx, gy, gyaw;
+    sample_to_global(lx, ly, lyaw, E.cg, E.sg, E.q0x, E.q0y, E.q0h, gx, gy, gyaw);
     mine = valid && (gx < E.xmin || gx > E.xmax || gy < E.ymin || gy > E.ymax);      // car_parking_base.py:462-464
     if (early && __any_sync(HOPE_FULL_MASK, mine)) return true;
     double cth, sth, bx[4], by[4];

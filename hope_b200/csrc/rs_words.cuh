@@ -4,6 +4,14 @@
 // reference's known answers through it; included by hope_kernels.cu inside namespace hope.
 #pragma once
 
+struct RsWord {  // one admitted word, lengths in curvature-normalised units
+    double len[HOPE_RS_MAX_SEG];
+    double L;        // sum |len|, normalised
+    uint8_t types[HOPE_RS_MAX_SEG];
+    uint8_t n;
+    uint8_t pad[2];
+};
+
 #ifndef HOPE_CONSTANT
 #define HOPE_CONSTANT __constant__
 #endif
