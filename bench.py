@@ -51,7 +51,7 @@ def hbm_peak():
     if os.path.exists(peaks_path):
         return json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
-CPU_SAMPLE_ENVS, CPU_SAMPLE_STEPS = 4096, 8
+CPU_SAMPLE_ENVS, CPU_SAMPLE_STEPS = 4096, 128  # ~12 s of CPU work on the GPU box (16 host threads)
 
 
 def scene_seed(rank):
