@@ -88,6 +88,21 @@ struct RsScratch {
     int *n_items;        // [1]   items of this step (reset by the host before k_rs_enumerate)
 };
 
+// k_rs_check, obstacle tests of a round: 0 = the warp votes "any sample hit?" after each obstacle, 1 = after each obstacle
+// edge (warp-uniform edge loop).  Same verdicts either way: one bad sample condemns the word.
+#ifndef HOPE_CHK_EDGE_EXIT
+#define HOPE_CHK_EDGE_EXIT 0
+#endif
+
+// Work counters of an instrumented build (-DHOPE_STATS, profiles/tools/kernel_stats.py): where k_rs_check's rounds end
+// and how many (quadrant, edge) / (ray, action) items k_observe visits.  The default build contains none of this.
+#ifdef HOPE_STATS
+__device__ unsigned long long g_stats[64];
+#define HOPE_STAT(i, v) atomicAdd(&g_stats[i], (unsigned long long)(v))
+#else
+#define HOPE_STAT(i, v) ((void)0)
+#endif
+
 __device__ __forceinline__ double4 ld_aabb(const double4 *p) {  // read-only path, two 128-bit loads
     const double2 *q = reinterpret_cast<const double2 *>(p);
     double2 lo = __ldg(q), hi = __ldg(q + 1);
@@ -428,8 +443,14 @@ __global__ void __launch_bounds__(64) k_observe(int n, Pool pool, EnvState st, T
             cnt += __popc(m);
         }
         if (lane == 0) sm.qcount[q] = (uint16_t)cnt;
+#ifdef HOPE_STATS
+        if (lane == 0) HOPE_STAT(41, cnt);
+#endif
     }
     __syncwarp();
+#ifdef HOPE_STATS
+    if (lane == 0) { HOPE_STAT(40, 1); HOPE_STAT(42, n_edges); }
+#endif
 
     // ---- raycast: quadrant q handles rays 30q .. 30q+29, one per lane ---------------------------
     const int per_quad = NRAY / 4;
@@ -482,6 +503,9 @@ __global__ void __launch_bounds__(64) k_observe(int n, Pool pool, EnvState st, T
             on = m * (1.0 - 1e-15) < __ldg(tb.gpmax + q);
         }
         gmask[w] = __ballot_sync(HOPE_FULL_MASK, on);
+#ifdef HOPE_STATS
+        if (lane == 0) HOPE_STAT(43, __popc(gmask[w]));
+#endif
     }
     // Screen 2, per upsampled ray of an active beam (three beams = 30 lanes per pass): d_rho < pmax[rho]
 #pragma unroll
@@ -498,6 +522,9 @@ __global__ void __launch_bounds__(64) k_observe(int n, Pool pool, EnvState st, T
             const int qn = (qd + 1 == NRAY) ? 0 : qd + 1;
             const double d = in ? sm.L[qd] * tb.w_lo[r] + sm.L[qn] * tb.w_hi[r] : 0.0;  // action_mask.py:158-162
             unsigned act = __ballot_sync(HOPE_FULL_MASK, in && d < __ldg(tb.pmax + rho));
+#ifdef HOPE_STATS
+            if (lane == 0) { HOPE_STAT(44, __popc(act)); HOPE_STAT(46, 1); }
+#endif
             while (act) {
                 const int bsel = __ffs(act) - 1;
                 act &= act - 1;
@@ -509,6 +536,9 @@ __global__ void __launch_bounds__(64) k_observe(int n, Pool pool, EnvState st, T
                 const bool need0 = s0 > 0 && db < __ldg(P + (s0 - 1) * NACT + lane);
                 const bool need1 = has2 && s1 > 0 && db < __ldg(P + (s1 - 1) * NACT + 32 + lane);
                 if (!__any_sync(HOPE_FULL_MASK, need0 || need1)) continue;
+#ifdef HOPE_STATS
+                if (lane == 0) HOPE_STAT(45, 1);
+#endif
                 // every lane fetches the 10 running maxima of its action(s) in one batch of independent, coalesced,
                 // unconditional loads (row k is 42 contiguous doubles; lanes without a second action re-read column
                 // 32), then takes the first exceedance; rows at or above the current bound cannot lower it
@@ -686,6 +716,9 @@ __device__ __forceinline__ bool warp_samples_hit(const CheckEnv &E, const hope_p
     double gx, gy, gyaw;
     sample_to_global(lx, ly, lyaw, E.cg, E.sg, E.q0x, E.q0y, E.q0h, gx, gy, gyaw);
     mine = valid && (gx < E.xmin || gx > E.xmax || gy < E.ymin || gy > E.ymax);      // car_parking_base.py:462-464
+#ifdef HOPE_STATS
+    if (early && __any_sync(HOPE_FULL_MASK, mine)) { if ((threadIdx.x & 31) == 0) HOPE_STAT(14, 1); return true; }
+#endif
     if (early && __any_sync(HOPE_FULL_MASK, mine)) return true;
     double cth, sth, bx[4], by[4];
     sincos(gyaw, &sth, &cth);
@@ -696,8 +729,53 @@ __device__ __forceinline__ bool warp_samples_hit(const CheckEnv &E, const hope_p
     }
     const double vxmin = dmin(dmin(bx[0], bx[1]), dmin(bx[2], bx[3])), vxmax = dmax(dmax(bx[0], bx[1]), dmax(bx[2], bx[3]));
     const double vymin = dmin(dmin(by[0], by[1]), dmin(by[2], by[3])), vymax = dmax(dmax(by[0], by[1]), dmax(by[2], by[3]));
+#if HOPE_CHK_EDGE_EXIT
     for (int ob = 0; ob < E.nobs; ++ob) {  // same trip count in every lane
         double4 bb = ld_aabb(E.aabb + ob);
+        // disjoint boxes cannot produce a hit (:518-526), so this reject is exact
+        const bool enter = valid && !mine && !(vxmax < bb.x || bb.y < vxmin || vymax < bb.z || bb.w < vymin);
+        if (!__any_sync(HOPE_FULL_MASK, enter)) continue;
+        // The edge loop is warp-uniform (every lane looks at the same obstacle, so nv is the same) and the warp votes
+        // after EACH obstacle edge: one bad sample condemns the word, and 95 % of the tried words are condemned in
+        // their first round (profiles/r01_kernel_stats_w.json), so most of the remaining edge tests are never needed.
+        const int nv = E.nvp[ob];
+        double2 p1 = __ldg(E.verts + ob * MAXV);
+        for (int j = 0; j < nv; ++j) {
+            double2 p2 = __ldg(E.verts + ob * MAXV + ((j + 1 == nv) ? 0 : j + 1));
+            if (enter && !mine &&
+                !((p1.x < vxmin && p2.x < vxmin) || (p1.x > vxmax && p2.x > vxmax) ||
+                  (p1.y < vymin && p2.y < vymin) || (p1.y > vymax && p2.y > vymax))) {
+                const double oxmax = dmax(p1.x, p2.x), oxmin = dmin(p1.x, p2.x), oymax = dmax(p1.y, p2.y), oymin = dmin(p1.y, p2.y);
+                const double dd = p2.y - p1.y, ee = p1.x - p2.x, ff = p1.y * p2.x - p1.x * p2.y;  // :504-506
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int q2 = (q + 1) & 3;
+                    const double vx1 = bx[q], vy1 = by[q], vx2 = bx[q2], vy2 = by[q2];
+                    if ((vx1 < oxmin && vx2 < oxmin) || (vx1 > oxmax && vx2 > oxmax) ||
+                        (vy1 < oymin && vy2 < oymin) || (vy1 > oymax && vy2 > oymax)) continue;
+                    const double a = vy2 - vy1, b = vx1 - vx2, c = vy1 * vx2 - vx1 * vy2;  // :477-479
+                    const double det = a * ee - b * dd;                                    // :509
+                    if (det == 0.0) continue;
+                    double rx, ry;
+                    div_pair(b * ff - c * ee, c * dd - a * ff, det, rx, ry);               // :512-513
+                    const bool okx = !(rx > oxmax) && !(rx < oxmin) && !(rx > dmax(vx1, vx2)) && !(rx < dmin(vx1, vx2));
+                    const bool oky = !(ry > oymax) && !(ry < oymin) && !(ry > dmax(vy1, vy2)) && !(ry < dmin(vy1, vy2));
+                    if (okx && oky) mine = true;
+                }
+            }
+            if (early && __any_sync(HOPE_FULL_MASK, mine)) return true;
+            p1 = p2;
+        }
+    }
+#else
+    for (int ob = 0; ob < E.nobs; ++ob) {  // same trip count in every lane
+        double4 bb = ld_aabb(E.aabb + ob);
+#ifdef HOPE_STATS
+        {
+            const unsigned mm = __ballot_sync(HOPE_FULL_MASK, valid && !mine && !(vxmax < bb.x || bb.y < vxmin || vymax < bb.z || bb.w < vymin));
+            if ((threadIdx.x & 31) == 0) { HOPE_STAT(32, 1); HOPE_STAT(33, __popc(mm)); if (mm) HOPE_STAT(34, 1); }
+        }
+#endif
         // a hit needs rx inside both segments' x-ranges and ry inside both y-ranges (:518-526): disjoint
         // boxes cannot produce one, so these rejects are exact
         if (valid && !mine && !(vxmax < bb.x || bb.y < vxmin || vymax < bb.z || bb.w < vymin)) {
@@ -729,8 +807,15 @@ __device__ __forceinline__ bool warp_samples_hit(const CheckEnv &E, const hope_p
                 p1 = p2;
             }
         }
+#ifdef HOPE_STATS
+        if (early && __any_sync(HOPE_FULL_MASK, mine)) {
+            if ((threadIdx.x & 31) == 0) { HOPE_STAT(15, 1); HOPE_STAT(16 + (ob < 15 ? ob : 15), 1); }
+            return true;
+        }
+#endif
         if (early && __any_sync(HOPE_FULL_MASK, mine)) return true;
     }
+#endif
     return __any_sync(HOPE_FULL_MASK, mine);
 }
 
@@ -746,6 +831,12 @@ __device__ bool chunk_is_bad(const WordSlot &s, const CheckEnv &E, const hope_pa
     for (int r = 0; r < RS_STRIDE; ++r) {
         const bool valid = code != RS_DONE;
         if (!__any_sync(HOPE_FULL_MASK, valid)) break;
+#ifdef HOPE_STATS
+        {
+            const unsigned vm = __ballot_sync(HOPE_FULL_MASK, valid);
+            if (lane == 0) { HOPE_STAT(12, __popc(vm)); HOPE_STAT(13, 1); }
+        }
+#endif
         double lx = 0.0, ly = 0.0, lyaw = 0.0;
         if (valid && code != RS_ORIGIN) {
             const int sgi = code & 0x7F;
@@ -753,6 +844,9 @@ __device__ bool chunk_is_bad(const WordSlot &s, const CheckEnv &E, const hope_pa
         }
         bool mine;
         const bool any_hit = warp_samples_hit(E, par, valid, !zero_tail, lx, ly, lyaw, mine);
+#ifdef HOPE_STATS
+        if (!zero_tail && any_hit && lane == 0) HOPE_STAT(2 + (r < 8 ? r : 7), 1);
+#endif
         if (!zero_tail) { if (any_hit) return true; }
         else if (valid) {  // degenerate goal: a hit on an x == 0.0 sample only counts if a later sample has x != 0.0
             if (lx != 0.0) { nonzero_bits |= 1u << r; }
@@ -827,6 +921,9 @@ __global__ void __launch_bounds__(CHK_WARPS * 32, HOPE_CHK_MINBLOCKS) k_rs_check
             __syncwarp();
         }
         if (lane == 0) rs.item_bad[item] = bad ? 1 : 0;
+#ifdef HOPE_STATS
+        if (lane == 0) { HOPE_STAT(0, 1); if (bad) HOPE_STAT(1, 1); if (chunk_base) HOPE_STAT(10, 1); if (s.total >= 0) { HOPE_STAT(11, s.total); HOPE_STAT(35, 1); } }
+#endif
         __syncwarp();
     }
 }
@@ -2032,5 +2129,17 @@ int hope_get_counters(hope_ctx *ctx, uint64_t h_counters[8]) {
     h_counters[5] = ctx->launches;
     return HOPE_OK;
 }
+
+#ifdef HOPE_STATS
+// instrumented builds only (not declared in include/hope_b200.h): read and optionally clear the work counters
+int hope_debug_stats(uint64_t h_stats[64], int reset) {
+    unsigned long long tmp[64];
+    if (cudaDeviceSynchronize() != cudaSuccess) return HOPE_ERR_CUDA;
+    if (cudaMemcpyFromSymbol(tmp, hope::g_stats, sizeof(tmp)) != cudaSuccess) return HOPE_ERR_CUDA;
+    if (h_stats) for (int k = 0; k < 64; ++k) h_stats[k] = tmp[k];
+    if (reset) { memset(tmp, 0, sizeof(tmp)); if (cudaMemcpyToSymbol(hope::g_stats, tmp, sizeof(tmp)) != cudaSuccess) return HOPE_ERR_CUDA; }
+    return HOPE_OK;
+}
+#endif
 
 }  // extern "C"
