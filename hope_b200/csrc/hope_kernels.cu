@@ -91,7 +91,7 @@ struct RsScratch {
 // k_rs_check, obstacle tests of a round: 0 = the warp votes "any sample hit?" after each obstacle, 1 = after each obstacle
 // edge (warp-uniform edge loop).  Same verdicts either way: one bad sample condemns the word.
 #ifndef HOPE_CHK_EDGE_EXIT
-#define HOPE_CHK_EDGE_EXIT 0
+#define HOPE_CHK_EDGE_EXIT 1
 #endif
 
 // Work counters of an instrumented build (-DHOPE_STATS, profiles/tools/kernel_stats.py): where k_rs_check's rounds end
