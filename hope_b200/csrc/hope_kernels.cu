@@ -696,6 +696,13 @@ __global__ void __launch_bounds__(128) k_rs_walk(RsScratch rs, Tables tb, hope_p
 }
 
 #include "rs_check.cuh"
+// 1 = k_rs_check gives every warp two work items, one per half-warp (rs_check_pair.cuh; experimental, not yet measured)
+#ifndef HOPE_CHK_PAIR
+#define HOPE_CHK_PAIR 0
+#endif
+#if HOPE_CHK_PAIR
+#include "rs_check_pair.cuh"
+#endif
 
 #ifndef HOPE_CHK_WARPS
 #define HOPE_CHK_WARPS 4
@@ -713,6 +720,76 @@ __device__ __forceinline__ void stage_slot_async(WordSlot *dst, const WordSlot *
     __pipeline_commit();
 }
 
+#if HOPE_CHK_PAIR
+__device__ __forceinline__ CheckEnv load_check_env(int env, const Pool &pool, const EnvState &st, const Tables &tb, const hope_params &par) {
+    const int sid = st.scene[env];
+    const double *meta = pool.meta + (size_t)sid * META;
+    CheckEnv E;
+    E.q0x = st.pose[3 * env]; E.q0y = st.pose[3 * env + 1]; E.q0h = st.pose[3 * env + 2];
+    E.cg = st.cs[2 * env]; E.sg = -st.cs[2 * env + 1];  // cos(-h), sin(-h)  (reeds_shepp.py:47-48)
+    E.xmin = meta[M_BOUNDS]; E.xmax = meta[M_BOUNDS + 1]; E.ymin = meta[M_BOUNDS + 2]; E.ymax = meta[M_BOUNDS + 3];
+    E.maxc = tb.maxc; E.step = par.rs_step * tb.maxc;
+    E.nobs = pool.nobs[sid];
+    E.aabb = reinterpret_cast<const double4 *>(pool.aabb) + (size_t)sid * MAXO;
+    E.verts = reinterpret_cast<const double2 *>(pool.obs) + (size_t)sid * MAXE;
+    E.nvp = pool.nv + (size_t)sid * MAXO;
+    return E;
+}
+
+// asynchronous global -> shared copy of one WordSlot by a half-warp (16 bytes per lane per pass)
+__device__ __forceinline__ void stage_slot_async_half(WordSlot *dst, const WordSlot *src, int hl) {
+    const char *g = reinterpret_cast<const char *>(src);
+    char *sh = reinterpret_cast<char *>(dst);
+    for (int q = hl * 16; q < (int)sizeof(WordSlot); q += 16 * 16) __pipeline_memcpy_async(sh + q, g + q, 16);
+    __pipeline_commit();
+}
+
+// Two work items per warp: lanes 0-15 check item 2g, lanes 16-31 item 2g + 1 (rs_check_pair.cuh).
+__global__ void __launch_bounds__(CHK_WARPS * 32, HOPE_CHK_MINBLOCKS) k_rs_check(Pool pool, EnvState st, Tables tb, RsScratch rs, hope_params par) {
+    __shared__ WordSlot smem[CHK_WARPS][2][2];  // [buffer][half]; the next pair's plans stream in while this pair is sampled
+    const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
+    const int n_items = *rs.n_items, n_pairs = (n_items + 1) >> 1;
+    const int warps_total = gridDim.x * CHK_WARPS;
+    int pair = blockIdx.x * CHK_WARPS + warp_in_block, buf = 0;
+    // a half without an item (odd n_items, last pair) stages and reads the other half's item and reports nothing
+    if (pair < n_pairs) stage_slot_async_half(&smem[warp_in_block][0][half], rs.slots + min(2 * pair + half, n_items - 1), hl);
+    for (; pair < n_pairs; pair += warps_total, buf ^= 1) {
+        const int item = 2 * pair + half;
+        const bool have = item < n_items;
+        const int src = have ? item : n_items - 1;
+        const int next = pair + warps_total;
+        if (next < n_pairs) stage_slot_async_half(&smem[warp_in_block][buf ^ 1][half], rs.slots + min(2 * next + half, n_items - 1), hl);
+        const CheckEnv E = load_check_env(rs.items[src] >> 4, pool, st, tb, par);
+        if (next < n_pairs) __pipeline_wait_prior(1); else __pipeline_wait_prior(0);  // this pair's plans have landed
+        __syncwarp();
+        WordSlot &s = smem[warp_in_block][buf][half];
+        bool bad = false;
+        if (!__any_sync(HOPE_FULL_MASK, have && s.end_lx == 0.0)) {
+            bad = pair_is_bad(s, E, par, lane, have);
+        } else {  // a degenerate trailing-zero word in the pair (reeds_shepp.py:501-505): one word at a time, whole warp
+            for (int h = 0; h < 2; ++h) {
+                const int it = 2 * pair + h;
+                if (it >= n_items) break;
+                const CheckEnv Eh = load_check_env(rs.items[it] >> 4, pool, st, tb, par);
+                WordSlot &sh = smem[warp_in_block][buf][h];
+                bool b = false;
+                int chunk_base = 0;
+                for (;;) {
+                    b = chunk_is_bad(sh, Eh, par, lane);
+                    if (b || sh.total >= 0) break;
+                    chunk_base += RS_CHUNK;
+                    __syncwarp();
+                    if (lane == 0) walk_chunk(sh, sh.len, Eh.step, chunk_base);
+                    __syncwarp();
+                }
+                if (h == half) bad = b;
+            }
+        }
+        if (have && hl == 0) rs.item_bad[item] = bad ? 1 : 0;
+        __syncwarp();
+    }
+}
+#else
 __global__ void __launch_bounds__(CHK_WARPS * 32, HOPE_CHK_MINBLOCKS) k_rs_check(Pool pool, EnvState st, Tables tb, RsScratch rs, hope_params par) {
     __shared__ WordSlot smem[CHK_WARPS][2];  // double buffer: the next word's plan streams in while this one is sampled
     const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -755,6 +832,7 @@ __global__ void __launch_bounds__(CHK_WARPS * 32, HOPE_CHK_MINBLOCKS) k_rs_check
         __syncwarp();
     }
 }
+#endif  // HOPE_CHK_PAIR
 
 __global__ void __launch_bounds__(128) k_rs_select(int n, Tables tb, RsScratch rs, hope_out out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

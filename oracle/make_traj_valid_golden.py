@@ -67,6 +67,50 @@ def record(mods, level, n_episodes, seed, follow_rs, max_steps=120):
     return scenes, calls
 
 
+def record_far(mods, level, n_scenes, seed, poses_per_scene=6):
+    """Words longer than one 256-sample chunk: `find_rs_path` called directly (the 10 m gate of car_parking_base.py:293-294
+    sits outside it) from poses 15-40 m away from the slot, with the map bounds widened so that not every word leaves
+    the map.  Same spies as above; the scene recorded is the one with the widened bounds."""
+    cpb, wrap, vehicle, rs, pmn, configs = mods
+    raw = cpb.CarParking(render_mode="rgb_array", fps=100, verbose=False,
+                         use_lidar_observation=True, use_img_observation=False, use_action_mask=True)
+    env = wrap.CarParkingWrapper(raw)
+    state = {"paths": [], "calls": []}
+    orig_all, orig_valid = rs.calc_all_paths, raw.is_traj_valid
+
+    def all_spy(*a, **k):
+        r = orig_all(*a, **k)
+        state["paths"] = r
+        return r
+
+    def valid_spy(traj):
+        verdict = orig_valid(traj)
+        xs = [t[0] for t in traj]
+        which = [i for i, p in enumerate(state["paths"]) if len(p.x) == len(xs) and list(p.x) == xs]
+        st = raw.vehicle.state
+        state["calls"].append((st.loc.x, st.loc.y, st.heading, which[0] if len(which) == 1 else -1, len(traj), bool(verdict)))
+        return verdict
+
+    rs.calc_all_paths, raw.is_traj_valid = all_spy, valid_spy
+    scenes, calls = [], []
+    rng = np.random.default_rng(seed)
+    for k in range(n_scenes):
+        np.random.seed(seed + k)
+        env.reset(None, None, level)
+        m = raw.map
+        m.xmin -= 45.0; m.xmax += 45.0; m.ymin -= 45.0; m.ymax += 45.0
+        scenes.append(mg.scene_arrays(m))
+        dx, dy, _ = m.dest.get_pos()
+        for _ in range(poses_per_scene):
+            r, th = rng.uniform(15.0, 40.0), rng.uniform(-np.pi, np.pi)
+            raw.vehicle.state = vehicle.State([dx + r * np.cos(th), dy + r * np.sin(th), rng.uniform(-np.pi, np.pi), 0.0, 0.0])
+            state["calls"] = []
+            raw.find_rs_path(None)
+            calls.extend((len(scenes) - 1,) + c for c in state["calls"])
+    rs.calc_all_paths, raw.is_traj_valid = orig_all, orig_valid
+    return scenes, calls
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
@@ -87,6 +131,13 @@ def main():
     print("kept", len(calls), "of", len(all_calls))
     # keep every valid (True) verdict and a strided subset of the invalid ones
     keep = [c for c in calls if c[-1]] + [c for c in calls if not c[-1]][::3]
+    for li, level in enumerate(("Normal", "Complex")):  # long words from far poses, all kept
+        scenes, calls = record_far(mods, level, 12, 9000 + 100 * li)
+        base = len(all_scenes)
+        all_scenes.extend(scenes)
+        far = [(c[0] + base,) + c[1:] for c in calls if c[4] >= 0]
+        keep.extend(far)
+        print(level, "far", len(far), "calls,", sum(c[-1] for c in far), "valid, longest", max(c[5] for c in far), flush=True)
     keep.sort(key=lambda c: c[0])
     np.savez_compressed(
         out,

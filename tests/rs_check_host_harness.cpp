@@ -46,72 +46,126 @@ static inline double4 ld_aabb(const double4 *p) { return *p; }  // the kernel's 
 #include "../hope_b200/csrc/rs_words.cuh"
 #include "../hope_b200/csrc/rs_walk.cuh"
 #include "../hope_b200/csrc/rs_check.cuh"
+#include "../hope_b200/csrc/rs_check_pair.cuh"
 }  // namespace hope
 
+// One tried word ready for the check: its sampling plan (k_rs_walk's output) and the check environment k_rs_check builds.
+struct Prepared {
+    hope::WordSlot s;
+    hope::CheckEnv E;
+    double4 aabb[hope::MAXO];
+    double2 verts[hope::MAXO * hope::MAXV];
+    uint8_t nvs[hope::MAXO];
+};
+
 // q = (start x, y, heading, goal x, y, heading); word = index in the product's enumeration order (== the reference's
-// calc_all_paths order).  obs[nobs][4][2], nv[nobs].  Returns 1 = the word leaves the map or touches an obstacle,
-// 0 = clean, < 0 = error (-1 bad word index, -2 convergence error of the warp, -3 lanes disagree).
-extern "C" int rs_check_host(const double *q, double maxc, double rs_step, int word, const double *bounds, int nobs, const double *obs,
-                             const uint8_t *nv, const double *box_x, const double *box_y, int force_zero_tail, int *n_samples,
-                             unsigned long long *n_collectives) {
+// calc_all_paths order).  obs[nobs][4][2], nv[nobs].
+static int prepare(Prepared &P, const double *q, double maxc, double rs_step, int word, const double *bounds, int nobs, const double *obs,
+                   const uint8_t *nv, int force_zero_tail) {
     using namespace hope;
     WordList w;
     enumerate_words(q[0], q[1], q[2], q[3], q[4], q[5], maxc, w, nullptr);
-    if (word < 0 || word >= w.count) return -1;
+    if (word < 0 || word >= w.count || nobs > MAXO) return -1;
     RsWord rw;
     std::memset(&rw, 0, sizeof(rw));
     for (int i = 0; i < 5; ++i) { rw.len[i] = w.len[word][i]; rw.types[i] = (uint8_t)((w.ty[word] >> (4 * i)) & 0xF); }
     rw.L = w.L[word]; rw.n = w.n[word];
-    static WordSlot s;
-    plan_word(s, rw, maxc, rs_step * maxc);
-    if (force_zero_tail) s.end_lx = 0.0;
-
-    hope_params par;
-    std::memset(&par, 0, sizeof(par));
-    for (int k = 0; k < 4; ++k) { par.box_x[k] = box_x[k]; par.box_y[k] = box_y[k]; }
-    par.rs_step = rs_step;
-
-    static double4 aabb[MAXO];
-    static double2 verts[MAXO * MAXV];
-    static uint8_t nvs[MAXO];
-    if (nobs > MAXO) return -1;
+    plan_word(P.s, rw, maxc, rs_step * maxc);
+    if (force_zero_tail) P.s.end_lx = 0.0;
+    std::memset(P.aabb, 0, sizeof(P.aabb)); std::memset(P.verts, 0, sizeof(P.verts)); std::memset(P.nvs, 0, sizeof(P.nvs));
     for (int o = 0; o < nobs; ++o) {  // per-ring bounding boxes as hope_set_scene_pool stores them (xmin xmax ymin ymax)
         double xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
-        nvs[o] = nv[o];
+        P.nvs[o] = nv[o];
         for (int v = 0; v < MAXV; ++v) {
             const double x = obs[(o * MAXV + v) * 2], y = obs[(o * MAXV + v) * 2 + 1];
-            verts[o * MAXV + v] = make_double2(x, y);
+            P.verts[o * MAXV + v] = make_double2(x, y);
             if (v < nv[o]) { xmin = fmin(xmin, x); xmax = fmax(xmax, x); ymin = fmin(ymin, y); ymax = fmax(ymax, y); }
         }
-        aabb[o] = make_double4(xmin, xmax, ymin, ymax);
+        P.aabb[o] = make_double4(xmin, xmax, ymin, ymax);
     }
     double sh, ch;
     sincos(q[2], &sh, &ch);  // k_advance hands cos / sin of the heading to the check (EnvState::cs)
-    CheckEnv E;
+    CheckEnv &E = P.E;
     E.q0x = q[0]; E.q0y = q[1]; E.q0h = q[2];
     E.cg = ch; E.sg = -sh;
     E.xmin = bounds[0]; E.xmax = bounds[1]; E.ymin = bounds[2]; E.ymax = bounds[3];
     E.maxc = maxc; E.step = rs_step * maxc;
-    E.nobs = nobs; E.aabb = aabb; E.verts = verts; E.nvp = nvs;
+    E.nobs = nobs; E.aabb = P.aabb; E.verts = P.verts; E.nvp = P.nvs;
+    return 0;
+}
 
+static hope_params make_params(const double *box_x, const double *box_y, double rs_step) {
+    hope_params par;
+    std::memset(&par, 0, sizeof(par));
+    for (int k = 0; k < 4; ++k) { par.box_x[k] = box_x[k]; par.box_y[k] = box_y[k]; }
+    par.rs_step = rs_step;
+    return par;
+}
+
+static const char *report(const char *err) {
+    if (err && getenv("WARP_EMU_VERBOSE")) fprintf(stderr, "warp_emu: %s\n", err);
+    return err;
+}
+
+// the word loop body of k_rs_check on one word, one fiber per lane
+static int whole_warp_verdict(Prepared &P, const hope_params &par, unsigned long long *n_collectives) {
+    using namespace hope;
     int verdict[32];
-    // the word loop body of k_rs_check, one fiber per lane
     const char *err = warp_emu::run([&](int lane) {
         bool bad = false;
         int chunk_base = 0;
         for (;;) {
-            bad = chunk_is_bad(s, E, par, lane);
-            if (bad || s.total >= 0) break;
+            bad = chunk_is_bad(P.s, P.E, par, lane);
+            if (bad || P.s.total >= 0) break;
             chunk_base += RS_CHUNK;
             __syncwarp();
-            if (lane == 0) walk_chunk(s, s.len, E.step, chunk_base);
+            if (lane == 0) walk_chunk(P.s, P.s.len, P.E.step, chunk_base);
             __syncwarp();
         }
         verdict[lane] = bad ? 1 : 0;
     }, n_collectives);
-    if (err) { if (getenv("WARP_EMU_VERBOSE")) fprintf(stderr, "warp_emu: %s\n", err); return -2; }
+    if (report(err)) return -2;
     for (int l = 1; l < 32; ++l)
         if (verdict[l] != verdict[0]) return -3;
-    if (n_samples) *n_samples = s.total;
     return verdict[0];
+}
+
+// Returns 1 = the word leaves the map or touches an obstacle, 0 = clean, < 0 = error (-1 bad word index, -2 convergence
+// error of the warp, -3 lanes disagree).
+extern "C" int rs_check_host(const double *q, double maxc, double rs_step, int word, const double *bounds, int nobs, const double *obs,
+                             const uint8_t *nv, const double *box_x, const double *box_y, int force_zero_tail, int *n_samples,
+                             unsigned long long *n_collectives) {
+    static Prepared P;
+    if (prepare(P, q, maxc, rs_step, word, bounds, nobs, obs, nv, force_zero_tail)) return -1;
+    const hope_params par = make_params(box_x, box_y, rs_step);
+    const int v = whole_warp_verdict(P, par, n_collectives);
+    if (n_samples) *n_samples = P.s.total;
+    return v;
+}
+
+// Two words in one warp (rs_check_pair.cuh).  Arrays of two: q[2][6], word[2], bounds[2][4], nobs[2], obs[2][MAXO][4][2],
+// nv[2][MAXO]; have_second = 0 leaves the upper half without an item.  verdict[2] as above; returns 0 or the error.
+extern "C" int rs_check_pair_host(const double *q, double maxc, double rs_step, const int *word, const double *bounds, const int *nobs,
+                                  const double *obs, const uint8_t *nv, const double *box_x, const double *box_y, int have_second,
+                                  int *verdict, unsigned long long *n_collectives) {
+    using namespace hope;
+    static Prepared P[2];
+    const int stride_obs = MAXO * MAXV * 2;
+    for (int h = 0; h < (have_second ? 2 : 1); ++h)
+        if (prepare(P[h], q + 6 * h, maxc, rs_step, word[h], bounds + 4 * h, nobs[h], obs + (size_t)stride_obs * h, nv + MAXO * h, 0)) return -1;
+    const hope_params par = make_params(box_x, box_y, rs_step);
+    int lane_verdict[32];
+    const char *err = warp_emu::run([&](int lane) {
+        const int half = lane >> 4;
+        const bool have = half == 0 || have_second;
+        Prepared &mine = P[have ? half : 0];  // a half without an item reads the other half's slot, like the kernel
+        lane_verdict[lane] = pair_is_bad(mine.s, mine.E, par, lane, have) ? 1 : 0;
+    }, n_collectives);
+    if (report(err)) return -2;
+    for (int h = 0; h < 2; ++h) {
+        for (int l = 1; l < 16; ++l)
+            if (lane_verdict[16 * h + l] != lane_verdict[16 * h]) return -3;
+        verdict[h] = lane_verdict[16 * h];
+    }
+    return 0;
 }
