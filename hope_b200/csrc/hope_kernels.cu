@@ -31,62 +31,7 @@
 
 namespace hope {
 
-constexpr int MAXO = HOPE_MAX_OBS;
-constexpr int MAXV = HOPE_MAX_VERTS;
-constexpr int MAXE = MAXO * MAXV;  // 64 edges (512 in the obs128 build)
-static_assert(MAXO <= 256 && MAXE % 32 == 0, "obstacle indices are packed into 8 bits, edges staged 32 at a time");
-constexpr int NRAY = HOPE_N_LIDAR;
-constexpr int NACT = HOPE_N_ACTION;
-constexpr int NITER = HOPE_N_MASK_ITER;
-constexpr int NUP = HOPE_N_UPSAMPLE;
-constexpr int META = 24;       // doubles of per-scene metadata
-constexpr int MAXW = 16;       // admitted Reeds-Shepp words kept per env
-constexpr int ADV_THREADS = 64;
-
-// per-scene metadata layout (doubles)
-enum { M_START = 0, M_DEST = 3, M_BOUNDS = 6, M_DBX = 10, M_DBY = 14, M_DAREA = 18, M_DNORM = 19, M_DAABB = 20 };
-
-struct Pool {
-    const double *obs;    // [P][16][4][2]
-    const uint8_t *nv;    // [P][16]
-    const double *aabb;   // [P][16][4] xmin xmax ymin ymax
-    const double *meta;   // [P][24]
-    const int *nobs;      // [P]
-    int size;
-};
-struct Tables {
-    const double *ray_a, *ray_b, *lidar_base, *mask_base;
-    const double *dist_star;  // [1200][42][10]
-    const double *pmaxk;      // [1200][10][42] running max over k of dist_star, action index contiguous
-    const double *pmax;       // [1200]       max_{j,k} dist_star
-    const double *gpmax;      // [120]        max of pmax over the 10 upsampled rays of a beam
-    const double *w_lo, *w_hi;
-    double maxc;
-};
-struct EnvState {
-    double *pose;     // [N][3]
-    double *cs;       // [N][2] cos, sin of the heading (k_advance -> k_observe)
-    int *t;           // [N]
-    double *accum;    // [N]
-    int *scene;       // [N]
-    uint8_t *pending; // [N] finished last step, takes its next scene on this one
-    uint8_t *gate;    // [N] RS gate of this step
-    unsigned long long *counters;  // [8]
-    double *traj;     // [N][20][4] ring buffer (x, y, cos h, sin h): tail of Vehicle.trajectory (vehicle.py:121-157), read by k_render
-    int *traj_n;      // [N] len(Vehicle.trajectory); entry j of the list lives in slot j % 20
-};
-struct RsWord;   // rs_words.cuh
-struct WordSlot;
-struct RsScratch {
-    RsWord *words;       // [N][MAXW] in try order
-    uint8_t *ntry;       // [N]
-    uint8_t *ncand;      // [N]
-    int *item_base;      // [N]   first work item of env i (its ntry items are consecutive, in try order)
-    int *items;          // [N*MAXW] work item -> (env << 4) | try slot
-    uint8_t *item_bad;   // [N*MAXW] 1 = the word leaves the map or touches an obstacle
-    WordSlot *slots;     // [N*MAXW] per-item sampling plan written by k_rs_walk
-    int *n_items;        // [1]   items of this step (reset by the host before k_rs_enumerate)
-};
+#include "hope_types.cuh"
 
 // k_rs_check, obstacle tests of a round: 0 = the warp votes "any sample hit?" after each obstacle, 1 = after each obstacle
 // edge (warp-uniform edge loop).  Same verdicts either way: one bad sample condemns the word.
@@ -364,21 +309,7 @@ __global__ void __launch_bounds__(ADV_THREADS, MINB) k_advance(int n, Pool pool,
 // =============================================================================================
 // k_observe: one warp per env.  LiDAR raycast -> action-mask sweep -> target representation.
 // =============================================================================================
-struct ObserveSmem {
-    // per edge, packed for 128-bit broadcast loads in the ray loop: line coefficients d x + e y + f = 0 (ego frame)
-    // and the edge bounding box
-    double2 de[MAXE];      // d, e
-    double2 fxn[MAXE];     // f, xmin
-    double2 xym[MAXE];     // xmax, ymin
-    double eymax[MAXE];
-    double L[NRAY];                                              // clip(lidar)+mask_base
-    int steps[NACT + 2];
-    uint8_t quad[MAXE];                                          // which ray quadrants can accept this edge
-    uint16_t qlist[4][MAXE];                                     // per quadrant: the edges that can be hit from it
-    uint16_t qcount[4];
-};
-
-#include "div_pair.cuh"
+#include "observe.cuh"
 
 __global__ void __launch_bounds__(64) k_observe(int n, Pool pool, EnvState st, Tables tb, hope_params par, hope_out out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -386,202 +317,7 @@ __global__ void __launch_bounds__(64) k_observe(int n, Pool pool, EnvState st, T
     const int env = blockIdx.x * (blockDim.x >> 5) + warp_in_block;
     if (env >= n) return;
     ObserveSmem &sm = reinterpret_cast<ObserveSmem *>(smem_raw)[warp_in_block];
-    const int sid = st.scene[env];
-    const double x = st.pose[3 * env], y = st.pose[3 * env + 1];
-
-    // ---- stage obstacle vertices, rotate into the ego frame (lidar_simulator.py:55-72) -------------
-    const double a = st.cs[2 * env], b = st.cs[2 * env + 1];  // cos, sin of the heading (from k_advance)
-    const double xoff = -x * a - y * b, yoff = x * b - y * a, mb = -b;
-    const double2 *verts = reinterpret_cast<const double2 *>(pool.obs) + (size_t)sid * MAXE;
-    const uint8_t *nvp = pool.nv + (size_t)sid * MAXO;
-    int n_edges = 0;
-    const int n_slots = pool.nobs[sid] * MAXV;  // rings are compacted to the front of the scene block
-    for (int half = 0; half * 32 < n_slots; ++half) {
-        int slot = half * 32 + lane, k = slot >> 2, j = slot & 3;
-        int nv = nvp[k];
-        bool valid = j < nv;
-        double2 p = __ldg(verts + slot);                                       // coalesced 128-bit loads
-        double2 q = __ldg(verts + (k << 2) + ((j + 1 >= nv) ? 0 : j + 1));
-        unsigned m = __ballot_sync(HOPE_FULL_MASK, valid);
-        if (valid) {
-            int e = n_edges + __popc(m & ((1u << lane) - 1));
-            double x1 = a * p.x + b * p.y + xoff, y1 = mb * p.x + a * p.y + yoff;
-            double x2 = a * q.x + b * q.y + xoff, y2 = mb * q.x + a * q.y + yoff;
-            double exmin = dmin(x1, x2), exmax = dmax(x1, x2), eymin = dmin(y1, y2), eymax = dmax(y1, y2);
-            sm.de[e] = make_double2(y2 - y1, x1 - x2);                   // :104-106
-            sm.fxn[e] = make_double2(y1 * x2 - x1 * y2, exmin);
-            sm.xym[e] = make_double2(exmax, eymin); sm.eymax[e] = eymax;
-            // exact culls: a hit must lie inside the edge's bbox (:126-129), on the ray's side of the
-            // axes up to 1e-8 (:120-124), and nearer than lidar_range to survive the clip (:134)
-            bool xp = exmax >= -1e-8, xn = exmin <= 1e-8, yp = eymax >= -1e-8, yn = eymin <= 1e-8;
-            bool reach = !(exmin > par.lidar_range || exmax < -par.lidar_range || eymin > par.lidar_range || eymax < -par.lidar_range);
-            uint8_t qm = 0;
-            if (reach) qm = (uint8_t)((xp && yp ? 1 : 0) | (xn && yp ? 2 : 0) | (xn && yn ? 4 : 0) | (xp && yn ? 8 : 0));
-            sm.quad[e] = qm;
-        }
-        n_edges += __popc(m);
-    }
-    __syncwarp();
-    // per-quadrant edge lists, so the ray loop below only visits edges that can be hit from its quadrant
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        int cnt = 0;
-        for (int half = 0; half < MAXE / 32; ++half) {
-            const int e = half * 32 + lane;
-            if (half * 32 >= n_edges) break;
-            const bool on = e < n_edges && ((sm.quad[e] >> q) & 1);
-            const unsigned m = __ballot_sync(HOPE_FULL_MASK, on);
-            if (on) sm.qlist[q][cnt + __popc(m & ((1u << lane) - 1))] = (uint16_t)e;
-            cnt += __popc(m);
-        }
-        if (lane == 0) sm.qcount[q] = (uint16_t)cnt;
-#ifdef HOPE_STATS
-        if (lane == 0) HOPE_STAT(41, cnt);
-#endif
-    }
-    __syncwarp();
-#ifdef HOPE_STATS
-    if (lane == 0) { HOPE_STAT(40, 1); HOPE_STAT(42, n_edges); }
-#endif
-
-    // ---- raycast: quadrant q handles rays 30q .. 30q+29, one per lane ---------------------------
-    const int per_quad = NRAY / 4;
-#pragma unroll 1
-    for (int q = 0; q < 4; ++q) {
-        const int ray = q * per_quad + lane;
-        const bool live = lane < per_quad;
-        const double A = live ? tb.ray_a[ray] : 0.0, B = live ? tb.ray_b[ray] : -1.0;
-        // sign conventions of the quadrant (:120-124): reject rx < -1e-8 (sx=+1) or rx > 1e-8 (sx=-1), same for ry
-        const double sx = (q == 0 || q == 3) ? 1.0 : -1.0, sy = (q < 2) ? 1.0 : -1.0;
-        double best2 = INFINITY;  // min over edges of rx^2 + ry^2; sqrt is monotone, so one sqrt at the end is exact
-        const int qn_edges = sm.qcount[q];
-        for (int t = 0; t < qn_edges; ++t) {
-            const int e = sm.qlist[q][t];            // warp-uniform
-            const double2 de = sm.de[e], fxn = sm.fxn[e], xym = sm.xym[e];
-            const double d = de.x, ee = de.y, f = fxn.x;
-            const double det = A * ee - B * d;        // :109
-            if (det == 0.0) continue;                 // parallel -> 100 -> clipped away (:131)
-            double rx, ry;
-            div_pair(B * f, -(A * f), det, rx, ry);   // :112-113 with c = 0
-            const bool ok = !(sx * rx < -1e-8) && !(sy * ry < -1e-8) &&
-                            !(rx > xym.x) && !(rx < fxn.y) && !(ry > sm.eymax[e]) && !(ry < xym.y);  // :126-129
-            if (ok) best2 = dmin(best2, rx * rx + ry * ry);  // :133
-        }
-        if (live) {
-            double r = dmin(dmax(sqrt(best2), 0.0), par.lidar_range) - tb.lidar_base[ray];  // :133-134, :46
-            if (out.lidar) out.lidar[(size_t)env * NRAY + ray] = r;
-            sm.L[ray] = dmin(dmax(r, 0.0), 10.0) + tb.mask_base[ray];  // action_mask.py:170
-        }
-    }
-    __syncwarp();
-
-    // ---- action-mask sweep (action_mask.py:166-184) --------------------------------------------
-    // s_j = min over the 1200 upsampled rays of (first k with dist_star[rho][j][k] > d_rho).  With the
-    // running maximum P[rho][k][j] = max_{k'<=k} dist_star[rho][j][k'] (same first exceedance), a ray can
-    // lower any s_j only if d_rho < P[rho][9][.] somewhere, i.e. d_rho < pmax[rho].  All screens compare
-    // stored doubles exactly, so the integers equal the reference's full 1200x42x10 sweep.
-    int s0 = NITER, s1 = NITER;  // lane owns actions lane and lane+32
-    const bool has2 = lane < NACT - 32;
-    // Screen 1, per lidar beam q: the 10 upsampled rays 10q..10q+9 interpolate L[q] and L[q+1] with weights that
-    // sum to 1 within one rounding, so each d is >= min(L[q], L[q+1]) (1 - 5e-16).  If that minimum, shrunk by
-    // 1e-15, still reaches gpmax[q] = max of pmax over the group, none of the 10 rays can lower any action.
-    unsigned gmask[4];
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {
-        const int q = w * 32 + lane;
-        bool on = false;
-        if (q < NRAY) {
-            const double m = dmin(sm.L[q], sm.L[(q + 1 == NRAY) ? 0 : q + 1]);
-            on = m * (1.0 - 1e-15) < __ldg(tb.gpmax + q);
-        }
-        gmask[w] = __ballot_sync(HOPE_FULL_MASK, on);
-#ifdef HOPE_STATS
-        if (lane == 0) HOPE_STAT(43, __popc(gmask[w]));
-#endif
-    }
-    // Screen 2, per upsampled ray of an active beam (three beams = 30 lanes per pass): d_rho < pmax[rho]
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {
-        unsigned gm = gmask[w];
-        while (gm) {
-            int g[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) { g[c] = gm ? (w * 32 + __ffs(gm) - 1) : -1; gm &= gm - 1; }
-            const int sub = lane / 10, r = lane - sub * 10;
-            const int qd = sub < 3 ? g[sub] : -1;
-            const bool in = qd >= 0;
-            const int rho = in ? qd * 10 + r : 0;
-            const int qn = (qd + 1 == NRAY) ? 0 : qd + 1;
-            const double d = in ? sm.L[qd] * tb.w_lo[r] + sm.L[qn] * tb.w_hi[r] : 0.0;  // action_mask.py:158-162
-            unsigned act = __ballot_sync(HOPE_FULL_MASK, in && d < __ldg(tb.pmax + rho));
-#ifdef HOPE_STATS
-            if (lane == 0) { HOPE_STAT(44, __popc(act)); HOPE_STAT(46, 1); }
-#endif
-            while (act) {
-                const int bsel = __ffs(act) - 1;
-                act &= act - 1;
-                const double db = __shfl_sync(HOPE_FULL_MASK, d, bsel);
-                const int rb = __shfl_sync(HOPE_FULL_MASK, rho, bsel);
-                const double *P = tb.pmaxk + (size_t)rb * NITER * NACT;  // [k][j], j contiguous
-                // the running maximum is monotone in k, so this ray lowers action j below its current bound s only if
-                // d < P[s-1][j]: one load per action decides; most rays after the nearest obstacles lower nothing
-                const bool need0 = s0 > 0 && db < __ldg(P + (s0 - 1) * NACT + lane);
-                const bool need1 = has2 && s1 > 0 && db < __ldg(P + (s1 - 1) * NACT + 32 + lane);
-                if (!__any_sync(HOPE_FULL_MASK, need0 || need1)) continue;
-#ifdef HOPE_STATS
-                if (lane == 0) HOPE_STAT(45, 1);
-#endif
-                // every lane fetches the 10 running maxima of its action(s) in one batch of independent, coalesced,
-                // unconditional loads (row k is 42 contiguous doubles; lanes without a second action re-read column
-                // 32), then takes the first exceedance; rows at or above the current bound cannot lower it
-                const double *P0 = P + lane, *P1 = P + 32 + (has2 ? lane : 0);
-                double v0[NITER], v1[NITER];
-#pragma unroll
-                for (int k = 0; k < NITER; ++k) { v0[k] = __ldg(P0 + k * NACT); v1[k] = __ldg(P1 + k * NACT); }
-                int f0 = NITER, f1 = NITER;
-#pragma unroll
-                for (int k = NITER - 1; k >= 0; --k) {
-                    if (db < v0[k]) f0 = k;
-                    if (db < v1[k]) f1 = k;
-                }
-                s0 = min(s0, f0);
-                if (has2) s1 = min(s1, f1);
-            }
-        }
-    }
-    sm.steps[lane] = s0;
-    if (has2) sm.steps[32 + lane] = s1;
-    __syncwarp();
-    // post_process (action_mask.py:186-196): per half subtract 1 at both ends, 5-tap min, clip, /10
-    int mine[2] = {0, 0};
-    int total = 0;
-#pragma unroll
-    for (int rep = 0; rep < 2; ++rep) {
-        int j = rep * 32 + lane;
-        if (j < NACT) {
-            int half = j >= 21 ? 21 : 0, p = j - half, m = 1 << 30;
-#pragma unroll
-            for (int dt = -2; dt <= 2; ++dt) {
-                int u = p + dt;
-                if (u < 0 || u > 20) continue;  // 'reflect' border == truncated window for a min filter
-                int vv = sm.steps[half + u] - ((u == 0 || u == 20) ? 1 : 0);
-                m = min(m, vv);
-            }
-            m = max(0, min(m, NITER));
-            mine[rep] = m;
-            total += m;
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(HOPE_FULL_MASK, total, o);
-#pragma unroll
-    for (int rep = 0; rep < 2; ++rep) {
-        int j = rep * 32 + lane;
-        if (j < NACT) {
-            if (out.mask) out.mask[(size_t)env * NACT + j] = total == 0 ? 0.01 : (double)mine[rep] / 10;  // :182-183
-            if (out.mask_steps) out.mask_steps[(size_t)env * NACT + j] = (uint8_t)mine[rep];
-        }
-    }
+#include "observe_body.inc"
 }
 
 // =============================================================================================

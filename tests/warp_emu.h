@@ -124,7 +124,10 @@ inline double shfl_at(int line, unsigned, double v, int src) {
     std::memcpy(&v, &b, 8);
     return v;
 }
+inline int lane_id() { return current()->cur; }
+template <typename T> inline T shfl_xor_at(int line, unsigned m, T v, int lane_mask) { return shfl_at(line, m, v, lane_id() ^ lane_mask); }
 }  // namespace warp_emu
+#define __shfl_xor_sync(mask, v, lm) warp_emu::shfl_xor_at(__LINE__, mask, v, lm)
 #define __any_sync(mask, pred) warp_emu::any_at(__LINE__, mask, pred)
 #define __ballot_sync(mask, pred) warp_emu::ballot_at(__LINE__, mask, pred)
 #define __shfl_sync(mask, v, src) warp_emu::shfl_at(__LINE__, mask, v, src)
