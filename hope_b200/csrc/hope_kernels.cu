@@ -58,72 +58,7 @@ __device__ __forceinline__ double4 ld_aabb(const double4 *p) {  // read-only pat
 // k_advance: one thread per env for the sequential part (pose integration, status, reward); the
 // ring-vs-ring collision tests of a warp's 32 envs are pooled and spread over all 32 lanes.
 // =============================================================================================
-struct AdvanceSmem {           // per warp
-    double bx[32][4], by[32][4];   // current vehicle box of each lane's env
-    int sid[32];
-    uint16_t queue[32 * MAXO];     // (lane << 8) | obstacle of every vehicle-AABB / obstacle-AABB overlap
-};
-
-// Per-lane result: does lane's vehicle ring touch any obstacle ring of its scene
-// (car_parking_base.py:153-158)?  `check` selects the lanes that ask.  Phase 1: every asking lane
-// walks its obstacle AABBs (exact reject) and enqueues the overlaps.  Phase 2: the warp drains the
-// queue two items at a time, 16 lanes per item = 4 vehicle edges x up to 4 obstacle edges, one
-// robust segment-pair test per lane.
-__device__ __forceinline__ unsigned warp_collisions(bool check, const double *bx, const double *by, int sid, int nobs,
-                                                    const Pool &pool, AdvanceSmem &sm, int lane, unsigned long long *fc) {
-    if (!__any_sync(HOPE_FULL_MASK, check)) return 0u;
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { sm.bx[lane][i] = bx[i]; sm.by[lane][i] = by[i]; }
-    sm.sid[lane] = sid;
-    const double vxmin = dmin(dmin(bx[0], bx[1]), dmin(bx[2], bx[3])), vxmax = dmax(dmax(bx[0], bx[1]), dmax(bx[2], bx[3]));
-    const double vymin = dmin(dmin(by[0], by[1]), dmin(by[2], by[3])), vymax = dmax(dmax(by[0], by[1]), dmax(by[2], by[3]));
-    int maxn = check ? nobs : 0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) maxn = max(maxn, __shfl_xor_sync(HOPE_FULL_MASK, maxn, o));
-    const double4 *aabb = reinterpret_cast<const double4 *>(pool.aabb) + (size_t)sid * MAXO;
-    int qn = 0;
-    for (int k = 0; k < maxn; ++k) {
-        bool over = false;
-        if (check && k < nobs) {
-            double4 bb = ld_aabb(aabb + k);  // xmin xmax ymin ymax
-            over = !(vxmax < bb.x || bb.y < vxmin || vymax < bb.z || bb.w < vymin);  // disjoint boxes: exact reject
-        }
-        unsigned m = __ballot_sync(HOPE_FULL_MASK, over);
-        if (over) sm.queue[qn + __popc(m & ((1u << lane) - 1))] = (uint16_t)((lane << 8) | k);
-        qn += __popc(m);
-    }
-    __syncwarp();
-    unsigned collided = 0;
-    const int half = lane >> 4, pair = lane & 15, vi = pair & 3, oj = pair >> 2;
-    for (int base = 0; base < qn; base += 2) {
-        const int item = base + half;
-        bool hit = false;
-        if (item < qn) {
-            const int code = sm.queue[item], owner = code >> 8, k = code & 255;
-            if (!((collided >> owner) & 1)) {
-                const int osid = sm.sid[owner];
-                const int nv = pool.nv[(size_t)osid * MAXO + k];
-                if (oj < nv) {
-                    const double2 *v = reinterpret_cast<const double2 *>(pool.obs) + ((size_t)osid * MAXO + k) * MAXV;
-                    const double2 p = __ldg(v + oj), q = __ldg(v + ((oj + 1 == nv) ? 0 : oj + 1));
-                    const int vi2 = (vi + 1) & 3;
-                    hit = segments_touch(sm.bx[owner][vi], sm.by[owner][vi], sm.bx[owner][vi2], sm.by[owner][vi2], p.x, p.y, q.x, q.y, fc);
-                }
-            }
-        }
-        const unsigned m = __ballot_sync(HOPE_FULL_MASK, hit);
-        if (m & 0xffffu) collided |= 1u << (sm.queue[base] >> 8);
-        if ((m >> 16) && base + 1 < qn) collided |= 1u << (sm.queue[base + 1] >> 8);
-    }
-    __syncwarp();
-    return collided;
-}
-
-__device__ __forceinline__ double angle_gap(double a1, double a2) {  // car_parking_base.py:203-206
-    double d = acos(cos(a1 - a2));
-    return d < HOPE_PI / 2 ? d : HOPE_PI - d;
-}
+#include "advance.cuh"
 
 // MINB = resident 64-thread blocks per SM the register allocation is sized for.  168 registers (6 blocks) is the
 // unconstrained optimum, but 65 536 envs are 1.15 waves of that; capped at 128 registers (8 blocks, a few spills) the
@@ -136,174 +71,7 @@ __global__ void __launch_bounds__(ADV_THREADS, MINB) k_advance(int n, Pool pool,
     const int lane = threadIdx.x & 31;
     AdvanceSmem &sm = smem[threadIdx.x >> 5];
     const int gi = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = gi < n;
-    const int i = valid ? gi : n - 1;  // tail lanes shadow the last env (no stores) so warp collectives stay full
-    unsigned long long *fc = st.counters + 2;
-    int sid = st.scene[i];
-    const bool pending = st.pending[i] != 0;
-    const bool is_reset = reset_all || pending || action == nullptr;
-    if (pending && !reset_all) {  // auto-reset: next scene of the pool for this slot
-        sid = (sid + reset_stride) % pool.size;  // env slot i cycles through scenes i, i+N, i+2N, ... of the pool
-        if (valid) st.scene[i] = sid;
-    }
-    const double *meta = pool.meta + (size_t)sid * META;
-    const int nobs = pool.nobs[sid];
-    double x, y, h, accum;
-    int t;
-    if (reset_all || pending) {
-        x = meta[M_START]; y = meta[M_START + 1]; h = meta[M_START + 2];
-        accum = 0.0; t = 0;
-    } else {
-        x = st.pose[3 * i]; y = st.pose[3 * i + 1]; h = st.pose[3 * i + 2];
-        accum = st.accum[i]; t = st.t[i];
-    }
-    const double px0 = x, py0 = y, ph0 = h;
-    double dbx[4], dby[4], bx[4], by[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { dbx[k] = meta[M_DBX + k]; dby[k] = meta[M_DBY + k]; }
-    const double dest_area = meta[M_DAREA];
-    const double daxmin = meta[M_DAABB], daxmax = meta[M_DAABB + 1], daymin = meta[M_DAABB + 2], daymax = meta[M_DAABB + 3];
-    // centre of the vehicle box in its own frame (mean of the two diagonal corners)
-    const double ccx = 0.5 * (par.box_x[0] + par.box_x[2]), ccy = 0.5 * (par.box_y[0] + par.box_y[2]);
-
-    bool arrive = false;
-    int nsub = 0, nret = 0;
-    double c, s;
-    sincos(h, &s, &c);
-    double v = 0.0, dh = 0.0, ds = 0.0, ratio = 0.0;
-    const int mi = par.mini_iter;
-    bool moving = !is_reset;
-    if (moving) {
-        // env_wrapper.py:37-50: clip to [-1,1], a*(hi-lo)/2 + (hi+lo)/2 with float32-exact bounds
-        double a0 = dmin(dmax(action[2 * i], -1.0), 1.0), a1 = dmin(dmax(action[2 * i + 1], -1.0), 1.0);
-        double steer = a0 * ((par.valid_steer[1] - par.valid_steer[0]) / 2) + (par.valid_steer[1] + par.valid_steer[0]) / 2;
-        double speed = a1 * ((par.valid_speed[1] - par.valid_speed[0]) / 2) + (par.valid_speed[1] + par.valid_speed[0]) / 2;
-        // vehicle.py:83-84
-        v = dmin(dmax(speed, par.valid_speed[0]), par.valid_speed[1]);
-        double phi = dmin(dmax(steer, par.valid_steer[0]), par.valid_steer[1]);
-        // vehicle.py:88-93, one mini-iteration: x += v cos(h) dt ; h += v tan(phi)/L dt   (dt = step_length/mini_iter)
-        dh = v * tan(phi) / par.wheel_base * par.step_length / par.mini_iter;
-        ds = v * par.step_length / par.mini_iter;
-        // closed form of the mini_iter explicit-Euler position sum: with h_k = h + k dh,
-        //   sum_k cos(h_k) = sin(mi dh/2)/sin(dh/2) * cos(h + (mi-1) dh/2)
-        ratio = (dh == 0.0) ? (double)mi : sin(0.5 * mi * dh) / sin(0.5 * dh);
-    }
-    for (int sub = 0; sub < par.num_step; ++sub) {  // car_parking_base.py:259-271, lock-step across the warp
-        if (!__any_sync(HOPE_FULL_MASK, moving)) break;
-        double kx = x, ky = y, kh = h, kc = c, ks = s;
-        if (moving) {
-            double sm_, cm_;
-            sincos(h + 0.5 * (mi - 1) * dh, &sm_, &cm_);
-            x = x + ds * (ratio * cm_);
-            y = y + ds * (ratio * sm_);
-            for (int q = 0; q < mi; ++q) h += dh;  // heading accumulates by repeated addition in the reference
-            sincos(h, &s, &c);
-            ++nsub;
-            vehicle_box(x, y, c, s, par.box_x, par.box_y, bx, by);
-            // arrival (:164-170) needs 95 % of the slot covered; a convex, centrally symmetric box whose centre
-            // lies outside the slot covers at most half of it, so the centre-in-slot-AABB test (with slack) is a
-            // safe necessary condition before paying for the polygon clip
-            double cx = c * ccx - s * ccy + x, cy = s * ccx + c * ccy + y;
-            if (cx >= daxmin - 1e-6 && cx <= daxmax + 1e-6 && cy >= daymin - 1e-6 && cy <= daymax + 1e-6) {
-                if (quad_clip_area(bx, by, dbx, dby) / dest_area > 0.95) { arrive = true; moving = false; }
-            }
-        }
-        unsigned hitmask = warp_collisions(moving, bx, by, sid, nobs, pool, sm, lane, fc);
-        if (moving && ((hitmask >> lane) & 1)) {  // :264-271 retreat one substep
-            x = kx; y = ky; h = kh; c = kc; s = ks;
-            ++nret;
-            moving = false;
-        }
-    }
-    t += 1;
-    vehicle_box(x, y, c, s, par.box_x, par.box_y, bx, by);
-    double inter = 0.0;
-    {
-        double vxmin = dmin(dmin(bx[0], bx[1]), dmin(bx[2], bx[3])), vxmax = dmax(dmax(bx[0], bx[1]), dmax(bx[2], bx[3]));
-        double vymin = dmin(dmin(by[0], by[1]), dmin(by[2], by[3])), vymax = dmax(dmax(by[0], by[1]), dmax(by[2], by[3]));
-        if (!(vxmax < daxmin || daxmax < vxmin || vymax < daymin || daymax < vymin)) inter = quad_clip_area(bx, by, dbx, dby);
-    }
-    const double xmin = meta[M_BOUNDS], xmax = meta[M_BOUNDS + 1], ymin = meta[M_BOUNDS + 2], ymax = meta[M_BOUNDS + 3];
-    const unsigned final_hits = warp_collisions(!arrive, bx, by, sid, nobs, pool, sm, lane, fc);
-    int status;  // car_parking_base.py:279-282, 175-184
-    if (arrive) status = HOPE_ARRIVED;
-    else if ((final_hits >> lane) & 1) status = HOPE_COLLIDED;
-    else if (x > xmax || x < xmin || y > ymax || y < ymin) status = HOPE_OUTBOUND;
-    else if (inter / dest_area > 0.95) status = HOPE_ARRIVED;
-    else if (t > par.tolerant_time) status = HOPE_OUTTIME;
-    else status = HOPE_CONTINUE;
-
-    const double dx = meta[M_DEST], dy = meta[M_DEST + 1], dhd = meta[M_DEST + 2];
-    double ri[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-    const double dist_now = hypot(x - dx, y - dy);
-    if (status == HOPE_CONTINUE) {  // :186-227
-        ri[0] = -tanh((double)t / (10 * par.tolerant_time));
-        double dist_prev = hypot(px0 - dx, py0 - dy), norm = meta[M_DNORM];
-        ri[2] = dist_prev / norm - dist_now / norm;
-        ri[3] = angle_gap(ph0, dhd) / HOPE_PI - angle_gap(h, dhd) / HOPE_PI;
-        double u = inter / (2 * dest_area - inter);
-        if (u < accum) u = 0.0;
-        else { double p = accum; accum = u; u -= p; }
-        ri[4] = u;
-    }
-    double reward;  // env_wrapper.py:10-35
-    if (status == HOPE_CONTINUE) {
-        reward = 0.0;
-#pragma unroll
-        for (int k = 0; k < 5; ++k) reward += par.reward_weight[k] * ri[k];
-    } else if (status == HOPE_OUTTIME) reward = -1.0;
-    else if (status == HOPE_ARRIVED) reward = 50.0;
-    else reward = -50.0;
-    reward *= par.reward_ratio;
-
-    const bool done = status != HOPE_CONTINUE;
-    if (valid) {
-        st.pose[3 * i] = x; st.pose[3 * i + 1] = y; st.pose[3 * i + 2] = h;
-        st.cs[2 * i] = c; st.cs[2 * i + 1] = s;
-        st.accum[i] = accum; st.t[i] = t;
-        st.pending[i] = (done && par.auto_reset) ? 1 : 0;
-        st.gate[i] = (t > 1 && status == HOPE_CONTINUE && dist_now < par.rs_max_dist) ? 1 : 0;  // :293-294
-        // Vehicle.trajectory: reset -> [start]; a step keeps exactly one new state (car_parking_base.py:273-275
-        // prunes the substeps) unless the very first substep collided and was popped again (vehicle.py:157)
-        if (reset_all || pending) {
-            double2 *tj = reinterpret_cast<double2 *>(st.traj) + (size_t)i * 40;
-            tj[0] = make_double2(x, y); tj[1] = make_double2(c, s);
-            st.traj_n[i] = 1;
-        } else if (nsub - nret >= 1) {
-            const int tn = st.traj_n[i];
-            double2 *tj = reinterpret_cast<double2 *>(st.traj) + ((size_t)i * 20 + tn % 20) * 2;
-            tj[0] = make_double2(x, y); tj[1] = make_double2(c, s);
-            st.traj_n[i] = tn + 1;
-        }
-        if (out.pose) { out.pose[3 * i] = x; out.pose[3 * i + 1] = y; out.pose[3 * i + 2] = h; }
-        if (out.status) out.status[i] = status;
-        if (out.done) out.done[i] = done;
-        if (out.reward) out.reward[i] = reward;
-        if (out.reward_info) {
-#pragma unroll
-            for (int k = 0; k < 5; ++k) out.reward_info[5 * i + k] = ri[k];
-        }
-        if (out.substeps) out.substeps[i] = (uint8_t)nsub;
-        if (out.retreated) out.retreated[i] = (uint8_t)nret;
-        if (out.was_reset) out.was_reset[i] = is_reset;
-        if (out.target) {  // car_parking_base.py:372-381; element 4 repeats cos (sic)
-            double ddx = dx - x, ddy = dy - y;
-            double rel = atan2(ddy, ddx) - h, relh = dhd - h;
-            double *tg = out.target + (size_t)i * 5;
-            double sr, cr;
-            sincos(rel, &sr, &cr);
-            tg[0] = sqrt(ddx * ddx + ddy * ddy);
-            tg[1] = cr; tg[2] = sr;
-            tg[3] = cos(relh); tg[4] = tg[3];
-        }
-    }
-    // whole-warp tallies -> one atomic per warp
-    const unsigned m_act = __ballot_sync(HOPE_FULL_MASK, valid && !is_reset);
-    const unsigned m_rst = __ballot_sync(HOPE_FULL_MASK, valid && pending && !reset_all);
-    if (lane == 0) {
-        if (m_act) atomicAdd(st.counters + 0, (unsigned long long)__popc(m_act));
-        if (m_rst) atomicAdd(st.counters + 1, (unsigned long long)__popc(m_rst));
-    }
+#include "advance_body.inc"
 }
 
 // =============================================================================================
