@@ -78,3 +78,47 @@ def test_lidar_and_mask_equal_the_recorded_reference(harness, device_tables, gol
         assert np.array_equal(mask, np.full(42, 0.01)) if steps.sum() == 0 else np.array_equal(mask, steps / 10)
     assert mask_diff == 0, f"{mask_diff} of {n} action masks differ from the reference's"
     assert worst < 3e-11, worst
+
+
+def test_adversarial_scenes_against_the_oracle(harness, device_tables):
+    """The C oracle is pinned on the reference's traces; here it and the product's k_observe code (both on the host libm)
+    see scenes the generators never produce.  Mask step counts must be identical and the lidar bit-identical."""
+    from oracle import parking_oracle as po
+    from oracle.adversarial import adversarial_scenes
+    rng = np.random.default_rng(77)  # other scenes than the recorded ones (seed 2024)
+    n = 500
+    start, obs, nverts = adversarial_scenes(rng, n)
+    dest = start + np.array([5.0, 5.0, 0.0])
+    bounds = np.tile(np.array([-100.0, 100.0, -100.0, 100.0]), (n, 1))
+    ref = po.OracleEnv(start, dest, bounds, obs, nverts).reset_step()
+    lidar_diff, mask_diff, hits = 0, 0, 0
+    for i in range(n):
+        lidar, mask, steps = observe(harness, device_tables, start[i], obs[i], nverts[i])
+        lidar_diff += int(not np.array_equal(lidar, ref["lidar"][i]))
+        mask_diff += int(not np.array_equal(steps, ref["mask_steps"][i].astype(np.uint8)))
+        hits += int((lidar < lidar.max() - 1e-9).sum())
+    assert hits > 20 * n  # the scenes are in view
+    assert mask_diff == 0, f"{mask_diff} of {n} masks differ"
+    assert lidar_diff == 0, f"{lidar_diff} of {n} lidar vectors are not bit-identical"
+
+
+def test_adversarial_scenes_against_the_recorded_reference(harness, device_tables, golden_dir):
+    """The same kind of boundary-case scenes, observed by the unmodified reference's LidarSimlator / ActionMask
+    (oracle/make_adversarial_golden.py).  The product's k_observe code and the C oracle must both reproduce them."""
+    from oracle import parking_oracle as po
+    g = np.load(os.path.join(golden_dir, "adversarial_observe.npz"))
+    n = len(g["start"])
+    ref = po.OracleEnv(g["start"], g["start"] + np.array([5.0, 5.0, 0.0]), np.tile(np.array([-100.0, 100.0, -100.0, 100.0]), (n, 1)),
+                       g["obs"], g["nverts"]).reset_step()
+    worst_p, worst_o, mask_p, mask_o, exact = 0.0, 0.0, 0, 0, 0
+    for i in range(n):
+        lidar, mask, _ = observe(harness, device_tables, g["start"][i], g["obs"][i], g["nverts"][i])
+        worst_p = max(worst_p, float(np.abs(lidar - g["lidar"][i]).max()))
+        worst_o = max(worst_o, float(np.abs(ref["lidar"][i] - g["lidar"][i]).max()))
+        mask_p += int(not np.array_equal(mask, g["mask"][i]))
+        mask_o += int(not np.array_equal(ref["mask"][i], g["mask"][i]))
+        exact += int(np.array_equal(lidar, g["lidar"][i]))
+    print(f"\nadversarial scenes vs the reference: product lidar worst |diff| {worst_p:.3g} ({exact} of {n} bit-identical), "
+          f"oracle {worst_o:.3g}; masks differing: product {mask_p}, oracle {mask_o}")
+    assert mask_p == 0 and mask_o == 0
+    assert worst_p < 3e-11 and worst_o < 3e-11
