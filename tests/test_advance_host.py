@@ -28,7 +28,7 @@ def harness(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("advance") / "advance_host.so")
     env = dict(os.environ)
     env.pop("CC", None); env.pop("CXX", None)
-    subprocess.check_call([gxx, "-O1", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-I", os.path.join(HERE, "host_stubs"),
+    subprocess.check_call([gxx, "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-I", os.path.join(HERE, "host_stubs"),
                            "-o", out, os.path.join(HERE, "advance_host_harness.cpp")], env=env)
     lib = C.CDLL(out)
     lib.adv_create.argtypes = [C.c_int, C.c_void_p]
@@ -52,7 +52,7 @@ def test_recorded_episodes_free_running(harness, golden_dir):
     from hope_b200 import capi
     par = capi.Params()
     capi.check(capi.load_library().hope_default_params(C.byref(par)))  # host-only call
-    files = [np.load(os.path.join(golden_dir, f"{stem}_{lv}.npz")) for stem in ("episodes", "episodes_follow") for lv in LEVELS]
+    files = [dict(np.load(os.path.join(golden_dir, f"{stem}_{lv}.npz"))) for stem in ("episodes", "episodes_follow") for lv in LEVELS]
     eps = [(g, e) for g in files for e in range(len(g["scene_start"]))]   # one lane per recorded episode
     n = len(eps)
     assert 33 <= n <= 64  # two emulated warps, the second with shadow lanes at the tail

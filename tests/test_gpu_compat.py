@@ -56,7 +56,7 @@ def test_surface_matches_what_the_scripts_touch(compat_env):
 @pytest.mark.parametrize("level", ["Normal", "Complex"])
 def test_replays_a_recorded_reference_episode(compat_env, golden_dir, level):
     CarParking, CarParkingWrapper, Status, _ = compat_env
-    g = np.load(os.path.join(golden_dir, f"episodes_follow_{level}.npz"))
+    g = dict(np.load(os.path.join(golden_dir, f"episodes_follow_{level}.npz")))
     env = CarParkingWrapper(CarParking(render_mode="rgb_array", verbose=False, use_img_observation=False))
     n_found = 0
     for e in range(3):
@@ -105,7 +105,7 @@ def test_image_modality_through_the_facade(compat_env, golden_dir):
     """USE_IMG defaults to True in the reference (configs.py:100): the facade returns the float64 (3, 64, 64)
     image of env_wrapper.py:52-55; replay of an episode recorded from the unmodified reference."""
     CarParking, CarParkingWrapper, Status, _ = compat_env
-    g = np.load(os.path.join(golden_dir, "images_Normal.npz"))
+    g = dict(np.load(os.path.join(golden_dir, "images_Normal.npz")))
     raw = CarParking(fps=100, verbose=False, render_mode="rgb_array")  # image on by default
     env = CarParkingWrapper(raw)
     assert env.observation_shape == {"action_mask": (42,), "img": (3, 64, 64), "lidar": (120,), "target": (5,)}

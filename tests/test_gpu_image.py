@@ -32,7 +32,7 @@ def _mismatch(a, b):
 
 @pytest.mark.parametrize("level", LEVELS)
 def test_golden_images_through_cuda(golden_dir, level):
-    g = np.load(os.path.join(golden_dir, f"images_{level}.npz"))
+    g = dict(np.load(os.path.join(golden_dir, f"images_{level}.npz")))
     n_ep = len(g["scene_start"])
     scenes = dict(start=g["scene_start"], dest=g["scene_dest"], bounds=g["scene_bounds"], obs=g["scene_obs"], nverts=g["scene_nverts"])
     env = BatchedParkingEnv(n_ep, scenes=scenes, auto_reset=False, use_img_observation=True)

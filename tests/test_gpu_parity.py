@@ -112,7 +112,7 @@ def test_library_reports_version_and_params():
 def test_golden_episodes_through_cuda(golden_dir, level, stem):
     """The traces recorded from the unmodified reference, replayed through the CUDA path: one env
     per recorded episode, recorded float64 actions, free-running (no state correction)."""
-    g = np.load(os.path.join(golden_dir, f"{stem}_{level}.npz"))
+    g = dict(np.load(os.path.join(golden_dir, f"{stem}_{level}.npz")))
     n_ep = len(g["scene_start"])
     scenes = dict(start=g["scene_start"], dest=g["scene_dest"], bounds=g["scene_bounds"], obs=g["scene_obs"], nverts=g["scene_nverts"])
     env = BatchedParkingEnv(n_ep, scenes=scenes, auto_reset=False)

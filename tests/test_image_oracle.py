@@ -15,7 +15,7 @@ LEVELS = ("Normal", "Complex", "Extrem")
 
 @pytest.mark.parametrize("level", LEVELS)
 def test_golden_images_replay_bit_exact(golden_dir, level):
-    g = np.load(os.path.join(golden_dir, f"images_{level}.npz"))
+    g = dict(np.load(os.path.join(golden_dir, f"images_{level}.npz")))
     n_ep = len(g["scene_start"])
     book = io.TrajectoryBook(n_ep)
     checked = stalled = 0

@@ -26,7 +26,7 @@ def harness(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("observe") / "observe_host.so")
     env = dict(os.environ)
     env.pop("CC", None); env.pop("CXX", None)
-    subprocess.check_call([gxx, "-O1", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-I", os.path.join(HERE, "host_stubs"),
+    subprocess.check_call([gxx, "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-I", os.path.join(HERE, "host_stubs"),
                            "-o", out, os.path.join(HERE, "observe_host_harness.cpp")], env=env)
     lib = C.CDLL(out)
     lib.observe_host.restype = C.c_int
@@ -63,7 +63,7 @@ def observe(lib, tb, pose, obs, nverts):
 @pytest.mark.parametrize("stem", ["episodes", "episodes_follow"])
 @pytest.mark.parametrize("level", ["Normal", "Complex", "Extrem"])
 def test_lidar_and_mask_equal_the_recorded_reference(harness, device_tables, golden_dir, level, stem):
-    g = np.load(os.path.join(golden_dir, f"{stem}_{level}.npz"))
+    g = dict(np.load(os.path.join(golden_dir, f"{stem}_{level}.npz")))  # arrays in memory: an NpzFile decompresses on every access
     n = len(g["ep"])
     worst, mask_diff = 0.0, 0
     for ep in range(len(g["scene_start"])):  # observation of reset (car_parking_base.py:127-138)
@@ -106,7 +106,7 @@ def test_adversarial_scenes_against_the_recorded_reference(harness, device_table
     """The same kind of boundary-case scenes, observed by the unmodified reference's LidarSimlator / ActionMask
     (oracle/make_adversarial_golden.py).  The product's k_observe code and the C oracle must both reproduce them."""
     from oracle import parking_oracle as po
-    g = np.load(os.path.join(golden_dir, "adversarial_observe.npz"))
+    g = dict(np.load(os.path.join(golden_dir, "adversarial_observe.npz")))
     n = len(g["start"])
     ref = po.OracleEnv(g["start"], g["start"] + np.array([5.0, 5.0, 0.0]), np.tile(np.array([-100.0, 100.0, -100.0, 100.0]), (n, 1)),
                        g["obs"], g["nverts"]).reset_step()

@@ -27,7 +27,7 @@ def test_mask_tables_bit_exact(golden_dir):
 
 
 def test_reeds_shepp_known_answers(golden_dir):
-    g = np.load(os.path.join(golden_dir, "reeds_shepp.npz"))
+    g = dict(np.load(os.path.join(golden_dir, "reeds_shepp.npz")))
     for i in range(len(g["q"])):
         r = po.rs_all_paths(g["q"][i, :3], g["q"][i, 3:], float(g["maxc"]))
         k = int(g["npaths"][i])
@@ -43,7 +43,7 @@ def test_reeds_shepp_known_answers(golden_dir):
 
 
 def _replay(path):
-    g = np.load(path)
+    g = dict(np.load(path))
     ep = g["ep"]
     n_steps = 0
     for e in range(len(g["scene_start"])):

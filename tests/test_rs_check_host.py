@@ -29,7 +29,7 @@ def harness(request, tmp_path_factory):
     out = str(tmp_path_factory.mktemp("rs_check") / f"rs_check_{request.param}.so")
     env = dict(os.environ)
     env.pop("CC", None); env.pop("CXX", None)
-    subprocess.check_call([gxx, "-O1", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-I", os.path.join(HERE, "host_stubs"),
+    subprocess.check_call([gxx, "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-I", os.path.join(HERE, "host_stubs"),
                            f"-DHOPE_CHK_EDGE_EXIT={request.param}", "-o", out, os.path.join(HERE, "rs_check_host_harness.cpp")], env=env)
     lib = C.CDLL(out)
     lib.rs_check_host.restype = C.c_int
@@ -40,7 +40,7 @@ def harness(request, tmp_path_factory):
 
 @pytest.fixture(scope="module")
 def golden(golden_dir):
-    return np.load(os.path.join(golden_dir, "traj_valid.npz"))
+    return dict(np.load(os.path.join(golden_dir, "traj_valid.npz")))  # arrays in memory: an NpzFile decompresses on every access
 
 
 @pytest.fixture(scope="module")
@@ -123,8 +123,8 @@ def test_two_words_per_warp_give_the_reference_verdicts(request, harness, golden
     n = len(g["call_valid"])
     rng = np.random.default_rng(5)
     valid_idx = np.flatnonzero(g["call_valid"] == 1)
-    pairs = [(i, i + 1) for i in range(0, n - 1, 2)]                                    # consecutive calls
-    pairs += [(int(a), int(b)) for a, b in zip(rng.integers(0, n, 600), rng.integers(0, n, 600))]  # unrelated scenes
+    pairs = [(i, i + 1) for i in range(0, n - 1)]                                       # consecutive calls, both alignments
+    pairs += [(int(a), int(b)) for a, b in zip(rng.integers(0, n, 2000), rng.integers(0, n, 2000))]  # unrelated scenes
     pairs += [(int(a), int(b)) for a, b in zip(valid_idx[:-1], valid_idx[1:])]           # two clean words: all rounds in both halves
     pairs += [(int(a), int(b)) for a, b in zip(valid_idx, rng.integers(0, n, len(valid_idx)))]
     wrong = 0

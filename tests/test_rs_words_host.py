@@ -31,7 +31,7 @@ def rs(tmp_path_factory):
 
 
 def test_known_answers_through_the_product_enumeration(rs, golden_dir):
-    g = np.load(os.path.join(golden_dir, "reeds_shepp.npz"))
+    g = dict(np.load(os.path.join(golden_dir, "reeds_shepp.npz")))
     maxc = float(g["maxc"])
     exact_len = exact_L = words = 0
     for i in range(len(g["q"])):
@@ -61,7 +61,7 @@ def test_sample_chain_through_the_product_walker(rs, golden_dir):
     last three map-frame samples and the coordinate sums of every known word, from k_rs_walk's plan and k_rs_check's
     per-lane replay compiled for the host.  The reference's trailing `while px[-1] == 0.0: pop` is applied here the
     way k_rs_check's zero-tail rule accounts for it."""
-    g = np.load(os.path.join(golden_dir, "reeds_shepp.npz"))
+    g = dict(np.load(os.path.join(golden_dir, "reeds_shepp.npz")))
     maxc = float(g["maxc"])
     cap = 40000
     gx, gy, gyaw, lx = (np.zeros(cap) for _ in range(4))

@@ -1,13 +1,15 @@
 // warp_emu.h — a 32-lane warp on the CPU for the host harnesses under tests/.
 //
-// Each lane is a ucontext fiber running the same callable; __any_sync / __ballot_sync / __shfl_sync / __syncwarp
+// Each lane is a fiber (its own stack) running the same callable; __any_sync / __ballot_sync / __shfl_sync / __syncwarp
 // suspend the lane until every lane of the warp has arrived at a collective, then all resume with the combined
 // result.  Between collectives the lanes run one after the other, which is a legal schedule of independent threads.
 // The emulation also does what compute-sanitizer's synccheck does for these call sites: it is an error if the lanes
 // wait at DIFFERENT collectives (source lines), or if a lane has returned while others still wait at a full-mask
 // collective (on the GPU that is undefined behaviour / a hang).  Only full masks are supported.
 #pragma once
+#if !defined(__x86_64__)
 #include <ucontext.h>
+#endif
 
 #include <cstdint>
 #include <cstring>
@@ -19,9 +21,41 @@ namespace warp_emu {
 constexpr int W = 32;
 constexpr size_t STACK = 256 * 1024;
 
+// Context switch between the scheduler and a lane.  glibc's swapcontext makes a sigprocmask system call per switch
+// (tens of thousands per emulated env), so on x86-64 a minimal switch of the callee-saved registers and the stack
+// pointer is used instead; other hosts fall back to ucontext.
+#if defined(__x86_64__)
+extern "C" void warp_emu_switch(void **save_sp, void *load_sp);
+asm(R"(
+    .text
+    .globl warp_emu_switch
+    .type warp_emu_switch,@function
+warp_emu_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+    .size warp_emu_switch,.-warp_emu_switch
+)");
+typedef void *Context;
+#else
+typedef ucontext_t Context;
+#endif
+
 struct Warp {
     enum State { READY, WAITING, DONE };
-    ucontext_t main_ctx, lane_ctx[W];
+    Context main_ctx, lane_ctx[W];
     State st[W];
     int cur = -1;
     // pending collective of each waiting lane
@@ -39,12 +73,28 @@ inline Warp *&current() {
     return w;
 }
 
+inline void to_lane(Warp *w, int l) {
+#if defined(__x86_64__)
+    warp_emu_switch(&w->main_ctx, w->lane_ctx[l]);
+#else
+    swapcontext(&w->main_ctx, &w->lane_ctx[l]);
+#endif
+}
+inline void to_scheduler(Warp *w, int l) {
+#if defined(__x86_64__)
+    warp_emu_switch(&w->lane_ctx[l], w->main_ctx);
+#else
+    swapcontext(&w->lane_ctx[l], &w->main_ctx);
+#endif
+}
+
 inline void lane_entry() {
     Warp *w = current();
     const int l = w->cur;
     w->body(l);
     w->st[l] = Warp::DONE;
-    swapcontext(&w->lane_ctx[l], &w->main_ctx);
+    to_scheduler(w, l);  // never resumed
+    __builtin_trap();
 }
 
 // Run `body(lane)` on 32 lanes.  Returns nullptr, or a description of the convergence error.
@@ -54,18 +104,29 @@ inline const char *run(const std::function<void(int)> &body, unsigned long long 
     w.body = body;
     current() = &w;
     for (int l = 0; l < W; ++l) {
+#if defined(__x86_64__)
+        // fresh stack: six zeroed callee-saved registers, then lane_entry as the return address; after the `ret` the
+        // stack pointer is 8 below a 16-byte boundary, as at any function entry
+        uintptr_t top = reinterpret_cast<uintptr_t>(stacks.data() + (size_t)(l + 1) * STACK) & ~uintptr_t(15);
+        void **sp = reinterpret_cast<void **>(top - 64);
+        for (int k = 0; k < 6; ++k) sp[k] = nullptr;
+        sp[6] = reinterpret_cast<void *>(&lane_entry);
+        sp[7] = nullptr;
+        w.lane_ctx[l] = sp;
+#else
         getcontext(&w.lane_ctx[l]);
         w.lane_ctx[l].uc_stack.ss_sp = stacks.data() + (size_t)l * STACK;
         w.lane_ctx[l].uc_stack.ss_size = STACK;
         w.lane_ctx[l].uc_link = &w.main_ctx;
         makecontext(&w.lane_ctx[l], lane_entry, 0);
+#endif
         w.st[l] = Warp::READY;
     }
     for (;;) {
         for (int l = 0; l < W; ++l)
             if (w.st[l] == Warp::READY) {
                 w.cur = l;
-                swapcontext(&w.main_ctx, &w.lane_ctx[l]);
+                to_lane(&w, l);
             }
         int waiting = 0, done = 0, first = -1;
         for (int l = 0; l < W; ++l) {
@@ -101,7 +162,7 @@ __attribute__((noinline)) inline uint64_t collective(int op, uint64_t v, int src
     const int l = w->cur;
     w->op[l] = op; w->val[l] = v; w->src[l] = src; w->site[l] = site;
     w->st[l] = Warp::WAITING;
-    swapcontext(&w->lane_ctx[l], &w->main_ctx);
+    to_scheduler(w, l);
     return w->res[l];
 }
 
