@@ -1,0 +1,81 @@
+"""The Reeds-Shepp search of an env, as the kernels run it, replayed on the CPU against the unmodified reference.
+
+tests/rs_search_host_harness.cpp chains the product's own code for one env: enumerate_env (rs_enumerate.cuh: admitted words
+in heapdict pop order, 1.6 x cut-off, car_parking_base.py:431-444), plan_word (rs_walk.cuh), k_rs_check's warp code for
+every tried word (rs_check.cuh on the warp emulation) and k_rs_select's body (first clean word wins, :436-450).  Every
+step of tests/golden/episodes*_*.npz is replayed from its recorded pose: found / words tried / candidates and the winning
+word's segment types must equal what `find_rs_path` returned in the reference, its lengths to 1e-9.
+"""
+import ctypes as C
+import math
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+MAXC = math.tan(0.75) / 2.8   # car_parking_base.py:422
+RS_STEP = 0.1
+
+
+@pytest.fixture(scope="module")
+def harness(tmp_path_factory):
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    out = str(tmp_path_factory.mktemp("rs_search") / "rs_search_host.so")
+    env = dict(os.environ)
+    env.pop("CC", None); env.pop("CXX", None)
+    subprocess.check_call([gxx, "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-I", os.path.join(HERE, "host_stubs"),
+                           "-o", out, os.path.join(HERE, "rs_search_host_harness.cpp")], env=env)
+    lib = C.CDLL(out)
+    lib.rs_search_host.restype = C.c_int
+    lib.rs_search_host.argtypes = [C.c_void_p] * 3 + [C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_double, C.c_double] + [C.c_void_p] * 7
+    return lib
+
+
+@pytest.fixture(scope="module")
+def box():
+    from hope_b200 import capi
+    p = capi.Params()
+    capi.check(capi.load_library().hope_default_params(C.byref(p)))  # host-only call
+    return np.array(list(p.box_x)), np.array(list(p.box_y))
+
+
+@pytest.mark.parametrize("stem", ["episodes", "episodes_follow"])
+@pytest.mark.parametrize("level", ["Normal", "Complex", "Extrem"])
+def test_search_results_equal_the_reference(harness, box, golden_dir, level, stem):
+    g = dict(np.load(os.path.join(golden_dir, f"{stem}_{level}.npz")))
+    n = len(g["ep"])
+    first = {e: int(np.flatnonzero(g["ep"] == e)[0]) for e in range(len(g["scene_start"]))}
+    searched = found = 0
+    worst = 0.0
+    for k in range(n):
+        e = int(g["ep"][k])
+        pose = np.ascontiguousarray(g["pose"][k])
+        dest = np.ascontiguousarray(g["scene_dest"][e])
+        t = k - first[e] + 2  # the reset ends with a step of its own (car_parking_base.py:127-138), so the first action sees t = 2
+        gate = int(t > 1 and g["status"][k] == 1 and math.hypot(pose[0] - dest[0], pose[1] - dest[1]) < 10.0)  # :293-294
+        nv = np.ascontiguousarray(g["scene_nverts"][e], dtype=np.uint8)
+        obs = np.ascontiguousarray(g["scene_obs"][e])
+        bounds = np.ascontiguousarray(g["scene_bounds"][e])
+        u8 = lambda m: np.zeros(m, dtype=np.uint8)
+        o_found, o_nseg, o_types, o_ncand, o_ntried = u8(1), u8(1), u8(5), u8(1), u8(1)
+        o_len, o_L = np.zeros(5), np.zeros(1)
+        rc = harness.rs_search_host(pose.ctypes.data, dest.ctypes.data, bounds.ctypes.data, gate, int((nv > 0).sum()), obs.ctypes.data,
+                                    nv.ctypes.data, box[0].ctypes.data, box[1].ctypes.data, MAXC, RS_STEP, o_found.ctypes.data,
+                                    o_nseg.ctypes.data, o_types.ctypes.data, o_len.ctypes.data, o_L.ctypes.data, o_ncand.ctypes.data,
+                                    o_ntried.ctypes.data)
+        msg = f"{stem}_{level} step {k}"
+        assert rc == 0, msg
+        assert o_ncand[0] == g["rs_ncand"][k] and o_ntried[0] == g["rs_ntried"][k], msg
+        assert o_found[0] == g["rs_found"][k] and o_nseg[0] == g["rs_nseg"][k], msg
+        assert np.array_equal(o_types, g["rs_types"][k]), msg
+        worst = max(worst, float(np.abs(o_len - g["rs_lengths"][k]).max()), abs(float(o_L[0] - g["rs_L"][k])))
+        searched += gate
+        found += int(o_found[0])
+    assert searched >= 100 and worst < 1e-9, (searched, found, worst)
+    if stem == "episodes_follow" and level != "Extrem":  # the reference finds no path in the recorded Extrem episodes
+        assert found >= 10
