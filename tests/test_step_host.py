@@ -1,0 +1,120 @@
+"""The whole env step as the kernels run it, chained on the CPU and stepped in lock step with the C oracle.
+
+tests/step_host_harness.cpp strings the product's device source together for test purposes — k_advance's body (32 envs per
+emulated warp), k_observe's body (a warp per env), enumerate_env, plan_word, k_rs_check's warp code (one word per warp, or
+with HOPE_CHK_PAIR=1 two work items per warp in work-list order like the pair kernel) and k_rs_select's body — and keeps
+the state arrays between steps.  This is the CPU counterpart of tests/test_gpu_parity.py::test_full_step_mixed_levels_vs_oracle:
+generated scenes of all three levels, uniform random actions, every output of every step against the oracle (which is
+pinned on the reference's traces by tests/test_oracle_golden.py).  Both run on the host libm, so floats agree much closer
+than on the GPU.
+"""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def build(tmp, pair):
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    out = str(tmp / f"step_host_{pair}.so")
+    env = dict(os.environ)
+    env.pop("CC", None); env.pop("CXX", None)
+    subprocess.check_call([gxx, "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-I", os.path.join(HERE, "host_stubs"),
+                           f"-DHOPE_CHK_PAIR={pair}", "-o", out, os.path.join(HERE, "step_host_harness.cpp")], env=env)
+    lib = C.CDLL(out)
+    lib.step_create.argtypes = [C.c_int] + [C.c_void_p] * 10
+    lib.step_set_scene.argtypes = [C.c_int] + [C.c_void_p] * 5
+    lib.step_launch.argtypes = [C.c_void_p, C.c_int]
+    lib.step_read.argtypes = [C.c_void_p] * 17
+    return lib
+
+
+OUT = [("pose", np.float64, (3,)), ("status", np.int32, ()), ("reward", np.float64, ()), ("reward_info", np.float64, (5,)),
+       ("target", np.float64, (5,)), ("substeps", np.uint8, ()), ("retreated", np.uint8, ()), ("lidar", np.float64, (120,)),
+       ("mask", np.float64, (42,)), ("mask_steps", np.uint8, (42,)), ("rs_found", np.uint8, ()), ("rs_nseg", np.uint8, ()),
+       ("rs_types", np.uint8, (5,)), ("rs_lengths", np.float64, (5,)), ("rs_L", np.float64, ()), ("rs_ncand", np.uint8, ()),
+       ("rs_ntried", np.uint8, ())]
+
+
+def read(lib, n):
+    o = {k: np.zeros((n,) + s, dtype=dt) for k, dt, s in OUT}
+    lib.step_read(*[o[k].ctypes.data for k, _, _ in OUT])
+    return o
+
+
+@pytest.mark.parametrize("pair", [0, 1], ids=["word_per_warp", "two_words_per_warp"])
+def test_full_step_lockstep_with_the_oracle(tmp_path_factory, pair):
+    from hope_b200 import capi, tables
+    from hope_b200.batched_env import generate_scenes
+    from oracle import parking_oracle as po
+    lib = build(tmp_path_factory.mktemp("step_host"), pair)
+    par = capi.Params()
+    capi.check(capi.load_library().hope_default_params(C.byref(par)))
+    tb = tables.host_tables()
+    ds = tb["dist_star"].reshape(1200, 42, 10)
+    pmaxk = np.ascontiguousarray(np.maximum.accumulate(ds, axis=2).transpose(0, 2, 1))
+    pmax = np.ascontiguousarray(pmaxk[:, 9, :].max(axis=1))
+    gpmax = np.ascontiguousarray(pmax.reshape(120, 10).max(axis=1))
+    n, steps = 96, 40
+    sc = generate_scenes(n, "mix", 321)
+    assert lib.step_create(n, C.addressof(par), *[a.ctypes.data for a in (tb["ray_a"], tb["ray_b"], tb["lidar_base"], tb["mask_base"],
+                                                                              tb["w_lo"], tb["w_hi"], pmaxk, pmax, gpmax)]) == 0
+    for i in range(n):
+        f8 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        s, d, b, o = f8(sc["start"][i]), f8(sc["dest"][i]), f8(sc["bounds"][i]), f8(sc["obs"][i])
+        nv = np.ascontiguousarray(sc["nverts"][i], dtype=np.int32)
+        assert lib.step_set_scene(i, s.ctypes.data, d.ctypes.data, b.ctypes.data, o.ctypes.data, nv.ctypes.data) == 0
+    orc = po.OracleEnv(sc["start"], sc["dest"], sc["bounds"], sc["obs"], sc["nverts"])
+    # Word totals: the product sums |lengths| left to right (CPython 3.8, the reference's README); the oracle defaults to
+    # CPython 3.12's compensated sum() because the golden traces were recorded under 3.12.  The two differ in the last ulp
+    # of L, which decides the pop order of mirror-image words.  Put the oracle on the 3.8 rule for this comparison.
+    po.lib().orc_set_py_sum(0)
+    try:
+        _lockstep(lib, orc, n, steps, pair)
+    finally:
+        po.lib().orc_set_py_sum(1)  # other tests replay the 3.12 recording
+
+
+def _lockstep(lib, orc, n, steps, pair):
+    assert lib.step_launch(None, 1) >= 0
+    ref = orc.reset_step()
+    out = read(lib, n)
+    assert np.array_equal(out["lidar"], ref["lidar"]) and np.array_equal(out["mask_steps"], ref["mask_steps"].astype(np.uint8))
+    rng = np.random.default_rng(99)
+    live = np.ones(n, dtype=bool)
+    compared = words = found = other_word = 0
+    worst = {}
+    for _ in range(steps):
+        act = np.ascontiguousarray(rng.uniform(-1.0, 1.0, size=(n, 2)))
+        n_items = lib.step_launch(act.ctypes.data, 0)
+        assert n_items >= 0, "warp convergence error in the emulation"
+        ref = orc.step(act)
+        out = read(lib, n)
+        for key in ("status", "substeps", "retreated", "rs_ncand", "rs_found"):
+            assert np.array_equal(out[key][live], ref[key][live].astype(out[key].dtype)), key
+        assert np.array_equal(out["mask_steps"][live], ref["mask_steps"][live].astype(np.uint8))
+        # The free-running poses differ in the last bits (closed-form position sum), which is enough to
+        # flip the pop order of mirror-image words whose lengths are equal in exact arithmetic: the number of words tried
+        # and, when both are clean, the word chosen may then differ (the reference itself derives that order from rounding
+        # noise).  From identical poses the search is identical: tests/test_rs_search_host.py.
+        same = live & (out["rs_found"] == 1) & (out["rs_types"] == ref["rs_types"]).all(axis=1)
+        other_word += int((live & (out["rs_found"] == 1)).sum() - same.sum())
+        for key, want, sel in (("pose", orc.pose, live), ("lidar", ref["lidar"], live), ("mask", ref["mask"], live), ("target", ref["target"], live),
+                               ("reward", ref["reward"], live), ("reward_info", ref["reward_info"], live), ("rs_lengths", ref["rs_len"], same),
+                               ("rs_L", ref["rs_L"], same)):
+            d = np.abs(out[key][sel] - want[sel])
+            if d.size:
+                worst[key] = max(worst.get(key, 0.0), float(d.max()))
+        compared += int(live.sum()); words += n_items; found += int(out["rs_found"][live].sum())
+        live &= ref["status"] == 1  # the oracle env has no auto-reset: stop comparing finished episodes
+    print(f"\nfull step on the CPU ({'two words' if pair else 'one word'} per warp): {compared} env-steps, {words} tried words, "
+          f"{found} paths found ({other_word} with another of two equal-length words), worst |diff| {worst}")
+    assert compared >= 2500 and words >= 3000 and found >= 50 and other_word <= max(2, found // 20)
+    assert all(v < 1e-9 for v in worst.values()), worst
