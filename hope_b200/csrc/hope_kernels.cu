@@ -39,6 +39,12 @@ namespace hope {
 #define HOPE_CHK_EDGE_EXIT 1
 #endif
 
+// k_observe, mask sweep: 1 = the per-ray screen loads are issued four rays at a time with the bounds of the batch start
+// (observe_body.inc; same step counts, fewer dependent L2 round trips).  Experimental, not yet measured.
+#ifndef HOPE_OBS_SCREEN_BATCH
+#define HOPE_OBS_SCREEN_BATCH 0
+#endif
+
 // Work counters of an instrumented build (-DHOPE_STATS, profiles/tools/kernel_stats.py): where k_rs_check's rounds end
 // and how many (quadrant, edge) / (ray, action) items k_observe visits.  The default build contains none of this.
 #ifdef HOPE_STATS
