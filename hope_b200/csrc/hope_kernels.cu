@@ -45,6 +45,12 @@ namespace hope {
 #define HOPE_OBS_SCREEN_BATCH 0
 #endif
 
+// k_observe as persistent warps: 0 = one block per two envs (shipped), B > 0 = at most B resident 64-thread blocks per SM (never
+// more than fit: the occupancy API decides) whose warps stride over the envs; 32 = as many as fit.  Experimental, not yet measured.
+#ifndef HOPE_OBS_PERSISTENT
+#define HOPE_OBS_PERSISTENT 0
+#endif
+
 // Work counters of an instrumented build (-DHOPE_STATS, profiles/tools/kernel_stats.py): where k_rs_check's rounds end
 // and how many (quadrant, edge) / (ray, action) items k_observe visits.  The default build contains none of this.
 #ifdef HOPE_STATS
@@ -85,6 +91,22 @@ __global__ void __launch_bounds__(ADV_THREADS, MINB) k_advance(int n, Pool pool,
 // =============================================================================================
 #include "observe.cuh"
 
+#if HOPE_OBS_PERSISTENT
+// Persistent warps: the grid is HOPE_OBS_PERSISTENT resident blocks per SM and every warp walks envs w, w + W, w + 2 W, ...
+// Why: with one env per warp and two warps per block a block's slot is held until its slower env is done, and ncu shows 41 %
+// active warps where the register and shared-memory limits allow 62 % (profiles/r01_ncu_full_summary_u.txt).  A warp that
+// never exits does not wait for its neighbour.  Same statements per env (observe_body.inc).  Experimental, not yet measured.
+__global__ void __launch_bounds__(64) k_observe(int n, Pool pool, EnvState st, Tables tb, hope_params par, hope_out out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    ObserveSmem &sm = reinterpret_cast<ObserveSmem *>(smem_raw)[warp_in_block];
+    const int total_warps = gridDim.x * (blockDim.x >> 5);
+    for (int env = blockIdx.x * (blockDim.x >> 5) + warp_in_block; env < n; env += total_warps) {
+#include "observe_body.inc"
+        __syncwarp();  // the next env reuses the warp's scratch
+    }
+}
+#else
 __global__ void __launch_bounds__(64) k_observe(int n, Pool pool, EnvState st, Tables tb, hope_params par, hope_out out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -93,6 +115,7 @@ __global__ void __launch_bounds__(64) k_observe(int n, Pool pool, EnvState st, T
     ObserveSmem &sm = reinterpret_cast<ObserveSmem *>(smem_raw)[warp_in_block];
 #include "observe_body.inc"
 }
+#endif  // HOPE_OBS_PERSISTENT
 
 // =============================================================================================
 // k_rs_enumerate: one thread per env.  46 candidate words -> admitted list -> heap pop order.
@@ -691,7 +714,17 @@ int launch_range(hope_ctx *ctx, const double *d_action, const hope_out &out_all,
         if (stages & HOPE_STAGE_OBSERVE) {
             const int wpb = OBS_THREADS / 32;
             prof_mark(ctx, 1, so);
+#if HOPE_OBS_PERSISTENT
+            static int obs_bps = 0;  // resident blocks per SM (occupancy of this build), capped by the switch
+            if (!obs_bps) {
+                int fit = 0;
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, k_observe, OBS_THREADS, wpb * sizeof(ObserveSmem)));
+                obs_bps = max(1, min(fit, HOPE_OBS_PERSISTENT));
+            }
+            k_observe<<<min((n + wpb - 1) / wpb, ctx->sm_count * obs_bps), OBS_THREADS, wpb * sizeof(ObserveSmem), so>>>(n, pool, st, tb, ctx->par, out);
+#else
             k_observe<<<(n + wpb - 1) / wpb, OBS_THREADS, wpb * sizeof(ObserveSmem), so>>>(n, pool, st, tb, ctx->par, out);
+#endif
             prof_mark(ctx, 1, so);
             ctx->launches++;
         }
