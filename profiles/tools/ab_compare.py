@@ -5,8 +5,9 @@ Steps the in-tree library (A) and a build with extra -D switches (B) over the sa
 (1) compares EVERY output array of every step bit for bit, (2) times both with CUDA events in alternating blocks.
 One JSON object per stage is printed as soon as it is known (a cut-off run still leaves the earlier ones).
 
-Usage (GPU box):  python profiles/tools/ab_compare.py --defs "-DHOPE_CHK_EDGE_EXIT=1" --name edge_exit [--envs 65536]
-                  python profiles/tools/ab_compare.py --defs ... --name ... --build-only     (here, no GPU needed)
+Usage (GPU box):  python profiles/tools/ab_compare.py --defs=-DHOPE_CHK_PAIR=1 --name pair [--envs 65536]
+                  python profiles/tools/ab_compare.py --variants "pair=-DHOPE_CHK_PAIR=1;persist=-DHOPE_OBS_PERSISTENT=32"
+                  python profiles/tools/ab_compare.py --variants ... --build-only     (here, no GPU needed; the .so files travel)
 """
 import argparse
 import json
@@ -40,38 +41,22 @@ def say(out, **kw):
             f.write(txt + "\n")
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--defs", required=True)
-    ap.add_argument("--name", required=True)
-    ap.add_argument("--envs", type=int, default=65536)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--check-steps", type=int, default=25)
-    ap.add_argument("--time-steps", type=int, default=50)
-    ap.add_argument("--blocks", type=int, default=3)
-    ap.add_argument("--out", default=None)
-    ap.add_argument("--build-only", action="store_true")
-    args = ap.parse_args()
-    path_b = build_variant(args.name, args.defs)
-    if args.build_only:
-        print(path_b)
-        return
+def run_variant(args, name, defs, env_a, scenes, act, total):
     import torch
     from hope_b200 import build as hb, capi
-    from hope_b200.batched_env import BatchedParkingEnv, generate_scenes
+    from hope_b200.batched_env import BatchedParkingEnv
     n = args.envs
-    scenes = generate_scenes(2 * n, "mix", 42)
-    env_a = BatchedParkingEnv(n, scenes=scenes, auto_reset=True)
+    path_b = build_variant(name, defs)
     path_a = hb.VARIANTS[16]
     hb.VARIANTS[16] = path_b
-    capi._LIBS.pop(16)
-    env_b = BatchedParkingEnv(n, scenes=scenes, auto_reset=True)  # binds the variant library
+    capi._LIBS.pop(16, None)
+    try:
+        env_b = BatchedParkingEnv(n, scenes=scenes, auto_reset=True)  # binds the variant library
+    finally:
+        hb.VARIANTS[16] = path_a
+        capi._LIBS[16] = env_a.lib
     assert env_a.lib is not env_b.lib
-    say(args.out, stage="loaded", a=os.path.basename(path_a), b=os.path.basename(path_b), defs=args.defs, envs=n)
-    dev = env_a.device
-    gen = torch.Generator(device=dev); gen.manual_seed(1234)
-    total = args.warmup + args.check_steps
-    act = torch.rand((total, n, 2), dtype=torch.float64, device=dev, generator=gen) * 2 - 1
+    say(args.out, stage="loaded", variant=name, a=os.path.basename(path_a), b=os.path.basename(path_b), defs=defs, envs=n)
 
     def bits(t):
         return t.view(torch.int64) if t.dtype == torch.float64 else t
@@ -80,14 +65,13 @@ def main():
     mismatches, compared = {}, 0
     for k in range(total):
         env_a.step(act[k]); env_b.step(act[k])
-        for name in env_a.out:
-            if not torch.equal(bits(env_a.out[name]), bits(env_b.out[name])):
-                mismatches[name] = mismatches.get(name, 0) + int((bits(env_a.out[name]) != bits(env_b.out[name])).sum().item())
+        for field in env_a.out:
+            if not torch.equal(bits(env_a.out[field]), bits(env_b.out[field])):
+                mismatches[field] = mismatches.get(field, 0) + int((bits(env_a.out[field]) != bits(env_b.out[field])).sum().item())
         compared += 1
     ca, cb = env_a.counters(), env_b.counters()
-    say(args.out, stage="parity", steps_compared=compared, fields=len(env_a.out), mismatching_elements=mismatches,
-        env_steps_a=ca["env_steps"], env_steps_b=cb["env_steps"], rs_found_per_step=float(env_a.out["rs_found"].sum().item()),
-        identical=(not mismatches and ca["env_steps"] == cb["env_steps"]))
+    say(args.out, stage="parity", variant=name, steps_compared=compared, fields=len(env_a.out), mismatching_elements=mismatches,
+        env_steps_a=ca["env_steps"], env_steps_b=cb["env_steps"], identical=(not mismatches and ca["env_steps"] == cb["env_steps"]))
 
     def timed(env, k0):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -102,15 +86,51 @@ def main():
     ms_a, ms_b = [], []
     for blk in range(args.blocks):
         ms_a.append(timed(env_a, blk)); ms_b.append(timed(env_b, blk))
-    say(args.out, stage="timing", ms_per_step_a=ms_a, ms_per_step_b=ms_b, a_over_b=[x / y for x, y in zip(ms_a, ms_b)],
+    say(args.out, stage="timing", variant=name, ms_per_step_a=ms_a, ms_per_step_b=ms_b, a_over_b=[x / y for x, y in zip(ms_a, ms_b)],
         note="device-resident hope_step, CUDA events, alternating blocks; not a bench value (two envs resident, no clock sampling)")
     for which, env in (("a", env_a), ("b", env_b)):  # per-kernel CUDA-event times inside the live step
         env.profile(True); env.profile_read()
         for k in range(20):
             env.step(act[k % total])
         pr = env.profile_read(); env.profile(False)
-        say(args.out, stage="kernels_" + which, ms_per_launch={kn: (v[0] / v[1] if v[1] else None) for kn, v in pr.items()})
-    env_a.close(); env_b.close()
+        say(args.out, stage="kernels_" + which, variant=name, ms_per_launch={kn: (v[0] / v[1] if v[1] else None) for kn, v in pr.items()})
+    env_b.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--defs", default=None, help="one variant: its -D switches (with --name)")
+    ap.add_argument("--name", default=None)
+    ap.add_argument("--variants", default=None, help="several variants: 'name=-DX=1 -DY=2;other=-DZ=1'")
+    ap.add_argument("--envs", type=int, default=65536)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--check-steps", type=int, default=25)
+    ap.add_argument("--time-steps", type=int, default=50)
+    ap.add_argument("--blocks", type=int, default=3)
+    ap.add_argument("--out", default=None)
+    ap.add_argument("--build-only", action="store_true")
+    args = ap.parse_args()
+    variants = []
+    if args.variants:
+        variants += [tuple(v.split("=", 1)) for v in args.variants.split(";") if v.strip()]
+    if args.defs:
+        variants.append((args.name or "variant", args.defs))
+    assert variants, "give --defs/--name or --variants"
+    if args.build_only:
+        for name, defs in variants:
+            print(build_variant(name, defs))
+        return
+    import torch
+    from hope_b200.batched_env import BatchedParkingEnv, generate_scenes
+    n = args.envs
+    scenes = generate_scenes(2 * n, "mix", 42)
+    env_a = BatchedParkingEnv(n, scenes=scenes, auto_reset=True)
+    gen = torch.Generator(device=env_a.device); gen.manual_seed(1234)
+    total = args.warmup + args.check_steps
+    act = torch.rand((total, n, 2), dtype=torch.float64, device=env_a.device, generator=gen) * 2 - 1
+    for name, defs in variants:
+        run_variant(args, name, defs, env_a, scenes, act, total)
+    env_a.close()
 
 
 if __name__ == "__main__":
