@@ -178,6 +178,9 @@ extern "C" int step_set_scene(int i, const double *start, const double *dest, co
     return 0;
 }
 
+static unsigned long long g_check_votes = 0, g_check_runs = 0;  // warp-level votes / warp runs of the k_rs_check stage
+extern "C" void step_check_work(unsigned long long *votes, unsigned long long *runs) { *votes = g_check_votes; *runs = g_check_runs; }
+
 static int fail(const char *err) {
     if (getenv("WARP_EMU_VERBOSE")) fprintf(stderr, "warp_emu: %s\n", err);
     return -2;
@@ -229,6 +232,7 @@ extern "C" int step_launch(const double *action, int reset_all) {
     slots.resize(std::max(1, n_items));
     for (int it = 0; it < n_items; ++it) plan_word(slots[it], g.words[(size_t)(g.items[it] >> 4) * MAXW + (g.items[it] & 15)], g.maxc, g.par.rs_step * g.maxc);
     // ---- k_rs_check ----
+    unsigned long long votes = 0;
 #if HOPE_CHK_PAIR
     for (int p = 0; 2 * p < n_items; ++p) {
         int verdict[32];
@@ -240,8 +244,9 @@ extern "C" int step_launch(const double *action, int reset_all) {
             const char *err = warp_emu::run([&](int lane) {
                 const int half = lane >> 4;
                 verdict[lane] = pair_is_bad(half ? slots[it1] : slots[it0], half ? E1 : E0, g.par, lane, half == 0 || have1) ? 1 : 0;
-            });
+            }, &votes);
             if (err) return fail(err);
+            g_check_votes += votes; ++g_check_runs;
             g.item_bad[it0] = (uint8_t)verdict[0];
             if (have1) g.item_bad[it1] = (uint8_t)verdict[16];
             continue;
@@ -259,8 +264,9 @@ extern "C" int step_launch(const double *action, int reset_all) {
                     __syncwarp();
                 }
                 verdict[lane] = bad ? 1 : 0;
-            });
+            }, &votes);
             if (err) return fail(err);
+            g_check_votes += votes; ++g_check_runs;
             g.item_bad[2 * p + h] = (uint8_t)verdict[0];
         }
     }
@@ -279,8 +285,9 @@ extern "C" int step_launch(const double *action, int reset_all) {
                 __syncwarp();
             }
             verdict[lane] = bad ? 1 : 0;
-        });
+        }, &votes);
         if (err) return fail(err);
+        g_check_votes += votes; ++g_check_runs;
         g.item_bad[it] = (uint8_t)verdict[0];
     }
 #endif
