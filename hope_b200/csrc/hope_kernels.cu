@@ -178,6 +178,13 @@ __global__ void __launch_bounds__(128) k_rs_walk(RsScratch rs, Tables tb, hope_p
 #if HOPE_CHK_PAIR
 #include "rs_check_pair.cuh"
 #endif
+// 1 = k_rs_check pools the line-pair tests of a round over the whole warp (rs_check_pooled.cuh; experimental, not yet measured)
+#ifndef HOPE_CHK_POOLED
+#define HOPE_CHK_POOLED 0
+#endif
+#if HOPE_CHK_POOLED
+#include "rs_check_pooled.cuh"
+#endif
 
 #ifndef HOPE_CHK_WARPS
 #define HOPE_CHK_WARPS 4
@@ -267,6 +274,9 @@ __global__ void __launch_bounds__(CHK_WARPS * 32, HOPE_CHK_MINBLOCKS) k_rs_check
 #else
 __global__ void __launch_bounds__(CHK_WARPS * 32, HOPE_CHK_MINBLOCKS) k_rs_check(Pool pool, EnvState st, Tables tb, RsScratch rs, hope_params par) {
     __shared__ WordSlot smem[CHK_WARPS][2];  // double buffer: the next word's plan streams in while this one is sampled
+#if HOPE_CHK_POOLED
+    __shared__ CheckSmem csm[CHK_WARPS];
+#endif
     const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_items = *rs.n_items;
     const int warps_total = gridDim.x * CHK_WARPS;
@@ -293,7 +303,11 @@ __global__ void __launch_bounds__(CHK_WARPS * 32, HOPE_CHK_MINBLOCKS) k_rs_check
         bool bad = false;
         int chunk_base = 0;
         for (;;) {
+#if HOPE_CHK_POOLED
+            bad = chunk_is_bad_pooled(s, E, par, lane, csm[warp_in_block]);
+#else
             bad = chunk_is_bad(s, E, par, lane);
+#endif
             if (bad || s.total >= 0) break;
             chunk_base += RS_CHUNK;  // a word longer than one chunk (rare): lane 0 walks on
             __syncwarp();

@@ -4,6 +4,7 @@
 // recorded from the unmodified reference (tests/golden/traj_valid.npz) can be replayed through the product's own code
 // without a GPU — including the trailing-zero path (reeds_shepp.py:501-505) that no generated
 // scene reaches.  Built twice by the test: -DHOPE_CHK_EDGE_EXIT=1 (the shipped vote placement) and =0.
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -21,12 +22,15 @@ static inline double __dsub_rn(double a, double b) { return a - b; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 static inline double __drcp_rn(double a) { return 1.0 / a; }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
 struct double2 { double x, y; };
 struct alignas(16) double4 { double x, y, z, w; };
 static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 static inline double4 make_double4(double x, double y, double z, double w) { return double4{x, y, z, w}; }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
+using std::max;
+using std::min;
 
 #include "warp_emu.h"
 
@@ -35,6 +39,9 @@ template <typename T> static inline T __ldg(const T *p) { return *p; }
 
 #ifndef HOPE_CHK_EDGE_EXIT
 #define HOPE_CHK_EDGE_EXIT 1
+#endif
+#ifndef HOPE_CHK_POOLED
+#define HOPE_CHK_POOLED 0
 #endif
 
 namespace hope {
@@ -47,6 +54,7 @@ static inline double4 ld_aabb(const double4 *p) { return *p; }  // the kernel's 
 #include "../hope_b200/csrc/rs_walk.cuh"
 #include "../hope_b200/csrc/rs_check.cuh"
 #include "../hope_b200/csrc/rs_check_pair.cuh"
+#include "../hope_b200/csrc/rs_check_pooled.cuh"
 }  // namespace hope
 
 // One tried word ready for the check: its sampling plan (k_rs_walk's output) and the check environment k_rs_check builds.
@@ -115,7 +123,12 @@ static int whole_warp_verdict(Prepared &P, const hope_params &par, unsigned long
         bool bad = false;
         int chunk_base = 0;
         for (;;) {
+#if HOPE_CHK_POOLED
+            static CheckSmem cs;
+            bad = chunk_is_bad_pooled(P.s, P.E, par, lane, cs);
+#else
             bad = chunk_is_bad(P.s, P.E, par, lane);
+#endif
             if (bad || P.s.total >= 0) break;
             chunk_base += RS_CHUNK;
             __syncwarp();

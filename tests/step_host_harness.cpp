@@ -51,6 +51,9 @@ using std::min;
 #ifndef HOPE_CHK_PAIR
 #define HOPE_CHK_PAIR 0
 #endif
+#ifndef HOPE_CHK_POOLED
+#define HOPE_CHK_POOLED 0
+#endif
 
 namespace hope {
 #include "../hope_b200/csrc/hope_types.cuh"
@@ -62,6 +65,7 @@ static inline double4 ld_aabb(const double4 *p) { return *p; }  // the kernel's 
 #include "../hope_b200/csrc/rs_walk.cuh"
 #include "../hope_b200/csrc/rs_check.cuh"
 #include "../hope_b200/csrc/rs_check_pair.cuh"
+#include "../hope_b200/csrc/rs_check_pooled.cuh"
 
 static void advance_one(const int n, const int gi, const int lane, AdvanceSmem &sm, Pool pool, EnvState st, const double *action, hope_params par,
                         hope_out out, int reset_all, int reset_stride) {
@@ -278,7 +282,12 @@ extern "C" int step_launch(const double *action, int reset_all) {
         const char *err = warp_emu::run([&](int lane) {
             bool bad = false; int chunk_base = 0;
             for (;;) {
+#if HOPE_CHK_POOLED
+                static CheckSmem cs;
+                bad = chunk_is_bad_pooled(s, E, g.par, lane, cs);
+#else
                 bad = chunk_is_bad(s, E, g.par, lane);
+#endif
                 if (bad || s.total >= 0) break;
                 chunk_base += RS_CHUNK; __syncwarp();
                 if (lane == 0) walk_chunk(s, s.len, E.step, chunk_base);

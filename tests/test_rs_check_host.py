@@ -21,16 +21,19 @@ MAXC = math.tan(0.75) / 2.8   # car_parking_base.py:422
 RS_STEP = 0.1                 # :424
 
 
-@pytest.fixture(scope="module", params=[1, 0], ids=["edge_exit", "obstacle_exit"])
+@pytest.fixture(scope="module", params=[(1, 0), (0, 0), (1, 1)], ids=["edge_exit", "obstacle_exit", "pooled"])
 def harness(request, tmp_path_factory):
+    """params: (HOPE_CHK_EDGE_EXIT, HOPE_CHK_POOLED).  edge_exit is the shipped build; obstacle_exit the former vote placement;
+    pooled the experimental rs_check_pooled.cuh (line-pair tests of a round pooled over the warp)."""
     gxx = shutil.which("g++")
     if gxx is None:
         pytest.skip("g++ not available")
-    out = str(tmp_path_factory.mktemp("rs_check") / f"rs_check_{request.param}.so")
+    edge_exit, pooled = request.param
+    out = str(tmp_path_factory.mktemp("rs_check") / f"rs_check_{edge_exit}_{pooled}.so")
     env = dict(os.environ)
     env.pop("CC", None); env.pop("CXX", None)
     subprocess.check_call([gxx, "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-I", os.path.join(HERE, "host_stubs"),
-                           f"-DHOPE_CHK_EDGE_EXIT={request.param}", "-o", out, os.path.join(HERE, "rs_check_host_harness.cpp")], env=env)
+                           f"-DHOPE_CHK_EDGE_EXIT={edge_exit}", f"-DHOPE_CHK_POOLED={pooled}", "-o", out, os.path.join(HERE, "rs_check_host_harness.cpp")], env=env)
     lib = C.CDLL(out)
     lib.rs_check_host.restype = C.c_int
     lib.rs_check_host.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
@@ -113,8 +116,8 @@ def test_two_words_per_warp_give_the_reference_verdicts(request, harness, golden
     """rs_check_pair.cuh (HOPE_CHK_PAIR, off by default): lanes 0-15 check one recorded word, lanes 16-31 another, in one
     instruction stream.  Pairs of consecutive calls (mostly the same env's next word, as the work list hands them to a
     warp), pairs from different scenes with different obstacle counts, and a lone word with an idle upper half."""
-    if "obstacle_exit" in request.node.name:
-        pytest.skip("rs_check_pair.cuh does not depend on HOPE_CHK_EDGE_EXIT: one build is enough")
+    if "edge_exit" not in request.node.name:
+        pytest.skip("rs_check_pair.cuh does not depend on the other switches: one build is enough")
     g = golden
     lib = harness
     lib.rs_check_pair_host.restype = C.c_int

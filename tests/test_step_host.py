@@ -19,15 +19,15 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def build(tmp, pair, screen_batch=0):
+def build(tmp, pair, screen_batch=0, pooled=0):
     gxx = shutil.which("g++")
     if gxx is None:
         pytest.skip("g++ not available")
-    out = str(tmp / f"step_host_{pair}_{screen_batch}.so")
+    out = str(tmp / f"step_host_{pair}_{screen_batch}_{pooled}.so")
     env = dict(os.environ)
     env.pop("CC", None); env.pop("CXX", None)
     subprocess.check_call([gxx, "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-I", os.path.join(HERE, "host_stubs"),
-                           f"-DHOPE_CHK_PAIR={pair}", f"-DHOPE_OBS_SCREEN_BATCH={screen_batch}", "-o", out, os.path.join(HERE, "step_host_harness.cpp")], env=env)
+                           f"-DHOPE_CHK_PAIR={pair}", f"-DHOPE_OBS_SCREEN_BATCH={screen_batch}", f"-DHOPE_CHK_POOLED={pooled}", "-o", out, os.path.join(HERE, "step_host_harness.cpp")], env=env)
     lib = C.CDLL(out)
     lib.step_create.argtypes = [C.c_int] + [C.c_void_p] * 10
     lib.step_set_scene.argtypes = [C.c_int] + [C.c_void_p] * 5
@@ -49,12 +49,13 @@ def read(lib, n):
     return o
 
 
-@pytest.mark.parametrize("pair,screen_batch", [(0, 0), (1, 0), (0, 1)], ids=["shipped", "two_words_per_warp", "batched_mask_screen"])
-def test_full_step_lockstep_with_the_oracle(tmp_path_factory, pair, screen_batch):
+@pytest.mark.parametrize("pair,screen_batch,pooled", [(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1)],
+                         ids=["shipped", "two_words_per_warp", "batched_mask_screen", "pooled_line_pairs"])
+def test_full_step_lockstep_with_the_oracle(tmp_path_factory, pair, screen_batch, pooled):
     from hope_b200 import capi, tables
     from hope_b200.batched_env import generate_scenes
     from oracle import parking_oracle as po
-    lib = build(tmp_path_factory.mktemp("step_host"), pair, screen_batch)
+    lib = build(tmp_path_factory.mktemp("step_host"), pair, screen_batch, pooled)
     par = capi.Params()
     capi.check(capi.load_library().hope_default_params(C.byref(par)))
     tb = tables.host_tables()
