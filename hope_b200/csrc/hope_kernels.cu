@@ -10,6 +10,12 @@
 //
 // All arithmetic is float64 with FMA contraction off (see hope_device.cuh).  Data layout in HBM is
 // documented in DESIGN.md §3.
+//
+// The per-work-item code of each kernel lives in headers / textual fragments next to this file (advance.cuh + advance_body.inc,
+// observe.cuh + observe_body.inc, rs_words.cuh, rs_enumerate.cuh, rs_walk.cuh, rs_check.cuh, rs_select_body.inc, div_pair.cuh,
+// hope_types.cuh) so that the host harnesses under tests/ compile the very same source with g++ on a CPU warp emulation
+// (tests/warp_emu.h) and replay traces of the unmodified reference through it; this file keeps the kernel shells, the launch
+// order and the C ABI.
 #include <cuda_pipeline.h>
 #include <cuda_runtime.h>
 #include <math.h>
