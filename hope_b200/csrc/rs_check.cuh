@@ -38,6 +38,12 @@ __device__ __forceinline__ bool warp_samples_hit(const CheckEnv &E, const hope_p
         double4 bb = ld_aabb(E.aabb + ob);
         // disjoint boxes cannot produce a hit (:518-526), so this reject is exact
         const bool enter = valid && !mine && !(vxmax < bb.x || bb.y < vxmin || vymax < bb.z || bb.w < vymin);
+#ifdef HOPE_STATS
+        {
+            const unsigned mm = __ballot_sync(HOPE_FULL_MASK, enter);
+            if ((threadIdx.x & 31) == 0) { HOPE_STAT(32, 1); HOPE_STAT(33, __popc(mm)); if (mm) HOPE_STAT(34, 1); }
+        }
+#endif
         if (!__any_sync(HOPE_FULL_MASK, enter)) continue;
         // The edge loop is warp-uniform (every lane looks at the same obstacle, so nv is the same) and the warp votes
         // after EACH obstacle edge: one bad sample condemns the word, and 95 % of the tried words are condemned in
@@ -67,6 +73,12 @@ __device__ __forceinline__ bool warp_samples_hit(const CheckEnv &E, const hope_p
                     if (okx && oky) mine = true;
                 }
             }
+#ifdef HOPE_STATS
+            if (early && __any_sync(HOPE_FULL_MASK, mine)) {
+                if ((threadIdx.x & 31) == 0) { HOPE_STAT(15, 1); HOPE_STAT(16 + (ob < 15 ? ob : 15), 1); HOPE_STAT(36 + (j < 3 ? j : 3), 1); }
+                return true;
+            }
+#endif
             if (early && __any_sync(HOPE_FULL_MASK, mine)) return true;
             p1 = p2;
         }

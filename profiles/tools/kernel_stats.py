@@ -88,6 +88,7 @@ def main():
             "share_of_rounds_spent_on_bad_words": bad_rounds / max(1, rounds),
             "exits_by_bounds": s[14], "exits_by_obstacle": s[15],
             "exit_obstacle_index_histogram": s[16:32],
+            "exit_obstacle_edge_histogram": s[36:40],  # per-edge vote (HOPE_CHK_EDGE_EXIT=1): after which edge of the obstacle
             "obstacle_iterations_per_round": s[32] / max(1, rounds),
             "obstacle_iterations_with_edge_work": s[34] / max(1, s[32]),
             "lanes_in_edge_loop_when_any": s[33] / max(1, s[34]),
