@@ -79,3 +79,27 @@ def test_search_results_equal_the_reference(harness, box, golden_dir, level, ste
     assert searched >= 100 and worst < 1e-9, (searched, found, worst)
     if stem == "episodes_follow" and level != "Extrem":  # the reference finds no path in the recorded Extrem episodes
         assert found >= 10
+
+
+def test_grazing_cases_follow_the_reference_at_both_poses(harness, box, golden_dir):
+    """Two searches found by the CPU lock step (tests/test_step_host.py, 768 envs x 80 steps) where the C oracle found a
+    path and the free-running product code did not.  The poses differ by 3.6e-15 and 3.3e-14 (closed-form position sum in
+    k_advance).  The unmodified reference, run on both poses of each case (`find_rs_path`, recorded in
+    tests/golden/grazing_cases.npz), flips in exactly the same way: its first word just grazes an obstacle.  The product's
+    search code must agree with the reference at BOTH poses — the sensitivity is the algorithm's, not the port's."""
+    g = dict(np.load(os.path.join(golden_dir, "grazing_cases.npz")))
+    for c in range(len(g["dest"])):
+        assert 0.0 < np.abs(g["pose"][c, 0] - g["pose"][c, 1]).max() < 1e-13
+        nv = np.ascontiguousarray(g["nverts"][c], dtype=np.uint8)
+        obs, bounds, dest = (np.ascontiguousarray(g[k][c]) for k in ("obs", "bounds", "dest"))
+        for which in (0, 1):
+            pose = np.ascontiguousarray(g["pose"][c, which])
+            u8 = lambda m: np.zeros(m, dtype=np.uint8)
+            o_found, o_nseg, o_types, o_ncand, o_ntried = u8(1), u8(1), u8(5), u8(1), u8(1)
+            o_len, o_L = np.zeros(5), np.zeros(1)
+            rc = harness.rs_search_host(pose.ctypes.data, dest.ctypes.data, bounds.ctypes.data, 1, int((nv > 0).sum()), obs.ctypes.data,
+                                        nv.ctypes.data, box[0].ctypes.data, box[1].ctypes.data, MAXC, RS_STEP, o_found.ctypes.data,
+                                        o_nseg.ctypes.data, o_types.ctypes.data, o_len.ctypes.data, o_L.ctypes.data, o_ncand.ctypes.data,
+                                        o_ntried.ctypes.data)
+            assert rc == 0
+            assert o_found[0] == g["ref_found"][c, which] and o_ntried[0] == g["ref_ntried"][c, which], (c, which)

@@ -63,8 +63,10 @@ def test_full_step_lockstep_with_the_oracle(tmp_path_factory, pair, screen_batch
     pmaxk = np.ascontiguousarray(np.maximum.accumulate(ds, axis=2).transpose(0, 2, 1))
     pmax = np.ascontiguousarray(pmaxk[:, 9, :].max(axis=1))
     gpmax = np.ascontiguousarray(pmax.reshape(120, 10).max(axis=1))
-    n, steps = 96, 40
-    sc = generate_scenes(n, "mix", 321)
+    n, steps, seed = 96, 40, 321
+    if os.environ.get("HOPE_STEP_SOAK"):  # longer run by hand: HOPE_STEP_SOAK="envs,steps,seed"
+        n, steps, seed = (int(v) for v in os.environ["HOPE_STEP_SOAK"].split(","))
+    sc = generate_scenes(n, "mix", seed)
     assert lib.step_create(n, C.addressof(par), *[a.ctypes.data for a in (tb["ray_a"], tb["ray_b"], tb["lidar_base"], tb["mask_base"],
                                                                               tb["w_lo"], tb["w_hi"], pmaxk, pmax, gpmax)]) == 0
     for i in range(n):
@@ -90,7 +92,7 @@ def _lockstep(lib, orc, n, steps, pair):
     assert np.array_equal(out["lidar"], ref["lidar"]) and np.array_equal(out["mask_steps"], ref["mask_steps"].astype(np.uint8))
     rng = np.random.default_rng(99)
     live = np.ones(n, dtype=bool)
-    compared = words = found = other_word = 0
+    compared = words = found = other_word = found_flips = 0
     worst = {}
     for _ in range(steps):
         act = np.ascontiguousarray(rng.uniform(-1.0, 1.0, size=(n, 2)))
@@ -98,15 +100,19 @@ def _lockstep(lib, orc, n, steps, pair):
         assert n_items >= 0, "warp convergence error in the emulation"
         ref = orc.step(act)
         out = read(lib, n)
-        for key in ("status", "substeps", "retreated", "rs_ncand", "rs_found"):
+        for key in ("status", "substeps", "retreated", "rs_ncand"):
             assert np.array_equal(out[key][live], ref[key][live].astype(out[key].dtype)), key
+        # a word that just grazes an obstacle flips with the last bits of the pose, in the reference itself
+        # (tests/test_rs_search_host.py::test_grazing_cases_follow_the_reference_at_both_poses): counted, not required
+        found_flips += int((out["rs_found"][live] != ref["rs_found"][live]).sum())
         assert np.array_equal(out["mask_steps"][live], ref["mask_steps"][live].astype(np.uint8))
         # The free-running poses differ in the last bits (closed-form position sum), which is enough to
         # flip the pop order of mirror-image words whose lengths are equal in exact arithmetic: the number of words tried
         # and, when both are clean, the word chosen may then differ (the reference itself derives that order from rounding
         # noise).  From identical poses the search is identical: tests/test_rs_search_host.py.
-        same = live & (out["rs_found"] == 1) & (out["rs_types"] == ref["rs_types"]).all(axis=1)
-        other_word += int((live & (out["rs_found"] == 1)).sum() - same.sum())
+        both = live & (out["rs_found"] == 1) & (ref["rs_found"] == 1)
+        same = both & (out["rs_types"] == ref["rs_types"]).all(axis=1)
+        other_word += int(both.sum() - same.sum())
         for key, want, sel in (("pose", orc.pose, live), ("lidar", ref["lidar"], live), ("mask", ref["mask"], live), ("target", ref["target"], live),
                                ("reward", ref["reward"], live), ("reward_info", ref["reward_info"], live), ("rs_lengths", ref["rs_len"], same),
                                ("rs_L", ref["rs_L"], same)):
@@ -116,6 +122,7 @@ def _lockstep(lib, orc, n, steps, pair):
         compared += int(live.sum()); words += n_items; found += int(out["rs_found"][live].sum())
         live &= ref["status"] == 1  # the oracle env has no auto-reset: stop comparing finished episodes
     print(f"\nfull step on the CPU ({'two words' if pair else 'one word'} per warp): {compared} env-steps, {words} tried words, "
-          f"{found} paths found ({other_word} with another of two equal-length words), worst |diff| {worst}")
-    assert compared >= 2500 and words >= 3000 and found >= 50 and other_word <= max(2, found // 20)
+          f"{found} paths found ({other_word} with another of two equal-length words, {found_flips} found/not-found flips), worst |diff| {worst}")
+    assert compared >= 2500 and words >= 3000 and found >= 50 and other_word <= max(2, found // 20), (compared, words, found, other_word)
+    assert found_flips <= max(2, compared // 5000), found_flips
     assert all(v < 1e-9 for v in worst.values()), worst
