@@ -19,15 +19,15 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def build(tmp, pair, screen_batch=0, pooled=0):
+def build(tmp, pair, screen_batch=0, pooled=0, max_obs=16):
     gxx = shutil.which("g++")
     if gxx is None:
         pytest.skip("g++ not available")
-    out = str(tmp / f"step_host_{pair}_{screen_batch}_{pooled}.so")
+    out = str(tmp / f"step_host_{pair}_{screen_batch}_{pooled}_{max_obs}.so")
     env = dict(os.environ)
     env.pop("CC", None); env.pop("CXX", None)
     subprocess.check_call([gxx, "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-I", os.path.join(HERE, "host_stubs"),
-                           f"-DHOPE_CHK_PAIR={pair}", f"-DHOPE_OBS_SCREEN_BATCH={screen_batch}", f"-DHOPE_CHK_POOLED={pooled}", "-o", out, os.path.join(HERE, "step_host_harness.cpp")], env=env)
+                           f"-DHOPE_CHK_PAIR={pair}", f"-DHOPE_OBS_SCREEN_BATCH={screen_batch}", f"-DHOPE_CHK_POOLED={pooled}", f"-DHOPE_MAX_OBS={max_obs}", "-o", out, os.path.join(HERE, "step_host_harness.cpp")], env=env)
     lib = C.CDLL(out)
     lib.step_create.argtypes = [C.c_int] + [C.c_void_p] * 10
     lib.step_set_scene.argtypes = [C.c_int] + [C.c_void_p] * 5
@@ -49,13 +49,9 @@ def read(lib, n):
     return o
 
 
-@pytest.mark.parametrize("pair,screen_batch,pooled", [(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1)],
-                         ids=["shipped", "two_words_per_warp", "batched_mask_screen", "pooled_line_pairs"])
-def test_full_step_lockstep_with_the_oracle(tmp_path_factory, pair, screen_batch, pooled):
+def _run(lib, sc, steps, pair, min_steps, min_words, min_found):
     from hope_b200 import capi, tables
-    from hope_b200.batched_env import generate_scenes
     from oracle import parking_oracle as po
-    lib = build(tmp_path_factory.mktemp("step_host"), pair, screen_batch, pooled)
     par = capi.Params()
     capi.check(capi.load_library().hope_default_params(C.byref(par)))
     tb = tables.host_tables()
@@ -63,10 +59,7 @@ def test_full_step_lockstep_with_the_oracle(tmp_path_factory, pair, screen_batch
     pmaxk = np.ascontiguousarray(np.maximum.accumulate(ds, axis=2).transpose(0, 2, 1))
     pmax = np.ascontiguousarray(pmaxk[:, 9, :].max(axis=1))
     gpmax = np.ascontiguousarray(pmax.reshape(120, 10).max(axis=1))
-    n, steps, seed = 96, 40, 321
-    if os.environ.get("HOPE_STEP_SOAK"):  # longer run by hand: HOPE_STEP_SOAK="envs,steps,seed"
-        n, steps, seed = (int(v) for v in os.environ["HOPE_STEP_SOAK"].split(","))
-    sc = generate_scenes(n, "mix", seed)
+    n = len(sc["start"])
     assert lib.step_create(n, C.addressof(par), *[a.ctypes.data for a in (tb["ray_a"], tb["ray_b"], tb["lidar_base"], tb["mask_base"],
                                                                               tb["w_lo"], tb["w_hi"], pmaxk, pmax, gpmax)]) == 0
     for i in range(n):
@@ -78,14 +71,40 @@ def test_full_step_lockstep_with_the_oracle(tmp_path_factory, pair, screen_batch
     # Word totals: the product sums |lengths| left to right (CPython 3.8, the reference's README); the oracle defaults to
     # CPython 3.12's compensated sum() because the golden traces were recorded under 3.12.  The two differ in the last ulp
     # of L, which decides the pop order of mirror-image words.  Put the oracle on the 3.8 rule for this comparison.
-    po.lib().orc_set_py_sum(0)
+    olib = po.lib(int(np.asarray(sc["nverts"]).shape[1]))
+    olib.orc_set_py_sum(0)
     try:
-        _lockstep(lib, orc, n, steps, pair)
+        _lockstep(lib, orc, n, steps, pair, min_steps, min_words, min_found)
     finally:
-        po.lib().orc_set_py_sum(1)  # other tests replay the 3.12 recording
+        olib.orc_set_py_sum(1)  # other tests replay the 3.12 recording
 
 
-def _lockstep(lib, orc, n, steps, pair):
+MODES = [(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1)]
+MODE_IDS = ["shipped", "two_words_per_warp", "batched_mask_screen", "pooled_line_pairs"]
+
+
+@pytest.mark.parametrize("pair,screen_batch,pooled", MODES, ids=MODE_IDS)
+def test_full_step_lockstep_with_the_oracle(tmp_path_factory, pair, screen_batch, pooled):
+    from hope_b200.batched_env import generate_scenes
+    lib = build(tmp_path_factory.mktemp("step_host"), pair, screen_batch, pooled)
+    n, steps, seed = 96, 40, 321
+    if os.environ.get("HOPE_STEP_SOAK"):  # longer run by hand: HOPE_STEP_SOAK="envs,steps,seed"
+        n, steps, seed = (int(v) for v in os.environ["HOPE_STEP_SOAK"].split(","))
+    _run(lib, generate_scenes(n, "mix", seed), steps, pair, 2500, 3000, 50)
+
+
+@pytest.mark.parametrize("pair,screen_batch,pooled", MODES, ids=MODE_IDS)
+def test_full_step_lockstep_on_dragon_lake_scenes(tmp_path_factory, golden_dir, pair, screen_batch, pooled):
+    """The same on the 128-ring build (-DHOPE_MAX_OBS=128) with Dragon Lake Parking scenes (31-119 obstacle rings per scene,
+    tests/golden/dlp_cases.npz): long obstacle loops, several queue groups per round in the pooled variant."""
+    from hope_b200 import dlp
+    lib = build(tmp_path_factory.mktemp("step_host_dlp"), pair, screen_batch, pooled, max_obs=128)
+    cases = dlp.cases_from_fixture(np.load(os.path.join(golden_dir, "dlp_cases.npz")))
+    sc = dlp.prepare_scenes(cases, np.arange(48) % 16, seed=11)
+    _run(lib, sc, 20, pair, 500, 50, 0)  # the recorded starts are mostly farther than 10 m from the slot: few searches
+
+
+def _lockstep(lib, orc, n, steps, pair, min_steps, min_words, min_found):
     assert lib.step_launch(None, 1) >= 0
     ref = orc.reset_step()
     out = read(lib, n)
@@ -123,6 +142,6 @@ def _lockstep(lib, orc, n, steps, pair):
         live &= ref["status"] == 1  # the oracle env has no auto-reset: stop comparing finished episodes
     print(f"\nfull step on the CPU ({'two words' if pair else 'one word'} per warp): {compared} env-steps, {words} tried words, "
           f"{found} paths found ({other_word} with another of two equal-length words, {found_flips} found/not-found flips), worst |diff| {worst}")
-    assert compared >= 2500 and words >= 3000 and found >= 50 and other_word <= max(2, found // 20), (compared, words, found, other_word)
+    assert compared >= min_steps and words >= min_words and found >= min_found and other_word <= max(2, found // 20), (compared, words, found, other_word)
     assert found_flips <= max(2, compared // 5000), found_flips
     assert all(v < 1e-9 for v in worst.values()), worst
