@@ -24,7 +24,7 @@ static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dsub_rn(double a, double b) { return a - b; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
-static inline double __drcp_rn(double a) { return 1.0 / a; }
+static inline double __drcp_rn(double a);  // below: counts one unit of "division" work per call
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
@@ -37,6 +37,8 @@ using std::max;
 using std::min;
 
 #include "warp_emu.h"
+static inline double __drcp_rn(double a) { warp_emu::work(0, 1); return 1.0 / a; }
+#define sincos(a, s, c) (warp_emu::work(1, 1), ::sincos(a, s, c))
 
 #ifndef HOPE_OBS_SCREEN_BATCH
 #define HOPE_OBS_SCREEN_BATCH 0
@@ -183,7 +185,9 @@ extern "C" int step_set_scene(int i, const double *start, const double *dest, co
 }
 
 static unsigned long long g_check_votes = 0, g_check_runs = 0;  // warp-level votes / warp runs of the k_rs_check stage
+static unsigned long long g_check_div = 0, g_check_sincos = 0;  // warp-level cost model of the check stage (warp_emu::work)
 extern "C" void step_check_work(unsigned long long *votes, unsigned long long *runs) { *votes = g_check_votes; *runs = g_check_runs; }
+extern "C" void step_check_cost(unsigned long long *div, unsigned long long *sc) { *div = g_check_div; *sc = g_check_sincos; }
 
 static int fail(const char *err) {
     if (getenv("WARP_EMU_VERBOSE")) fprintf(stderr, "warp_emu: %s\n", err);
@@ -237,6 +241,7 @@ extern "C" int step_launch(const double *action, int reset_all) {
     for (int it = 0; it < n_items; ++it) plan_word(slots[it], g.words[(size_t)(g.items[it] >> 4) * MAXW + (g.items[it] & 15)], g.maxc, g.par.rs_step * g.maxc);
     // ---- k_rs_check ----
     unsigned long long votes = 0;
+    const unsigned long long div0 = warp_emu::total_work()[0], sc0 = warp_emu::total_work()[1];
 #if HOPE_CHK_PAIR
     for (int p = 0; 2 * p < n_items; ++p) {
         int verdict[32];
@@ -300,6 +305,7 @@ extern "C" int step_launch(const double *action, int reset_all) {
         g.item_bad[it] = (uint8_t)verdict[0];
     }
 #endif
+    g_check_div += warp_emu::total_work()[0] - div0; g_check_sincos += warp_emu::total_work()[1] - sc0;
     // ---- k_rs_select ----
     for (int i = 0; i < n; ++i) select_one(i, tb, rs, out);
     return n_items;

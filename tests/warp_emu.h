@@ -66,11 +66,30 @@ struct Warp {
     const char *error = nullptr;
     std::function<void(int)> body;
     unsigned long long collectives = 0;
+    // optional cost model: a lane reports units of work of kind k (work()); between two collectives the warp pays the
+    // maximum over its lanes (lock-step execution of divergent lanes), summed into warp_work[k]
+    unsigned long long lane_work[W][2] = {}, warp_work[2] = {0, 0};
+    void settle() {
+        for (int k = 0; k < 2; ++k) {
+            unsigned long long m = 0;
+            for (int l = 0; l < W; ++l) { if (lane_work[l][k] > m) m = lane_work[l][k]; lane_work[l][k] = 0; }
+            warp_work[k] += m;
+        }
+    }
 };
+
+inline unsigned long long (&total_work())[2] {
+    static thread_local unsigned long long t[2] = {0, 0};
+    return t;
+}
 
 inline Warp *&current() {
     static thread_local Warp *w = nullptr;
     return w;
+}
+inline void work(int kind, int units) {
+    Warp *w = current();
+    if (w) w->lane_work[w->cur][kind] += (unsigned long long)units;
 }
 
 inline void to_lane(Warp *w, int l) {
@@ -133,6 +152,7 @@ inline const char *run(const std::function<void(int)> &body, unsigned long long 
             if (w.st[l] == Warp::WAITING) { ++waiting; if (first < 0) first = l; }
             else if (w.st[l] == Warp::DONE) ++done;
         }
+        w.settle();
         if (waiting == 0) break;
         if (done) { w.error = "a lane returned while others wait at a full-mask collective"; break; }
         uint64_t bits = 0;
@@ -153,6 +173,7 @@ inline const char *run(const std::function<void(int)> &body, unsigned long long 
         ++w.collectives;
     }
     current() = nullptr;
+    total_work()[0] += w.warp_work[0]; total_work()[1] += w.warp_work[1];
     if (n_collectives) *n_collectives = w.collectives;
     return w.error;
 }
