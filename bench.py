@@ -384,6 +384,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="scenes per GPU (default: the BASELINE cfg-3 size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--device-only", action="store_true", help="profiling runs: stop after the device-resident timing (no e2e, no CPU baseline, no JSON line)")
     ap.add_argument("--config", default="step", choices=["step", "rollout", "sac", "dlp", "cfg2", "image"],
                     help="step: BASELINE cfg 3 (default, the headline metric); rollout: cfg 4, PPO acting loop with the transformer policy")
     args = ap.parse_args()
@@ -468,6 +469,11 @@ def main():
     total_steps = sum_over_ranks(float(steps_local))
     value = total_steps / (ms * 1e-3)
 
+    if args.device_only:
+        if rank == 0:
+            print(json.dumps({"device_only": True, "value": value, "ms_per_step": ms / K}))
+        env.close()
+        return
     # ---- end-to-end through the host-buffer C ABI ---------------------------------------------------
     h_actions = actions[:, :, :].cpu().numpy()
     for k in range(W):

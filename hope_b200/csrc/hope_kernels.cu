@@ -45,18 +45,6 @@ namespace hope {
 #define HOPE_CHK_EDGE_EXIT 1
 #endif
 
-// k_observe, mask sweep: 1 = the per-ray screen loads are issued four rays at a time with the bounds of the batch start
-// (observe_body.inc; same step counts, fewer dependent L2 round trips).  Experimental, not yet measured.
-#ifndef HOPE_OBS_SCREEN_BATCH
-#define HOPE_OBS_SCREEN_BATCH 0
-#endif
-
-// k_observe as persistent warps: 0 = one block per two envs (shipped), B > 0 = at most B resident 64-thread blocks per SM (never
-// more than fit: the occupancy API decides) whose warps stride over the envs; 32 = as many as fit.  Experimental, not yet measured.
-#ifndef HOPE_OBS_PERSISTENT
-#define HOPE_OBS_PERSISTENT 0
-#endif
-
 // Work counters of an instrumented build (-DHOPE_STATS, profiles/tools/kernel_stats.py): where k_rs_check's rounds end
 // and how many (quadrant, edge) / (ray, action) items k_observe visits.  The default build contains none of this.
 #ifdef HOPE_STATS
@@ -97,22 +85,6 @@ __global__ void __launch_bounds__(ADV_THREADS, MINB) k_advance(int n, Pool pool,
 // =============================================================================================
 #include "observe.cuh"
 
-#if HOPE_OBS_PERSISTENT
-// Persistent warps: the grid is HOPE_OBS_PERSISTENT resident blocks per SM and every warp walks envs w, w + W, w + 2 W, ...
-// Why: with one env per warp and two warps per block a block's slot is held until its slower env is done, and ncu shows 41 %
-// active warps where the register and shared-memory limits allow 62 % (profiles/r01_ncu_full_summary_u.txt).  A warp that
-// never exits does not wait for its neighbour.  Same statements per env (observe_body.inc).  Experimental, not yet measured.
-__global__ void __launch_bounds__(64) k_observe(int n, Pool pool, EnvState st, Tables tb, hope_params par, hope_out out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    ObserveSmem &sm = reinterpret_cast<ObserveSmem *>(smem_raw)[warp_in_block];
-    const int total_warps = gridDim.x * (blockDim.x >> 5);
-    for (int env = blockIdx.x * (blockDim.x >> 5) + warp_in_block; env < n; env += total_warps) {
-#include "observe_body.inc"
-        __syncwarp();  // the next env reuses the warp's scratch
-    }
-}
-#else
 __global__ void __launch_bounds__(64) k_observe(int n, Pool pool, EnvState st, Tables tb, hope_params par, hope_out out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -121,7 +93,6 @@ __global__ void __launch_bounds__(64) k_observe(int n, Pool pool, EnvState st, T
     ObserveSmem &sm = reinterpret_cast<ObserveSmem *>(smem_raw)[warp_in_block];
 #include "observe_body.inc"
 }
-#endif  // HOPE_OBS_PERSISTENT
 
 // =============================================================================================
 // k_rs_enumerate: one thread per env.  46 candidate words -> admitted list -> heap pop order.
@@ -177,16 +148,12 @@ __global__ void __launch_bounds__(128) k_rs_walk(RsScratch rs, Tables tb, hope_p
 }
 
 #include "rs_check.cuh"
-// 1 = k_rs_check gives every warp two work items, one per half-warp (rs_check_pair.cuh; experimental, not yet measured)
-#ifndef HOPE_CHK_PAIR
-#define HOPE_CHK_PAIR 0
-#endif
-#if HOPE_CHK_PAIR
-#include "rs_check_pair.cuh"
-#endif
-// 1 = k_rs_check pools the line-pair tests of a round over the whole warp (rs_check_pooled.cuh; experimental, not yet measured)
+// 1 (shipped) = k_rs_check pools the line-pair tests of a round over the whole warp (rs_check_pooled.cuh): on B200 the step is
+// 9 % faster than with each lane walking its obstacle's edges alone (0), all outputs bit-identical
+// (profiles/r02_ab_variants.jsonl; the two-words-per-warp, persistent-k_observe and batched-screen variants of round 1
+// measured -3 %, +100 % and +20 % and were deleted).
 #ifndef HOPE_CHK_POOLED
-#define HOPE_CHK_POOLED 0
+#define HOPE_CHK_POOLED 1
 #endif
 #if HOPE_CHK_POOLED
 #include "rs_check_pooled.cuh"
@@ -208,76 +175,6 @@ __device__ __forceinline__ void stage_slot_async(WordSlot *dst, const WordSlot *
     __pipeline_commit();
 }
 
-#if HOPE_CHK_PAIR
-__device__ __forceinline__ CheckEnv load_check_env(int env, const Pool &pool, const EnvState &st, const Tables &tb, const hope_params &par) {
-    const int sid = st.scene[env];
-    const double *meta = pool.meta + (size_t)sid * META;
-    CheckEnv E;
-    E.q0x = st.pose[3 * env]; E.q0y = st.pose[3 * env + 1]; E.q0h = st.pose[3 * env + 2];
-    E.cg = st.cs[2 * env]; E.sg = -st.cs[2 * env + 1];  // cos(-h), sin(-h)  (reeds_shepp.py:47-48)
-    E.xmin = meta[M_BOUNDS]; E.xmax = meta[M_BOUNDS + 1]; E.ymin = meta[M_BOUNDS + 2]; E.ymax = meta[M_BOUNDS + 3];
-    E.maxc = tb.maxc; E.step = par.rs_step * tb.maxc;
-    E.nobs = pool.nobs[sid];
-    E.aabb = reinterpret_cast<const double4 *>(pool.aabb) + (size_t)sid * MAXO;
-    E.verts = reinterpret_cast<const double2 *>(pool.obs) + (size_t)sid * MAXE;
-    E.nvp = pool.nv + (size_t)sid * MAXO;
-    return E;
-}
-
-// asynchronous global -> shared copy of one WordSlot by a half-warp (16 bytes per lane per pass)
-__device__ __forceinline__ void stage_slot_async_half(WordSlot *dst, const WordSlot *src, int hl) {
-    const char *g = reinterpret_cast<const char *>(src);
-    char *sh = reinterpret_cast<char *>(dst);
-    for (int q = hl * 16; q < (int)sizeof(WordSlot); q += 16 * 16) __pipeline_memcpy_async(sh + q, g + q, 16);
-    __pipeline_commit();
-}
-
-// Two work items per warp: lanes 0-15 check item 2g, lanes 16-31 item 2g + 1 (rs_check_pair.cuh).
-__global__ void __launch_bounds__(CHK_WARPS * 32, HOPE_CHK_MINBLOCKS) k_rs_check(Pool pool, EnvState st, Tables tb, RsScratch rs, hope_params par) {
-    __shared__ WordSlot smem[CHK_WARPS][2][2];  // [buffer][half]; the next pair's plans stream in while this pair is sampled
-    const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
-    const int n_items = *rs.n_items, n_pairs = (n_items + 1) >> 1;
-    const int warps_total = gridDim.x * CHK_WARPS;
-    int pair = blockIdx.x * CHK_WARPS + warp_in_block, buf = 0;
-    // a half without an item (odd n_items, last pair) stages and reads the other half's item and reports nothing
-    if (pair < n_pairs) stage_slot_async_half(&smem[warp_in_block][0][half], rs.slots + min(2 * pair + half, n_items - 1), hl);
-    for (; pair < n_pairs; pair += warps_total, buf ^= 1) {
-        const int item = 2 * pair + half;
-        const bool have = item < n_items;
-        const int src = have ? item : n_items - 1;
-        const int next = pair + warps_total;
-        if (next < n_pairs) stage_slot_async_half(&smem[warp_in_block][buf ^ 1][half], rs.slots + min(2 * next + half, n_items - 1), hl);
-        const CheckEnv E = load_check_env(rs.items[src] >> 4, pool, st, tb, par);
-        if (next < n_pairs) __pipeline_wait_prior(1); else __pipeline_wait_prior(0);  // this pair's plans have landed
-        __syncwarp();
-        WordSlot &s = smem[warp_in_block][buf][half];
-        bool bad = false;
-        if (!__any_sync(HOPE_FULL_MASK, have && s.end_lx == 0.0)) {
-            bad = pair_is_bad(s, E, par, lane, have);
-        } else {  // a degenerate trailing-zero word in the pair (reeds_shepp.py:501-505): one word at a time, whole warp
-            for (int h = 0; h < 2; ++h) {
-                const int it = 2 * pair + h;
-                if (it >= n_items) break;
-                const CheckEnv Eh = load_check_env(rs.items[it] >> 4, pool, st, tb, par);
-                WordSlot &sh = smem[warp_in_block][buf][h];
-                bool b = false;
-                int chunk_base = 0;
-                for (;;) {
-                    b = chunk_is_bad(sh, Eh, par, lane);
-                    if (b || sh.total >= 0) break;
-                    chunk_base += RS_CHUNK;
-                    __syncwarp();
-                    if (lane == 0) walk_chunk(sh, sh.len, Eh.step, chunk_base);
-                    __syncwarp();
-                }
-                if (h == half) bad = b;
-            }
-        }
-        if (have && hl == 0) rs.item_bad[item] = bad ? 1 : 0;
-        __syncwarp();
-    }
-}
-#else
 __global__ void __launch_bounds__(CHK_WARPS * 32, HOPE_CHK_MINBLOCKS) k_rs_check(Pool pool, EnvState st, Tables tb, RsScratch rs, hope_params par) {
     __shared__ WordSlot smem[CHK_WARPS][2];  // double buffer: the next word's plan streams in while this one is sampled
 #if HOPE_CHK_POOLED
@@ -327,7 +224,6 @@ __global__ void __launch_bounds__(CHK_WARPS * 32, HOPE_CHK_MINBLOCKS) k_rs_check
         __syncwarp();
     }
 }
-#endif  // HOPE_CHK_PAIR
 
 __global__ void __launch_bounds__(128) k_rs_select(int n, Tables tb, RsScratch rs, hope_out out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -734,17 +630,7 @@ int launch_range(hope_ctx *ctx, const double *d_action, const hope_out &out_all,
         if (stages & HOPE_STAGE_OBSERVE) {
             const int wpb = OBS_THREADS / 32;
             prof_mark(ctx, 1, so);
-#if HOPE_OBS_PERSISTENT
-            static int obs_bps = 0;  // resident blocks per SM (occupancy of this build), capped by the switch
-            if (!obs_bps) {
-                int fit = 0;
-                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, k_observe, OBS_THREADS, wpb * sizeof(ObserveSmem)));
-                obs_bps = max(1, min(fit, HOPE_OBS_PERSISTENT));
-            }
-            k_observe<<<min((n + wpb - 1) / wpb, ctx->sm_count * obs_bps), OBS_THREADS, wpb * sizeof(ObserveSmem), so>>>(n, pool, st, tb, ctx->par, out);
-#else
             k_observe<<<(n + wpb - 1) / wpb, OBS_THREADS, wpb * sizeof(ObserveSmem), so>>>(n, pool, st, tb, ctx->par, out);
-#endif
             prof_mark(ctx, 1, so);
             ctx->launches++;
         }

@@ -33,9 +33,6 @@ using std::min;
 
 #include "warp_emu.h"
 
-#ifndef HOPE_OBS_SCREEN_BATCH
-#define HOPE_OBS_SCREEN_BATCH 0
-#endif
 
 #include "../include/hope_b200.h"
 #include "../hope_b200/csrc/hope_device.cuh"

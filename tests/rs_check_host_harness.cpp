@@ -41,7 +41,7 @@ using std::min;
 #define HOPE_CHK_EDGE_EXIT 1
 #endif
 #ifndef HOPE_CHK_POOLED
-#define HOPE_CHK_POOLED 0
+#define HOPE_CHK_POOLED 1
 #endif
 
 namespace hope {
@@ -53,7 +53,6 @@ static inline double4 ld_aabb(const double4 *p) { return *p; }  // the kernel's 
 #include "../hope_b200/csrc/rs_words.cuh"
 #include "../hope_b200/csrc/rs_walk.cuh"
 #include "../hope_b200/csrc/rs_check.cuh"
-#include "../hope_b200/csrc/rs_check_pair.cuh"
 #include "../hope_b200/csrc/rs_check_pooled.cuh"
 }  // namespace hope
 
@@ -154,31 +153,4 @@ extern "C" int rs_check_host(const double *q, double maxc, double rs_step, int w
     const int v = whole_warp_verdict(P, par, n_collectives);
     if (n_samples) *n_samples = P.s.total;
     return v;
-}
-
-// Two words in one warp (rs_check_pair.cuh).  Arrays of two: q[2][6], word[2], bounds[2][4], nobs[2], obs[2][MAXO][4][2],
-// nv[2][MAXO]; have_second = 0 leaves the upper half without an item.  verdict[2] as above; returns 0 or the error.
-extern "C" int rs_check_pair_host(const double *q, double maxc, double rs_step, const int *word, const double *bounds, const int *nobs,
-                                  const double *obs, const uint8_t *nv, const double *box_x, const double *box_y, int have_second,
-                                  int *verdict, unsigned long long *n_collectives) {
-    using namespace hope;
-    static Prepared P[2];
-    const int stride_obs = MAXO * MAXV * 2;
-    for (int h = 0; h < (have_second ? 2 : 1); ++h)
-        if (prepare(P[h], q + 6 * h, maxc, rs_step, word[h], bounds + 4 * h, nobs[h], obs + (size_t)stride_obs * h, nv + MAXO * h, 0)) return -1;
-    const hope_params par = make_params(box_x, box_y, rs_step);
-    int lane_verdict[32];
-    const char *err = warp_emu::run([&](int lane) {
-        const int half = lane >> 4;
-        const bool have = half == 0 || have_second;
-        Prepared &mine = P[have ? half : 0];  // a half without an item reads the other half's slot, like the kernel
-        lane_verdict[lane] = pair_is_bad(mine.s, mine.E, par, lane, have) ? 1 : 0;
-    }, n_collectives);
-    if (report(err)) return -2;
-    for (int h = 0; h < 2; ++h) {
-        for (int l = 1; l < 16; ++l)
-            if (lane_verdict[16 * h + l] != lane_verdict[16 * h]) return -3;
-        verdict[h] = lane_verdict[16 * h];
-    }
-    return 0;
 }

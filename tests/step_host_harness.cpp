@@ -1,7 +1,7 @@
 // CPU harness for tests/test_step_host.py: the whole env step as the kernels run it, chained on the host for test purposes —
 // k_advance (advance_body.inc, 32 envs per emulated warp), k_observe (observe_body.inc, one emulated warp per env),
-// k_rs_enumerate's enumerate_env, k_rs_walk's plan_word, k_rs_check (rs_check.cuh, or with -DHOPE_CHK_PAIR=1 two work items
-// per warp through rs_check_pair.cuh in work-list order, like the pair kernel) and k_rs_select (rs_select_body.inc) — with
+// k_rs_enumerate's enumerate_env, k_rs_walk's plan_word, k_rs_check (rs_check_pooled.cuh, or with -DHOPE_CHK_POOLED=0 the per-lane edge
+// loop of rs_check.cuh) and k_rs_select (rs_select_body.inc) — with
 // the state arrays the kernels keep between steps.  tests/test_step_host.py runs it in lock step with the C oracle on
 // generated scenes, the way tests/test_gpu_parity.py does with the real kernels on the GPU.  This is test plumbing around
 // the product's device source, not a CPU path of the product (nothing under hope_b200/ can reach it).
@@ -40,9 +40,6 @@ using std::min;
 static inline double __drcp_rn(double a) { warp_emu::work(0, 1); return 1.0 / a; }
 #define sincos(a, s, c) (warp_emu::work(1, 1), ::sincos(a, s, c))
 
-#ifndef HOPE_OBS_SCREEN_BATCH
-#define HOPE_OBS_SCREEN_BATCH 0
-#endif
 
 #include "../include/hope_b200.h"
 #include "../hope_b200/csrc/hope_device.cuh"
@@ -50,11 +47,8 @@ static inline double __drcp_rn(double a) { warp_emu::work(0, 1); return 1.0 / a;
 #ifndef HOPE_CHK_EDGE_EXIT
 #define HOPE_CHK_EDGE_EXIT 1
 #endif
-#ifndef HOPE_CHK_PAIR
-#define HOPE_CHK_PAIR 0
-#endif
 #ifndef HOPE_CHK_POOLED
-#define HOPE_CHK_POOLED 0
+#define HOPE_CHK_POOLED 1
 #endif
 
 namespace hope {
@@ -66,7 +60,6 @@ static inline double4 ld_aabb(const double4 *p) { return *p; }  // the kernel's 
 #include "../hope_b200/csrc/rs_enumerate.cuh"
 #include "../hope_b200/csrc/rs_walk.cuh"
 #include "../hope_b200/csrc/rs_check.cuh"
-#include "../hope_b200/csrc/rs_check_pair.cuh"
 #include "../hope_b200/csrc/rs_check_pooled.cuh"
 
 static void advance_one(const int n, const int gi, const int lane, AdvanceSmem &sm, Pool pool, EnvState st, const double *action, hope_params par,
@@ -242,44 +235,6 @@ extern "C" int step_launch(const double *action, int reset_all) {
     // ---- k_rs_check ----
     unsigned long long votes = 0;
     const unsigned long long div0 = warp_emu::total_work()[0], sc0 = warp_emu::total_work()[1];
-#if HOPE_CHK_PAIR
-    for (int p = 0; 2 * p < n_items; ++p) {
-        int verdict[32];
-        const int it0 = 2 * p, it1 = std::min(2 * p + 1, n_items - 1);
-        const bool have1 = 2 * p + 1 < n_items;
-        const CheckEnv E0 = check_env(g.items[it0] >> 4), E1 = check_env(g.items[it1] >> 4);
-        bool zero = slots[it0].end_lx == 0.0 || (have1 && slots[it1].end_lx == 0.0);
-        if (!zero) {
-            const char *err = warp_emu::run([&](int lane) {
-                const int half = lane >> 4;
-                verdict[lane] = pair_is_bad(half ? slots[it1] : slots[it0], half ? E1 : E0, g.par, lane, half == 0 || have1) ? 1 : 0;
-            }, &votes);
-            if (err) return fail(err);
-            g_check_votes += votes; ++g_check_runs;
-            g.item_bad[it0] = (uint8_t)verdict[0];
-            if (have1) g.item_bad[it1] = (uint8_t)verdict[16];
-            continue;
-        }
-        for (int h = 0; h < (have1 ? 2 : 1); ++h) {  // a trailing-zero word in the pair: one word at a time, whole warp
-            WordSlot &s = slots[2 * p + h];
-            const CheckEnv &E = h ? E1 : E0;
-            const char *err = warp_emu::run([&](int lane) {
-                bool bad = false; int chunk_base = 0;
-                for (;;) {
-                    bad = chunk_is_bad(s, E, g.par, lane);
-                    if (bad || s.total >= 0) break;
-                    chunk_base += RS_CHUNK; __syncwarp();
-                    if (lane == 0) walk_chunk(s, s.len, E.step, chunk_base);
-                    __syncwarp();
-                }
-                verdict[lane] = bad ? 1 : 0;
-            }, &votes);
-            if (err) return fail(err);
-            g_check_votes += votes; ++g_check_runs;
-            g.item_bad[2 * p + h] = (uint8_t)verdict[0];
-        }
-    }
-#else
     for (int it = 0; it < n_items; ++it) {
         int verdict[32];
         WordSlot &s = slots[it];
@@ -304,7 +259,6 @@ extern "C" int step_launch(const double *action, int reset_all) {
         g_check_votes += votes; ++g_check_runs;
         g.item_bad[it] = (uint8_t)verdict[0];
     }
-#endif
     g_check_div += warp_emu::total_work()[0] - div0; g_check_sincos += warp_emu::total_work()[1] - sc0;
     // ---- k_rs_select ----
     for (int i = 0; i < n; ++i) select_one(i, tb, rs, out);

@@ -18,17 +18,16 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.fixture(scope="module", params=[0, 1], ids=["shipped", "batched_screen"])
-def harness(request, tmp_path_factory):
-    """params: HOPE_OBS_SCREEN_BATCH = 0 (the shipped mask screen) and 1 (experimental: screen loads four rays at a time)."""
+@pytest.fixture(scope="module")
+def harness(tmp_path_factory):
     gxx = shutil.which("g++")
     if gxx is None:
         pytest.skip("g++ not available")
-    out = str(tmp_path_factory.mktemp("observe") / f"observe_host_{request.param}.so")
+    out = str(tmp_path_factory.mktemp("observe") / "observe_host.so")
     env = dict(os.environ)
     env.pop("CC", None); env.pop("CXX", None)
     subprocess.check_call([gxx, "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-I", os.path.join(HERE, "host_stubs"),
-                           f"-DHOPE_OBS_SCREEN_BATCH={request.param}", "-o", out, os.path.join(HERE, "observe_host_harness.cpp")], env=env)
+                           "-o", out, os.path.join(HERE, "observe_host_harness.cpp")], env=env)
     lib = C.CDLL(out)
     lib.observe_host.restype = C.c_int
     lib.observe_host.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 11 + [C.c_double] + [C.c_void_p] * 3

@@ -5,7 +5,8 @@ compiled with g++ by tests/rs_check_host_harness.cpp on top of a 32-fiber warp e
 flags lanes that wait at different collectives or leave early, like synccheck).  The fixture tests/golden/traj_valid.npz
 holds `CarParking.is_traj_valid` verdicts (car_parking_base.py:452-534) recorded from the unmodified reference by
 oracle/make_traj_valid_golden.py: scene, start pose, which word of calc_all_paths, number of samples, verdict.
-Both vote placements (HOPE_CHK_EDGE_EXIT = 1, the shipped one, and 0) and the trailing-zero path are covered.
+The shipped pooled test (rs_check_pooled.cuh), both vote placements of the per-lane edge loop (HOPE_CHK_EDGE_EXIT = 1 and 0)
+and the trailing-zero path are covered.
 """
 import ctypes as C
 import math
@@ -21,10 +22,10 @@ MAXC = math.tan(0.75) / 2.8   # car_parking_base.py:422
 RS_STEP = 0.1                 # :424
 
 
-@pytest.fixture(scope="module", params=[(1, 0), (0, 0), (1, 1)], ids=["edge_exit", "obstacle_exit", "pooled"])
+@pytest.fixture(scope="module", params=[(1, 1), (1, 0), (0, 0)], ids=["pooled", "edge_exit", "obstacle_exit"])
 def harness(request, tmp_path_factory):
-    """params: (HOPE_CHK_EDGE_EXIT, HOPE_CHK_POOLED).  edge_exit is the shipped build; obstacle_exit the former vote placement;
-    pooled the experimental rs_check_pooled.cuh (line-pair tests of a round pooled over the warp)."""
+    """params: (HOPE_CHK_EDGE_EXIT, HOPE_CHK_POOLED).  pooled is the shipped build (rs_check_pooled.cuh: line-pair tests of a round
+    pooled over the warp); edge_exit / obstacle_exit are the per-lane edge loops of rs_check.cuh with either vote placement."""
     gxx = shutil.which("g++")
     if gxx is None:
         pytest.skip("g++ not available")
@@ -97,53 +98,3 @@ def test_trailing_zero_path_gives_the_same_verdicts(harness, golden, box):
         a = run_call(harness, g, box, int(i), 0)
         b = run_call(harness, g, box, int(i), 1)
         assert a[0] in (0, 1) and b[0] == a[0], (int(i), a, b)
-
-
-def _pair_args(g, box, i, j):
-    qs, bounds, obs, nvs, nobs, words = [], [], [], [], [], []
-    for c in (i, j):
-        sc = int(g["call_scene"][c])
-        qs.append(np.concatenate([g["call_pose"][c], g["scene_dest"][sc]]))
-        bounds.append(g["scene_bounds"][sc]); obs.append(g["scene_obs"][sc])
-        nv = g["scene_nverts"][sc].astype(np.uint8)
-        nvs.append(nv); nobs.append(int((nv > 0).sum())); words.append(int(g["call_word"][c]))
-    f8 = lambda a: np.ascontiguousarray(np.array(a), dtype=np.float64)
-    return (f8(qs), np.array(words, dtype=np.int32), f8(bounds), np.array(nobs, dtype=np.int32), f8(obs),
-            np.ascontiguousarray(np.array(nvs), dtype=np.uint8))
-
-
-def test_two_words_per_warp_give_the_reference_verdicts(request, harness, golden, box):
-    """rs_check_pair.cuh (HOPE_CHK_PAIR, off by default): lanes 0-15 check one recorded word, lanes 16-31 another, in one
-    instruction stream.  Pairs of consecutive calls (mostly the same env's next word, as the work list hands them to a
-    warp), pairs from different scenes with different obstacle counts, and a lone word with an idle upper half."""
-    if "edge_exit" not in request.node.name:
-        pytest.skip("rs_check_pair.cuh does not depend on the other switches: one build is enough")
-    g = golden
-    lib = harness
-    lib.rs_check_pair_host.restype = C.c_int
-    lib.rs_check_pair_host.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                       C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_ulonglong)]
-    n = len(g["call_valid"])
-    rng = np.random.default_rng(5)
-    valid_idx = np.flatnonzero(g["call_valid"] == 1)
-    pairs = [(i, i + 1) for i in range(0, n - 1)]                                       # consecutive calls, both alignments
-    pairs += [(int(a), int(b)) for a, b in zip(rng.integers(0, n, 2000), rng.integers(0, n, 2000))]  # unrelated scenes
-    pairs += [(int(a), int(b)) for a, b in zip(valid_idx[:-1], valid_idx[1:])]           # two clean words: all rounds in both halves
-    pairs += [(int(a), int(b)) for a, b in zip(valid_idx, rng.integers(0, n, len(valid_idx)))]
-    wrong = 0
-    for i, j in pairs:
-        q, words, bounds, nobs, obs, nv = _pair_args(g, box, i, j)
-        verdict = np.zeros(2, dtype=np.int32)
-        nc = C.c_ulonglong(0)
-        rc = lib.rs_check_pair_host(q.ctypes.data, MAXC, RS_STEP, words.ctypes.data, bounds.ctypes.data, nobs.ctypes.data, obs.ctypes.data,
-                                    nv.ctypes.data, box[0].ctypes.data, box[1].ctypes.data, 1, verdict.ctypes.data, C.byref(nc))
-        assert rc == 0, f"pair ({i}, {j}): harness error {rc}"
-        want = [0 if g["call_valid"][i] else 1, 0 if g["call_valid"][j] else 1]
-        wrong += int(list(verdict) != want)
-    assert wrong == 0, f"{wrong} of {len(pairs)} pairs differ from the reference's verdicts"
-    for i in list(valid_idx[:40]) + list(range(0, 200, 5)):  # a lone word: the upper half has no item
-        q, words, bounds, nobs, obs, nv = _pair_args(g, box, int(i), int(i))
-        verdict = np.full(2, 7, dtype=np.int32)
-        rc = lib.rs_check_pair_host(q.ctypes.data, MAXC, RS_STEP, words.ctypes.data, bounds.ctypes.data, nobs.ctypes.data, obs.ctypes.data,
-                                    nv.ctypes.data, box[0].ctypes.data, box[1].ctypes.data, 0, verdict.ctypes.data, None)
-        assert rc == 0 and verdict[0] == (0 if g["call_valid"][i] else 1) and verdict[1] == 0

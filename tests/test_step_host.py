@@ -1,8 +1,8 @@
 """The whole env step as the kernels run it, chained on the CPU and stepped in lock step with the C oracle.
 
 tests/step_host_harness.cpp strings the product's device source together for test purposes — k_advance's body (32 envs per
-emulated warp), k_observe's body (a warp per env), enumerate_env, plan_word, k_rs_check's warp code (one word per warp, or
-with HOPE_CHK_PAIR=1 two work items per warp in work-list order like the pair kernel) and k_rs_select's body — and keeps
+emulated warp), k_observe's body (a warp per env), enumerate_env, plan_word, k_rs_check's warp code (the shipped pooled line-pair
+test, or with HOPE_CHK_POOLED=0 the per-lane edge loop) and k_rs_select's body — and keeps
 the state arrays between steps.  This is the CPU counterpart of tests/test_gpu_parity.py::test_full_step_mixed_levels_vs_oracle:
 generated scenes of all three levels, uniform random actions, every output of every step against the oracle (which is
 pinned on the reference's traces by tests/test_oracle_golden.py).  Both run on the host libm, so floats agree much closer
@@ -19,15 +19,15 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def build(tmp, pair, screen_batch=0, pooled=0, max_obs=16):
+def build(tmp, pooled=1, max_obs=16):
     gxx = shutil.which("g++")
     if gxx is None:
         pytest.skip("g++ not available")
-    out = str(tmp / f"step_host_{pair}_{screen_batch}_{pooled}_{max_obs}.so")
+    out = str(tmp / f"step_host_{pooled}_{max_obs}.so")
     env = dict(os.environ)
     env.pop("CC", None); env.pop("CXX", None)
     subprocess.check_call([gxx, "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-I", os.path.join(HERE, "host_stubs"),
-                           f"-DHOPE_CHK_PAIR={pair}", f"-DHOPE_OBS_SCREEN_BATCH={screen_batch}", f"-DHOPE_CHK_POOLED={pooled}", f"-DHOPE_MAX_OBS={max_obs}", "-o", out, os.path.join(HERE, "step_host_harness.cpp")], env=env)
+                           f"-DHOPE_CHK_POOLED={pooled}", f"-DHOPE_MAX_OBS={max_obs}", "-o", out, os.path.join(HERE, "step_host_harness.cpp")], env=env)
     lib = C.CDLL(out)
     lib.step_create.argtypes = [C.c_int] + [C.c_void_p] * 10
     lib.step_set_scene.argtypes = [C.c_int] + [C.c_void_p] * 5
@@ -49,7 +49,7 @@ def read(lib, n):
     return o
 
 
-def _run(lib, sc, steps, pair, min_steps, min_words, min_found):
+def _run(lib, sc, steps, min_steps, min_words, min_found):
     from hope_b200 import capi, tables
     from oracle import parking_oracle as po
     par = capi.Params()
@@ -74,37 +74,37 @@ def _run(lib, sc, steps, pair, min_steps, min_words, min_found):
     olib = po.lib(int(np.asarray(sc["nverts"]).shape[1]))
     olib.orc_set_py_sum(0)
     try:
-        _lockstep(lib, orc, n, steps, pair, min_steps, min_words, min_found)
+        _lockstep(lib, orc, n, steps, min_steps, min_words, min_found)
     finally:
         olib.orc_set_py_sum(1)  # other tests replay the 3.12 recording
 
 
-MODES = [(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1)]
-MODE_IDS = ["shipped", "two_words_per_warp", "batched_mask_screen", "pooled_line_pairs"]
+MODES = [1, 0]
+MODE_IDS = ["shipped_pooled_line_pairs", "per_lane_edge_loop"]
 
 
-@pytest.mark.parametrize("pair,screen_batch,pooled", MODES, ids=MODE_IDS)
-def test_full_step_lockstep_with_the_oracle(tmp_path_factory, pair, screen_batch, pooled):
+@pytest.mark.parametrize("pooled", MODES, ids=MODE_IDS)
+def test_full_step_lockstep_with_the_oracle(tmp_path_factory, pooled):
     from hope_b200.batched_env import generate_scenes
-    lib = build(tmp_path_factory.mktemp("step_host"), pair, screen_batch, pooled)
+    lib = build(tmp_path_factory.mktemp("step_host"), pooled)
     n, steps, seed = 96, 40, 321
     if os.environ.get("HOPE_STEP_SOAK"):  # longer run by hand: HOPE_STEP_SOAK="envs,steps,seed"
         n, steps, seed = (int(v) for v in os.environ["HOPE_STEP_SOAK"].split(","))
-    _run(lib, generate_scenes(n, "mix", seed), steps, pair, 2500, 3000, 50)
+    _run(lib, generate_scenes(n, "mix", seed), steps, 2500, 3000, 50)
 
 
-@pytest.mark.parametrize("pair,screen_batch,pooled", MODES, ids=MODE_IDS)
-def test_full_step_lockstep_on_dragon_lake_scenes(tmp_path_factory, golden_dir, pair, screen_batch, pooled):
+@pytest.mark.parametrize("pooled", MODES, ids=MODE_IDS)
+def test_full_step_lockstep_on_dragon_lake_scenes(tmp_path_factory, golden_dir, pooled):
     """The same on the 128-ring build (-DHOPE_MAX_OBS=128) with Dragon Lake Parking scenes (31-119 obstacle rings per scene,
     tests/golden/dlp_cases.npz): long obstacle loops, several queue groups per round in the pooled variant."""
     from hope_b200 import dlp
-    lib = build(tmp_path_factory.mktemp("step_host_dlp"), pair, screen_batch, pooled, max_obs=128)
+    lib = build(tmp_path_factory.mktemp("step_host_dlp"), pooled, max_obs=128)
     cases = dlp.cases_from_fixture(np.load(os.path.join(golden_dir, "dlp_cases.npz")))
     sc = dlp.prepare_scenes(cases, np.arange(48) % 16, seed=11)
-    _run(lib, sc, 20, pair, 500, 50, 0)  # the recorded starts are mostly farther than 10 m from the slot: few searches
+    _run(lib, sc, 20, 500, 50, 0)  # the recorded starts are mostly farther than 10 m from the slot: few searches
 
 
-def _lockstep(lib, orc, n, steps, pair, min_steps, min_words, min_found):
+def _lockstep(lib, orc, n, steps, min_steps, min_words, min_found):
     assert lib.step_launch(None, 1) >= 0
     ref = orc.reset_step()
     out = read(lib, n)
@@ -140,7 +140,7 @@ def _lockstep(lib, orc, n, steps, pair, min_steps, min_words, min_found):
                 worst[key] = max(worst.get(key, 0.0), float(d.max()))
         compared += int(live.sum()); words += n_items; found += int(out["rs_found"][live].sum())
         live &= ref["status"] == 1  # the oracle env has no auto-reset: stop comparing finished episodes
-    print(f"\nfull step on the CPU ({'two words' if pair else 'one word'} per warp): {compared} env-steps, {words} tried words, "
+    print(f"\nfull step on the CPU: {compared} env-steps, {words} tried words, "
           f"{found} paths found ({other_word} with another of two equal-length words, {found_flips} found/not-found flips), worst |diff| {worst}")
     assert compared >= min_steps and words >= min_words and found >= min_found and other_word <= max(2, found // 20), (compared, words, found, other_word)
     assert found_flips <= max(2, compared // 5000), found_flips
