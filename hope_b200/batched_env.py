@@ -16,7 +16,7 @@ import ctypes as C
 
 import numpy as np
 
-from . import capi, tables
+from . import capi, refconfig, tables
 
 LEVELS = {"Normal": 0, "Complex": 1, "Extrem": 2}
 _NP = {C.c_double: np.float64, C.c_uint8: np.uint8, C.c_int32: np.int32}
@@ -44,10 +44,13 @@ def generate_scenes(n, level="Normal", seed=42, nthreads=0, max_obs=16):
 
 class BatchedParkingEnv(object):
     def __init__(self, n_envs, scenes=None, pool_size=None, level="Normal", seed=42, device=0, auto_reset=True,
-                 params=None, device_scenes=False, max_obs=None, use_img_observation=False):
+                 params=None, device_scenes=False, max_obs=None, use_img_observation=False, config=None):
         """scenes: dict of host arrays (start/dest/bounds/obs/nverts) to upload as the pool; None -> generate
         `pool_size` (default 2 n) scenes of `level` on the host, or with device_scenes=True on the GPU
-        (then finished envs also get a fresh device-generated scene instead of cycling the pool)."""
+        (then finished envs also get a fresh device-generated scene instead of cycling the pool).
+        config: a configs snapshot (refconfig.from_module / defaults); None -> refconfig.load(), i.e. the caller's own
+        `configs` module when one is importable, so that edits to the reference's configs.py keep taking effect.
+        params: hope_params fields that override the snapshot (e.g. {'tolerant_time': 50})."""
         import torch
         if not torch.cuda.is_available():
             raise capi.HopeError("BatchedParkingEnv needs a CUDA device; there is no CPU path")
@@ -63,8 +66,16 @@ class BatchedParkingEnv(object):
             scenes = generate_scenes(pool_size, level, seed, max_obs=max_obs)
         self.scenes = scenes
         self.pool_size = int(scenes["start"].shape[0]) if scenes is not None else int(pool_size or self.n)
+        self.config = refconfig.validate(config or refconfig.load())
         self.params = capi.Params()
         capi.check(self.lib.hope_default_params(C.byref(self.params)))
+        for k, v in refconfig.step_params(self.config).items():
+            if isinstance(v, list):
+                arr = getattr(self.params, k)
+                for q, x in enumerate(v):
+                    arr[q] = x
+            else:
+                setattr(self.params, k, v)
         self.params.auto_reset = 1 if auto_reset else 0
         if device_scenes:
             self.params.regen_on_reset = 1
@@ -74,7 +85,7 @@ class BatchedParkingEnv(object):
             setattr(self.params, k, v)
         self.ctx = C.c_void_p()
         capi.check(self.lib.hope_create(C.byref(self.ctx), device, self.n, self.pool_size, C.byref(self.params)), self.ctx)
-        tb = tables.host_tables()
+        tb = tables.host_tables(self.config)
         capi.check(self.lib.hope_upload_tables(self.ctx, *[tb[k].ctypes.data for k in
                                                             ("ray_a", "ray_b", "lidar_base", "mask_base", "dist_star", "w_lo", "w_hi")]), self.ctx)
         if scenes is not None:
@@ -85,6 +96,11 @@ class BatchedParkingEnv(object):
         self.out = {}
         self._out_struct = capi.Out()
         self.use_img = bool(use_img_observation)
+        if self.use_img:
+            if not refconfig.image_supported(self.config):
+                raise capi.HopeError("image observation: k_render is compiled for WIN 500x500, OBS 256x256, K 12, TRAJ_RENDER_LEN 20 "
+                                     "(car_parking_base.py:301-350); configs.py asks for another raster geometry")
+            self.set_palette(refconfig.palette(self.config))
         self.default_stages = capi.STAGE_ALL | (capi.STAGE_IMAGE if self.use_img else 0)
         for name, ct, shape in capi.OUT_FIELDS:
             if name == "img" and not self.use_img:
@@ -140,14 +156,18 @@ class BatchedParkingEnv(object):
                                        self._stream()), self.ctx)
         return self._obs()
 
-    def step(self, actions, stages=None):
-        """actions: (N,2) float64 CUDA tensor in [-1,1] (steer, speed), as the policy emits them."""
+    def step(self, actions, stages=None, raw_action=False):
+        """actions: (N,2) float64 CUDA tensor in [-1,1] (steer, speed), as the policy emits them (raw_action=True: physical
+        [steer rad, speed m/s] as CarParking.step takes them); None = a step without motion (CarParking.step(None))."""
         t = self.torch
         stages = self.default_stages if stages is None else stages
-        if not (isinstance(actions, t.Tensor) and actions.is_cuda and actions.dtype == t.float64 and actions.is_contiguous()
-                and tuple(actions.shape) == (self.n, 2)):
+        if raw_action:
+            stages |= capi.STAGE_RAW_ACTION
+        if actions is not None and not (isinstance(actions, t.Tensor) and actions.is_cuda and actions.dtype == t.float64 and actions.is_contiguous()
+                                        and tuple(actions.shape) == (self.n, 2)):
             raise capi.HopeError("step() expects a contiguous float64 CUDA tensor of shape (n_envs, 2)")
-        capi.check(self.lib.hope_step(self.ctx, actions.data_ptr(), C.byref(self._out_struct), stages, self._stream()), self.ctx)
+        capi.check(self.lib.hope_step(self.ctx, actions.data_ptr() if actions is not None else None, C.byref(self._out_struct), stages,
+                                      self._stream()), self.ctx)
         return self._obs(), self.out["reward"], self.out["done"], self._info()
 
     def step_kinematics_collision(self, actions):
@@ -175,13 +195,19 @@ class BatchedParkingEnv(object):
             setattr(st, name, self._host[name].data_ptr())
         return st
 
-    def step_host(self, actions, stages=None, outputs=HOST_DEFAULT):
-        """actions: (N,2) float64 numpy array on the host.  Copies it in, steps, copies `outputs`
-        back into pinned host buffers, synchronises.  Returns dict of numpy views."""
+    def step_host(self, actions, stages=None, outputs=HOST_DEFAULT, raw_action=False):
+        """actions: (N,2) float64 numpy array on the host: the policy's output in [-1,1]^2 (CarParkingWrapper.step), or with
+        raw_action=True the physical [steer, speed] CarParking.step takes; None = a step without motion (CarParking.step(None)).
+        Copies it in, steps, copies `outputs` back into pinned host buffers, synchronises.  Returns dict of numpy views."""
         st = self._host_buffers(outputs)
         stages = (capi.STAGE_ALL | (capi.STAGE_IMAGE if "img" in outputs else 0)) if stages is None else stages
-        self._host["action"].numpy()[...] = actions
-        capi.check(self.lib.hope_step_host(self.ctx, self._host["action"].data_ptr(), C.byref(st), stages), self.ctx)
+        if raw_action:
+            stages |= capi.STAGE_RAW_ACTION
+        ptr = None
+        if actions is not None:
+            self._host["action"].numpy()[...] = actions
+            ptr = self._host["action"].data_ptr()
+        capi.check(self.lib.hope_step_host(self.ctx, ptr, C.byref(st), stages), self.ctx)
         return {k: self._host[k].numpy() for k in outputs}
 
     def reset_host(self, scene_ids=None, outputs=HOST_DEFAULT):

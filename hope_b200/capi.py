@@ -5,7 +5,7 @@ import os
 from . import build as _build
 
 MAX_OBS, MAX_VERTS, N_LIDAR, N_ACTION, N_MASK_ITER, N_UPSAMPLE, RS_MAX_SEG = 16, 4, 120, 42, 10, 1200, 5
-STAGE_ADVANCE, STAGE_OBSERVE, STAGE_RS, STAGE_ALL, STAGE_IMAGE = 1, 2, 4, 7, 8
+STAGE_ADVANCE, STAGE_OBSERVE, STAGE_RS, STAGE_ALL, STAGE_IMAGE, STAGE_RAW_ACTION = 1, 2, 4, 7, 8, 16
 IMG_C, IMG_HW, N_COLOR = 3, 64, 25
 CONTINUE, ARRIVED, COLLIDED, OUTBOUND, OUTTIME = 1, 2, 3, 4, 5
 RS_S, RS_L, RS_R, RS_NONE = 0, 1, 2, 255

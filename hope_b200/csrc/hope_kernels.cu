@@ -72,8 +72,9 @@ __device__ __forceinline__ double4 ld_aabb(const double4 *p) {  // read-only pat
 // 148 SMs within 1 % (512 blocks of 128 leave SMs with 3 or 4).
 template <int MINB>
 __global__ void __launch_bounds__(ADV_THREADS, MINB) k_advance(int n, Pool pool, EnvState st, const double *__restrict__ action,
-                                                       hope_params par, hope_out out, int reset_all, int reset_stride) {
+                                                       hope_params par, hope_out out, int reset_all, int reset_stride, int raw_action_flag) {
     __shared__ AdvanceSmem smem[ADV_THREADS / 32];
+    const bool raw_action = raw_action_flag != 0;
     const int lane = threadIdx.x & 31;
     AdvanceSmem &sm = smem[threadIdx.x >> 5];
     const int gi = blockIdx.x * blockDim.x + threadIdx.x;
@@ -497,6 +498,11 @@ struct hope_ctx {
     unsigned hg_stages = 0;
     unsigned long long hg_launches = 0;
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
+    // The device API (hope_reset / hope_step / hope_planner_actions) is asynchronous on the CALLER's stream, the host API
+    // runs on the context's own non-blocking streams: the last device-API call leaves an event here and the host API
+    // waits for it, so the two can be mixed without an explicit synchronisation in between.
+    cudaEvent_t ev_dev = nullptr;
+    bool dev_pending = false;
     unsigned long long launches = 0;
     bool profile = false;
     std::vector<cudaEvent_t> prof_events[8];  // begin/end pairs per kernel
@@ -604,10 +610,11 @@ int launch_range(hope_ctx *ctx, const double *d_action, const hope_out &out_all,
     if (do_advance) {
         prof_mark(ctx, 0, s);
         const int adv_blocks = (n + ADV_THREADS - 1) / ADV_THREADS;
+        const int raw = (stages & HOPE_STAGE_RAW_ACTION) ? 1 : 0;
         if (adv_blocks > 6 * ctx->sm_count)  // more than one wave at 6 blocks per SM
-            k_advance<8><<<adv_blocks, ADV_THREADS, 0, s>>>(n, pool, st, act, ctx->par, out, reset_all, regen ? 0 : ctx->n);
+            k_advance<8><<<adv_blocks, ADV_THREADS, 0, s>>>(n, pool, st, act, ctx->par, out, reset_all, regen ? 0 : ctx->n, raw);
         else
-            k_advance<6><<<adv_blocks, ADV_THREADS, 0, s>>>(n, pool, st, act, ctx->par, out, reset_all, regen ? 0 : ctx->n);
+            k_advance<6><<<adv_blocks, ADV_THREADS, 0, s>>>(n, pool, st, act, ctx->par, out, reset_all, regen ? 0 : ctx->n, raw);
         prof_mark(ctx, 0, s);
         ctx->launches++;
     }
@@ -683,6 +690,18 @@ int launch_step(hope_ctx *ctx, const double *d_action, const hope_out &out, unsi
     return launch_range(ctx, d_action, out, stages, reset_all, s, 0, 0, 0, ctx->n);
 }
 
+// device API epilogue: remember where the caller's stream is, for a host-API call that may follow
+int mark_device_call(hope_ctx *ctx, cudaStream_t s) {
+    CK(cudaEventRecord(ctx->ev_dev, s));
+    ctx->dev_pending = true;
+    return HOPE_OK;
+}
+// host API prologue: order the context's own streams behind the last device-API call
+int join_device_calls(hope_ctx *ctx, cudaStream_t s) {
+    if (ctx->dev_pending) CK(cudaStreamWaitEvent(s, ctx->ev_dev, 0));
+    return HOPE_OK;
+}
+
 // staging buffers of the host API; the image (12 KB per env) only when a caller asks for it
 int ensure_stage(hope_ctx *ctx, bool want_img) {
     if (want_img && !ctx->d_stage_img) {
@@ -712,7 +731,7 @@ int ensure_stage(hope_ctx *ctx, bool want_img) {
 
 extern "C" {
 
-int hope_version(void) { return 110; }  // 110: hope_out.img, HOPE_STAGE_IMAGE, hope_set_palette, hope_expand_mask
+int hope_version(void) { return 120; }  // 120: HOPE_STAGE_RAW_ACTION, NULL action = step without motion, env_collide, host/device API ordering
 int hope_max_obs(void) { return HOPE_MAX_OBS; }
 
 int hope_default_params(hope_params *p) {
@@ -755,7 +774,6 @@ int hope_create(hope_ctx **out, int device, int n_envs, int pool_size, const hop
     ctx->device = device; ctx->n = n_envs; ctx->pool = pool_size;
     if (p) ctx->par = *p; else hope_default_params(&ctx->par);
     if (ctx->par.regen_on_reset && pool_size < n_envs) { ctx->last_error = "regen_on_reset needs pool_size >= n_envs (env i owns slot i)"; return HOPE_ERR_INVALID; }
-    if (ctx->par.env_collide) { ctx->last_error = "ENV_COLLIDE=True is not supported (reference default False, configs.py:79)"; return HOPE_ERR_INVALID; }
     memset(&ctx->stage_out, 0, sizeof(ctx->stage_out));
     ctx->maxc = tan(ctx->par.valid_steer[1]) / ctx->par.wheel_base;  // car_parking_base.py:422
     CK(cudaSetDevice(device));
@@ -829,6 +847,7 @@ int hope_create(hope_ctx **out, int device, int n_envs, int pool_size, const hop
         CK(cudaEventCreateWithFlags(&ln.ev_observed, cudaEventDisableTiming));
     }
     CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_dev, cudaEventDisableTiming));
     for (int li = 0; li < hope_ctx::MAX_LANES; ++li) CK(cudaEventCreateWithFlags(&ctx->ev_join[li], cudaEventDisableTiming));
     for (auto &e : ctx->ev_chunk) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto &e : ctx->ev_adv) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -874,6 +893,7 @@ int hope_destroy(hope_ctx *ctx) {
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->host_graph) cudaGraphExecDestroy(ctx->host_graph);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_dev) cudaEventDestroy(ctx->ev_dev);
     for (auto e : ctx->ev_join) if (e) cudaEventDestroy(e);
     for (auto e : ctx->ev_chunk) if (e) cudaEventDestroy(e);
     for (auto e : ctx->ev_adv) if (e) cudaEventDestroy(e);
@@ -900,6 +920,8 @@ int hope_set_palette(hope_ctx *ctx, const uint8_t *h_rgb) {
         ctx->palette.rg[k] = white ? 0u : ((uint32_t)c[0] | ((uint32_t)c[1] << 16));
         ctx->palette.b[k] = white ? 0u : (uint32_t)c[2];
     }
+    // k_render takes the palette by value: a captured host step would keep painting with the old colours
+    if (ctx->host_graph) { cudaGraphExecDestroy(ctx->host_graph); ctx->host_graph = nullptr; ctx->hg_action = nullptr; }
     return HOPE_OK;
 }
 
@@ -1024,11 +1046,13 @@ int hope_reset(hope_ctx *ctx, const int32_t *h_scene_ids, const hope_out *d_out,
     CK(cudaStreamSynchronize(s));  // ids is a local buffer
     ctx->have_reset = true;
     // the reset step computes the observation; RS is gated off by t > 1 (car_parking_base.py:293)
-    return launch_step(ctx, nullptr, *d_out, HOPE_STAGE_ADVANCE | HOPE_STAGE_OBSERVE | HOPE_STAGE_RS | HOPE_STAGE_IMAGE, 1, s);
+    int rc = launch_step(ctx, nullptr, *d_out, HOPE_STAGE_ADVANCE | HOPE_STAGE_OBSERVE | HOPE_STAGE_RS | HOPE_STAGE_IMAGE, 1, s);
+    if (rc) return rc;
+    return mark_device_call(ctx, s);
 }
 
 int hope_step(hope_ctx *ctx, const double *d_action, const hope_out *d_out, unsigned stages, void *stream) {
-    if (!ctx || !d_action || !d_out) return HOPE_ERR_INVALID;
+    if (!ctx || !d_out) return HOPE_ERR_INVALID;  // d_action == NULL: CarParking.step(None), no motion (car_parking_base.py:255)
     if (!ctx->have_tables) return HOPE_ERR_NO_TABLES;
     if (!ctx->have_reset) return HOPE_ERR_NO_SCENES;
     CK(cudaSetDevice(ctx->device));
@@ -1037,7 +1061,10 @@ int hope_step(hope_ctx *ctx, const double *d_action, const hope_out *d_out, unsi
     const int n = ctx->n;
     int chunks = ctx->device_chunks;
     if (n < 8192 * chunks) chunks = n / 8192 > 0 ? n / 8192 : 1;
-    if (chunks <= 1) return launch_step(ctx, d_action, *d_out, stages, 0, s);
+    if (chunks <= 1) {
+        int rc1 = launch_step(ctx, d_action, *d_out, stages, 0, s);
+        return rc1 ? rc1 : mark_device_call(ctx, s);
+    }
     // fork the lanes from the caller's stream, one env range per lane (round robin), join back
     const int per = ((n + chunks - 1) / chunks + 127) / 128 * 128;
     CK(cudaEventRecord(ctx->ev_fork, s));
@@ -1052,7 +1079,7 @@ int hope_step(hope_ctx *ctx, const double *d_action, const hope_out *d_out, unsi
         CK(cudaEventRecord(ctx->ev_join[li], ctx->lanes[li].main));
         CK(cudaStreamWaitEvent(s, ctx->ev_join[li], 0));
     }
-    return HOPE_OK;
+    return mark_device_call(ctx, s);
 }
 
 int hope_step_kinematics_collision(hope_ctx *ctx, const double *d_action, double *d_pose, uint8_t *d_collided, uint8_t *d_substeps,
@@ -1063,7 +1090,8 @@ int hope_step_kinematics_collision(hope_ctx *ctx, const double *d_action, double
     hope_out o;
     memset(&o, 0, sizeof(o));
     o.pose = d_pose; o.retreated = d_collided; o.substeps = d_substeps;
-    return launch_step(ctx, d_action, o, HOPE_STAGE_ADVANCE, 0, static_cast<cudaStream_t>(stream));
+    int rc = launch_step(ctx, d_action, o, HOPE_STAGE_ADVANCE, 0, static_cast<cudaStream_t>(stream));
+    return rc ? rc : mark_device_call(ctx, static_cast<cudaStream_t>(stream));
 }
 
 // enqueue one pipelined host step (see hope_step_host) on the context's lanes; lane 0's main stream is the origin:
@@ -1170,7 +1198,9 @@ static int enqueue_host_step(hope_ctx *ctx, const double *h_action, const hope_h
     struct Scope { hope_ctx *c; ~Scope() { c->in_host_step = false; } } scope{ctx};
     ctx->in_host_step = true;
     cudaStream_t s0 = ctx->lanes[0].main, s_obs = ctx->lanes[0].aux, s_copy = ctx->lanes[1].main;
-    CK(cudaMemcpyAsync(ctx->d_action, h_action, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, s0));
+    const double *d_act = h_action ? ctx->d_action : nullptr;  // NULL: step without motion (CarParking.step(None))
+    const unsigned adv = HOPE_STAGE_ADVANCE | (stages & HOPE_STAGE_RAW_ACTION);
+    if (h_action) CK(cudaMemcpyAsync(ctx->d_action, h_action, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, s0));
     if (ctx->expanding) { k_bump_seq<<<1, 1, 0, s0>>>(ctx->d_seq); ctx->launches++; }
     int rc;
     int chunks = ctx->host_chunks;
@@ -1178,7 +1208,7 @@ static int enqueue_host_step(hope_ctx *ctx, const double *h_action, const hope_h
     const int per = ((n + chunks - 1) / chunks + 127) / 128 * 128;
     const bool split_advance = side && ctx->host_split_advance;  // k_advance per range too: the first range's k_observe starts earlier
     if (!split_advance) {
-        rc = launch_range(ctx, ctx->d_action, ctx->step_out, HOPE_STAGE_ADVANCE, 0, s0, 0, 0, 0, n);
+        rc = launch_range(ctx, d_act, ctx->step_out, adv, 0, s0, 0, 0, 0, n);
         if (rc) return rc;
     }
     int last_chunk = 0;
@@ -1191,13 +1221,13 @@ static int enqueue_host_step(hope_ctx *ctx, const double *h_action, const hope_h
         for (int c = 0, lo = 0; lo < n; ++c, lo += per) {
             const int cnt = (lo + per <= n) ? per : n - lo;
             if (split_advance) {
-                rc = launch_range(ctx, ctx->d_action, ctx->step_out, HOPE_STAGE_ADVANCE, 0, s0, 0, c, lo, cnt);
+                rc = launch_range(ctx, d_act, ctx->step_out, adv, 0, s0, 0, c, lo, cnt);
                 if (rc) return rc;
                 cudaEvent_t ea = ctx->ev_adv[c % hope_ctx::MAX_CHUNK_EVENTS];
                 CK(cudaEventRecord(ea, s0));
                 CK(cudaStreamWaitEvent(s_obs, ea, 0));
             }
-            rc = launch_range(ctx, ctx->d_action, ctx->step_out, side, 0, s_obs, 0, c, lo, cnt, nullptr, false);
+            rc = launch_range(ctx, d_act, ctx->step_out, side, 0, s_obs, 0, c, lo, cnt, nullptr, false);
             if (rc) return rc;
             last_chunk = c;
             cudaEvent_t ev = ctx->ev_chunk[c % hope_ctx::MAX_CHUNK_EVENTS];
@@ -1217,7 +1247,7 @@ static int enqueue_host_step(hope_ctx *ctx, const double *h_action, const hope_h
         // the persistent Reeds-Shepp grids would occupy every SM and starve the (later launched) k_observe ranges
         // whatever the stream priorities, so they start behind the last range and run under the copies instead
         if (side && ctx->host_rs_after_observe) CK(cudaStreamWaitEvent(s0, ctx->ev_chunk[(last_chunk) % hope_ctx::MAX_CHUNK_EVENTS], 0));
-        rc = launch_range(ctx, ctx->d_action, ctx->step_out, HOPE_STAGE_RS, 0, s0, 0, 0, 0, n, nullptr, false);
+        rc = launch_range(ctx, d_act, ctx->step_out, HOPE_STAGE_RS, 0, s0, 0, 0, 0, n, nullptr, false);
         if (rc) return rc;
     }
     rc = copy_fields(ctx, h_out, side ? 0 : -1, s0, 0, n);
@@ -1236,7 +1266,7 @@ int hope_expand_mask(const uint8_t *h_steps, double *h_mask, int n) {
 }
 
 int hope_step_host(hope_ctx *ctx, const double *h_action, const hope_host_out *h_out, unsigned stages) {
-    if (!ctx || !h_action || !h_out) return HOPE_ERR_INVALID;
+    if (!ctx || !h_out) return HOPE_ERR_INVALID;  // h_action == NULL: CarParking.step(None), no motion
     if (!ctx->have_tables) return HOPE_ERR_NO_TABLES;
     if (!ctx->have_reset) return HOPE_ERR_NO_SCENES;
     CK(cudaSetDevice(ctx->device));
@@ -1247,6 +1277,9 @@ int hope_step_host(hope_ctx *ctx, const double *h_action, const hope_host_out *h
     // buffers start their D2H copy behind it, under the Reeds-Shepp kernels.  Envs are independent, so the split
     // changes nothing.
     cudaStream_t s0 = ctx->lanes[0].main;
+    rc = join_device_calls(ctx, s0);  // a device-API call may still be running on the caller's stream
+    if (rc) return rc;
+    ctx->dev_pending = false;         // everything below is ordered behind s0 and this call returns synchronised
     if (ctx->host_graph_enabled && !ctx->profile) {
         const bool same = ctx->host_graph && ctx->hg_action == h_action && ctx->hg_stages == stages &&
                           memcmp(&ctx->hg_out, h_out, sizeof(hope_out)) == 0;
@@ -1292,6 +1325,8 @@ int hope_reset_host(hope_ctx *ctx, const int32_t *h_scene_ids, const hope_host_o
     if (rc) return rc;
     hope_out reset_out = ctx->stage_out;
     if (!h_out->img) reset_out.img = nullptr;  // nobody reads the staged image: skip the render
+    rc = join_device_calls(ctx, ctx->own_stream);
+    if (rc) return rc;
     rc = hope_reset(ctx, h_scene_ids, &reset_out, ctx->own_stream);
     if (rc) return rc;
     const unsigned keep_mask = ctx->zero_copy_mask;
@@ -1300,6 +1335,7 @@ int hope_reset_host(hope_ctx *ctx, const int32_t *h_scene_ids, const hope_host_o
     ctx->zero_copy_mask = keep_mask;
     if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->own_stream));
+    ctx->dev_pending = false;
     return HOPE_OK;
 }
 
@@ -1336,7 +1372,7 @@ int hope_planner_actions(hope_ctx *ctx, const double *d_policy_action, const hop
                                                                                      d_executing, step_ratio);
     ctx->launches++;
     CK(cudaGetLastError());
-    return HOPE_OK;
+    return mark_device_call(ctx, static_cast<cudaStream_t>(stream));
 }
 
 int hope_planner_reset(hope_ctx *ctx, void *stream) {

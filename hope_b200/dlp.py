@@ -35,13 +35,20 @@ def _decode_wkb_linestring(b):
     return np.array(pts, dtype=np.float64)
 
 
+# the only globals the reference's dlp.data refers to (besides the ring class): numpy scalars of a given dtype
+_ALLOWED = {("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar"), ("numpy", "dtype"),
+            ("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"), ("numpy", "ndarray")}
+
+
 class _Unpickler(pickle.Unpickler):
+    """Exact allow-list: anything else (builtins.eval, os.system, ...) is refused, so a crafted file cannot run code."""
+
     def find_class(self, module, name):
         if module.startswith("shapely"):
             if name == "LinearRing":
                 return _Ring
             raise pickle.UnpicklingError(f"unexpected shapely class {module}.{name}")
-        if module.split(".")[0] not in ("numpy", "builtins", "collections"):
+        if (module, name) not in _ALLOWED:
             raise pickle.UnpicklingError(f"refusing to load {module}.{name}")
         return super().find_class(module, name)
 
@@ -61,6 +68,9 @@ def read_dlp(path):
                 xy = xy[:-1]
             rings.append(xy.copy())
         cases.append(dict(starts=starts, dest=np.array(dest, dtype=np.float64), rings=rings))
+    multi = isinstance(raw[0][0], list)  # ParkingMapDLP.__init__ decides `multi_start` on the first case (parking_map_dlp.py:33-35)
+    for c in cases:
+        c["multi"] = multi
     return cases
 
 
@@ -75,9 +85,11 @@ def _flip(pose):
 def prepare_scene(case, rng, start_index=None, flips=None, max_obs=MAX_OBS_DLP):
     """One `ParkingMapDLP.reset` (:38-86): pick and jitter a start, bounds = floor/ceil of the poses -/+ 20,
     keep the rings whose bounding box reaches into the bounds, flip dest / start with p = 0.5 each.
-    `rng` is a numpy Generator (the reference draws from the global RNG)."""
+    `rng` is a numpy Generator, or any object with integers(lo, hi) / standard_normal(n) / random(): the facade passes
+    numpy's global generator (the one the reference draws from) and the draws below come in the reference's order
+    (:62 start index, :64 three jitters, :81 dest flip, :83 start flip), so the same np.random.seed gives the same scene."""
     starts = case["starts"]
-    if len(starts) > 1:
+    if case.get("multi", len(starts) > 1):
         k = int(rng.integers(0, len(starts))) if start_index is None else start_index
         st = starts[k] + rng.standard_normal(3) * np.array([0.05, 0.05, 0.02])
     else:
@@ -118,5 +130,5 @@ def cases_from_fixture(npz):
     for j in range(len(npz["case_ids"])):
         nv = npz[f"ring_nv_{j}"]
         rings = [npz[f"rings_{j}"][k, :nv[k]].copy() for k in range(len(nv))]
-        cases.append(dict(starts=npz[f"starts_{j}"].copy(), dest=npz[f"dest_{j}"].copy(), rings=rings))
+        cases.append(dict(starts=npz[f"starts_{j}"].copy(), dest=npz[f"dest_{j}"].copy(), rings=rings, multi=True))
     return cases

@@ -24,7 +24,7 @@ N_ACTION = 42
 def possible_actions(device, dtype=torch.float64):
     """configs.py:108-115 scaled like action_mask.py:218-222: steer / 0.75, speed / 1."""
     a = torch.as_tensor(tables.discrete_actions(), device=device, dtype=dtype)
-    return a / torch.tensor([tables.VALID_STEER, 1.0], device=device, dtype=dtype)
+    return a / torch.tensor([float(tables.refconfig.load().VALID_STEER[-1]), 1.0], device=device, dtype=dtype)
 
 
 def masked_action_probs(mean, std, mask, actions):

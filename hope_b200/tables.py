@@ -8,34 +8,31 @@ the mask sweep compares against carry the same bits:
                     rear-axle origin to where beam i leaves VehicleBox
   dist_star         model/action_mask.py:84-163: for the 42 discrete actions (configs.py:108-115)
                     x 10 arc steps, farthest ray/box intersection, x10 circular upsample
+
+Every constant comes from the configs snapshot of `refconfig.load()` (the caller's own `configs` module when importable,
+SURVEY.md §5): WHEEL_BASE, the VehicleBox corners, LIDAR_RANGE, VALID_STEER, PRECISION / step_speed.
 """
 import math
 
 import numpy as np
 
-N_RAY, N_ACT, N_ITER, UPSAMPLE = 120, 42, 10, 10
-WHEEL_BASE, FRONT_HANG, REAR_HANG, WIDTH = 2.8, 0.96, 0.93, 1.94
-LIDAR_RANGE = 10.0
-VALID_STEER = 0.75
-PRECISION = 10
-BOX_XY = np.array([(-REAR_HANG, -WIDTH / 2), (FRONT_HANG + WHEEL_BASE, -WIDTH / 2),
-                   (FRONT_HANG + WHEEL_BASE, WIDTH / 2), (-REAR_HANG, WIDTH / 2)])
+from . import refconfig
+
+N_RAY, N_ACT, N_ITER, UPSAMPLE = 120, 42, 10, 10  # compiled sizes (include/hope_b200.h); refconfig.validate checks configs against them
 
 
-def discrete_actions():
-    steer = np.arange(VALID_STEER, -(VALID_STEER + VALID_STEER / PRECISION), -VALID_STEER / PRECISION)
-    fwd = np.stack([steer, np.full_like(steer, 1.0)], axis=1)
-    bwd = np.stack([steer, np.full_like(steer, -1.0)], axis=1)
-    return np.concatenate([fwd, bwd], axis=0)
+def discrete_actions(cfg=None):
+    cfg = cfg or refconfig.load()
+    return np.array(cfg.discrete_actions, dtype=np.float64)  # configs.py:108-115
 
 
-def _exit_distance(ex, ey):
+def _exit_distance(ex, ey, box):
     """Where the segment (0,0)->(ex,ey) crosses the box ring, as a distance from the origin.
     The origin is strictly inside the box, so exactly one edge is crossed."""
     best = math.inf
     for k in range(4):
-        qx, qy = BOX_XY[k]
-        sx, sy = BOX_XY[(k + 1) % 4] - BOX_XY[k]
+        qx, qy = box[k]
+        sx, sy = box[(k + 1) % 4] - box[k]
         den = ex * sy - ey * sx
         if den == 0.0:
             continue
@@ -47,11 +44,12 @@ def _exit_distance(ex, ey):
     return best
 
 
-def own_box_offsets(cos_fn, sin_fn):
+def own_box_offsets(cos_fn, sin_fn, cfg=None):
+    cfg = cfg or refconfig.load()
     out = np.zeros(N_RAY)
     for i in range(N_RAY):
         ang = i * math.pi / N_RAY * 2
-        out[i] = _exit_distance(float(cos_fn(ang) * LIDAR_RANGE), float(sin_fn(ang) * LIDAR_RANGE))
+        out[i] = _exit_distance(float(cos_fn(ang) * cfg.LIDAR_RANGE), float(sin_fn(ang) * cfg.LIDAR_RANGE), cfg.VEHICLE_BOX)
     return out
 
 
@@ -65,11 +63,12 @@ def circular_upsample(x, rate=UPSAMPLE):
     return wrap[j // rate, ...] * lo + wrap[j // rate + 1, ...] * hi
 
 
-def swept_box_corners():
-    act = discrete_actions()
-    radius = 1 / (np.tan(act[:, 0]) / WHEEL_BASE)
-    bx = BOX_XY[:, 0].reshape(1, -1)
-    by = BOX_XY[:, 1].reshape(1, -1)
+def swept_box_corners(cfg=None):
+    cfg = cfg or refconfig.load()
+    act = discrete_actions(cfg)
+    radius = 1 / (np.tan(act[:, 0]) / cfg.WHEEL_BASE)
+    bx = cfg.VEHICLE_BOX[:, 0].reshape(1, -1)
+    by = cfg.VEHICLE_BOX[:, 1].reshape(1, -1)
     ox = 0 - radius * np.sin(0)
     oy = 0 + radius * np.cos(0)
     dpsi = 0.5 * act[:, 1] / 10 / radius
@@ -86,10 +85,11 @@ def swept_box_corners():
     return out
 
 
-def dist_star():
-    corners = swept_box_corners()
+def dist_star(cfg=None):
+    cfg = cfg or refconfig.load()
+    corners = swept_box_corners(cfg)
     ray = np.arange(N_RAY)
-    far = LIDAR_RANGE * 10
+    far = cfg.LIDAR_RANGE * 10
     x2r = (np.cos(ray / N_RAY * 2 * np.pi) * far).reshape(-1, 1)
     y2r = (np.sin(ray / N_RAY * 2 * np.pi) * far).reshape(-1, 1)
     x1r = np.zeros_like(x2r)
@@ -127,18 +127,20 @@ def dist_star():
     return np.ascontiguousarray(circular_upsample(reach))
 
 
-_CACHE = None
+_CACHE = {}
 
 
-def host_tables():
-    """dict of contiguous float64 arrays in hope_upload_tables order."""
-    global _CACHE
-    if _CACHE is None:
+def host_tables(cfg=None):
+    """dict of contiguous float64 arrays in hope_upload_tables order, for the configs snapshot `cfg` (default: refconfig.load())."""
+    cfg = refconfig.validate(cfg or refconfig.load())
+    key = (float(cfg.WHEEL_BASE), cfg.VEHICLE_BOX.tobytes(), float(cfg.LIDAR_RANGE), float(cfg.VALID_STEER[-1]), int(cfg.PRECISION),
+           float(cfg.step_speed))
+    if key not in _CACHE:
         theta = np.array([i * math.pi / N_RAY * 2 for i in range(N_RAY)])
         r = np.arange(UPSAMPLE)
-        _CACHE = dict(
+        _CACHE[key] = dict(
             ray_a=np.ascontiguousarray(np.sin(theta)), ray_b=np.ascontiguousarray(-np.cos(theta)),
-            lidar_base=own_box_offsets(math.cos, math.sin), mask_base=own_box_offsets(np.cos, np.sin),
-            dist_star=dist_star(),
+            lidar_base=own_box_offsets(math.cos, math.sin, cfg), mask_base=own_box_offsets(np.cos, np.sin, cfg),
+            dist_star=dist_star(cfg),
             w_lo=np.ascontiguousarray(1 - (r % UPSAMPLE) / UPSAMPLE), w_hi=np.ascontiguousarray((r % UPSAMPLE) / UPSAMPLE))
-    return _CACHE
+    return _CACHE[key]

@@ -57,8 +57,10 @@ enum {
     HOPE_STAGE_OBSERVE = 2,  /* LiDAR raycast + action-mask sweep + target representation */
     HOPE_STAGE_RS = 4,       /* Reeds-Shepp search (car_parking_base.py:293-297 gate) */
     HOPE_STAGE_ALL = 7,      /* the lidar + action-mask + Reeds-Shepp step (use_img_observation=False) */
-    HOPE_STAGE_IMAGE = 8     /* ego-centric image observation into hope_out.img (car_parking_base.py:301-350,
+    HOPE_STAGE_IMAGE = 8,    /* ego-centric image observation into hope_out.img (car_parking_base.py:301-350,
                                 observation_processor.py:6-23); needs a non-NULL img pointer */
+    HOPE_STAGE_RAW_ACTION = 16 /* modifier: the action is CarParking.step's [steer rad, speed m/s] (car_parking_base.py:235),
+                                not the wrapper's policy output in [-1,1]^2: skip the rescale of env_wrapper.py:37-50 */
 };
 #define HOPE_IMG_C 3         /* observation_processor.py:9  n_channels */
 #define HOPE_IMG_HW 64       /* configs.py:89-90 OBS_W, OBS_H = 256, observation_processor.py:8 downsample_rate 4 */
@@ -79,7 +81,8 @@ typedef struct hope_params {
     double rs_step;           /* car_parking_base.py:424 sampling interval 0.1 m */
     double reward_weight[5];  /* configs.py:181-187 time, rs_dist, dist, angle, box_union */
     double reward_ratio;      /* configs.py:180 0.1 */
-    int env_collide;          /* configs.py:79  0 */
+    int env_collide;          /* configs.py:79  ENV_COLLIDE: 1 = a collision on the first substep ends the episode
+                                 (status COLLIDED, car_parking_base.py:264-267, 279-282); default 0 */
     int auto_reset;           /* 1: an env that finished takes its next pool scene on the following step */
     int regen_on_reset;       /* 1 (needs pool_size >= n_envs): env i owns pool slot i and, when it finishes, a fresh
                                  scene is generated ON THE DEVICE into that slot (scope row f4) instead of cycling
@@ -162,7 +165,9 @@ int hope_get_scene_pool(hope_ctx *ctx, int first, int n, double *h_start, double
 int hope_reset(hope_ctx *ctx, const int32_t *h_scene_ids, const hope_out *d_out, void *stream);
 
 /* One CarParkingWrapper.step for every env.  d_action[n][2]: policy output in [-1,1]^2
- * (env_wrapper.py:37-50 rescale happens on the device). */
+ * (env_wrapper.py:37-50 rescale happens on the device), or with HOPE_STAGE_RAW_ACTION the physical [steer, speed] of
+ * CarParking.step.  d_action == NULL is CarParking.step(None) (car_parking_base.py:255): no motion, t += 1, the full
+ * observation, status, reward and (when t > 1) the Reeds-Shepp search from the current pose. */
 int hope_step(hope_ctx *ctx, const double *d_action, const hope_out *d_out, unsigned stages, void *stream);
 
 /* BASELINE cfg 2: kinematics + collision (+ arrival) only. */
@@ -171,7 +176,8 @@ int hope_step_kinematics_collision(hope_ctx *ctx, const double *d_action, double
 
 /* Same step with HOST buffers: copies h_action in, runs, copies the non-NULL outputs back,
  * synchronises.  This is the end-to-end entry point a host-only caller (the reference's
- * training loop) would use. */
+ * training loop) would use.  The host calls order themselves behind the last device-API call on this context
+ * (hope_reset / hope_step / hope_planner_actions on the caller's stream), so the two APIs can be mixed. */
 int hope_step_host(hope_ctx *ctx, const double *h_action, const hope_host_out *h_out, unsigned stages);
 int hope_reset_host(hope_ctx *ctx, const int32_t *h_scene_ids, const hope_host_out *h_out);
 

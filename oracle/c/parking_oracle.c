@@ -676,6 +676,10 @@ typedef struct {
     double *rs_len, *rs_L;
 } orc_io;
 
+/* ENV_COLLIDE (configs.py:79, default False): 1 = a collision on the first substep ends the episode (:264-267, :279-282) */
+static int g_env_collide = 0;
+void orc_set_env_collide(int on) { g_env_collide = on; }
+
 static double angle_diff(double a1, double a2) { /* car_parking_base.py:203-206 */
     double d = acos(cos(a1 - a2));
     return d < PI / 2 ? d : PI - d;
@@ -689,7 +693,7 @@ static void step_one(int i, const orc_io *io, const double *action, const orc_ta
     double *pose = io->pose + 3 * i;
     double prev[3] = {pose[0], pose[1], pose[2]};
     double bx[4], by[4], dbx[4], dby[4];
-    int arrive = 0, nsub = 0, nret = 0;
+    int arrive = 0, collide = 0, nsub = 0, nret = 0;
     make_box(dest, dbx, dby);
     double dest_area = shoelace(dbx, dby, 4);
     if (action) {
@@ -702,7 +706,11 @@ static void step_one(int i, const orc_io *io, const double *action, const orc_ta
             ++nsub;
             make_box(pose, bx, by);
             if (clip_area(bx, by, dbx, dby) / dest_area > 0.95) { arrive = 1; break; }
-            if (collides(bx, by, so)) { pose[0] = keep[0]; pose[1] = keep[1]; pose[2] = keep[2]; ++nret; break; }
+            if (collides(bx, by, so)) {
+                pose[0] = keep[0]; pose[1] = keep[1]; pose[2] = keep[2]; ++nret;
+                if (s == 0) collide = g_env_collide;
+                break;
+            }
         }
     }
     io->t[i] += 1;
@@ -711,6 +719,7 @@ static void step_one(int i, const orc_io *io, const double *action, const orc_ta
     double inter = clip_area(bx, by, dbx, dby);
     int status;
     if (arrive) status = ST_ARRIVED;
+    else if (collide) status = ST_COLLIDED; /* :282 */
     else if (collides(bx, by, so)) status = ST_COLLIDED; /* :175-184 */
     else if (pose[0] > bounds[1] || pose[0] < bounds[0] || pose[1] > bounds[3] || pose[1] < bounds[2]) status = ST_OUTBOUND;
     else if (inter / dest_area > 0.95) status = ST_ARRIVED;

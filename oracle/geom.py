@@ -205,3 +205,71 @@ def ring_centroid(ring):
         sx += seg * ((x0 + x1) / 2)
         sy += seg * ((y0 + y1) / 2)
     return sx / total, sy / total
+
+
+def rings_equal(ring_a, ring_b):
+    """`equals` for two simple closed rings (first == last): the same curve from any start vertex, in either direction."""
+    a, b = list(ring_a[:-1]), list(ring_b[:-1])
+    if len(a) != len(b):
+        return False
+    n = len(a)
+    for seq in (b, b[::-1]):
+        for s in range(n):
+            if all(a[i] == seq[(s + i) % n] for i in range(n)):
+                return True
+    return False
+
+
+def convex_hull(pts):
+    """counter-clockwise hull (gift wrapping from the lowest-leftmost point), collinear points dropped"""
+    pts = list(dict.fromkeys((float(x), float(y)) for x, y in pts))
+    if len(pts) < 3:
+        return pts
+    start = min(pts, key=lambda p: (p[1], p[0]))
+    hull, cur = [], start
+    while True:
+        hull.append(cur)
+        nxt = pts[0] if pts[0] != cur else pts[1]
+        for p in pts:
+            if p == cur:
+                continue
+            o = orient(cur[0], cur[1], nxt[0], nxt[1], p[0], p[1])
+            if o < 0 or (o == 0 and math.hypot(p[0] - cur[0], p[1] - cur[1]) > math.hypot(nxt[0] - cur[0], nxt[1] - cur[1])):
+                nxt = p
+        cur = nxt
+        if cur == start:
+            return hull
+
+
+def min_area_rectangle(pts):
+    """shapely 1.x `minimum_rotated_rectangle`: min over hull edges of the bounding rectangle in the edge's frame (4 corners)"""
+    hull = convex_hull(pts)
+    best = None
+    n = len(hull)
+    for i in range(n):
+        (ax, ay), (bx, by) = hull[i], hull[(i + 1) % n]
+        length = math.sqrt((bx - ax) ** 2 + (by - ay) ** 2)
+        ux, uy = (bx - ax) / length, (by - ay) / length
+        vx, vy = -uy, ux
+        us = [ux * x + uy * y for x, y in hull]
+        vs = [vx * x + vy * y for x, y in hull]
+        area = (max(us) - min(us)) * (max(vs) - min(vs))
+        if best is None or area < best[0]:
+            best = (area, [(ux * u + vx * v, uy * u + vy * v) for u, v in
+                           ((min(us), min(vs)), (max(us), min(vs)), (max(us), max(vs)), (min(us), max(vs)))])
+    return best[1]
+
+
+def point_in_convex(p, poly):
+    """p inside or on the convex polygon (open vertex list, either winding), exact orientation signs"""
+    sign = 0
+    n = len(poly)
+    for i in range(n):
+        a, b = poly[i], poly[(i + 1) % n]
+        o = orient(a[0], a[1], b[0], b[1], p[0], p[1])
+        if o != 0:
+            if sign == 0:
+                sign = o
+            elif o != sign:
+                return False
+    return True

@@ -18,6 +18,8 @@ Fixtures written (all float64 unless noted):
   images_<Level>.npz     CarParkingWrapper with use_img_observation=True: per step the uint8 image
                          (obs['img'] * 255, exact), pose, trajectory length, substep counters; pygame is the
                          software restatement oracle/softraster.py (unpinned), cv2 is the real one
+  episodes_collide.npz   random-action episodes of all three levels recorded with ENV_COLLIDE = True (configs.py:79): a collision on
+                         the first substep ends the episode with status COLLIDED (car_parking_base.py:264-267, 279-282)
   mask_table.npz         ActionMask constants: vehicle_lidar_base, sha256 + strided sample of
                          dist_star (action_mask.py:114-143), LidarSimlator.vehicle_boundary
 
@@ -98,8 +100,11 @@ def plan_actions(types, lengths, step_ratio):
     return acts
 
 
-def record_episodes(mods, level, n_episodes, seed, steps_per_episode=200, follow_rs=False):
+def record_episodes(mods, level, n_episodes, seed, steps_per_episode=200, follow_rs=False, env_collide=False):
     cpb, wrap, vehicle, rs, pmn, configs = mods
+    # ENV_COLLIDE (configs.py:79) is read by CarParking.step as a module global of car_parking_base (star-imported from configs):
+    # setting it there is what editing configs.py does, without touching a reference file
+    cpb.ENV_COLLIDE = bool(env_collide)
     raw = cpb.CarParking(render_mode="rgb_array", fps=100, verbose=False,
                          use_lidar_observation=True, use_img_observation=False, use_action_mask=True)
     env = wrap.CarParkingWrapper(raw)
@@ -182,6 +187,7 @@ def record_episodes(mods, level, n_episodes, seed, steps_per_episode=200, follow
             if done:
                 break
     rs.calc_all_paths = orig_all
+    cpb.ENV_COLLIDE = False
     out = {k: np.asarray(v) for k, v in rec.items()}
     out.update({"scene_" + k: np.asarray(v) for k, v in scn.items()})
     return out
@@ -321,7 +327,7 @@ def main():
     ap.add_argument("--episodes", type=int, default=3)
     ap.add_argument("--scenes", type=int, default=96)
     ap.add_argument("--follow-episodes", type=int, default=12)
-    ap.add_argument("--only", default=None, help="'rs', 'tables' or 'images': regenerate just that fixture")
+    ap.add_argument("--only", default=None, help="'rs', 'tables', 'images' or 'collide': regenerate just that fixture")
     ap.add_argument("--image-episodes", type=int, default=4)
     args = ap.parse_args()
     out = os.path.abspath(args.out)
@@ -336,6 +342,19 @@ def main():
             im = record_images(mods, level, args.image_episodes, 777)
             np.savez_compressed(os.path.join(out, f"images_{level}.npz"), **im)
             print(level, "image steps", len(im["traj_len"]), "max traj", int(im["traj_len"].max()))
+    if args.only in (None, "collide"):
+        parts = [record_episodes(mods, level, 25, 9000 + 100 * k, env_collide=True) for k, level in enumerate(("Normal", "Complex", "Extrem"))]
+        merged = {}
+        ep_off = 0
+        for part in parts:
+            part = dict(part)
+            part["ep"] = part["ep"] + ep_off
+            ep_off += len(part["scene_start"])
+            for k, v in part.items():
+                merged.setdefault(k, []).append(v)
+        merged = {k: np.concatenate(v) for k, v in merged.items()}
+        np.savez_compressed(os.path.join(out, "episodes_collide.npz"), **merged)
+        print("ENV_COLLIDE episodes", ep_off, "steps", len(merged["status"]), "status hist", np.bincount(merged["status"], minlength=6))
     if args.only is not None:
         return
     for level in ("Normal", "Complex", "Extrem"):

@@ -38,7 +38,13 @@ class Point(BaseGeometry):
 
 class MultiPoint(BaseGeometry):
     def __init__(self, pts=()):
-        self.pts = _as_pairs(pts)
+        self.pts = _as_pairs([p.coords[0] if isinstance(p, Point) else p for p in pts])
+
+    @property
+    def minimum_rotated_rectangle(self):
+        """shapely 1.x geometry/base.py: over the edges of the convex hull, the axis-parallel bounding rectangle in the
+        edge's frame with the smallest area, transformed back (map_level.py:71, :98)"""
+        return Polygon._from_open(_g.min_area_rectangle(self.pts))
 
     @property
     def coords(self):
@@ -57,13 +63,32 @@ class MultiPoint(BaseGeometry):
 class LineString(BaseGeometry):
     closed = False
 
-    def __init__(self, coords):
+    def __init__(self, coords=None):
+        if coords is None:  # unpickling: shapely 1.x reduces a geometry to (class, (), wkb) and restores it in __setstate__
+            self._coords = []
+            return
         if isinstance(coords, LineString):
             coords = coords.coords
         pts = _as_pairs(coords)
         if self.closed and pts[0] != pts[-1]:
             pts.append(pts[0])
         self._coords = pts
+
+    def __setstate__(self, state):
+        """data/dlp.data pickles shapely-1.x LinearRings: the state is the WKB of a (closed) LineString"""
+        if isinstance(state, dict):  # a stand-in object pickled by this module (oracle/make_dlp_golden.py)
+            self.__dict__.update(state)
+            return
+        import struct
+        b = bytes(state)
+        order = "<" if b[0] == 1 else ">"
+        gtype, n = struct.unpack_from(order + "II", b, 1)
+        assert gtype & 0xFF == 2 and not gtype & 0x80000000, "2-D LineString WKB expected"
+        flat = struct.unpack_from(order + "%dd" % (2 * n), b, 9)
+        self._coords = [(flat[2 * i], flat[2 * i + 1]) for i in range(n)]
+
+    def equals(self, other):
+        return _g.rings_equal(self._coords, other._coords)
 
     @property
     def coords(self):
@@ -114,3 +139,14 @@ class Polygon(BaseGeometry):
         p = cls.__new__(cls)
         p._open = list(pts)
         return p
+
+    @property
+    def exterior(self):
+        return LinearRing(self._open)
+
+    def intersects(self, other):
+        """filled convex polygon vs a curve (map_level.py:79, :106): a curve vertex inside or on the polygon, or crossing boundaries"""
+        ring = self._open + [self._open[0]]
+        if any(_g.point_in_convex(p, self._open) for p in other._coords):
+            return True
+        return _g.rings_intersect(ring, other._coords)

@@ -46,7 +46,7 @@ static inline double4 ld_aabb(const double4 *p) { return *p; }  // the kernel's 
 #include "../hope_b200/csrc/advance.cuh"
 
 static void advance_one(const int n, const int gi, const int lane, AdvanceSmem &sm, Pool pool, EnvState st, const double *action, hope_params par,
-                        hope_out out, int reset_all, int reset_stride) {
+                        hope_out out, int reset_all, int reset_stride, bool raw_action = false) {
 #include "../hope_b200/csrc/advance_body.inc"
 }
 }  // namespace hope

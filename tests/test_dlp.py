@@ -66,7 +66,7 @@ def test_cuda_128_ring_build_matches_the_oracle_on_dlp_scenes(cases):
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     from hope_b200.batched_env import BatchedParkingEnv
-    from tests.test_gpu_parity import Tally, compare_step, gather, assert_bars, FLOAT_TOL
+    from tests.test_gpu_parity import Tally, compare_step, gather, assert_bars, check_rs_found, FLOAT_TOL
     ids = np.arange(96) % 16
     sc = dlp.prepare_scenes(cases, ids, seed=11)
     env = BatchedParkingEnv(96, scenes=sc, auto_reset=False)
@@ -78,12 +78,15 @@ def test_cuda_128_ring_build_matches_the_oracle_on_dlp_scenes(cases):
     assert np.array_equal(out["mask_steps"], ref["mask_steps"].astype(np.uint8))
     rng = np.random.default_rng(2)
     tl = Tally(); live = np.ones(96, dtype=bool)
-    for _ in range(60):
+    flips = []
+    for k in range(60):
         act = rng.uniform(-1, 1, size=(96, 2))
         env.step(torch.as_tensor(act, device=env.device).contiguous())
         ref = orc.step(act)
-        compare_step(tl, gather(env), {**ref, "mask_steps": ref["mask_steps"].astype(np.uint8)}, orc.pose, live)
+        nf = compare_step(tl, gather(env), {**ref, "mask_steps": ref["mask_steps"].astype(np.uint8)}, orc.pose, live)
+        flips += [(k, e) for e in np.flatnonzero(nf)]
         live &= ref["status"] == 1
     tl.report("DLP scenes (128-ring build), 96 envs x 60 steps")
-    assert_bars(tl, rs_found_slack=2)
+    assert_bars(tl)
+    check_rs_found("dlp:96x60", flips)
     env.close()

@@ -25,6 +25,28 @@ LEVELS = ("Normal", "Complex", "Extrem")
 POSE_TOL = 1e-9      # spec: 1e-5
 FLOAT_TOL = 1e-9
 
+# Reeds-Shepp found / not-found may differ from the reference only on the steps listed here, each one looked at by hand: the
+# first word tried grazes an obstacle (is_traj_valid's untoleranced bbox test flips with the last bit of a sample, and the
+# unmodified reference itself flips when fed the other side's pose: tests/golden/grazing_cases.npz), or two
+# mirror-image words have equal length and the reference's heap order comes from rounding noise.  libdevice's
+# transcendentals are deterministic, so the list is stable; anything outside it is a regression.
+#   key: test id -> set of (step index, env index)
+RS_FOUND_KNOWN = {
+}
+_RS_RECORD = os.environ.get("HOPE_RS_RECORD")  # write the observed sets to this JSON file instead of failing (to refresh the list)
+
+
+def check_rs_found(test_id, observed):
+    observed = {(int(a), int(b)) for a, b in observed}
+    if _RS_RECORD:
+        import json
+        prev = json.load(open(_RS_RECORD)) if os.path.exists(_RS_RECORD) else {}
+        prev[test_id] = sorted(observed)
+        json.dump(prev, open(_RS_RECORD, "w"), indent=1)
+        return
+    known = RS_FOUND_KNOWN.get(test_id, set())
+    assert observed <= known, f"{test_id}: rs_found differs on steps outside the allow-list: {sorted(observed - known)}"
+
 
 def _np(t):
     return t.detach().cpu().numpy()
@@ -87,7 +109,8 @@ def gather(env):
     return {k: _np(v) for k, v in env.out.items()}
 
 
-def assert_bars(tl, rs_found_slack=0):
+def assert_bars(tl, rs_found_slack=None):
+    """rs_found_slack=None: the caller checks found / not-found against RS_FOUND_KNOWN with check_rs_found"""
     for k in ("status", "substeps", "retreated(collision)", "mask_steps", "rs_ncand"):
         assert tl.mismatch[k] == 0, (k, tl.mismatch)
     assert tl.maxdiff["pose"] <= POSE_TOL, tl.maxdiff
@@ -96,7 +119,8 @@ def assert_bars(tl, rs_found_slack=0):
     for k in ("rs_lengths(same word)", "rs_L(same word)"):
         if k in tl.maxdiff:
             assert tl.maxdiff[k] <= FLOAT_TOL, (k, tl.maxdiff)
-    assert tl.mismatch["rs_found"] <= rs_found_slack, tl.mismatch
+    if rs_found_slack is not None:
+        assert tl.mismatch["rs_found"] <= rs_found_slack, tl.mismatch
 
 
 def test_library_reports_version_and_params():
@@ -107,15 +131,18 @@ def test_library_reports_version_and_params():
     assert p.num_step == 10 and p.mini_iter == 20 and abs(p.box_x[1] - 3.76) < 1e-12
 
 
-@pytest.mark.parametrize("stem", ["episodes", "episodes_follow"])
-@pytest.mark.parametrize("level", LEVELS)
-def test_golden_episodes_through_cuda(golden_dir, level, stem):
+GOLDEN_FILES = [f"{stem}_{level}" for level in LEVELS for stem in ("episodes", "episodes_follow")] + ["episodes_collide"]
+
+
+@pytest.mark.parametrize("name", GOLDEN_FILES)
+def test_golden_episodes_through_cuda(golden_dir, name):
     """The traces recorded from the unmodified reference, replayed through the CUDA path: one env
-    per recorded episode, recorded float64 actions, free-running (no state correction)."""
-    g = dict(np.load(os.path.join(golden_dir, f"{stem}_{level}.npz")))
+    per recorded episode, recorded float64 actions, free-running (no state correction).  `episodes_collide` was recorded
+    with ENV_COLLIDE = True (configs.py:79) and is replayed with hope_params.env_collide = 1."""
+    g = dict(np.load(os.path.join(golden_dir, f"{name}.npz")))
     n_ep = len(g["scene_start"])
     scenes = dict(start=g["scene_start"], dest=g["scene_dest"], bounds=g["scene_bounds"], obs=g["scene_obs"], nverts=g["scene_nverts"])
-    env = BatchedParkingEnv(n_ep, scenes=scenes, auto_reset=False)
+    env = BatchedParkingEnv(n_ep, scenes=scenes, auto_reset=False, params={"env_collide": 1} if name == "episodes_collide" else None)
     env.reset()
     out = gather(env)
     assert np.abs(out["lidar"] - g["scene_reset_lidar"]).max() <= FLOAT_TOL
@@ -123,6 +150,7 @@ def test_golden_episodes_through_cuda(golden_dir, level, stem):
     assert np.abs(out["target"] - g["scene_reset_target"]).max() <= FLOAT_TOL
     idx = [np.where(g["ep"] == e)[0] for e in range(n_ep)]
     tl = Tally()
+    flips = []
     for k in range(max(len(i) for i in idx)):
         live = np.array([k < len(i) for i in idx])
         rows = np.array([i[k] if k < len(i) else i[-1] for i in idx])
@@ -135,9 +163,13 @@ def test_golden_episodes_through_cuda(golden_dir, level, stem):
                    rs_found=g["rs_found"][rows], rs_types=g["rs_types"][rows], rs_len=g["rs_lengths"][rows], rs_L=g["rs_L"][rows])
         allz = (g["mask"][rows] == 0.01).all(axis=1)
         ref["mask_steps"][allz] = 0
-        compare_step(tl, out, ref, g["pose"][rows], live)
-    tl.report(f"golden {stem}_{level} via CUDA")
-    assert_bars(tl, rs_found_slack=max(2, tl.n // 200))
+        nf = compare_step(tl, out, ref, g["pose"][rows], live)
+        flips += [(k, e) for e in np.flatnonzero(nf)]
+    tl.report(f"golden {name} via CUDA")
+    assert_bars(tl)
+    check_rs_found(f"golden:{name}", flips)
+    if name == "episodes_collide":
+        assert (g["status"] == capi.COLLIDED).sum() >= 50
     env.close()
 
 
@@ -152,8 +184,9 @@ def _lockstep(n, level, steps, seed, stages, cfg2=False):
     assert np.array_equal(out["mask_steps"], ref["mask_steps"].astype(np.uint8))
     rng = np.random.default_rng(10_000 + seed)
     tl = Tally()
+    tl.flips = []
     live = np.ones(n, dtype=bool)
-    for _ in range(steps):
+    for k in range(steps):
         act = rng.uniform(-1.0, 1.0, size=(n, 2))
         a_dev = torch.as_tensor(act, device=env.device).contiguous()
         if cfg2:
@@ -168,7 +201,8 @@ def _lockstep(n, level, steps, seed, stages, cfg2=False):
             tl.exact("retreated(collision)", out["retreated"], ref["retreated"], live)
             tl.exact("substeps", out["substeps"], ref["substeps"], live)
         else:
-            compare_step(tl, out, {**ref, "mask_steps": ref["mask_steps"].astype(np.uint8)}, orc.pose, live)
+            nf = compare_step(tl, out, {**ref, "mask_steps": ref["mask_steps"].astype(np.uint8)}, orc.pose, live)
+            tl.flips += [(k, e) for e in np.flatnonzero(nf)]
         live &= ref["status"] == 1  # the oracle env has no auto-reset: stop comparing finished episodes
     return tl, env
 
@@ -187,7 +221,8 @@ def test_full_step_mixed_levels_vs_oracle():
     """BASELINE cfg 3 at a size the oracle finishes in seconds: all stages, levels cycled."""
     tl, env = _lockstep(3072, "mix", 48, 7, capi.STAGE_ALL)
     tl.report("full step 3072 mixed scenes x 48 steps")
-    assert_bars(tl, rs_found_slack=max(2, tl.n // 500))
+    assert_bars(tl)
+    check_rs_found("lockstep:3072x48", tl.flips)
     c = env.counters()
     print("  counters:", c)
     assert c["rs_capacity_overflows"] == 0 and c["rs_zero_length_words"] == 0
@@ -256,13 +291,16 @@ def test_edge_cases_empty_and_ragged_scenes():
     assert np.abs(out["lidar"][0] - (10.0 - tb["lidar_base"])).max() <= FLOAT_TOL
     rng = np.random.default_rng(1)
     tl = Tally()
-    for _ in range(20):
+    flips = []
+    for k in range(20):
         act = rng.uniform(-1, 1, size=(3, 2))
         env.step(torch.as_tensor(act, device=env.device).contiguous())
         ref = orc.step(act)
-        compare_step(tl, gather(env), {**ref, "mask_steps": ref["mask_steps"].astype(np.uint8)}, orc.pose, ref["status"] >= 1)
+        nf = compare_step(tl, gather(env), {**ref, "mask_steps": ref["mask_steps"].astype(np.uint8)}, orc.pose, ref["status"] >= 1)
+        flips += [(k, e) for e in np.flatnonzero(nf)]
     tl.report("edge cases")
-    assert_bars(tl, rs_found_slack=1)
+    assert_bars(tl)
+    check_rs_found("edge_cases:3x20", flips)
     env.close()
 
 
@@ -295,14 +333,17 @@ def test_device_generated_scenes_are_valid_and_step_like_the_oracle():
     assert np.abs(out["lidar"] - ref["lidar"]).max() <= FLOAT_TOL
     rng = np.random.default_rng(4)
     tl = Tally(); live = np.ones(n, dtype=bool)
-    for _ in range(16):
+    flips = []
+    for k in range(16):
         act = rng.uniform(-1, 1, size=(n, 2))
         env.step(torch.as_tensor(act, device=env.device).contiguous())
         ref = orc.step(act)
-        compare_step(tl, gather(env), {**ref, "mask_steps": ref["mask_steps"].astype(np.uint8)}, orc.pose, live)
+        nf = compare_step(tl, gather(env), {**ref, "mask_steps": ref["mask_steps"].astype(np.uint8)}, orc.pose, live)
+        flips += [(k, e) for e in np.flatnonzero(nf)]
         live &= ref["status"] == 1
     tl.report("device-generated scenes, 3072 x 16 steps")
-    assert_bars(tl, rs_found_slack=2)
+    assert_bars(tl)
+    check_rs_found("device_scenes:3072x16", flips)
     env.close()
 
 
@@ -346,6 +387,7 @@ def test_full_size_65536_placement_invariance_and_oracle_subset():
     orc = po.OracleEnv(*[base[k][sub] for k in ("start", "dest", "bounds", "obs", "nverts")])
     env.reset(); orc.reset_step(stages=1)
     tl = Tally(); live = np.ones(len(sub), dtype=bool)
+    flips = []
     keys = ("pose", "lidar", "mask", "mask_steps", "target", "reward", "reward_info", "status", "done", "substeps", "retreated",
             "rs_found", "rs_nseg", "rs_types", "rs_lengths", "rs_L", "rs_ncand", "rs_ntried")
     for step in range(12):
@@ -360,10 +402,12 @@ def test_full_size_65536_placement_invariance_and_oracle_subset():
         for k in keys:
             assert np.array_equal(out[k][:half], out[k][half:]), (step, k)
         ref = orc.step(a_half[sub])
-        compare_step(tl, {k: out[k][sub] for k in keys}, {**ref, "mask_steps": ref["mask_steps"].astype(np.uint8)}, orc.pose, live)
+        nf = compare_step(tl, {k: out[k][sub] for k in keys}, {**ref, "mask_steps": ref["mask_steps"].astype(np.uint8)}, orc.pose, live)
+        flips += [(step, e) for e in np.flatnonzero(nf)]
         live &= ref["status"] == 1
     tl.report("65536 envs, oracle subset 1536 x 12 steps")
-    assert_bars(tl, rs_found_slack=2)
+    assert_bars(tl)
+    check_rs_found("full_size:1536x12", flips)
     env.close()
 
 

@@ -89,12 +89,26 @@ def test_rs_following_episodes(golden_dir, level):
     assert _replay(os.path.join(golden_dir, f"episodes_follow_{level}.npz")) > 1000
 
 
+def test_env_collide_episodes(golden_dir):
+    """ENV_COLLIDE = True (configs.py:79): 75 random-action episodes of all three levels recorded from the unmodified reference
+    with the flag on; a collision on the first substep ends the episode with status COLLIDED (car_parking_base.py:264-267, 279-282)."""
+    lib = po.lib()
+    lib.orc_set_env_collide(1)
+    try:
+        assert _replay(os.path.join(golden_dir, "episodes_collide.npz")) > 3000
+    finally:
+        lib.orc_set_env_collide(0)
+    assert (np.load(os.path.join(golden_dir, "episodes_collide.npz"))["status"] == 3).sum() >= 50
+
+
 def test_golden_covers_every_status(golden_dir):
     seen = set()
     for level in LEVELS:
         for stem in ("episodes", "episodes_follow"):
             seen |= set(np.load(os.path.join(golden_dir, f"{stem}_{level}.npz"))["status"].tolist())
-    assert {1, 2, 4, 5} <= seen  # COLLIDED (3) is unreachable with ENV_COLLIDE=False (configs.py:79)
+    assert {1, 2, 4, 5} <= seen  # COLLIDED (3) is unreachable with ENV_COLLIDE=False (configs.py:79) ...
+    seen |= set(np.load(os.path.join(golden_dir, "episodes_collide.npz"))["status"].tolist())
+    assert {1, 2, 3, 4, 5} <= seen  # ... and comes from the ENV_COLLIDE=True recording
 
 
 def test_geometry_predicates_agree_with_python_restatement():
