@@ -46,8 +46,10 @@ class DeviceReplay(object):
 
     KEYS = (("lidar", 120), ("target", 5), ("action_mask", 42))
 
-    def __init__(self, capacity, device):
+    def __init__(self, capacity, device, keys=None):
         self.capacity, self.device, self.size, self.head = int(capacity), device, 0, 0
+        if keys is not None:
+            self.KEYS = tuple(keys)
         f = lambda *s: torch.zeros(s, dtype=torch.float32, device=device)
         self.obs = {k: f(capacity, d) for k, d in self.KEYS}
         self.nxt = {k: f(capacity, d) for k, d in self.KEYS}
@@ -82,8 +84,8 @@ class FlatGradAllReduce(object):
     is a few MB, latency-bound on NVLink).  `launch` is asynchronous; `wait` averages and
     scatters the result back into the .grad tensors."""
 
-    def __init__(self, modules, world):
-        self.params = [p for m in modules for p in m.parameters() if p.requires_grad]
+    def __init__(self, modules, world, extra_params=()):
+        self.params = [p for m in modules for p in m.parameters() if p.requires_grad] + [p for p in extra_params if p.requires_grad]
         self.world = world
         self.numel = sum(p.numel() for p in self.params)
         self.bucket = torch.zeros(self.numel, dtype=torch.float32, device=self.params[0].device)
@@ -127,7 +129,8 @@ class SacLite(object):
         self.opt_actor = torch.optim.Adam(list(self.actor.parameters()), lr=lr)
         self.opt_q = torch.optim.Adam(list(self.q1.parameters()) + list(self.q2.parameters()), lr=lr)
         self.opt_alpha = torch.optim.Adam([self.log_alpha], lr=lr)
-        self.reducer = FlatGradAllReduce([self.actor, self.q1, self.q2], world)
+        # the temperature is a replicated parameter too: its gradient rides in the same bucket, or the ranks' alphas drift apart
+        self.reducer = FlatGradAllReduce([self.actor, self.q1, self.q2], world, extra_params=[self.log_alpha])
 
     def _pi(self, obs):
         mean = self.actor(obs)

@@ -132,21 +132,32 @@ class RolloutEngine(object):
             action, _ = masked_discrete_actions(mean, std, obs["action_mask"], self.actions42, self.gen)
         else:
             action = torch.clamp(mean + std * torch.randn(mean.shape, dtype=mean.dtype, device=mean.device, generator=self.gen), -1, 1)
-        log_prob = (-0.5 * ((action - mean) / std) ** 2 - torch.log(std) - 0.5 * math.log(2 * math.pi))
-        return action.contiguous(), log_prob
+        return action.contiguous(), (mean, std)
+
+    @staticmethod
+    def log_prob(action, dist):
+        """Gaussian log-density of `action` under the policy's (mean, std) (ppo_agent.py get_log_prob)"""
+        mean, std = dist
+        return -0.5 * ((action - mean) / std) ** 2 - torch.log(std) - 0.5 * math.log(2 * math.pi)
 
     @torch.no_grad()
     def collect(self, n_steps, store=None):
-        """Run n_steps env steps.  `store`, if given, is called with (t, obs, action, reward, done, log_prob,
-        executing) device tensors each step (views into buffers that the next step overwrites)."""
+        """Run n_steps env steps.  `store`, if given, is called each step with (t, obs, action, reward, done, log_prob, executing):
+        `obs` is the observation the policy ACTED ON (the env writes its outputs in place, so it is copied before the step when a
+        store is given), `action` the action the env executed — the Reeds-Shepp plan's where a route is being executed — and
+        `log_prob` the policy's log-density of that executed action (parking_agent.py:93-97 recomputes it for plan actions)."""
         env = self.env
         for t in range(n_steps):
-            action, log_prob = self.act(self.obs)
+            action, dist = self.act(self.obs)
             executing = None
             if self.use_planner:
                 action, executing = env.planner_actions(action)
+            acted_on = None
+            if store is not None:
+                acted_on = {k: (v.clone() if v is not None else None) for k, v in self.obs.items()}
+                log_prob = self.log_prob(action, dist)
             obs, reward, done, info = env.step(action)
             if store is not None:
-                store(t, self.obs, action, reward, done, log_prob, executing)
+                store(t, acted_on, action, reward, done, log_prob, executing)
             self.obs = obs
         return self.obs

@@ -106,3 +106,41 @@ def test_rollout_engine_runs_device_resident():
     assert c1["env_steps"] - c0["env_steps"] > 20 * n
     assert eng.norm.n == 24 * n and torch.isfinite(eng.norm.mean["lidar"]).all()
     env.close()
+
+
+def test_stored_transition_pairs_the_action_with_the_observation_it_was_chosen_from():
+    """the env writes its outputs in place: what `store` receives must be the observation act() saw, not the next one, and the
+    log-probability must be that of the EXECUTED action (the plan's where a route is being executed, parking_agent.py:93-97)"""
+    import math
+    n = 2048
+    env = BatchedParkingEnv(n, scenes=generate_scenes(2 * n, "Normal", 4), auto_reset=True)
+    actor = rollout.ReferenceShapedActor().to(env.device)
+    eng = rollout.RolloutEngine(env, actor, seed=0)
+    seen, dists = [], []
+    orig_act = eng.act
+
+    def spy_act(obs):
+        seen.append({k: obs[k].clone() for k in ("lidar", "target", "action_mask")})
+        a, dist = orig_act(obs)
+        dists.append(dist)
+        return a, dist
+
+    eng.act = spy_act
+    n_exec = [0]
+
+    def store(t, obs, action, reward, done, log_prob, executing):
+        for k in ("lidar", "target", "action_mask"):
+            assert torch.equal(obs[k], seen[t][k]), (t, k)
+        mean, std = dists[t]
+        want = -0.5 * ((action - mean) / std) ** 2 - torch.log(std) - 0.5 * math.log(2 * math.pi)
+        assert torch.equal(log_prob, want)
+        ex = executing.bool()
+        n_exec[0] += int(ex.sum())
+        if ex.any():  # plan actions are {-1,0,1} steers with unit or remainder speeds: not what the sampler drew
+            assert torch.all((action[ex, 0] == 0) | (action[ex, 0].abs() == 1))
+
+    eng.collect(40, store=store)
+    torch.cuda.synchronize()
+    assert len(seen) == 40 and n_exec[0] > 0
+    assert not torch.equal(seen[0]["lidar"], seen[1]["lidar"])
+    env.close()
