@@ -274,8 +274,9 @@ class BatchedParkingEnv(object):
             raise capi.HopeError("palette must be (25, 3) uint8")
         capi.check(self.lib.hope_set_palette(self.ctx, a.ctypes.data), self.ctx)
 
-    def profile(self, on=True):
-        capi.check(self.lib.hope_profile_enable(self.ctx, 1 if on else 0), self.ctx)
+    def profile(self, on=True, serial=False):
+        """per-kernel CUDA-event timing; serial=True keeps the whole step on one stream so every kernel is timed running alone"""
+        capi.check(self.lib.hope_profile_enable(self.ctx, (2 if serial else 1) if on else 0), self.ctx)
 
     def profile_read(self):
         """{kernel: (total_ms, launches)} measured with CUDA events on the launch stream."""

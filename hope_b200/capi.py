@@ -84,6 +84,9 @@ def load_library(max_obs=16):
         "hope_planner_actions": (C.c_int, [vp, dp, C.POINTER(Out), dp, vp, C.c_double, vp]),
         "hope_planner_reset": (C.c_int, [vp, vp]),
         "hope_fp64_peak_tflops": (C.c_int, [i32, C.POINTER(C.c_double)]),
+        "hope_state_norm_scratch_bytes": (C.c_int, [i32]),
+        "hope_state_norm": (C.c_int, [dp, dp, dp, i32, dp, C.c_double, i32, vp, vp, vp, vp, vp]),
+        "hope_masked_sample": (C.c_int, [i32, vp, dp, dp, dp, u64, u64, dp, vp, vp, vp]),
         "hope_profile_enable": (C.c_int, [vp, i32]),
         "hope_profile_read": (C.c_int, [vp, C.POINTER(C.c_double * 8), C.POINTER(u64 * 8)]),
     }

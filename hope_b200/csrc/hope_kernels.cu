@@ -505,6 +505,7 @@ struct hope_ctx {
     bool dev_pending = false;
     unsigned long long launches = 0;
     bool profile = false;
+    bool profile_serial = false;  // hope_profile_enable(ctx, 2): no k_observe / Reeds-Shepp overlap, so each kernel is timed alone
     std::vector<cudaEvent_t> prof_events[8];  // begin/end pairs per kernel
     std::string last_error;
 };
@@ -627,7 +628,7 @@ int launch_range(hope_ctx *ctx, const double *d_action, const hope_out &out_all,
     // next to them on the auxiliary one; measured equal within 2 % (11.0 vs 10.8 ms per 65 536-env step), so off
     const bool image_last = image && (stages & HOPE_STAGE_RS) && !ctx->in_host_step && ctx->render_after_rs;
     const bool side = (stages & HOPE_STAGE_OBSERVE) || (image && !image_last);  // work that only depends on k_advance, besides RS
-    const bool fork = side && (stages & HOPE_STAGE_RS);
+    const bool fork = side && (stages & HOPE_STAGE_RS) && !(ctx->profile && ctx->profile_serial);
     cudaStream_t so = fork ? lane.aux : s;
     if (side) {
         if (fork) {
@@ -1413,6 +1414,7 @@ int hope_fp64_peak_tflops(int device, double *tflops) {
 int hope_profile_enable(hope_ctx *ctx, int on) {
     if (!ctx) return HOPE_ERR_INVALID;
     ctx->profile = on != 0;
+    ctx->profile_serial = on == 2;
     return HOPE_OK;
 }
 

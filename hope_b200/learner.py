@@ -166,6 +166,18 @@ class SacLite(object):
         self.reducer.launch()
         return lq.detach(), la.detach()
 
+    def time_allreduce(self, reps=5):
+        """milliseconds of the flat gradient all-reduce alone (launch + wait, nothing overlapping), CUDA events"""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.reducer.launch(); self.reducer.wait()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            self.reducer.launch(); self.reducer.wait()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
     def apply(self):
         self.reducer.wait()
         self.opt_q.step(); self.opt_actor.step(); self.opt_alpha.step()

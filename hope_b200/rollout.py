@@ -13,10 +13,12 @@ stock PyTorch (bf16 autocast -> tensor cores); everything else stays in float64 
 """
 import math
 
+import ctypes as C
+
 import torch
 from torch import nn
 
-from . import tables
+from . import capi, tables
 
 N_ACTION = 42
 
@@ -70,33 +72,160 @@ class RunningNorm(object):
         return out
 
 
-class ReferenceShapedActor(nn.Module):
-    """Same shapes as MultiObsEmbedding(ACTOR_CONFIGS) with the image modality off: three 2-layer tanh
-    embeddings -> 3 x 128 tokens -> one pre-norm transformer block (8 heads x 32, FF 128) ->
-    Linear(384,128) tanh Linear(128,2) tanh   (network.py:34-196, attention.py:16-92)."""
+class FusedStateNorm(object):
+    """RunningNorm as one C-ABI call (hope_state_norm, csrc/policy_glue.cu): batch Welford + Chan merge of the running
+    statistics, normalisation and the float32 cast for the network in three small launches instead of ~20 elementwise
+    PyTorch kernels over (N, 120) float64 tensors.  Same statistics as RunningNorm (tests/test_gpu_rollout.py)."""
 
-    def __init__(self, lidar=120, target=5, mask=42, embed=128, heads=8, dim_head=32, mlp=128, hidden=128, out=2):
+    def __init__(self, n_envs, device):
+        self.lib = capi.load_library()
+        self.device, self.n_envs, self.n = device, int(n_envs), 0
+        self.stats = torch.zeros((2, 125), dtype=torch.float64, device=device)   # mean, M2 of [lidar | target]
+        self.scratch = torch.zeros(self.lib.hope_state_norm_scratch_bytes(self.n_envs), dtype=torch.uint8, device=device)
+        f32 = lambda *s: torch.zeros(s, dtype=torch.float32, device=device)
+        self.out = {"lidar": f32(self.n_envs, 120), "target": f32(self.n_envs, 5), "action_mask": f32(self.n_envs, 42)}
+
+    @property
+    def mean(self):
+        return {"lidar": self.stats[0, :120], "target": self.stats[0, 120:]}
+
+    @property
+    def m2(self):
+        return {"lidar": self.stats[1, :120], "target": self.stats[1, 120:]}
+
+    def __call__(self, obs, update=True):
+        """obs: the env's float64 lidar / target / action_mask tensors -> float32 network inputs (buffers reused every call)"""
+        n = obs["lidar"].shape[0]
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        capi.check(self.lib.hope_state_norm(obs["lidar"].data_ptr(), obs["target"].data_ptr(), obs["action_mask"].data_ptr(), n,
+                                            self.stats.data_ptr(), float(self.n), 1 if update else 0, self.scratch.data_ptr(),
+                                            self.out["lidar"].data_ptr(), self.out["target"].data_ptr(), self.out["action_mask"].data_ptr(), stream))
+        if update:
+            self.n += n
+        return self.out
+
+
+class FusedMaskedSampler(object):
+    """masked_discrete_actions as one kernel (hope_masked_sample): 42 clipped Gaussian log-densities x mask per env and an
+    inverse-CDF draw from a Philox stream keyed by (seed, step, env)."""
+
+    def __init__(self, n_envs, device, seed=0):
+        self.lib = capi.load_library()
+        self.device, self.seed, self.step = device, int(seed), 0
+        self.actions42 = possible_actions(device).contiguous()
+        self.action = torch.zeros((n_envs, 2), dtype=torch.float64, device=device)
+        self.index = torch.zeros(n_envs, dtype=torch.int32, device=device)
+        self.u = torch.zeros(n_envs, dtype=torch.float64, device=device)
+
+    def __call__(self, mean_f32, log_std, mask):
+        n = mean_f32.shape[0]
+        assert mean_f32.dtype == torch.float32 and mean_f32.is_contiguous() and mask.dtype == torch.float64
+        ls = log_std.detach().double().contiguous()
+        capi.check(self.lib.hope_masked_sample(n, mean_f32.data_ptr(), ls.data_ptr(), mask.data_ptr(), self.actions42.data_ptr(), self.seed, self.step,
+                                               self.action.data_ptr(), self.index.data_ptr(), self.u.data_ptr(),
+                                               torch.cuda.current_stream(self.device).cuda_stream))
+        self.step += 1
+        return self.action, self.index
+
+
+class _ConvBlock(nn.Module):
+    """network.py:198-232 with the shipped switches (no batch norm, residual on, tanh): conv3x3 -> tanh -> maxpool2, plus the
+    conv1x1 -> avgpool2 shortcut"""
+
+    def __init__(self, cin, cout, k=3):
+        super().__init__()
+        self.layer = nn.Sequential(nn.Conv2d(cin, cout, kernel_size=k, padding=k // 2), nn.Tanh(), nn.MaxPool2d(2))
+        self.shortcut = nn.Sequential(nn.Conv2d(cin, cout, kernel_size=1), nn.AvgPool2d(2))
+
+    def forward(self, x):
+        return self.layer(x) + self.shortcut(x)
+
+
+class _ImgEncoder(nn.Module):
+    """network.py:278-299: two conv blocks (3 -> 4 -> 8 channels), flatten, Linear(2048, 256), tanh, mean / std heads"""
+
+    def __init__(self, shape=(3, 64, 64), convs=(4, 8), fc=256, embed=128):
+        super().__init__()
+        c, w, h = shape
+        layers, cin = [], c
+        for cout in convs:
+            layers.append(_ConvBlock(cin, cout))
+            cin = cout
+        layers += [nn.Flatten(), nn.Linear(w * h * convs[-1] // (4 ** len(convs)), fc), nn.Tanh()]
+        self.net = nn.Sequential(*layers)
+        self.output_mean, self.output_std = nn.Linear(fc, embed), nn.Linear(fc, embed)
+
+    def forward(self, x):
+        x = self.net(x)
+        return self.output_mean(x), self.output_std(x)
+
+
+class ReferenceShapedActor(nn.Module):
+    """The reference's actor, `MultiObsEmbedding(ACTOR_CONFIGS)` (network.py:34-196, attention.py:16-92, configs.py:134-153),
+    restated so that it runs where the reference tree is not importable (the GPU box): per-modality 2-layer tanh embeddings
+    (lidar, target, action mask and — with use_img — the ImgEncoder conv stack + re-embedding) -> n_modal x 128 tokens -> one
+    pre-norm transformer block (8 heads x 32, FF 128) -> Linear(n_modal * 128, 128) tanh Linear(128, 2) tanh.
+    Parameter names follow the reference module tree, so `load_state_dict(MultiObsEmbedding(...).state_dict())` and the
+    `actor_net` of the shipped checkpoints load as they are (tests/test_policy_shape.py checks outputs against the real class)."""
+
+    def __init__(self, lidar=120, target=5, mask=42, embed=128, heads=8, dim_head=32, mlp=128, hidden=128, out=2, use_img=False):
         super().__init__()
         emb = lambda d: nn.Sequential(nn.Linear(d, embed), nn.Tanh(), nn.Linear(embed, embed))
         self.embed_lidar, self.embed_tgt, self.embed_am = emb(lidar), emb(target), emb(mask)
-        self.norm1, self.norm2 = nn.LayerNorm(embed), nn.LayerNorm(embed)
+        self.use_img = bool(use_img)
+        if self.use_img:
+            self.embed_img = _ImgEncoder(embed=embed)
+            self.re_embed_img = nn.Sequential(nn.Tanh(), nn.Linear(embed, embed))
+        self.n_modal = 3 + int(self.use_img)
         self.heads, self.dim_head = heads, dim_head
-        self.to_qkv = nn.Linear(embed, heads * dim_head * 3, bias=False)
-        self.to_out = nn.Linear(heads * dim_head, embed)
-        self.ff = nn.Sequential(nn.Linear(embed, mlp), nn.Tanh(), nn.Linear(mlp, embed))
-        self.head = nn.Sequential(nn.Linear(3 * embed, hidden), nn.Tanh(), nn.Linear(hidden, out))
-        self.log_std = nn.Parameter(torch.zeros(out))
+        inner = heads * dim_head
+        attn = nn.Module()
+        attn.norm = nn.LayerNorm(embed)
+        attn.fn = nn.Module()
+        attn.fn.to_qkv = nn.Linear(embed, inner * 3, bias=False)
+        attn.fn.to_out = nn.Sequential(nn.Linear(inner, embed), nn.Identity())
+        ff = nn.Module()
+        ff.norm = nn.LayerNorm(embed)
+        ff.fn = nn.Module()
+        ff.fn.net = nn.Sequential(nn.Linear(embed, mlp), nn.Tanh(), nn.Identity(), nn.Linear(mlp, embed), nn.Identity())
+        self.net = nn.Module()
+        self.net.encoder = nn.Module()
+        self.net.encoder.layers = nn.ModuleList([nn.ModuleList([attn, ff])])
+        self.net.output = nn.Sequential(nn.Linear(self.n_modal * embed, hidden), nn.Tanh(), nn.Linear(hidden, out))
+        self.net.view_embed = nn.Parameter(torch.zeros(1, self.n_modal, embed))  # present (and unused) in the reference too
+        self.log_std = nn.Parameter(torch.zeros(out))  # the agents keep it next to the net (ppo_agent.py / sac_agent.py); not a key of the net
 
     def forward(self, obs):
-        x = torch.stack([self.embed_lidar(obs["lidar"]), self.embed_tgt(obs["target"]), self.embed_am(obs["action_mask"])], dim=1)
+        feats = [self.embed_lidar(obs["lidar"]), self.embed_tgt(obs["target"]), self.embed_am(obs["action_mask"])]
+        if self.use_img:
+            feats.append(self.re_embed_img(self.embed_img(obs["img"])[0]))
+        x = torch.stack(feats, dim=1)
         b, n, _ = x.shape
-        q, k, v = self.to_qkv(self.norm1(x)).view(b, n, 3, self.heads, self.dim_head).permute(2, 0, 3, 1, 4)
-        # 3 tokens per env: explicit softmax(q k^T / sqrt(d)) v like attention.py:33-46 (the fused SDPA back ends
+        attn, ff = self.net.encoder.layers[0]
+        q, k, v = attn.fn.to_qkv(attn.norm(x)).view(b, n, 3, self.heads, self.dim_head).permute(2, 0, 3, 1, 4)
+        # n_modal tokens per env: explicit softmax(q k^T / sqrt(d)) v like attention.py:33-46 (the fused SDPA back ends
         # reject a 65 536 x 8-head batch of 3-token sequences)
         a = torch.matmul(torch.softmax(torch.matmul(q, k.transpose(-1, -2)) * (self.dim_head ** -0.5), dim=-1), v)
-        x = self.to_out(a.transpose(1, 2).reshape(b, n, self.heads * self.dim_head)) + x
-        x = self.ff(self.norm2(x)) + x
-        return torch.tanh(self.head(x.reshape(b, n * x.shape[-1])))
+        x = attn.fn.to_out(a.transpose(1, 2).reshape(b, n, self.heads * self.dim_head)) + x
+        x = ff.fn.net(ff.norm(x)) + x
+        return torch.tanh(self.net.output(x.reshape(b, n * x.shape[-1])))
+
+
+def reference_actor(use_img=False, device=None):
+    """The policy of BASELINE cfg 4: the reference's own `MultiObsEmbedding(ACTOR_CONFIGS)` when its tree is importable
+    (src/ on sys.path), else the restatement above.  Returns (module, description)."""
+    try:
+        from model.network import MultiObsEmbedding  # the reference's src/model, untouched
+        import configs
+        cfg = dict(configs.ACTOR_CONFIGS)
+        cfg["img_shape"] = (3, 64, 64) if use_img else None
+        cfg["n_modal"] = 3 + int(use_img)
+        net, what = MultiObsEmbedding(cfg), "model.network.MultiObsEmbedding(ACTOR_CONFIGS) from the reference tree"
+    except Exception:
+        net, what = ReferenceShapedActor(use_img=use_img), "ReferenceShapedActor (restatement of MultiObsEmbedding(ACTOR_CONFIGS); reference tree not importable here)"
+    if not hasattr(net, "log_std"):
+        net.log_std = nn.Parameter(torch.zeros(2))
+    return (net.to(device) if device is not None else net), what
 
 
 class RolloutEngine(object):
@@ -104,29 +233,74 @@ class RolloutEngine(object):
     RS plan override -> env.step, all on the device; no host synchronisation inside `collect`."""
 
     def __init__(self, env, policy, log_std=None, use_planner=True, use_mask_sampling=True, state_norm=True,
-                 autocast_dtype=torch.bfloat16, seed=0):
+                 autocast_dtype=torch.bfloat16, seed=0, fused=True, graph=True):
+        """fused: state norm and masked sampling through the CUDA kernels of csrc/policy_glue.cu (False: the eager PyTorch
+        versions above, kept as their numerics reference).  graph: the policy forward is captured once into a CUDA graph
+        and replayed (one launch instead of ~60 small kernels per step)."""
         self.env, self.policy = env, policy
         dev = env.device
         self.actions42 = possible_actions(dev)
         self.use_planner, self.use_mask_sampling = use_planner, use_mask_sampling
-        self.norm = RunningNorm({"lidar": (120,), "target": (5,)}, dev) if state_norm else None
+        self.fused = bool(fused) and state_norm and use_mask_sampling
+        self.norm = (FusedStateNorm(env.n, dev) if self.fused else RunningNorm({"lidar": (120,), "target": (5,)}, dev)) if state_norm else None
+        self.sampler = FusedMaskedSampler(env.n, dev, seed) if self.fused else None
         self.log_std = log_std if log_std is not None else getattr(policy, "log_std", torch.zeros(2, device=dev))
         self.autocast_dtype = autocast_dtype
         self.gen = torch.Generator(device=dev); self.gen.manual_seed(seed)
+        self.use_img = env.use_img and getattr(policy, "use_img", False)
+        self._graph, self._graph_in, self._graph_out = None, None, None
+        self.use_graph = bool(graph) and self.fused
+        self.glue = ("hope_state_norm + hope_masked_sample kernels (csrc/policy_glue.cu)" if self.fused else "eager PyTorch") + \
+                    (", policy forward replayed from a CUDA graph" if self.use_graph else "")
         self.obs = env.reset()
         if use_planner:
             env.planner_reset()
 
+    def _forward(self, net_in):
+        with torch.autocast("cuda", dtype=self.autocast_dtype, enabled=self.autocast_dtype is not None):
+            return self.policy(net_in).float()
+
+    def _policy_mean(self, net_in):
+        """float32 policy output for the (persistent) float32 input buffers `net_in`"""
+        if not self.use_graph:
+            return self._forward(net_in)
+        if self._graph is None:
+            self._graph_in = net_in
+            side = torch.cuda.Stream(device=self.env.device)
+            side.wait_stream(torch.cuda.current_stream(self.env.device))
+            with torch.cuda.stream(side):  # warm-up outside the capture (cuBLAS workspaces, autocast weight casts)
+                for _ in range(2):
+                    self._forward(net_in)
+            torch.cuda.current_stream(self.env.device).wait_stream(side)
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._graph_out = self._forward(net_in)
+        assert all(net_in[k] is self._graph_in[k] for k in net_in), "the captured policy reads the persistent input buffers"
+        self._graph.replay()
+        return self._graph_out
+
     @torch.no_grad()
     def act(self, obs):
+        if self.fused:
+            net_in = dict(self.norm(obs))                      # float32 lidar / target / action_mask, statistics updated
+            if self.use_img:
+                if not hasattr(self, "_img_f32"):
+                    self._img_f32 = torch.zeros(obs["img"].shape, dtype=torch.float32, device=self.env.device)
+                torch.mul(obs["img"], 1.0 / 255.0, out=self._img_f32)   # the reference's float image (observation_processor.py:13-17)
+                net_in["img"] = self._img_f32
+            mean32 = self._policy_mean(net_in).contiguous()
+            action, _ = self.sampler(mean32, self.log_std, obs["action_mask"])
+            mean = torch.clamp(mean32.double(), -1, 1)
+            std = torch.exp(self.log_std.detach().double()).expand_as(mean)
+            return action, (mean, std)
         o = {"lidar": obs["lidar"], "target": obs["target"]}
         if self.norm is not None:
             self.norm.update(o)
             o = self.norm(o)
         net_in = {"lidar": o["lidar"].float(), "target": o["target"].float(), "action_mask": obs["action_mask"].float()}
-        with torch.autocast("cuda", dtype=self.autocast_dtype, enabled=self.autocast_dtype is not None):
-            mean = self.policy(net_in)
-        mean = torch.clamp(mean.double(), -1, 1)  # ppo_agent.py:141
+        if self.use_img:
+            net_in["img"] = obs["img"].float() / 255.0
+        mean = torch.clamp(self._forward(net_in).double(), -1, 1)  # ppo_agent.py:141
         std = torch.exp(self.log_std.detach().double()).expand_as(mean)
         if self.use_mask_sampling:
             action, _ = masked_discrete_actions(mean, std, obs["action_mask"], self.actions42, self.gen)

@@ -197,6 +197,23 @@ int hope_planner_actions(hope_ctx *ctx, const double *d_policy_action, const hop
                          uint8_t *d_executing, double step_ratio, void *stream);
 int hope_planner_reset(hope_ctx *ctx, void *stream);
 
+/* The two non-GEMM steps between the env and the policy network of the rollout loop (row f2), stateless (no context):
+ *
+ * hope_state_norm — StateNorm.state_norm (model/state_norm.py:25-46) for a batch: with update != 0 the running statistics
+ *   d_stats[2][125] (mean then M2 of the 120 lidar + 5 target columns; the caller keeps the sample count and passes the count
+ *   BEFORE this batch) take in all n observations (Welford per block, Chan merge), then every observation is normalised as
+ *   (x - mean) / (std + 1e-8), std = sqrt(M2 / count), and written as float32; d_mask [n][42] (optional) is cast along.
+ *   d_scratch: hope_state_norm_scratch_bytes(n) bytes of device memory.
+ * hope_masked_sample — ActionMask.choose_action (model/action_mask.py:199-227) for a batch: d_mean[n][2] float32 policy output
+ *   (clamped to [-1,1]), d_log_std[2], d_mask[n][42], d_actions[42][2] = discrete actions in policy scale; draws one action per env
+ *   by inverse CDF from a Philox4x32-10 stream keyed by (seed, step, env).  d_index_out / d_u_out (optional): the index drawn
+ *   and the uniform variate used. */
+int hope_state_norm_scratch_bytes(int n);
+int hope_state_norm(const double *d_lidar, const double *d_target, const double *d_mask, int n, double *d_stats, double count_before,
+                    int update, void *d_scratch, float *d_out_lidar, float *d_out_target, float *d_out_mask, void *stream);
+int hope_masked_sample(int n, const float *d_mean, const double *d_log_std, const double *d_mask, const double *d_actions, uint64_t seed,
+                       uint64_t step, double *d_action_out, int32_t *d_index_out, double *d_u_out, void *stream);
+
 /* State access (device -> host copies; synchronous). */
 int hope_get_state(hope_ctx *ctx, double *h_pose, int32_t *h_t, double *h_accum, int32_t *h_scene_id);
 int hope_set_state(hope_ctx *ctx, const double *h_pose, const int32_t *h_t, const double *h_accum);
@@ -204,8 +221,9 @@ int hope_set_state(hope_ctx *ctx, const double *h_pose, const int32_t *h_t, cons
  * fallbacks taken, [3] RS word-capacity overflows, [4] RS zero-length words (reference asserts),
  * [5] kernels launched by this context, [6] scenes generated on the device */
 int hope_get_counters(hope_ctx *ctx, uint64_t h_counters[8]);
-/* Per-kernel device timing: when enabled every kernel launch of a step is bracketed by CUDA
- * events on the launch stream.  hope_profile_read synchronises, returns the accumulated
+/* Per-kernel device timing: when enabled (on = 1) every kernel launch of a step is bracketed by CUDA
+ * events on the launch stream; on = 2 additionally keeps all kernels of hope_step on ONE stream (k_observe does not overlap
+ * the Reeds-Shepp chain), so each duration is that kernel running alone inside the live loop.  hope_profile_read synchronises, returns the accumulated
  * milliseconds and launch counts per kernel [0] advance [1] observe [2] rs_enumerate [3] rs_walk
  * [4] rs_check [5] rs_select [6] render ([7] reserved) since the last read, and clears them. */
 int hope_profile_enable(hope_ctx *ctx, int on);

@@ -1,5 +1,7 @@
 """GPU tests of the rollout-side rows (a19, f2): batched RS planner hand-off vs a restatement of
 RsPlanner/ParkingAgent, masked discrete sampling, and the device-resident acting loop."""
+import math
+
 import numpy as np
 import pytest
 
@@ -144,3 +146,116 @@ def test_stored_transition_pairs_the_action_with_the_observation_it_was_chosen_f
     assert len(seen) == 40 and n_exec[0] > 0
     assert not torch.equal(seen[0]["lidar"], seen[1]["lidar"])
     env.close()
+
+
+def test_fused_state_norm_kernel_equals_the_torch_reference_and_the_recording(golden_dir):
+    """hope_state_norm (csrc/policy_glue.cu) against RunningNorm (plain PyTorch float64, itself pinned on the reference's StateNorm by
+    tests/test_rollout_helpers.py) and against the recording of the unmodified StateNorm directly"""
+    import os
+    g = dict(np.load(os.path.join(golden_dir, "f2_helpers.npz")))
+    dev = torch.device("cuda")
+    n_all = len(g["norm_lidar"])
+    for batch in (96, 512, n_all):
+        fused = rollout.FusedStateNorm(batch, dev)
+        ref = rollout.RunningNorm({"lidar": (120,), "target": (5,)}, dev)
+        for lo in range(0, n_all - batch + 1, batch):
+            obs = {"lidar": torch.as_tensor(g["norm_lidar"][lo:lo + batch], device=dev).contiguous(),
+                   "target": torch.as_tensor(g["norm_target"][lo:lo + batch], device=dev).contiguous(),
+                   "action_mask": torch.rand((batch, 42), dtype=torch.float64, device=dev)}
+            out = fused(obs)
+            ref.update({"lidar": obs["lidar"], "target": obs["target"]})
+            want = ref({"lidar": obs["lidar"], "target": obs["target"]})
+            for k in ("lidar", "target"):
+                assert out[k].dtype == torch.float32
+                # float32 outputs: equal to the float64 reference within float32 rounding of values up to ~1e2
+                assert torch.allclose(out[k].double(), want[k], rtol=2e-7, atol=2e-6), (batch, lo, k, (out[k].double() - want[k]).abs().max())
+            assert torch.equal(out["action_mask"], obs["action_mask"].float())
+        assert fused.n == ref.n
+        for k in ("lidar", "target"):
+            assert torch.allclose(fused.mean[k], ref.mean[k], rtol=1e-12, atol=1e-12)
+            assert torch.allclose(fused.m2[k], ref.m2[k], rtol=1e-10, atol=1e-9)
+        if fused.n == n_all:  # every recorded observation went in: the reference's final statistics
+            std = torch.sqrt(fused.m2["lidar"] / fused.n).cpu().numpy()
+            np.testing.assert_allclose(fused.mean["lidar"].cpu().numpy(), g["norm_mean_lidar"], rtol=1e-12, atol=1e-12)
+            np.testing.assert_allclose(std, g["norm_std_lidar"], rtol=1e-10, atol=1e-12)
+            probe = {"lidar": torch.as_tensor(g["norm_probe_lidar"], device=dev)[None].repeat(batch, 1).contiguous(),
+                     "target": torch.as_tensor(g["norm_probe_target"], device=dev)[None].repeat(batch, 1).contiguous(),
+                     "action_mask": torch.ones((batch, 42), dtype=torch.float64, device=dev)}
+            out = fused(probe, update=False)
+            np.testing.assert_allclose(out["lidar"][0].cpu().numpy(), g["norm_probe_out_lidar"], rtol=1e-6, atol=1e-6)
+            np.testing.assert_allclose(out["target"][3].cpu().numpy(), g["norm_probe_out_target"], rtol=1e-6, atol=1e-6)
+            assert fused.n == n_all  # update=False leaves the statistics alone
+
+
+def test_fused_masked_sampler_kernel_draws_from_choose_actions_distribution(golden_dir):
+    """hope_masked_sample against the probabilities ActionMask.choose_action hands to np.random.choice (recorded from the reference)
+    and against the inverse-CDF rule evaluated in PyTorch float64 with the kernel's own uniform variates"""
+    import os
+    g = dict(np.load(os.path.join(golden_dir, "f2_helpers.npz")))
+    dev = torch.device("cuda")
+    acts = rollout.possible_actions(dev)
+    # (1) exact: given u, the drawn index is the first one whose cumulative weight exceeds u * total
+    n = 50000
+    gen = torch.Generator(device=dev); gen.manual_seed(3)
+    mean = (torch.rand((n, 2), device=dev, generator=gen) * 2.4 - 1.2).float().contiguous()   # partly outside [-1, 1]: clamped like ppo_agent.py:141
+    log_std = torch.tensor([-0.4, 0.2], dtype=torch.float64, device=dev)
+    mask = torch.round(torch.rand((n, 42), dtype=torch.float64, device=dev, generator=gen) * 10) / 10
+    mask *= (torch.rand((n, 42), device=dev, generator=gen) < 0.5)
+    mask[:, 5] = torch.clamp(mask[:, 5], min=0.1)
+    smp = rollout.FusedMaskedSampler(n, dev, seed=11)
+    action, idx = smp(mean, log_std, mask)
+    torch.cuda.synchronize()
+    m = torch.clamp(mean.double(), -1, 1)
+    std = torch.exp(log_std).expand_as(m)
+    z = (acts.unsqueeze(0) - m.unsqueeze(1)) / std.unsqueeze(1)
+    lp = -0.5 * z * z - torch.log(math.sqrt(2 * math.pi) * std).unsqueeze(1)
+    e = torch.exp(torch.clamp(lp, -10, 10).sum(dim=2)) * mask
+    cdf = torch.cumsum(e, dim=1)
+    want = (cdf > (smp.u * cdf[:, -1]).unsqueeze(1)).float().argmax(dim=1)
+    same = (want == idx.long())
+    assert same.float().mean() > 0.9995, float(same.float().mean())      # sequential vs pairwise summation may flip a boundary case
+    assert (mask.gather(1, idx.long().unsqueeze(1)) > 0).all()            # never a masked action
+    assert torch.equal(action, acts[idx.long()])
+    u = smp.u.cpu().numpy()
+    assert abs(u.mean() - 0.5) < 0.01 and abs(np.quantile(u, 0.1) - 0.1) < 0.01 and 0 <= u.min() and u.max() < 1
+    a2, idx2 = smp(mean, log_std, mask)                                   # next step: a different stream position
+    assert (idx2 != idx).float().mean() > 0.3
+    # (2) distribution: 20 000 draws per recorded (mean, std, mask) triple against the reference's probabilities
+    for row in (0, 7, 50, 123):
+        k = 20000
+        mean_r = torch.as_tensor(g["choose_mean"][row], device=dev).float().expand(k, 2).contiguous()
+        ls = torch.log(torch.as_tensor(g["choose_std"][row], device=dev))
+        mask_r = torch.as_tensor(g["choose_mask"][row], device=dev).expand(k, 42).contiguous()
+        s2 = rollout.FusedMaskedSampler(k, dev, seed=row)
+        _, ix = s2(mean_r, ls, mask_r)
+        got = np.bincount(ix.cpu().numpy(), minlength=42) / k
+        want_p = g["choose_prob"][row]
+        assert (got[want_p == 0] == 0).all()
+        assert np.abs(got - want_p).max() < 4 * np.sqrt(0.25 / k) + 1e-3, (row, np.abs(got - want_p).max())
+
+
+def test_rollout_engine_fused_path_and_eager_path_agree_in_distribution():
+    """the engine with the CUDA glue kernels + graph-replayed policy vs the eager PyTorch engine: same running statistics after the
+    same env steps when both are driven by the same actions"""
+    n = 4096
+    sc = generate_scenes(2 * n, "mix", 9)
+    env_a = BatchedParkingEnv(n, scenes=sc, auto_reset=True)
+    env_b = BatchedParkingEnv(n, scenes=sc, auto_reset=True)
+    torch.manual_seed(0)
+    actor = rollout.ReferenceShapedActor().to(env_a.device)
+    fused = rollout.RolloutEngine(env_a, actor, seed=0, fused=True, graph=True)
+    eager = rollout.RolloutEngine(env_b, actor, seed=0, fused=False)
+    assert "policy_glue" in fused.glue and "CUDA graph" in fused.glue and eager.glue == "eager PyTorch"
+    for t in range(6):
+        a, (mean_f, _) = fused.act(fused.obs)
+        _, (mean_e, _) = eager.act(eager.obs)
+        assert torch.allclose(mean_f, mean_e, atol=3e-2), (t, (mean_f - mean_e).abs().max())   # bf16 policy on float32-rounded vs float64-normalised inputs
+        a = a.clone()
+        fused.obs = env_a.step(a)[0]
+        eager.obs = env_b.step(a)[0]
+    assert fused.norm.n == eager.norm.n == 6 * n
+    assert torch.allclose(fused.norm.mean["lidar"], eager.norm.mean["lidar"], rtol=1e-12, atol=1e-12)
+    assert torch.allclose(fused.norm.m2["target"], eager.norm.m2["target"], rtol=1e-10, atol=1e-9)
+    fused.collect(8)
+    torch.cuda.synchronize()
+    env_a.close(); env_b.close()
