@@ -62,6 +62,7 @@ def run_variant(args, name, defs, env_a, scenes, act, total):
         return t.view(torch.int64) if t.dtype == torch.float64 else t
 
     env_a.reset(); env_b.reset()
+    ca0, cb0 = env_a.counters(), env_b.counters()
     mismatches, compared = {}, 0
     for k in range(total):
         env_a.step(act[k]); env_b.step(act[k])
@@ -71,7 +72,8 @@ def run_variant(args, name, defs, env_a, scenes, act, total):
         compared += 1
     ca, cb = env_a.counters(), env_b.counters()
     say(args.out, stage="parity", variant=name, steps_compared=compared, fields=len(env_a.out), mismatching_elements=mismatches,
-        env_steps_a=ca["env_steps"], env_steps_b=cb["env_steps"], identical=(not mismatches and ca["env_steps"] == cb["env_steps"]))
+        env_steps_a=ca["env_steps"] - ca0["env_steps"], env_steps_b=cb["env_steps"] - cb0["env_steps"],
+        identical=(not mismatches and ca["env_steps"] - ca0["env_steps"] == cb["env_steps"] - cb0["env_steps"]))
 
     def timed(env, k0):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -94,6 +96,12 @@ def run_variant(args, name, defs, env_a, scenes, act, total):
             env.step(act[k % total])
         pr = env.profile_read(); env.profile(False)
         say(args.out, stage="kernels_" + which, variant=name, ms_per_launch={kn: (v[0] / v[1] if v[1] else None) for kn, v in pr.items()})
+    for which, env in (("a", env_a), ("b", env_b), ("a", env_a), ("b", env_b)):  # each kernel alone (no observe / Reeds-Shepp overlap): the figure to compare kernels on
+        env.profile(True, serial=True); env.profile_read()
+        for k in range(20):
+            env.step(act[k % total])
+        pr = env.profile_read(); env.profile(False)
+        say(args.out, stage="kernels_serial_" + which, variant=name, ms_per_launch={kn: (v[0] / v[1] if v[1] else None) for kn, v in pr.items()})
     env_b.close()
 
 

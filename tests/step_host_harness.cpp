@@ -32,6 +32,10 @@ struct alignas(16) double2 { double x, y; };
 struct alignas(16) double4 { double x, y, z, w; };
 static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 static inline double4 make_double4(double x, double y, double z, double w) { return double4{x, y, z, w}; }
+struct alignas(16) float4 { float x, y, z, w; };
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+static inline float __double2float_rd(double a) { float f = (float)a; return (double)f > a ? std::nextafterf(f, -INFINITY) : f; }
+static inline float __double2float_ru(double a) { float f = (float)a; return (double)f < a ? std::nextafterf(f, INFINITY) : f; }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
 using std::max;
 using std::min;

@@ -204,6 +204,7 @@ def test_fused_masked_sampler_kernel_draws_from_choose_actions_distribution(gold
     mask[:, 5] = torch.clamp(mask[:, 5], min=0.1)
     smp = rollout.FusedMaskedSampler(n, dev, seed=11)
     action, idx = smp(mean, log_std, mask)
+    action, idx = action.clone(), idx.clone()   # the sampler reuses its output buffers
     torch.cuda.synchronize()
     m = torch.clamp(mean.double(), -1, 1)
     std = torch.exp(log_std).expand_as(m)
