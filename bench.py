@@ -81,7 +81,7 @@ def reduce_scalar(x, op, world, device):
 def host_threads_for_rank(world):
     """host threads one rank may use (mask expansion inside hope_step_host): the box's CPUs shared evenly"""
     cpus = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    return max(1, min(6, cpus // max(1, world) - 1))
+    return max(1, min(12, cpus // max(1, world) - 1))
 
 
 def _dist_env():
@@ -486,7 +486,8 @@ def main():
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     c3 = env.counters()
     e2e_steps = sum_over_ranks(float(c3["env_steps"] - c2["env_steps"]))
-    h2d, d2h = env.host_io_bytes()
+    wire = env.host_wire_info()  # counted by the library from the copies of the last step (the kept lidar values are data dependent)
+    h2d, d2h = wire["h2d_bytes"], wire["d2h_bytes"]
     # context for the e2e number: what a plain pinned D2H copy of the lidar buffer achieves on this box while EVERY rank copies
     pin = torch.empty_like(env.out["lidar"], device="cpu").pin_memory()
     barrier()
@@ -531,8 +532,10 @@ def main():
                        "l2": "per-step working set (scene pool 2N x 1.7 KB + outputs N x 1.5 KB = 320 MB) exceeds the 126 MB L2; no explicit flush",
                        "counted": "env-steps with an action; auto-reset steps excluded"},
             "e2e": {"value": e2e_steps / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "hope_step_host (pinned host buffers, synchronous; the float64 mask crosses PCIe as uint8 step counts and is expanded by "
-                           f"{os.environ['HOPE_B200_HOST_THREADS']} host threads inside the call)",
+                    "api": "hope_step_host (pinned host buffers, synchronous; lossless narrow wire format: the float64 mask crosses PCIe as uint8 step counts, "
+                           "the float64 lidar as 120 flag bits + the beams that differ from the per-ray no-hit constant; "
+                           f"{wire['host_threads']} host threads rebuild both arrays inside the call, AVX-512 {'on' if wire['avx512'] else 'off'})",
+                    "wire": wire,
                     "host_bytes_delivered_per_step": int(env.n * 1436), "ms_per_step": 1e3 * e2e_s / K,
                     "d2h_gbs_per_rank_in_step": d2h / (e2e_s / K) / 1e9,
                     "plain_d2h_copy_gbs": {"per_rank_min": pcie_min, "all_ranks_sum": pcie_sum, "note": "all ranks copying at the same time"}},

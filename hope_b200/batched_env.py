@@ -218,17 +218,18 @@ class BatchedParkingEnv(object):
         capi.check(self.lib.hope_reset_host(self.ctx, ids.ctypes.data if ids is not None else None, C.byref(st)), self.ctx)
         return {k: self._host[k].numpy() for k in outputs}
 
-    def host_io_bytes(self, outputs=HOST_DEFAULT):
-        """(h2d, d2h) bytes one step_host call moves over PCIe.  The float64 action mask travels as its 42 uint8
-        step counts and is expanded by host threads inside hope_step_host (unless HOPE_B200_HOST_MASK_EXPAND=0)."""
-        import os
-        narrow_mask = os.environ.get("HOPE_B200_HOST_MASK_EXPAND", "1") != "0"
-        d2h = 0
-        for name, ct, shape in capi.OUT_FIELDS:
-            if name in outputs:
-                size = C.sizeof(C.c_uint8) if (name == "mask" and narrow_mask) else C.sizeof(ct)
-                d2h += self.n * int(np.prod(shape, dtype=np.int64)) * size
-        return self.n * 2 * 8, d2h
+    def host_io_bytes(self):
+        """(h2d, d2h) bytes the LAST step_host call moved over PCIe, counted by the library from the copies it issued.  The
+        float64 action mask travels as its 42 uint8 step counts and the lidar as flag bits + the beams that hit something;
+        host threads inside hope_step_host rebuild both (HOPE_B200_HOST_MASK_EXPAND=0 / HOPE_B200_HOST_LIDAR_PACK=0 turn it off)."""
+        w = self.host_wire_info()
+        return w["h2d_bytes"], w["d2h_bytes"]
+
+    def host_wire_info(self):
+        info = (C.c_uint64 * 8)()
+        capi.check(self.lib.hope_host_wire_info(self.ctx, C.byref(info)), self.ctx)
+        return {"h2d_bytes": int(info[0]), "d2h_bytes": int(info[1]), "mask_narrow": bool(info[2]), "lidar_packed": bool(info[3]),
+                "host_threads": int(info[4]), "avx512": bool(info[5]), "env_ranges": int(info[6])}
 
     # ---- state / diagnostics -------------------------------------------------------------------
     def get_state(self):

@@ -67,6 +67,9 @@ def load_library(max_obs=16):
         "hope_upload_tables": (C.c_int, [vp] + [dp] * 7),
         "hope_set_palette": (C.c_int, [vp, vp]),
         "hope_expand_mask": (C.c_int, [vp, vp, i32]),
+        "hope_expand_mask_portable": (C.c_int, [vp, vp, i32]),
+        "hope_expand_lidar": (C.c_int, [vp, vp, vp, vp, vp, i32, i32]),
+        "hope_host_wire_info": (C.c_int, [vp, C.POINTER(u64 * 8)]),
         "hope_set_scene_pool": (C.c_int, [vp, i32, i32, dp, dp, dp, dp, ip]),
         "hope_generate_scenes": (C.c_int, [i32, i32, u64, i32, dp, dp, dp, dp, ip, ip]),
         "hope_generate_scene_pool_device": (C.c_int, [vp, i32, i32, i32, u64, vp]),

@@ -23,6 +23,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -32,7 +33,10 @@
 #include <vector>
 
 #include "../../include/hope_b200.h"
+#include <sched.h>
+
 #include "hope_device.cuh"
+#include "host_wire.h"
 #include "scene_gen.h"
 
 namespace hope {
@@ -360,6 +364,50 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters, doubl
 
 __global__ void k_bump_seq(unsigned long long *seq) { *seq += 1ull; }
 
+// k_pack_lidar: one warp per env, behind k_observe in the host API.  A beam that hits nothing within range reads exactly
+// lidar_range - lidar_base[ray] (observe_body.inc: clip to the range, subtract the vehicle's extent; lidar_simulator.py:46,134),
+// 43 % of the beams of a random-action step.  Only the values whose BITS differ from that per-ray constant are kept: bits[env]
+// flags them (bit j of word q = ray 32 q + j), off[env] is where the env's kept values start in its sub-range's region of
+// `packed` (one atomic per env on the sub-range's counter, so the order of envs in `packed` varies from run to run while the
+// expansion on the host does not).
+// Streaming kernel: reads 960 B per env (still in L2 behind k_observe), writes 20 B + 8 B per kept beam.
+static_assert(NRAY <= 128, "k_pack_lidar: four 32-bit flag words per env");
+__global__ void __launch_bounds__(128) k_pack_lidar(int n, const double *__restrict__ lidar, const double *__restrict__ lidar_base, double range,
+                                                    uint32_t *__restrict__ bits, uint32_t *__restrict__ off, double *__restrict__ packed,
+                                                    unsigned *__restrict__ count, int sub) {
+    const int env = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (env >= n) return;
+    const int g = env / sub;          // sub-range of the launch's env range: own counter, own region of `packed`
+    count += g;
+    packed += (size_t)g * sub * NRAY;
+    const double *row = lidar + (size_t)env * NRAY;
+    double v[4];
+    unsigned m[4];
+    int total = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int j = q * 32 + lane;
+        const bool in = j < NRAY;
+        v[q] = in ? row[j] : 0.0;
+        const double nohit = in ? range - __ldg(lidar_base + j) : 0.0;
+        m[q] = __ballot_sync(HOPE_FULL_MASK, in && __double_as_longlong(v[q]) != __double_as_longlong(nohit));
+        total += __popc(m[q]);
+    }
+    unsigned base = 0;
+    if (lane == 0 && total) base = atomicAdd(count, (unsigned)total);
+    base = __shfl_sync(HOPE_FULL_MASK, base, 0);
+    if (lane == 0) {
+        *reinterpret_cast<uint4 *>(bits + 4 * (size_t)env) = make_uint4(m[0], m[1], m[2], m[3]);
+        off[env] = base;
+    }
+    unsigned pos = base;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if ((m[q] >> lane) & 1) packed[pos + __popc(m[q] & ((1u << lane) - 1))] = v[q];
+        pos += __popc(m[q]);
+    }
+}
+
 __global__ void k_table_group(const double *__restrict__ pmax, double *__restrict__ gpmax) {
     int q = threadIdx.x;
     if (q >= NRAY) return;
@@ -378,36 +426,41 @@ using namespace hope;
 // A few persistent host threads for the one piece of host-side work in hope_step_host (expanding the uint8
 // action-mask steps into the float64 mask while the remaining copies are still travelling).
 struct HostPool {
+    // Jobs are queued by the stepping thread and run in order; every worker runs its own share (part, nparts) of each job
+    // and moves on without waiting for the others (the jobs of one step write disjoint memory).
     std::vector<std::thread> workers;
     std::mutex m;
     std::condition_variable cv, done_cv;
-    std::function<void(int, int)> job;  // (part, nparts)
-    int generation = 0, pending = 0;
+    std::vector<std::function<void(int, int)>> jobs;  // of the current step; cleared by wait_all
+    std::vector<size_t> progress;                      // per worker: jobs finished
     bool stop = false;
     void start(int n) {
+        progress.assign(n, 0);
         for (int w = 0; w < n; ++w)
             workers.emplace_back([this, w, n] {
-                int seen = 0;
                 for (;;) {
                     std::function<void(int, int)> f;
                     {
                         std::unique_lock<std::mutex> lk(m);
-                        cv.wait(lk, [&] { return stop || generation != seen; });
+                        cv.wait(lk, [&] { return stop || progress[w] < jobs.size(); });
                         if (stop) return;
-                        seen = generation;
-                        f = job;
+                        f = jobs[progress[w]];
                     }
                     f(w, n);
                     std::lock_guard<std::mutex> lk(m);
-                    if (--pending == 0) done_cv.notify_one();
+                    if (++progress[w] == jobs.size()) done_cv.notify_one();
                 }
             });
     }
-    void run(const std::function<void(int, int)> &f) {
-        std::unique_lock<std::mutex> lk(m);
-        job = f; pending = (int)workers.size(); ++generation;
+    void submit(std::function<void(int, int)> f) {
+        { std::lock_guard<std::mutex> lk(m); jobs.push_back(std::move(f)); }
         cv.notify_all();
-        done_cv.wait(lk, [&] { return pending == 0; });
+    }
+    void wait_all() {
+        std::unique_lock<std::mutex> lk(m);
+        done_cv.wait(lk, [&] { for (size_t p : progress) if (p < jobs.size()) return false; return true; });
+        jobs.clear();
+        for (size_t &p : progress) p = 0;
     }
     ~HostPool() {
         { std::lock_guard<std::mutex> lk(m); stop = true; }
@@ -459,7 +512,7 @@ struct hope_ctx {
     struct Lane { cudaStream_t main = nullptr, aux = nullptr; cudaEvent_t ev_advanced = nullptr, ev_observed = nullptr; } lanes[MAX_LANES];
     int host_chunks = 2;   // measured on B200 at 65 536 envs with the narrow mask format: 2 -> 2.18 ms, 3 -> 2.21, 4 -> 2.35 per
                            // host step (with the float64 mask copied: 2 -> 2.60, 3 -> 2.53, 4 -> 2.63, 8 -> 3.30)
-    bool host_rs_after_observe = true;
+    bool host_rs_after_observe = false;  // HOPE_B200_HOST_RS_AFTER=1: start the Reeds-Shepp kernels behind the last k_observe range (better when the copies, not the kernels, bound the step)
     bool in_host_step = false;
     bool render_after_rs = false;
     bool image_ok = true;  // false: the vehicle box is too large for k_render's per-box span table
@@ -469,8 +522,37 @@ struct hope_ctx {
     // still in flight.  HOPE_B200_HOST_MASK_EXPAND=0 copies the float64 mask instead.
     bool host_mask_expand = true, expanding = false;
     uint8_t *h_mask_steps = nullptr;   // pinned [N][42]
+    // Same idea for the lidar (960 B per env, 84 % of the bytes): beams that hit nothing read a per-ray constant, so
+    // k_pack_lidar keeps the others and the host threads rebuild the float64 rows (host_wire.cpp).  The kept values of an env
+    // range are copied by a cudaMemcpyAsync the stepping thread issues as soon as the range's count has landed (its size is
+    // only known then, so it cannot be part of the replayed graph).  HOPE_B200_HOST_LIDAR_PACK=0 copies the float64 rows.
+    bool host_lidar_pack = true, packing = false;
+    uint32_t *d_lbits = nullptr, *d_loff = nullptr, *h_lbits = nullptr, *h_loff = nullptr;   // [N][4], [N]
+    double *d_lpacked = nullptr, *h_lpacked = nullptr;                                        // [N][120] worst case; range c uses [lo_c * 120, ...)
+    unsigned *d_lcount = nullptr, *h_lcount = nullptr;                                        // [MAX_CHUNK_EVENTS] kept values per range
+    cudaStream_t s_pack = nullptr;
+    cudaEvent_t ev_pack[64] = {};
+    // an env range's kept values are packed, copied and expanded in sub-ranges of pk_sub envs (own counter, own copy, own
+    // expansion job), so the host work left when the last copy lands is one sub-range, not one range
+    int pk_sub = 8192, pk_total = 0;
+    int pk_lo[64] = {}, pk_hi[64] = {}, pk_first[65] = {};   // sub-range g covers envs [pk_lo, pk_hi); range c owns sub-ranges [pk_first[c], pk_first[c+1])
+    double h_nohit[HOPE_N_LIDAR] = {};   // lidar_range - lidar_base[ray], the same float64 subtraction k_observe performs
+    int wire_force_portable = 0;
+    bool host_noexpand = false;  // HOPE_B200_HOST_NOEXPAND=1: timing experiments only (the host arrays are not rebuilt)
+    // HOPE_B200_HOST_TRACE=k: the k-th hope_step_host call (and every 50th after it) is enqueued directly instead of replayed
+    // from the graph, with timing events between its parts, and its device and host timelines are printed to stderr as JSON
+    int host_trace = 0;
+    bool tracing = false;
+    unsigned long long host_steps = 0;
+    std::vector<std::pair<std::string, cudaEvent_t>> trace_ev;
+    std::vector<std::pair<std::string, double>> trace_host;
+    std::chrono::steady_clock::time_point trace_t0;
+    unsigned long long io_h2d = 0, io_d2h = 0, io_d2h_static = 0;   // bytes of the last hope_step_host (static = the part enqueued / captured)
     HostPool *host_pool = nullptr;
-    int hm_chunks = 0, hm_per = 0;
+    int host_threads = 0;
+    int hm_chunks = 0;
+    int ch_lo[65] = {};      // env range c of the pipelined host step = [ch_lo[c], ch_lo[c + 1])
+    std::string host_split;  // HOPE_B200_HOST_SPLIT="50,30,20": the ranges as percentages of the envs instead of host_chunks equal ones
     // "range c's step counts have landed": a device sequence number, bumped once per host step, is copied into
     // pinned host memory right behind each range's step counts (same stream, so in order); the host spins on it.
     // (An event recorded inside a replayed graph cannot be used for this: until the node runs it still reports the
@@ -541,19 +623,54 @@ void prof_mark(hope_ctx *ctx, int which, cudaStream_t s) {
     ctx->prof_events[which].push_back(e);
 }
 
+void tmark(hope_ctx *ctx, const char *what, int idx, cudaStream_t s) {  // device timeline of a traced host step
+    if (!ctx->tracing) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, s);
+    ctx->trace_ev.emplace_back(idx >= 0 ? std::string(what) + "[" + std::to_string(idx) + "]" : std::string(what), e);
+}
+void hmark(hope_ctx *ctx, const char *what, int idx) {  // host timeline of a traced host step
+    if (!ctx->tracing) return;
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ctx->trace_t0).count();
+    ctx->trace_host.emplace_back(idx >= 0 ? std::string(what) + "[" + std::to_string(idx) + "]" : std::string(what), ms);
+}
+void trace_print(hope_ctx *ctx) {
+    if (!ctx->tracing) return;
+    std::string out = "{\"host_step\": " + std::to_string(ctx->host_steps) + ", \"device_ms\": {";
+    for (size_t k = 0; k < ctx->trace_ev.size(); ++k) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->trace_ev[0].second, ctx->trace_ev[k].second);
+        char buf[64]; snprintf(buf, sizeof(buf), "%.4f", ms);
+        out += (k ? ", \"" : "\"") + ctx->trace_ev[k].first + "\": " + buf;
+    }
+    out += "}, \"host_ms\": {";
+    for (size_t k = 0; k < ctx->trace_host.size(); ++k) {
+        char buf[64]; snprintf(buf, sizeof(buf), "%.4f", ctx->trace_host[k].second);
+        out += (k ? ", \"" : "\"") + ctx->trace_host[k].first + "\": " + buf;
+    }
+    out += "}}\n";
+    fputs(out.c_str(), stderr);
+    for (auto &e : ctx->trace_ev) cudaEventDestroy(e.second);
+    ctx->trace_ev.clear(); ctx->trace_host.clear();
+    ctx->tracing = false;
+}
+
 // Kernel order of one step.  k_observe and the Reeds-Shepp pair both depend only on k_advance, so when
 // both stages are requested k_observe goes to the context's auxiliary stream and overlaps the RS kernels;
 // the caller's stream waits for it before hope_step returns control of the stream.  With `early_out`
 // (host API) the observation buffers are copied to the host right behind k_observe, under the RS kernels.
-struct OutField { size_t offset; size_t elem; int per_env; int observe; };  // observe = 1: produced by k_observe
-#define OF(member, type, per) OutField{offsetof(hope_out, member), sizeof(type), per, 0}
-#define OFO(member, type, per) OutField{offsetof(hope_out, member), sizeof(type), per, 1}
+enum { BY_ADVANCE = 1, BY_OBSERVE = 2, BY_RS = 4, BY_ANY = 7 };  // which kernel produces an output array
+struct OutField { size_t offset; size_t elem; int per_env; int by; };
+#define OF(member, type, per) OutField{offsetof(hope_out, member), sizeof(type), per, BY_ADVANCE}
+#define OFO(member, type, per) OutField{offsetof(hope_out, member), sizeof(type), per, BY_OBSERVE}
+#define OFR(member, type, per) OutField{offsetof(hope_out, member), sizeof(type), per, BY_RS}
 const OutField kOutFields[] = {
     OF(pose, double, 3), OFO(lidar, double, NRAY), OFO(mask, double, NACT), OFO(mask_steps, uint8_t, NACT),
     OF(target, double, 5), OF(reward, double, 1), OF(reward_info, double, 5), OF(status, int32_t, 1),
     OF(done, uint8_t, 1), OF(substeps, uint8_t, 1), OF(retreated, uint8_t, 1), OF(was_reset, uint8_t, 1),
-    OF(rs_found, uint8_t, 1), OF(rs_nseg, uint8_t, 1), OF(rs_types, uint8_t, 5), OF(rs_lengths, double, 5),
-    OF(rs_L, double, 1), OF(rs_ncand, uint8_t, 1), OF(rs_ntried, uint8_t, 1), OFO(img, uint8_t, HOPE_IMG_C * HOPE_IMG_HW * HOPE_IMG_HW)};
+    OFR(rs_found, uint8_t, 1), OFR(rs_nseg, uint8_t, 1), OFR(rs_types, uint8_t, 5), OFR(rs_lengths, double, 5),
+    OFR(rs_L, double, 1), OFR(rs_ncand, uint8_t, 1), OFR(rs_ntried, uint8_t, 1), OFO(img, uint8_t, HOPE_IMG_C * HOPE_IMG_HW * HOPE_IMG_HW)};
 constexpr int kNumOutFields = sizeof(kOutFields) / sizeof(kOutFields[0]);
 
 void *&field_ptr(hope_out &o, const OutField &f) { return *reinterpret_cast<void **>(reinterpret_cast<char *>(&o) + f.offset); }
@@ -568,15 +685,17 @@ hope_out offset_out(const hope_out &o, size_t lo) {  // the same arrays, startin
     return r;
 }
 
-// observe: 1 = only k_observe's outputs, 0 = only the others, -1 = all; envs [lo, lo+cnt)
-int copy_fields(hope_ctx *ctx, const hope_host_out *h_out, int observe, cudaStream_t s, size_t lo, size_t cnt) {
+// by: the arrays of which producers to copy (BY_* bits); envs [lo, lo+cnt)
+int copy_fields(hope_ctx *ctx, const hope_host_out *h_out, int by, cudaStream_t s, size_t lo, size_t cnt) {
     if (ctx->host_debug == 1 && ctx->in_host_step) return HOPE_OK;
     for (int k = 0; k < kNumOutFields; ++k) {
         void *dst = field_ptr_c(*h_out, kOutFields[k]);
-        if (!dst || (observe >= 0 && kOutFields[k].observe != observe)) continue;
+        if (!dst || !(kOutFields[k].by & by)) continue;
         if ((ctx->zero_copy_mask >> k) & 1) continue;  // the kernels wrote this array straight into the caller's mapped buffer
         if (ctx->expanding && ctx->in_host_step && kOutFields[k].offset == offsetof(hope_out, mask)) continue;  // rebuilt on the host
+        if (ctx->packing && ctx->in_host_step && kOutFields[k].offset == offsetof(hope_out, lidar)) continue;   // rebuilt on the host
         const size_t row = kOutFields[k].elem * kOutFields[k].per_env;
+        if (ctx->in_host_step) ctx->io_d2h_static += row * cnt;
         CK(cudaMemcpyAsync(static_cast<char *>(dst) + lo * row, static_cast<const char *>(field_ptr_c(ctx->stage_out, kOutFields[k])) + lo * row,
                            row * cnt, cudaMemcpyDeviceToHost, s));
     }
@@ -651,7 +770,7 @@ int launch_range(hope_ctx *ctx, const double *d_action, const hope_out &out_all,
             prof_mark(ctx, 6, so);
             ctx->launches++;
         }
-        if (early_out) { int rc = copy_fields(ctx, early_out, 1, so, lo, cnt); if (rc) return rc; }
+        if (early_out) { int rc = copy_fields(ctx, early_out, BY_OBSERVE, so, lo, cnt); if (rc) return rc; }
         if (fork) CK(cudaEventRecord(lane.ev_observed, so));
     }
     if (stages & HOPE_STAGE_RS) {
@@ -860,6 +979,11 @@ int hope_create(hope_ctx **out, int device, int n_envs, int pool_size, const hop
     if (const char *e = getenv("HOPE_B200_DEVICE_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= 16) ctx->device_chunks = v; }
     if (const char *e = getenv("HOPE_B200_RENDER_AFTER_RS")) ctx->render_after_rs = atoi(e) != 0;
     if (const char *e = getenv("HOPE_B200_HOST_MASK_EXPAND")) ctx->host_mask_expand = atoi(e) != 0;
+    if (const char *e = getenv("HOPE_B200_HOST_LIDAR_PACK")) ctx->host_lidar_pack = atoi(e) != 0;
+    if (const char *e = getenv("HOPE_B200_WIRE_PORTABLE")) ctx->wire_force_portable = atoi(e) != 0;
+    if (const char *e = getenv("HOPE_B200_HOST_NOEXPAND")) ctx->host_noexpand = atoi(e) != 0;
+    if (const char *e = getenv("HOPE_B200_HOST_TRACE")) ctx->host_trace = atoi(e);
+    if (const char *e = getenv("HOPE_B200_HOST_SPLIT")) ctx->host_split = e;
     if (const char *e = getenv("HOPE_B200_HOST_DEBUG")) ctx->host_debug = atoi(e);
     if (const char *e = getenv("HOPE_B200_HOST_RS_AFTER")) ctx->host_rs_after_observe = atoi(e) != 0;
     if (const char *e = getenv("HOPE_B200_HOST_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->host_chunks = v; }
@@ -899,6 +1023,10 @@ int hope_destroy(hope_ctx *ctx) {
     for (auto e : ctx->ev_chunk) if (e) cudaEventDestroy(e);
     for (auto e : ctx->ev_adv) if (e) cudaEventDestroy(e);
     if (ctx->h_mask_steps) cudaFreeHost(ctx->h_mask_steps);
+    for (void *p : {(void *)ctx->d_lbits, (void *)ctx->d_loff, (void *)ctx->d_lpacked, (void *)ctx->d_lcount}) if (p) cudaFree(p);
+    for (void *p : {(void *)ctx->h_lbits, (void *)ctx->h_loff, (void *)ctx->h_lpacked, (void *)ctx->h_lcount}) if (p) cudaFreeHost(p);
+    if (ctx->s_pack) cudaStreamDestroy(ctx->s_pack);
+    for (auto e : ctx->ev_pack) if (e) cudaEventDestroy(e);
     if (ctx->h_seq) cudaFreeHost(const_cast<unsigned long long *>(ctx->h_seq));
     if (ctx->d_seq) cudaFree(ctx->d_seq);
     delete ctx->host_pool;
@@ -934,6 +1062,7 @@ int hope_upload_tables(hope_ctx *ctx, const double *ray_a, const double *ray_b, 
     memcpy(&head[0], ray_a, 120 * 8); memcpy(&head[120], ray_b, 120 * 8); memcpy(&head[240], lidar_base, 120 * 8);
     memcpy(&head[360], mask_base, 120 * 8); memcpy(&head[480], w_lo, 80); memcpy(&head[496], w_hi, 80);
     CK(cudaMemcpy(ctx->d_tab, head.data(), 512 * 8, cudaMemcpyHostToDevice));
+    for (int j = 0; j < NRAY; ++j) ctx->h_nohit[j] = ctx->par.lidar_range - lidar_base[j];
     double *ds = ctx->d_tab + 512;
     CK(cudaMemcpy(ds, dist_star, sizeof(double) * NUP * NACT * NITER, cudaMemcpyHostToDevice));
     double *pmaxk = ds + (size_t)NUP * NACT * NITER, *pmax = pmaxk + (size_t)NUP * NACT * NITER;
@@ -1113,74 +1242,133 @@ static void plan_zero_copy(hope_ctx *ctx, const hope_host_out *h_out) {
     }
 }
 
-// Decide whether this host step returns the action mask through its uint8 step counts (see hope_ctx::host_mask_expand).
-static int plan_mask_expand(hope_ctx *ctx, const hope_host_out *h_out, unsigned stages) {
-    const int mask_field = 2;  // index of `mask` in kOutFields
+// Decide which arrays of this host step travel in the narrow wire format (see hope_ctx::host_mask_expand, host_lidar_pack).
+static int plan_wire(hope_ctx *ctx, const hope_host_out *h_out, unsigned stages) {
+    const int lidar_field = 1, mask_field = 2;  // indices of `lidar`, `mask` in kOutFields
     ctx->expanding = ctx->host_mask_expand && h_out->mask && (stages & HOPE_STAGE_OBSERVE) && !((ctx->zero_copy_mask >> mask_field) & 1);
-    if (!ctx->expanding) return HOPE_OK;
-    if (!ctx->h_mask_steps) {
-        CK(cudaMallocHost(&ctx->h_mask_steps, (size_t)ctx->n * NACT));
+    ctx->packing = ctx->host_lidar_pack && h_out->lidar && (stages & HOPE_STAGE_OBSERVE) && !((ctx->zero_copy_mask >> lidar_field) & 1);
+    if (!ctx->expanding && !ctx->packing) return HOPE_OK;
+    if (!ctx->h_seq) {
         unsigned long long *hs = nullptr;
-        CK(cudaMallocHost(&hs, sizeof(unsigned long long) * hope_ctx::MAX_CHUNK_EVENTS));
-        memset(hs, 0, sizeof(unsigned long long) * hope_ctx::MAX_CHUNK_EVENTS);
+        CK(cudaMallocHost(&hs, sizeof(unsigned long long) * 2 * hope_ctx::MAX_CHUNK_EVENTS));  // two flags per env range
+        memset(hs, 0, sizeof(unsigned long long) * 2 * hope_ctx::MAX_CHUNK_EVENTS);
         ctx->h_seq = hs;
         CK(cudaMalloc(&ctx->d_seq, sizeof(unsigned long long)));
         CK(cudaMemset(ctx->d_seq, 0, sizeof(unsigned long long)));
         CK(cudaDeviceSynchronize());  // the step runs on non-blocking streams, which do not order after the memset
         ctx->host_seq = 0;
     }
+    if (ctx->expanding && !ctx->h_mask_steps) CK(cudaMallocHost(&ctx->h_mask_steps, (size_t)ctx->n * NACT));
+    if (ctx->packing && !ctx->d_lpacked) {
+        const size_t N = ctx->n;
+        CK(cudaMalloc(&ctx->d_lbits, sizeof(uint32_t) * 4 * N));
+        CK(cudaMalloc(&ctx->d_loff, sizeof(uint32_t) * N));
+        CK(cudaMalloc(&ctx->d_lpacked, sizeof(double) * NRAY * N));
+        CK(cudaMalloc(&ctx->d_lcount, sizeof(unsigned) * hope_ctx::MAX_CHUNK_EVENTS));
+        CK(cudaMallocHost(&ctx->h_lbits, sizeof(uint32_t) * 4 * N));
+        CK(cudaMallocHost(&ctx->h_loff, sizeof(uint32_t) * N));
+        CK(cudaMallocHost(&ctx->h_lpacked, sizeof(double) * NRAY * N + 64));  // + what the 8-wide expansion may read behind the last value
+        CK(cudaMallocHost(&ctx->h_lcount, sizeof(unsigned) * hope_ctx::MAX_CHUNK_EVENTS));
+        CK(cudaStreamCreateWithFlags(&ctx->s_pack, cudaStreamNonBlocking));
+        for (auto &e : ctx->ev_pack) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     if (!ctx->host_pool) {
         ctx->host_pool = new (std::nothrow) HostPool();
         if (!ctx->host_pool) return HOPE_ERR_INVALID;
-        int nt = 6;
+        // default: the CPUs this process may run on, shared by the ranks of the node (torchrun's LOCAL_WORLD_SIZE), one left
+        // to the stepping thread; HOPE_B200_HOST_THREADS overrides
+        int cpus = (int)std::thread::hardware_concurrency();
+        cpu_set_t set;
+        if (sched_getaffinity(0, sizeof(set), &set) == 0) cpus = CPU_COUNT(&set);
+        int ranks = 1;
+        if (const char *e = getenv("LOCAL_WORLD_SIZE")) { int v = atoi(e); if (v >= 1) ranks = v; }
+        int nt = cpus / ranks - 1;
+        nt = nt < 1 ? 1 : (nt > 12 ? 12 : nt);
         if (const char *e = getenv("HOPE_B200_HOST_THREADS")) { int v = atoi(e); if (v >= 1 && v <= 64) nt = v; }
+        ctx->host_threads = nt;
         ctx->host_pool->start(nt);
     }
-    ctx->step_out.mask = nullptr;  // k_observe does not write the float64 mask at all
+    if (ctx->expanding) ctx->step_out.mask = nullptr;  // k_observe does not write the float64 mask at all
     return HOPE_OK;
 }
 
-// action_mask.py:182-183 on the host: mask = steps / 10, or 0.01 everywhere when every step count of the env is 0
-// (the same expression k_observe evaluates; steps / 10 through a table of the 11 possible quotients).
-static void expand_mask_range(const uint8_t *steps, double *mask, size_t lo, size_t hi) {
-    double lut[NITER + 1];
-    for (int k = 0; k <= NITER; ++k) lut[k] = (double)k / 10;
-    for (size_t i = lo; i < hi; ++i) {
-        const uint8_t *sp = steps + i * NACT;
-        double *mp = mask + i * NACT;
-        unsigned total = 0;
-        for (int j = 0; j < NACT; ++j) total += sp[j];
-        if (total == 0) { for (int j = 0; j < NACT; ++j) mp[j] = 0.01; }
-        else { for (int j = 0; j < NACT; ++j) mp[j] = lut[sp[j] <= NITER ? sp[j] : NITER]; }
-    }
-}
-
-// After the step has been launched: expand each env range's mask as soon as its step counts have landed, then wait
-// for everything else.
+// After the step has been launched: the stepping thread watches the per-range flags.  When range c's narrow arrays have
+// landed it issues the copy of the range's kept lidar values (now that their count is known) and queues the mask expansion;
+// when that copy has finished it queues the lidar expansion.  Then it waits for the workers and for the rest of the step.
 static int finish_host_step(hope_ctx *ctx, const hope_host_out *h_out, cudaStream_t s0) {
-    if (ctx->expanding) {
-        double *mask = h_out->mask;
+    ctx->io_d2h = ctx->io_d2h_static;
+    if (ctx->expanding || ctx->packing) {
         const unsigned long long expected = ++ctx->host_seq;  // k_bump_seq ran (or will run) once more on the device
-        for (int c = 0; c < ctx->hm_chunks; ++c) {
-            volatile unsigned long long *flag = ctx->h_seq + c % hope_ctx::MAX_CHUNK_EVENTS;
-            for (unsigned spins = 0; *flag != expected; ++spins) {
-                if ((spins & 0xfff) == 0xfff) {  // the step died or finished without delivering: do not spin forever
-                    cudaError_t q = cudaStreamQuery(s0);
-                    if (q != cudaErrorNotReady) {
-                        if (q != cudaSuccess) return fail(ctx, q, "hope_step_host");
-                        if (*flag != expected) { ctx->last_error = "hope_step_host: mask step counts did not arrive"; return HOPE_ERR_CUDA; }
+        const int C = ctx->hm_chunks, portable = ctx->wire_force_portable;
+        const int G = ctx->packing ? ctx->pk_total : 0;
+        volatile unsigned long long *flag_a = ctx->h_seq, *flag_b = ctx->h_seq + hope_ctx::MAX_CHUNK_EVENTS;
+        int next_a = ctx->packing ? 0 : C, next_b = 0, next_lidar = 0, issued = 0;
+        for (unsigned spins = 0; next_a < C || next_b < C || next_lidar < G; ++spins) {
+            if (next_a < C && flag_a[next_a] == expected) {  // the range's sub-range counts are here: copy the kept values
+                const int c = next_a++;
+                hmark(ctx, "counts_seen", c);
+                for (int g = ctx->pk_first[c]; g < ctx->pk_first[c + 1]; ++g) {
+                    const size_t glo = ctx->pk_lo[g], kept = ctx->h_lcount[g];
+                    if (kept > (size_t)(ctx->pk_hi[g] - ctx->pk_lo[g]) * NRAY) { ctx->last_error = "hope_step_host: lidar pack count out of range"; return HOPE_ERR_CUDA; }
+                    if (g == ctx->pk_first[c]) tmark(ctx, "kept_copy_begin", c, ctx->s_pack);
+                    if (kept) CK(cudaMemcpyAsync(ctx->h_lpacked + glo * NRAY, ctx->d_lpacked + glo * NRAY, kept * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_pack));
+                    CK(cudaEventRecord(ctx->ev_pack[g], ctx->s_pack));
+                    ctx->io_d2h += kept * sizeof(double);
+                }
+                tmark(ctx, "kept_copy_end", c, ctx->s_pack);
+                hmark(ctx, "kept_copy_issued", c);
+                continue;
+            }
+            if (next_b < C && next_b < (ctx->packing ? next_a : C) && flag_b[next_b] == expected) {  // step counts, beam flags and offsets are here
+                const int c = next_b++;
+                const size_t lo = ctx->ch_lo[c], hi = ctx->ch_lo[c + 1];
+                hmark(ctx, "narrow_seen", c);
+                issued = ctx->packing ? ctx->pk_first[c + 1] : 0;
+                if (ctx->expanding && !ctx->host_noexpand) {
+                    const uint8_t *steps = ctx->h_mask_steps;
+                    double *mask = h_out->mask;
+                    ctx->host_pool->submit([=](int part, int nparts) {
+                        const size_t span = (hi - lo + nparts - 1) / nparts, a = lo + span * part, b = a + span < hi ? a + span : hi;
+                        if (a < b) hope_wire::expand_mask(steps, mask, a, b, portable);
+                    });
+                }
+                continue;
+            }
+            if (next_lidar < issued) {
+                const cudaError_t q = cudaEventQuery(ctx->ev_pack[next_lidar]);
+                if (q == cudaSuccess) {
+                    const int g = next_lidar++;
+                    hmark(ctx, "kept_copy_seen_done", g);
+                    if (ctx->host_noexpand) continue;
+                    const size_t lo = ctx->pk_lo[g], hi = ctx->pk_hi[g];
+                    const uint32_t *bits = ctx->h_lbits, *off = ctx->h_loff;
+                    const double *packed = ctx->h_lpacked + lo * NRAY, *nohit = ctx->h_nohit;
+                    double *lidar = h_out->lidar;
+                    ctx->host_pool->submit([=](int part, int nparts) {
+                        const size_t span = (hi - lo + nparts - 1) / nparts, a = lo + span * part, b = a + span < hi ? a + span : hi;
+                        if (a < b) hope_wire::expand_lidar(bits, off, packed, nohit, lidar, a, b, portable);
+                    });
+                    continue;
+                }
+                if (q != cudaErrorNotReady) return fail(ctx, q, "hope_step_host (lidar values)");
+            }
+            if ((spins & 0xfff) == 0xfff && (next_a < C || next_b < C)) {  // the step died or finished without delivering: do not spin forever
+                const cudaError_t q = cudaStreamQuery(s0);
+                if (q != cudaErrorNotReady) {
+                    if (q != cudaSuccess) return fail(ctx, q, "hope_step_host");
+                    if ((next_a < C && flag_a[next_a] != expected) || (next_b < C && flag_b[next_b] != expected)) {
+                        ctx->last_error = "hope_step_host: narrow observation arrays did not arrive";
+                        return HOPE_ERR_CUDA;
                     }
                 }
             }
-            const size_t lo = (size_t)c * ctx->hm_per, hi = (lo + ctx->hm_per < (size_t)ctx->n) ? lo + ctx->hm_per : (size_t)ctx->n;
-            const uint8_t *steps = ctx->h_mask_steps;
-            ctx->host_pool->run([=](int part, int nparts) {
-                const size_t span = (hi - lo + nparts - 1) / nparts, a = lo + span * part, b = a + span < hi ? a + span : hi;
-                if (a < b) expand_mask_range(steps, mask, a, b);
-            });
         }
+        hmark(ctx, "all_jobs_queued", -1);
+        ctx->host_pool->wait_all();
+        hmark(ctx, "workers_done", -1);
     }
     CK(cudaStreamSynchronize(s0));
+    hmark(ctx, "stream_synchronised", -1);
     return HOPE_OK;
 }
 
@@ -1201,58 +1389,142 @@ static int enqueue_host_step(hope_ctx *ctx, const double *h_action, const hope_h
     cudaStream_t s0 = ctx->lanes[0].main, s_obs = ctx->lanes[0].aux, s_copy = ctx->lanes[1].main;
     const double *d_act = h_action ? ctx->d_action : nullptr;  // NULL: step without motion (CarParking.step(None))
     const unsigned adv = HOPE_STAGE_ADVANCE | (stages & HOPE_STAGE_RAW_ACTION);
+    tmark(ctx, "start", -1, s0);
     if (h_action) CK(cudaMemcpyAsync(ctx->d_action, h_action, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, s0));
-    if (ctx->expanding) { k_bump_seq<<<1, 1, 0, s0>>>(ctx->d_seq); ctx->launches++; }
+    tmark(ctx, "actions_in", -1, s0);
+    ctx->io_h2d = h_action ? sizeof(double) * 2 * (size_t)n : 0;
+    ctx->io_d2h_static = 0;
+    const bool flagging = ctx->expanding || ctx->packing;
+    if (flagging) { k_bump_seq<<<1, 1, 0, s0>>>(ctx->d_seq); ctx->launches++; }
     int rc;
-    int chunks = ctx->host_chunks;
-    if (n < 4096 * chunks) chunks = n / 4096 > 0 ? n / 4096 : 1;
-    const int per = ((n + chunks - 1) / chunks + 127) / 128 * 128;
+    // env ranges of the pipeline: host_chunks equal ones, or the percentages of HOPE_B200_HOST_SPLIT; boundaries on multiples of 128
+    int C = 0;
+    {
+        int chunks = ctx->host_chunks;
+        if (n < 4096 * chunks) chunks = n / 4096 > 0 ? n / 4096 : 1;
+        std::vector<double> share;
+        if (!ctx->host_split.empty() && n >= 8192) {
+            const char *p = ctx->host_split.c_str();
+            while (*p) { char *end = nullptr; const double v = strtod(p, &end); if (end == p) break; if (v > 0) share.push_back(v); p = *end ? end + 1 : end; }
+            if ((int)share.size() > hope_ctx::MAX_CHUNK_EVENTS) share.clear();
+        }
+        if (share.empty()) share.assign(chunks, 1.0);
+        double total = 0, acc = 0;
+        for (double v : share) total += v;
+        ctx->ch_lo[0] = 0;
+        for (size_t k = 0; k < share.size(); ++k) {
+            acc += share[k];
+            int hi = k + 1 == share.size() ? n : (int)((double)n * acc / total + 127) / 128 * 128;
+            if (hi > n) hi = n;
+            if (hi > ctx->ch_lo[C]) ctx->ch_lo[++C] = hi;
+        }
+        if (ctx->ch_lo[C] != n) ctx->ch_lo[++C] = n;
+    }
     const bool split_advance = side && ctx->host_split_advance;  // k_advance per range too: the first range's k_observe starts earlier
     if (!split_advance) {
         rc = launch_range(ctx, d_act, ctx->step_out, adv, 0, s0, 0, 0, 0, n);
         if (rc) return rc;
+        tmark(ctx, "advance_end", -1, s0);
     }
     int last_chunk = 0;
+    bool advance_copied = false;
     if (side) {
         if (!split_advance) {
             CK(cudaEventRecord(ctx->ev_fork, s0));
             CK(cudaStreamWaitEvent(s_obs, ctx->ev_fork, 0));
+            CK(cudaStreamWaitEvent(s_copy, ctx->ev_fork, 0));
+            rc = copy_fields(ctx, h_out, BY_ADVANCE, s_copy, 0, n);
+            if (rc) return rc;
+            advance_copied = true;
         }
-        ctx->hm_per = per; ctx->hm_chunks = (n + per - 1) / per;
-        for (int c = 0, lo = 0; lo < n; ++c, lo += per) {
-            const int cnt = (lo + per <= n) ? per : n - lo;
+        ctx->hm_chunks = C;
+        {   // sub-ranges of the kept-value copies: at most 64 over all ranges
+            int sub = 8192;
+            if (const char *e = getenv("HOPE_B200_PACK_SUB")) { int v = atoi(e); if (v >= 128) sub = v / 128 * 128; }
+            for (;;) {
+                int total = 0;
+                for (int c = 0; c < C; ++c) total += (ctx->ch_lo[c + 1] - ctx->ch_lo[c] + sub - 1) / sub;
+                if (total <= 64) break;
+                sub *= 2;
+            }
+            ctx->pk_sub = sub;
+            int g = 0;
+            for (int c = 0; c < C; ++c) {
+                const int lo = ctx->ch_lo[c], cnt = ctx->ch_lo[c + 1] - lo;
+                ctx->pk_first[c] = g;
+                for (int a = 0; a < cnt; a += sub, ++g) { ctx->pk_lo[g] = lo + a; ctx->pk_hi[g] = lo + (a + sub < cnt ? a + sub : cnt); }
+                ctx->pk_first[c + 1] = g;
+            }
+            ctx->pk_total = g;
+        }
+        unsigned long long *h_flags = const_cast<unsigned long long *>(ctx->h_seq);
+        for (int c = 0; c < C; ++c) {
+            const int lo = ctx->ch_lo[c], cnt = ctx->ch_lo[c + 1] - lo;
             if (split_advance) {
                 rc = launch_range(ctx, d_act, ctx->step_out, adv, 0, s0, 0, c, lo, cnt);
                 if (rc) return rc;
-                cudaEvent_t ea = ctx->ev_adv[c % hope_ctx::MAX_CHUNK_EVENTS];
+                tmark(ctx, "advance_end", c, s0);
+                cudaEvent_t ea = ctx->ev_adv[c];
                 CK(cudaEventRecord(ea, s0));
                 CK(cudaStreamWaitEvent(s_obs, ea, 0));
+                // pose, target, reward, status ... are final once k_advance has run: they travel now, not behind the Reeds-Shepp kernels
+                CK(cudaStreamWaitEvent(s_copy, ea, 0));
+                rc = copy_fields(ctx, h_out, BY_ADVANCE, s_copy, lo, cnt);
+                if (rc) return rc;
+                advance_copied = true;
             }
             rc = launch_range(ctx, d_act, ctx->step_out, side, 0, s_obs, 0, c, lo, cnt, nullptr, false);
             if (rc) return rc;
             last_chunk = c;
-            cudaEvent_t ev = ctx->ev_chunk[c % hope_ctx::MAX_CHUNK_EVENTS];
+            tmark(ctx, "observe_end", c, s_obs);
+            if (ctx->packing && (stages & HOPE_STAGE_OBSERVE) && !(ctx->host_debug == 2)) {  // keep the beams that differ from the no-hit constant
+                unsigned *count = ctx->d_lcount + ctx->pk_first[c];
+                CK(cudaMemsetAsync(count, 0, sizeof(unsigned) * (ctx->pk_first[c + 1] - ctx->pk_first[c]), s_obs));
+                k_pack_lidar<<<(cnt * 32 + 127) / 128, 128, 0, s_obs>>>(cnt, ctx->step_out.lidar + (size_t)lo * NRAY, make_tables(ctx).lidar_base, ctx->par.lidar_range,
+                                                                       ctx->d_lbits + 4 * (size_t)lo, ctx->d_loff + lo, ctx->d_lpacked + (size_t)lo * NRAY, count, ctx->pk_sub);
+                ctx->launches++;
+            }
+            tmark(ctx, "pack_end", c, s_obs);
+            cudaEvent_t ev = ctx->ev_chunk[c];
             CK(cudaEventRecord(ev, s_obs));
             CK(cudaStreamWaitEvent(s_copy, ev, 0));
-            if (ctx->expanding) {  // the step counts first, so the host can start expanding this range right away
+            // Flag A behind the sub-range counts: the host can issue the kept-value copies.  Flag B behind the other narrow
+            // arrays (step counts, beam flags, offsets): the host can expand this range.
+            if (ctx->packing) {
+                const int nsub = ctx->pk_first[c + 1] - ctx->pk_first[c];
+                CK(cudaMemcpyAsync(ctx->h_lcount + ctx->pk_first[c], ctx->d_lcount + ctx->pk_first[c], sizeof(unsigned) * nsub, cudaMemcpyDeviceToHost, s_copy));
+                CK(cudaMemcpyAsync(h_flags + c, ctx->d_seq, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s_copy));
+                CK(cudaMemcpyAsync(ctx->h_lbits + 4 * (size_t)lo, ctx->d_lbits + 4 * (size_t)lo, sizeof(uint32_t) * 4 * cnt, cudaMemcpyDeviceToHost, s_copy));
+                CK(cudaMemcpyAsync(ctx->h_loff + lo, ctx->d_loff + lo, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost, s_copy));
+                ctx->io_d2h_static += (size_t)cnt * 20 + 4 * nsub + 8;
+            }
+            if (ctx->expanding) {
                 CK(cudaMemcpyAsync(ctx->h_mask_steps + (size_t)lo * NACT, ctx->stage_out.mask_steps + (size_t)lo * NACT, (size_t)cnt * NACT,
                                    cudaMemcpyDeviceToHost, s_copy));
-                CK(cudaMemcpyAsync(const_cast<unsigned long long *>(ctx->h_seq) + c % hope_ctx::MAX_CHUNK_EVENTS, ctx->d_seq, sizeof(unsigned long long),
-                                   cudaMemcpyDeviceToHost, s_copy));
+                ctx->io_d2h_static += (size_t)cnt * NACT;
             }
-            rc = copy_fields(ctx, h_out, 1, s_copy, lo, cnt);
+            if (flagging) {
+                CK(cudaMemcpyAsync(h_flags + hope_ctx::MAX_CHUNK_EVENTS + c, ctx->d_seq, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s_copy));
+                ctx->io_d2h_static += 8;
+            }
+            tmark(ctx, "flags_copied", c, s_copy);
+            rc = copy_fields(ctx, h_out, BY_OBSERVE, s_copy, lo, cnt);
             if (rc) return rc;
+            tmark(ctx, "observe_copies_end", c, s_copy);
         }
     }
     if (stages & HOPE_STAGE_RS) {
         // the persistent Reeds-Shepp grids would occupy every SM and starve the (later launched) k_observe ranges
         // whatever the stream priorities, so they start behind the last range and run under the copies instead
-        if (side && ctx->host_rs_after_observe) CK(cudaStreamWaitEvent(s0, ctx->ev_chunk[(last_chunk) % hope_ctx::MAX_CHUNK_EVENTS], 0));
+        if (side && ctx->host_rs_after_observe) CK(cudaStreamWaitEvent(s0, ctx->ev_chunk[last_chunk], 0));
+        tmark(ctx, "rs_begin", -1, s0);
         rc = launch_range(ctx, d_act, ctx->step_out, HOPE_STAGE_RS, 0, s0, 0, 0, 0, n, nullptr, false);
         if (rc) return rc;
+        tmark(ctx, "rs_end", -1, s0);
     }
-    rc = copy_fields(ctx, h_out, side ? 0 : -1, s0, 0, n);
+    rc = copy_fields(ctx, h_out, side ? (advance_copied ? BY_RS : BY_ADVANCE | BY_RS) : BY_ANY, s0, 0, n);
     if (rc) return rc;
+    tmark(ctx, "last_copies_end", -1, s0);
     if (side) {  // s_obs joins through the last range's event, s_copy joins here
         CK(cudaEventRecord(ctx->ev_join[1], s_copy));
         CK(cudaStreamWaitEvent(s0, ctx->ev_join[1], 0));
@@ -1262,7 +1534,26 @@ static int enqueue_host_step(hope_ctx *ctx, const double *h_action, const hope_h
 
 int hope_expand_mask(const uint8_t *h_steps, double *h_mask, int n) {
     if (!h_steps || !h_mask || n < 0) return HOPE_ERR_INVALID;
-    expand_mask_range(h_steps, h_mask, 0, (size_t)n);
+    hope_wire::expand_mask(h_steps, h_mask, 0, (size_t)n, 0);
+    return HOPE_OK;
+}
+
+int hope_expand_lidar(const uint32_t *h_bits, const uint32_t *h_off, const double *h_packed, const double *h_nohit, double *h_lidar, int n, int portable) {
+    if (!h_bits || !h_off || !h_packed || !h_nohit || !h_lidar || n < 0) return HOPE_ERR_INVALID;
+    hope_wire::expand_lidar(h_bits, h_off, h_packed, h_nohit, h_lidar, 0, (size_t)n, portable);
+    return HOPE_OK;
+}
+
+int hope_expand_mask_portable(const uint8_t *h_steps, double *h_mask, int n) {
+    if (!h_steps || !h_mask || n < 0) return HOPE_ERR_INVALID;
+    hope_wire::expand_mask(h_steps, h_mask, 0, (size_t)n, 1);
+    return HOPE_OK;
+}
+
+int hope_host_wire_info(const hope_ctx *ctx, uint64_t info[8]) {
+    if (!ctx || !info) return HOPE_ERR_INVALID;
+    info[0] = ctx->io_h2d; info[1] = ctx->io_d2h; info[2] = ctx->expanding ? 1 : 0; info[3] = ctx->packing ? 1 : 0;
+    info[4] = (uint64_t)ctx->host_threads; info[5] = (uint64_t)hope_wire::vector_path(); info[6] = (uint64_t)ctx->hm_chunks; info[7] = 0;
     return HOPE_OK;
 }
 
@@ -1281,13 +1572,16 @@ int hope_step_host(hope_ctx *ctx, const double *h_action, const hope_host_out *h
     rc = join_device_calls(ctx, s0);  // a device-API call may still be running on the caller's stream
     if (rc) return rc;
     ctx->dev_pending = false;         // everything below is ordered behind s0 and this call returns synchronised
-    if (ctx->host_graph_enabled && !ctx->profile) {
+    ++ctx->host_steps;
+    ctx->tracing = ctx->host_trace > 0 && ctx->host_steps >= (unsigned long long)ctx->host_trace && (ctx->host_steps - ctx->host_trace) % 50 == 0;
+    if (ctx->tracing) ctx->trace_t0 = std::chrono::steady_clock::now();
+    if (ctx->host_graph_enabled && !ctx->profile && !ctx->tracing) {
         const bool same = ctx->host_graph && ctx->hg_action == h_action && ctx->hg_stages == stages &&
                           memcmp(&ctx->hg_out, h_out, sizeof(hope_out)) == 0;
         if (!same) {
             if (ctx->host_graph) { cudaGraphExecDestroy(ctx->host_graph); ctx->host_graph = nullptr; }
             plan_zero_copy(ctx, h_out);
-            rc = plan_mask_expand(ctx, h_out, stages);
+            rc = plan_wire(ctx, h_out, stages);
             if (rc) return rc;
             const unsigned long long before = ctx->launches;
             cudaGraph_t g = nullptr;
@@ -1312,11 +1606,14 @@ int hope_step_host(hope_ctx *ctx, const double *h_action, const hope_host_out *h
         }
     }
     plan_zero_copy(ctx, h_out);
-    rc = plan_mask_expand(ctx, h_out, stages);
+    rc = plan_wire(ctx, h_out, stages);
     if (rc) return rc;
     rc = enqueue_host_step(ctx, h_action, h_out, stages);
     if (rc) return rc;
-    return finish_host_step(ctx, h_out, s0);
+    hmark(ctx, "enqueued", -1);
+    rc = finish_host_step(ctx, h_out, s0);
+    trace_print(ctx);
+    return rc;
 }
 
 int hope_reset_host(hope_ctx *ctx, const int32_t *h_scene_ids, const hope_host_out *h_out) {
@@ -1332,7 +1629,7 @@ int hope_reset_host(hope_ctx *ctx, const int32_t *h_scene_ids, const hope_host_o
     if (rc) return rc;
     const unsigned keep_mask = ctx->zero_copy_mask;
     ctx->zero_copy_mask = 0;  // the reset step always goes through the staging buffers
-    rc = copy_fields(ctx, h_out, -1, ctx->own_stream, 0, ctx->n);
+    rc = copy_fields(ctx, h_out, BY_ANY, ctx->own_stream, 0, ctx->n);
     ctx->zero_copy_mask = keep_mask;
     if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->own_stream));

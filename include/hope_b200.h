@@ -185,6 +185,21 @@ int hope_reset_host(hope_ctx *ctx, const int32_t *h_scene_ids, const hope_host_o
  * step counts, exactly as action_mask.py:182-183 / k_observe compute it (steps / 10, or 0.01 for all 42 actions of an
  * env whose counts are all 0).  HOST pointers h_steps[n][42], h_mask[n][42]; pure host code, no CUDA call. */
 int hope_expand_mask(const uint8_t *h_steps, double *h_mask, int n);
+int hope_expand_mask_portable(const uint8_t *h_steps, double *h_mask, int n); /* the same without the AVX-512 routine (tests) */
+
+/* The other narrow array of hope_step_host: the float64 lidar (lidar_simulator.py:31-135; 960 of the 1 436 bytes a step returns
+ * per env).  A beam that hits nothing within range reads exactly lidar_range - lidar_base[ray] (:46, :134), so on the device
+ * k_pack_lidar keeps only the values whose bits differ from that constant and the host rebuilds the rows, bit for bit:
+ * h_bits[n][4] (bit j of word q = beam 32 q + j travelled), h_off[n] (index of env i's first kept value in h_packed),
+ * h_nohit[120] (the per-ray constant), h_lidar[n][120] (result).  h_packed must stay readable for 64 bytes behind its last
+ * kept value (the vector routine loads 8 values at a time).  `portable` != 0 skips the AVX-512 routine.  Pure host code. */
+int hope_expand_lidar(const uint32_t *h_bits, const uint32_t *h_off, const double *h_packed, const double *h_nohit, double *h_lidar,
+                      int n, int portable);
+
+/* What the last hope_step_host moved and how: info[0] = host-to-device bytes, [1] = device-to-host bytes (all copies of the
+ * step, including the data-dependent kept lidar values), [2] / [3] = 1 when the mask / lidar travelled narrow, [4] = host
+ * expansion threads, [5] = 1 when the AVX-512 expansion routines are in use, [6] = env ranges the step was pipelined over. */
+int hope_host_wire_info(const hope_ctx *ctx, uint64_t info[8]);
 
 /* Batched RsPlanner + ParkingAgent hand-off (model/agent/parking_agent.py:2-47, 64-70, 93-110;
  * train_HOPE_sac.py:194-213).  Call once per rollout step BEFORE hope_step, with the outputs of the

@@ -146,3 +146,47 @@ def test_host_mask_expansion_equals_the_reference_formula():
     want[steps.sum(axis=1) == 0] = 0.01
     assert np.array_equal(mask, want)
     assert lib.hope_expand_mask(None, mask.ctypes.data, 1) == -1
+    for n in (4096, 4095, 1, 0):        # the portable routine and ragged tails of the 8-wide one
+        for fn in (lib.hope_expand_mask, lib.hope_expand_mask_portable):
+            m2 = np.full((4096, 42), -1.0)
+            capi.check(fn(steps.ctypes.data, m2.ctypes.data, n))
+            assert np.array_equal(m2[:n], want[:n]) and (m2[n:] == -1.0).all()
+
+
+def test_host_lidar_expansion_rebuilds_the_rows_bit_for_bit():
+    """hope_step_host ships, per env, 120 flag bits + an offset + only the lidar values that differ from the per-ray no-hit
+    constant lidar_range - lidar_base[ray] (lidar_simulator.py:46, 134); hope_expand_lidar rebuilds the float64 rows.  Packed
+    here the way k_pack_lidar does (envs in arbitrary order in the value array), expanded by both routines."""
+    from hope_b200 import capi, tables
+    lib = capi.load_library()
+    rng = np.random.default_rng(5)
+    n = 3000
+    nohit = 10.0 - tables.host_tables()["lidar_base"]
+    lidar = np.tile(nohit, (n, 1))
+    hit = rng.random((n, 120)) < 0.57
+    hit[::11] = False                    # nothing in range at all
+    hit[1::11] = True                    # every beam hits
+    hit[2::11, :] = False; hit[2::11, 119] = True; hit[2::11, 0] = True
+    vals = rng.uniform(-1.0, 9.0, size=(n, 120))
+    vals[5, 7] = -0.0; vals[6, 8] = np.nextafter(nohit[8], 0.0)    # a signed zero and a value one ulp off the constant are kept as they are
+    lidar[hit] = vals[hit]
+    keep = lidar.view(np.int64) != np.tile(nohit, (n, 1)).view(np.int64)
+    bits = np.zeros((n, 4), dtype=np.uint32)
+    for j in range(120):
+        bits[:, j // 32] |= keep[:, j].astype(np.uint32) << np.uint32(j % 32)
+    order = rng.permutation(n)           # atomics hand out the space in any order
+    off = np.zeros(n, dtype=np.uint32)
+    packed = np.zeros(int(keep.sum()) + 8)
+    pos = 0
+    for i in order:
+        k = keep[i]
+        off[i] = pos
+        packed[pos:pos + k.sum()] = lidar[i, k]
+        pos += int(k.sum())
+    for portable in (0, 1):
+        for m in (n, n - 1, 1, 0):
+            out = np.full((n, 120), np.nan)
+            capi.check(lib.hope_expand_lidar(bits.ctypes.data, off.ctypes.data, packed.ctypes.data, nohit.ctypes.data, out.ctypes.data, m, portable))
+            assert np.array_equal(out[:m].view(np.int64), lidar[:m].view(np.int64)), portable
+            assert np.isnan(out[m:]).all()
+    assert lib.hope_expand_lidar(None, off.ctypes.data, packed.ctypes.data, nohit.ctypes.data, out.ctypes.data, 1, 0) == -1

@@ -231,11 +231,18 @@ def test_full_step_mixed_levels_vs_oracle():
     env.close()
 
 
+@pytest.mark.parametrize("wire", ["narrow", "narrow_portable", "plain"])
 @pytest.mark.parametrize("n", [512, 20000])
-def test_host_buffer_api_matches_device_api(n):
-    """hope_step_host steps k_observe env range by env range (2 ranges at n = 20 000), copies each range behind it and
-    rebuilds the float64 mask from its step counts on the host; the result must be the same arrays the one-launch
-    device path produces."""
+def test_host_buffer_api_matches_device_api(n, wire, monkeypatch):
+    """hope_step_host steps k_observe env range by env range (2 ranges at n = 20 000), copies each range behind it, ships the
+    mask as step counts and the lidar as flag bits + the beams that differ from the no-hit constant (k_pack_lidar) and
+    rebuilds both float64 arrays on the host; the result must be, bit for bit, the arrays the one-launch device path
+    produces.  `plain` copies the float64 arrays instead; `narrow_portable` expands without the AVX-512 routines."""
+    if wire == "plain":
+        monkeypatch.setenv("HOPE_B200_HOST_MASK_EXPAND", "0"); monkeypatch.setenv("HOPE_B200_HOST_LIDAR_PACK", "0")
+    if wire == "narrow_portable":
+        monkeypatch.setenv("HOPE_B200_WIRE_PORTABLE", "1")
+    monkeypatch.setenv("HOPE_B200_HOST_THREADS", "3")
     sc = generate_scenes(n, "Complex", 3)
     a = BatchedParkingEnv(n, scenes=sc, auto_reset=True)
     b = BatchedParkingEnv(n, scenes=sc, auto_reset=True)
@@ -247,7 +254,15 @@ def test_host_buffer_api_matches_device_api(n):
         h = b.step_host(act)
         d = gather(a)
         for k in ("lidar", "mask", "target", "reward", "status", "done", "reward_info", "rs_found", "rs_nseg", "rs_types", "rs_lengths"):
-            assert np.array_equal(d[k], h[k]), k
+            x, y = np.ascontiguousarray(d[k]), np.ascontiguousarray(h[k])
+            assert x.dtype == y.dtype and np.array_equal(x.view(np.uint8), y.view(np.uint8)), k
+    w = b.host_wire_info()
+    plain_bytes = n * (120 * 8 + 42 * 8 + 5 * 8 + 8 + 4 + 1 + 5 * 8 + 1 + 1 + 5 + 5 * 8)
+    assert w["lidar_packed"] == (wire != "plain") and w["mask_narrow"] == (wire != "plain") and w["h2d_bytes"] == 16 * n
+    if wire == "plain":
+        assert w["d2h_bytes"] == plain_bytes
+    else:
+        assert 0.25 * plain_bytes < w["d2h_bytes"] < 0.8 * plain_bytes and w["host_threads"] == 3
     sa, sb = a.get_state(), b.get_state()
     for k in sa:
         assert np.array_equal(sa[k], sb[k]), k
