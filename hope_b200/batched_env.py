@@ -229,7 +229,7 @@ class BatchedParkingEnv(object):
         info = (C.c_uint64 * 8)()
         capi.check(self.lib.hope_host_wire_info(self.ctx, C.byref(info)), self.ctx)
         return {"h2d_bytes": int(info[0]), "d2h_bytes": int(info[1]), "mask_narrow": bool(info[2]), "lidar_packed": bool(info[3]),
-                "host_threads": int(info[4]), "avx512": bool(info[5]), "env_ranges": int(info[6])}
+                "host_threads": int(info[4]), "avx512": bool(info[5]), "env_ranges": int(info[6]), "lidar_packed_envs": int(info[7])}
 
     # ---- state / diagnostics -------------------------------------------------------------------
     def get_state(self):

@@ -23,6 +23,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <functional>
@@ -427,33 +428,48 @@ using namespace hope;
 // action-mask steps into the float64 mask while the remaining copies are still travelling).
 struct HostPool {
     // Jobs are queued by the stepping thread and run in order; every worker runs its own share (part, nparts) of each job
-    // and moves on without waiting for the others (the jobs of one step write disjoint memory).
+    // and moves on without waiting for the others (the jobs of one step write disjoint memory).  A worker that runs out of
+    // jobs polls for spin_us microseconds before it sleeps on the condition variable: the jobs of a step arrive 0.1 - 0.3 ms
+    // apart, and a futex wake-up costs about as much as a job.
     std::vector<std::thread> workers;
     std::mutex m;
     std::condition_variable cv, done_cv;
     std::vector<std::function<void(int, int)>> jobs;  // of the current step; cleared by wait_all
     std::vector<size_t> progress;                      // per worker: jobs finished
-    bool stop = false;
+    std::atomic<size_t> submitted{0};                  // jobs queued since the pool started (never reset), readable without the lock
+    std::atomic<bool> stop{false};
+    int spin_us = 200;
     void start(int n) {
         progress.assign(n, 0);
         for (int w = 0; w < n; ++w)
             workers.emplace_back([this, w, n] {
+                size_t mine = 0;  // jobs this worker has finished since the pool started
                 for (;;) {
+                    if (spin_us > 0) {
+                        const auto t0 = std::chrono::steady_clock::now();
+                        for (unsigned k = 0; submitted.load(std::memory_order_acquire) <= mine && !stop.load(std::memory_order_relaxed); ++k) {
+#if defined(__x86_64__)
+                            __builtin_ia32_pause();
+#endif
+                            if ((k & 63) == 63 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(spin_us)) break;
+                        }
+                    }
                     std::function<void(int, int)> f;
                     {
                         std::unique_lock<std::mutex> lk(m);
-                        cv.wait(lk, [&] { return stop || progress[w] < jobs.size(); });
-                        if (stop) return;
+                        cv.wait(lk, [&] { return stop.load() || progress[w] < jobs.size(); });
+                        if (stop.load()) return;
                         f = jobs[progress[w]];
                     }
                     f(w, n);
+                    ++mine;
                     std::lock_guard<std::mutex> lk(m);
                     if (++progress[w] == jobs.size()) done_cv.notify_one();
                 }
             });
     }
     void submit(std::function<void(int, int)> f) {
-        { std::lock_guard<std::mutex> lk(m); jobs.push_back(std::move(f)); }
+        { std::lock_guard<std::mutex> lk(m); jobs.push_back(std::move(f)); submitted.fetch_add(1, std::memory_order_release); }
         cv.notify_all();
     }
     void wait_all() {
@@ -463,7 +479,7 @@ struct HostPool {
         for (size_t &p : progress) p = 0;
     }
     ~HostPool() {
-        { std::lock_guard<std::mutex> lk(m); stop = true; }
+        { std::lock_guard<std::mutex> lk(m); stop.store(true); }
         cv.notify_all();
         for (auto &t : workers) t.join();
     }
@@ -536,6 +552,13 @@ struct hope_ctx {
     // expansion job), so the host work left when the last copy lands is one sub-range, not one range
     int pk_sub = 8192, pk_total = 0;
     int pk_lo[64] = {}, pk_hi[64] = {}, pk_first[65] = {};   // sub-range g covers envs [pk_lo, pk_hi); range c owns sub-ranges [pk_first[c], pk_first[c+1])
+    // Packing trades PCIe bytes (37 instead of 63 MB of lidar per 65 536-env step) for host work (the rows are rebuilt by CPU
+    // stores).  With one rank per box and a dozen host threads the trade wins; with 8 ranks sharing 32 CPUs the expansion
+    // becomes the bottleneck (B200 x8: 9.8 ms per step all packed, 8.0 ms none packed).  So only pack_frac of the sub-ranges
+    // travel packed, spread evenly; the others' float64 rows are copied straight into the caller's buffer.  Both kinds of copy
+    // are issued by the stepping thread, outside the replayed graph, so the split can change from step to step.
+    double pack_frac = 1.0;
+    bool pk_packed[64] = {};
     double h_nohit[HOPE_N_LIDAR] = {};   // lidar_range - lidar_base[ray], the same float64 subtraction k_observe performs
     int wire_force_portable = 0;
     bool host_noexpand = false;  // HOPE_B200_HOST_NOEXPAND=1: timing experiments only (the host arrays are not rebuilt)
@@ -1286,6 +1309,9 @@ static int plan_wire(hope_ctx *ctx, const hope_host_out *h_out, unsigned stages)
         nt = nt < 1 ? 1 : (nt > 12 ? 12 : nt);
         if (const char *e = getenv("HOPE_B200_HOST_THREADS")) { int v = atoi(e); if (v >= 1 && v <= 64) nt = v; }
         ctx->host_threads = nt;
+        ctx->pack_frac = ranks == 1 ? 1.0 : (ranks == 2 ? 0.75 : 0.25);  // B200 x8 (32 CPUs): 0.25 -> 7.7 ms per step, 0.5 -> 8.1, 1.0 -> 9.8, none -> 8.2 (profiles/r02_e2e_ranks8.jsonl)
+        if (const char *e = getenv("HOPE_B200_HOST_PACK_FRAC")) { const double v = atof(e); if (v >= 0.0 && v <= 1.0) ctx->pack_frac = v; }
+        if (const char *e = getenv("HOPE_B200_HOST_SPIN_US")) ctx->host_pool->spin_us = atoi(e);
         ctx->host_pool->start(nt);
     }
     if (ctx->expanding) ctx->step_out.mask = nullptr;  // k_observe does not write the float64 mask at all
@@ -1311,9 +1337,15 @@ static int finish_host_step(hope_ctx *ctx, const hope_host_out *h_out, cudaStrea
                     const size_t glo = ctx->pk_lo[g], kept = ctx->h_lcount[g];
                     if (kept > (size_t)(ctx->pk_hi[g] - ctx->pk_lo[g]) * NRAY) { ctx->last_error = "hope_step_host: lidar pack count out of range"; return HOPE_ERR_CUDA; }
                     if (g == ctx->pk_first[c]) tmark(ctx, "kept_copy_begin", c, ctx->s_pack);
-                    if (kept) CK(cudaMemcpyAsync(ctx->h_lpacked + glo * NRAY, ctx->d_lpacked + glo * NRAY, kept * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_pack));
+                    if (!ctx->pk_packed[g]) {  // this sub-range's float64 rows go straight into the caller's buffer
+                        const size_t bytes = (size_t)(ctx->pk_hi[g] - ctx->pk_lo[g]) * NRAY * sizeof(double);
+                        CK(cudaMemcpyAsync(h_out->lidar + glo * NRAY, ctx->stage_out.lidar + glo * NRAY, bytes, cudaMemcpyDeviceToHost, ctx->s_pack));
+                        ctx->io_d2h += bytes;
+                    } else if (kept) {
+                        CK(cudaMemcpyAsync(ctx->h_lpacked + glo * NRAY, ctx->d_lpacked + glo * NRAY, kept * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_pack));
+                        ctx->io_d2h += kept * sizeof(double);
+                    }
                     CK(cudaEventRecord(ctx->ev_pack[g], ctx->s_pack));
-                    ctx->io_d2h += kept * sizeof(double);
                 }
                 tmark(ctx, "kept_copy_end", c, ctx->s_pack);
                 hmark(ctx, "kept_copy_issued", c);
@@ -1339,7 +1371,7 @@ static int finish_host_step(hope_ctx *ctx, const hope_host_out *h_out, cudaStrea
                 if (q == cudaSuccess) {
                     const int g = next_lidar++;
                     hmark(ctx, "kept_copy_seen_done", g);
-                    if (ctx->host_noexpand) continue;
+                    if (ctx->host_noexpand || !ctx->pk_packed[g]) continue;
                     const size_t lo = ctx->pk_lo[g], hi = ctx->pk_hi[g];
                     const uint32_t *bits = ctx->h_lbits, *off = ctx->h_loff;
                     const double *packed = ctx->h_lpacked + lo * NRAY, *nohit = ctx->h_nohit;
@@ -1456,6 +1488,8 @@ static int enqueue_host_step(hope_ctx *ctx, const double *h_action, const hope_h
                 ctx->pk_first[c + 1] = g;
             }
             ctx->pk_total = g;
+            double acc = 0.0;  // spread the packed sub-ranges evenly (error diffusion)
+            for (int k = 0; k < g; ++k) { acc += ctx->pack_frac; ctx->pk_packed[k] = acc >= 0.999999; if (ctx->pk_packed[k]) acc -= 1.0; }
         }
         unsigned long long *h_flags = const_cast<unsigned long long *>(ctx->h_seq);
         for (int c = 0; c < C; ++c) {
@@ -1553,7 +1587,9 @@ int hope_expand_mask_portable(const uint8_t *h_steps, double *h_mask, int n) {
 int hope_host_wire_info(const hope_ctx *ctx, uint64_t info[8]) {
     if (!ctx || !info) return HOPE_ERR_INVALID;
     info[0] = ctx->io_h2d; info[1] = ctx->io_d2h; info[2] = ctx->expanding ? 1 : 0; info[3] = ctx->packing ? 1 : 0;
-    info[4] = (uint64_t)ctx->host_threads; info[5] = (uint64_t)hope_wire::vector_path(); info[6] = (uint64_t)ctx->hm_chunks; info[7] = 0;
+    info[4] = (uint64_t)ctx->host_threads; info[5] = (uint64_t)hope_wire::vector_path(); info[6] = (uint64_t)ctx->hm_chunks;
+    info[7] = 0;
+    for (int g = 0; g < ctx->pk_total; ++g) info[7] += ctx->packing && ctx->pk_packed[g] ? (uint64_t)(ctx->pk_hi[g] - ctx->pk_lo[g]) : 0;  // envs whose lidar travelled packed
     return HOPE_OK;
 }
 

@@ -198,7 +198,8 @@ int hope_expand_lidar(const uint32_t *h_bits, const uint32_t *h_off, const doubl
 
 /* What the last hope_step_host moved and how: info[0] = host-to-device bytes, [1] = device-to-host bytes (all copies of the
  * step, including the data-dependent kept lidar values), [2] / [3] = 1 when the mask / lidar travelled narrow, [4] = host
- * expansion threads, [5] = 1 when the AVX-512 expansion routines are in use, [6] = env ranges the step was pipelined over. */
+ * expansion threads, [5] = 1 when the AVX-512 expansion routines are in use, [6] = env ranges the step was pipelined over, [7] = envs whose lidar
+ * rows travelled packed (the others' float64 rows were copied as they are: HOPE_B200_HOST_PACK_FRAC, default by ranks per box). */
 int hope_host_wire_info(const hope_ctx *ctx, uint64_t info[8]);
 
 /* Batched RsPlanner + ParkingAgent hand-off (model/agent/parking_agent.py:2-47, 64-70, 93-110;

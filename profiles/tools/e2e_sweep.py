@@ -43,6 +43,38 @@ def child(envs, steps, warmup):
     env.close()
 
 
+def hostinfo():
+    """what kind of host this is: the e2e number moves with the host's store bandwidth (the expansion writes 85 MB per step)"""
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    from hope_b200 import capi, tables
+    lib = capi.load_library()
+    n = 65536
+    rng = np.random.default_rng(0)
+    nohit = 10.0 - tables.host_tables()["lidar_base"]
+    keep = rng.random((n, 120)) < 0.57
+    bits = np.zeros((n, 4), dtype=np.uint32)
+    for j in range(120):
+        bits[:, j // 32] |= keep[:, j].astype(np.uint32) << np.uint32(j % 32)
+    cnt = keep.sum(1)
+    off = np.concatenate([[0], np.cumsum(cnt)[:-1]]).astype(np.uint32)
+    packed = rng.random(int(cnt.sum()) + 8)
+    out = np.zeros((n, 120))
+    best = 1e9
+    for _ in range(5):
+        t = time.perf_counter()
+        lib.hope_expand_lidar(bits.ctypes.data, off.ctypes.data, packed.ctypes.data, nohit.ctypes.data, out.ctypes.data, n, 0)
+        best = min(best, time.perf_counter() - t)
+    a = np.zeros(32 << 20); b = np.zeros(32 << 20)
+    cp = 1e9
+    for _ in range(3):
+        t = time.perf_counter(); np.copyto(b, a); cp = min(cp, time.perf_counter() - t)
+    model = [l.split(":", 1)[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name")]
+    mhz = [float(l.split(":", 1)[1]) for l in open("/proc/cpuinfo") if l.startswith("cpu MHz")]
+    print(json.dumps({"hostinfo": {"cpus": len(model), "model": model[0] if model else None, "mhz_max": max(mhz) if mhz else None,
+                                   "expand_lidar_65536_one_thread_ms": 1e3 * best, "numpy_copy_256MB_gbs": 2 * a.nbytes / cp / 1e9}}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("settings", nargs="*")
@@ -54,6 +86,7 @@ def main():
     args = ap.parse_args()
     if args.child:
         return child(args.envs, args.steps, args.warmup)
+    hostinfo()
     for setting in (args.settings or [""]):
         env = dict(os.environ)
         for kv in setting.split():

@@ -231,7 +231,7 @@ def test_full_step_mixed_levels_vs_oracle():
     env.close()
 
 
-@pytest.mark.parametrize("wire", ["narrow", "narrow_portable", "plain"])
+@pytest.mark.parametrize("wire", ["narrow", "narrow_portable", "mixed", "plain"])
 @pytest.mark.parametrize("n", [512, 20000])
 def test_host_buffer_api_matches_device_api(n, wire, monkeypatch):
     """hope_step_host steps k_observe env range by env range (2 ranges at n = 20 000), copies each range behind it, ships the
@@ -242,6 +242,9 @@ def test_host_buffer_api_matches_device_api(n, wire, monkeypatch):
         monkeypatch.setenv("HOPE_B200_HOST_MASK_EXPAND", "0"); monkeypatch.setenv("HOPE_B200_HOST_LIDAR_PACK", "0")
     if wire == "narrow_portable":
         monkeypatch.setenv("HOPE_B200_WIRE_PORTABLE", "1")
+    if wire == "mixed":   # every other sub-range of the lidar rows travels packed, the rest as float64 (what several ranks per box default to)
+        monkeypatch.setenv("HOPE_B200_HOST_PACK_FRAC", "0.5")
+        monkeypatch.setenv("HOPE_B200_PACK_SUB", "2048")
     monkeypatch.setenv("HOPE_B200_HOST_THREADS", "3")
     sc = generate_scenes(n, "Complex", 3)
     a = BatchedParkingEnv(n, scenes=sc, auto_reset=True)
@@ -261,6 +264,8 @@ def test_host_buffer_api_matches_device_api(n, wire, monkeypatch):
     assert w["lidar_packed"] == (wire != "plain") and w["mask_narrow"] == (wire != "plain") and w["h2d_bytes"] == 16 * n
     if wire == "plain":
         assert w["d2h_bytes"] == plain_bytes
+    elif wire == "mixed":
+        assert w["d2h_bytes"] < plain_bytes and (n < 4096 or 0.3 * n < w["lidar_packed_envs"] < 0.7 * n)
     else:
         assert 0.25 * plain_bytes < w["d2h_bytes"] < 0.8 * plain_bytes and w["host_threads"] == 3
     sa, sb = a.get_state(), b.get_state()
