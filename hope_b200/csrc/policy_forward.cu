@@ -1,0 +1,342 @@
+// policy_forward.cu — the actor network of the rollout loop (BASELINE cfg 4) as ONE sm_100a kernel.
+//
+// The reference's actor is MultiObsEmbedding(ACTOR_CONFIGS) (src/model/network.py:34-196, src/model/attention.py:16-92,
+// src/configs.py:134-153) with lidar / target / action-mask inputs: three 2-layer tanh embeddings -> 3 tokens x 128 ->
+// one pre-norm transformer block (8 heads x 32, feed-forward 128) -> Linear(384, 128) tanh Linear(128, 2) tanh.  That is
+// 1.23 MFLOP per env in 12 small GEMMs; run as ~25 PyTorch kernels the 65 536-env forward is bound by the activations it
+// writes and re-reads (the (N, 3, 768) qkv tensor alone is 300 MB) and by 524 288 batched 3 x 3 attention products.
+//
+// Here a CTA of 8 warps owns 32 envs (96 token rows) and carries them through the whole network with every activation in
+// shared memory: bf16 operands, float32 accumulation on the tensor cores (mma.sync m16n8k16; the GEMMs are M = 96 per CTA,
+// far too small for a tcgen05 / TMEM pipeline to pay), float32 residual stream, LayerNorm, softmax and tanh in float32.
+// Weights (bf16, PyTorch's [out][in] layout, K padded to 16) are read straight from L2 into B fragments: each warp loads only
+// the columns it owns, once per CTA.  Attention is folded into the head loop: per head, qkv for that head (N = 96) -> 3 x 3
+// softmax per env -> the head's slice of to_out accumulated in registers, so the 768-wide qkv row never exists.
+// HBM traffic per env: 668 B of float32 inputs in, 8 B out.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/hope_b200.h"
+
+namespace hope_policy {
+
+constexpr int BM = 32;                 // envs per CTA
+constexpr int ROWS = 3 * BM;           // token rows per CTA, row = modality * BM + env
+constexpr int E = 128;                 // embedding width
+constexpr int HEADS = 8, DH = 32;
+constexpr int THREADS = 256, WARPS = THREADS / 32;
+constexpr int KL = 128, KT = 16, KA = 48;             // padded input widths (120, 5, 42)
+constexpr int LDX = E + 8;             // bf16 row stride of a 128-wide operand (272 B: ldmatrix rows fall on different banks)
+constexpr int LDQ = 3 * DH + 8;        // qkv of one head
+constexpr int LDA = DH + 8;            // attention output of one head
+constexpr int LDR = E + 4;             // float32 residual stream
+
+struct Smem {
+    float x[ROWS][LDR];                        // residual stream
+    __nv_bfloat16 h[ROWS][LDX];                // embed hidden -> LayerNorm output -> bf16 copy of x for the output head
+    union {
+        struct { __nv_bfloat16 lidar[BM][KL + 8], target[BM][KT + 8], mask[BM][KA + 8]; } in;
+        struct { __nv_bfloat16 qkv[ROWS][LDQ], att[ROWS][LDA]; } hd;
+        __nv_bfloat16 ff[ROWS][LDX];           // feed-forward hidden
+        float head[BM][E + 4];                 // hidden of the output head
+    } u;
+};
+
+__device__ __forceinline__ float tanh_fast(float v) {
+    float r;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// A fragment of the 16 x 16 tile at (row0, k0) of a row-major bf16 matrix in shared memory
+__device__ __forceinline__ void lda16x16(uint32_t (&a)[4], const __nv_bfloat16 *base, int ld, int row0, int k0, int lane) {
+    const __nv_bfloat16 *p = base + (size_t)(row0 + (lane & 15)) * ld + k0 + ((lane >> 4) << 3);
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(addr));
+}
+
+// B fragment (k16 x n8) of W^T from the row-major weight W[n][k] in global memory: two adjacent bf16 per register
+__device__ __forceinline__ void ldb16x8(uint32_t &b0, uint32_t &b1, const __nv_bfloat16 *w_row /* W + n * ldw for this lane's n */, int k0, int lane) {
+    const uint32_t *p = reinterpret_cast<const uint32_t *>(w_row + k0 + ((lane & 3) << 1));
+    b0 = __ldg(p);
+    b1 = __ldg(p + 4);
+}
+
+// acc[mi][ni] += A[row0 + 16 mi .. +15][0 .. K) * W[wrow(ni) .. +7][0 .. K)^T for MT row tiles and NT column tiles.
+// a_row_of_k: row offset added per K block of E (the output head reads env e's three tokens as one 384-wide row).
+template <int MT, int NT, int K, typename RowFn>
+__device__ __forceinline__ void warp_gemm(float (&acc)[MT][NT][4], const __nv_bfloat16 *a, int lda, int row0, const __nv_bfloat16 *w, int ldw, RowFn wrow,
+                                          int lane, int a_rows_per_kblock = 0) {
+    const __nv_bfloat16 *wr[NT];
+#pragma unroll
+    for (int ni = 0; ni < NT; ++ni) wr[ni] = w + (size_t)(wrow(ni) + (lane >> 2)) * ldw;
+#pragma unroll
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        uint32_t b[NT][2];
+#pragma unroll
+        for (int ni = 0; ni < NT; ++ni) ldb16x8(b[ni][0], b[ni][1], wr[ni], k0, lane);
+        const int arow = row0 + (k0 / E) * a_rows_per_kblock, ak = a_rows_per_kblock ? k0 % E : k0;
+#pragma unroll
+        for (int mi = 0; mi < MT; ++mi) {
+            uint32_t af[4];
+            lda16x16(af, a, lda, arow + 16 * mi, ak, lane);
+#pragma unroll
+            for (int ni = 0; ni < NT; ++ni) mma16816(acc[mi][ni], af, b[ni][0], b[ni][1]);
+        }
+    }
+}
+
+template <int MT, int NT>
+__device__ __forceinline__ void zero(float (&acc)[MT][NT][4]) {
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < NT; ++ni)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[mi][ni][q] = 0.f;
+}
+
+// LayerNorm (eps 1e-5, affine) of the 96 residual rows -> bf16 operand; one warp per row, 4 columns per lane
+__device__ __forceinline__ void layer_norm_rows(Smem &sm, const float *__restrict__ g, const float *__restrict__ b, int warp, int lane) {
+    const float4 gg = __ldg(reinterpret_cast<const float4 *>(g) + lane), bb = __ldg(reinterpret_cast<const float4 *>(b) + lane);
+    for (int r = warp; r < ROWS; r += WARPS) {
+        const float4 v = *reinterpret_cast<const float4 *>(&sm.x[r][4 * lane]);
+        float s = v.x + v.y + v.z + v.w;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s * (1.f / E);
+        const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
+        float q = dx * dx + dy * dy + dz * dz + dw * dw;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float rstd = rsqrtf(q * (1.f / E) + 1e-5f);
+        __nv_bfloat162 lo = __floats2bfloat162_rn(dx * rstd * gg.x + bb.x, dy * rstd * gg.y + bb.y);
+        __nv_bfloat162 hi = __floats2bfloat162_rn(dz * rstd * gg.z + bb.z, dw * rstd * gg.w + bb.w);
+        *reinterpret_cast<__nv_bfloat162 *>(&sm.h[r][4 * lane]) = lo;
+        *reinterpret_cast<__nv_bfloat162 *>(&sm.h[r][4 * lane + 2]) = hi;
+    }
+}
+
+__global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const float *__restrict__ lidar, const float *__restrict__ target, const float *__restrict__ mask,
+                                                               hope_policy_weights W, float *__restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int env0 = blockIdx.x * BM;
+    using bf16p = const __nv_bfloat16 *;
+    bf16p w1_lidar = static_cast<bf16p>(W.w1_lidar), w1_target = static_cast<bf16p>(W.w1_target), w1_mask = static_cast<bf16p>(W.w1_mask);
+    bf16p w_qkv = static_cast<bf16p>(W.w_qkv), w_out = static_cast<bf16p>(W.w_out), w_ff1 = static_cast<bf16p>(W.w_ff1), w_ff2 = static_cast<bf16p>(W.w_ff2),
+          w_o1 = static_cast<bf16p>(W.w_o1);
+    const int crow = lane >> 2, ccol = (lane & 3) << 1;  // this lane's place in a 16 x 8 accumulator tile: rows crow, crow + 8; columns ccol, ccol + 1
+
+    // ---- inputs -> bf16, zero padded --------------------------------------------------------------------------
+    for (int i = tid; i < BM * KL; i += THREADS) {
+        const int e = i / KL, c = i % KL;
+        const float v = (c < 120 && env0 + e < n) ? lidar[(size_t)(env0 + e) * 120 + c] : 0.f;
+        sm.u.in.lidar[e][c] = __float2bfloat16(v);
+    }
+    for (int i = tid; i < BM * KT; i += THREADS) {
+        const int e = i / KT, c = i % KT;
+        sm.u.in.target[e][c] = __float2bfloat16((c < 5 && env0 + e < n) ? target[(size_t)(env0 + e) * 5 + c] : 0.f);
+    }
+    for (int i = tid; i < BM * KA; i += THREADS) {
+        const int e = i / KA, c = i % KA;
+        sm.u.in.mask[e][c] = __float2bfloat16((c < 42 && env0 + e < n) ? mask[(size_t)(env0 + e) * 42 + c] : 0.f);
+    }
+    __syncthreads();
+
+    // ---- embeddings, layer 1: h[m * BM + e] = tanh(in_m W1_m^T + b1_m).  Warp w owns columns 16 w .. 16 w + 15 of every modality ----
+    const int ncol0 = 16 * warp;
+    auto cols = [&](int ni) { return ncol0 + 8 * ni; };
+    {
+        float acc[2][2][4];
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+            zero(acc);
+            if (m == 0) warp_gemm<2, 2, KL>(acc, &sm.u.in.lidar[0][0], KL + 8, 0, w1_lidar, KL, cols, lane);
+            if (m == 1) warp_gemm<2, 2, KT>(acc, &sm.u.in.target[0][0], KT + 8, 0, w1_target, KT, cols, lane);
+            if (m == 2) warp_gemm<2, 2, KA>(acc, &sm.u.in.mask[0][0], KA + 8, 0, w1_mask, KA, cols, lane);
+            const float *bias = W.b1[m];
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni) {
+                    const int c = ncol0 + 8 * ni + ccol, r = m * BM + 16 * mi + crow;
+                    const float b0 = __ldg(bias + c), b1 = __ldg(bias + c + 1);
+                    *reinterpret_cast<__nv_bfloat162 *>(&sm.h[r][c]) = __floats2bfloat162_rn(tanh_fast(acc[mi][ni][0] + b0), tanh_fast(acc[mi][ni][1] + b1));
+                    *reinterpret_cast<__nv_bfloat162 *>(&sm.h[r + 8][c]) = __floats2bfloat162_rn(tanh_fast(acc[mi][ni][2] + b0), tanh_fast(acc[mi][ni][3] + b1));
+                }
+        }
+    }
+    __syncthreads();
+    // ---- embeddings, layer 2: x = h W2_m^T + b2_m (float32 residual stream) --------------------------------------
+    {
+        float acc[2][2][4];
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+            zero(acc);
+            warp_gemm<2, 2, E>(acc, &sm.h[0][0], LDX, m * BM, static_cast<bf16p>(W.w2[m]), E, cols, lane);
+            const float *bias = W.b2[m];
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 2; ++ni) {
+                    const int c = ncol0 + 8 * ni + ccol, r = m * BM + 16 * mi + crow;
+                    const float b0 = __ldg(bias + c), b1 = __ldg(bias + c + 1);
+                    *reinterpret_cast<float2 *>(&sm.x[r][c]) = make_float2(acc[mi][ni][0] + b0, acc[mi][ni][1] + b1);
+                    *reinterpret_cast<float2 *>(&sm.x[r + 8][c]) = make_float2(acc[mi][ni][2] + b0, acc[mi][ni][3] + b1);
+                }
+        }
+    }
+    __syncthreads();
+
+    // ---- attention block: x += to_out(softmax(q k^T / sqrt(32)) v) over the 3 tokens of each env, pre-norm -----------
+    layer_norm_rows(sm, W.ln1_g, W.ln1_b, warp, lane);
+    __syncthreads();
+    {
+        float oacc[6][2][4];  // this warp's 16 columns of to_out for all 96 rows, accumulated over the heads
+        zero(oacc);
+        // qkv of one head: 96 rows x 96 columns = 6 x 12 tiles; warp w takes row tiles 3 (w / 4) .. + 2 and column tiles 3 (w % 4) .. + 2
+        const int qm0 = 3 * (warp >> 2), qn0 = 3 * (warp & 3);
+        for (int hd = 0; hd < HEADS; ++hd) {
+            float qacc[3][3][4];
+            zero(qacc);
+            auto qrow = [&](int ni) { const int t = qn0 + ni; return (t >> 2) * (HEADS * DH) + hd * DH + (t & 3) * 8; };  // q | k | v blocks of to_qkv, head hd
+            warp_gemm<3, 3, E>(qacc, &sm.h[0][0], LDX, 16 * qm0, w_qkv, E, qrow, lane);
+#pragma unroll
+            for (int mi = 0; mi < 3; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 3; ++ni) {
+                    const int c = 8 * (qn0 + ni) + ccol, r = 16 * (qm0 + mi) + crow;
+                    *reinterpret_cast<__nv_bfloat162 *>(&sm.u.hd.qkv[r][c]) = __floats2bfloat162_rn(qacc[mi][ni][0], qacc[mi][ni][1]);
+                    *reinterpret_cast<__nv_bfloat162 *>(&sm.u.hd.qkv[r + 8][c]) = __floats2bfloat162_rn(qacc[mi][ni][2], qacc[mi][ni][3]);
+                }
+            __syncthreads();
+            // softmax over the env's 3 tokens: thread = (query row, half of the 32 output dims)
+            if (tid < 2 * ROWS) {
+                const int r = tid >> 1, half = tid & 1, e = r % BM;
+                float s[3];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const __nv_bfloat16 *q = &sm.u.hd.qkv[r][0], *k = &sm.u.hd.qkv[j * BM + e][DH];
+                    float d = 0.f;
+#pragma unroll
+                    for (int c = 0; c < DH; c += 2) {
+                        const float2 qa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(q + c)), ka = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(k + c));
+                        d += qa.x * ka.x + qa.y * ka.y;
+                    }
+                    s[j] = d * 0.17677669529663687f;  // dim_head ** -0.5
+                }
+                const float mx = fmaxf(s[0], fmaxf(s[1], s[2]));
+                const float p0 = __expf(s[0] - mx), p1 = __expf(s[1] - mx), p2 = __expf(s[2] - mx), inv = 1.f / (p0 + p1 + p2);
+                const __nv_bfloat16 *v0 = &sm.u.hd.qkv[e][2 * DH + 16 * half], *v1 = &sm.u.hd.qkv[BM + e][2 * DH + 16 * half], *v2 = &sm.u.hd.qkv[2 * BM + e][2 * DH + 16 * half];
+#pragma unroll
+                for (int c = 0; c < 16; c += 2) {
+                    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(v0 + c)), b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(v1 + c)),
+                                 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(v2 + c));
+                    *reinterpret_cast<__nv_bfloat162 *>(&sm.u.hd.att[r][16 * half + c]) =
+                        __floats2bfloat162_rn((p0 * a.x + p1 * b.x + p2 * d.x) * inv, (p0 * a.y + p1 * b.y + p2 * d.y) * inv);
+                }
+            }
+            __syncthreads();
+            // the head's slice of to_out: oacc += att (96 x 32) * w_out[:, 32 hd .. 32 hd + 31]^T
+            warp_gemm<6, 2, DH>(oacc, &sm.u.hd.att[0][0], LDA, 0, w_out + hd * DH, HEADS * DH, cols, lane);
+        }
+#pragma unroll
+        for (int mi = 0; mi < 6; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni) {
+                const int c = ncol0 + 8 * ni + ccol, r = 16 * mi + crow;
+                const float b0 = __ldg(W.b_out + c), b1 = __ldg(W.b_out + c + 1);
+                float2 *p = reinterpret_cast<float2 *>(&sm.x[r][c]), *q = reinterpret_cast<float2 *>(&sm.x[r + 8][c]);
+                *p = make_float2(p->x + oacc[mi][ni][0] + b0, p->y + oacc[mi][ni][1] + b1);
+                *q = make_float2(q->x + oacc[mi][ni][2] + b0, q->y + oacc[mi][ni][3] + b1);
+            }
+    }
+    __syncthreads();
+
+    // ---- feed-forward block: x += W2 tanh(W1 LN(x) + b1) + b2 ---------------------------------------------------------
+    layer_norm_rows(sm, W.ln2_g, W.ln2_b, warp, lane);
+    __syncthreads();
+    {
+        float acc[6][2][4];
+        zero(acc);
+        warp_gemm<6, 2, E>(acc, &sm.h[0][0], LDX, 0, w_ff1, E, cols, lane);
+#pragma unroll
+        for (int mi = 0; mi < 6; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni) {
+                const int c = ncol0 + 8 * ni + ccol, r = 16 * mi + crow;
+                const float b0 = __ldg(W.b_ff1 + c), b1 = __ldg(W.b_ff1 + c + 1);
+                *reinterpret_cast<__nv_bfloat162 *>(&sm.u.ff[r][c]) = __floats2bfloat162_rn(tanh_fast(acc[mi][ni][0] + b0), tanh_fast(acc[mi][ni][1] + b1));
+                *reinterpret_cast<__nv_bfloat162 *>(&sm.u.ff[r + 8][c]) = __floats2bfloat162_rn(tanh_fast(acc[mi][ni][2] + b0), tanh_fast(acc[mi][ni][3] + b1));
+            }
+        __syncthreads();
+        zero(acc);
+        warp_gemm<6, 2, E>(acc, &sm.u.ff[0][0], LDX, 0, w_ff2, E, cols, lane);
+        // the residual stream's last use is the output head's bf16 operand: write x + ff straight into h
+#pragma unroll
+        for (int mi = 0; mi < 6; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni) {
+                const int c = ncol0 + 8 * ni + ccol, r = 16 * mi + crow;
+                const float b0 = __ldg(W.b_ff2 + c), b1 = __ldg(W.b_ff2 + c + 1);
+                const float2 p = *reinterpret_cast<const float2 *>(&sm.x[r][c]), q = *reinterpret_cast<const float2 *>(&sm.x[r + 8][c]);
+                *reinterpret_cast<__nv_bfloat162 *>(&sm.h[r][c]) = __floats2bfloat162_rn(p.x + acc[mi][ni][0] + b0, p.y + acc[mi][ni][1] + b1);
+                *reinterpret_cast<__nv_bfloat162 *>(&sm.h[r + 8][c]) = __floats2bfloat162_rn(q.x + acc[mi][ni][2] + b0, q.y + acc[mi][ni][3] + b1);
+            }
+    }
+    __syncthreads();  // h complete (all warps also passed their last read of u.ff before this point: u.head may be written now)
+
+    // ---- output head: tanh(W_o2 tanh(W_o1 [x_0 | x_1 | x_2] + b_o1) + b_o2) ---------------------------------------------
+    {
+        float acc[2][2][4];
+        zero(acc);
+        warp_gemm<2, 2, 3 * E>(acc, &sm.h[0][0], LDX, 0, w_o1, 3 * E, cols, lane, BM);  // K block m reads token rows m * BM + env
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 2; ++ni) {
+                const int c = ncol0 + 8 * ni + ccol, r = 16 * mi + crow;
+                const float b0 = __ldg(W.b_o1 + c), b1 = __ldg(W.b_o1 + c + 1);
+                *reinterpret_cast<float2 *>(&sm.u.head[r][c]) = make_float2(tanh_fast(acc[mi][ni][0] + b0), tanh_fast(acc[mi][ni][1] + b1));
+                *reinterpret_cast<float2 *>(&sm.u.head[r + 8][c]) = make_float2(tanh_fast(acc[mi][ni][2] + b0), tanh_fast(acc[mi][ni][3] + b1));
+            }
+    }
+    __syncthreads();
+    {   // Linear(128, 2): 4 lanes per (env, output), 32 products each
+        const int pair = tid >> 2, part = tid & 3, e = pair >> 1, o = pair & 1;  // 64 pairs x 4 lanes = 256 threads
+        const float *hrow = &sm.u.head[e][32 * part], *wrow = W.w_o2 + o * E + 32 * part;
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) s += hrow[c] * __ldg(wrow + c);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (part == 0 && env0 + e < n) out[(size_t)(env0 + e) * 2 + o] = tanhf(s + __ldg(W.b_o2 + o));
+    }
+}
+
+}  // namespace hope_policy
+
+extern "C" {
+
+int hope_policy_forward(int n, const float *d_lidar, const float *d_target, const float *d_mask, const hope_policy_weights *w, float *d_out, void *stream) {
+    if (n <= 0 || !d_lidar || !d_target || !d_mask || !w || !d_out) return HOPE_ERR_INVALID;
+    using namespace hope_policy;
+    const int smem = (int)sizeof(Smem);
+    if (cudaFuncSetAttribute(k_policy_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return HOPE_ERR_CUDA;
+    k_policy_forward<<<(n + BM - 1) / BM, THREADS, smem, static_cast<cudaStream_t>(stream)>>>(n, d_lidar, d_target, d_mask, *w, d_out);
+    return cudaGetLastError() == cudaSuccess ? HOPE_OK : HOPE_ERR_CUDA;
+}
+
+int hope_policy_forward_smem_bytes(void) { return (int)sizeof(hope_policy::Smem); }
+
+}  // extern "C"

@@ -2,7 +2,7 @@
 // (SURVEY.md §8 row f2), as sm_100a kernels instead of chains of elementwise PyTorch ops on (N, 120) float64 tensors:
 //
 //   hope_state_norm      StateNorm.state_norm (src/model/state_norm.py:25-46): running mean / std of `lidar` and `target`
-//                        updated with a whole batch of N observations (Welford per block, Chan merge), every observation
+//                        updated with a whole batch of N observations (two-pass moments per block, Chan merge), every observation
 //                        normalised as (x - mean) / (std + 1e-8) and cast to float32 for the network, the action mask cast
 //                        along — 3 launches, one read of the float64 observations per pass
 //   hope_masked_sample   ActionMask.choose_action (src/model/action_mask.py:199-227): probabilities of the 42 discrete
@@ -40,32 +40,49 @@ __device__ __forceinline__ double load_col(const double *lidar, const double *ta
     return c < NL ? lidar[row * NL + c] : target[row * NT + (c - NL)];
 }
 
-// pass 1: block b reduces rows [b R, (b+1) R) column by column (thread = column: consecutive threads read consecutive doubles)
+// pass 1: block b reduces rows [b R, (b+1) R) column by column (thread = column: consecutive threads read consecutive doubles).
+// Two sweeps over the block's rows (the second one hits L2): the column sum with four independent accumulators, then the
+// squared deviations from the block mean — no division per element and no loop-carried dependence between the loads.
 __global__ void __launch_bounds__(NORM_THREADS) k_norm_partial(const double *__restrict__ lidar, const double *__restrict__ target, int n, int rows_per_block,
                                                                Moments *__restrict__ partial) {
     const int c = threadIdx.x;
     if (c >= NC) return;
     const size_t lo = (size_t)blockIdx.x * rows_per_block, hi = min((size_t)n, lo + rows_per_block);
-    double cnt = 0.0, mean = 0.0, m2 = 0.0;
-    for (size_t r = lo; r < hi; ++r) {  // Welford
-        const double x = load_col(lidar, target, r, c);
-        cnt += 1.0;
-        const double d = x - mean;
-        mean += d / cnt;
-        m2 += d * (x - mean);
+    const double *base = c < NL ? lidar + c : target + (c - NL);
+    const size_t stride = c < NL ? NL : NT;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    size_t r = lo;
+    for (; r + 4 <= hi; r += 4) {
+        s0 += base[r * stride]; s1 += base[(r + 1) * stride]; s2 += base[(r + 2) * stride]; s3 += base[(r + 3) * stride];
     }
-    partial[(size_t)blockIdx.x * NC + c] = Moments{cnt, mean, m2};
+    for (; r < hi; ++r) s0 += base[r * stride];
+    const double cnt = (double)(hi - lo), mean = ((s0 + s1) + (s2 + s3)) / fmax(cnt, 1.0);
+    double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
+    for (r = lo; r + 4 <= hi; r += 4) {
+        const double d0 = base[r * stride] - mean, d1 = base[(r + 1) * stride] - mean, d2 = base[(r + 2) * stride] - mean, d3 = base[(r + 3) * stride] - mean;
+        q0 += d0 * d0; q1 += d1 * d1; q2 += d2 * d2; q3 += d3 * d3;
+    }
+    for (; r < hi; ++r) { const double d = base[r * stride] - mean; q0 += d * d; }
+    partial[(size_t)blockIdx.x * NC + c] = Moments{cnt, mean, (q0 + q1) + (q2 + q3)};
 }
 
-// pass 2: merge the block partials, then into the running statistics stats[0][c] = mean, stats[1][c] = m2 (count kept by the host)
-__global__ void __launch_bounds__(NORM_THREADS) k_norm_merge(const Moments *__restrict__ partial, int n_blocks, double *__restrict__ stats, double count_before,
-                                                             int update, double *__restrict__ scale /* [2][NC]: mean, std + 1e-8 */) {
-    const int c = threadIdx.x;
-    if (c >= NC) return;
+// pass 2: merge the block partials (MERGE_GROUPS interleaved chains per column, combined through shared memory), then into the
+// running statistics stats[0][c] = mean, stats[1][c] = m2 (count kept by the host)
+constexpr int MERGE_GROUPS = 8;
+__global__ void __launch_bounds__(NORM_THREADS * MERGE_GROUPS) k_norm_merge(const Moments *__restrict__ partial, int n_blocks, double *__restrict__ stats,
+                                                                            double count_before, int update, double *__restrict__ scale /* [2][NC]: mean, std + 1e-8 */) {
+    __shared__ Moments part[MERGE_GROUPS][NORM_THREADS];
+    const int c = threadIdx.x % NORM_THREADS, g = threadIdx.x / NORM_THREADS;
+    Moments acc{0.0, 0.0, 0.0};
+    if (update && c < NC)
+        for (int b = g; b < n_blocks; b += MERGE_GROUPS) acc = merge(acc, partial[(size_t)b * NC + c]);
+    part[g][c] = acc;
+    __syncthreads();
+    if (g != 0 || c >= NC) return;
     Moments run{count_before, stats[c], stats[NC + c]};
     if (update) {
-        Moments batch{0.0, 0.0, 0.0};
-        for (int b = 0; b < n_blocks; ++b) batch = merge(batch, partial[(size_t)b * NC + c]);
+        Moments batch = part[0][c];
+        for (int k = 1; k < MERGE_GROUPS; ++k) batch = merge(batch, part[k][c]);
         run = merge(run, batch);
         stats[c] = run.mean; stats[NC + c] = run.m2;
     }
@@ -73,24 +90,21 @@ __global__ void __launch_bounds__(NORM_THREADS) k_norm_merge(const Moments *__re
     scale[NC + c] = sqrt(run.m2 / fmax(run.n, 1.0)) + 1e-8;  // state_norm.py:43-44
 }
 
-// pass 3: (x - mean) / (std + 1e-8) -> float32; the action mask is only cast
-__global__ void __launch_bounds__(256) k_norm_apply(const double *__restrict__ lidar, const double *__restrict__ target, const double *__restrict__ mask, int n,
-                                                    const double *__restrict__ scale, float *__restrict__ out_lidar, float *__restrict__ out_target,
-                                                    float *__restrict__ out_mask) {
-    const size_t total = (size_t)n * (NC + NA);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        if (i < (size_t)n * NL) {
-            const int c = (int)(i % NL);
-            out_lidar[i] = (float)((lidar[i] - scale[c]) / scale[NC + c]);
-        } else if (i < (size_t)n * NC) {
-            const size_t j = i - (size_t)n * NL;
-            const int c = NL + (int)(j % NT);
-            out_target[j] = (float)((target[j] - scale[c]) / scale[NC + c]);
-        } else if (out_mask) {
-            const size_t j = i - (size_t)n * NC;
-            out_mask[j] = (float)mask[j];
-        }
+// pass 3: (x - mean) / (std + 1e-8) -> float32; the action mask is only cast.  Thread = column again (its mean and scale stay
+// in registers, no index arithmetic per element), rows strided over the grid.
+__global__ void __launch_bounds__(NORM_THREADS) k_norm_apply(const double *__restrict__ lidar, const double *__restrict__ target, const double *__restrict__ mask, int n,
+                                                             const double *__restrict__ scale, float *__restrict__ out_lidar, float *__restrict__ out_target,
+                                                             float *__restrict__ out_mask) {
+    const int c = threadIdx.x;
+    if (c < NC) {
+        const double mean = scale[c], denom = scale[NC + c];
+        const double *src = c < NL ? lidar + c : target + (c - NL);
+        float *dst = c < NL ? out_lidar + c : out_target + (c - NL);
+        const size_t stride = c < NL ? NL : NT;
+        for (size_t r = blockIdx.x; r < (size_t)n; r += gridDim.x) dst[r * stride] = (float)((src[r * stride] - mean) / denom);
     }
+    if (out_mask && c < NA)
+        for (size_t r = blockIdx.x; r < (size_t)n; r += gridDim.x) out_mask[r * NA + c] = (float)mask[r * NA + c];
 }
 
 // Philox4x32-10 (Salmon et al. 2011): counter (env, step), key (seed) -> 4 x 32 random bits
@@ -151,7 +165,7 @@ __global__ void __launch_bounds__(128) k_masked_sample(int n, const float *__res
 extern "C" {
 
 int hope_state_norm_scratch_bytes(int n) {
-    const int blocks = (n + 255) / 256 > 592 ? 592 : (n + 255) / 256;
+    const int blocks = (n + 63) / 64 > 592 ? 592 : (n + 63) / 64;
     return (int)(sizeof(hope_glue::Moments) * hope_glue::NC * (blocks > 0 ? blocks : 1) + sizeof(double) * 2 * hope_glue::NC);
 }
 
@@ -160,15 +174,15 @@ int hope_state_norm(const double *d_lidar, const double *d_target, const double 
     using namespace hope_glue;
     if (!d_lidar || !d_target || n <= 0 || !d_stats || !d_scratch || !d_out_lidar || !d_out_target || (d_out_mask && !d_mask)) return HOPE_ERR_INVALID;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    int blocks = (n + 255) / 256;
+    int blocks = (n + 63) / 64;
     if (blocks > 592) blocks = 592;
     const int rows = (n + blocks - 1) / blocks;
     blocks = (n + rows - 1) / rows;
     double *scale = static_cast<double *>(d_scratch);
     Moments *partial = reinterpret_cast<Moments *>(scale + 2 * NC);
     if (update) k_norm_partial<<<blocks, NORM_THREADS, 0, s>>>(d_lidar, d_target, n, rows, partial);
-    k_norm_merge<<<1, NORM_THREADS, 0, s>>>(partial, blocks, d_stats, count_before, update, scale);
-    k_norm_apply<<<592, 256, 0, s>>>(d_lidar, d_target, d_mask, n, scale, d_out_lidar, d_out_target, d_out_mask);
+    k_norm_merge<<<1, NORM_THREADS * MERGE_GROUPS, 0, s>>>(partial, blocks, d_stats, count_before, update, scale);
+    k_norm_apply<<<n < 148 * 16 ? n : 148 * 16, NORM_THREADS, 0, s>>>(d_lidar, d_target, d_mask, n, scale, d_out_lidar, d_out_target, d_out_mask);
     return cudaGetLastError() == cudaSuccess ? HOPE_OK : HOPE_ERR_CUDA;
 }
 

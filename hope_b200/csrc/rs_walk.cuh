@@ -25,7 +25,8 @@ static_assert(sizeof(WordSlot) % 16 == 0, "WordSlot is staged with 16-byte async
 // One step of generate_local_course's sample sequence (:452-507).  (code, pd) is the sample just
 // emitted; on return it is the next one.  code: RS_ORIGIN = path start, seg index = loop sample of
 // that segment at arc parameter pd, RS_END|seg = the final end point, RS_DONE = no more samples.
-__device__ __forceinline__ void walker_next(const double *len, int nseg, double step, uint8_t &code, double &pd) {
+template <class LenT>
+__device__ __forceinline__ void walker_next(const LenT &len, int nseg, double step, uint8_t &code, double &pd) {
     int seg;
     double d;
     if (code == RS_ORIGIN) {
@@ -52,27 +53,32 @@ __device__ __forceinline__ void walker_next(const double *len, int nseg, double 
     }
 }
 
-// interpolate (:510-537) from a segment origin; returns the local-frame pose of the sample.
-__device__ __forceinline__ void rs_interp(double p, int m, double maxc, const double *org, double &lx, double &ly, double &lyaw) {
+// interpolate (:510-537) from a segment origin (ox, oy, oyaw, cos oyaw, sin oyaw); returns the local-frame pose of the sample.
+__device__ __forceinline__ void rs_interp(double p, int m, double maxc, double ox, double oy, double oyaw, double oc, double os, double &lx, double &ly,
+                                          double &lyaw) {
     if (m == HOPE_RS_S) {
-        lx = org[0] + p / maxc * org[3];
-        ly = org[1] + p / maxc * org[4];
-        lyaw = org[2];
+        lx = ox + p / maxc * oc;
+        ly = oy + p / maxc * os;
+        lyaw = oyaw;
     } else {
         double sl, cl;
         sincos(p, &sl, &cl);
         double ldx = sl / maxc, ldy = (1.0 - cl) / (m == HOPE_RS_L ? maxc : -maxc);
-        double cy_ = org[3], sy_ = -org[4];             // cos(-oyaw), sin(-oyaw)
+        double cy_ = oc, sy_ = -os;             // cos(-oyaw), sin(-oyaw)
         double gdx = cy_ * ldx + sy_ * ldy, gdy = -sy_ * ldx + cy_ * ldy;
-        lx = org[0] + gdx; ly = org[1] + gdy;
-        lyaw = (m == HOPE_RS_L) ? org[2] + p : org[2] - p;
+        lx = ox + gdx; ly = oy + gdy;
+        lyaw = (m == HOPE_RS_L) ? oyaw + p : oyaw - p;
     }
+}
+__device__ __forceinline__ void rs_interp(double p, int m, double maxc, const double *org, double &lx, double &ly, double &lyaw) {
+    rs_interp(p, m, maxc, org[0], org[1], org[2], org[3], org[4], lx, ly, lyaw);
 }
 
 // Replay up to RS_CHUNK samples of a word's chain from its resume state, saving a state every
 // RS_STRIDE.  Inside a segment the step is the bare `pd += d; |pd| <= |l|` of the reference;
 // everything else (origin, segment changes, end point) goes through walker_next.
-__device__ void walk_chunk(WordSlot &s, const double *len, double step, int chunk_base) {
+template <class LenT>
+__device__ void walk_chunk(WordSlot &s, const LenT &len, double step, int chunk_base) {
     uint8_t code = s.resume_code;
     double pd = s.resume_pd;
     const int nseg = s.n;
@@ -106,21 +112,22 @@ __device__ void walk_chunk(WordSlot &s, const double *len, double step, int chun
 // The sampling plan of one tried word: segment origins in the local frame (each segment starts where the previous one
 // ends, reeds_shepp.py:468-507 through interpolate) and the first chunk of the walk.
 __device__ void plan_word(WordSlot &s, const RsWord &w, double maxc, double step) {
+    // (the lengths stay a local array: a register-resident select chain for len[seg] measured 25 % slower on B200, the
+    // local loads hit L1)
     double len[HOPE_RS_MAX_SEG];
     uint32_t ty = 0;
 #pragma unroll
     for (int k = 0; k < HOPE_RS_MAX_SEG; ++k) { len[k] = w.len[k]; s.len[k] = w.len[k]; ty |= (uint32_t)(w.types[k] & 0xF) << (4 * k); }
     s.types = ty; s.n = w.n;
-    double org[5] = {0.0, 0.0, 0.0, 1.0, 0.0};
+    double ox = 0.0, oy = 0.0, oyaw = 0.0, oc = 1.0, os = 0.0;  // scalars, not an array: sincos' output pointers would put an array on the stack
     for (int k = 0; k < w.n; ++k) {
-#pragma unroll
-        for (int q = 0; q < 5; ++q) s.org[k][q] = org[q];
+        s.org[k][0] = ox; s.org[k][1] = oy; s.org[k][2] = oyaw; s.org[k][3] = oc; s.org[k][4] = os;
         double ex, ey, eyaw;
-        rs_interp(len[k], (int)((ty >> (4 * k)) & 0xF), maxc, org, ex, ey, eyaw);  // end of segment k = origin of k+1
-        org[0] = ex; org[1] = ey;
-        if (eyaw != org[2]) { org[2] = eyaw; sincos(eyaw, &org[4], &org[3]); }
+        rs_interp(len[k], (int)((ty >> (4 * k)) & 0xF), maxc, ox, oy, oyaw, oc, os, ex, ey, eyaw);  // end of segment k = origin of k+1
+        ox = ex; oy = ey;
+        if (eyaw != oyaw) { oyaw = eyaw; double sn, cs; sincos(eyaw, &sn, &cs); os = sn; oc = cs; }
     }
-    s.end_lx = org[0];
+    s.end_lx = ox;
     s.resume_code = RS_ORIGIN; s.resume_pd = 0.0;
     walk_chunk(s, len, step, 0);
 }

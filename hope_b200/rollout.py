@@ -8,8 +8,9 @@ policy-side helpers that are batch-1 host code in the reference (row f2):
 
 The policy itself is the reference's (`model.network.MultiObsEmbedding` works with batch > 1); for
 synthetic benchmarks without the reference tree, `ReferenceShapedActor` has the same layer shapes
-(ACTOR_CONFIGS, configs.py:134-152, three modalities when the image is off).  Policy GEMMs run through
-stock PyTorch (bf16 autocast -> tensor cores); everything else stays in float64 device tensors.
+(ACTOR_CONFIGS, configs.py:134-152, three modalities when the image is off).  The 3-modal actor's forward is one kernel
+(FusedPolicy -> hope_policy_forward, bf16 tensor-core GEMMs); other policies run through stock PyTorch (bf16 autocast);
+everything else stays in float64 device tensors.
 """
 import math
 
@@ -128,6 +129,75 @@ class FusedMaskedSampler(object):
         return self.action, self.index
 
 
+class FusedPolicy(object):
+    """The 3-modal actor (MultiObsEmbedding(ACTOR_CONFIGS) / ReferenceShapedActor: lidar, target, action mask) as one kernel,
+    hope_policy_forward (csrc/policy_forward.cu): 32 envs per CTA carried through the embeddings, the transformer block and the
+    output head with every activation in shared memory, bf16 tensor-core GEMMs with float32 accumulation.  The parameters are
+    read from the module's state_dict by the reference's names and packed once (`refresh()` after an optimiser step)."""
+
+    _MATS = (("w1_lidar", "embed_lidar.0.weight", 128), ("w1_target", "embed_tgt.0.weight", 16), ("w1_mask", "embed_am.0.weight", 48),
+             ("w2_0", "embed_lidar.2.weight", 128), ("w2_1", "embed_tgt.2.weight", 128), ("w2_2", "embed_am.2.weight", 128),
+             ("w_qkv", "net.encoder.layers.0.0.fn.to_qkv.weight", 128), ("w_out", "net.encoder.layers.0.0.fn.to_out.0.weight", 256),
+             ("w_ff1", "net.encoder.layers.0.1.fn.net.0.weight", 128), ("w_ff2", "net.encoder.layers.0.1.fn.net.3.weight", 128),
+             ("w_o1", "net.output.0.weight", 384))
+    _VECS = (("b1_0", "embed_lidar.0.bias"), ("b1_1", "embed_tgt.0.bias"), ("b1_2", "embed_am.0.bias"),
+             ("b2_0", "embed_lidar.2.bias"), ("b2_1", "embed_tgt.2.bias"), ("b2_2", "embed_am.2.bias"),
+             ("ln1_g", "net.encoder.layers.0.0.norm.weight"), ("ln1_b", "net.encoder.layers.0.0.norm.bias"),
+             ("b_out", "net.encoder.layers.0.0.fn.to_out.0.bias"),
+             ("ln2_g", "net.encoder.layers.0.1.norm.weight"), ("ln2_b", "net.encoder.layers.0.1.norm.bias"),
+             ("b_ff1", "net.encoder.layers.0.1.fn.net.0.bias"), ("b_ff2", "net.encoder.layers.0.1.fn.net.3.bias"),
+             ("b_o1", "net.output.0.bias"), ("w_o2", "net.output.2.weight"), ("b_o2", "net.output.2.bias"))
+    _SHAPES = {"embed_lidar.0.weight": (128, 120), "embed_tgt.0.weight": (128, 5), "embed_am.0.weight": (128, 42),
+               "net.encoder.layers.0.0.fn.to_qkv.weight": (768, 128), "net.encoder.layers.0.0.fn.to_out.0.weight": (128, 256),
+               "net.output.0.weight": (128, 384), "net.output.2.weight": (2, 128)}
+
+    @classmethod
+    def supports(cls, module):
+        """True when `module` has exactly the lidar + target + action-mask architecture the kernel implements"""
+        sd = module.state_dict()
+        if any(k.startswith(("embed_img", "re_embed_img")) for k in sd):
+            return False
+        names = [m[1] for m in cls._MATS] + [v[1] for v in cls._VECS]
+        return all(k in sd for k in names) and all(tuple(sd[k].shape) == shp for k, shp in cls._SHAPES.items())
+
+    def __init__(self, module, n_envs, device):
+        assert self.supports(module), "hope_policy_forward implements the 3-modal actor of ACTOR_CONFIGS only"
+        self.lib = capi.load_library()
+        self.module, self.device = module, device
+        self.out = torch.zeros((n_envs, 2), dtype=torch.float32, device=device)
+        self.weights = capi.PolicyWeights()
+        self._keep = {}
+        self.refresh()
+
+    @torch.no_grad()
+    def refresh(self):
+        sd = self.module.state_dict()
+        keep = {}
+        for name, key, kpad in self._MATS:
+            w = sd[key].detach().to(self.device, torch.float32)
+            buf = torch.zeros((w.shape[0], kpad), dtype=torch.bfloat16, device=self.device)
+            buf[:, :w.shape[1]] = w.to(torch.bfloat16)
+            keep[name] = buf.contiguous()
+        for name, key in self._VECS:
+            keep[name] = sd[key].detach().to(self.device, torch.float32).contiguous().clone()
+        self._keep = keep  # the struct only holds raw pointers
+        W = self.weights
+        W.w1_lidar, W.w1_target, W.w1_mask = (keep[k].data_ptr() for k in ("w1_lidar", "w1_target", "w1_mask"))
+        for m in range(3):
+            W.w2[m] = keep[f"w2_{m}"].data_ptr(); W.b1[m] = keep[f"b1_{m}"].data_ptr(); W.b2[m] = keep[f"b2_{m}"].data_ptr()
+        for k in ("w_qkv", "w_out", "w_ff1", "w_ff2", "w_o1", "ln1_g", "ln1_b", "b_out", "ln2_g", "ln2_b", "b_ff1", "b_ff2", "b_o1", "w_o2", "b_o2"):
+            setattr(W, k, keep[k].data_ptr())
+
+    def __call__(self, net_in):
+        """net_in: float32 lidar (N,120), target (N,5), action_mask (N,42) -> float32 (N,2) policy mean in [-1,1] (buffer reused)"""
+        lidar, target, mask = net_in["lidar"], net_in["target"], net_in["action_mask"]
+        n = lidar.shape[0]
+        assert n <= self.out.shape[0] and all(t.dtype == torch.float32 and t.is_contiguous() for t in (lidar, target, mask))
+        capi.check(self.lib.hope_policy_forward(n, lidar.data_ptr(), target.data_ptr(), mask.data_ptr(), C.byref(self.weights), self.out.data_ptr(),
+                                                torch.cuda.current_stream(self.device).cuda_stream))
+        return self.out[:n]
+
+
 class _ConvBlock(nn.Module):
     """network.py:198-232 with the shipped switches (no batch norm, residual on, tanh): conv3x3 -> tanh -> maxpool2, plus the
     conv1x1 -> avgpool2 shortcut"""
@@ -233,10 +303,11 @@ class RolloutEngine(object):
     RS plan override -> env.step, all on the device; no host synchronisation inside `collect`."""
 
     def __init__(self, env, policy, log_std=None, use_planner=True, use_mask_sampling=True, state_norm=True,
-                 autocast_dtype=torch.bfloat16, seed=0, fused=True, graph=True):
+                 autocast_dtype=torch.bfloat16, seed=0, fused=True, graph=True, policy_kernel=True):
         """fused: state norm and masked sampling through the CUDA kernels of csrc/policy_glue.cu (False: the eager PyTorch
-        versions above, kept as their numerics reference).  graph: the policy forward is captured once into a CUDA graph
-        and replayed (one launch instead of ~60 small kernels per step)."""
+        versions above, kept as their numerics reference).  policy_kernel: a 3-modal actor runs as the one-kernel forward of
+        csrc/policy_forward.cu (call `refresh_policy()` after changing its parameters); otherwise graph: the PyTorch forward
+        is captured once into a CUDA graph and replayed (one launch instead of ~60 small kernels per step)."""
         self.env, self.policy = env, policy
         dev = env.device
         self.actions42 = possible_actions(dev)
@@ -250,8 +321,10 @@ class RolloutEngine(object):
         self.use_img = env.use_img and getattr(policy, "use_img", False)
         self._graph, self._graph_in, self._graph_out = None, None, None
         self.use_graph = bool(graph) and self.fused
+        self.policy_kernel = FusedPolicy(policy, env.n, dev) if (policy_kernel and self.fused and not self.use_img and FusedPolicy.supports(policy)) else None
         self.glue = ("hope_state_norm + hope_masked_sample kernels (csrc/policy_glue.cu)" if self.fused else "eager PyTorch") + \
-                    (", policy forward replayed from a CUDA graph" if self.use_graph else "")
+                    (", policy forward = hope_policy_forward (csrc/policy_forward.cu, one kernel)" if self.policy_kernel is not None else
+                     (", policy forward replayed from a CUDA graph" if self.use_graph else ""))
         self.obs = env.reset()
         if use_planner:
             env.planner_reset()
@@ -260,8 +333,15 @@ class RolloutEngine(object):
         with torch.autocast("cuda", dtype=self.autocast_dtype, enabled=self.autocast_dtype is not None):
             return self.policy(net_in).float()
 
+    def refresh_policy(self):
+        """re-read the policy's parameters into the kernel's packed copy (after an optimiser step or load_state_dict)"""
+        if self.policy_kernel is not None:
+            self.policy_kernel.refresh()
+
     def _policy_mean(self, net_in):
         """float32 policy output for the (persistent) float32 input buffers `net_in`"""
+        if self.policy_kernel is not None:
+            return self.policy_kernel(net_in)
         if not self.use_graph:
             return self._forward(net_in)
         if self._graph is None:

@@ -217,7 +217,7 @@ int hope_planner_reset(hope_ctx *ctx, void *stream);
  *
  * hope_state_norm — StateNorm.state_norm (model/state_norm.py:25-46) for a batch: with update != 0 the running statistics
  *   d_stats[2][125] (mean then M2 of the 120 lidar + 5 target columns; the caller keeps the sample count and passes the count
- *   BEFORE this batch) take in all n observations (Welford per block, Chan merge), then every observation is normalised as
+ *   BEFORE this batch) take in all n observations (two-pass moments per block, Chan merge), then every observation is normalised as
  *   (x - mean) / (std + 1e-8), std = sqrt(M2 / count), and written as float32; d_mask [n][42] (optional) is cast along.
  *   d_scratch: hope_state_norm_scratch_bytes(n) bytes of device memory.
  * hope_masked_sample — ActionMask.choose_action (model/action_mask.py:199-227) for a batch: d_mean[n][2] float32 policy output
@@ -229,6 +229,26 @@ int hope_state_norm(const double *d_lidar, const double *d_target, const double 
                     int update, void *d_scratch, float *d_out_lidar, float *d_out_target, float *d_out_mask, void *stream);
 int hope_masked_sample(int n, const float *d_mean, const double *d_log_std, const double *d_mask, const double *d_actions, uint64_t seed,
                        uint64_t step, double *d_action_out, int32_t *d_index_out, double *d_u_out, void *stream);
+
+/* The actor network between them, as one kernel (row f2 / BASELINE cfg 4): MultiObsEmbedding(ACTOR_CONFIGS) with lidar, target
+ * and action-mask inputs (model/network.py:34-196, model/attention.py:16-92, configs.py:134-153) — three 2-layer tanh embeddings,
+ * one pre-norm transformer block over the 3 tokens (8 heads x 32, feed-forward 128), Linear(384,128) tanh Linear(128,2) tanh.
+ * Weights: bf16 matrices in PyTorch's [out][in] layout with the input width zero-padded to a multiple of 16 (120 -> 128, 5 -> 16,
+ * 42 -> 48), float32 biases / LayerNorm parameters / last layer; all DEVICE pointers.  d_lidar [n][120], d_target [n][5],
+ * d_mask [n][42] float32 (hope_state_norm's outputs), d_out [n][2] float32 in [-1, 1].  bf16 operands, float32 accumulation. */
+typedef struct hope_policy_weights {
+    const void *w1_lidar, *w1_target, *w1_mask; /* bf16 [128][128], [128][16], [128][48]: embed_*.0.weight, input width padded   */
+    const void *w2[3];                          /* bf16 [128][128]: embed_lidar.2 / embed_tgt.2 / embed_am.2 .weight             */
+    const void *w_qkv, *w_out;                  /* bf16 [768][128] attn.fn.to_qkv.weight, [128][256] attn.fn.to_out.0.weight    */
+    const void *w_ff1, *w_ff2;                  /* bf16 [128][128]: ff.fn.net.0 / ff.fn.net.3 .weight                            */
+    const void *w_o1;                           /* bf16 [128][384]: net.output.0.weight                                          */
+    const float *b1[3], *b2[3];                 /* [128] each, order lidar, target, mask                                         */
+    const float *ln1_g, *ln1_b, *b_out, *ln2_g, *ln2_b, *b_ff1, *b_ff2, *b_o1; /* [128] each                                     */
+    const float *w_o2, *b_o2;                   /* [2][128], [2]: net.output.2                                                   */
+} hope_policy_weights;
+int hope_policy_forward(int n, const float *d_lidar, const float *d_target, const float *d_mask, const hope_policy_weights *w, float *d_out,
+                        void *stream);
+int hope_policy_forward_smem_bytes(void);
 
 /* State access (device -> host copies; synchronous). */
 int hope_get_state(hope_ctx *ctx, double *h_pose, int32_t *h_t, double *h_accum, int32_t *h_scene_id);

@@ -244,7 +244,7 @@ def test_rollout_engine_fused_path_and_eager_path_agree_in_distribution():
     env_b = BatchedParkingEnv(n, scenes=sc, auto_reset=True)
     torch.manual_seed(0)
     actor = rollout.ReferenceShapedActor().to(env_a.device)
-    fused = rollout.RolloutEngine(env_a, actor, seed=0, fused=True, graph=True)
+    fused = rollout.RolloutEngine(env_a, actor, seed=0, fused=True, graph=True, policy_kernel=False)
     eager = rollout.RolloutEngine(env_b, actor, seed=0, fused=False)
     assert "policy_glue" in fused.glue and "CUDA graph" in fused.glue and eager.glue == "eager PyTorch"
     for t in range(6):
@@ -260,3 +260,58 @@ def test_rollout_engine_fused_path_and_eager_path_agree_in_distribution():
     fused.collect(8)
     torch.cuda.synchronize()
     env_a.close(); env_b.close()
+
+
+@pytest.mark.parametrize("n", [65, 4096])
+def test_policy_forward_kernel_matches_the_float32_module(n):
+    """hope_policy_forward (one kernel, bf16 operands, float32 accumulation) against the plain float32 PyTorch forward of the
+    same 3-modal actor, default initialisation and a 3x scaled copy (larger pre-activations, saturating tanh).  Bar: no further
+    from float32 than twice what PyTorch's own bf16 autocast forward (the path it replaces) is, plus 2e-3; and absolutely
+    max |diff| <= 3e-2 on outputs in [-1, 1] at default initialisation."""
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(7)
+    for scale in (1.0, 3.0):
+        net = rollout.ReferenceShapedActor().to(dev).eval()
+        with torch.no_grad():
+            for name, p in net.named_parameters():
+                if name.endswith("weight") and p.dim() == 2:
+                    p.mul_(scale)
+                if name.endswith("bias") or "norm" in name:
+                    p.add_(0.1 * torch.randn_like(p))
+        obs = {"lidar": torch.randn(n, 120, device=dev), "target": torch.randn(n, 5, device=dev), "action_mask": torch.rand(n, 42, device=dev)}
+        obs["action_mask"][::5] = 0.0
+        with torch.no_grad():
+            ref = net(obs)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                low = net(obs).float()
+        fp = rollout.FusedPolicy(net, n, dev)
+        got = fp(obs).clone()
+        torch.cuda.synchronize()
+        assert got.shape == (n, 2) and torch.isfinite(got).all() and got.abs().max() <= 1.0
+        err, err_autocast = (got - ref).abs(), (low - ref).abs()
+        print(f"  scale {scale}: kernel max {err.max():.2e} mean {err.mean():.2e} | autocast max {err_autocast.max():.2e} mean {err_autocast.mean():.2e}")
+        assert err.max() <= 2 * err_autocast.max() + 2e-3 and err.mean() <= 2 * err_autocast.mean() + 5e-4
+        assert err.max() <= (3e-2 if scale == 1.0 else 1.5e-1)
+        # a parameter change is picked up by refresh()
+        with torch.no_grad():
+            net.net.output[2].bias.add_(0.25)
+            ref2 = net(obs)
+        fp.refresh()
+        assert (fp(obs) - ref2).abs().max() <= (3e-2 if scale == 1.0 else 1.5e-1) and (ref2 - ref).abs().max() > 0.05
+
+
+def test_rollout_engine_uses_the_policy_kernel():
+    n = 2048
+    env = BatchedParkingEnv(n, scenes=generate_scenes(n, "Normal", 4), auto_reset=True)
+    policy, _ = rollout.reference_actor(device=env.device)
+    eng = rollout.RolloutEngine(env, policy, seed=3)
+    assert eng.policy_kernel is not None and "hope_policy_forward" in eng.glue
+    ref = rollout.RolloutEngine(BatchedParkingEnv(n, scenes=generate_scenes(n, "Normal", 4), auto_reset=True), policy, seed=3, policy_kernel=False)
+    a, (mean_a, _) = eng.act(eng.obs)
+    b, (mean_b, _) = ref.act(ref.obs)
+    torch.cuda.synchronize()
+    assert (mean_a - mean_b).abs().max() < 2e-2            # same observations, same statistics: kernel vs autocast graph forward
+    assert (a == b).all(dim=1).float().mean() > 0.97       # same Philox stream: the draws differ only where the means' difference moves a boundary
+    eng.collect(4)
+    torch.cuda.synchronize()
+    eng.env.close(); ref.env.close()
