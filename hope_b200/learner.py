@@ -13,7 +13,7 @@ import torch
 from torch import nn
 import torch.distributed as dist
 
-from .rollout import ReferenceShapedActor
+from .rollout import FusedPolicy, ReferenceShapedActor
 
 
 class QNet(nn.Module):
@@ -47,33 +47,56 @@ class DeviceReplay(object):
     KEYS = (("lidar", 120), ("target", 5), ("action_mask", 42))
 
     def __init__(self, capacity, device, keys=None):
-        self.capacity, self.device, self.size, self.head = int(capacity), device, 0, 0
+        self.capacity, self.device = int(capacity), device
+        self._head = self._size = self._ar = self._trash = None
+        self.pushed_upper_bound = 0  # rows offered so far (host counter; >= the number kept)
         if keys is not None:
             self.KEYS = tuple(keys)
         f = lambda *s: torch.zeros(s, dtype=torch.float32, device=device)
-        self.obs = {k: f(capacity, d) for k, d in self.KEYS}
-        self.nxt = {k: f(capacity, d) for k, d in self.KEYS}
-        self.action, self.reward, self.done = f(capacity, 2), f(capacity), f(capacity)
+        rows = self.capacity + 1     # + the spare slot rows that are not kept are written to
+        self._obs = {k: f(rows, d) for k, d in self.KEYS}
+        self._nxt = {k: f(rows, d) for k, d in self.KEYS}
+        self._action, self._reward, self._done = f(rows, 2), f(rows), f(rows)
+        # the ring itself (views without the spare slot)
+        self.obs = {k: v[:self.capacity] for k, v in self._obs.items()}
+        self.nxt = {k: v[:self.capacity] for k, v in self._nxt.items()}
+        self.action, self.reward, self.done = self._action[:self.capacity], self._reward[:self.capacity], self._done[:self.capacity]
 
     def push(self, obs, action, reward, done, nxt, keep=None):
+        """Append the rows with keep != 0 (all rows when keep is None).  No host synchronisation: the write position and the
+        fill level live on the device, rows that are not kept are written to a spare slot behind the ring."""
         n = action.shape[0]
-        idx = (torch.arange(n, device=self.device) + self.head) % self.capacity
+        if self._head is None:
+            self._head = torch.zeros((), dtype=torch.long, device=self.device)
+            self._size = torch.zeros((), dtype=torch.long, device=self.device)
+            self._ar = torch.arange(n, device=self.device)
+            self._trash = torch.full((), self.capacity, dtype=torch.long, device=self.device)
+        if self._ar.numel() != n:
+            self._ar = torch.arange(n, device=self.device)
         if keep is not None:  # e.g. drop the auto-reset pseudo-steps
-            sel = keep.nonzero(as_tuple=True)[0]
-            idx = (torch.arange(sel.numel(), device=self.device) + self.head) % self.capacity
-            n = sel.numel()
-            pick = lambda t: t[sel]
+            k = keep.to(torch.bool)
+            rank = torch.cumsum(k.to(torch.long), 0) - 1
+            idx = torch.where(k, (rank + self._head) % self.capacity, self._trash)
+            cnt = rank[-1] + 1
         else:
-            pick = lambda t: t
-        for k, _ in self.KEYS:
-            self.obs[k][idx] = pick(obs[k]).float()
-            self.nxt[k][idx] = pick(nxt[k]).float()
-        self.action[idx] = pick(action).float(); self.reward[idx] = pick(reward).float(); self.done[idx] = pick(done).float()
-        self.head = (self.head + n) % self.capacity
-        self.size = min(self.capacity, self.size + n)
+            idx = (self._ar + self._head) % self.capacity
+            cnt = torch.full((), n, dtype=torch.long, device=self.device)
+        for key, _ in self.KEYS:
+            self._obs[key].index_copy_(0, idx, obs[key].float())
+            self._nxt[key].index_copy_(0, idx, nxt[key].float())
+        self._action.index_copy_(0, idx, action.float()); self._reward.index_copy_(0, idx, reward.float()); self._done.index_copy_(0, idx, done.float())
+        self._head = (self._head + cnt) % self.capacity
+        self._size = torch.clamp(self._size + cnt, max=self.capacity)
+        self.pushed_upper_bound += n
+
+    @property
+    def size(self):
+        """fill level (reads the device counter: synchronises; the rollout loop uses `pushed_upper_bound` instead)"""
+        return 0 if self._size is None else int(self._size.item())
 
     def sample(self, batch, generator=None):
-        idx = torch.randint(0, max(self.size, 1), (batch,), device=self.device, generator=generator)
+        size = self._size.clamp(min=1)
+        idx = (torch.rand(batch, device=self.device, generator=generator) * size).long().clamp_(max=self.capacity - 1)
         o = {k: self.obs[k][idx] for k, _ in self.KEYS}
         n = {k: self.nxt[k][idx] for k, _ in self.KEYS}
         return o, self.action[idx], self.reward[idx], self.done[idx], n
@@ -192,7 +215,7 @@ class SacRollout(object):
     hand-off on), push every real transition to the device replay, and every `update_every` env steps run one
     SAC update whose gradient all-reduce overlaps the following rollout steps."""
 
-    def __init__(self, env, world=1, batch=8192, update_every=8, replay_capacity=1 << 20, seed=0):
+    def __init__(self, env, world=1, batch=8192, update_every=8, replay_capacity=1 << 20, seed=0, policy_kernel=True):
         self.env, self.batch, self.update_every = env, batch, update_every
         self.learner = SacLite(env.device, world, seed=seed)
         self.replay = DeviceReplay(replay_capacity, env.device)
@@ -201,6 +224,17 @@ class SacRollout(object):
         env.planner_reset()
         self.pending_update = False
         self.updates = 0
+        # acting: the actor's forward as one kernel (csrc/policy_forward.cu), its packed weights re-read after every update
+        self.actor_kernel = FusedPolicy(self.learner.actor, env.n, env.device) if (policy_kernel and FusedPolicy.supports(self.learner.actor)) else None
+
+    @torch.no_grad()
+    def _act(self, obs):
+        L = self.learner
+        if self.actor_kernel is None:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return L._pi(obs)[0]
+        mean = self.actor_kernel(obs)
+        return torch.tanh(mean + torch.exp(L.actor.log_std) * torch.randn(mean.shape, dtype=mean.dtype, device=mean.device, generator=self.gen))
 
     @staticmethod
     def _f32(o):
@@ -209,19 +243,22 @@ class SacRollout(object):
     def run(self, n_steps):
         env, L = self.env, self.learner
         for t in range(n_steps):
-            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
-                a, _ = L._pi(self.obs)
+            a = self._act(self.obs)
             act, executing = env.planner_actions(a.double().contiguous())
             obs, reward, done, info = env.step(act)
             nxt = self._f32(obs)
             self.replay.push(self.obs, act, reward, done, nxt, keep=info["was_reset"] == 0)
             self.obs = nxt
-            if (t + 1) % self.update_every == 0 and self.replay.size >= self.batch:
+            if (t + 1) % self.update_every == 0 and self.replay.pushed_upper_bound >= 2 * self.batch:
                 if self.pending_update:
                     L.apply()            # finishes the previous update: its all-reduce ran under the last rollout steps
+                    if self.actor_kernel is not None:
+                        self.actor_kernel.refresh()
                 L.backward(self.replay.sample(self.batch, self.gen))
                 self.pending_update = True
                 self.updates += 1
         if self.pending_update:
             L.apply()
+            if self.actor_kernel is not None:
+                self.actor_kernel.refresh()
             self.pending_update = False

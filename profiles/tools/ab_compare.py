@@ -22,6 +22,7 @@ sys.path.insert(0, ROOT)
 
 def build_variant(name, defs, force=False):
     from hope_b200 import build as hb
+    defs = " ".join(tok for tok in defs.split() if not tok.startswith("ENV:"))
     path = os.path.join(HERE, "_ab", f"libhope_b200_{name}.so")
     deps = [os.path.join(hb.CSRC, d) for d in hb.DEPS]
     if not force and os.path.exists(path) and all(os.path.getmtime(d) <= os.path.getmtime(path) for d in deps):
@@ -46,13 +47,23 @@ def run_variant(args, name, defs, env_a, scenes, act, total):
     from hope_b200 import build as hb, capi
     from hope_b200.batched_env import BatchedParkingEnv
     n = args.envs
+    env_sets = [tok[4:].split("=", 1) for tok in defs.split() if tok.startswith("ENV:")]   # "ENV:NAME=VALUE": set while the variant's context is created
+    defs = " ".join(tok for tok in defs.split() if not tok.startswith("ENV:"))
     path_b = build_variant(name, defs)
     path_a = hb.VARIANTS[16]
     hb.VARIANTS[16] = path_b
     capi._LIBS.pop(16, None)
+    saved = {k: os.environ.get(k) for k, _ in env_sets}
     try:
+        for k, v in env_sets:
+            os.environ[k] = v
         env_b = BatchedParkingEnv(n, scenes=scenes, auto_reset=True)  # binds the variant library
     finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
         hb.VARIANTS[16] = path_a
         capi._LIBS[16] = env_a.lib
     assert env_a.lib is not env_b.lib
