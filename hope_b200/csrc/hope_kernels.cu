@@ -91,7 +91,10 @@ __global__ void __launch_bounds__(ADV_THREADS, MINB) k_advance(int n, Pool pool,
 // =============================================================================================
 #include "observe.cuh"
 
-__global__ void __launch_bounds__(64) k_observe(int n, Pool pool, EnvState st, Tables tb, hope_params par, hope_out out) {
+#ifndef HOPE_OBS_MINBLOCKS
+#define HOPE_OBS_MINBLOCKS 18  // resident 64-thread blocks per SM the register allocation is sized for (56 registers; shared memory allows 20)
+#endif
+__global__ void __launch_bounds__(64, HOPE_OBS_MINBLOCKS) k_observe(int n, Pool pool, EnvState st, Tables tb, hope_params par, hope_out out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int env = blockIdx.x * (blockDim.x >> 5) + warp_in_block;
@@ -169,7 +172,7 @@ __global__ void __launch_bounds__(128) k_rs_walk(RsScratch rs, Tables tb, hope_p
 #define HOPE_CHK_WARPS 4
 #endif
 #ifndef HOPE_CHK_MINBLOCKS
-#define HOPE_CHK_MINBLOCKS 4
+#define HOPE_CHK_MINBLOCKS 5   // 96 registers, 5 blocks = 20 warps per SM: k_rs_check 7 % faster on B200 than 4 blocks of 116 registers, 6 blocks of 80 no better (profiles/r02_ab_occupancy.jsonl)
 #endif
 constexpr int CHK_WARPS = HOPE_CHK_WARPS;  // warps per block of k_rs_check
 
