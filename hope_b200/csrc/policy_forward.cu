@@ -78,19 +78,25 @@ __device__ __forceinline__ void warp_gemm(float (&acc)[MT][NT][4], const __nv_bf
     const __nv_bfloat16 *wr[NT];
 #pragma unroll
     for (int ni = 0; ni < NT; ++ni) wr[ni] = w + (size_t)(wrow(ni) + (lane >> 2)) * ldw;
+    // the weights come from L2: the fragments of K block k + 1 are requested before the tensor-core work of block k
+    uint32_t b[2][NT][2];
+#pragma unroll
+    for (int ni = 0; ni < NT; ++ni) ldb16x8(b[0][ni][0], b[0][ni][1], wr[ni], 0, lane);
 #pragma unroll
     for (int k0 = 0; k0 < K; k0 += 16) {
-        uint32_t b[NT][2];
+        const int cur = (k0 >> 4) & 1;
+        if (k0 + 16 < K) {
 #pragma unroll
-        for (int ni = 0; ni < NT; ++ni) ldb16x8(b[ni][0], b[ni][1], wr[ni], k0, lane);
-        const int arow = row0 + (k0 / E) * a_rows_per_kblock, ak = a_rows_per_kblock ? k0 % E : k0;
-#pragma unroll
-        for (int mi = 0; mi < MT; ++mi) {
-            uint32_t af[4];
-            lda16x16(af, a, lda, arow + 16 * mi, ak, lane);
-#pragma unroll
-            for (int ni = 0; ni < NT; ++ni) mma16816(acc[mi][ni], af, b[ni][0], b[ni][1]);
+            for (int ni = 0; ni < NT; ++ni) ldb16x8(b[cur ^ 1][ni][0], b[cur ^ 1][ni][1], wr[ni], k0 + 16, lane);
         }
+        const int arow = row0 + (k0 / E) * a_rows_per_kblock, ak = a_rows_per_kblock ? k0 % E : k0;
+        uint32_t af[MT][4];  // all row tiles' A fragments first: their shared-memory latency is paid once per K block, not once per tile
+#pragma unroll
+        for (int mi = 0; mi < MT; ++mi) lda16x16(af[mi], a, lda, arow + 16 * mi, ak, lane);
+#pragma unroll
+        for (int mi = 0; mi < MT; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < NT; ++ni) mma16816(acc[mi][ni], af[mi], b[cur][ni][0], b[cur][ni][1]);
     }
 }
 
@@ -220,30 +226,60 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
                     *reinterpret_cast<__nv_bfloat162 *>(&sm.u.hd.qkv[r + 8][c]) = __floats2bfloat162_rn(qacc[mi][ni][2], qacc[mi][ni][3]);
                 }
             __syncthreads();
-            // softmax over the env's 3 tokens: thread = (query row, half of the 32 output dims)
-            if (tid < 2 * ROWS) {
+            // softmax over the env's 3 tokens: two adjacent threads per query row, each owns 16 of the head's 32 dims (its half of
+            // every q . k, summed with one shuffle, and its half of the output)
+            {
                 const int r = tid >> 1, half = tid & 1, e = r % BM;
-                float s[3];
+                const bool on = r < ROWS;
+                float qv[16];
+                float s[3] = {0.f, 0.f, 0.f};
+                if (on) {
+                    const uint4 *qp = reinterpret_cast<const uint4 *>(&sm.u.hd.qkv[r][16 * half]);
 #pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    const __nv_bfloat16 *q = &sm.u.hd.qkv[r][0], *k = &sm.u.hd.qkv[j * BM + e][DH];
-                    float d = 0.f;
+                    for (int v = 0; v < 2; ++v) {
+                        const uint4 w4 = qp[v];
+                        const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-                    for (int c = 0; c < DH; c += 2) {
-                        const float2 qa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(q + c)), ka = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(k + c));
-                        d += qa.x * ka.x + qa.y * ka.y;
+                        for (int c = 0; c < 4; ++c) { qv[8 * v + 2 * c] = __uint_as_float(ws[c] << 16); qv[8 * v + 2 * c + 1] = __uint_as_float(ws[c] & 0xffff0000u); }
                     }
-                    s[j] = d * 0.17677669529663687f;  // dim_head ** -0.5
-                }
-                const float mx = fmaxf(s[0], fmaxf(s[1], s[2]));
-                const float p0 = __expf(s[0] - mx), p1 = __expf(s[1] - mx), p2 = __expf(s[2] - mx), inv = 1.f / (p0 + p1 + p2);
-                const __nv_bfloat16 *v0 = &sm.u.hd.qkv[e][2 * DH + 16 * half], *v1 = &sm.u.hd.qkv[BM + e][2 * DH + 16 * half], *v2 = &sm.u.hd.qkv[2 * BM + e][2 * DH + 16 * half];
 #pragma unroll
-                for (int c = 0; c < 16; c += 2) {
-                    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(v0 + c)), b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(v1 + c)),
-                                 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(v2 + c));
-                    *reinterpret_cast<__nv_bfloat162 *>(&sm.u.hd.att[r][16 * half + c]) =
-                        __floats2bfloat162_rn((p0 * a.x + p1 * b.x + p2 * d.x) * inv, (p0 * a.y + p1 * b.y + p2 * d.y) * inv);
+                    for (int j = 0; j < 3; ++j) {
+                        const uint4 *kp = reinterpret_cast<const uint4 *>(&sm.u.hd.qkv[j * BM + e][DH + 16 * half]);
+                        float d = 0.f;
+#pragma unroll
+                        for (int v = 0; v < 2; ++v) {
+                            const uint4 w4 = kp[v];
+                            const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) d += qv[8 * v + 2 * c] * __uint_as_float(ws[c] << 16) + qv[8 * v + 2 * c + 1] * __uint_as_float(ws[c] & 0xffff0000u);
+                        }
+                        s[j] = d;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 3; ++j) s[j] = (s[j] + __shfl_xor_sync(0xffffffffu, s[j], 1)) * 0.17677669529663687f;  // dim_head ** -0.5
+                if (on) {
+                    const float mx = fmaxf(s[0], fmaxf(s[1], s[2]));
+                    const float p0 = __expf(s[0] - mx), p1 = __expf(s[1] - mx), p2 = __expf(s[2] - mx), inv = 1.f / (p0 + p1 + p2);
+                    const float w0 = p0 * inv, w1 = p1 * inv, w2 = p2 * inv;
+                    const uint4 *v0 = reinterpret_cast<const uint4 *>(&sm.u.hd.qkv[e][2 * DH + 16 * half]);
+                    const uint4 *v1 = reinterpret_cast<const uint4 *>(&sm.u.hd.qkv[BM + e][2 * DH + 16 * half]);
+                    const uint4 *v2 = reinterpret_cast<const uint4 *>(&sm.u.hd.qkv[2 * BM + e][2 * DH + 16 * half]);
+                    uint4 *dst = reinterpret_cast<uint4 *>(&sm.u.hd.att[r][16 * half]);
+#pragma unroll
+                    for (int v = 0; v < 2; ++v) {
+                        const uint4 a4 = v0[v], b4 = v1[v], c4 = v2[v];
+                        const uint32_t as[4] = {a4.x, a4.y, a4.z, a4.w}, bs[4] = {b4.x, b4.y, b4.z, b4.w}, cs[4] = {c4.x, c4.y, c4.z, c4.w};
+                        uint32_t o[4];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const float lo = w0 * __uint_as_float(as[c] << 16) + w1 * __uint_as_float(bs[c] << 16) + w2 * __uint_as_float(cs[c] << 16);
+                            const float hi = w0 * __uint_as_float(as[c] & 0xffff0000u) + w1 * __uint_as_float(bs[c] & 0xffff0000u) + w2 * __uint_as_float(cs[c] & 0xffff0000u);
+                            const __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
+                            o[c] = *reinterpret_cast<const uint32_t *>(&pk);
+                        }
+                        dst[v] = make_uint4(o[0], o[1], o[2], o[3]);
+                    }
                 }
             }
             __syncthreads();
