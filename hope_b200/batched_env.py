@@ -170,6 +170,12 @@ class BatchedParkingEnv(object):
                                       self._stream()), self.ctx)
         return self._obs(), self.out["reward"], self.out["done"], self._info()
 
+    def wait_observed(self, stream):
+        """Make the torch stream `stream` wait for the observation of the last step() / reset() without waiting for that step's
+        Reeds-Shepp kernels (hope_wait_observed).  Returns False when the library cannot offer that (the caller then orders
+        itself behind the stream step() ran on, as usual)."""
+        return self.lib.hope_wait_observed(self.ctx, stream.cuda_stream) == 0
+
     def step_kinematics_collision(self, actions):
         """BASELINE cfg 2: pose integration + collision (+ arrival) only."""
         o = self.out

@@ -94,6 +94,7 @@ def load_library(max_obs=16):
         "hope_max_obs": (C.c_int, []),
         "hope_planner_actions": (C.c_int, [vp, dp, C.POINTER(Out), dp, vp, C.c_double, vp]),
         "hope_planner_reset": (C.c_int, [vp, vp]),
+        "hope_wait_observed": (C.c_int, [vp, vp]),
         "hope_fp64_peak_tflops": (C.c_int, [i32, C.POINTER(C.c_double)]),
         "hope_state_norm_scratch_bytes": (C.c_int, [i32]),
         "hope_state_norm": (C.c_int, [dp, dp, dp, i32, dp, C.c_double, i32, vp, vp, vp, vp, vp]),

@@ -611,6 +611,8 @@ struct hope_ctx {
     // waits for it, so the two can be mixed without an explicit synchronisation in between.
     cudaEvent_t ev_dev = nullptr;
     bool dev_pending = false;
+    cudaEvent_t ev_obs_done = nullptr;  // recorded behind k_observe [+ k_render] of the last hope_step / hope_reset over the whole batch
+    bool obs_done_valid = false;
     unsigned long long launches = 0;
     bool profile = false;
     bool profile_serial = false;  // hope_profile_enable(ctx, 2): no k_observe / Reeds-Shepp overlap, so each kernel is timed alone
@@ -798,6 +800,10 @@ int launch_range(hope_ctx *ctx, const double *d_action, const hope_out &out_all,
         }
         if (early_out) { int rc = copy_fields(ctx, early_out, BY_OBSERVE, so, lo, cnt); if (rc) return rc; }
         if (fork) CK(cudaEventRecord(lane.ev_observed, so));
+        if (!ctx->in_host_step && lo == 0 && cnt == ctx->n) {  // hope_wait_observed: the observation of the whole batch is complete here
+            CK(cudaEventRecord(ctx->ev_obs_done, so));
+            ctx->obs_done_valid = true;
+        }
     }
     if (stages & HOPE_STAGE_RS) {
         const size_t wo = (size_t)lo * MAXW;
@@ -994,6 +1000,7 @@ int hope_create(hope_ctx **out, int device, int n_envs, int pool_size, const hop
     }
     CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_dev, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_obs_done, cudaEventDisableTiming));
     for (int li = 0; li < hope_ctx::MAX_LANES; ++li) CK(cudaEventCreateWithFlags(&ctx->ev_join[li], cudaEventDisableTiming));
     for (auto &e : ctx->ev_chunk) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto &e : ctx->ev_adv) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1045,6 +1052,7 @@ int hope_destroy(hope_ctx *ctx) {
     if (ctx->host_graph) cudaGraphExecDestroy(ctx->host_graph);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_dev) cudaEventDestroy(ctx->ev_dev);
+    if (ctx->ev_obs_done) cudaEventDestroy(ctx->ev_obs_done);
     for (auto e : ctx->ev_join) if (e) cudaEventDestroy(e);
     for (auto e : ctx->ev_chunk) if (e) cudaEventDestroy(e);
     for (auto e : ctx->ev_adv) if (e) cudaEventDestroy(e);
@@ -1214,6 +1222,7 @@ int hope_step(hope_ctx *ctx, const double *d_action, const hope_out *d_out, unsi
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     stages |= HOPE_STAGE_ADVANCE;
+    ctx->obs_done_valid = false;
     const int n = ctx->n;
     int chunks = ctx->device_chunks;
     if (n < 8192 * chunks) chunks = n / 8192 > 0 ? n / 8192 : 1;
@@ -1710,6 +1719,14 @@ int hope_planner_actions(hope_ctx *ctx, const double *d_policy_action, const hop
     ctx->launches++;
     CK(cudaGetLastError());
     return mark_device_call(ctx, static_cast<cudaStream_t>(stream));
+}
+
+int hope_wait_observed(hope_ctx *ctx, void *stream) {
+    if (!ctx) return HOPE_ERR_INVALID;
+    if (!ctx->obs_done_valid) return HOPE_ERR_INVALID;  // the last step had no observation stage, or ran in several env ranges
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), ctx->ev_obs_done, 0));
+    return HOPE_OK;
 }
 
 int hope_planner_reset(hope_ctx *ctx, void *stream) {

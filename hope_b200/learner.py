@@ -224,6 +224,7 @@ class SacRollout(object):
         env.planner_reset()
         self.pending_update = False
         self.updates = 0
+        self.overlap, self._pol_stream, self._next_action, self._steps_done = True, None, None, 0
         # acting: the actor's forward as one kernel (csrc/policy_forward.cu), its packed weights re-read after every update
         self.actor_kernel = FusedPolicy(self.learner.actor, env.n, env.device) if (policy_kernel and FusedPolicy.supports(self.learner.actor)) else None
 
@@ -241,15 +242,34 @@ class SacRollout(object):
         return {"lidar": o["lidar"].float(), "target": o["target"].float(), "action_mask": o["action_mask"].float()}
 
     def run(self, n_steps):
+        """n_steps rollout steps.  The policy side of the next step (float32 casts + actor forward: it needs the observation
+        only) runs on a second stream next to the Reeds-Shepp kernels of the current step (hope_wait_observed), except on the
+        steps that finish an update, where the actor's new weights have to be in place first."""
         env, L = self.env, self.learner
+        dev = env.device
+        main = torch.cuda.current_stream(dev)
+        if self._pol_stream is None:
+            self._pol_stream = torch.cuda.Stream(device=dev)
+        pol = self._pol_stream
+        a = self._act(self.obs) if self._next_action is None else self._next_action
         for t in range(n_steps):
-            a = self._act(self.obs)
             act, executing = env.planner_actions(a.double().contiguous())
             obs, reward, done, info = env.step(act)
-            nxt = self._f32(obs)
+            update_due = (self._steps_done + 1) % self.update_every == 0 and self.replay.pushed_upper_bound + env.n >= 2 * self.batch
+            ahead = self.overlap and not update_due and env.wait_observed(pol)
+            if ahead:
+                with torch.cuda.stream(pol):
+                    nxt = self._f32(obs)
+                    a = self._act(nxt)
+                    for x in (a,) + tuple(nxt.values()):
+                        x.record_stream(main)
+                main.wait_stream(pol)
+            else:
+                nxt = self._f32(obs)
             self.replay.push(self.obs, act, reward, done, nxt, keep=info["was_reset"] == 0)
             self.obs = nxt
-            if (t + 1) % self.update_every == 0 and self.replay.pushed_upper_bound >= 2 * self.batch:
+            self._steps_done += 1
+            if update_due:
                 if self.pending_update:
                     L.apply()            # finishes the previous update: its all-reduce ran under the last rollout steps
                     if self.actor_kernel is not None:
@@ -257,8 +277,12 @@ class SacRollout(object):
                 L.backward(self.replay.sample(self.batch, self.gen))
                 self.pending_update = True
                 self.updates += 1
+            if not ahead:
+                a = self._act(self.obs)
+        self._next_action = a
         if self.pending_update:
             L.apply()
             if self.actor_kernel is not None:
                 self.actor_kernel.refresh()
             self.pending_update = False
+            self._next_action = None   # computed with the weights before this update

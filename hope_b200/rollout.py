@@ -303,7 +303,7 @@ class RolloutEngine(object):
     RS plan override -> env.step, all on the device; no host synchronisation inside `collect`."""
 
     def __init__(self, env, policy, log_std=None, use_planner=True, use_mask_sampling=True, state_norm=True,
-                 autocast_dtype=torch.bfloat16, seed=0, fused=True, graph=True, policy_kernel=True):
+                 autocast_dtype=torch.bfloat16, seed=0, fused=True, graph=True, policy_kernel=True, overlap=True):
         """fused: state norm and masked sampling through the CUDA kernels of csrc/policy_glue.cu (False: the eager PyTorch
         versions above, kept as their numerics reference).  policy_kernel: a 3-modal actor runs as the one-kernel forward of
         csrc/policy_forward.cu (call `refresh_policy()` after changing its parameters); otherwise graph: the PyTorch forward
@@ -320,6 +320,7 @@ class RolloutEngine(object):
         self.gen = torch.Generator(device=dev); self.gen.manual_seed(seed)
         self.use_img = env.use_img and getattr(policy, "use_img", False)
         self._graph, self._graph_in, self._graph_out = None, None, None
+        self.overlap, self._pol_stream = bool(overlap), None  # collect(store=None): next action computed next to the Reeds-Shepp kernels
         self.use_graph = bool(graph) and self.fused
         self.policy_kernel = FusedPolicy(policy, env.n, dev) if (policy_kernel and self.fused and not self.use_img and FusedPolicy.supports(policy)) else None
         self.glue = ("hope_state_norm + hope_masked_sample kernels (csrc/policy_glue.cu)" if self.fused else "eager PyTorch") + \
@@ -388,6 +389,34 @@ class RolloutEngine(object):
             action = torch.clamp(mean + std * torch.randn(mean.shape, dtype=mean.dtype, device=mean.device, generator=self.gen), -1, 1)
         return action.contiguous(), (mean, std)
 
+    def _collect_overlapped(self, n_steps):
+        """collect() without a store, software-pipelined by one step: the policy side of step t + 1 (state norm, actor forward,
+        masked sampling: it needs lidar / target / action mask only) runs on a second stream as soon as k_observe of step t is
+        done (hope_wait_observed), next to the Reeds-Shepp kernels of step t; the plan hand-off of step t + 1, which needs their
+        result, waits for both.  Same kernels, same inputs, same order per stream as the plain loop."""
+        env, dev = self.env, self.env.device
+        main = torch.cuda.current_stream(dev)
+        if self._pol_stream is None:
+            self._pol_stream = torch.cuda.Stream(device=dev)
+        pol = self._pol_stream
+        action, dist = self.act(self.obs)
+        for t in range(n_steps):
+            if self.use_planner:
+                action, _ = env.planner_actions(action)
+            obs, reward, done, info = env.step(action)
+            self.obs = obs
+            if t + 1 == n_steps:
+                break
+            if env.wait_observed(pol):
+                with torch.cuda.stream(pol):
+                    action, dist = self.act(obs)
+                    for x in (action,) + tuple(dist):
+                        x.record_stream(main)
+                main.wait_stream(pol)      # the hand-off and the next step read the sampled action
+            else:
+                action, dist = self.act(obs)
+        return self.obs
+
     @staticmethod
     def log_prob(action, dist):
         """Gaussian log-density of `action` under the policy's (mean, std) (ppo_agent.py get_log_prob)"""
@@ -401,6 +430,8 @@ class RolloutEngine(object):
         store is given), `action` the action the env executed — the Reeds-Shepp plan's where a route is being executed — and
         `log_prob` the policy's log-density of that executed action (parking_agent.py:93-97 recomputes it for plan actions)."""
         env = self.env
+        if store is None and self.fused and self.overlap and n_steps > 0:
+            return self._collect_overlapped(n_steps)
         for t in range(n_steps):
             action, dist = self.act(self.obs)
             executing = None

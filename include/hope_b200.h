@@ -213,6 +213,13 @@ int hope_planner_actions(hope_ctx *ctx, const double *d_policy_action, const hop
                          uint8_t *d_executing, double step_ratio, void *stream);
 int hope_planner_reset(hope_ctx *ctx, void *stream);
 
+/* Makes `stream` wait until the observation arrays of the last hope_step / hope_reset (lidar, mask, mask_steps, img; pose, target,
+ * reward, status, done are complete even earlier) have been written, WITHOUT waiting for the Reeds-Shepp kernels of that step,
+ * which hope_step runs next to k_observe.  A rollout loop uses it to start the policy's forward pass for the next action in the
+ * shadow of the Reeds-Shepp search (the plan hand-off, which needs rs_*, waits on the stream hope_step was given as usual).
+ * HOPE_ERR_INVALID if the last step had no observation stage or was split into several env ranges. */
+int hope_wait_observed(hope_ctx *ctx, void *stream);
+
 /* The two non-GEMM steps between the env and the policy network of the rollout loop (row f2), stateless (no context):
  *
  * hope_state_norm — StateNorm.state_norm (model/state_norm.py:25-46) for a batch: with update != 0 the running statistics

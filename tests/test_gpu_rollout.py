@@ -315,3 +315,29 @@ def test_rollout_engine_uses_the_policy_kernel():
     eng.collect(4)
     torch.cuda.synchronize()
     eng.env.close(); ref.env.close()
+
+
+def test_overlapped_collect_equals_the_plain_loop():
+    """RolloutEngine.collect without a store computes the next action next to the Reeds-Shepp kernels of the current step
+    (hope_wait_observed + a second stream); kernels, inputs and per-stream order are the plain loop's, so after 12 steps the two
+    engines must hold identical states, observations and running statistics."""
+    n = 4096
+    sc = generate_scenes(2 * n, "mix", 21)
+    torch.manual_seed(5)
+    actor = rollout.ReferenceShapedActor().to(torch.device("cuda", 0))
+    engines = []
+    for overlap in (True, False):
+        env = BatchedParkingEnv(n, scenes=sc, auto_reset=True)
+        eng = rollout.RolloutEngine(env, actor, seed=9, overlap=overlap)
+        eng.collect(5); eng.collect(7)
+        torch.cuda.synchronize()
+        engines.append(eng)
+    a, b = engines
+    sa, sb = a.env.get_state(), b.env.get_state()
+    for k in sa:
+        assert np.array_equal(sa[k], sb[k]), k
+    for k in ("lidar", "target", "action_mask"):
+        assert torch.equal(a.obs[k], b.obs[k]), k
+    assert torch.equal(a.norm.stats, b.norm.stats) and a.norm.n == b.norm.n
+    assert a.env.wait_observed(torch.cuda.current_stream()) is True
+    a.env.close(); b.env.close()
