@@ -250,6 +250,8 @@ class SacRollout(object):
         main = torch.cuda.current_stream(dev)
         if self._pol_stream is None:
             self._pol_stream = torch.cuda.Stream(device=dev)
+            self._upd_stream = torch.cuda.Stream(device=dev)
+            self._weights_ready = torch.cuda.Event()
         pol = self._pol_stream
         a = self._act(self.obs) if self._next_action is None else self._next_action
         for t in range(n_steps):
@@ -270,19 +272,33 @@ class SacRollout(object):
             self.obs = nxt
             self._steps_done += 1
             if update_due:
-                if self.pending_update:
-                    L.apply()            # finishes the previous update: its all-reduce ran under the last rollout steps
-                    if self.actor_kernel is not None:
-                        self.actor_kernel.refresh()
-                L.backward(self.replay.sample(self.batch, self.gen))
+                # The learner has a stream of its own: the batch is gathered here (a private copy of the sampled rows, so the
+                # following pushes cannot tear it), the previous update is finished (its all-reduce ran under the last rollout
+                # steps) and the actor's packed weights are refreshed; the rollout only waits for THAT, while the forward /
+                # backward passes of the new update and their all-reduce run under the next update_every rollout steps.
+                batch = self.replay.sample(self.batch, self.gen)
+                upd = self._upd_stream
+                upd.wait_stream(main)
+                with torch.cuda.stream(upd):
+                    for x in list(batch[0].values()) + list(batch[4].values()) + [batch[1], batch[2], batch[3]]:
+                        x.record_stream(upd)
+                    if self.pending_update:
+                        L.apply()
+                        if self.actor_kernel is not None:
+                            self.actor_kernel.refresh()
+                    self._weights_ready.record(upd)
+                    L.backward(batch)
+                main.wait_event(self._weights_ready)
                 self.pending_update = True
                 self.updates += 1
             if not ahead:
                 a = self._act(self.obs)
         self._next_action = a
         if self.pending_update:
-            L.apply()
-            if self.actor_kernel is not None:
-                self.actor_kernel.refresh()
+            with torch.cuda.stream(self._upd_stream):
+                L.apply()
+                if self.actor_kernel is not None:
+                    self.actor_kernel.refresh()
+            main.wait_stream(self._upd_stream)
             self.pending_update = False
             self._next_action = None   # computed with the weights before this update

@@ -171,16 +171,20 @@ class FusedPolicy(object):
 
     @torch.no_grad()
     def refresh(self):
+        """copy the module's parameters into the kernel's packed buffers, in place (the buffers are allocated once: a forward
+        that is still in flight on another stream never sees freed memory; the caller orders refresh against forwards)"""
         sd = self.module.state_dict()
-        keep = {}
+        keep = self._keep
         for name, key, kpad in self._MATS:
-            w = sd[key].detach().to(self.device, torch.float32)
-            buf = torch.zeros((w.shape[0], kpad), dtype=torch.bfloat16, device=self.device)
-            buf[:, :w.shape[1]] = w.to(torch.bfloat16)
-            keep[name] = buf.contiguous()
+            w = sd[key].detach()
+            if name not in keep:
+                keep[name] = torch.zeros((w.shape[0], kpad), dtype=torch.bfloat16, device=self.device)
+            keep[name][:, :w.shape[1]].copy_(w)
         for name, key in self._VECS:
-            keep[name] = sd[key].detach().to(self.device, torch.float32).contiguous().clone()
-        self._keep = keep  # the struct only holds raw pointers
+            v = sd[key].detach()
+            if name not in keep:
+                keep[name] = torch.zeros(tuple(v.shape), dtype=torch.float32, device=self.device)
+            keep[name].copy_(v)
         W = self.weights
         W.w1_lidar, W.w1_target, W.w1_mask = (keep[k].data_ptr() for k in ("w1_lidar", "w1_target", "w1_mask"))
         for m in range(3):
