@@ -559,7 +559,8 @@ struct hope_ctx {
     // stores).  With one rank per box and a dozen host threads the trade wins; with 8 ranks sharing 32 CPUs the expansion
     // becomes the bottleneck (B200 x8: 9.8 ms per step all packed, 8.0 ms none packed).  So only pack_frac of the sub-ranges
     // travel packed, spread evenly; the others' float64 rows are copied straight into the caller's buffer.  Both kinds of copy
-    // are issued by the stepping thread, outside the replayed graph, so the split can change from step to step.
+    // are issued by the stepping thread, outside the replayed graph, so the split can change from step to step.  Default: all
+    // packed for one rank per box, 3/4 for two, none for more.
     double pack_frac = 1.0;
     bool pk_packed[64] = {};
     double h_nohit[HOPE_N_LIDAR] = {};   // lidar_range - lidar_base[ray], the same float64 subtraction k_observe performs
@@ -1321,7 +1322,7 @@ static int plan_wire(hope_ctx *ctx, const hope_host_out *h_out, unsigned stages)
         nt = nt < 1 ? 1 : (nt > 12 ? 12 : nt);
         if (const char *e = getenv("HOPE_B200_HOST_THREADS")) { int v = atoi(e); if (v >= 1 && v <= 64) nt = v; }
         ctx->host_threads = nt;
-        ctx->pack_frac = ranks == 1 ? 1.0 : (ranks == 2 ? 0.75 : 0.25);  // B200 x8 (32 CPUs): 0.25 -> 7.7 ms per step, 0.5 -> 8.1, 1.0 -> 9.8, none -> 8.2 (profiles/r02_e2e_ranks8.jsonl)
+        ctx->pack_frac = ranks == 1 ? 1.0 : (ranks == 2 ? 0.75 : 0.0);  // measured on B200 boxes with 32 CPUs (profiles/r02_e2e_ranks{2,4,8}.jsonl): 2 ranks 1.0 -> 2.24 ms per step, 0.75 -> 2.08, 0.5 -> 2.27, 0 -> 2.63; 4 ranks 1.0 -> 4.49, 0.5 -> 3.51, 0.25 -> 3.43, 0 -> 3.16; 8 ranks 1.0 -> 9.8, 0.25 -> 7.7, 0 -> 8.2 (7.7 - 8.2 is the spread between runs)
         if (const char *e = getenv("HOPE_B200_HOST_PACK_FRAC")) { const double v = atof(e); if (v >= 0.0 && v <= 1.0) ctx->pack_frac = v; }
         if (const char *e = getenv("HOPE_B200_HOST_SPIN_US")) ctx->host_pool->spin_us = atoi(e);
         ctx->host_pool->start(nt);
