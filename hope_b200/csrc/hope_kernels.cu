@@ -562,6 +562,7 @@ struct hope_ctx {
     // are issued by the stepping thread, outside the replayed graph, so the split can change from step to step.  Default: all
     // packed for one rank per box, 3/4 for two, none for more.
     double pack_frac = 1.0;
+    int ranks_per_box = 1;
     bool pk_packed[64] = {};
     double h_nohit[HOPE_N_LIDAR] = {};   // lidar_range - lidar_base[ray], the same float64 subtraction k_observe performs
     int wire_force_portable = 0;
@@ -1014,6 +1015,10 @@ int hope_create(hope_ctx **out, int device, int n_envs, int pool_size, const hop
     if (const char *e = getenv("HOPE_B200_RENDER_AFTER_RS")) ctx->render_after_rs = atoi(e) != 0;
     if (const char *e = getenv("HOPE_B200_HOST_MASK_EXPAND")) ctx->host_mask_expand = atoi(e) != 0;
     if (const char *e = getenv("HOPE_B200_HOST_LIDAR_PACK")) ctx->host_lidar_pack = atoi(e) != 0;
+    if (const char *e = getenv("LOCAL_WORLD_SIZE")) { int v = atoi(e); if (v >= 1) ctx->ranks_per_box = v; }  // torchrun: ranks sharing this host
+    ctx->pack_frac = ctx->ranks_per_box == 1 ? 1.0 : (ctx->ranks_per_box == 2 ? 0.75 : 0.0);  // measured on B200 boxes with 32 CPUs (profiles/r02_e2e_ranks{2,4,8}.jsonl): 2 ranks 1.0 -> 2.24 ms per step, 0.75 -> 2.08, 0.5 -> 2.27, 0 -> 2.63; 4 ranks 1.0 -> 4.49, 0.5 -> 3.51, 0.25 -> 3.43, 0 -> 3.16; 8 ranks 1.0 -> 9.8, 0.25 -> 7.7, 0 -> 8.2 (7.7 - 8.2 is the spread between runs)
+    if (const char *e = getenv("HOPE_B200_HOST_PACK_FRAC")) { const double v = atof(e); if (v >= 0.0 && v <= 1.0) ctx->pack_frac = v; }
+    if (ctx->pack_frac <= 0.0) ctx->host_lidar_pack = false;   // nothing would travel packed: skip k_pack_lidar and its arrays altogether
     if (const char *e = getenv("HOPE_B200_WIRE_PORTABLE")) ctx->wire_force_portable = atoi(e) != 0;
     if (const char *e = getenv("HOPE_B200_HOST_NOEXPAND")) ctx->host_noexpand = atoi(e) != 0;
     if (const char *e = getenv("HOPE_B200_HOST_TRACE")) ctx->host_trace = atoi(e);
@@ -1316,14 +1321,10 @@ static int plan_wire(hope_ctx *ctx, const hope_host_out *h_out, unsigned stages)
         int cpus = (int)std::thread::hardware_concurrency();
         cpu_set_t set;
         if (sched_getaffinity(0, sizeof(set), &set) == 0) cpus = CPU_COUNT(&set);
-        int ranks = 1;
-        if (const char *e = getenv("LOCAL_WORLD_SIZE")) { int v = atoi(e); if (v >= 1) ranks = v; }
-        int nt = cpus / ranks - 1;
+        int nt = cpus / ctx->ranks_per_box - 1;
         nt = nt < 1 ? 1 : (nt > 12 ? 12 : nt);
         if (const char *e = getenv("HOPE_B200_HOST_THREADS")) { int v = atoi(e); if (v >= 1 && v <= 64) nt = v; }
         ctx->host_threads = nt;
-        ctx->pack_frac = ranks == 1 ? 1.0 : (ranks == 2 ? 0.75 : 0.0);  // measured on B200 boxes with 32 CPUs (profiles/r02_e2e_ranks{2,4,8}.jsonl): 2 ranks 1.0 -> 2.24 ms per step, 0.75 -> 2.08, 0.5 -> 2.27, 0 -> 2.63; 4 ranks 1.0 -> 4.49, 0.5 -> 3.51, 0.25 -> 3.43, 0 -> 3.16; 8 ranks 1.0 -> 9.8, 0.25 -> 7.7, 0 -> 8.2 (7.7 - 8.2 is the spread between runs)
-        if (const char *e = getenv("HOPE_B200_HOST_PACK_FRAC")) { const double v = atof(e); if (v >= 0.0 && v <= 1.0) ctx->pack_frac = v; }
         if (const char *e = getenv("HOPE_B200_HOST_SPIN_US")) ctx->host_pool->spin_us = atoi(e);
         ctx->host_pool->start(nt);
     }
