@@ -517,7 +517,7 @@ struct hope_ctx {
     render::Camera *d_cams = nullptr;
     double *d_plan_rem = nullptr;
     uint8_t *d_plan_u8 = nullptr;  // types[N][5] | big[N] | n[N] | seg[N] | active[N]
-    int sm_count = 148, walk_blocks = 148 * 4, check_blocks = 148 * 4;
+    int sm_count = 148, walk_blocks = 148 * 4, check_blocks = 148 * 4, host_check_blocks = 148 * 4;
     // host-API staging
     double *d_action = nullptr;
     void *d_stage = nullptr, *d_stage_img = nullptr;
@@ -553,7 +553,7 @@ struct hope_ctx {
     cudaEvent_t ev_pack[64] = {};
     // an env range's kept values are packed, copied and expanded in sub-ranges of pk_sub envs (own counter, own copy, own
     // expansion job), so the host work left when the last copy lands is one sub-range, not one range
-    int pk_sub = 8192, pk_total = 0;
+    int pk_sub = 2048, pk_total = 0;
     int pk_lo[64] = {}, pk_hi[64] = {}, pk_first[65] = {};   // sub-range g covers envs [pk_lo, pk_hi); range c owns sub-ranges [pk_first[c], pk_first[c+1])
     // Packing trades PCIe bytes (37 instead of 63 MB of lidar per 65 536-env step) for host work (the rows are rebuilt by CPU
     // stores).  With one rank per box and a dozen host threads the trade wins; with 8 ranks sharing 32 CPUs the expansion
@@ -820,7 +820,9 @@ int launch_range(hope_ctx *ctx, const double *d_action, const hope_out &out_all,
         k_rs_walk<<<ctx->walk_blocks, 128, 0, s>>>(rs, tb, ctx->par);
         prof_mark(ctx, 3, s);
         prof_mark(ctx, 4, s);
-        k_rs_check<<<ctx->check_blocks, CHK_WARPS * 32, 0, s>>>(pool, st, tb, rs, ctx->par);
+        // (host API: one resident block per SM fewer, so that the k_observe ranges and k_pack_lidar, which the copies wait for,
+        // find registers next to the persistent grid; measured 2.11 -> 2.03 ms per host step)
+        k_rs_check<<<ctx->in_host_step ? ctx->host_check_blocks : ctx->check_blocks, CHK_WARPS * 32, 0, s>>>(pool, st, tb, rs, ctx->par);
         prof_mark(ctx, 4, s);
         prof_mark(ctx, 5, s);
         k_rs_select<<<(n + 127) / 128, 128, 0, s>>>(n, tb, rs, out);
@@ -983,7 +985,9 @@ int hope_create(hope_ctx **out, int device, int n_envs, int pool_size, const hop
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_rs_check, CHK_WARPS * 32, 0));
         ctx->check_blocks = ctx->sm_count * (nb > 0 ? nb : 1);
         // tuning experiments: fewer resident Reeds-Shepp blocks per SM leave registers for k_observe's blocks
-        if (const char *e = getenv("HOPE_B200_CHECK_BPS")) { int v = atoi(e); if (v >= 1 && v <= 8) ctx->check_blocks = ctx->sm_count * v; }
+        ctx->host_check_blocks = ctx->sm_count * (nb > 1 ? nb - 1 : 1);
+        if (const char *e = getenv("HOPE_B200_CHECK_BPS")) { int v = atoi(e); if (v >= 1 && v <= 8) ctx->check_blocks = ctx->host_check_blocks = ctx->sm_count * v; }
+        if (const char *e = getenv("HOPE_B200_HOST_CHECK_BPS")) { int v = atoi(e); if (v >= 1 && v <= 8) ctx->host_check_blocks = ctx->sm_count * v; }
         if (const char *e = getenv("HOPE_B200_WALK_BPS")) { int v = atoi(e); if (v >= 1 && v <= 16) ctx->walk_blocks = ctx->sm_count * v; }
     }
     for (auto &ln : ctx->lanes) {
@@ -1485,7 +1489,7 @@ static int enqueue_host_step(hope_ctx *ctx, const double *h_action, const hope_h
         }
         ctx->hm_chunks = C;
         {   // sub-ranges of the kept-value copies: at most 64 over all ranges
-            int sub = 8192;
+            int sub = 2048;  // 32 sub-ranges at 65 536 envs: the host work left behind the last copy is 1/32 of the expansion (B200, a box whose memory bounds the expansion: 8192 -> 2.09 ms per host step, 4096 -> 1.95, 2048 -> 1.88; equal on faster hosts)
             if (const char *e = getenv("HOPE_B200_PACK_SUB")) { int v = atoi(e); if (v >= 128) sub = v / 128 * 128; }
             for (;;) {
                 int total = 0;
