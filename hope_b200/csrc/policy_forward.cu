@@ -12,7 +12,8 @@
 // Weights (bf16, PyTorch's [out][in] layout, K padded to 16) are read straight from L2 into B fragments: each warp loads only
 // the columns it owns, once per CTA.  Attention is folded into the head loop: per head, qkv for that head (N = 96) -> 3 x 3
 // softmax per env -> the head's slice of to_out accumulated in registers, so the 768-wide qkv row never exists.
-// HBM traffic per env: 668 B of float32 inputs in, 8 B out.
+// HBM traffic per env: 668 B of float32 inputs in, 8 B out.  (The library is built with -fmad=false for the float64 env kernels, which
+// must round every product and sum separately; the float32 arithmetic here has no such constraint and fuses explicitly with fmaf.)
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math.h>
@@ -78,25 +79,42 @@ __device__ __forceinline__ void warp_gemm(float (&acc)[MT][NT][4], const __nv_bf
     const __nv_bfloat16 *wr[NT];
 #pragma unroll
     for (int ni = 0; ni < NT; ++ni) wr[ni] = w + (size_t)(wrow(ni) + (lane >> 2)) * ldw;
-    // the weights come from L2: the fragments of K block k + 1 are requested before the tensor-core work of block k
-    uint32_t b[2][NT][2];
+    // the weights come from L2 (300+ cycles): the B fragments run PF K blocks ahead of the tensor-core work in a register ring
+    constexpr int KB = K / 16, PF = KB < 4 ? KB : 4;
+    uint32_t b[PF][NT][2];
 #pragma unroll
-    for (int ni = 0; ni < NT; ++ni) ldb16x8(b[0][ni][0], b[0][ni][1], wr[ni], 0, lane);
+    for (int p = 0; p < PF; ++p)
 #pragma unroll
-    for (int k0 = 0; k0 < K; k0 += 16) {
-        const int cur = (k0 >> 4) & 1;
-        if (k0 + 16 < K) {
+        for (int ni = 0; ni < NT; ++ni) ldb16x8(b[p][ni][0], b[p][ni][1], wr[ni], 16 * p, lane);
 #pragma unroll
-            for (int ni = 0; ni < NT; ++ni) ldb16x8(b[cur ^ 1][ni][0], b[cur ^ 1][ni][1], wr[ni], k0 + 16, lane);
-        }
+    for (int kb = 0; kb < KB; ++kb) {
+        const int k0 = 16 * kb, cur = kb % PF;
         const int arow = row0 + (k0 / E) * a_rows_per_kblock, ak = a_rows_per_kblock ? k0 % E : k0;
         uint32_t af[MT][4];  // all row tiles' A fragments first: their shared-memory latency is paid once per K block, not once per tile
 #pragma unroll
         for (int mi = 0; mi < MT; ++mi) lda16x16(af[mi], a, lda, arow + 16 * mi, ak, lane);
+        uint32_t bc[NT][2];
+#pragma unroll
+        for (int ni = 0; ni < NT; ++ni) { bc[ni][0] = b[cur][ni][0]; bc[ni][1] = b[cur][ni][1]; }
+        if (kb + PF < KB) {  // refill the slot just consumed
+#pragma unroll
+            for (int ni = 0; ni < NT; ++ni) ldb16x8(b[cur][ni][0], b[cur][ni][1], wr[ni], k0 + 16 * PF, lane);
+        }
 #pragma unroll
         for (int mi = 0; mi < MT; ++mi)
 #pragma unroll
-            for (int ni = 0; ni < NT; ++ni) mma16816(acc[mi][ni], af[mi], b[cur][ni][0], b[cur][ni][1]);
+            for (int ni = 0; ni < NT; ++ni) mma16816(acc[mi][ni], af[mi], bc[ni][0], bc[ni][1]);
+    }
+}
+
+// accumulators start at the bias of their columns (column pair ccol, ccol + 1 of tile ni starting at col0 + 8 ni), so the epilogue has no add
+template <int MT, int NT>
+__device__ __forceinline__ void init_bias(float (&acc)[MT][NT][4], const float *__restrict__ bias, int col0, int ccol) {
+#pragma unroll
+    for (int ni = 0; ni < NT; ++ni) {
+        const float b0 = __ldg(bias + col0 + 8 * ni + ccol), b1 = __ldg(bias + col0 + 8 * ni + ccol + 1);
+#pragma unroll
+        for (int mi = 0; mi < MT; ++mi) { acc[mi][ni][0] = b0; acc[mi][ni][1] = b1; acc[mi][ni][2] = b0; acc[mi][ni][3] = b1; }
     }
 }
 
@@ -120,12 +138,12 @@ __device__ __forceinline__ void layer_norm_rows(Smem &sm, const float *__restric
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         const float mean = s * (1.f / E);
         const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
-        float q = dx * dx + dy * dy + dz * dz + dw * dw;
+        float q = fmaf(dw, dw, fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
         const float rstd = rsqrtf(q * (1.f / E) + 1e-5f);
-        __nv_bfloat162 lo = __floats2bfloat162_rn(dx * rstd * gg.x + bb.x, dy * rstd * gg.y + bb.y);
-        __nv_bfloat162 hi = __floats2bfloat162_rn(dz * rstd * gg.z + bb.z, dw * rstd * gg.w + bb.w);
+        __nv_bfloat162 lo = __floats2bfloat162_rn(fmaf(dx * rstd, gg.x, bb.x), fmaf(dy * rstd, gg.y, bb.y));
+        __nv_bfloat162 hi = __floats2bfloat162_rn(fmaf(dz * rstd, gg.z, bb.z), fmaf(dw * rstd, gg.w, bb.w));
         *reinterpret_cast<__nv_bfloat162 *>(&sm.h[r][4 * lane]) = lo;
         *reinterpret_cast<__nv_bfloat162 *>(&sm.h[r][4 * lane + 2]) = hi;
     }
@@ -166,19 +184,17 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
         float acc[2][2][4];
 #pragma unroll
         for (int m = 0; m < 3; ++m) {
-            zero(acc);
+            init_bias(acc, W.b1[m], ncol0, ccol);
             if (m == 0) warp_gemm<2, 2, KL>(acc, &sm.u.in.lidar[0][0], KL + 8, 0, w1_lidar, KL, cols, lane);
             if (m == 1) warp_gemm<2, 2, KT>(acc, &sm.u.in.target[0][0], KT + 8, 0, w1_target, KT, cols, lane);
             if (m == 2) warp_gemm<2, 2, KA>(acc, &sm.u.in.mask[0][0], KA + 8, 0, w1_mask, KA, cols, lane);
-            const float *bias = W.b1[m];
 #pragma unroll
             for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
                 for (int ni = 0; ni < 2; ++ni) {
                     const int c = ncol0 + 8 * ni + ccol, r = m * BM + 16 * mi + crow;
-                    const float b0 = __ldg(bias + c), b1 = __ldg(bias + c + 1);
-                    *reinterpret_cast<__nv_bfloat162 *>(&sm.h[r][c]) = __floats2bfloat162_rn(tanh_fast(acc[mi][ni][0] + b0), tanh_fast(acc[mi][ni][1] + b1));
-                    *reinterpret_cast<__nv_bfloat162 *>(&sm.h[r + 8][c]) = __floats2bfloat162_rn(tanh_fast(acc[mi][ni][2] + b0), tanh_fast(acc[mi][ni][3] + b1));
+                    *reinterpret_cast<__nv_bfloat162 *>(&sm.h[r][c]) = __floats2bfloat162_rn(tanh_fast(acc[mi][ni][0]), tanh_fast(acc[mi][ni][1]));
+                    *reinterpret_cast<__nv_bfloat162 *>(&sm.h[r + 8][c]) = __floats2bfloat162_rn(tanh_fast(acc[mi][ni][2]), tanh_fast(acc[mi][ni][3]));
                 }
         }
     }
@@ -188,17 +204,15 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
         float acc[2][2][4];
 #pragma unroll
         for (int m = 0; m < 3; ++m) {
-            zero(acc);
+            init_bias(acc, W.b2[m], ncol0, ccol);
             warp_gemm<2, 2, E>(acc, &sm.h[0][0], LDX, m * BM, static_cast<bf16p>(W.w2[m]), E, cols, lane);
-            const float *bias = W.b2[m];
 #pragma unroll
             for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
                 for (int ni = 0; ni < 2; ++ni) {
                     const int c = ncol0 + 8 * ni + ccol, r = m * BM + 16 * mi + crow;
-                    const float b0 = __ldg(bias + c), b1 = __ldg(bias + c + 1);
-                    *reinterpret_cast<float2 *>(&sm.x[r][c]) = make_float2(acc[mi][ni][0] + b0, acc[mi][ni][1] + b1);
-                    *reinterpret_cast<float2 *>(&sm.x[r + 8][c]) = make_float2(acc[mi][ni][2] + b0, acc[mi][ni][3] + b1);
+                    *reinterpret_cast<float2 *>(&sm.x[r][c]) = make_float2(acc[mi][ni][0], acc[mi][ni][1]);
+                    *reinterpret_cast<float2 *>(&sm.x[r + 8][c]) = make_float2(acc[mi][ni][2], acc[mi][ni][3]);
                 }
         }
     }
@@ -209,7 +223,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
     __syncthreads();
     {
         float oacc[6][2][4];  // this warp's 16 columns of to_out for all 96 rows, accumulated over the heads
-        zero(oacc);
+        init_bias(oacc, W.b_out, ncol0, ccol);
         // qkv of one head: 96 rows x 96 columns = 6 x 12 tiles; warp w takes row tiles 3 (w / 4) .. + 2 and column tiles 3 (w % 4) .. + 2
         const int qm0 = 3 * (warp >> 2), qn0 = 3 * (warp & 3);
         for (int hd = 0; hd < HEADS; ++hd) {
@@ -251,7 +265,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
                             const uint4 w4 = kp[v];
                             const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-                            for (int c = 0; c < 4; ++c) d += qv[8 * v + 2 * c] * __uint_as_float(ws[c] << 16) + qv[8 * v + 2 * c + 1] * __uint_as_float(ws[c] & 0xffff0000u);
+                            for (int c = 0; c < 4; ++c) d = fmaf(qv[8 * v + 2 * c + 1], __uint_as_float(ws[c] & 0xffff0000u), fmaf(qv[8 * v + 2 * c], __uint_as_float(ws[c] << 16), d));
                         }
                         s[j] = d;
                     }
@@ -273,8 +287,8 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
                         uint32_t o[4];
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
-                            const float lo = w0 * __uint_as_float(as[c] << 16) + w1 * __uint_as_float(bs[c] << 16) + w2 * __uint_as_float(cs[c] << 16);
-                            const float hi = w0 * __uint_as_float(as[c] & 0xffff0000u) + w1 * __uint_as_float(bs[c] & 0xffff0000u) + w2 * __uint_as_float(cs[c] & 0xffff0000u);
+                            const float lo = fmaf(w2, __uint_as_float(cs[c] << 16), fmaf(w1, __uint_as_float(bs[c] << 16), w0 * __uint_as_float(as[c] << 16)));
+                            const float hi = fmaf(w2, __uint_as_float(cs[c] & 0xffff0000u), fmaf(w1, __uint_as_float(bs[c] & 0xffff0000u), w0 * __uint_as_float(as[c] & 0xffff0000u)));
                             const __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
                             o[c] = *reinterpret_cast<const uint32_t *>(&pk);
                         }
@@ -291,10 +305,9 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
 #pragma unroll
             for (int ni = 0; ni < 2; ++ni) {
                 const int c = ncol0 + 8 * ni + ccol, r = 16 * mi + crow;
-                const float b0 = __ldg(W.b_out + c), b1 = __ldg(W.b_out + c + 1);
                 float2 *p = reinterpret_cast<float2 *>(&sm.x[r][c]), *q = reinterpret_cast<float2 *>(&sm.x[r + 8][c]);
-                *p = make_float2(p->x + oacc[mi][ni][0] + b0, p->y + oacc[mi][ni][1] + b1);
-                *q = make_float2(q->x + oacc[mi][ni][2] + b0, q->y + oacc[mi][ni][3] + b1);
+                *p = make_float2(p->x + oacc[mi][ni][0], p->y + oacc[mi][ni][1]);
+                *q = make_float2(q->x + oacc[mi][ni][2], q->y + oacc[mi][ni][3]);
             }
     }
     __syncthreads();
@@ -304,19 +317,18 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
     __syncthreads();
     {
         float acc[6][2][4];
-        zero(acc);
+        init_bias(acc, W.b_ff1, ncol0, ccol);
         warp_gemm<6, 2, E>(acc, &sm.h[0][0], LDX, 0, w_ff1, E, cols, lane);
 #pragma unroll
         for (int mi = 0; mi < 6; ++mi)
 #pragma unroll
             for (int ni = 0; ni < 2; ++ni) {
                 const int c = ncol0 + 8 * ni + ccol, r = 16 * mi + crow;
-                const float b0 = __ldg(W.b_ff1 + c), b1 = __ldg(W.b_ff1 + c + 1);
-                *reinterpret_cast<__nv_bfloat162 *>(&sm.u.ff[r][c]) = __floats2bfloat162_rn(tanh_fast(acc[mi][ni][0] + b0), tanh_fast(acc[mi][ni][1] + b1));
-                *reinterpret_cast<__nv_bfloat162 *>(&sm.u.ff[r + 8][c]) = __floats2bfloat162_rn(tanh_fast(acc[mi][ni][2] + b0), tanh_fast(acc[mi][ni][3] + b1));
+                *reinterpret_cast<__nv_bfloat162 *>(&sm.u.ff[r][c]) = __floats2bfloat162_rn(tanh_fast(acc[mi][ni][0]), tanh_fast(acc[mi][ni][1]));
+                *reinterpret_cast<__nv_bfloat162 *>(&sm.u.ff[r + 8][c]) = __floats2bfloat162_rn(tanh_fast(acc[mi][ni][2]), tanh_fast(acc[mi][ni][3]));
             }
         __syncthreads();
-        zero(acc);
+        init_bias(acc, W.b_ff2, ncol0, ccol);
         warp_gemm<6, 2, E>(acc, &sm.u.ff[0][0], LDX, 0, w_ff2, E, cols, lane);
         // the residual stream's last use is the output head's bf16 operand: write x + ff straight into h
 #pragma unroll
@@ -324,10 +336,9 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
 #pragma unroll
             for (int ni = 0; ni < 2; ++ni) {
                 const int c = ncol0 + 8 * ni + ccol, r = 16 * mi + crow;
-                const float b0 = __ldg(W.b_ff2 + c), b1 = __ldg(W.b_ff2 + c + 1);
                 const float2 p = *reinterpret_cast<const float2 *>(&sm.x[r][c]), q = *reinterpret_cast<const float2 *>(&sm.x[r + 8][c]);
-                *reinterpret_cast<__nv_bfloat162 *>(&sm.h[r][c]) = __floats2bfloat162_rn(p.x + acc[mi][ni][0] + b0, p.y + acc[mi][ni][1] + b1);
-                *reinterpret_cast<__nv_bfloat162 *>(&sm.h[r + 8][c]) = __floats2bfloat162_rn(q.x + acc[mi][ni][2] + b0, q.y + acc[mi][ni][3] + b1);
+                *reinterpret_cast<__nv_bfloat162 *>(&sm.h[r][c]) = __floats2bfloat162_rn(p.x + acc[mi][ni][0], p.y + acc[mi][ni][1]);
+                *reinterpret_cast<__nv_bfloat162 *>(&sm.h[r + 8][c]) = __floats2bfloat162_rn(q.x + acc[mi][ni][2], q.y + acc[mi][ni][3]);
             }
     }
     __syncthreads();  // h complete (all warps also passed their last read of u.ff before this point: u.head may be written now)
@@ -335,16 +346,15 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
     // ---- output head: tanh(W_o2 tanh(W_o1 [x_0 | x_1 | x_2] + b_o1) + b_o2) ---------------------------------------------
     {
         float acc[2][2][4];
-        zero(acc);
+        init_bias(acc, W.b_o1, ncol0, ccol);
         warp_gemm<2, 2, 3 * E>(acc, &sm.h[0][0], LDX, 0, w_o1, 3 * E, cols, lane, BM);  // K block m reads token rows m * BM + env
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
             for (int ni = 0; ni < 2; ++ni) {
                 const int c = ncol0 + 8 * ni + ccol, r = 16 * mi + crow;
-                const float b0 = __ldg(W.b_o1 + c), b1 = __ldg(W.b_o1 + c + 1);
-                *reinterpret_cast<float2 *>(&sm.u.head[r][c]) = make_float2(tanh_fast(acc[mi][ni][0] + b0), tanh_fast(acc[mi][ni][1] + b1));
-                *reinterpret_cast<float2 *>(&sm.u.head[r + 8][c]) = make_float2(tanh_fast(acc[mi][ni][2] + b0), tanh_fast(acc[mi][ni][3] + b1));
+                *reinterpret_cast<float2 *>(&sm.u.head[r][c]) = make_float2(tanh_fast(acc[mi][ni][0]), tanh_fast(acc[mi][ni][1]));
+                *reinterpret_cast<float2 *>(&sm.u.head[r + 8][c]) = make_float2(tanh_fast(acc[mi][ni][2]), tanh_fast(acc[mi][ni][3]));
             }
     }
     __syncthreads();
@@ -353,7 +363,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
         const float *hrow = &sm.u.head[e][32 * part], *wrow = W.w_o2 + o * E + 32 * part;
         float s = 0.f;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) s += hrow[c] * __ldg(wrow + c);
+        for (int c = 0; c < 32; ++c) s = fmaf(hrow[c], __ldg(wrow + c), s);
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
         if (part == 0 && env0 + e < n) out[(size_t)(env0 + e) * 2 + o] = tanhf(s + __ldg(W.b_o2 + o));
