@@ -101,6 +101,7 @@ def load_library(max_obs=16):
         "hope_masked_sample": (C.c_int, [i32, vp, dp, dp, dp, u64, u64, dp, vp, vp, vp]),
         "hope_policy_forward": (C.c_int, [i32, vp, vp, vp, C.POINTER(PolicyWeights), vp, vp]),
         "hope_policy_forward_smem_bytes": (C.c_int, []),
+        "hope_policy_pack_matrix": (C.c_int, [vp, i32, i32, i32, vp]),
         "hope_profile_enable": (C.c_int, [vp, i32]),
         "hope_profile_read": (C.c_int, [vp, C.POINTER(C.c_double * 8), C.POINTER(u64 * 8)]),
     }

@@ -9,8 +9,8 @@
 // Here a CTA of 8 warps owns 32 envs (96 token rows) and carries them through the whole network with every activation in
 // shared memory: bf16 operands, float32 accumulation on the tensor cores (mma.sync m16n8k16; the GEMMs are M = 96 per CTA,
 // far too small for a tcgen05 / TMEM pipeline to pay), float32 residual stream, LayerNorm, softmax and tanh in float32.
-// Weights (bf16, PyTorch's [out][in] layout, K padded to 16) are read straight from L2 into B fragments: each warp loads only
-// the columns it owns, once per CTA.  Attention is folded into the head loop: per head, qkv for that head (N = 96) -> 3 x 3
+// Weights (bf16, fragment-packed by hope_policy_pack_matrix, K padded to 16) are read straight from L2 into B fragments, 256
+// contiguous bytes per warp and fragment: each warp loads only the columns it owns, once per CTA.  Attention is folded into the head loop: per head, qkv for that head (N = 96) -> 3 x 3
 // softmax per env -> the head's slice of to_out accumulated in registers, so the 768-wide qkv row never exists.
 // HBM traffic per env: 668 B of float32 inputs in, 8 B out.  (The library is built with -fmad=false for the float64 env kernels, which
 // must round every product and sum separately; the float32 arithmetic here has no such constraint and fuses explicitly with fmaf.)
@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/hope_b200.h"
 
@@ -52,7 +53,8 @@ __device__ __forceinline__ float tanh_fast(float v) {
 }
 
 __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+    // (not volatile: pure register in / out, so the compiler may interleave it with the fragment loads of the next K block)
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -61,31 +63,37 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
 __device__ __forceinline__ void lda16x16(uint32_t (&a)[4], const __nv_bfloat16 *base, int ld, int row0, int k0, int lane) {
     const __nv_bfloat16 *p = base + (size_t)(row0 + (lane & 15)) * ld + k0 + ((lane >> 4) << 3);
     const uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(addr));
+    // (reads shared memory: ordered against the stores and barriers around it by the memory clobber, free to move among the MMAs)
+    asm("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(addr) : "memory");
 }
 
-// B fragment (k16 x n8) of W^T from the row-major weight W[n][k] in global memory: two adjacent bf16 per register
-__device__ __forceinline__ void ldb16x8(uint32_t &b0, uint32_t &b1, const __nv_bfloat16 *w_row /* W + n * ldw for this lane's n */, int k0, int lane) {
-    const uint32_t *p = reinterpret_cast<const uint32_t *>(w_row + k0 + ((lane & 3) << 1));
-    b0 = __ldg(p);
-    b1 = __ldg(p + 4);
+// B fragments come from a FRAGMENT-PACKED copy of the weight W[n][k] (hope_policy_pack_matrix): for every 8-row tile nt and
+// every 16-wide K block ks, the 32 lanes' register pairs (b0, b1) of the k16 x n8 operand lie side by side,
+//   packed[((nt * KS + ks) * 32 + lane) * 4 + {0,1}] = W[8 nt + lane / 4][16 ks + 2 (lane % 4) + {0,1}]          (b0)
+//   packed[((nt * KS + ks) * 32 + lane) * 4 + {2,3}] = W[8 nt + lane / 4][16 ks + 8 + 2 (lane % 4) + {0,1}]      (b1)
+// so a warp reads one fragment as 256 contiguous bytes (2 L1 wavefronts).  Reading them from the row-major matrix instead
+// (4 bytes per lane from 8 different rows, twice) costs 16 wavefronts per fragment and made the kernel LSU-bound: 85 % of the
+// L1 data-pipe cycles, 62 % of them these loads (ncu, profiles/r02_ncu_full_summary_p.txt).
+__device__ __forceinline__ void ldb16x8(uint32_t &b0, uint32_t &b1, const uint2 *frag /* packed + (nt * KS + ks) * 32 */, int lane) {
+    const uint2 v = __ldg(frag + lane);
+    b0 = v.x; b1 = v.y;
 }
 
 // acc[mi][ni] += A[row0 + 16 mi .. +15][0 .. K) * W[wrow(ni) .. +7][0 .. K)^T for MT row tiles and NT column tiles.
 // a_row_of_k: row offset added per K block of E (the output head reads env e's three tokens as one 384-wide row).
 template <int MT, int NT, int K, typename RowFn>
-__device__ __forceinline__ void warp_gemm(float (&acc)[MT][NT][4], const __nv_bfloat16 *a, int lda, int row0, const __nv_bfloat16 *w, int ldw, RowFn wrow,
+__device__ __forceinline__ void warp_gemm(float (&acc)[MT][NT][4], const __nv_bfloat16 *a, int lda, int row0, const uint2 *w, int ks_total, int kb0, RowFn wrow,
                                           int lane, int a_rows_per_kblock = 0) {
-    const __nv_bfloat16 *wr[NT];
+    const uint2 *wr[NT];  // this warp's column tiles: first fragment of each
 #pragma unroll
-    for (int ni = 0; ni < NT; ++ni) wr[ni] = w + (size_t)(wrow(ni) + (lane >> 2)) * ldw;
+    for (int ni = 0; ni < NT; ++ni) wr[ni] = w + ((size_t)(wrow(ni) >> 3) * ks_total + kb0) * 32;
     // the weights come from L2 (300+ cycles): the B fragments run PF K blocks ahead of the tensor-core work in a register ring
     constexpr int KB = K / 16, PF = KB < 4 ? KB : 4;
     uint32_t b[PF][NT][2];
 #pragma unroll
     for (int p = 0; p < PF; ++p)
 #pragma unroll
-        for (int ni = 0; ni < NT; ++ni) ldb16x8(b[p][ni][0], b[p][ni][1], wr[ni], 16 * p, lane);
+        for (int ni = 0; ni < NT; ++ni) ldb16x8(b[p][ni][0], b[p][ni][1], wr[ni] + 32 * p, lane);
 #pragma unroll
     for (int kb = 0; kb < KB; ++kb) {
         const int k0 = 16 * kb, cur = kb % PF;
@@ -98,7 +106,7 @@ __device__ __forceinline__ void warp_gemm(float (&acc)[MT][NT][4], const __nv_bf
         for (int ni = 0; ni < NT; ++ni) { bc[ni][0] = b[cur][ni][0]; bc[ni][1] = b[cur][ni][1]; }
         if (kb + PF < KB) {  // refill the slot just consumed
 #pragma unroll
-            for (int ni = 0; ni < NT; ++ni) ldb16x8(b[cur][ni][0], b[cur][ni][1], wr[ni], k0 + 16 * PF, lane);
+            for (int ni = 0; ni < NT; ++ni) ldb16x8(b[cur][ni][0], b[cur][ni][1], wr[ni] + 32 * (kb + PF), lane);
         }
 #pragma unroll
         for (int mi = 0; mi < MT; ++mi)
@@ -128,26 +136,42 @@ __device__ __forceinline__ void zero(float (&acc)[MT][NT][4]) {
             for (int q = 0; q < 4; ++q) acc[mi][ni][q] = 0.f;
 }
 
-// LayerNorm (eps 1e-5, affine) of the 96 residual rows -> bf16 operand; one warp per row, 4 columns per lane
+// LayerNorm (eps 1e-5, affine) of the 96 residual rows -> bf16 operand.  8 lanes per row (16 columns each), 4 rows per warp pass:
+// three shuffle steps per reduction instead of five, and four independent rows in flight per warp.
 __device__ __forceinline__ void layer_norm_rows(Smem &sm, const float *__restrict__ g, const float *__restrict__ b, int warp, int lane) {
-    const float4 gg = __ldg(reinterpret_cast<const float4 *>(g) + lane), bb = __ldg(reinterpret_cast<const float4 *>(b) + lane);
-    for (int r = warp; r < ROWS; r += WARPS) {
-        const float4 v = *reinterpret_cast<const float4 *>(&sm.x[r][4 * lane]);
-        float s = v.x + v.y + v.z + v.w;
+    const int sub = lane >> 3, part = lane & 7;  // row within the pass, 16-column slice of the row
+    float4 gg[4], bb[4];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    for (int v = 0; v < 4; ++v) { gg[v] = __ldg(reinterpret_cast<const float4 *>(g) + 4 * part + v); bb[v] = __ldg(reinterpret_cast<const float4 *>(b) + 4 * part + v); }
+#pragma unroll
+    for (int pass = 0; pass < ROWS / (4 * WARPS); ++pass) {
+        const int r = (pass * WARPS + warp) * 4 + sub;
+        float4 x[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) x[v] = *reinterpret_cast<const float4 *>(&sm.x[r][16 * part + 4 * v]);
+        float s = 0.f;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) s += (x[v].x + x[v].y) + (x[v].z + x[v].w);
+        s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
         const float mean = s * (1.f / E);
-        const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
-        float q = fmaf(dw, dw, fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+        float q = 0.f;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        for (int v = 0; v < 4; ++v) {
+            x[v].x -= mean; x[v].y -= mean; x[v].z -= mean; x[v].w -= mean;
+            q = fmaf(x[v].x, x[v].x, q); q = fmaf(x[v].y, x[v].y, q); q = fmaf(x[v].z, x[v].z, q); q = fmaf(x[v].w, x[v].w, q);
+        }
+        q += __shfl_xor_sync(0xffffffffu, q, 1); q += __shfl_xor_sync(0xffffffffu, q, 2); q += __shfl_xor_sync(0xffffffffu, q, 4);
         const float rstd = rsqrtf(q * (1.f / E) + 1e-5f);
-        __nv_bfloat162 lo = __floats2bfloat162_rn(fmaf(dx * rstd, gg.x, bb.x), fmaf(dy * rstd, gg.y, bb.y));
-        __nv_bfloat162 hi = __floats2bfloat162_rn(fmaf(dz * rstd, gg.z, bb.z), fmaf(dw * rstd, gg.w, bb.w));
-        *reinterpret_cast<__nv_bfloat162 *>(&sm.h[r][4 * lane]) = lo;
-        *reinterpret_cast<__nv_bfloat162 *>(&sm.h[r][4 * lane + 2]) = hi;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(fmaf(x[v].x * rstd, gg[v].x, bb[v].x), fmaf(x[v].y * rstd, gg[v].y, bb[v].y));
+            const __nv_bfloat162 hi = __floats2bfloat162_rn(fmaf(x[v].z * rstd, gg[v].z, bb[v].z), fmaf(x[v].w * rstd, gg[v].w, bb[v].w));
+            *reinterpret_cast<__nv_bfloat162 *>(&sm.h[r][16 * part + 4 * v]) = lo;
+            *reinterpret_cast<__nv_bfloat162 *>(&sm.h[r][16 * part + 4 * v + 2]) = hi;
+        }
     }
 }
+static_assert(ROWS % (4 * WARPS) == 0, "layer_norm_rows: whole passes of 4 rows per warp");
 
 __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const float *__restrict__ lidar, const float *__restrict__ target, const float *__restrict__ mask,
                                                                hope_policy_weights W, float *__restrict__ out) {
@@ -155,25 +179,29 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int env0 = blockIdx.x * BM;
-    using bf16p = const __nv_bfloat16 *;
-    bf16p w1_lidar = static_cast<bf16p>(W.w1_lidar), w1_target = static_cast<bf16p>(W.w1_target), w1_mask = static_cast<bf16p>(W.w1_mask);
-    bf16p w_qkv = static_cast<bf16p>(W.w_qkv), w_out = static_cast<bf16p>(W.w_out), w_ff1 = static_cast<bf16p>(W.w_ff1), w_ff2 = static_cast<bf16p>(W.w_ff2),
-          w_o1 = static_cast<bf16p>(W.w_o1);
+    using fragp = const uint2 *;
+    fragp w1_lidar = static_cast<fragp>(W.w1_lidar), w1_target = static_cast<fragp>(W.w1_target), w1_mask = static_cast<fragp>(W.w1_mask);
+    fragp w_qkv = static_cast<fragp>(W.w_qkv), w_out = static_cast<fragp>(W.w_out), w_ff1 = static_cast<fragp>(W.w_ff1), w_ff2 = static_cast<fragp>(W.w_ff2),
+          w_o1 = static_cast<fragp>(W.w_o1);
     const int crow = lane >> 2, ccol = (lane & 3) << 1;  // this lane's place in a 16 x 8 accumulator tile: rows crow, crow + 8; columns ccol, ccol + 1
 
     // ---- inputs -> bf16, zero padded --------------------------------------------------------------------------
-    for (int i = tid; i < BM * KL; i += THREADS) {
-        const int e = i / KL, c = i % KL;
-        const float v = (c < 120 && env0 + e < n) ? lidar[(size_t)(env0 + e) * 120 + c] : 0.f;
-        sm.u.in.lidar[e][c] = __float2bfloat16(v);
+    // (rows of lidar are 480 B, of the mask 168 B: both multiples of 8, so float2 loads stay aligned for every env)
+    for (int i = tid; i < BM * (KL / 2); i += THREADS) {
+        const int e = i / (KL / 2), c = 2 * (i % (KL / 2));
+        float2 v = make_float2(0.f, 0.f);
+        if (c < 120 && env0 + e < n) v = __ldg(reinterpret_cast<const float2 *>(lidar + (size_t)(env0 + e) * 120 + c));
+        *reinterpret_cast<__nv_bfloat162 *>(&sm.u.in.lidar[e][c]) = __floats2bfloat162_rn(v.x, v.y);
     }
     for (int i = tid; i < BM * KT; i += THREADS) {
         const int e = i / KT, c = i % KT;
-        sm.u.in.target[e][c] = __float2bfloat16((c < 5 && env0 + e < n) ? target[(size_t)(env0 + e) * 5 + c] : 0.f);
+        sm.u.in.target[e][c] = __float2bfloat16((c < 5 && env0 + e < n) ? __ldg(target + (size_t)(env0 + e) * 5 + c) : 0.f);
     }
-    for (int i = tid; i < BM * KA; i += THREADS) {
-        const int e = i / KA, c = i % KA;
-        sm.u.in.mask[e][c] = __float2bfloat16((c < 42 && env0 + e < n) ? mask[(size_t)(env0 + e) * 42 + c] : 0.f);
+    for (int i = tid; i < BM * (KA / 2); i += THREADS) {
+        const int e = i / (KA / 2), c = 2 * (i % (KA / 2));
+        float2 v = make_float2(0.f, 0.f);
+        if (c < 42 && env0 + e < n) v = __ldg(reinterpret_cast<const float2 *>(mask + (size_t)(env0 + e) * 42 + c));
+        *reinterpret_cast<__nv_bfloat162 *>(&sm.u.in.mask[e][c]) = __floats2bfloat162_rn(v.x, v.y);
     }
     __syncthreads();
 
@@ -185,9 +213,9 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
 #pragma unroll
         for (int m = 0; m < 3; ++m) {
             init_bias(acc, W.b1[m], ncol0, ccol);
-            if (m == 0) warp_gemm<2, 2, KL>(acc, &sm.u.in.lidar[0][0], KL + 8, 0, w1_lidar, KL, cols, lane);
-            if (m == 1) warp_gemm<2, 2, KT>(acc, &sm.u.in.target[0][0], KT + 8, 0, w1_target, KT, cols, lane);
-            if (m == 2) warp_gemm<2, 2, KA>(acc, &sm.u.in.mask[0][0], KA + 8, 0, w1_mask, KA, cols, lane);
+            if (m == 0) warp_gemm<2, 2, KL>(acc, &sm.u.in.lidar[0][0], KL + 8, 0, w1_lidar, KL / 16, 0, cols, lane);
+            if (m == 1) warp_gemm<2, 2, KT>(acc, &sm.u.in.target[0][0], KT + 8, 0, w1_target, KT / 16, 0, cols, lane);
+            if (m == 2) warp_gemm<2, 2, KA>(acc, &sm.u.in.mask[0][0], KA + 8, 0, w1_mask, KA / 16, 0, cols, lane);
 #pragma unroll
             for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
@@ -205,7 +233,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
 #pragma unroll
         for (int m = 0; m < 3; ++m) {
             init_bias(acc, W.b2[m], ncol0, ccol);
-            warp_gemm<2, 2, E>(acc, &sm.h[0][0], LDX, m * BM, static_cast<bf16p>(W.w2[m]), E, cols, lane);
+            warp_gemm<2, 2, E>(acc, &sm.h[0][0], LDX, m * BM, static_cast<fragp>(W.w2[m]), E / 16, 0, cols, lane);
 #pragma unroll
             for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
@@ -230,7 +258,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
             float qacc[3][3][4];
             zero(qacc);
             auto qrow = [&](int ni) { const int t = qn0 + ni; return (t >> 2) * (HEADS * DH) + hd * DH + (t & 3) * 8; };  // q | k | v blocks of to_qkv, head hd
-            warp_gemm<3, 3, E>(qacc, &sm.h[0][0], LDX, 16 * qm0, w_qkv, E, qrow, lane);
+            warp_gemm<3, 3, E>(qacc, &sm.h[0][0], LDX, 16 * qm0, w_qkv, E / 16, 0, qrow, lane);
 #pragma unroll
             for (int mi = 0; mi < 3; ++mi)
 #pragma unroll
@@ -259,15 +287,15 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
 #pragma unroll
                     for (int j = 0; j < 3; ++j) {
                         const uint4 *kp = reinterpret_cast<const uint4 *>(&sm.u.hd.qkv[j * BM + e][DH + 16 * half]);
-                        float d = 0.f;
+                        float d[4] = {0.f, 0.f, 0.f, 0.f};  // four independent chains
 #pragma unroll
                         for (int v = 0; v < 2; ++v) {
                             const uint4 w4 = kp[v];
                             const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-                            for (int c = 0; c < 4; ++c) d = fmaf(qv[8 * v + 2 * c + 1], __uint_as_float(ws[c] & 0xffff0000u), fmaf(qv[8 * v + 2 * c], __uint_as_float(ws[c] << 16), d));
+                            for (int c = 0; c < 4; ++c) d[c] = fmaf(qv[8 * v + 2 * c + 1], __uint_as_float(ws[c] & 0xffff0000u), fmaf(qv[8 * v + 2 * c], __uint_as_float(ws[c] << 16), d[c]));
                         }
-                        s[j] = d;
+                        s[j] = (d[0] + d[1]) + (d[2] + d[3]);
                     }
                 }
 #pragma unroll
@@ -298,7 +326,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
             }
             __syncthreads();
             // the head's slice of to_out: oacc += att (96 x 32) * w_out[:, 32 hd .. 32 hd + 31]^T
-            warp_gemm<6, 2, DH>(oacc, &sm.u.hd.att[0][0], LDA, 0, w_out + hd * DH, HEADS * DH, cols, lane);
+            warp_gemm<6, 2, DH>(oacc, &sm.u.hd.att[0][0], LDA, 0, w_out, HEADS * DH / 16, hd * (DH / 16), cols, lane);
         }
 #pragma unroll
         for (int mi = 0; mi < 6; ++mi)
@@ -318,7 +346,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
     {
         float acc[6][2][4];
         init_bias(acc, W.b_ff1, ncol0, ccol);
-        warp_gemm<6, 2, E>(acc, &sm.h[0][0], LDX, 0, w_ff1, E, cols, lane);
+        warp_gemm<6, 2, E>(acc, &sm.h[0][0], LDX, 0, w_ff1, E / 16, 0, cols, lane);
 #pragma unroll
         for (int mi = 0; mi < 6; ++mi)
 #pragma unroll
@@ -329,7 +357,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
             }
         __syncthreads();
         init_bias(acc, W.b_ff2, ncol0, ccol);
-        warp_gemm<6, 2, E>(acc, &sm.u.ff[0][0], LDX, 0, w_ff2, E, cols, lane);
+        warp_gemm<6, 2, E>(acc, &sm.u.ff[0][0], LDX, 0, w_ff2, E / 16, 0, cols, lane);
         // the residual stream's last use is the output head's bf16 operand: write x + ff straight into h
 #pragma unroll
         for (int mi = 0; mi < 6; ++mi)
@@ -347,7 +375,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
     {
         float acc[2][2][4];
         init_bias(acc, W.b_o1, ncol0, ccol);
-        warp_gemm<2, 2, 3 * E>(acc, &sm.h[0][0], LDX, 0, w_o1, 3 * E, cols, lane, BM);  // K block m reads token rows m * BM + env
+        warp_gemm<2, 2, 3 * E>(acc, &sm.h[0][0], LDX, 0, w_o1, 3 * E / 16, 0, cols, lane, BM);  // K block m reads token rows m * BM + env
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
@@ -384,5 +412,27 @@ int hope_policy_forward(int n, const float *d_lidar, const float *d_target, cons
 }
 
 int hope_policy_forward_smem_bytes(void) { return (int)sizeof(hope_policy::Smem); }
+
+int hope_policy_pack_matrix(const float *h_w, int n_out, int n_in, int k_pad, void *h_packed) {
+    if (!h_w || !h_packed || n_out <= 0 || n_in <= 0 || n_out % 8 || k_pad % 16 || k_pad < n_in) return HOPE_ERR_INVALID;
+    uint16_t *out = static_cast<uint16_t *>(h_packed);
+    const int ks_total = k_pad / 16;
+    auto bf16 = [](float f) {  // round to nearest even, like torch's .to(bfloat16)
+        uint32_t u;
+        memcpy(&u, &f, 4);
+        if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40u);  // NaN stays NaN
+        u += 0x7fffu + ((u >> 16) & 1u);
+        return (uint16_t)(u >> 16);
+    };
+    for (int nt = 0; nt < n_out / 8; ++nt)
+        for (int ks = 0; ks < ks_total; ++ks)
+            for (int lane = 0; lane < 32; ++lane)
+                for (int half = 0; half < 2; ++half)
+                    for (int e = 0; e < 2; ++e) {
+                        const int row = 8 * nt + lane / 4, col = 16 * ks + 8 * half + 2 * (lane % 4) + e;
+                        out[(((size_t)nt * ks_total + ks) * 32 + lane) * 4 + 2 * half + e] = col < n_in ? bf16(h_w[(size_t)row * n_in + col]) : (uint16_t)0;
+                    }
+    return HOPE_OK;
+}
 
 }  // extern "C"

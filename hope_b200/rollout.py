@@ -133,7 +133,8 @@ class FusedPolicy(object):
     """The 3-modal actor (MultiObsEmbedding(ACTOR_CONFIGS) / ReferenceShapedActor: lidar, target, action mask) as one kernel,
     hope_policy_forward (csrc/policy_forward.cu): 32 envs per CTA carried through the embeddings, the transformer block and the
     output head with every activation in shared memory, bf16 tensor-core GEMMs with float32 accumulation.  The parameters are
-    read from the module's state_dict by the reference's names and packed once (`refresh()` after an optimiser step)."""
+    read from the module's state_dict by the reference's names and packed once (`refresh()` after an optimiser step): bf16, input
+    width padded to 16, in the kernel's fragment order (include/hope_b200.h, hope_policy_pack_matrix)."""
 
     _MATS = (("w1_lidar", "embed_lidar.0.weight", 128), ("w1_target", "embed_tgt.0.weight", 16), ("w1_mask", "embed_am.0.weight", 48),
              ("w2_0", "embed_lidar.2.weight", 128), ("w2_1", "embed_tgt.2.weight", 128), ("w2_2", "embed_am.2.weight", 128),
@@ -179,7 +180,12 @@ class FusedPolicy(object):
             w = sd[key].detach()
             if name not in keep:
                 keep[name] = torch.zeros((w.shape[0], kpad), dtype=torch.bfloat16, device=self.device)
-            keep[name][:, :w.shape[1]].copy_(w)
+                keep["_pad_" + name] = torch.zeros((w.shape[0], kpad), dtype=torch.bfloat16, device=self.device)
+            pad = keep["_pad_" + name]
+            pad[:, :w.shape[1]].copy_(w)          # float32 -> bf16 (round to nearest even), zero-padded input width
+            # fragment packing (hope_policy_pack_matrix on the device): [nt][8 rows][ks][half][4 lane%4][2] -> [nt][ks][row][lane%4][half][2]
+            n_out = w.shape[0]
+            keep[name].view(n_out // 8, kpad // 16, 8, 4, 2, 2).copy_(pad.view(n_out // 8, 8, kpad // 16, 2, 4, 2).permute(0, 2, 1, 4, 3, 5))
         for name, key in self._VECS:
             v = sd[key].detach()
             if name not in keep:

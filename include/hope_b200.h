@@ -240,15 +240,17 @@ int hope_masked_sample(int n, const float *d_mean, const double *d_log_std, cons
 /* The actor network between them, as one kernel (row f2 / BASELINE cfg 4): MultiObsEmbedding(ACTOR_CONFIGS) with lidar, target
  * and action-mask inputs (model/network.py:34-196, model/attention.py:16-92, configs.py:134-153) — three 2-layer tanh embeddings,
  * one pre-norm transformer block over the 3 tokens (8 heads x 32, feed-forward 128), Linear(384,128) tanh Linear(128,2) tanh.
- * Weights: bf16 matrices in PyTorch's [out][in] layout with the input width zero-padded to a multiple of 16 (120 -> 128, 5 -> 16,
- * 42 -> 48), float32 biases / LayerNorm parameters / last layer; all DEVICE pointers.  d_lidar [n][120], d_target [n][5],
- * d_mask [n][42] float32 (hope_state_norm's outputs), d_out [n][2] float32 in [-1, 1].  bf16 operands, float32 accumulation. */
+ * Weights: every matrix is a bf16 FRAGMENT-PACKED copy of PyTorch's [out][in] weight with the input width zero-padded to a multiple
+ * of 16 (120 -> 128, 5 -> 16, 42 -> 48), as hope_policy_pack_matrix produces it (the tensor-core B operand of every 8-row x 16-column
+ * tile stored as 256 contiguous bytes, tiles ordered [out / 8][k_pad / 16]: one coalesced load per warp and fragment); biases,
+ * LayerNorm parameters and the last layer are float32; all DEVICE pointers.  d_lidar [n][120], d_target [n][5], d_mask [n][42]
+ * float32 (hope_state_norm's outputs), d_out [n][2] float32 in [-1, 1].  bf16 operands, float32 accumulation. */
 typedef struct hope_policy_weights {
-    const void *w1_lidar, *w1_target, *w1_mask; /* bf16 [128][128], [128][16], [128][48]: embed_*.0.weight, input width padded   */
-    const void *w2[3];                          /* bf16 [128][128]: embed_lidar.2 / embed_tgt.2 / embed_am.2 .weight             */
-    const void *w_qkv, *w_out;                  /* bf16 [768][128] attn.fn.to_qkv.weight, [128][256] attn.fn.to_out.0.weight    */
-    const void *w_ff1, *w_ff2;                  /* bf16 [128][128]: ff.fn.net.0 / ff.fn.net.3 .weight                            */
-    const void *w_o1;                           /* bf16 [128][384]: net.output.0.weight                                          */
+    const void *w1_lidar, *w1_target, *w1_mask; /* packed [128][128], [128][16], [128][48]: embed_*.0.weight, input width padded */
+    const void *w2[3];                          /* packed [128][128]: embed_lidar.2 / embed_tgt.2 / embed_am.2 .weight           */
+    const void *w_qkv, *w_out;                  /* packed [768][128] attn.fn.to_qkv.weight, [128][256] attn.fn.to_out.0.weight  */
+    const void *w_ff1, *w_ff2;                  /* packed [128][128]: ff.fn.net.0 / ff.fn.net.3 .weight                          */
+    const void *w_o1;                           /* packed [128][384]: net.output.0.weight                                        */
     const float *b1[3], *b2[3];                 /* [128] each, order lidar, target, mask                                         */
     const float *ln1_g, *ln1_b, *b_out, *ln2_g, *ln2_b, *b_ff1, *b_ff2, *b_o1; /* [128] each                                     */
     const float *w_o2, *b_o2;                   /* [2][128], [2]: net.output.2                                                   */
@@ -256,6 +258,10 @@ typedef struct hope_policy_weights {
 int hope_policy_forward(int n, const float *d_lidar, const float *d_target, const float *d_mask, const hope_policy_weights *w, float *d_out,
                         void *stream);
 int hope_policy_forward_smem_bytes(void);
+/* HOST helper: float32 weight h_w[n_out][n_in] (PyTorch layout) -> the fragment-packed bf16 matrix hope_policy_forward reads,
+ * n_out * k_pad bf16 values (n_out multiple of 8, k_pad >= n_in multiple of 16), round to nearest even:
+ *   packed[((nt * (k_pad/16) + ks) * 32 + lane) * 4 + 2 * half + e] = W[8 nt + lane / 4][16 ks + 8 half + 2 (lane % 4) + e]. */
+int hope_policy_pack_matrix(const float *h_w, int n_out, int n_in, int k_pad, void *h_packed);
 
 /* State access (device -> host copies; synchronous). */
 int hope_get_state(hope_ctx *ctx, double *h_pose, int32_t *h_t, double *h_accum, int32_t *h_scene_id);

@@ -190,3 +190,26 @@ def test_host_lidar_expansion_rebuilds_the_rows_bit_for_bit():
             assert np.array_equal(out[:m].view(np.int64), lidar[:m].view(np.int64)), portable
             assert np.isnan(out[m:]).all()
     assert lib.hope_expand_lidar(None, off.ctypes.data, packed.ctypes.data, nohit.ctypes.data, out.ctypes.data, 1, 0) == -1
+
+
+def test_policy_weight_packing_follows_its_definition():
+    """hope_policy_pack_matrix (host): float32 [out][in] -> bf16 (round to nearest even), input width zero-padded, stored in the
+    order the tensor-core B fragments are read: packed[((nt * KS + ks) * 32 + lane) * 4 + 2 * half + e] =
+    W[8 nt + lane / 4][16 ks + 8 half + 2 (lane % 4) + e]."""
+    import torch
+    from hope_b200 import capi
+    lib = capi.load_library()
+    rng = np.random.default_rng(2)
+    for n_out, n_in, k_pad in ((128, 120, 128), (128, 5, 16), (768, 128, 128), (8, 42, 48)):
+        w = rng.standard_normal((n_out, n_in)).astype(np.float32)
+        w[0, 0] = 1.00390625          # exactly half way between two bf16 values: ties to even
+        out = np.zeros(n_out * k_pad, dtype=np.uint16)
+        capi.check(lib.hope_policy_pack_matrix(w.ctypes.data, n_out, n_in, k_pad, out.ctypes.data))
+        ref = torch.zeros((n_out, k_pad), dtype=torch.bfloat16)
+        ref[:, :n_in] = torch.from_numpy(w).to(torch.bfloat16)
+        ref16 = ref.view(torch.int16).numpy().view(np.uint16)
+        ks_total = k_pad // 16
+        nt, ks, lane, half, e = np.meshgrid(np.arange(n_out // 8), np.arange(ks_total), np.arange(32), np.arange(2), np.arange(2), indexing="ij")
+        want = ref16[8 * nt + lane // 4, 16 * ks + 8 * half + 2 * (lane % 4) + e].reshape(-1)
+        assert np.array_equal(out, want), (n_out, n_in, k_pad)
+    assert lib.hope_policy_pack_matrix(w.ctypes.data, 12, 5, 16, out.ctypes.data) == -1   # rows not a multiple of 8
