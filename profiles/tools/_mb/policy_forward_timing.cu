@@ -20,9 +20,11 @@
 #include <stdint.h>
 #include <string.h>
 
-#include "../../include/hope_b200.h"
+#include "../../../include/hope_b200.h"
 
 namespace hope_policy {
+__device__ long long g_pol_t[32];
+#define PT(i) do { if (blockIdx.x == 777 && threadIdx.x == 0) g_pol_t[i] = clock64(); } while (0)
 
 constexpr int BM = 32;                 // envs per CTA
 constexpr int ROWS = 3 * BM;           // token rows per CTA, row = modality * BM + env
@@ -33,7 +35,7 @@ constexpr int KL = 128, KT = 16, KA = 48;             // padded input widths (12
 constexpr int LDX = E + 8;             // bf16 row stride of a 128-wide operand (272 B: ldmatrix rows fall on different banks)
 constexpr int LDQ = 3 * DH + 8;        // qkv of one head
 constexpr int LDA = DH + 8;            // attention output of one head
-constexpr int LDR = E + 8;             // float32 residual stream (row stride = 8 banks mod 32: the float2 epilogue stores of 4 rows per phase do not collide)
+constexpr int LDR = E + 4;             // float32 residual stream
 
 struct Smem {
     float x[ROWS][LDR];                        // residual stream
@@ -42,7 +44,7 @@ struct Smem {
         struct { __nv_bfloat16 lidar[BM][KL + 8], target[BM][KT + 8], mask[BM][KA + 8]; } in;
         struct { __nv_bfloat16 qkv[ROWS][LDQ], att[ROWS][LDA]; } hd;
         __nv_bfloat16 ff[ROWS][LDX];           // feed-forward hidden
-        float head[BM][E + 8];                 // hidden of the output head
+        float head[BM][E + 4];                 // hidden of the output head
     } u;
 };
 
@@ -139,17 +141,16 @@ __device__ __forceinline__ void zero(float (&acc)[MT][NT][4]) {
 // LayerNorm (eps 1e-5, affine) of the 96 residual rows -> bf16 operand.  8 lanes per row (16 columns each), 4 rows per warp pass:
 // three shuffle steps per reduction instead of five, and four independent rows in flight per warp.
 __device__ __forceinline__ void layer_norm_rows(Smem &sm, const float *__restrict__ g, const float *__restrict__ b, int warp, int lane) {
-    const int sub = lane >> 3, part = lane & 7;  // row within the pass; the lane's columns are 32 v + 4 part .. + 3, v = 0..3, so that the
-                                                 // 8 lanes of a row read 128 contiguous bytes per load (no bank conflicts)
+    const int sub = lane >> 3, part = lane & 7;  // row within the pass, 16-column slice of the row
     float4 gg[4], bb[4];
 #pragma unroll
-    for (int v = 0; v < 4; ++v) { gg[v] = __ldg(reinterpret_cast<const float4 *>(g) + 8 * v + part); bb[v] = __ldg(reinterpret_cast<const float4 *>(b) + 8 * v + part); }
+    for (int v = 0; v < 4; ++v) { gg[v] = __ldg(reinterpret_cast<const float4 *>(g) + 4 * part + v); bb[v] = __ldg(reinterpret_cast<const float4 *>(b) + 4 * part + v); }
 #pragma unroll
     for (int pass = 0; pass < ROWS / (4 * WARPS); ++pass) {
         const int r = (pass * WARPS + warp) * 4 + sub;
         float4 x[4];
 #pragma unroll
-        for (int v = 0; v < 4; ++v) x[v] = *reinterpret_cast<const float4 *>(&sm.x[r][32 * v + 4 * part]);
+        for (int v = 0; v < 4; ++v) x[v] = *reinterpret_cast<const float4 *>(&sm.x[r][16 * part + 4 * v]);
         float s = 0.f;
 #pragma unroll
         for (int v = 0; v < 4; ++v) s += (x[v].x + x[v].y) + (x[v].z + x[v].w);
@@ -167,7 +168,8 @@ __device__ __forceinline__ void layer_norm_rows(Smem &sm, const float *__restric
         for (int v = 0; v < 4; ++v) {
             const __nv_bfloat162 lo = __floats2bfloat162_rn(fmaf(x[v].x * rstd, gg[v].x, bb[v].x), fmaf(x[v].y * rstd, gg[v].y, bb[v].y));
             const __nv_bfloat162 hi = __floats2bfloat162_rn(fmaf(x[v].z * rstd, gg[v].z, bb[v].z), fmaf(x[v].w * rstd, gg[v].w, bb[v].w));
-            *reinterpret_cast<uint2 *>(&sm.h[r][32 * v + 4 * part]) = make_uint2(*reinterpret_cast<const uint32_t *>(&lo), *reinterpret_cast<const uint32_t *>(&hi));
+            *reinterpret_cast<__nv_bfloat162 *>(&sm.h[r][16 * part + 4 * v]) = lo;
+            *reinterpret_cast<__nv_bfloat162 *>(&sm.h[r][16 * part + 4 * v + 2]) = hi;
         }
     }
 }
@@ -186,6 +188,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
     const int crow = lane >> 2, ccol = (lane & 3) << 1;  // this lane's place in a 16 x 8 accumulator tile: rows crow, crow + 8; columns ccol, ccol + 1
 
     // ---- inputs -> bf16, zero padded --------------------------------------------------------------------------
+    PT(0);
     // (rows of lidar are 480 B, of the mask 168 B: both multiples of 8, so float2 loads stay aligned for every env)
     for (int i = tid; i < BM * (KL / 2); i += THREADS) {
         const int e = i / (KL / 2), c = 2 * (i % (KL / 2));
@@ -205,6 +208,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
     }
     __syncthreads();
 
+    PT(1);
     // ---- embeddings, layer 1: h[m * BM + e] = tanh(in_m W1_m^T + b1_m).  Warp w owns columns 16 w .. 16 w + 15 of every modality ----
     const int ncol0 = 16 * warp;
     auto cols = [&](int ni) { return ncol0 + 8 * ni; };
@@ -227,6 +231,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
         }
     }
     __syncthreads();
+    PT(2);
     // ---- embeddings, layer 2: x = h W2_m^T + b2_m (float32 residual stream) --------------------------------------
     {
         float acc[2][2][4];
@@ -246,10 +251,12 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
     }
     __syncthreads();
 
+    PT(3);
     // ---- attention block: x += to_out(softmax(q k^T / sqrt(32)) v) over the 3 tokens of each env, pre-norm -----------
     layer_norm_rows(sm, W.ln1_g, W.ln1_b, warp, lane);
     __syncthreads();
     {
+        PT(4);
         float oacc[6][2][4];  // this warp's 16 columns of to_out for all 96 rows, accumulated over the heads
         init_bias(oacc, W.b_out, ncol0, ccol);
         // qkv of one head: 96 rows x 96 columns = 6 x 12 tiles; warp w takes row tiles 3 (w / 4) .. + 2 and column tiles 3 (w % 4) .. + 2
@@ -258,7 +265,9 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
             float qacc[3][3][4];
             zero(qacc);
             auto qrow = [&](int ni) { const int t = qn0 + ni; return (t >> 2) * (HEADS * DH) + hd * DH + (t & 3) * 8; };  // q | k | v blocks of to_qkv, head hd
+            if (hd == 3) PT(10);
             warp_gemm<3, 3, E>(qacc, &sm.h[0][0], LDX, 16 * qm0, w_qkv, E / 16, 0, qrow, lane);
+            if (hd == 3) PT(11);
 #pragma unroll
             for (int mi = 0; mi < 3; ++mi)
 #pragma unroll
@@ -268,12 +277,11 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
                     *reinterpret_cast<__nv_bfloat162 *>(&sm.u.hd.qkv[r + 8][c]) = __floats2bfloat162_rn(qacc[mi][ni][2], qacc[mi][ni][3]);
                 }
             __syncthreads();
-            // softmax over the env's 3 tokens: two threads per query row, each owns 16 of the head's 32 dims (its half of every q . k,
-            // summed with one shuffle, and its half of the output)
+            if (hd == 3) PT(12);
+            // softmax over the env's 3 tokens: two adjacent threads per query row, each owns 16 of the head's 32 dims (its half of
+            // every q . k, summed with one shuffle, and its half of the output)
             {
-                // lanes L and L + 16 of a warp share query row 16 warp + L % 16 (first / second half of the head's dims): the 8 lanes
-                // of a 128-bit shared-memory phase then sit in 8 different rows (row strides of 13 and 5 chunks of 16 B: no conflicts)
-                const int r = (tid >> 5) * 16 + (lane & 15), half = lane >> 4, e = r % BM;
+                const int r = tid >> 1, half = tid & 1, e = r % BM;
                 const bool on = r < ROWS;
                 float qv[16];
                 float s[3] = {0.f, 0.f, 0.f};
@@ -301,7 +309,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < 3; ++j) s[j] = (s[j] + __shfl_xor_sync(0xffffffffu, s[j], 16)) * 0.17677669529663687f;  // dim_head ** -0.5
+                for (int j = 0; j < 3; ++j) s[j] = (s[j] + __shfl_xor_sync(0xffffffffu, s[j], 1)) * 0.17677669529663687f;  // dim_head ** -0.5
                 if (on) {
                     const float mx = fmaxf(s[0], fmaxf(s[1], s[2]));
                     const float p0 = __expf(s[0] - mx), p1 = __expf(s[1] - mx), p2 = __expf(s[2] - mx), inv = 1.f / (p0 + p1 + p2);
@@ -327,8 +335,10 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
                 }
             }
             __syncthreads();
+            if (hd == 3) PT(13);
             // the head's slice of to_out: oacc += att (96 x 32) * w_out[:, 32 hd .. 32 hd + 31]^T
             warp_gemm<6, 2, DH>(oacc, &sm.u.hd.att[0][0], LDA, 0, w_out, HEADS * DH / 16, hd * (DH / 16), cols, lane);
+            if (hd == 3) PT(14);
         }
 #pragma unroll
         for (int mi = 0; mi < 6; ++mi)
@@ -342,6 +352,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
     }
     __syncthreads();
 
+    PT(5);
     // ---- feed-forward block: x += W2 tanh(W1 LN(x) + b1) + b2 ---------------------------------------------------------
     layer_norm_rows(sm, W.ln2_g, W.ln2_b, warp, lane);
     __syncthreads();
@@ -373,6 +384,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
     }
     __syncthreads();  // h complete (all warps also passed their last read of u.ff before this point: u.head may be written now)
 
+    PT(6);
     // ---- output head: tanh(W_o2 tanh(W_o1 [x_0 | x_1 | x_2] + b_o1) + b_o2) ---------------------------------------------
     {
         float acc[2][2][4];
@@ -388,6 +400,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
             }
     }
     __syncthreads();
+    PT(7);
     {   // Linear(128, 2): 4 lanes per (env, output), 32 products each
         const int pair = tid >> 2, part = tid & 3, e = pair >> 1, o = pair & 1;  // 64 pairs x 4 lanes = 256 threads
         const float *hrow = &sm.u.head[e][32 * part], *wrow = W.w_o2 + o * E + 32 * part;
@@ -398,6 +411,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
         s += __shfl_xor_sync(0xffffffffu, s, 2);
         if (part == 0 && env0 + e < n) out[(size_t)(env0 + e) * 2 + o] = tanhf(s + __ldg(W.b_o2 + o));
     }
+    PT(8);
 }
 
 }  // namespace hope_policy
@@ -414,6 +428,7 @@ int hope_policy_forward(int n, const float *d_lidar, const float *d_target, cons
 }
 
 int hope_policy_forward_smem_bytes(void) { return (int)sizeof(hope_policy::Smem); }
+int hope_policy_debug_times(long long *h) { return cudaMemcpyFromSymbol(h, hope_policy::g_pol_t, sizeof(long long) * 32) == cudaSuccess ? 0 : -2; }
 
 int hope_policy_pack_matrix(const float *h_w, int n_out, int n_in, int k_pad, void *h_packed) {
     if (!h_w || !h_packed || n_out <= 0 || n_in <= 0 || n_out % 8 || k_pad % 16 || k_pad < n_in) return HOPE_ERR_INVALID;
