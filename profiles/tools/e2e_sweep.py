@@ -36,10 +36,12 @@ def child(envs, steps, warmup):
         env.step_host(act[k])
         per.append(time.perf_counter() - t1)
     dt = time.perf_counter() - t0
+    in_order = [round(1e3 * x, 3) for x in per[:12]]
     per.sort()
     w = env.host_wire_info()
+    first = [round(1e3 * x, 3) for x in per[:0]]
     print(json.dumps({"ms_per_step": 1e3 * dt / steps, "ms_median": 1e3 * per[len(per) // 2], "ms_p10": 1e3 * per[len(per) // 10],
-                      "env_steps_per_s_nominal": envs * steps / dt, "wire": w, "d2h_gbs": w["d2h_bytes"] * steps / dt / 1e9}))
+                      "first_steps_ms": in_order, "env_steps_per_s_nominal": envs * steps / dt, "wire": w, "d2h_gbs": w["d2h_bytes"] * steps / dt / 1e9}))
     env.close()
 
 
