@@ -104,25 +104,23 @@ class DeviceReplay(object):
 
 class FlatGradAllReduce(object):
     """All gradients of several modules as ONE contiguous bucket -> one all-reduce per update (the message
-    is a few MB, latency-bound on NVLink).  `launch` is asynchronous; `wait` averages and
-    scatters the result back into the .grad tensors."""
+    is a few MB, latency-bound on NVLink).  The parameters' .grad tensors ARE views into the bucket (assigned once,
+    kept by zero_grad(set_to_none=False)), so there is nothing to gather or scatter: `launch` is the asynchronous all-reduce,
+    `wait` averages in place."""
 
     def __init__(self, modules, world, extra_params=()):
         self.params = [p for m in modules for p in m.parameters() if p.requires_grad] + [p for p in extra_params if p.requires_grad]
         self.world = world
         self.numel = sum(p.numel() for p in self.params)
         self.bucket = torch.zeros(self.numel, dtype=torch.float32, device=self.params[0].device)
-        self.handle = None
-
-    def launch(self):
         off = 0
         for p in self.params:
             n = p.numel()
-            if p.grad is None:
-                self.bucket[off:off + n].zero_()
-            else:
-                self.bucket[off:off + n].copy_(p.grad.reshape(-1))
+            p.grad = self.bucket[off:off + n].view_as(p)
             off += n
+        self.handle = None
+
+    def launch(self):
         if self.world > 1:
             self.handle = dist.all_reduce(self.bucket, op=dist.ReduceOp.SUM, async_op=True)
 
@@ -132,12 +130,6 @@ class FlatGradAllReduce(object):
             self.handle = None
         if self.world > 1:
             self.bucket.div_(self.world)
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            if p.grad is not None:
-                p.grad.copy_(self.bucket[off:off + n].view_as(p.grad))
-            off += n
 
 
 class SacLite(object):
@@ -149,9 +141,11 @@ class SacLite(object):
         self.q1_t.load_state_dict(self.q1.state_dict()); self.q2_t.load_state_dict(self.q2.state_dict())
         self.log_alpha = torch.zeros((), device=device, requires_grad=True)
         self.gamma, self.tau, self.target_entropy = gamma, tau, -2.0
-        self.opt_actor = torch.optim.Adam(list(self.actor.parameters()), lr=lr)
-        self.opt_q = torch.optim.Adam(list(self.q1.parameters()) + list(self.q2.parameters()), lr=lr)
-        self.opt_alpha = torch.optim.Adam([self.log_alpha], lr=lr)
+        self.use_graph, self._graph, self._static, self.graph_error = True, None, None, None
+        fused = torch.device(device).type == "cuda"   # one kernel per optimiser step instead of one per parameter group of tensors
+        self.opt_actor = torch.optim.Adam(list(self.actor.parameters()), lr=lr, fused=fused)
+        self.opt_q = torch.optim.Adam(list(self.q1.parameters()) + list(self.q2.parameters()), lr=lr, fused=fused)
+        self.opt_alpha = torch.optim.Adam([self.log_alpha], lr=lr, fused=fused)
         # the temperature is a replicated parameter too: its gradient rides in the same bucket, or the ranks' alphas drift apart
         self.reducer = FlatGradAllReduce([self.actor, self.q1, self.q2], world, extra_params=[self.log_alpha])
 
@@ -165,7 +159,48 @@ class SacLite(object):
 
     def backward(self, batch):
         """Forward + backward of critic, actor and temperature losses; leaves gradients in .grad and
-        launches their all-reduce.  Call `apply()` later (after some rollout steps) to finish the update."""
+        launches their all-reduce.  Call `apply()` later (after some rollout steps) to finish the update.
+        On a CUDA device the ~800 kernels of the forward / backward passes are captured once into a CUDA graph (static batch
+        buffers, gradients kept allocated) and replayed: what an update costs in eager mode is the host time to launch them."""
+        if self.use_graph and batch[1].is_cuda:
+            return self._backward_graphed(batch)
+        out = self._forward_backward(batch)
+        self.reducer.launch()
+        return out
+
+    def _backward_graphed(self, batch):
+        obs, act, rew, done, nxt = batch
+        if self._graph is None:
+            self._static = ({k: v.clone() for k, v in obs.items()}, act.clone(), rew.clone(), done.clone(), {k: v.clone() for k, v in nxt.items()})
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream(device=act.device)
+            side.wait_stream(cur)
+            try:
+                with torch.cuda.stream(side):     # warm-up outside the capture (cuBLAS workspaces, autograd buffers, .grad tensors)
+                    for _ in range(3):
+                        self._forward_backward(self._static)
+                cur.wait_stream(side)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._forward_backward(self._static)
+                self._graph = g
+            except Exception as e:                # no capture on this build: eager updates from now on
+                self.use_graph, self._graph, self.graph_error = False, None, repr(e)
+                cur.wait_stream(side)
+                torch.cuda.synchronize()
+                out = self._forward_backward(batch)
+                self.reducer.launch()
+                return out
+        so, sa, sr, sd, sn = self._static
+        for k in so:
+            so[k].copy_(obs[k]); sn[k].copy_(nxt[k])
+        sa.copy_(act); sr.copy_(rew); sd.copy_(done)
+        self._graph.replay()
+        self.reducer.launch()
+        return None, None
+
+    def _forward_backward(self, batch):
         obs, act, rew, done, nxt = batch
         alpha = self.log_alpha.exp().detach()
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=obs["lidar"].is_cuda):
@@ -184,9 +219,8 @@ class SacLite(object):
         la.backward()
         for p in list(self.q1.parameters()) + list(self.q2.parameters()):
             p.requires_grad_(True)
-        self.opt_alpha.zero_grad()
+        self.opt_alpha.zero_grad(set_to_none=False)
         (-(self.log_alpha * (logp.detach().float().mean() + self.target_entropy))).backward()
-        self.reducer.launch()
         return lq.detach(), la.detach()
 
     def time_allreduce(self, reps=5):
@@ -204,10 +238,8 @@ class SacLite(object):
     def apply(self):
         self.reducer.wait()
         self.opt_q.step(); self.opt_actor.step(); self.opt_alpha.step()
-        with torch.no_grad():
-            for t, s in ((self.q1_t, self.q1), (self.q2_t, self.q2)):
-                for pt, ps in zip(t.parameters(), s.parameters()):
-                    pt.lerp_(ps, self.tau)
+        with torch.no_grad():  # Polyak averaging of both target critics as one multi-tensor operation
+            torch._foreach_lerp_(list(self.q1_t.parameters()) + list(self.q2_t.parameters()), list(self.q1.parameters()) + list(self.q2.parameters()), self.tau)
 
 
 class SacRollout(object):
