@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhope_b200.so")
 # second build of the same sources with 128 obstacle rings per scene (Dragon Lake Parking scenes, scope row f3)
 VARIANTS = {16: LIB, 128: os.path.join(HERE, "libhope_b200_obs128.so")}
-SOURCES = ["hope_kernels.cu", "scene_gen.cu", "policy_glue.cu", "policy_forward.cu", "host_wire.cpp"]
+SOURCES = ["hope_kernels.cu", "scene_gen.cu", "policy_glue.cu", "policy_forward.cu", "img_encoder.cu", "host_wire.cpp"]
 DEPS = SOURCES + ["host_wire.h", "hope_device.cuh", "render.cuh", "rs_words.cuh", "rs_walk.cuh", "rs_check.cuh", "rs_check_pooled.cuh", "div_pair.cuh", "hope_types.cuh", "observe.cuh", "observe_body.inc", "advance.cuh", "advance_body.inc", "rs_enumerate.cuh", "rs_select_body.inc", "scene_gen.h", os.path.join("..", "..", "include", "hope_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -51,6 +51,12 @@ class PolicyWeights(C.Structure):
                 [(k, C.c_void_p) for k in ("ln1_g", "ln1_b", "b_out", "ln2_g", "ln2_b", "b_ff1", "b_ff2", "b_o1", "w_o2", "b_o2")])
 
 
+class ImgConvWeights(C.Structure):
+    """hope_img_conv_weights (include/hope_b200.h): the two residual conv blocks of the image encoder, by value, PyTorch layouts"""
+    _fields_ = [("conv1_w", C.c_float * 108), ("conv1_b", C.c_float * 4), ("short1_w", C.c_float * 12), ("short1_b", C.c_float * 4),
+                ("conv2_w", C.c_float * 288), ("conv2_b", C.c_float * 8), ("short2_w", C.c_float * 32), ("short2_b", C.c_float * 8)]
+
+
 def load_library(max_obs=16):
     """Load (building if necessary) libhope_b200.so, or its 128-obstacle build for max_obs=128.  There is no
     fallback path: a missing toolchain or library is an error."""
@@ -102,6 +108,7 @@ def load_library(max_obs=16):
         "hope_policy_forward": (C.c_int, [i32, vp, vp, vp, C.POINTER(PolicyWeights), vp, vp]),
         "hope_policy_forward_smem_bytes": (C.c_int, []),
         "hope_policy_pack_matrix": (C.c_int, [vp, i32, i32, i32, vp]),
+        "hope_img_conv_forward": (C.c_int, [i32, vp, C.POINTER(ImgConvWeights), vp, vp]),
         "hope_profile_enable": (C.c_int, [vp, i32]),
         "hope_profile_read": (C.c_int, [vp, C.POINTER(C.c_double * 8), C.POINTER(u64 * 8)]),
     }

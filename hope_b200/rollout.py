@@ -208,6 +208,43 @@ class FusedPolicy(object):
         return self.out[:n]
 
 
+class FusedImgConv(object):
+    """The two residual conv blocks of the 4-modal actor's image encoder (embed_img.net[0:3]: conv blocks + flatten) as one
+    kernel, hope_img_conv_forward (csrc/img_encoder.cu): one CTA per image, both blocks in shared memory, uint8 image in,
+    bf16 features (N, 2048) out.  The 464 weights travel by value in the kernel's parameter block; `refresh()` re-reads them."""
+
+    _KEYS = (("conv1_w", "embed_img.net.0.layer.0.weight", (4, 3, 3, 3)), ("conv1_b", "embed_img.net.0.layer.0.bias", (4,)),
+             ("short1_w", "embed_img.net.0.shortcut.0.weight", (4, 3, 1, 1)), ("short1_b", "embed_img.net.0.shortcut.0.bias", (4,)),
+             ("conv2_w", "embed_img.net.1.layer.0.weight", (8, 4, 3, 3)), ("conv2_b", "embed_img.net.1.layer.0.bias", (8,)),
+             ("short2_w", "embed_img.net.1.shortcut.0.weight", (8, 4, 1, 1)), ("short2_b", "embed_img.net.1.shortcut.0.bias", (8,)))
+
+    @classmethod
+    def supports(cls, module):
+        sd = module.state_dict()
+        return all(k in sd and tuple(sd[k].shape) == shp for _, k, shp in cls._KEYS) and hasattr(module, "forward_from_img_features")
+
+    def __init__(self, module, n_envs, device):
+        assert self.supports(module)
+        self.lib = capi.load_library()
+        self.module, self.device = module, device
+        self.feat = torch.zeros((n_envs, 2048), dtype=torch.bfloat16, device=device)
+        self.weights = capi.ImgConvWeights()
+        self.refresh()
+
+    @torch.no_grad()
+    def refresh(self):
+        sd = self.module.state_dict()
+        flat = torch.cat([sd[k].detach().float().reshape(-1) for _, k, _ in self._KEYS]).cpu().numpy()   # 464 floats, one copy
+        C.memmove(C.addressof(self.weights), flat.ctypes.data, flat.nbytes)
+
+    def __call__(self, img_u8):
+        n = img_u8.shape[0]
+        assert img_u8.dtype == torch.uint8 and img_u8.is_contiguous() and tuple(img_u8.shape[1:]) == (3, 64, 64) and n <= self.feat.shape[0]
+        capi.check(self.lib.hope_img_conv_forward(n, img_u8.data_ptr(), C.byref(self.weights), self.feat.data_ptr(),
+                                                  torch.cuda.current_stream(self.device).cuda_stream))
+        return self.feat if n == self.feat.shape[0] else self.feat[:n]
+
+
 class _ConvBlock(nn.Module):
     """network.py:198-232 with the shipped switches (no batch norm, residual on, tanh): conv3x3 -> tanh -> maxpool2, plus the
     conv1x1 -> avgpool2 shortcut"""
@@ -279,6 +316,16 @@ class ReferenceShapedActor(nn.Module):
         feats = [self.embed_lidar(obs["lidar"]), self.embed_tgt(obs["target"]), self.embed_am(obs["action_mask"])]
         if self.use_img:
             feats.append(self.re_embed_img(self.embed_img(obs["img"])[0]))
+        return self._from_tokens(feats)
+
+    def forward_from_img_features(self, obs, conv_feat):
+        """forward() with the conv stack of the image encoder already applied: conv_feat (N, 2048) = embed_img.net[0:3](img)
+        (FusedImgConv); the image encoder's Linear / tanh / mean head and everything after them run here"""
+        feats = [self.embed_lidar(obs["lidar"]), self.embed_tgt(obs["target"]), self.embed_am(obs["action_mask"])]
+        feats.append(self.re_embed_img(self.embed_img.output_mean(self.embed_img.net[3:](conv_feat))))
+        return self._from_tokens(feats)
+
+    def _from_tokens(self, feats):
         x = torch.stack(feats, dim=1)
         b, n, _ = x.shape
         attn, ff = self.net.encoder.layers[0]
@@ -333,21 +380,27 @@ class RolloutEngine(object):
         self.overlap, self._pol_stream = bool(overlap), None  # collect(store=None): next action computed next to the Reeds-Shepp kernels
         self.use_graph = bool(graph) and self.fused
         self.policy_kernel = FusedPolicy(policy, env.n, dev) if (policy_kernel and self.fused and not self.use_img and FusedPolicy.supports(policy)) else None
+        self.img_conv = FusedImgConv(policy, env.n, dev) if (policy_kernel and self.fused and self.use_img and FusedImgConv.supports(policy)) else None
         self.glue = ("hope_state_norm + hope_masked_sample kernels (csrc/policy_glue.cu)" if self.fused else "eager PyTorch") + \
                     (", policy forward = hope_policy_forward (csrc/policy_forward.cu, one kernel)" if self.policy_kernel is not None else
-                     (", policy forward replayed from a CUDA graph" if self.use_graph else ""))
+                     (", policy forward replayed from a CUDA graph" if self.use_graph else "")) + \
+                    (", image conv stack = hope_img_conv_forward (csrc/img_encoder.cu)" if self.img_conv is not None else "")
         self.obs = env.reset()
         if use_planner:
             env.planner_reset()
 
     def _forward(self, net_in):
         with torch.autocast("cuda", dtype=self.autocast_dtype, enabled=self.autocast_dtype is not None):
+            if "img_feat" in net_in:
+                return self.policy.forward_from_img_features(net_in, net_in["img_feat"]).float()
             return self.policy(net_in).float()
 
     def refresh_policy(self):
         """re-read the policy's parameters into the kernel's packed copy (after an optimiser step or load_state_dict)"""
         if self.policy_kernel is not None:
             self.policy_kernel.refresh()
+        if self.img_conv is not None:
+            self.img_conv.refresh()
 
     def _policy_mean(self, net_in):
         """float32 policy output for the (persistent) float32 input buffers `net_in`"""
@@ -374,7 +427,9 @@ class RolloutEngine(object):
     def act(self, obs):
         if self.fused:
             net_in = dict(self.norm(obs))                      # float32 lidar / target / action_mask, statistics updated
-            if self.use_img:
+            if self.img_conv is not None:
+                net_in["img_feat"] = self.img_conv(obs["img"])       # uint8 image -> conv features, one kernel (persistent buffer)
+            elif self.use_img:
                 if not hasattr(self, "_img_f32"):
                     self._img_f32 = torch.zeros(obs["img"].shape, dtype=torch.float32, device=self.env.device)
                 torch.mul(obs["img"], 1.0 / 255.0, out=self._img_f32)   # the reference's float image (observation_processor.py:13-17)

@@ -263,6 +263,17 @@ int hope_policy_forward_smem_bytes(void);
  *   packed[((nt * (k_pad/16) + ks) * 32 + lane) * 4 + 2 * half + e] = W[8 nt + lane / 4][16 ks + 8 half + 2 (lane % 4) + e]. */
 int hope_policy_pack_matrix(const float *h_w, int n_out, int n_in, int k_pad, void *h_packed);
 
+/* The convolutional front of the actor's image encoder for the 4-modal network (USE_IMG): ImgEncoder's two residual blocks
+ * (model/network.py:198-299 with the shipped switches — no batch norm, tanh, residual): out = maxpool2(tanh(conv3x3(x))) +
+ * avgpool2(conv1x1(x)), 3 -> 4 -> 8 channels on d_img / 255, flattened (channel, row, column) = what embed_img.net[0:3]
+ * returns.  Weights by VALUE in PyTorch's layouts (float32, HOST memory: they travel in the kernel parameter block);
+ * d_img [n][3][64][64] uint8 (hope_outputs.img), d_feat_bf16 [n][2048] bf16.  float32 arithmetic. */
+typedef struct hope_img_conv_weights {
+    float conv1_w[4 * 3 * 9], conv1_b[4], short1_w[4 * 3], short1_b[4]; /* embed_img.net.0.layer.0 / .shortcut.0 */
+    float conv2_w[8 * 4 * 9], conv2_b[8], short2_w[8 * 4], short2_b[8]; /* embed_img.net.1.layer.0 / .shortcut.0 */
+} hope_img_conv_weights;
+int hope_img_conv_forward(int n, const uint8_t *d_img, const hope_img_conv_weights *w, void *d_feat_bf16, void *stream);
+
 /* State access (device -> host copies; synchronous). */
 int hope_get_state(hope_ctx *ctx, double *h_pose, int32_t *h_t, double *h_accum, int32_t *h_scene_id);
 int hope_set_state(hope_ctx *ctx, const double *h_pose, const int32_t *h_t, const double *h_accum);

@@ -232,7 +232,7 @@ def test_full_step_mixed_levels_vs_oracle():
 
 
 @pytest.mark.parametrize("wire", ["narrow", "narrow_portable", "mixed", "plain"])
-@pytest.mark.parametrize("n", [512, 20000])
+@pytest.mark.parametrize("n", [512, 4999, 20000])
 def test_host_buffer_api_matches_device_api(n, wire, monkeypatch):
     """hope_step_host steps k_observe env range by env range (2 ranges at n = 20 000), copies each range behind it, ships the
     mask as step counts and the lidar as flag bits + the beams that differ from the no-hit constant (k_pack_lidar) and

@@ -341,3 +341,52 @@ def test_overlapped_collect_equals_the_plain_loop():
     assert torch.equal(a.norm.stats, b.norm.stats) and a.norm.n == b.norm.n
     assert a.env.wait_observed(torch.cuda.current_stream()) is True
     a.env.close(); b.env.close()
+
+
+@pytest.mark.parametrize("n", [3, 1000])
+def test_img_conv_kernel_matches_the_float32_conv_stack(n):
+    """hope_img_conv_forward (both residual conv blocks of the image encoder in one kernel, float32 arithmetic, tanh.approx,
+    bf16 output) against PyTorch's float32 embed_img.net[0:3] on uint8 images: |diff| <= 2^-8 relative (the bf16 output
+    rounding) + 4e-3 absolute (tanh.approx: 2^-11 relative per block)."""
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(11)
+    net = rollout.ReferenceShapedActor(use_img=True).to(dev).eval()
+    with torch.no_grad():
+        for name, p in net.embed_img.named_parameters():
+            if "net.0" in name or "net.1" in name:
+                p.mul_(2.0).add_(0.05 * torch.randn_like(p))
+    img = torch.randint(0, 256, (n, 3, 64, 64), dtype=torch.uint8, device=dev)
+    img[0, :, :20] = 0; img[-1, :, :, 40:] = 255          # flat regions: borders and pooling ties
+    with torch.backends.cudnn.flags(allow_tf32=False), torch.no_grad():
+        want = net.embed_img.net[:3](img.float() / 255.0)
+    conv = rollout.FusedImgConv(net, n, dev)
+    got = conv(img).float()
+    torch.cuda.synchronize()
+    assert got.shape == want.shape == (n, 2048)
+    err = (got - want).abs()
+    print(f"  conv stack: max |diff| {err.max():.2e}, mean {err.mean():.2e}, |want| max {want.abs().max():.2f}")
+    assert (err <= want.abs() * 2.0 ** -8 + 4e-3).all()
+    with torch.no_grad():                                  # refresh() picks up a parameter change
+        net.embed_img.net[1].shortcut[0].bias.add_(0.5)
+        want2 = net.embed_img.net[:3](img.float() / 255.0)
+    conv.refresh()
+    assert ((conv(img).float() - want2).abs() <= want2.abs() * 2.0 ** -8 + 4e-3).all() and (want2 - want).abs().min() > 0.4
+
+
+def test_rollout_engine_with_images_uses_the_conv_kernel():
+    n = 1024
+    sc = generate_scenes(n, "Normal", 6)
+    torch.manual_seed(2)
+    policy = rollout.ReferenceShapedActor(use_img=True).to(torch.device("cuda", 0)).eval()
+    eng = rollout.RolloutEngine(BatchedParkingEnv(n, scenes=sc, auto_reset=True, use_img_observation=True), policy, seed=3)
+    assert eng.img_conv is not None and eng.policy_kernel is None and "hope_img_conv_forward" in eng.glue
+    ref = rollout.RolloutEngine(BatchedParkingEnv(n, scenes=sc, auto_reset=True, use_img_observation=True), policy, seed=3, policy_kernel=False)
+    assert ref.img_conv is None
+    a, (mean_a, _) = eng.act(eng.obs)
+    b, (mean_b, _) = ref.act(ref.obs)
+    torch.cuda.synchronize()
+    assert (mean_a - mean_b).abs().max() < 2e-2            # same observations and statistics: conv kernel vs cuDNN under autocast
+    assert (a == b).all(dim=1).float().mean() > 0.97
+    eng.collect(4)
+    torch.cuda.synchronize()
+    eng.env.close(); ref.env.close()

@@ -58,6 +58,12 @@ def test_restated_actor_is_the_reference_actor(ref_modules, use_img):
         want, got = ref(obs), mine(obs)
     assert want.shape == got.shape == (n, 2)
     np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=0, atol=1e-5)
+    if use_img:  # the split the conv kernel uses (FusedImgConv): conv stack first, the rest of the network from its features
+        with torch.no_grad():
+            conv = mine.embed_img.net[:3](obs["img"])
+            assert conv.shape == (n, 2048)
+            split = mine.forward_from_img_features(obs, conv)
+        assert torch.equal(split, got)
 
 
 def test_reference_actor_prefers_the_real_class(ref_modules):
