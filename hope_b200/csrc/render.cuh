@@ -50,7 +50,16 @@ constexpr int MAXSHAPES = MAXO + 3 + TRAJ;
 constexpr int NDYN = 1 + TRAJ;    // vehicle box + trajectory boxes
 constexpr int DROWS = 64;         // screen rows a vehicle-sized box can span: its diagonal is 5.07 m * K = 60.9 pixels
 constexpr int NCOLOR = 5 + TRAJ;  // 0 background, 1 obstacle, 2 start outline, 3 dest, 4 vehicle, 5.. trajectory old -> new
-static_assert(THREADS >= ROWS + 1 && MAXSHAPES <= THREADS - 2 - NCOLOR, "row owners + the probe thread; shape threads, palette threads and the camera thread are disjoint");
+// What a window byte holds: a thermometer code of the colour index, so that OR = "the later painted shape wins".  Indices 1..4:
+// the low (index) bits set.  Trajectory boxes (20 colours, old -> new) set bits 0..4 plus a 3-bit thermometer of their GROUP
+// (TGROUP consecutive boxes): the OR keeps the newest group exactly, and the gather finds the newest box of that group
+// that covers the sample in the span table (<= TGROUP look-ups).
+constexpr int TGROUP = 5;
+static_assert((TRAJ + TGROUP - 1) / TGROUP - 1 <= 3, "group thermometer: 3 bits");
+constexpr unsigned CODE_DYN = 0x10u;    // bit 4: a trajectory box covers the pixel
+__host__ __device__ constexpr unsigned colour_code(int index) { return (1u << index) - 1u; }                                      // index 1..4
+__host__ __device__ constexpr unsigned traj_code(int i) { return 0x1fu | (((1u << (i / TGROUP)) - 1u) << 5); }                    // i = 0 oldest
+static_assert(TRAJ <= 32 && THREADS >= ROWS + 1 && MAXSHAPES <= THREADS - 2 - NCOLOR, "row owners + the probe thread; shape threads, palette threads and the camera thread are disjoint");
 
 struct Palette { uint32_t rg[NCOLOR], b[NCOLOR]; };  // R | G << 16 and B: 16-bit lanes so four samples add without carry
 
@@ -74,7 +83,7 @@ struct Edge { short ylo, yhi, xlo, dx; int dy; float rdy; };  // non-horizontal 
 
 struct Shape {   // one ring prepared for draw_fillpoly
     short miny, maxy, minx, maxx;
-    short color, ne, nh, outline;      // outline = 1: the width-1 start box (runs in Smem::orun), 0: filled
+    short color, ne, nh, outline;      // color: the byte code painted (colour_code / traj_code); outline = 1: the width-1 start box, 0: filled
     Edge e[4];                         // in the order draw_fillpoly visits them (decides floor / ceil)
     short hy[4], hxa[4], hxb[4];       // horizontal edges strictly between miny and maxy (incl. the closing zero-length edge)
 };
@@ -92,8 +101,9 @@ struct Smem {
     int nstatic;                        // shapes [0, nstatic) are painted, [nstatic, nshapes) are the dynamic boxes, old -> new
     Seg seg[5];
     uint2 pal[NCOLOR];                  // (R | G << 16, B)
+    short2 drange[NDYN];                // (miny, maxy) of dynamic box d: what the gather needs of its Shape
     short2 dyn[NDYN][DROWS];            // span of dynamic box d on screen row miny_d + r; x > y: nothing; x == DYN_DIRECT: evaluate
-    alignas(16) uint32_t win[ROWS * PITCHW + 3];
+    alignas(16) uint32_t win[ROWS * PITCHW + 5];   // + gather slack, rounded to whole uint4 for the clear
 };
 
 // _coord_transform + pygame's (int) conversion of one world point
@@ -160,21 +170,22 @@ __device__ void make_seg(Seg &g, int x1, int y1, int x2, int y2) {
     g.rdy = dy ? __frcp_rn((float)dy) : 0.0f;
 }
 
-// inclusive run [x1, x2] of screen row `row` (byte offset of screen x is x - base), clipped to [cx0, cx1]; the
-// calling thread owns the row
+// inclusive run [x1, x2] of screen row `row` (byte offset of screen x is x - base), clipped to [cx0, cx1].  Pixels hold
+// THERMOMETER codes (colour_code below) and are OR-ed in: a bytewise OR of thermometer codes is the bytewise maximum, and the
+// painter's order of _render is the order of increasing colour index, so the result does not depend on which thread paints
+// which (shape, row) pair first — any thread may paint any row (shared-memory atomics, no ownership, no ordering).
 __device__ __forceinline__ void span(uint32_t *row, int base, int cx0, int cx1, int x1, int x2, uint32_t fill) {
     int a = max(min(x1, x2), cx0) - base, b = min(max(x1, x2), cx1) - base;
     if (b < a) return;
     const int wa = a >> 2, wb = b >> 2;
     const uint32_t ma = 0xffffffffu << (8 * (a & 3)), mb = 0xffffffffu >> (8 * (3 - (b & 3)));
     if (wa == wb) {
-        const uint32_t m = ma & mb;
-        row[wa] = (row[wa] & ~m) | (fill & m);
+        atomicOr(&row[wa], fill & ma & mb);
         return;
     }
-    row[wa] = (row[wa] & ~ma) | (fill & ma);
-    for (int w = wa + 1; w < wb; ++w) row[w] = fill;
-    row[wb] = (row[wb] & ~mb) | (fill & mb);
+    atomicOr(&row[wa], fill & ma);
+    for (int w = wa + 1; w < wb; ++w) atomicOr(&row[w], fill);
+    atomicOr(&row[wb], fill & mb);
 }
 
 // exact floor / ceil of num / dy (dy > 0, |num| < 2^22): the reference's float division followed by floor / ceil
@@ -209,7 +220,7 @@ __device__ __forceinline__ int row_crossings(const Shape &S, int y, int &x0, int
 
 // Does the filled shape S paint screen pixel (sx, sy)?  Exact, straight from the scan conversion (used for the rare
 // rows the span table cannot express, and for the background probe).
-__device__ bool shape_covers(const Shape &S, int sx, int sy) {
+__device__ __noinline__ bool shape_covers(const Shape &S, int sx, int sy) {
     if (sy < S.miny || sy > S.maxy) return false;
     if (S.miny == S.maxy) return sx >= S.minx && sx <= S.maxx;
     int x0, x1, x2, x3;
@@ -230,7 +241,7 @@ __device__ bool shape_covers(const Shape &S, int sx, int sy) {
 }
 
 // What one shape paints on screen row y (owned by the calling thread).
-__device__ void paint_shape_row(const Smem &sm, const Shape &S, int y, uint32_t *row, int base, int cx0, int cx1) {
+__device__ __noinline__ void paint_shape_row(const Smem &sm, const Shape &S, int y, uint32_t *row, int base, int cx0, int cx1) {
     {
         if (y < S.miny || y > S.maxy) return;
         const uint32_t fill = (uint32_t)S.color * 0x01010101u;
@@ -392,56 +403,77 @@ k_render(int n, Pool pool, EnvState st, const render::Camera *__restrict__ cams,
         const int ntraj = tn > 1 ? min(tn, TRAJ) : 0;
         const int total = nobs + 3 + ntraj;
         if (tid == 0) { sm.nshapes = total; sm.nstatic = nobs + 2; }
-        if (tid < total) {
-            const int s = tid;
+        // which shape this thread prepares.  With <= 32 obstacles every KIND of shape gets a warp of its own (obstacles, trajectory
+        // boxes, start, dest, vehicle): the five branches below then run side by side on the SM's schedulers instead of one after
+        // the other inside warp 0, and this phase, which the other warps sit out at the barrier, is as long as its longest branch
+        int s = tid < total ? tid : -1;
+        if constexpr (MAXO <= 32) {
+            const int w = tid >> 5;
+            s = -1;
+            if (w == 0) { if (lane < nobs) s = lane; }
+            else if (w == 1) { if (lane < ntraj) s = nobs + 3 + lane; }
+            else if (w <= 4 && lane == 0) s = nobs + (w - 2);
+        }
+        if (s >= 0) {
             Shape &S = sm.shapes[s];
             double bx[4], by[4];
             Camera cam;  // only the screen offsets are read here
             cam.kbx = cams[env].kbx; cam.kby = cams[env].kby;
+            // the branches only fetch what describes the shape; the box corners, the scan-conversion record and the outline
+            // segments are built once below (one copy of that code in the instruction cache, no divergence inside it)
+            int nv = 4, code, outline = 0;
+            bool is_box = true, skip = false;
+            double x = 0.0, y = 0.0, c = 1.0, sn = 0.0;
             if (s < nobs) {  // :303-305 obstacles
-                const int nv = pool.nv[(size_t)sid * MAXO + s];
+                nv = pool.nv[(size_t)sid * MAXO + s];
                 const double2 *v = reinterpret_cast<const double2 *>(pool.obs) + ((size_t)sid * MAXO + s) * MAXV;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) if (k < nv) { const double2 p = __ldg(v + k); bx[k] = p.x; by[k] = p.y; }
-                ring_shape(S, cam, bx, by, nv, 1, 0);
+                code = (int)colour_code(1); is_box = false;
             } else if (s == nobs) {  // :307-308 start box, width = 1: lines(closed=True) over the 5 coordinates
-                double ss, cc;
-                sincos(meta[M_START + 2], &ss, &cc);
-                vehicle_box(meta[M_START], meta[M_START + 1], cc, ss, par.box_x, par.box_y, bx, by);
-                ring_shape(S, cam, bx, by, 4, 2, 1);
-                int px[4], py[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) to_screen(cam, bx[q], by[q], px[q], py[q]);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) make_seg(sm.seg[k], px[k], py[k], px[(k + 1) & 3], py[(k + 1) & 3]);
-                make_seg(sm.seg[4], px[0], py[0], px[0], py[0]);  // (p4 = p0) -> p0: a single pixel
+                sincos(meta[M_START + 2], &sn, &c);
+                x = meta[M_START]; y = meta[M_START + 1];
+                code = (int)colour_code(2); outline = 1;
             } else if (s == nobs + 1) {  // :309-310 dest box
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { bx[k] = meta[M_DBX + k]; by[k] = meta[M_DBY + k]; }
-                ring_shape(S, cam, bx, by, 4, 3, 0);
+                code = (int)colour_code(3); is_box = false;
             } else if (s == nobs + 2) {  // :312-313 vehicle
-                const double x = st.pose[3 * env], y = st.pose[3 * env + 1], c = st.cs[2 * env], sn = st.cs[2 * env + 1];
-                vehicle_box(x, y, c, sn, par.box_x, par.box_y, bx, by);
-                ring_shape(S, cam, bx, by, 4, 4, 0);
+                x = st.pose[3 * env]; y = st.pose[3 * env + 1]; c = st.cs[2 * env]; sn = st.cs[2 * env + 1];
+                code = (int)colour_code(4);
                 if (ntraj > 0) {  // the newest trajectory box is painted later over the very same pixels: skip this one
                     const double2 *p = reinterpret_cast<const double2 *>(st.traj) + ((size_t)env * TRAJ + (tn - 1) % TRAJ) * 2;
                     const double2 xy = p[0], cs = p[1];
-                    if (xy.x == x && xy.y == y && cs.x == c && cs.y == sn) { S.miny = 1; S.maxy = 0; }
+                    skip = xy.x == x && xy.y == y && cs.x == c && cs.y == sn;
                 }
             } else {  // :315-319 trajectory[-(ntraj - i)], colour TRAJ_COLORS[-(ntraj - i)]
                 const int i = s - (nobs + 3), back = ntraj - i;  // back = 1: newest
                 const double2 *p = reinterpret_cast<const double2 *>(st.traj) + ((size_t)env * TRAJ + (tn - back) % TRAJ) * 2;
                 const double2 xy = p[0], cs = p[1];
-                vehicle_box(xy.x, xy.y, cs.x, cs.y, par.box_x, par.box_y, bx, by);
-                ring_shape(S, cam, bx, by, 4, 5 + TRAJ - back, 0);
+                x = xy.x; y = xy.y; c = cs.x; sn = cs.y;
+                code = (int)traj_code(i);  // palette index 5 + TRAJ - back
             }
+            if (is_box) vehicle_box(x, y, c, sn, par.box_x, par.box_y, bx, by);
+            ring_shape(S, cam, bx, by, nv, code, outline);
+            if (skip) { S.miny = 1; S.maxy = 0; }
+            if (outline) {
+                int px[4], py[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) to_screen(cam, bx[q], by[q], px[q], py[q]);
+#pragma unroll 1
+                for (int k = 0; k < 5; ++k) {  // (p4 = p0) -> p0: a single pixel
+                    const int k0 = k & 3, k1 = k == 4 ? 0 : (k + 1) & 3;
+                    make_seg(sm.seg[k], px[k0], py[k0], px[k1], py[k1]);
+                }
+            }
+            if (s >= nobs + 2) sm.drange[s - (nobs + 2)] = make_short2(S.miny, S.maxy);
         }
     }
     __syncthreads();
     const Camera &cam = sm.cam;
     const int nstatic = sm.nstatic, ndyn = sm.nshapes - nstatic;
     // ---------------------------------------------------------------- 2a. span table of the dynamic boxes: one
-    // (box, row) pair per thread and pass, all threads, once per env
+    // (box, row) pair per thread and pass, all threads, once per env; the window is cleared for the first quadrant
     for (int idx = tid; idx < ndyn * DROWS; idx += THREADS) {
         const int d = idx / DROWS, r = idx - d * DROWS;
         const Shape &S = sm.shapes[nstatic + d];
@@ -456,58 +488,81 @@ k_render(int n, Pool pool, EnvState st, const render::Camera *__restrict__ cams,
                 else if (cnt == 3) {
                     const int lo = min(x0, min(x1, x2)), hi = max(x0, max(x1, x2));
                     e = make_short2((short)lo, (short)(x0 + x1 + x2 - lo - hi));
-                } else if (cnt == 4) e = make_short2(DYN_DIRECT, 0);  // two runs: left to paint_shape_row
+                } else if (cnt == 4) e = make_short2(DYN_DIRECT, 0);  // two runs: left to paint_shape_row / shape_covers
+                for (int k = 0; k < S.nh; ++k)  // a horizontal edge on this row (the closing zero-length edge, usually): one more run
+                    if (S.hy[k] == y && e.x != DYN_DIRECT) {
+                        const int c = min(S.hxa[k], S.hxb[k]), dd = max(S.hxa[k], S.hxb[k]);
+                        if (e.x > e.y) e = make_short2((short)c, (short)dd);
+                        else if (c <= e.y + 1 && dd >= e.x - 1) e = make_short2((short)min((int)e.x, c), (short)max((int)e.y, dd));  // touches the run: one run
+                        else e = make_short2(DYN_DIRECT, 0);
+                    }
             }
         }
         sm.dyn[d][r] = e;
     }
-    if (tid == THREADS - 1) {  // screen pixel (0, 0), rotate()'s background colour, as a 1-pixel "row" in the painter's order
+    constexpr int WINQ = (int)(sizeof(sm.win) / 16);
+    for (int k = tid; k < WINQ; k += THREADS) reinterpret_cast<uint4 *>(sm.win)[k] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid == THREADS - 1) {  // screen pixel (0, 0), rotate()'s background colour, as a 1-pixel "row"; kept as a palette index
         for (int s = 0; s < nstatic; ++s) paint_shape_row(sm, sm.shapes[s], 0, &sm.probe, 0, 0, 0);
+        unsigned idx = __popc(sm.probe & 0xffu);
         for (int d = 0; d < ndyn; ++d)
-            if (shape_covers(sm.shapes[nstatic + d], 0, 0)) sm.probe = (uint32_t)sm.shapes[nstatic + d].color;
+            if (shape_covers(sm.shapes[nstatic + d], 0, 0)) idx = d == 0 ? 4u : (unsigned)(5 + TRAJ - ndyn + d);  // trajectory i = d - 1 of ndyn - 1
+        sm.probe = idx;
     }
     __syncthreads();
     const unsigned bgidx = sm.probe & 0xffu;
+    const int ntraj = ndyn - 1;
+    // palette index of a window byte at screen pixel (sx, sy): thermometer codes 0..4 by bit count, trajectory bytes through resolve_traj
+    // A trajectory byte names the newest GROUP of boxes that covers the pixel; the newest box of that group whose stored run
+    // contains sx is the one on top (and if none of the newer ones does, it is the group's oldest: one of them set the bit).
+    auto resolve = [&](unsigned code, int sx, int sy) -> unsigned {
+        if (code < CODE_DYN) return (unsigned)__popc(code);
+        const int g0 = __popc(code >> 5) * TGROUP;
+        int i = min(g0 + TGROUP - 1, ntraj - 1);
+#pragma unroll 1
+        for (; i > g0; --i) {
+            const short2 rg = sm.drange[1 + i];
+            const int r = sy - rg.x;
+            if ((unsigned)r >= (unsigned)DROWS || sy > rg.y) continue;
+            const short2 e = sm.dyn[1 + i][r];
+            if (sx >= e.x && sx <= e.y) break;
+            if (e.x == DYN_DIRECT && shape_covers(sm.shapes[nstatic + 1 + i], sx, sy)) break;
+        }
+        return (unsigned)(5 + TRAJ - ntraj + i);
+    };
 #pragma unroll 1
     for (int quad = 0; quad < 4; ++quad) {
         const QuadWindow win = sm.quad[quad];
         const int u0 = (quad & 1) * (OBS / 2), v0 = (quad >> 1) * (OBS / 2);  // crop origin of this quadrant
-        // ------------------------------------------------------------ 2b. one thread owns one window row: clear it,
-        // paint the static shapes that cross it, replay the stored runs of the dynamic boxes
-        {
-            const int nrows = win.wy1 - win.wy0 + 1;
-            const int y = tid < nrows ? win.wy0 + tid : -1;
-            uint32_t *row = sm.win + tid * PITCHW;
-            if (y >= 0) {
-#pragma unroll
-                for (int w = 0; w < PITCHW; ++w) row[w] = 0u;
+        // ------------------------------------------------------------ 2b. paint: every (shape, window row) pair is one work
+        // item, any thread paints any item (span() ORs thermometer codes).  Static shapes: shape s gives its rows to the threads
+        // starting at thread 41 s (mod 256), so that consecutive shapes load different warps; dynamic boxes: their stored runs.
+        for (int sb = 0; sb < nstatic; sb += 32) {  // each lane tests one shape against the window, the warp walks the hits
+            bool touch = false;
+            if (sb + lane < nstatic) {
+                const Shape &S = sm.shapes[sb + lane];
+                touch = S.maxy >= win.wy0 && S.miny <= win.wy1 && S.maxx >= win.wx0 && S.minx <= win.wx1;
             }
-            const int band_lo = __reduce_min_sync(HOPE_FULL_MASK, y >= 0 ? y : 0x7fffffff);
-            const int band_hi = __reduce_max_sync(HOPE_FULL_MASK, y);
-            if (band_hi >= 0) {
-                for (int sb = 0; sb < nstatic; sb += 32) {  // shapes that touch this warp's band of rows, in the painter's order
-                    const int s = sb + lane;
-                    unsigned m = __ballot_sync(HOPE_FULL_MASK, s < nstatic && sm.shapes[s].maxy >= band_lo && sm.shapes[s].miny <= band_hi);
-                    while (m) {
-                        const int hit = sb + __ffs(m) - 1;
-                        m &= m - 1;
-                        if (y >= 0) paint_shape_row(sm, sm.shapes[hit], y, row, win.wx0, win.wx0, win.wx1);
-                    }
-                }
+            unsigned m = __ballot_sync(HOPE_FULL_MASK, touch);
+            while (m) {
+                const int s = sb + __ffs(m) - 1;
+                m &= m - 1;
+                const Shape &S = sm.shapes[s];
+                const int lo = max((int)S.miny, win.wy0), cnt = min((int)S.maxy, win.wy1) - lo + 1;
+                const int t = (tid - s * 41) & (THREADS - 1);
+                if (t < cnt) paint_shape_row(sm, S, lo + t, sm.win + (lo + t - win.wy0) * PITCHW, win.wx0, win.wx0, win.wx1);
             }
-            if (y >= 0) {  // the dynamic boxes, oldest first (the painter's order)
-                for (int d = 0; d < ndyn; ++d) {
-                    const Shape &S = sm.shapes[nstatic + d];
-                    const int r = y - S.miny;
-                    if ((unsigned)r >= (unsigned)DROWS || y > S.maxy) continue;
-                    const short2 e = sm.dyn[d][r];
-                    if (e.x == DYN_DIRECT) { paint_shape_row(sm, S, y, row, win.wx0, win.wx0, win.wx1); continue; }
-                    const uint32_t fill = (uint32_t)S.color * 0x01010101u;
-                    if (e.x <= e.y) span(row, win.wx0, win.wx0, win.wx1, e.x, e.y, fill);
-                    for (int k = 0; k < S.nh; ++k)
-                        if (S.hy[k] == y) span(row, win.wx0, win.wx0, win.wx1, S.hxa[k], S.hxb[k], fill);
-                }
-            }
+        }
+        for (int idx = tid; idx < ndyn * DROWS; idx += THREADS) {
+            const int d = idx / DROWS, r = idx - d * DROWS;
+            const Shape &S = sm.shapes[nstatic + d];
+            const int y = S.miny + r;
+            if (y > S.maxy || y < win.wy0 || y > win.wy1) continue;
+            uint32_t *row = sm.win + (y - win.wy0) * PITCHW;
+            const short2 e = sm.dyn[d][r];
+            if (e.x == DYN_DIRECT) { paint_shape_row(sm, S, y, row, win.wx0, win.wx0, win.wx1); continue; }
+            const uint32_t fill = (uint32_t)S.color * 0x01010101u;
+            if (e.x <= e.y) span(row, win.wx0, win.wx0, win.wx1, e.x, e.y, fill);
         }
         __syncthreads();
         // ------------------------------------------------------------ 3. gather 32 x 32 x (2 x 2 samples)
@@ -519,7 +574,7 @@ k_render(int n, Pool pool, EnvState st, const render::Camera *__restrict__ cams,
             const int ub = u0 + 4 * i + 1, xc = ub + cam.cx0;
             uint8_t *out = img + (size_t)env * 3 * IMG * IMG + (quad >> 1) * QUAD * IMG + (quad & 1) * QUAD + i;
             if (win.fast) {
-#pragma unroll
+#pragma unroll 1
                 for (int r = 0; r < QUAD * QUAD / THREADS; ++r) {
                     const int j = (tid >> 5) + r * (THREADS / QUAD);
                     const int yc = v0 + 4 * j + 1 + cam.cy0;
@@ -528,7 +583,7 @@ k_render(int n, Pool pool, EnvState st, const render::Camera *__restrict__ cams,
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const int fx = fxb + ((k & 1) ? a1 : 0) + ((k >> 1) ? a2 : 0), fy = fyb + ((k & 1) ? b1 : 0) + ((k >> 1) ? b2 : 0);
-                        const uint2 c = sm.pal[win8[(fy >> 16) * PITCH + (fx >> 16) - woff]];
+                        const uint2 c = sm.pal[resolve(win8[(fy >> 16) * PITCH + (fx >> 16) - woff], fx >> 16, fy >> 16)];
                         srg += c.x; sb += c.y;
                     }
                     srg = ((srg + 0x00020002u) >> 2) & 0x00ff00ffu;  // (a + b + c + d + 2) >> 2 per 16-bit lane
@@ -553,7 +608,7 @@ k_render(int n, Pool pool, EnvState st, const render::Camera *__restrict__ cams,
                             if ((unsigned)fx > xmaxv || (unsigned)fy > xmaxv) idx = bgidx;  // negative wraps to a huge unsigned
                             else {
                                 const unsigned off = (unsigned)((fy >> 16) * PITCH + (fx >> 16) - woff);
-                                if (off < (unsigned)(ROWS * PITCH)) idx = win8[off];
+                                if (off < (unsigned)(ROWS * PITCH)) idx = resolve(win8[off], fx >> 16, fy >> 16);
                             }
                         }
                         const uint2 c = sm.pal[idx];
@@ -566,7 +621,11 @@ k_render(int n, Pool pool, EnvState st, const render::Camera *__restrict__ cams,
                 }
             }
         }
-        __syncthreads();  // the window is cleared and repainted for the next quadrant
+        if (quad < 3) {  // the window is cleared and repainted for the next quadrant
+            __syncthreads();
+            for (int k = tid; k < WINQ; k += THREADS) reinterpret_cast<uint4 *>(sm.win)[k] = make_uint4(0u, 0u, 0u, 0u);
+            __syncthreads();
+        }
     }
 }
 

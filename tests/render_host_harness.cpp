@@ -10,12 +10,15 @@
 
 #define HOPE_RENDER_HOST_TEST 1
 #define __device__
+#define __host__
+#define __noinline__
 #define __forceinline__ inline
 struct short2 { short x, y; };
 struct uint2 { unsigned x, y; };
 static inline short2 make_short2(short x, short y) { return short2{x, y}; }
 template <class A, class B> static inline auto min(A a, B b) -> decltype(a + b) { return a < b ? a : b; }
 template <class A, class B> static inline auto max(A a, B b) -> decltype(a + b) { return a > b ? a : b; }
+static inline uint32_t atomicOr(uint32_t *p, uint32_t v) { const uint32_t old = *p; *p = old | v; return old; }  // one host thread
 static inline float __frcp_rn(float x) { return 1.0f / x; }             // IEEE round-to-nearest reciprocal
 static inline float __int2float_rn(int x) { return (float)x; }
 static inline int __float2int_rd(float x) { return (int)std::floor(x); }
