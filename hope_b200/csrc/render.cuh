@@ -503,10 +503,13 @@ k_render(int n, Pool pool, EnvState st, const render::Camera *__restrict__ cams,
     constexpr int WINQ = (int)(sizeof(sm.win) / 16);
     for (int k = tid; k < WINQ; k += THREADS) reinterpret_cast<uint4 *>(sm.win)[k] = make_uint4(0u, 0u, 0u, 0u);
     if (tid == THREADS - 1) {  // screen pixel (0, 0), rotate()'s background colour, as a 1-pixel "row"; kept as a palette index
-        for (int s = 0; s < nstatic; ++s) paint_shape_row(sm, sm.shapes[s], 0, &sm.probe, 0, 0, 0);
+        for (int s = 0; s < nstatic; ++s) {
+            const Shape &S = sm.shapes[s];
+            if (S.miny <= 0 && S.maxy >= 0 && S.minx <= 0 && S.maxx >= 0) paint_shape_row(sm, S, 0, &sm.probe, 0, 0, 0);
+        }
         unsigned idx = __popc(sm.probe & 0xffu);
         for (int d = 0; d < ndyn; ++d)
-            if (shape_covers(sm.shapes[nstatic + d], 0, 0)) idx = d == 0 ? 4u : (unsigned)(5 + TRAJ - ndyn + d);  // trajectory i = d - 1 of ndyn - 1
+            if (sm.shapes[nstatic + d].miny <= 0 && sm.shapes[nstatic + d].minx <= 0 && shape_covers(sm.shapes[nstatic + d], 0, 0)) idx = d == 0 ? 4u : (unsigned)(5 + TRAJ - ndyn + d);  // trajectory i = d - 1 of ndyn - 1
         sm.probe = idx;
     }
     __syncthreads();
@@ -535,8 +538,10 @@ k_render(int n, Pool pool, EnvState st, const render::Camera *__restrict__ cams,
         const QuadWindow win = sm.quad[quad];
         const int u0 = (quad & 1) * (OBS / 2), v0 = (quad >> 1) * (OBS / 2);  // crop origin of this quadrant
         // ------------------------------------------------------------ 2b. paint: every (shape, window row) pair is one work
-        // item, any thread paints any item (span() ORs thermometer codes).  Static shapes: shape s gives its rows to the threads
-        // starting at thread 41 s (mod 256), so that consecutive shapes load different warps; dynamic boxes: their stored runs.
+        // item, any thread paints any item (span() ORs thermometer codes).  Static shapes: their rows are dealt round the threads;
+        // dynamic boxes: their stored runs.
+        int first = 0;  // rows handed out so far (mod 256): shape after shape the items go round the threads, so every thread
+                        // gets floor or ceil of (all rows of all shapes) / 256 of them
         for (int sb = 0; sb < nstatic; sb += 32) {  // each lane tests one shape against the window, the warp walks the hits
             bool touch = false;
             if (sb + lane < nstatic) {
@@ -549,7 +554,8 @@ k_render(int n, Pool pool, EnvState st, const render::Camera *__restrict__ cams,
                 m &= m - 1;
                 const Shape &S = sm.shapes[s];
                 const int lo = max((int)S.miny, win.wy0), cnt = min((int)S.maxy, win.wy1) - lo + 1;
-                const int t = (tid - s * 41) & (THREADS - 1);
+                const int t = (tid - first) & (THREADS - 1);
+                first += cnt;
                 if (t < cnt) paint_shape_row(sm, S, lo + t, sm.win + (lo + t - win.wy0) * PITCHW, win.wx0, win.wx0, win.wx1);
             }
         }
