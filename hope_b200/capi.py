@@ -48,7 +48,7 @@ class PolicyWeights(C.Structure):
     _fields_ = ([("w1_lidar", C.c_void_p), ("w1_target", C.c_void_p), ("w1_mask", C.c_void_p), ("w2", C.c_void_p * 3),
                  ("w_qkv", C.c_void_p), ("w_out", C.c_void_p), ("w_ff1", C.c_void_p), ("w_ff2", C.c_void_p), ("w_o1", C.c_void_p),
                  ("b1", C.c_void_p * 3), ("b2", C.c_void_p * 3)] +
-                [(k, C.c_void_p) for k in ("ln1_g", "ln1_b", "b_out", "ln2_g", "ln2_b", "b_ff1", "b_ff2", "b_o1", "w_o2", "b_o2")])
+                [(k, C.c_void_p) for k in ("ln1_g", "ln1_b", "b_out", "ln2_g", "ln2_b", "b_ff1", "b_ff2", "b_o1", "w_o2", "b_o2", "w2_img", "b2_img")])
 
 
 class ImgConvWeights(C.Structure):
@@ -106,6 +106,7 @@ def load_library(max_obs=16):
         "hope_state_norm": (C.c_int, [dp, dp, dp, i32, dp, C.c_double, i32, vp, vp, vp, vp, vp]),
         "hope_masked_sample": (C.c_int, [i32, vp, dp, dp, dp, u64, u64, dp, vp, vp, vp]),
         "hope_policy_forward": (C.c_int, [i32, vp, vp, vp, C.POINTER(PolicyWeights), vp, vp]),
+        "hope_policy_forward_img": (C.c_int, [i32, vp, vp, vp, vp, C.POINTER(PolicyWeights), vp, vp]),
         "hope_policy_forward_smem_bytes": (C.c_int, []),
         "hope_policy_pack_matrix": (C.c_int, [vp, i32, i32, i32, vp]),
         "hope_img_conv_forward": (C.c_int, [i32, vp, C.POINTER(ImgConvWeights), vp, vp]),

@@ -24,8 +24,6 @@
 
 namespace hope_policy {
 
-constexpr int BM = 32;                 // envs per CTA
-constexpr int ROWS = 3 * BM;           // token rows per CTA, row = modality * BM + env
 constexpr int E = 128;                 // embedding width
 constexpr int HEADS = 8, DH = 32;
 constexpr int THREADS = 256, WARPS = THREADS / 32;
@@ -35,7 +33,21 @@ constexpr int LDQ = 3 * DH + 8;        // qkv of one head
 constexpr int LDA = DH + 8;            // attention output of one head
 constexpr int LDR = E + 8;             // float32 residual stream (row stride = 8 banks mod 32: the float2 epilogue stores of 4 rows per phase do not collide)
 
-struct Smem {
+// NM = 3: lidar, target, action mask (ACTOR_CONFIGS without the image).  NM = 4: the same plus the image token, whose encoder
+// (conv stack -> Linear(2048, 256) tanh -> mean head) runs before this kernel; its tanh + re-embedding Linear(128, 128) is the
+// "second embedding layer" of token 3 here.  Shared memory per CTA is NM x BM token rows: 32 envs for NM = 3 (106 KB, 2 CTAs
+// per SM), 16 envs for NM = 4 (71 KB, 3 CTAs per SM).
+template <int NM> struct Cfg {
+    static constexpr int BM = NM == 3 ? 32 : 16;   // envs per CTA
+    static constexpr int ROWS = NM * BM;           // token rows per CTA, row = modality * BM + env
+    static constexpr int MTM = BM / 16;            // 16-row tiles of one modality
+    static constexpr int MTA = ROWS / 16;          // 16-row tiles of all tokens
+    static constexpr int MINB = NM == 3 ? 2 : 3;   // CTAs per SM
+    static_assert(ROWS % (4 * WARPS) == 0 && MTA % 2 == 0 && ROWS <= 16 * WARPS, "LayerNorm passes, qkv tiling, one softmax row per lane pair");
+};
+
+template <int NM> struct Smem {
+    static constexpr int BM = Cfg<NM>::BM, ROWS = Cfg<NM>::ROWS;
     float x[ROWS][LDR];                        // residual stream
     __nv_bfloat16 h[ROWS][LDX];                // embed hidden -> LayerNorm output -> bf16 copy of x for the output head
     union {
@@ -136,9 +148,11 @@ __device__ __forceinline__ void zero(float (&acc)[MT][NT][4]) {
             for (int q = 0; q < 4; ++q) acc[mi][ni][q] = 0.f;
 }
 
-// LayerNorm (eps 1e-5, affine) of the 96 residual rows -> bf16 operand.  8 lanes per row (16 columns each), 4 rows per warp pass:
+// LayerNorm (eps 1e-5, affine) of the residual rows -> bf16 operand.  8 lanes per row (16 columns each), 4 rows per warp pass:
 // three shuffle steps per reduction instead of five, and four independent rows in flight per warp.
-__device__ __forceinline__ void layer_norm_rows(Smem &sm, const float *__restrict__ g, const float *__restrict__ b, int warp, int lane) {
+template <int NM>
+__device__ __forceinline__ void layer_norm_rows(Smem<NM> &sm, const float *__restrict__ g, const float *__restrict__ b, int warp, int lane) {
+    constexpr int ROWS = Cfg<NM>::ROWS;
     const int sub = lane >> 3, part = lane & 7;  // row within the pass; the lane's columns are 32 v + 4 part .. + 3, v = 0..3, so that the
                                                  // 8 lanes of a row read 128 contiguous bytes per load (no bank conflicts)
     float4 gg[4], bb[4];
@@ -171,12 +185,13 @@ __device__ __forceinline__ void layer_norm_rows(Smem &sm, const float *__restric
         }
     }
 }
-static_assert(ROWS % (4 * WARPS) == 0, "layer_norm_rows: whole passes of 4 rows per warp");
 
-__global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const float *__restrict__ lidar, const float *__restrict__ target, const float *__restrict__ mask,
-                                                               hope_policy_weights W, float *__restrict__ out) {
+template <int NM>
+__global__ void __launch_bounds__(THREADS, Cfg<NM>::MINB) k_policy_forward(int n, const float *__restrict__ lidar, const float *__restrict__ target, const float *__restrict__ mask,
+                                                                        const float *__restrict__ img_mean, hope_policy_weights W, float *__restrict__ out) {
+    constexpr int BM = Cfg<NM>::BM, ROWS = Cfg<NM>::ROWS, MTM = Cfg<NM>::MTM, MTA = Cfg<NM>::MTA;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    Smem<NM> &sm = *reinterpret_cast<Smem<NM> *>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int env0 = blockIdx.x * BM;
     using fragp = const uint2 *;
@@ -203,21 +218,29 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
         if (c < 42 && env0 + e < n) v = __ldg(reinterpret_cast<const float2 *>(mask + (size_t)(env0 + e) * 42 + c));
         *reinterpret_cast<__nv_bfloat162 *>(&sm.u.in.mask[e][c]) = __floats2bfloat162_rn(v.x, v.y);
     }
+    if constexpr (NM == 4) {  // re_embed_img.0: tanh of the image encoder's mean head = the hidden layer of token 3
+        for (int i = tid; i < BM * (E / 2); i += THREADS) {
+            const int e = i / (E / 2), c = 2 * (i % (E / 2));
+            float2 v = make_float2(0.f, 0.f);
+            if (env0 + e < n) v = __ldg(reinterpret_cast<const float2 *>(img_mean + (size_t)(env0 + e) * E + c));
+            *reinterpret_cast<__nv_bfloat162 *>(&sm.h[3 * BM + e][c]) = __floats2bfloat162_rn(tanh_fast(v.x), tanh_fast(v.y));
+        }
+    }
     __syncthreads();
 
     // ---- embeddings, layer 1: h[m * BM + e] = tanh(in_m W1_m^T + b1_m).  Warp w owns columns 16 w .. 16 w + 15 of every modality ----
     const int ncol0 = 16 * warp;
     auto cols = [&](int ni) { return ncol0 + 8 * ni; };
     {
-        float acc[2][2][4];
+        float acc[MTM][2][4];
 #pragma unroll
         for (int m = 0; m < 3; ++m) {
             init_bias(acc, W.b1[m], ncol0, ccol);
-            if (m == 0) warp_gemm<2, 2, KL>(acc, &sm.u.in.lidar[0][0], KL + 8, 0, w1_lidar, KL / 16, 0, cols, lane);
-            if (m == 1) warp_gemm<2, 2, KT>(acc, &sm.u.in.target[0][0], KT + 8, 0, w1_target, KT / 16, 0, cols, lane);
-            if (m == 2) warp_gemm<2, 2, KA>(acc, &sm.u.in.mask[0][0], KA + 8, 0, w1_mask, KA / 16, 0, cols, lane);
+            if (m == 0) warp_gemm<MTM, 2, KL>(acc, &sm.u.in.lidar[0][0], KL + 8, 0, w1_lidar, KL / 16, 0, cols, lane);
+            if (m == 1) warp_gemm<MTM, 2, KT>(acc, &sm.u.in.target[0][0], KT + 8, 0, w1_target, KT / 16, 0, cols, lane);
+            if (m == 2) warp_gemm<MTM, 2, KA>(acc, &sm.u.in.mask[0][0], KA + 8, 0, w1_mask, KA / 16, 0, cols, lane);
 #pragma unroll
-            for (int mi = 0; mi < 2; ++mi)
+            for (int mi = 0; mi < MTM; ++mi)
 #pragma unroll
                 for (int ni = 0; ni < 2; ++ni) {
                     const int c = ncol0 + 8 * ni + ccol, r = m * BM + 16 * mi + crow;
@@ -229,13 +252,13 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
     __syncthreads();
     // ---- embeddings, layer 2: x = h W2_m^T + b2_m (float32 residual stream) --------------------------------------
     {
-        float acc[2][2][4];
+        float acc[MTM][2][4];
 #pragma unroll
-        for (int m = 0; m < 3; ++m) {
-            init_bias(acc, W.b2[m], ncol0, ccol);
-            warp_gemm<2, 2, E>(acc, &sm.h[0][0], LDX, m * BM, static_cast<fragp>(W.w2[m]), E / 16, 0, cols, lane);
+        for (int m = 0; m < NM; ++m) {
+            init_bias(acc, m < 3 ? W.b2[m < 3 ? m : 0] : W.b2_img, ncol0, ccol);
+            warp_gemm<MTM, 2, E>(acc, &sm.h[0][0], LDX, m * BM, static_cast<fragp>(m < 3 ? W.w2[m < 3 ? m : 0] : W.w2_img), E / 16, 0, cols, lane);
 #pragma unroll
-            for (int mi = 0; mi < 2; ++mi)
+            for (int mi = 0; mi < MTM; ++mi)
 #pragma unroll
                 for (int ni = 0; ni < 2; ++ni) {
                     const int c = ncol0 + 8 * ni + ccol, r = m * BM + 16 * mi + crow;
@@ -250,17 +273,18 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
     layer_norm_rows(sm, W.ln1_g, W.ln1_b, warp, lane);
     __syncthreads();
     {
-        float oacc[6][2][4];  // this warp's 16 columns of to_out for all 96 rows, accumulated over the heads
+        float oacc[MTA][2][4];  // this warp's 16 columns of to_out for all token rows, accumulated over the heads
         init_bias(oacc, W.b_out, ncol0, ccol);
-        // qkv of one head: 96 rows x 96 columns = 6 x 12 tiles; warp w takes row tiles 3 (w / 4) .. + 2 and column tiles 3 (w % 4) .. + 2
-        const int qm0 = 3 * (warp >> 2), qn0 = 3 * (warp & 3);
+        // qkv of one head: ROWS rows x 96 columns = MTA x 12 tiles; warp w takes row tiles QM (w / 4) .. + QM - 1 and column tiles 3 (w % 4) .. + 2
+        constexpr int QM = MTA / 2;
+        const int qm0 = QM * (warp >> 2), qn0 = 3 * (warp & 3);
         for (int hd = 0; hd < HEADS; ++hd) {
-            float qacc[3][3][4];
+            float qacc[QM][3][4];
             zero(qacc);
             auto qrow = [&](int ni) { const int t = qn0 + ni; return (t >> 2) * (HEADS * DH) + hd * DH + (t & 3) * 8; };  // q | k | v blocks of to_qkv, head hd
-            warp_gemm<3, 3, E>(qacc, &sm.h[0][0], LDX, 16 * qm0, w_qkv, E / 16, 0, qrow, lane);
+            warp_gemm<QM, 3, E>(qacc, &sm.h[0][0], LDX, 16 * qm0, w_qkv, E / 16, 0, qrow, lane);
 #pragma unroll
-            for (int mi = 0; mi < 3; ++mi)
+            for (int mi = 0; mi < QM; ++mi)
 #pragma unroll
                 for (int ni = 0; ni < 3; ++ni) {
                     const int c = 8 * (qn0 + ni) + ccol, r = 16 * (qm0 + mi) + crow;
@@ -268,7 +292,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
                     *reinterpret_cast<__nv_bfloat162 *>(&sm.u.hd.qkv[r + 8][c]) = __floats2bfloat162_rn(qacc[mi][ni][2], qacc[mi][ni][3]);
                 }
             __syncthreads();
-            // softmax over the env's 3 tokens: two threads per query row, each owns 16 of the head's 32 dims (its half of every q . k,
+            // softmax over the env's NM tokens: two threads per query row, each owns 16 of the head's 32 dims (its half of every q . k,
             // summed with one shuffle, and its half of the output)
             {
                 // lanes L and L + 16 of a warp share query row 16 warp + L % 16 (first / second half of the head's dims): the 8 lanes
@@ -276,7 +300,9 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
                 const int r = (tid >> 5) * 16 + (lane & 15), half = lane >> 4, e = r % BM;
                 const bool on = r < ROWS;
                 float qv[16];
-                float s[3] = {0.f, 0.f, 0.f};
+                float s[NM];
+#pragma unroll
+                for (int j = 0; j < NM; ++j) s[j] = 0.f;
                 if (on) {
                     const uint4 *qp = reinterpret_cast<const uint4 *>(&sm.u.hd.qkv[r][16 * half]);
 #pragma unroll
@@ -287,7 +313,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
                         for (int c = 0; c < 4; ++c) { qv[8 * v + 2 * c] = __uint_as_float(ws[c] << 16); qv[8 * v + 2 * c + 1] = __uint_as_float(ws[c] & 0xffff0000u); }
                     }
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) {
+                    for (int j = 0; j < NM; ++j) {
                         const uint4 *kp = reinterpret_cast<const uint4 *>(&sm.u.hd.qkv[j * BM + e][DH + 16 * half]);
                         float d[4] = {0.f, 0.f, 0.f, 0.f};  // four independent chains
 #pragma unroll
@@ -301,25 +327,34 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < 3; ++j) s[j] = (s[j] + __shfl_xor_sync(0xffffffffu, s[j], 16)) * 0.17677669529663687f;  // dim_head ** -0.5
+                for (int j = 0; j < NM; ++j) s[j] = (s[j] + __shfl_xor_sync(0xffffffffu, s[j], 16)) * 0.17677669529663687f;  // dim_head ** -0.5
                 if (on) {
-                    const float mx = fmaxf(s[0], fmaxf(s[1], s[2]));
-                    const float p0 = __expf(s[0] - mx), p1 = __expf(s[1] - mx), p2 = __expf(s[2] - mx), inv = 1.f / (p0 + p1 + p2);
-                    const float w0 = p0 * inv, w1 = p1 * inv, w2 = p2 * inv;
-                    const uint4 *v0 = reinterpret_cast<const uint4 *>(&sm.u.hd.qkv[e][2 * DH + 16 * half]);
-                    const uint4 *v1 = reinterpret_cast<const uint4 *>(&sm.u.hd.qkv[BM + e][2 * DH + 16 * half]);
-                    const uint4 *v2 = reinterpret_cast<const uint4 *>(&sm.u.hd.qkv[2 * BM + e][2 * DH + 16 * half]);
+                    float mx = s[0];
+#pragma unroll
+                    for (int j = 1; j < NM; ++j) mx = fmaxf(mx, s[j]);
+                    float pw[NM], den = 0.f;
+#pragma unroll
+                    for (int j = 0; j < NM; ++j) { pw[j] = __expf(s[j] - mx); den += pw[j]; }
+                    const float inv = 1.f / den;
                     uint4 *dst = reinterpret_cast<uint4 *>(&sm.u.hd.att[r][16 * half]);
 #pragma unroll
                     for (int v = 0; v < 2; ++v) {
-                        const uint4 a4 = v0[v], b4 = v1[v], c4 = v2[v];
-                        const uint32_t as[4] = {a4.x, a4.y, a4.z, a4.w}, bs[4] = {b4.x, b4.y, b4.z, b4.w}, cs[4] = {c4.x, c4.y, c4.z, c4.w};
+                        float lo[4] = {0.f, 0.f, 0.f, 0.f}, hi[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int j = 0; j < NM; ++j) {
+                            const uint4 a4 = reinterpret_cast<const uint4 *>(&sm.u.hd.qkv[j * BM + e][2 * DH + 16 * half])[v];
+                            const uint32_t as[4] = {a4.x, a4.y, a4.z, a4.w};
+                            const float wj = pw[j] * inv;
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                lo[c] = j == 0 ? wj * __uint_as_float(as[c] << 16) : fmaf(wj, __uint_as_float(as[c] << 16), lo[c]);
+                                hi[c] = j == 0 ? wj * __uint_as_float(as[c] & 0xffff0000u) : fmaf(wj, __uint_as_float(as[c] & 0xffff0000u), hi[c]);
+                            }
+                        }
                         uint32_t o[4];
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
-                            const float lo = fmaf(w2, __uint_as_float(cs[c] << 16), fmaf(w1, __uint_as_float(bs[c] << 16), w0 * __uint_as_float(as[c] << 16)));
-                            const float hi = fmaf(w2, __uint_as_float(cs[c] & 0xffff0000u), fmaf(w1, __uint_as_float(bs[c] & 0xffff0000u), w0 * __uint_as_float(as[c] & 0xffff0000u)));
-                            const __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
+                            const __nv_bfloat162 pk = __floats2bfloat162_rn(lo[c], hi[c]);
                             o[c] = *reinterpret_cast<const uint32_t *>(&pk);
                         }
                         dst[v] = make_uint4(o[0], o[1], o[2], o[3]);
@@ -328,10 +363,10 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
             }
             __syncthreads();
             // the head's slice of to_out: oacc += att (96 x 32) * w_out[:, 32 hd .. 32 hd + 31]^T
-            warp_gemm<6, 2, DH>(oacc, &sm.u.hd.att[0][0], LDA, 0, w_out, HEADS * DH / 16, hd * (DH / 16), cols, lane);
+            warp_gemm<MTA, 2, DH>(oacc, &sm.u.hd.att[0][0], LDA, 0, w_out, HEADS * DH / 16, hd * (DH / 16), cols, lane);
         }
 #pragma unroll
-        for (int mi = 0; mi < 6; ++mi)
+        for (int mi = 0; mi < MTA; ++mi)
 #pragma unroll
             for (int ni = 0; ni < 2; ++ni) {
                 const int c = ncol0 + 8 * ni + ccol, r = 16 * mi + crow;
@@ -346,11 +381,11 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
     layer_norm_rows(sm, W.ln2_g, W.ln2_b, warp, lane);
     __syncthreads();
     {
-        float acc[6][2][4];
+        float acc[MTA][2][4];
         init_bias(acc, W.b_ff1, ncol0, ccol);
-        warp_gemm<6, 2, E>(acc, &sm.h[0][0], LDX, 0, w_ff1, E / 16, 0, cols, lane);
+        warp_gemm<MTA, 2, E>(acc, &sm.h[0][0], LDX, 0, w_ff1, E / 16, 0, cols, lane);
 #pragma unroll
-        for (int mi = 0; mi < 6; ++mi)
+        for (int mi = 0; mi < MTA; ++mi)
 #pragma unroll
             for (int ni = 0; ni < 2; ++ni) {
                 const int c = ncol0 + 8 * ni + ccol, r = 16 * mi + crow;
@@ -359,10 +394,10 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
             }
         __syncthreads();
         init_bias(acc, W.b_ff2, ncol0, ccol);
-        warp_gemm<6, 2, E>(acc, &sm.u.ff[0][0], LDX, 0, w_ff2, E / 16, 0, cols, lane);
+        warp_gemm<MTA, 2, E>(acc, &sm.u.ff[0][0], LDX, 0, w_ff2, E / 16, 0, cols, lane);
         // the residual stream's last use is the output head's bf16 operand: write x + ff straight into h
 #pragma unroll
-        for (int mi = 0; mi < 6; ++mi)
+        for (int mi = 0; mi < MTA; ++mi)
 #pragma unroll
             for (int ni = 0; ni < 2; ++ni) {
                 const int c = ncol0 + 8 * ni + ccol, r = 16 * mi + crow;
@@ -373,13 +408,13 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
     }
     __syncthreads();  // h complete (all warps also passed their last read of u.ff before this point: u.head may be written now)
 
-    // ---- output head: tanh(W_o2 tanh(W_o1 [x_0 | x_1 | x_2] + b_o1) + b_o2) ---------------------------------------------
+    // ---- output head: tanh(W_o2 tanh(W_o1 [x_0 | .. | x_NM-1] + b_o1) + b_o2) ---------------------------------------------
     {
-        float acc[2][2][4];
+        float acc[MTM][2][4];
         init_bias(acc, W.b_o1, ncol0, ccol);
-        warp_gemm<2, 2, 3 * E>(acc, &sm.h[0][0], LDX, 0, w_o1, 3 * E / 16, 0, cols, lane, BM);  // K block m reads token rows m * BM + env
+        warp_gemm<MTM, 2, NM * E>(acc, &sm.h[0][0], LDX, 0, w_o1, NM * E / 16, 0, cols, lane, BM);  // K block m reads token rows m * BM + env
 #pragma unroll
-        for (int mi = 0; mi < 2; ++mi)
+        for (int mi = 0; mi < MTM; ++mi)
 #pragma unroll
             for (int ni = 0; ni < 2; ++ni) {
                 const int c = ncol0 + 8 * ni + ccol, r = 16 * mi + crow;
@@ -389,31 +424,44 @@ __global__ void __launch_bounds__(THREADS, 2) k_policy_forward(int n, const floa
     }
     __syncthreads();
     {   // Linear(128, 2): 4 lanes per (env, output), 32 products each
-        const int pair = tid >> 2, part = tid & 3, e = pair >> 1, o = pair & 1;  // 64 pairs x 4 lanes = 256 threads
+        const int pair = tid >> 2, part = tid & 3, e = (pair >> 1) % BM, o = pair & 1;  // 2 BM pairs x 4 lanes (whole warps either way)
         const float *hrow = &sm.u.head[e][32 * part], *wrow = W.w_o2 + o * E + 32 * part;
         float s = 0.f;
 #pragma unroll
         for (int c = 0; c < 32; ++c) s = fmaf(hrow[c], __ldg(wrow + c), s);
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if (part == 0 && env0 + e < n) out[(size_t)(env0 + e) * 2 + o] = tanhf(s + __ldg(W.b_o2 + o));
+        if (part == 0 && pair < 2 * BM && env0 + e < n) out[(size_t)(env0 + e) * 2 + o] = tanhf(s + __ldg(W.b_o2 + o));
     }
 }
 
 }  // namespace hope_policy
 
+template <int NM>
+static int launch_policy(int n, const float *d_lidar, const float *d_target, const float *d_mask, const float *d_img_mean, const hope_policy_weights *w, float *d_out,
+                         void *stream) {
+    using namespace hope_policy;
+    const int smem = (int)sizeof(Smem<NM>);
+    if (cudaFuncSetAttribute(k_policy_forward<NM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return HOPE_ERR_CUDA;
+    constexpr int BM = Cfg<NM>::BM;
+    k_policy_forward<NM><<<(n + BM - 1) / BM, THREADS, smem, static_cast<cudaStream_t>(stream)>>>(n, d_lidar, d_target, d_mask, d_img_mean, *w, d_out);
+    return cudaGetLastError() == cudaSuccess ? HOPE_OK : HOPE_ERR_CUDA;
+}
+
 extern "C" {
 
 int hope_policy_forward(int n, const float *d_lidar, const float *d_target, const float *d_mask, const hope_policy_weights *w, float *d_out, void *stream) {
     if (n <= 0 || !d_lidar || !d_target || !d_mask || !w || !d_out) return HOPE_ERR_INVALID;
-    using namespace hope_policy;
-    const int smem = (int)sizeof(Smem);
-    if (cudaFuncSetAttribute(k_policy_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return HOPE_ERR_CUDA;
-    k_policy_forward<<<(n + BM - 1) / BM, THREADS, smem, static_cast<cudaStream_t>(stream)>>>(n, d_lidar, d_target, d_mask, *w, d_out);
-    return cudaGetLastError() == cudaSuccess ? HOPE_OK : HOPE_ERR_CUDA;
+    return launch_policy<3>(n, d_lidar, d_target, d_mask, nullptr, w, d_out, stream);
 }
 
-int hope_policy_forward_smem_bytes(void) { return (int)sizeof(hope_policy::Smem); }
+int hope_policy_forward_img(int n, const float *d_lidar, const float *d_target, const float *d_mask, const float *d_img_mean, const hope_policy_weights *w,
+                            float *d_out, void *stream) {
+    if (n <= 0 || !d_lidar || !d_target || !d_mask || !d_img_mean || !w || !d_out || !w->w2_img || !w->b2_img) return HOPE_ERR_INVALID;
+    return launch_policy<4>(n, d_lidar, d_target, d_mask, d_img_mean, w, d_out, stream);
+}
+
+int hope_policy_forward_smem_bytes(void) { return (int)sizeof(hope_policy::Smem<3>); }
 
 int hope_policy_pack_matrix(const float *h_w, int n_out, int n_in, int k_pad, void *h_packed) {
     if (!h_w || !h_packed || n_out <= 0 || n_in <= 0 || n_out % 8 || k_pad % 16 || k_pad < n_in) return HOPE_ERR_INVALID;

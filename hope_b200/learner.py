@@ -258,7 +258,7 @@ class SacRollout(object):
         self.updates = 0
         self.overlap, self._pol_stream, self._next_action, self._steps_done = True, None, None, 0
         # acting: the actor's forward as one kernel (csrc/policy_forward.cu), its packed weights re-read after every update
-        self.actor_kernel = FusedPolicy(self.learner.actor, env.n, env.device) if (policy_kernel and FusedPolicy.supports(self.learner.actor)) else None
+        self.actor_kernel = FusedPolicy(self.learner.actor, env.n, env.device) if (policy_kernel and FusedPolicy.supports(self.learner.actor) == 3) else None
 
     @torch.no_grad()
     def _act(self, obs):

@@ -130,9 +130,10 @@ class FusedMaskedSampler(object):
 
 
 class FusedPolicy(object):
-    """The 3-modal actor (MultiObsEmbedding(ACTOR_CONFIGS) / ReferenceShapedActor: lidar, target, action mask) as one kernel,
-    hope_policy_forward (csrc/policy_forward.cu): 32 envs per CTA carried through the embeddings, the transformer block and the
-    output head with every activation in shared memory, bf16 tensor-core GEMMs with float32 accumulation.  The parameters are
+    """The actor (MultiObsEmbedding(ACTOR_CONFIGS) / ReferenceShapedActor: lidar, target, action mask, and with the 4-modal
+    network the image token from its encoder's mean head) as one kernel, hope_policy_forward[_img] (csrc/policy_forward.cu):
+    32 (4-modal: 16) envs per CTA carried through the embeddings, the transformer block and the output head with every
+    activation in shared memory, bf16 tensor-core GEMMs with float32 accumulation.  The parameters are
     read from the module's state_dict by the reference's names and packed once (`refresh()` after an optimiser step): bf16, input
     width padded to 16, in the kernel's fragment order (include/hope_b200.h, hope_policy_pack_matrix)."""
 
@@ -152,22 +153,39 @@ class FusedPolicy(object):
                "net.encoder.layers.0.0.fn.to_qkv.weight": (768, 128), "net.encoder.layers.0.0.fn.to_out.0.weight": (128, 256),
                "net.output.0.weight": (128, 384), "net.output.2.weight": (2, 128)}
 
+    _IMG_MATS = (("w2_img", "re_embed_img.1.weight", 128),)
+    _IMG_VECS = (("b2_img", "re_embed_img.1.bias"),)
+
     @classmethod
     def supports(cls, module):
-        """True when `module` has exactly the lidar + target + action-mask architecture the kernel implements"""
+        """3 when `module` has exactly the lidar + target + action-mask architecture the kernel implements, 4 when it is the
+        4-modal network (the same plus the image token: embed_img / re_embed_img, Linear(512, 128) head) and exposes the image
+        encoder's tail (`img_mean_from_conv`), else 0"""
         sd = module.state_dict()
-        if any(k.startswith(("embed_img", "re_embed_img")) for k in sd):
-            return False
         names = [m[1] for m in cls._MATS] + [v[1] for v in cls._VECS]
-        return all(k in sd for k in names) and all(tuple(sd[k].shape) == shp for k, shp in cls._SHAPES.items())
+        if not all(k in sd for k in names):
+            return 0
+        has_img = any(k.startswith(("embed_img", "re_embed_img")) for k in sd)
+        shapes = dict(cls._SHAPES)
+        if has_img:
+            shapes["net.output.0.weight"] = (128, 512)
+            shapes["re_embed_img.1.weight"] = (128, 128)
+            if "re_embed_img.1.weight" not in sd or not hasattr(module, "img_mean_from_conv"):
+                return 0
+        if not all(tuple(sd[k].shape) == shp for k, shp in shapes.items()):
+            return 0
+        return 4 if has_img else 3
 
     def __init__(self, module, n_envs, device):
-        assert self.supports(module), "hope_policy_forward implements the 3-modal actor of ACTOR_CONFIGS only"
+        self.n_modal = self.supports(module)
+        assert self.n_modal, "hope_policy_forward implements the 3- and 4-modal actors of ACTOR_CONFIGS only"
         self.lib = capi.load_library()
         self.module, self.device = module, device
         self.out = torch.zeros((n_envs, 2), dtype=torch.float32, device=device)
         self.weights = capi.PolicyWeights()
         self._keep = {}
+        self.mats = tuple((n, k, 512 if (n == "w_o1" and self.n_modal == 4) else kp) for n, k, kp in self._MATS) + (self._IMG_MATS if self.n_modal == 4 else ())
+        self.vecs = self._VECS + (self._IMG_VECS if self.n_modal == 4 else ())
         self.refresh()
 
     @torch.no_grad()
@@ -176,7 +194,7 @@ class FusedPolicy(object):
         that is still in flight on another stream never sees freed memory; the caller orders refresh against forwards)"""
         sd = self.module.state_dict()
         keep = self._keep
-        for name, key, kpad in self._MATS:
+        for name, key, kpad in self.mats:
             w = sd[key].detach()
             if name not in keep:
                 keep[name] = torch.zeros((w.shape[0], kpad), dtype=torch.bfloat16, device=self.device)
@@ -186,7 +204,7 @@ class FusedPolicy(object):
             # fragment packing (hope_policy_pack_matrix on the device): [nt][8 rows][ks][half][4 lane%4][2] -> [nt][ks][row][lane%4][half][2]
             n_out = w.shape[0]
             keep[name].view(n_out // 8, kpad // 16, 8, 4, 2, 2).copy_(pad.view(n_out // 8, 8, kpad // 16, 2, 4, 2).permute(0, 2, 1, 4, 3, 5))
-        for name, key in self._VECS:
+        for name, key in self.vecs:
             v = sd[key].detach()
             if name not in keep:
                 keep[name] = torch.zeros(tuple(v.shape), dtype=torch.float32, device=self.device)
@@ -197,14 +215,22 @@ class FusedPolicy(object):
             W.w2[m] = keep[f"w2_{m}"].data_ptr(); W.b1[m] = keep[f"b1_{m}"].data_ptr(); W.b2[m] = keep[f"b2_{m}"].data_ptr()
         for k in ("w_qkv", "w_out", "w_ff1", "w_ff2", "w_o1", "ln1_g", "ln1_b", "b_out", "ln2_g", "ln2_b", "b_ff1", "b_ff2", "b_o1", "w_o2", "b_o2"):
             setattr(W, k, keep[k].data_ptr())
+        if self.n_modal == 4:
+            W.w2_img, W.b2_img = keep["w2_img"].data_ptr(), keep["b2_img"].data_ptr()
 
     def __call__(self, net_in):
         """net_in: float32 lidar (N,120), target (N,5), action_mask (N,42) -> float32 (N,2) policy mean in [-1,1] (buffer reused)"""
         lidar, target, mask = net_in["lidar"], net_in["target"], net_in["action_mask"]
         n = lidar.shape[0]
         assert n <= self.out.shape[0] and all(t.dtype == torch.float32 and t.is_contiguous() for t in (lidar, target, mask))
-        capi.check(self.lib.hope_policy_forward(n, lidar.data_ptr(), target.data_ptr(), mask.data_ptr(), C.byref(self.weights), self.out.data_ptr(),
-                                                torch.cuda.current_stream(self.device).cuda_stream))
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        if self.n_modal == 4:  # net_in["img_mean"]: float32 (N, 128), the image encoder's mean head (module.img_mean_from_conv)
+            mean = net_in["img_mean"]
+            assert mean.dtype == torch.float32 and mean.is_contiguous() and tuple(mean.shape) == (n, 128)
+            capi.check(self.lib.hope_policy_forward_img(n, lidar.data_ptr(), target.data_ptr(), mask.data_ptr(), mean.data_ptr(), C.byref(self.weights),
+                                                        self.out.data_ptr(), stream))
+        else:
+            capi.check(self.lib.hope_policy_forward(n, lidar.data_ptr(), target.data_ptr(), mask.data_ptr(), C.byref(self.weights), self.out.data_ptr(), stream))
         return self.out[:n]
 
 
@@ -322,8 +348,12 @@ class ReferenceShapedActor(nn.Module):
         """forward() with the conv stack of the image encoder already applied: conv_feat (N, 2048) = embed_img.net[0:3](img)
         (FusedImgConv); the image encoder's Linear / tanh / mean head and everything after them run here"""
         feats = [self.embed_lidar(obs["lidar"]), self.embed_tgt(obs["target"]), self.embed_am(obs["action_mask"])]
-        feats.append(self.re_embed_img(self.embed_img.output_mean(self.embed_img.net[3:](conv_feat))))
+        feats.append(self.re_embed_img(self.img_mean_from_conv(conv_feat)))
         return self._from_tokens(feats)
+
+    def img_mean_from_conv(self, conv_feat):
+        """the image encoder after its conv stack: Linear(2048, 256), tanh, mean head -> (N, 128) (what re_embed_img consumes)"""
+        return self.embed_img.output_mean(self.embed_img.net[3:](conv_feat))
 
     def _from_tokens(self, feats):
         x = torch.stack(feats, dim=1)
@@ -379,8 +409,10 @@ class RolloutEngine(object):
         self._graph, self._graph_in, self._graph_out = None, None, None
         self.overlap, self._pol_stream = bool(overlap), None  # collect(store=None): next action computed next to the Reeds-Shepp kernels
         self.use_graph = bool(graph) and self.fused
-        self.policy_kernel = FusedPolicy(policy, env.n, dev) if (policy_kernel and self.fused and not self.use_img and FusedPolicy.supports(policy)) else None
         self.img_conv = FusedImgConv(policy, env.n, dev) if (policy_kernel and self.fused and self.use_img and FusedImgConv.supports(policy)) else None
+        want = 4 if self.use_img else 3   # (a 4-modal network on an env without images is not something the kernel path handles)
+        ok = policy_kernel and self.fused and FusedPolicy.supports(policy) == want and (self.img_conv is not None or not self.use_img)
+        self.policy_kernel = FusedPolicy(policy, env.n, dev) if ok else None
         self.glue = ("hope_state_norm + hope_masked_sample kernels (csrc/policy_glue.cu)" if self.fused else "eager PyTorch") + \
                     (", policy forward = hope_policy_forward (csrc/policy_forward.cu, one kernel)" if self.policy_kernel is not None else
                      (", policy forward replayed from a CUDA graph" if self.use_graph else "")) + \
@@ -388,6 +420,11 @@ class RolloutEngine(object):
         self.obs = env.reset()
         if use_planner:
             env.planner_reset()
+
+    def _img_mean(self, conv_feat):
+        """the image encoder's tail on the conv kernel's features (two small library GEMMs under autocast) -> float32 (N, 128)"""
+        with torch.autocast("cuda", dtype=self.autocast_dtype, enabled=self.autocast_dtype is not None):
+            return self.policy.img_mean_from_conv(conv_feat).float().contiguous()
 
     def _forward(self, net_in):
         with torch.autocast("cuda", dtype=self.autocast_dtype, enabled=self.autocast_dtype is not None):
@@ -405,6 +442,8 @@ class RolloutEngine(object):
     def _policy_mean(self, net_in):
         """float32 policy output for the (persistent) float32 input buffers `net_in`"""
         if self.policy_kernel is not None:
+            if self.policy_kernel.n_modal == 4:
+                net_in["img_mean"] = self._img_mean(net_in["img_feat"])
             return self.policy_kernel(net_in)
         if not self.use_graph:
             return self._forward(net_in)

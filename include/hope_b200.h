@@ -254,9 +254,16 @@ typedef struct hope_policy_weights {
     const float *b1[3], *b2[3];                 /* [128] each, order lidar, target, mask                                         */
     const float *ln1_g, *ln1_b, *b_out, *ln2_g, *ln2_b, *b_ff1, *b_ff2, *b_o1; /* [128] each                                     */
     const float *w_o2, *b_o2;                   /* [2][128], [2]: net.output.2                                                   */
+    const void *w2_img; const float *b2_img;    /* 4-modal network only: packed [128][128] re_embed_img.1.weight, [128] its bias; w_o1 is then packed [128][512] */
 } hope_policy_weights;
 int hope_policy_forward(int n, const float *d_lidar, const float *d_target, const float *d_mask, const hope_policy_weights *w, float *d_out,
                         void *stream);
+/* The 4-modal network (img_shape set, n_modal = 4: what the reference trains with USE_IMG and what its shipped checkpoints hold):
+ * d_img_mean [n][128] float32 = embed_img(img)[0], the image encoder's mean head (conv stack by hope_img_conv_forward, then
+ * Linear(2048, 256) tanh Linear(256, 128)); the kernel applies re_embed_img (tanh, Linear(128, 128)) as token 3 and runs the
+ * 4-token transformer block and the Linear(512, 128) head.  16 envs per CTA. */
+int hope_policy_forward_img(int n, const float *d_lidar, const float *d_target, const float *d_mask, const float *d_img_mean,
+                            const hope_policy_weights *w, float *d_out, void *stream);
 int hope_policy_forward_smem_bytes(void);
 /* HOST helper: float32 weight h_w[n_out][n_in] (PyTorch layout) -> the fragment-packed bf16 matrix hope_policy_forward reads,
  * n_out * k_pad bf16 values (n_out multiple of 8, k_pad >= n_in multiple of 16), round to nearest even:

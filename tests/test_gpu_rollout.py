@@ -379,7 +379,8 @@ def test_rollout_engine_with_images_uses_the_conv_kernel():
     torch.manual_seed(2)
     policy = rollout.ReferenceShapedActor(use_img=True).to(torch.device("cuda", 0)).eval()
     eng = rollout.RolloutEngine(BatchedParkingEnv(n, scenes=sc, auto_reset=True, use_img_observation=True), policy, seed=3)
-    assert eng.img_conv is not None and eng.policy_kernel is None and "hope_img_conv_forward" in eng.glue
+    assert eng.img_conv is not None and eng.policy_kernel is not None and eng.policy_kernel.n_modal == 4
+    assert "hope_img_conv_forward" in eng.glue and "hope_policy_forward" in eng.glue
     ref = rollout.RolloutEngine(BatchedParkingEnv(n, scenes=sc, auto_reset=True, use_img_observation=True), policy, seed=3, policy_kernel=False)
     assert ref.img_conv is None
     a, (mean_a, _) = eng.act(eng.obs)
@@ -390,3 +391,44 @@ def test_rollout_engine_with_images_uses_the_conv_kernel():
     eng.collect(4)
     torch.cuda.synchronize()
     eng.env.close(); ref.env.close()
+
+
+@pytest.mark.parametrize("n", [37, 2048])
+def test_policy_forward_kernel_4_modal_matches_the_float32_module(n):
+    """hope_policy_forward_img (the 4-token network: lidar, target, action mask, image token from the encoder's mean head) against
+    the plain float32 PyTorch forward of the same module, image encoder included (conv kernel -> library GEMMs -> kernel vs
+    cuDNN float32).  Same bar as the 3-modal kernel: no further from float32 than twice PyTorch's bf16 autocast forward + 2e-3."""
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(13)
+    net = rollout.ReferenceShapedActor(use_img=True).to(dev).eval()
+    with torch.no_grad():
+        for name, p in net.named_parameters():
+            if name.endswith("bias") or "norm" in name:
+                p.add_(0.1 * torch.randn_like(p))
+    assert rollout.FusedPolicy.supports(net) == 4
+    obs = {"lidar": torch.randn(n, 120, device=dev), "target": torch.randn(n, 5, device=dev), "action_mask": torch.rand(n, 42, device=dev)}
+    img = torch.randint(0, 256, (n, 3, 64, 64), dtype=torch.uint8, device=dev)
+    obs["img"] = img.float() / 255.0
+    with torch.backends.cudnn.flags(allow_tf32=False), torch.no_grad():
+        ref = net(obs)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            low = net(obs).float()
+    conv, fp = rollout.FusedImgConv(net, n, dev), rollout.FusedPolicy(net, n, dev)
+    assert fp.n_modal == 4
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        mean = net.img_mean_from_conv(conv(img)).float().contiguous()
+    got = fp({**obs, "img_mean": mean}).clone()
+    torch.cuda.synchronize()
+    assert got.shape == (n, 2) and torch.isfinite(got).all() and got.abs().max() <= 1.0
+    err, err_autocast = (got - ref).abs(), (low - ref).abs()
+    print(f"  4-modal: kernel max {err.max():.2e} mean {err.mean():.2e} | autocast max {err_autocast.max():.2e} mean {err_autocast.mean():.2e}")
+    assert err.max() <= 2 * err_autocast.max() + 2e-3 and err.mean() <= 2 * err_autocast.mean() + 5e-4
+    assert err.max() <= 3e-2
+    # the image token matters (the kernel does not ignore it), and refresh() picks up re_embed_img
+    got0 = fp({**obs, "img_mean": torch.zeros_like(mean)}).clone()
+    assert (got0 - got).abs().max() > 1e-3
+    with torch.no_grad():
+        net.re_embed_img[1].bias.add_(0.5)
+        ref2 = net(obs)
+    fp.refresh()
+    assert (fp({**obs, "img_mean": mean}) - ref2).abs().max() <= 3e-2 and (ref2 - ref).abs().max() > 1e-3
