@@ -18,7 +18,8 @@ Timed regions of the main line
   roofline   per-kernel CUDA-event durations of a second, SERIALISED pass over the same steps (every kernel alone on one
              stream): the dominant kernel and its HBM fraction come from these, not from the overlapped live step.
   secondary  BASELINE cfg 4 (PPO acting loop with the transformer policy) and cfg 5 (SAC rollout + update + NCCL gradient
-             all-reduce) on the same envs, a few steps each, with their own clock records.
+             all-reduce) on the same envs, a few steps each, with their own clock records; cfg4_img = cfg 4 as the reference ships
+             it (USE_IMG: image observation rendered every step, 4-modal actor).
 """
 import argparse
 import json
@@ -503,6 +504,13 @@ def main():
         K2, W2 = min(K, 16), 4
         secondary = {"cfg4": measure_rollout(env, rank, local_rank, world, dev, K2, W2),
                      "cfg5": measure_sac(env, rank, local_rank, world, dev, K2, W2)}
+        # cfg 4 as the reference ships it (USE_IMG: 4-modal actor, image observation rendered every step): the same scenes, a
+        # second env with the image stage on
+        env_img = BatchedParkingEnv(n, scenes=scenes, device=local_rank, auto_reset=True, use_img_observation=True)
+        secondary["cfg4_img"] = measure_rollout(env_img, rank, local_rank, world, dev, K2, 22, use_img=True)  # 22 warm-up steps: the trajectory boxes k_render draws are all there
+        secondary["cfg4_img"]["config"]["workload"] = "cfg4 with USE_IMG: k_render + image conv stack kernel + 4-modal actor kernel in the loop"
+        env_img.close()
+        del env_img
 
     if rank == 0:
         ser = {k: (v[0] / v[1] if v[1] else None) for k, v in serial.items()}

@@ -14,21 +14,25 @@
 //   k_render (CTA / env, 256 threads, ~44 KB of shared memory, 5 CTAs per SM; the four quadrants of the image go
 //   through the same window one after the other, set-up and span table are built once):
 //   1. set-up: the screen window the quadrant's 64 x 64 sample lattice can touch (<= 180 x 180 pixels) is kept as
-//      one byte per pixel (the colour index) in shared memory; one thread per shape turns its ring into integer
-//      screen vertices and a scan-conversion record (edges in draw_fillpoly's visiting order); the start-box
-//      outline (draw_line, Bresenham) becomes 5 segment records whose pixel run on any row has a closed form;
-//   2. paint: one thread OWNS one window row and replays the painter's order over the STATIC shapes that cross it
-//      (obstacles, start outline, dest box) — pygame's scan conversion restated literally, plain (non-atomic) word
-//      stores, no inter-thread ordering; each warp first ballots the shapes that touch its 32-row band.
-//      The DYNAMIC shapes (vehicle box + up to 20 trajectory boxes, all stacked around the image centre, where one
-//      row owner would have to scan-convert ~22 of them in sequence) go through a span table first: every
-//      (box, row) pair is one entry, computed by all threads in parallel (2a); the row owners then only replay the
-//      stored runs on top of the static paint (2b).  Two ways of not writing pixels a newer box overwrites anyway
-//      were measured slower than the plain replay (6.2 ms per 65 536 images): newest-first with a covered interval
-//      (8.8 ms: rows whose runs do not merge into one interval are common) and oldest-first writing only what the
-//      successor's run leaves uncovered (7.0 ms: the extra branches cost more than the stores they save);
-//   3. gather: each thread resolves output pixels = 4 window bytes -> palette -> (sum + 2) >> 2 and stores them as
-//      uint8 [3][64][64], a warp writing one 32-byte sector per channel (the reference's float64 image is this / 255).
+//      one byte per pixel in shared memory; one thread per shape turns its ring into integer screen vertices and a
+//      scan-conversion record (edges in draw_fillpoly's visiting order); the start-box outline (draw_line, Bresenham)
+//      becomes 5 segment records whose pixel run on any row has a closed form.  Every KIND of shape is prepared by a warp of
+//      its own (the branches run side by side), through ONE copy of the float64 set-up code;
+//   2. paint, order-free: _render's painter's order is the order of increasing colour index, so "the later shape wins" is a
+//      per-pixel MAXIMUM.  A window byte holds a thermometer code of the colour index (colour_code / traj_code below) and
+//      spans are OR-ed in with shared-memory atomics: OR of thermometer codes = maximum, whichever thread paints whichever
+//      (shape, row) pair first.  Every such pair is one work item — pygame's scan conversion restated literally per row —
+//      and the items are dealt round all 256 threads (static shapes: by a running row offset; vehicle + trajectory boxes:
+//      from a span table built once per image, 2a).  A byte has room for 8 thermometer levels and there are 25 colours: the
+//      20 trajectory colours share one level plus a 3-bit thermometer of their GROUP of 5; the gather finds the newest box
+//      of the newest group that covers the sample in the span table (at most 4 look-ups).
+//      (Round 1 let one thread OWN one window row and replay the painter's order on it: the rows through the image centre
+//      carry ~22 boxes, the others none, and half of all warp samples sat at the paint -> gather barrier; 6.5 ms per 65 536
+//      images against 4.9 ms now.  The first order-free build was SLOWER (11 ms): 16.7 k SASS instructions, a third of
+//      the stall samples "no instruction" — the L1.5 instruction cache holds 32 KB.  Out-of-line cold paths and the shared
+//      set-up code brought it to 4.0 k instructions.)
+//   3. gather: each thread resolves output pixels = 4 window bytes -> colour index -> palette -> (sum + 2) >> 2 and stores them
+//      as uint8 [3][64][64], a warp writing one 32-byte sector per channel (the reference's float64 image is this / 255).
 // HBM traffic per env-step: 12 288 B written + ~1.3 KB read (scene ring vertices, trajectory ring buffer; the other
 // three quadrants hit L2).
 #pragma once
