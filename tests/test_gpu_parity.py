@@ -254,13 +254,13 @@ def test_host_buffer_api_matches_device_api(n, wire, monkeypatch):
     for _ in range(5):
         act = rng.uniform(-1, 1, size=(n, 2))
         a.step(torch.as_tensor(act, device=a.device).contiguous())
-        h = b.step_host(act)
+        h = b.step_host(act, outputs=BatchedParkingEnv.HOST_DEFAULT + ("mask_steps",))
         d = gather(a)
-        for k in ("lidar", "mask", "target", "reward", "status", "done", "reward_info", "rs_found", "rs_nseg", "rs_types", "rs_lengths"):
+        for k in ("lidar", "mask", "mask_steps", "target", "reward", "status", "done", "reward_info", "rs_found", "rs_nseg", "rs_types", "rs_lengths"):
             x, y = np.ascontiguousarray(d[k]), np.ascontiguousarray(h[k])
             assert x.dtype == y.dtype and np.array_equal(x.view(np.uint8), y.view(np.uint8)), k
     w = b.host_wire_info()
-    plain_bytes = n * (120 * 8 + 42 * 8 + 5 * 8 + 8 + 4 + 1 + 5 * 8 + 1 + 1 + 5 + 5 * 8)
+    plain_bytes = n * (120 * 8 + 42 * 8 + 42 + 5 * 8 + 8 + 4 + 1 + 5 * 8 + 1 + 1 + 5 + 5 * 8)
     assert w["lidar_packed"] == (wire != "plain") and w["mask_narrow"] == (wire != "plain") and w["h2d_bytes"] == 16 * n
     if wire == "plain":
         assert w["d2h_bytes"] == plain_bytes
