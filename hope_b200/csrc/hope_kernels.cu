@@ -515,6 +515,9 @@ struct hope_ctx {
     int *d_traj_n = nullptr;
     render::Palette palette;
     render::Camera *d_cams = nullptr;
+    uint8_t *d_screen = nullptr;      // [N][500][125]: the static part of every env's screen, 2 bits per pixel (k_render_static), allocated with the first image
+    uint2 *d_screen_key = nullptr;
+    int render_force_lattice = 0;     // HOPE_B200_RENDER_LATTICE=1 (tests): k_render resolves the dynamic layer per lattice sample even when its window fits    // [N]: (pool slot, its regeneration count) the cached screen was painted for; all ones = none
     double *d_plan_rem = nullptr;
     uint8_t *d_plan_u8 = nullptr;  // types[N][5] | big[N] | n[N] | seg[N] | active[N]
     int sm_count = 148, walk_blocks = 148 * 4, check_blocks = 148 * 4, host_check_blocks = 148 * 4;
@@ -795,7 +798,9 @@ int launch_range(hope_ctx *ctx, const double *d_action, const hope_out &out_all,
             prof_mark(ctx, 6, so);
             render::Camera *cams = ctx->d_cams + lo;
             k_render_camera<<<(n + 127) / 128, 128, 0, so>>>(n, pool, st, ctx->par, cams);
-            k_render<<<n, render::THREADS, sizeof(render::Smem), so>>>(n, pool, st, cams, ctx->par, ctx->palette, out.img);
+            uint8_t *screen = ctx->d_screen + (size_t)lo * render::SCREEN_BYTES;
+            k_render_static<<<n, render::THREADS, sizeof(render::Smem), so>>>(n, pool, st, ctx->d_episode, cams, ctx->par, screen, ctx->d_screen_key + lo);
+            k_render<<<n, render::THREADS, sizeof(render::SmemDyn), so>>>(n, st, cams, ctx->par, ctx->palette, screen, out.img, ctx->render_force_lattice);
             ctx->launches++;
             prof_mark(ctx, 6, so);
             ctx->launches++;
@@ -833,7 +838,9 @@ int launch_range(hope_ctx *ctx, const double *d_action, const hope_out &out_all,
         prof_mark(ctx, 6, s);
         render::Camera *cams = ctx->d_cams + lo;
         k_render_camera<<<(n + 127) / 128, 128, 0, s>>>(n, pool, st, ctx->par, cams);
-        k_render<<<n, render::THREADS, sizeof(render::Smem), s>>>(n, pool, st, cams, ctx->par, ctx->palette, out.img);
+        uint8_t *screen = ctx->d_screen + (size_t)lo * render::SCREEN_BYTES;
+        k_render_static<<<n, render::THREADS, sizeof(render::Smem), s>>>(n, pool, st, ctx->d_episode, cams, ctx->par, screen, ctx->d_screen_key + lo);
+        k_render<<<n, render::THREADS, sizeof(render::SmemDyn), s>>>(n, st, cams, ctx->par, ctx->palette, screen, out.img, ctx->render_force_lattice);
         prof_mark(ctx, 6, s);
         ctx->launches += 2;
     }
@@ -858,8 +865,27 @@ int join_device_calls(hope_ctx *ctx, cudaStream_t s) {
     return HOPE_OK;
 }
 
+// the static-screen cache of the image stage (62.5 KB per env), with the first image; never inside a stream capture
+int ensure_screen(hope_ctx *ctx) {
+    if (ctx->d_screen) return HOPE_OK;
+    CK(cudaMalloc(&ctx->d_screen, (size_t)ctx->n * render::SCREEN_BYTES));
+    CK(cudaMalloc(&ctx->d_screen_key, sizeof(uint2) * (size_t)ctx->n));
+    CK(cudaMemset(ctx->d_screen_key, 0xff, sizeof(uint2) * (size_t)ctx->n));
+    CK(cudaDeviceSynchronize());  // the steps run on non-blocking streams, which do not order after the memset
+    return HOPE_OK;
+}
+// the scene pool changed under the cached screens
+int invalidate_screens(hope_ctx *ctx) {
+    if (!ctx->d_screen_key) return HOPE_OK;
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemset(ctx->d_screen_key, 0xff, sizeof(uint2) * (size_t)ctx->n));
+    CK(cudaDeviceSynchronize());
+    return HOPE_OK;
+}
+
 // staging buffers of the host API; the image (12 KB per env) only when a caller asks for it
 int ensure_stage(hope_ctx *ctx, bool want_img) {
+    if (want_img) { const int rcs = ensure_screen(ctx); if (rcs) return rcs; }
     if (want_img && !ctx->d_stage_img) {
         CK(cudaMalloc(&ctx->d_stage_img, (size_t)ctx->n * HOPE_IMG_C * HOPE_IMG_HW * HOPE_IMG_HW));
         ctx->stage_out.img = static_cast<uint8_t *>(ctx->d_stage_img);
@@ -1028,10 +1054,12 @@ int hope_create(hope_ctx **out, int device, int n_envs, int pool_size, const hop
     if (const char *e = getenv("HOPE_B200_HOST_TRACE")) ctx->host_trace = atoi(e);
     if (const char *e = getenv("HOPE_B200_HOST_SPLIT")) ctx->host_split = e;
     if (const char *e = getenv("HOPE_B200_HOST_DEBUG")) ctx->host_debug = atoi(e);
+    if (const char *e = getenv("HOPE_B200_RENDER_LATTICE")) ctx->render_force_lattice = atoi(e) != 0;
     if (const char *e = getenv("HOPE_B200_HOST_RS_AFTER")) ctx->host_rs_after_observe = atoi(e) != 0;
     if (const char *e = getenv("HOPE_B200_HOST_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->host_chunks = v; }
     CK(cudaFuncSetAttribute(k_observe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((OBS_THREADS / 32) * sizeof(ObserveSmem))));
-    CK(cudaFuncSetAttribute(k_render, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(render::Smem)));
+    CK(cudaFuncSetAttribute(k_render_static, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(render::Smem)));
+    CK(cudaFuncSetAttribute(k_render, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(render::SmemDyn)));
     {   // a vehicle-sized box covers at most diagonal * K + 2 screen rows after truncation
         double diag = 0.0;
         for (int a = 0; a < 4; ++a)
@@ -1056,7 +1084,7 @@ int hope_destroy(hope_ctx *ctx) {
     cudaSetDevice(ctx->device);
     void *ptrs[] = {ctx->d_obs, ctx->d_aabb, ctx->d_meta, ctx->d_nv, ctx->d_nobs, ctx->d_tab, ctx->d_pose, ctx->d_accum, ctx->d_t,
                     ctx->d_scene, ctx->d_pending, ctx->d_gate, ctx->d_counters, ctx->d_words, ctx->d_ntry, ctx->d_ncand, ctx->d_cs, ctx->d_item_base, ctx->d_items, ctx->d_item_bad, ctx->d_slots, ctx->d_n_items, ctx->d_plan_rem, ctx->d_plan_u8, ctx->d_regen_slots, ctx->d_regen_count, ctx->d_gen_status, ctx->d_episode,
-                    ctx->d_action, ctx->d_stage, ctx->d_stage_img, ctx->d_traj, ctx->d_traj_n, ctx->d_cams};
+                    ctx->d_action, ctx->d_stage, ctx->d_stage_img, ctx->d_traj, ctx->d_traj_n, ctx->d_cams, ctx->d_screen, ctx->d_screen_key};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->host_graph) cudaGraphExecDestroy(ctx->host_graph);
@@ -1171,7 +1199,7 @@ int hope_set_scene_pool(hope_ctx *ctx, int first, int n, const double *start, co
     CK(cudaMemcpy(ctx->d_nv + (size_t)first * MAXO, nv.data(), nv.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_nobs + first, nobs.data(), nobs.size() * sizeof(int), cudaMemcpyHostToDevice));
     ctx->have_scenes = true;
-    return HOPE_OK;
+    return invalidate_screens(ctx);
 }
 
 int hope_generate_scene_pool_device(hope_ctx *ctx, int first, int n, int level, uint64_t seed, void *stream) {
@@ -1181,7 +1209,7 @@ int hope_generate_scene_pool_device(hope_ctx *ctx, int first, int n, int level, 
                                     ctx->d_gen_status, stream) != HOPE_OK) return fail(ctx, cudaGetLastError(), "k_generate_scenes");
     ctx->launches++;
     ctx->have_scenes = true;
-    return HOPE_OK;
+    return invalidate_screens(ctx);
 }
 
 int hope_get_scene_pool(hope_ctx *ctx, int first, int n, double *h_start, double *h_dest, double *h_bounds, double *h_obs_xy, int32_t *h_nverts) {
@@ -1219,6 +1247,7 @@ int hope_reset(hope_ctx *ctx, const int32_t *h_scene_ids, const hope_out *d_out,
     CK(cudaMemcpyAsync(ctx->d_scene, ids.data(), sizeof(int) * ctx->n, cudaMemcpyHostToDevice, s));
     CK(cudaStreamSynchronize(s));  // ids is a local buffer
     ctx->have_reset = true;
+    if (d_out->img) { const int rcs = ensure_screen(ctx); if (rcs) return rcs; }
     // the reset step computes the observation; RS is gated off by t > 1 (car_parking_base.py:293)
     int rc = launch_step(ctx, nullptr, *d_out, HOPE_STAGE_ADVANCE | HOPE_STAGE_OBSERVE | HOPE_STAGE_RS | HOPE_STAGE_IMAGE, 1, s);
     if (rc) return rc;
@@ -1232,6 +1261,7 @@ int hope_step(hope_ctx *ctx, const double *d_action, const hope_out *d_out, unsi
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     stages |= HOPE_STAGE_ADVANCE;
+    if ((stages & HOPE_STAGE_IMAGE) && d_out->img) { const int rcs = ensure_screen(ctx); if (rcs) return rcs; }
     ctx->obs_done_valid = false;
     const int n = ctx->n;
     int chunks = ctx->device_chunks;

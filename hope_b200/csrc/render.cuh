@@ -44,13 +44,7 @@ constexpr int OBS = 256;          // configs.py:89-90 OBS_W, OBS_H
 constexpr int IMG = 64;           // OBS / downsample_rate (observation_processor.py:8)
 constexpr int KSCALE = 12;        // configs.py:103 K
 constexpr int TRAJ = 20;          // configs.py:86 TRAJ_RENDER_LEN
-constexpr int QUAD = 32;          // output pixels per quadrant side (4 quadrants of the 64 x 64 image)
-constexpr int PITCHW = 47;        // window words per row (188 pixels >= 125 sqrt(2) + 2 + alignment); odd, so the rows
-                                  // owned by adjacent lanes start in different banks
-constexpr int PITCH = PITCHW * 4;
-constexpr int ROWS = 180;
 constexpr int THREADS = 256;
-constexpr int MAXSHAPES = MAXO + 3 + TRAJ;
 constexpr int NDYN = 1 + TRAJ;    // vehicle box + trajectory boxes
 constexpr int DROWS = 64;         // screen rows a vehicle-sized box can span: its diagonal is 5.07 m * K = 60.9 pixels
 constexpr int NCOLOR = 5 + TRAJ;  // 0 background, 1 obstacle, 2 start outline, 3 dest, 4 vehicle, 5.. trajectory old -> new
@@ -63,7 +57,7 @@ static_assert((TRAJ + TGROUP - 1) / TGROUP - 1 <= 3, "group thermometer: 3 bits"
 constexpr unsigned CODE_DYN = 0x10u;    // bit 4: a trajectory box covers the pixel
 __host__ __device__ constexpr unsigned colour_code(int index) { return (1u << index) - 1u; }                                      // index 1..4
 __host__ __device__ constexpr unsigned traj_code(int i) { return 0x1fu | (((1u << (i / TGROUP)) - 1u) << 5); }                    // i = 0 oldest
-static_assert(TRAJ <= 32 && THREADS >= ROWS + 1 && MAXSHAPES <= THREADS - 2 - NCOLOR, "row owners + the probe thread; shape threads, palette threads and the camera thread are disjoint");
+static_assert(TRAJ <= 32 && MAXO + 2 <= THREADS && 33 <= THREADS - 2 - NCOLOR, "one thread per dynamic box; shape threads, palette threads and the camera thread are disjoint");
 
 struct Palette { uint32_t rg[NCOLOR], b[NCOLOR]; };  // R | G << 16 and B: 16-bit lanes so four samples add without carry
 
@@ -78,9 +72,6 @@ struct Camera {
     double kbx, kby;       // coord_transform_matrix offsets
     int ulo, uhi, vlo, vhi;  // crop pixels that land on the rotated screen copy at all (the rest reads as background)
 };
-// what k_render derives per image quadrant: the screen window (inclusive, wx0 aligned to 4) its sample lattice can
-// touch, and fast = 1 when every sample of the quadrant maps inside the screen (no per-sample checks)
-struct QuadWindow { int wx0, wy0, wx1, wy1, fast; };
 static_assert(sizeof(Camera) == 96, "one Camera per env in HBM");
 
 struct Edge { short ylo, yhi, xlo, dx; int dy; float rdy; };  // non-horizontal edge, lower end first: x(y) = xlo + (y - ylo) dx / dy
@@ -96,18 +87,53 @@ struct Shape {   // one ring prepared for draw_fillpoly
 // 2: x-major Bresenham, 3: y-major Bresenham (dx <= dy)
 struct Seg { short ylo, yhi, x1, y1, xa, xb, dx, dy, sx, sy, err0, kind; float rdy; };
 
-struct Smem {
-    Camera cam;
-    QuadWindow quad[4];
-    Shape shapes[MAXSHAPES];
-    int nshapes;
-    uint32_t probe;                     // screen pixel (0, 0) in byte 0: rotate()'s background colour index
-    int nstatic;                        // shapes [0, nstatic) are painted, [nstatic, nshapes) are the dynamic boxes, old -> new
+// The static part of the screen (obstacles, start outline, dest box) does not change during an episode: k_render_static paints
+// it ONCE per (env, scene) into HBM as 2 bits per pixel (the colour index 0..3), 128 bytes per screen row (500 pixels + padding, so
+// that every row and every 16-byte chunk of it is aligned for bulk copies): 64 000 bytes per env.  k_render stages the rows its
+// sample lattice can touch into shared memory (cp.async.bulk, one copy per row, one mbarrier) and reads the pixels from there.
+constexpr int SCREEN_PITCH = 128;                  // bytes per screen row
+constexpr int SCREEN_BYTES = WIN * SCREEN_PITCH;   // per env
+constexpr int TROWS = 100;                         // screen rows per shared-memory tile of k_render_static
+constexpr int TPITCHW = SCREEN_PITCH;              // words per tile row: one thermometer byte per pixel while painting, 512 pixels
+constexpr int TILEW = TROWS * TPITCHW;             // words per tile
+static_assert(WIN <= 4 * SCREEN_PITCH && SCREEN_PITCH % 16 == 0 && WIN % TROWS == 0, "padded rows, whole tiles");
+
+struct Smem {                           // k_render_static
+    Shape shapes[MAXO + 2];             // obstacles, start outline, dest box: the painter's order
     Seg seg[5];
-    uint2 pal[NCOLOR];                  // (R | G << 16, B)
-    short2 drange[NDYN];                // (miny, maxy) of dynamic box d: what the gather needs of its Shape
+    int nstatic;
+    alignas(16) uint32_t tile[TILEW];
+};
+
+// k_render's sample lattice: cv2's 4x INTER_LINEAR reads crop pixels 4i+1, 4i+2 of either axis = 128 x 128 samples,
+// lattice index a <-> crop pixel 2a + 1 - (a & 1)
+constexpr int LAT = 2 * IMG;
+constexpr int WROWS = 360;              // screen rows the lattice can touch: 253 sqrt(2) (1 + 2^-15) + 2 <= 360
+constexpr int DWORDS = 6144;            // capacity of the dynamic layer's screen window, 8 pixels per word (e.g. 192 rows x 256 pixels)
+constexpr unsigned CODE_VEHICLE = 15u;  // nibble codes of the dynamic layer: 0 none, 1 + t % 14 trajectory box t (old -> new), 15 vehicle
+constexpr int CODE_MOD = 14;
+constexpr int WCHUNK = 7;               // 16-byte chunks (64 pixels) per staged row: 361 pixels straddle at most 7
+constexpr int WPITCH = WCHUNK * 16;
+
+struct SmemDyn {                        // k_render
+    Camera cam;
+    int fast;                           // every sample of the image maps inside the screen: no per-sample checks
+    int ndyn;
+    uint32_t probe;                     // palette index of screen pixel (0, 0): rotate()'s background colour
+    int wy0, nrows, cb0, nch;           // staged window: screen rows [wy0, wy0 + nrows), 16-byte chunks [cb0, cb0 + nch) of each
+    alignas(8) unsigned long long bar;  // mbarrier of the staging copies
+    alignas(16) Shape shapes[NDYN];     // vehicle box (0), trajectory boxes old -> new (1 ..)
+    short2 drange[NDYN];                // (miny, maxy) of dynamic box d
+    uchar4 lbox[NDYN];                  // lattice columns [x, y] and rows [z, w] the box can cover (x > y: none)
+    uint32_t pal[NCOLOR];               // R | G << 10 | B << 20: four samples add without carry
     short2 dyn[NDYN][DROWS];            // span of dynamic box d on screen row miny_d + r; x > y: nothing; x == DYN_DIRECT: evaluate
-    alignas(16) uint32_t win[ROWS * PITCHW + 5];   // + gather slack, rounded to whole uint4 for the clear
+    int dx0, dy0, dnw, dnr;             // dynamic layer as a screen window: rows [dy0, dy0 + dnr), pixels [dx0, dx0 + 8 dnw), dx0 % 8 == 0
+    int lattice_mode;                   // the window would not fit: the layer is resolved per lattice sample instead (didx)
+    union {
+        alignas(16) uint32_t dwin[DWORDS];   // window mode: one nibble per screen pixel, the code of the newest box painted there
+        alignas(16) uint8_t didx[LAT][LAT];  // lattice mode: palette index of the newest dynamic box on the sample, 0: none
+    };
+    alignas(16) uint8_t swin[WROWS * WPITCH];  // the static screen rows, 2 bits per pixel
 };
 
 // _coord_transform + pygame's (int) conversion of one world point
@@ -290,7 +316,6 @@ __device__ __noinline__ void paint_shape_row(const Smem &sm, const Shape &S, int
     }
 }
 
-static_assert(MAXO != 16 || sizeof(Smem) <= 44400, "5 CTAs per SM (227 KB, 1 KB reserved per CTA)");
 
 }  // namespace render
 
@@ -359,107 +384,57 @@ __global__ void __launch_bounds__(128) k_render_camera(int n, Pool pool, EnvStat
     cams[env] = c;
 }
 
-// One CTA per env.  Set-up and the span table of the dynamic boxes are built once, then the four image quadrants are
-// painted and gathered one after the other through the same shared-memory window.
-// traj: [N][20][4] ring buffer (x, y, cos h, sin h) of Vehicle.trajectory's tail, traj_n: [N] its length (see k_advance)
-__global__ void __launch_bounds__(render::THREADS, 5)
-k_render(int n, Pool pool, EnvState st, const render::Camera *__restrict__ cams, hope_params par, render::Palette pal,
-         uint8_t *__restrict__ img) {
+// One CTA per env, every step; returns at once unless the env's scene changed since its static screen was painted (key = pool slot +
+// the slot's regeneration count).  Paints obstacles, start outline and dest box tile by tile (100 screen rows of thermometer bytes
+// in shared memory, every (shape, row) pair one work item, spans OR-ed in) and stores the tile as 2 bits per pixel.
+__global__ void __launch_bounds__(render::THREADS)
+k_render_static(int n, Pool pool, EnvState st, const unsigned *__restrict__ episode, const render::Camera *__restrict__ cams, hope_params par,
+                uint8_t *__restrict__ screen, uint2 *__restrict__ keys) {
     using namespace render;
+    const int env = blockIdx.x;
+    const int sid = st.scene[env];
+    const unsigned ep = episode ? episode[sid] : 0u;
+    {
+        const uint2 key = keys[env];
+        if (key.x == (unsigned)sid && key.y == ep) return;
+    }
     extern __shared__ __align__(16) unsigned char render_smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(render_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
-    const int env = blockIdx.x;
-    const int sid = st.scene[env];
     const double *meta = pool.meta + (size_t)sid * META;
-    // ---------------------------------------------------------------- 1. set-up, one phase: camera + the four windows
-    // (one otherwise idle thread), shapes (one thread each; they only need the two screen offsets), palette
-    if (tid == THREADS - 2) {
-        Camera c = cams[env];
-        // crop pixels inside the 500 x 500 blit target AND inside the rotated copy (both axis-aligned in u, v)
-        c.ulo = max(-c.rx0, -c.cx0); c.uhi = min(WIN - 1 - c.rx0, c.nx - 1 - c.cx0);
-        c.vlo = max(-c.ry0, -c.cy0); c.vhi = min(WIN - 1 - c.ry0, c.ny - 1 - c.cy0);
-        sm.cam = c;
-        const int fmax_ = (WIN << 16) - 1;
-        for (int quad = 0; quad < 4; ++quad) {
-            const int u0 = (quad & 1) * (OBS / 2), v0 = (quad >> 1) * (OBS / 2);
-            // screen window touched by the sample lattice u, v in {4i+1, 4i+2} of this quadrant: the map is affine, so
-            // the corners bound it
-            int fx0 = 0x7fffffff, fx1 = -0x7fffffff - 1, fy0 = 0x7fffffff, fy1 = -0x7fffffff - 1;
-            for (int k = 0; k < 4; ++k) {
-                const int xc = u0 + ((k & 1) ? OBS / 2 - 2 : 1) + c.cx0, yc = v0 + ((k & 2) ? OBS / 2 - 2 : 1) + c.cy0;
-                const int fx = c.a0 + c.a1 * xc + c.a2 * yc, fy = c.b0 + c.b1 * xc + c.b2 * yc;
-                fx0 = min(fx0, fx); fx1 = max(fx1, fx); fy0 = min(fy0, fy); fy1 = max(fy1, fy);
-            }
-            QuadWindow w;
-            w.wx0 = min(max(fx0 >> 16, 0), WIN - 1) & ~3; w.wx1 = min(min(max(fx1 >> 16, 0), WIN - 1), w.wx0 + PITCH - 1);
-            w.wy0 = min(max(fy0 >> 16, 0), WIN - 1); w.wy1 = min(min(max(fy1 >> 16, 0), WIN - 1), w.wy0 + ROWS - 1);
-            w.fast = (u0 + 1 >= c.ulo && u0 + OBS / 2 - 2 <= c.uhi && v0 + 1 >= c.vlo && v0 + OBS / 2 - 2 <= c.vhi &&
-                      fx0 >= 0 && fy0 >= 0 && fx1 <= fmax_ && fy1 <= fmax_) ? 1 : 0;
-            sm.quad[quad] = w;
-        }
-        sm.probe = 0u;
-    }
-    if (tid >= THREADS - 2 - NCOLOR && tid < THREADS - 2) sm.pal[tid - (THREADS - 2 - NCOLOR)] = make_uint2(pal.rg[tid - (THREADS - 2 - NCOLOR)], pal.b[tid - (THREADS - 2 - NCOLOR)]);
-    {
-        const int nobs = pool.nobs[sid];
-        const int tn = st.traj_n[env];
-        const int ntraj = tn > 1 ? min(tn, TRAJ) : 0;
-        const int total = nobs + 3 + ntraj;
-        if (tid == 0) { sm.nshapes = total; sm.nstatic = nobs + 2; }
-        // which shape this thread prepares.  With <= 32 obstacles every KIND of shape gets a warp of its own (obstacles, trajectory
-        // boxes, start, dest, vehicle): the five branches below then run side by side on the SM's schedulers instead of one after
-        // the other inside warp 0, and this phase, which the other warps sit out at the barrier, is as long as its longest branch
-        int s = tid < total ? tid : -1;
+    const int nobs = pool.nobs[sid];
+    {   // one thread per shape; start and dest in warps of their own next to the obstacles' (when those fit one warp)
+        int s = tid < nobs + 2 ? tid : -1;
         if constexpr (MAXO <= 32) {
             const int w = tid >> 5;
             s = -1;
             if (w == 0) { if (lane < nobs) s = lane; }
-            else if (w == 1) { if (lane < ntraj) s = nobs + 3 + lane; }
-            else if (w <= 4 && lane == 0) s = nobs + (w - 2);
+            else if (w <= 2 && lane == 0) s = nobs + (w - 1);
         }
+        if (tid == 0) sm.nstatic = nobs + 2;
         if (s >= 0) {
             Shape &S = sm.shapes[s];
             double bx[4], by[4];
             Camera cam;  // only the screen offsets are read here
             cam.kbx = cams[env].kbx; cam.kby = cams[env].kby;
-            // the branches only fetch what describes the shape; the box corners, the scan-conversion record and the outline
-            // segments are built once below (one copy of that code in the instruction cache, no divergence inside it)
             int nv = 4, code, outline = 0;
-            bool is_box = true, skip = false;
-            double x = 0.0, y = 0.0, c = 1.0, sn = 0.0;
             if (s < nobs) {  // :303-305 obstacles
                 nv = pool.nv[(size_t)sid * MAXO + s];
                 const double2 *v = reinterpret_cast<const double2 *>(pool.obs) + ((size_t)sid * MAXO + s) * MAXV;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) if (k < nv) { const double2 p = __ldg(v + k); bx[k] = p.x; by[k] = p.y; }
-                code = (int)colour_code(1); is_box = false;
+                code = (int)colour_code(1);
             } else if (s == nobs) {  // :307-308 start box, width = 1: lines(closed=True) over the 5 coordinates
+                double sn, c;
                 sincos(meta[M_START + 2], &sn, &c);
-                x = meta[M_START]; y = meta[M_START + 1];
+                vehicle_box(meta[M_START], meta[M_START + 1], c, sn, par.box_x, par.box_y, bx, by);
                 code = (int)colour_code(2); outline = 1;
-            } else if (s == nobs + 1) {  // :309-310 dest box
+            } else {  // :309-310 dest box
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { bx[k] = meta[M_DBX + k]; by[k] = meta[M_DBY + k]; }
-                code = (int)colour_code(3); is_box = false;
-            } else if (s == nobs + 2) {  // :312-313 vehicle
-                x = st.pose[3 * env]; y = st.pose[3 * env + 1]; c = st.cs[2 * env]; sn = st.cs[2 * env + 1];
-                code = (int)colour_code(4);
-                if (ntraj > 0) {  // the newest trajectory box is painted later over the very same pixels: skip this one
-                    const double2 *p = reinterpret_cast<const double2 *>(st.traj) + ((size_t)env * TRAJ + (tn - 1) % TRAJ) * 2;
-                    const double2 xy = p[0], cs = p[1];
-                    skip = xy.x == x && xy.y == y && cs.x == c && cs.y == sn;
-                }
-            } else {  // :315-319 trajectory[-(ntraj - i)], colour TRAJ_COLORS[-(ntraj - i)]
-                const int i = s - (nobs + 3), back = ntraj - i;  // back = 1: newest
-                const double2 *p = reinterpret_cast<const double2 *>(st.traj) + ((size_t)env * TRAJ + (tn - back) % TRAJ) * 2;
-                const double2 xy = p[0], cs = p[1];
-                x = xy.x; y = xy.y; c = cs.x; sn = cs.y;
-                code = (int)traj_code(i);  // palette index 5 + TRAJ - back
+                code = (int)colour_code(3);
             }
-            if (is_box) vehicle_box(x, y, c, sn, par.box_x, par.box_y, bx, by);
             ring_shape(S, cam, bx, by, nv, code, outline);
-            if (skip) { S.miny = 1; S.maxy = 0; }
             if (outline) {
                 int px[4], py[4];
 #pragma unroll
@@ -470,29 +445,235 @@ k_render(int n, Pool pool, EnvState st, const render::Camera *__restrict__ cams,
                     make_seg(sm.seg[k], px[k0], py[k0], px[k1], py[k1]);
                 }
             }
-            if (s >= nobs + 2) sm.drange[s - (nobs + 2)] = make_short2(S.miny, S.maxy);
+        }
+    }
+    __syncthreads();
+    const int nstatic = sm.nstatic;
+    uint32_t *dst = reinterpret_cast<uint32_t *>(screen + (size_t)env * SCREEN_BYTES);
+#pragma unroll 1
+    for (int t = 0; t < WIN / TROWS; ++t) {
+        const int ty0 = t * TROWS, ty1 = ty0 + TROWS - 1;
+        for (int k = tid; k < TILEW / 4; k += THREADS) reinterpret_cast<uint4 *>(sm.tile)[k] = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+        int first = 0;  // rows handed out so far (mod 256): shape after shape the items go round the threads
+        for (int sb = 0; sb < nstatic; sb += 32) {  // each lane tests one shape against the tile, the warp walks the hits
+            bool touch = false;
+            if (sb + lane < nstatic) {
+                const Shape &S = sm.shapes[sb + lane];
+                touch = S.maxy >= ty0 && S.miny <= ty1 && S.maxx >= 0 && S.minx <= WIN - 1;
+            }
+            unsigned m = __ballot_sync(HOPE_FULL_MASK, touch);
+            while (m) {
+                const int s = sb + __ffs(m) - 1;
+                m &= m - 1;
+                const Shape &S = sm.shapes[s];
+                const int lo = max((int)S.miny, ty0), cnt = min((int)S.maxy, ty1) - lo + 1;
+                const int tt = (tid - first) & (THREADS - 1);
+                first += cnt;
+                if (tt < cnt) paint_shape_row(sm, S, lo + tt, sm.tile + (lo + tt - ty0) * TPITCHW, 0, 0, WIN - 1);
+            }
+        }
+        __syncthreads();
+        // thermometer bytes (0, 1, 3, 7) -> 2-bit colour indices, 16 pixels per stored word
+        for (int k = tid; k < TILEW / 4; k += THREADS) {
+            const uint4 w4 = reinterpret_cast<const uint4 *>(sm.tile)[k];
+            const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
+            uint32_t o = 0u;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t l = (ws[q] & 0x01010101u) + ((ws[q] >> 1) & 0x01010101u) + ((ws[q] >> 2) & 0x01010101u);  // per byte: 0..3
+                o |= ((l & 3u) | ((l >> 6) & 0xcu) | ((l >> 12) & 0x30u) | ((l >> 18) & 0xc0u)) << (8 * q);
+            }
+            dst[t * (TILEW / 4) + k] = o;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) keys[env] = make_uint2((unsigned)sid, ep);
+}
+
+// One CTA per env.
+//   1. set-up: the camera thread derives the screen window the 128 x 128 sample lattice can touch; one thread per dynamic box
+//      (vehicle + the last <= 20 trajectory boxes) prepares its scan-conversion record and the lattice rectangle it can cover;
+//   2. the window's rows of the cached static screen are requested into shared memory (cp.async.bulk, one copy per row, completion
+//      counted by one mbarrier) and arrive under steps 3 and 4;
+//   3. span table: what each dynamic box paints on each of its screen rows, one (box, row) pair per thread and pass;
+//   4. dynamic layer in LATTICE space: newest box first, every thread tests ITS samples (lattice row % 8 = warp, column % 32 = lane: a
+//      sample always belongs to the same thread, so program order replaces barriers) of the box's lattice rectangle against the span
+//      table and records the box's palette index where nothing newer did;
+//   5. gather: an output pixel = 4 samples; a sample = its dynamic index if any, else the 2-bit static pixel of the staged window;
+//      palette sums in one packed word, rounded mean, uint8 [3][64][64] with a warp writing whole 32-byte sectors.
+// traj: [N][20][4] ring buffer (x, y, cos h, sin h) of Vehicle.trajectory's tail, traj_n: [N] its length (see k_advance)
+__global__ void __launch_bounds__(render::THREADS, 3)
+k_render(int n, EnvState st, const render::Camera *__restrict__ cams, hope_params par, render::Palette pal, const uint8_t *__restrict__ screen,
+         uint8_t *__restrict__ img, int force_lattice) {
+    using namespace render;
+    extern __shared__ __align__(16) unsigned char render_smem_raw[];
+    SmemDyn &sm = *reinterpret_cast<SmemDyn *>(render_smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int env = blockIdx.x;
+    const uint8_t *scr = screen + (size_t)env * SCREEN_BYTES;
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&sm.bar);
+    // ---------------------------------------------------------------- 1. set-up
+    static_assert(offsetof(SmemDyn, dwin) % 16 == 0 && offsetof(SmemDyn, swin) % 16 == 0 && DWORDS % (4 * THREADS) == 0 && DWORDS * 4 >= LAT * LAT,
+                  "cleared as uint4; bulk copy targets; didx fits");
+    static_assert(sizeof(SmemDyn) <= 74 * 1024, "3 CTAs per SM (227 KB, 1 KB reserved per CTA)");
+#pragma unroll
+    for (int k = 0; k < DWORDS / (4 * THREADS); ++k) reinterpret_cast<uint4 *>(sm.dwin)[tid + k * THREADS] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid == THREADS - 2) {
+        Camera c = cams[env];
+        // crop pixels inside the 500 x 500 blit target AND inside the rotated copy (both axis-aligned in u, v)
+        c.ulo = max(-c.rx0, -c.cx0); c.uhi = min(WIN - 1 - c.rx0, c.nx - 1 - c.cx0);
+        c.vlo = max(-c.ry0, -c.cy0); c.vhi = min(WIN - 1 - c.ry0, c.ny - 1 - c.cy0);
+        sm.cam = c;
+        // the sample lattice u, v in {4i+1, 4i+2}: the map is affine, so its corners bound it
+        const int fmax_ = (WIN << 16) - 1;
+        int fx0 = 0x7fffffff, fx1 = -0x7fffffff - 1, fy0 = 0x7fffffff, fy1 = -0x7fffffff - 1;
+        for (int k = 0; k < 4; ++k) {
+            const int xc = ((k & 1) ? OBS - 2 : 1) + c.cx0, yc = ((k & 2) ? OBS - 2 : 1) + c.cy0;
+            const int fx = c.a0 + c.a1 * xc + c.a2 * yc, fy = c.b0 + c.b1 * xc + c.b2 * yc;
+            fx0 = min(fx0, fx); fx1 = max(fx1, fx); fy0 = min(fy0, fy); fy1 = max(fy1, fy);
+        }
+        sm.fast = (1 >= c.ulo && OBS - 2 <= c.uhi && 1 >= c.vlo && OBS - 2 <= c.vhi && fx0 >= 0 && fy0 >= 0 && fx1 <= fmax_ && fy1 <= fmax_) ? 1 : 0;
+        // staged window: the on-screen part of the lattice's bounding box, whole 16-byte chunks (64 pixels) per row
+        const int wx0 = max(fx0 >> 16, 0), wx1 = min(fx1 >> 16, WIN - 1), wy0 = max(fy0 >> 16, 0), wy1 = min(fy1 >> 16, WIN - 1);
+        int nrows = 0, nch = 0, cb0 = 0;
+        if (wx0 <= wx1 && wy0 <= wy1) {
+            nrows = min(wy1 - wy0 + 1, WROWS);
+            cb0 = wx0 >> 6; nch = min((wx1 >> 6) - cb0 + 1, WCHUNK);
+        }
+        sm.wy0 = wy0; sm.nrows = nrows; sm.cb0 = cb0; sm.nch = nch;
+        sm.cam.wx0 = wx0; sm.cam.wy0 = wy0; sm.cam.wx1 = wx1; sm.cam.wy1 = wy1;  // on-screen part of the lattice's bounding box (empty: wx0 > wx1 or wy0 > wy1)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(nrows * nch * 16) : "memory");
+    }
+    if (tid >= THREADS - 2 - NCOLOR && tid < THREADS - 2) {
+        const int k = tid - (THREADS - 2 - NCOLOR);
+        sm.pal[k] = (pal.rg[k] & 0xffu) | (((pal.rg[k] >> 16) & 0xffu) << 10) | ((pal.b[k] & 0xffu) << 20);
+    }
+    {
+        const int tn = st.traj_n[env];
+        const int ntraj = tn > 1 ? min(tn, TRAJ) : 0;
+        if (tid == 0) sm.ndyn = 1 + ntraj;
+        // dynamic box d: 0 = the vehicle (warp 1, lane 0), 1 + i = trajectory box i, old -> new (warp 0)
+        int d = -1;
+        if (tid < ntraj) d = 1 + tid; else if (tid == 32) d = 0;
+        if (d >= 0) {
+            Shape &S = sm.shapes[d];
+            double bx[4], by[4];
+            const Camera cam = cams[env];
+            double x, y, c, sn;
+            bool skip = false;
+            if (d == 0) {  // :312-313 vehicle
+                x = st.pose[3 * env]; y = st.pose[3 * env + 1]; c = st.cs[2 * env]; sn = st.cs[2 * env + 1];
+                if (ntraj > 0) {  // the newest trajectory box is painted later over the very same pixels: skip this one
+                    const double2 *p = reinterpret_cast<const double2 *>(st.traj) + ((size_t)env * TRAJ + (tn - 1) % TRAJ) * 2;
+                    const double2 xy = p[0], cs = p[1];
+                    skip = xy.x == x && xy.y == y && cs.x == c && cs.y == sn;
+                }
+            } else {  // :315-319 trajectory[-(ntraj - i)], colour TRAJ_COLORS[-(ntraj - i)]
+                const int back = ntraj - (d - 1);  // back = 1: newest
+                const double2 *p = reinterpret_cast<const double2 *>(st.traj) + ((size_t)env * TRAJ + (tn - back) % TRAJ) * 2;
+                const double2 xy = p[0], cs = p[1];
+                x = xy.x; y = xy.y; c = cs.x; sn = cs.y;
+            }
+            vehicle_box(x, y, c, sn, par.box_x, par.box_y, bx, by);
+            ring_shape(S, cam, bx, by, 4, 0, 0);
+            if (skip) { S.miny = 1; S.maxy = 0; }
+            sm.drange[d] = make_short2(S.miny, S.maxy);
+            // lattice rectangle: the box's integer screen corners through the inverse of the camera map, in float.  What the box
+            // paints lies within a pixel of their hull (floor / ceil of the crossings) and a sample within a pixel of its screen
+            // pixel: 2.5 pixels of margin absorb both and the float rounding.
+            uchar4 lb = make_uchar4(1, 0, 1, 0);
+            if (!skip) {
+                const float a1 = (float)cam.a1, a2 = (float)cam.a2, b1 = (float)cam.b1, b2 = (float)cam.b2;
+                const float rdet = 1.0f / (a1 * b2 - a2 * b1);
+                float umin = 1e30f, umax = -1e30f, vmin = 1e30f, vmax = -1e30f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    int px, py;
+                    to_screen(cam, bx[k], by[k], px, py);
+                    const float X = ((float)px + 0.5f) * 65536.0f - (float)cam.a0, Y = ((float)py + 0.5f) * 65536.0f - (float)cam.b0;
+                    const float u = (b2 * X - a2 * Y) * rdet - (float)cam.cx0, v = (a1 * Y - b1 * X) * rdet - (float)cam.cy0;
+                    umin = fminf(umin, u); umax = fmaxf(umax, u); vmin = fminf(vmin, v); vmax = fmaxf(vmax, v);
+                }
+                umin -= 2.5f; vmin -= 2.5f; umax += 2.5f; vmax += 2.5f;
+                // lattice index a <-> crop pixel 4 (a >> 1) + 1 + (a & 1): [2 floor((umin - 2) / 4), 2 floor(umax / 4) + 1] covers [umin, umax]
+                const int iu0 = max(2 * (int)floorf((umin - 2.0f) * 0.25f), 0), iu1 = min(2 * (int)floorf(umax * 0.25f) + 1, LAT - 1);
+                const int iv0 = max(2 * (int)floorf((vmin - 2.0f) * 0.25f), 0), iv1 = min(2 * (int)floorf(vmax * 0.25f) + 1, LAT - 1);
+                if (iu0 <= iu1 && iv0 <= iv1) lb = make_uchar4((unsigned char)iu0, (unsigned char)iu1, (unsigned char)iv0, (unsigned char)iv1);
+            }
+            sm.lbox[d] = lb;
         }
     }
     __syncthreads();
     const Camera &cam = sm.cam;
-    const int nstatic = sm.nstatic, ndyn = sm.nshapes - nstatic;
-    // ---------------------------------------------------------------- 2a. span table of the dynamic boxes: one
-    // (box, row) pair per thread and pass, all threads, once per env; the window is cleared for the first quadrant
+    const int ndyn = sm.ndyn, ntraj = ndyn - 1;
+    // ---------------------------------------------------------------- 2. request the static rows of the window
+    {
+        const int nrows = sm.nrows, bytes = sm.nch * 16;
+        const uint8_t *src = scr + (size_t)sm.wy0 * SCREEN_PITCH + sm.cb0 * 16;
+        for (int r = tid; r < nrows; r += THREADS) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(&sm.swin[r * WPITCH]);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(dst), "l"(src + (size_t)r * SCREEN_PITCH), "r"(bytes), "r"(bar) : "memory");
+        }
+    }
+    if (warp == 0) {  // the dynamic layer's window: bounding box of the boxes, cut to what the lattice can touch
+        int x0 = 0x7fff, y0 = 0x7fff, x1 = -0x8000, y1 = -0x8000;
+        if (lane < ndyn) {
+            const Shape &S = sm.shapes[lane];
+            if (S.miny <= S.maxy) { x0 = S.minx; x1 = S.maxx; y0 = S.miny; y1 = S.maxy; }
+        }
+        static_assert(NDYN <= 32, "one lane per dynamic box");
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            x0 = min(x0, __shfl_xor_sync(HOPE_FULL_MASK, x0, o)); y0 = min(y0, __shfl_xor_sync(HOPE_FULL_MASK, y0, o));
+            x1 = max(x1, __shfl_xor_sync(HOPE_FULL_MASK, x1, o)); y1 = max(y1, __shfl_xor_sync(HOPE_FULL_MASK, y1, o));
+        }
+        if (lane == 0) {
+            x0 = max(x0, cam.wx0); x1 = min(x1, cam.wx1); y0 = max(y0, cam.wy0); y1 = min(y1, cam.wy1);
+            int dnw = 0, dnr = 0;
+            if (x0 <= x1 && y0 <= y1) { dnw = (x1 >> 3) - (x0 >> 3) + 1; dnr = y1 - y0 + 1; }
+            const int lattice = dnw * dnr > DWORDS || (force_lattice && dnr > 0);
+            sm.dx0 = x0 & ~7; sm.dy0 = y0; sm.dnw = lattice ? 0 : dnw; sm.dnr = lattice ? 0 : dnr; sm.lattice_mode = lattice;
+        }
+    }
+    // screen pixel (0, 0) of the static screen, for rotate()'s background colour: only read when a sample can leave the screen, and
+    // requested here so that it arrives under the span table
+    unsigned probe_static = 0u;
+    if (tid == THREADS - 1 && !sm.fast) probe_static = scr[0];
+    // ---------------------------------------------------------------- 3. span table of the dynamic boxes
     for (int idx = tid; idx < ndyn * DROWS; idx += THREADS) {
         const int d = idx / DROWS, r = idx - d * DROWS;
-        const Shape &S = sm.shapes[nstatic + d];
+        const Shape &S = sm.shapes[d];
         const int y = S.miny + r;
         short2 e = make_short2(1, 0);  // nothing on this row
         if (y <= S.maxy && y >= 0 && y < WIN) {
             if (S.miny == S.maxy) e = make_short2(S.minx, S.maxx);
             else {
-                int x0, x1, x2, x3;
-                const int cnt = row_crossings(S, y, x0, x1, x2, x3);
-                if (cnt == 2) e = make_short2((short)min(x0, x1), (short)max(x0, x1));
-                else if (cnt == 3) {
-                    const int lo = min(x0, min(x1, x2)), hi = max(x0, max(x1, x2));
-                    e = make_short2((short)lo, (short)(x0 + x1 + x2 - lo - hi));
-                } else if (cnt == 4) e = make_short2(DYN_DIRECT, 0);  // two runs: left to paint_shape_row / shape_covers
+                // which edges cross the row (row_crossings' test), then the crossings of the usual two only: the first visited
+                // rounds down, the second up
+                int x0, x1, x2, x3, cnt = 0, ea = 0, eb = 0;
+#pragma unroll
+                const int last = y == S.maxy ? 1 : 0;  // [ylo, yhi), and the edges that end on the last row count there
+                for (int k = 0; k < 4; ++k)
+                    if (k < S.ne) {
+                        const int t = y - S.e[k].ylo, dy = S.e[k].dy;
+                        if ((unsigned)t < (unsigned)dy || (last && t == dy)) { if (cnt == 0) ea = k; else eb = k; ++cnt; }
+                    }
+                if (cnt == 2) {
+                    const Edge A = S.e[ea], B = S.e[eb];
+                    x0 = A.xlo + div_round((y - A.ylo) * A.dx, A.dy, A.rdy, false);
+                    x1 = B.xlo + div_round((y - B.ylo) * B.dx, B.dy, B.rdy, true);
+                    e = make_short2((short)min(x0, x1), (short)max(x0, x1));
+                } else if (cnt > 2) {
+                    cnt = row_crossings(S, y, x0, x1, x2, x3);
+                    if (cnt == 3) {
+                        const int lo = min(x0, min(x1, x2)), hi = max(x0, max(x1, x2));
+                        e = make_short2((short)lo, (short)(x0 + x1 + x2 - lo - hi));
+                    } else if (cnt == 4) e = make_short2(DYN_DIRECT, 0);  // two runs: left to shape_covers
+                }
                 for (int k = 0; k < S.nh; ++k)  // a horizontal edge on this row (the closing zero-length edge, usually): one more run
                     if (S.hy[k] == y && e.x != DYN_DIRECT) {
                         const int c = min(S.hxa[k], S.hxb[k]), dd = max(S.hxa[k], S.hxb[k]);
@@ -504,137 +685,186 @@ k_render(int n, Pool pool, EnvState st, const render::Camera *__restrict__ cams,
         }
         sm.dyn[d][r] = e;
     }
-    constexpr int WINQ = (int)(sizeof(sm.win) / 16);
-    for (int k = tid; k < WINQ; k += THREADS) reinterpret_cast<uint4 *>(sm.win)[k] = make_uint4(0u, 0u, 0u, 0u);
-    if (tid == THREADS - 1) {  // screen pixel (0, 0), rotate()'s background colour, as a 1-pixel "row"; kept as a palette index
-        for (int s = 0; s < nstatic; ++s) {
-            const Shape &S = sm.shapes[s];
-            if (S.miny <= 0 && S.maxy >= 0 && S.minx <= 0 && S.maxx >= 0) paint_shape_row(sm, S, 0, &sm.probe, 0, 0, 0);
+    __syncthreads();
+    const int a0 = cam.a0, a1 = cam.a1, a2 = cam.a2, b0 = cam.b0, b1 = cam.b1, b2 = cam.b2;
+    // ---------------------------------------------------------------- 4. dynamic layer
+    const int dx0 = sm.dx0, dy0 = sm.dy0, dnw = sm.dnw, dnr = sm.dnr;
+    const bool lattice_mode = sm.lattice_mode != 0;
+    if (!lattice_mode) {
+        // window mode: a thread owns a window row and paints the boxes' runs on it old -> new (the painter's order) as nibbles, whole
+        // words between the ends; rows are independent, so there is nothing to wait for.  (Measured on B200 before this: one pass
+        // per box with a block barrier, and rows dealt to warps modulo 8 with four lanes per row: 2.5 and 4.7 times the instructions.)
+#pragma unroll 1
+        // Rows go to warps in blocks of 16 (lanes 0-15: rows 16 w .. 16 w + 15, lanes 16-31: the same + 128): a box touches
+        // few warps, a trail of 128 rows all eight.
+        for (int wr = ((lane >> 4) << 7) | (warp << 4) | (lane & 15); wr < dnr; wr += THREADS) {
+            const int y = wr + dy0, xend = 8 * dnw - 1;
+            uint32_t *row = sm.dwin + wr * dnw;
+#pragma unroll 1
+            for (int d = 0; d < ndyn; ++d) {
+                const short2 dr = sm.drange[d];
+                if (y < dr.x || y > dr.y) continue;
+                const short2 e = sm.dyn[d][y - dr.x];
+                const uint32_t fill = (d == 0 ? CODE_VEHICLE : (uint32_t)(1 + (d - 1) % CODE_MOD)) * 0x11111111u;
+                if (e.x != DYN_DIRECT) {
+                    const int na = max((int)e.x - dx0, 0), nb = min((int)e.y - dx0, xend);
+                    if (na <= nb) {
+                        const int wa = na >> 3, wb = nb >> 3;
+                        const uint32_t ma = 0xffffffffu << (4 * (na & 7)), mb = 0xffffffffu >> (4 * (7 - (nb & 7)));
+                        if (wa == wb) row[wa] = (row[wa] & ~(ma & mb)) | (fill & ma & mb);
+                        else {
+                            row[wa] = (row[wa] & ~ma) | (fill & ma);
+                            for (int w = wa + 1; w < wb; ++w) row[w] = fill;
+                            row[wb] = (row[wb] & ~mb) | (fill & mb);
+                        }
+                    }
+                } else {  // two runs on this row (never for a rectangle): pixel by pixel
+                    const Shape &S = sm.shapes[d];
+                    for (int x = max((int)S.minx, dx0); x <= min((int)S.maxx, dx0 + xend); ++x)
+                        if (shape_covers(S, x, y)) {
+                            const int nx = x - dx0;
+                            row[nx >> 3] = (row[nx >> 3] & ~(0xfu << (4 * (nx & 7)))) | (fill & (0xfu << (4 * (nx & 7))));
+                        }
+                }
+            }
         }
-        unsigned idx = __popc(sm.probe & 0xffu);
+    } else {
+        // lattice mode (a long trail across the whole view): newest box first, every thread tests ITS samples (lattice row % 8 = warp,
+        // column % 32 = lane: a sample always belongs to the same thread, so program order replaces barriers) of the box's lattice
+        // rectangle against the span table and records the box's palette index where nothing newer did
+        const int fx00 = a0 + a1 * cam.cx0 + a2 * cam.cy0, fy00 = b0 + b1 * cam.cx0 + b2 * cam.cy0;
+#pragma unroll 1
+        for (int d = ndyn - 1; d >= 0; --d) {
+            const uchar4 lb = sm.lbox[d];
+            if (lb.x > lb.y) continue;
+            const int miny = sm.drange[d].x;
+            const uint8_t pidx = (uint8_t)(d == 0 ? 4 : 5 + TRAJ - ntraj + d - 1);
+            const int acol = lb.x + ((lane - lb.x) & 31);
+#pragma unroll 1
+            for (int b = lb.z + ((warp - lb.z) & 7); b <= lb.w; b += 8) {
+                const int v = 2 * b + 1 - (b & 1);
+                const int fxr = fx00 + a2 * v, fyr = fy00 + b2 * v;
+                for (int a = acol; a <= lb.y; a += 32) {
+                    const int u = 2 * a + 1 - (a & 1);
+                    const int sx = (fxr + a1 * u) >> 16, sy = (fyr + b1 * u) >> 16;
+                    const unsigned r = (unsigned)(sy - miny);
+                    if (r < (unsigned)DROWS && sm.didx[b][a] == 0) {
+                        const short2 e = sm.dyn[d][r];
+                        if ((sx >= e.x && sx <= e.y) || (e.x == DYN_DIRECT && shape_covers(sm.shapes[d], sx, sy))) sm.didx[b][a] = pidx;
+                    }
+                }
+            }
+        }
+    }
+    if (tid == THREADS - 1 && !sm.fast) {  // screen pixel (0, 0), rotate()'s background colour
+        unsigned idx = probe_static & 3u;
         for (int d = 0; d < ndyn; ++d)
-            if (sm.shapes[nstatic + d].miny <= 0 && sm.shapes[nstatic + d].minx <= 0 && shape_covers(sm.shapes[nstatic + d], 0, 0)) idx = d == 0 ? 4u : (unsigned)(5 + TRAJ - ndyn + d);  // trajectory i = d - 1 of ndyn - 1
+            if (sm.shapes[d].miny <= 0 && sm.shapes[d].minx <= 0 && shape_covers(sm.shapes[d], 0, 0)) idx = d == 0 ? 4u : (unsigned)(5 + TRAJ - ntraj + d - 1);
         sm.probe = idx;
     }
     __syncthreads();
-    const unsigned bgidx = sm.probe & 0xffu;
-    const int ntraj = ndyn - 1;
-    // palette index of a window byte at screen pixel (sx, sy): thermometer codes 0..4 by bit count, trajectory bytes through resolve_traj
-    // A trajectory byte names the newest GROUP of boxes that covers the pixel; the newest box of that group whose stored run
-    // contains sx is the one on top (and if none of the newer ones does, it is the group's oldest: one of them set the bit).
-    auto resolve = [&](unsigned code, int sx, int sy) -> unsigned {
-        if (code < CODE_DYN) return (unsigned)__popc(code);
-        const int g0 = __popc(code >> 5) * TGROUP;
-        int i = min(g0 + TGROUP - 1, ntraj - 1);
-#pragma unroll 1
-        for (; i > g0; --i) {
-            const short2 rg = sm.drange[1 + i];
-            const int r = sy - rg.x;
-            if ((unsigned)r >= (unsigned)DROWS || sy > rg.y) continue;
-            const short2 e = sm.dyn[1 + i][r];
-            if (sx >= e.x && sx <= e.y) break;
-            if (e.x == DYN_DIRECT && shape_covers(sm.shapes[nstatic + 1 + i], sx, sy)) break;
-        }
-        return (unsigned)(5 + TRAJ - ntraj + i);
-    };
-#pragma unroll 1
-    for (int quad = 0; quad < 4; ++quad) {
-        const QuadWindow win = sm.quad[quad];
-        const int u0 = (quad & 1) * (OBS / 2), v0 = (quad >> 1) * (OBS / 2);  // crop origin of this quadrant
-        // ------------------------------------------------------------ 2b. paint: every (shape, window row) pair is one work
-        // item, any thread paints any item (span() ORs thermometer codes).  Static shapes: their rows are dealt round the threads;
-        // dynamic boxes: their stored runs.
-        int first = 0;  // rows handed out so far (mod 256): shape after shape the items go round the threads, so every thread
-                        // gets floor or ceil of (all rows of all shapes) / 256 of them
-        for (int sb = 0; sb < nstatic; sb += 32) {  // each lane tests one shape against the window, the warp walks the hits
-            bool touch = false;
-            if (sb + lane < nstatic) {
-                const Shape &S = sm.shapes[sb + lane];
-                touch = S.maxy >= win.wy0 && S.miny <= win.wy1 && S.maxx >= win.wx0 && S.minx <= win.wx1;
-            }
-            unsigned m = __ballot_sync(HOPE_FULL_MASK, touch);
-            while (m) {
-                const int s = sb + __ffs(m) - 1;
-                m &= m - 1;
-                const Shape &S = sm.shapes[s];
-                const int lo = max((int)S.miny, win.wy0), cnt = min((int)S.maxy, win.wy1) - lo + 1;
-                const int t = (tid - first) & (THREADS - 1);
-                first += cnt;
-                if (t < cnt) paint_shape_row(sm, S, lo + t, sm.win + (lo + t - win.wy0) * PITCHW, win.wx0, win.wx0, win.wx1);
-            }
-        }
-        for (int idx = tid; idx < ndyn * DROWS; idx += THREADS) {
-            const int d = idx / DROWS, r = idx - d * DROWS;
-            const Shape &S = sm.shapes[nstatic + d];
-            const int y = S.miny + r;
-            if (y > S.maxy || y < win.wy0 || y > win.wy1) continue;
-            uint32_t *row = sm.win + (y - win.wy0) * PITCHW;
-            const short2 e = sm.dyn[d][r];
-            if (e.x == DYN_DIRECT) { paint_shape_row(sm, S, y, row, win.wx0, win.wx0, win.wx1); continue; }
-            const uint32_t fill = (uint32_t)S.color * 0x01010101u;
-            if (e.x <= e.y) span(row, win.wx0, win.wx0, win.wx1, e.x, e.y, fill);
-        }
-        __syncthreads();
-        // ------------------------------------------------------------ 3. gather 32 x 32 x (2 x 2 samples)
-        {
-            const unsigned char *win8 = reinterpret_cast<const unsigned char *>(sm.win);
-            const int a0 = cam.a0, a1 = cam.a1, a2 = cam.a2, b0 = cam.b0, b1 = cam.b1, b2 = cam.b2;
-            const int woff = win.wy0 * PITCH + win.wx0;
-            const int i = tid & (QUAD - 1);
-            const int ub = u0 + 4 * i + 1, xc = ub + cam.cx0;
-            uint8_t *out = img + (size_t)env * 3 * IMG * IMG + (quad >> 1) * QUAD * IMG + (quad & 1) * QUAD + i;
-            if (win.fast) {
-#pragma unroll 1
-                for (int r = 0; r < QUAD * QUAD / THREADS; ++r) {
-                    const int j = (tid >> 5) + r * (THREADS / QUAD);
-                    const int yc = v0 + 4 * j + 1 + cam.cy0;
-                    const int fxb = a0 + a1 * xc + a2 * yc, fyb = b0 + b1 * xc + b2 * yc;
-                    uint32_t srg = 0u, sb = 0u;
+    {   // the staged rows have landed
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar) : "memory");
+    }
+    // ---------------------------------------------------------------- 5. gather 64 x 64 x (2 x 2 samples)
+    {
+        // a warp resolves a tile of 8 x 4 output pixels per round (16 rounds): a compact patch of the screen, so that few warps
+        // meet the dynamic layer's window; its stores are 4 x 8 bytes per channel and merge with the neighbour tiles' in L2
+        const int il = lane & 7, jl = lane >> 3;
+        uint8_t *out = img + (size_t)env * 3 * IMG * IMG;
+        const int woff = sm.wy0 * WPITCH + sm.cb0 * 16;  // static pixel (sx, sy): 2 bits of swin[sy * WPITCH + (sx >> 2) - woff]
+        const uint32_t round2 = 2u | (2u << 10) | (2u << 20);  // (a + b + c + d + 2) >> 2 per 10-bit lane
+        // palette indices of the dynamic layer on the four samples of output pixel (i, j), one per byte, 0: none
+        auto dyn_of = [&](int i_, int j_, int fxb, int fyb) -> unsigned {
+            if (lattice_mode)
+                return (unsigned)*reinterpret_cast<const unsigned short *>(&sm.didx[2 * j_][2 * i_]) |
+                       ((unsigned)*reinterpret_cast<const unsigned short *>(&sm.didx[2 * j_ + 1][2 * i_]) << 16);
+            // the four samples lie within two pixels of the first
+            if ((unsigned)((fyb >> 16) - dy0 + 2) >= (unsigned)(dnr + 4) || (unsigned)((fxb >> 16) - dx0 + 2) >= (unsigned)(8 * dnw + 4)) return 0u;
+            unsigned out4 = 0u;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int fx = fxb + ((k & 1) ? a1 : 0) + ((k >> 1) ? a2 : 0), fy = fyb + ((k & 1) ? b1 : 0) + ((k >> 1) ? b2 : 0);
-                        const uint2 c = sm.pal[resolve(win8[(fy >> 16) * PITCH + (fx >> 16) - woff], fx >> 16, fy >> 16)];
-                        srg += c.x; sb += c.y;
+            for (int k = 0; k < 4; ++k) {
+                const int fx = fxb + ((k & 1) ? a1 : 0) + ((k >> 1) ? a2 : 0), fy = fyb + ((k & 1) ? b1 : 0) + ((k >> 1) ? b2 : 0);
+                const int sx = fx >> 16, sy = fy >> 16, rx = sx - dx0, ry = sy - dy0;
+                if ((unsigned)ry < (unsigned)dnr && (unsigned)rx < (unsigned)(8 * dnw)) {
+                    const unsigned c = (sm.dwin[ry * dnw + (rx >> 3)] >> (4 * (rx & 7))) & 15u;
+                    if (c) {
+                        unsigned idx = 4u;
+                        if (c != CODE_VEHICLE) {
+                            int d = (int)c;  // trajectory box t = c - 1, unless the one CODE_MOD steps newer covers the pixel too
+                            if (d + CODE_MOD <= ntraj) {
+                                const int d1 = d + CODE_MOD;
+                                const unsigned r1 = (unsigned)(sy - sm.drange[d1].x);
+                                if (r1 < (unsigned)DROWS) {
+                                    const short2 e = sm.dyn[d1][r1];
+                                    if ((sx >= e.x && sx <= e.y) || (e.x == DYN_DIRECT && shape_covers(sm.shapes[d1], sx, sy))) d = d1;
+                                }
+                            }
+                            idx = (unsigned)(5 + TRAJ - ntraj + d - 1);
+                        }
+                        out4 |= idx << (8 * k);
                     }
-                    srg = ((srg + 0x00020002u) >> 2) & 0x00ff00ffu;  // (a + b + c + d + 2) >> 2 per 16-bit lane
-                    sb = (sb + 2u) >> 2;
-                    uint8_t *o = out + j * IMG;  // a warp writes 32 consecutive bytes per channel: one full sector each
-                    o[0] = (uint8_t)(srg & 0xffu); o[IMG * IMG] = (uint8_t)(srg >> 16); o[2 * IMG * IMG] = (uint8_t)sb;
                 }
-            } else {
-                const unsigned xmaxv = (WIN << 16) - 1;
-                const int ulo = cam.ulo, uhi = cam.uhi, vlo = cam.vlo, vhi = cam.vhi;
-                for (int r = 0; r < QUAD * QUAD / THREADS; ++r) {
-                    const int j = (tid >> 5) + r * (THREADS / QUAD);
-                    const int vb = v0 + 4 * j + 1, yc = vb + cam.cy0;
-                    const int fxb = a0 + a1 * xc + a2 * yc, fyb = b0 + b1 * xc + b2 * yc;
-                    uint32_t srg = 0u, sb = 0u;
+            }
+            return out4;
+        };
+        if (sm.fast) {
+#pragma unroll 1
+            for (int r = 0; r < IMG * IMG / THREADS; ++r) {
+                const int i = ((warp & 7) << 3) | il, j = (r << 2) | jl;
+                const int xc = 4 * i + 1 + cam.cx0, yc = 4 * j + 1 + cam.cy0;
+                const int fxb = a0 + a1 * xc + a2 * yc, fyb = b0 + b1 * xc + b2 * yc;
+                const unsigned dyn4 = dyn_of(i, j, fxb, fyb);
+                unsigned st4[4];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int u = ub + (k & 1), v = vb + (k >> 1);
-                        unsigned idx = 0u;  // background: white -> black, and the untouched (black) blit target
-                        if (u >= ulo && u <= uhi && v >= vlo && v <= vhi) {
-                            const int fx = fxb + ((k & 1) ? a1 : 0) + ((k >> 1) ? a2 : 0), fy = fyb + ((k & 1) ? b1 : 0) + ((k >> 1) ? b2 : 0);
-                            if ((unsigned)fx > xmaxv || (unsigned)fy > xmaxv) idx = bgidx;  // negative wraps to a huge unsigned
-                            else {
-                                const unsigned off = (unsigned)((fy >> 16) * PITCH + (fx >> 16) - woff);
-                                if (off < (unsigned)(ROWS * PITCH)) idx = resolve(win8[off], fx >> 16, fy >> 16);
+                for (int k = 0; k < 4; ++k) {
+                    const int fx = fxb + ((k & 1) ? a1 : 0) + ((k >> 1) ? a2 : 0), fy = fyb + ((k & 1) ? b1 : 0) + ((k >> 1) ? b2 : 0);
+                    const int sx = fx >> 16, sy = fy >> 16;
+                    st4[k] = ((unsigned)sm.swin[sy * WPITCH + (sx >> 2) - woff] >> (2 * (sx & 3))) & 3u;
+                }
+                uint32_t sum = round2;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const unsigned dk = (dyn4 >> (8 * k)) & 0xffu;
+                    sum += sm.pal[dk ? dk : st4[k]];
+                }
+                uint8_t *o = out + j * IMG + i;
+                o[0] = (uint8_t)((sum >> 2) & 0xffu); o[IMG * IMG] = (uint8_t)((sum >> 12) & 0xffu); o[2 * IMG * IMG] = (uint8_t)((sum >> 22) & 0xffu);
+            }
+        } else {
+            const unsigned bgidx = sm.probe;
+            const unsigned xmaxv = (WIN << 16) - 1;
+            const int ulo = cam.ulo, uhi = cam.uhi, vlo = cam.vlo, vhi = cam.vhi;
+#pragma unroll 1
+            for (int r = 0; r < IMG * IMG / THREADS; ++r) {
+                const int i = ((warp & 7) << 3) | il, j = (r << 2) | jl;
+                const int ub = 4 * i + 1, xc = ub + cam.cx0;
+                const int vb = 4 * j + 1, yc = vb + cam.cy0;
+                const int fxb = a0 + a1 * xc + a2 * yc, fyb = b0 + b1 * xc + b2 * yc;
+                const unsigned dyn4 = dyn_of(i, j, fxb, fyb);
+                uint32_t sum = round2;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int u = ub + (k & 1), v = vb + (k >> 1);
+                    unsigned idx = 0u;  // background: white -> black, and the untouched (black) blit target
+                    if (u >= ulo && u <= uhi && v >= vlo && v <= vhi) {
+                        const int fx = fxb + ((k & 1) ? a1 : 0) + ((k >> 1) ? a2 : 0), fy = fyb + ((k & 1) ? b1 : 0) + ((k >> 1) ? b2 : 0);
+                        if ((unsigned)fx > xmaxv || (unsigned)fy > xmaxv) idx = bgidx;  // negative wraps to a huge unsigned
+                        else {
+                            idx = (dyn4 >> (8 * k)) & 0xffu;
+                            if (idx == 0u) {
+                                const int sx = fx >> 16, sy = fy >> 16;
+                                idx = ((unsigned)sm.swin[sy * WPITCH + (sx >> 2) - woff] >> (2 * (sx & 3))) & 3u;
                             }
                         }
-                        const uint2 c = sm.pal[idx];
-                        srg += c.x; sb += c.y;
                     }
-                    srg = ((srg + 0x00020002u) >> 2) & 0x00ff00ffu;
-                    sb = (sb + 2u) >> 2;
-                    uint8_t *o = out + j * IMG;
-                    o[0] = (uint8_t)(srg & 0xffu); o[IMG * IMG] = (uint8_t)(srg >> 16); o[2 * IMG * IMG] = (uint8_t)sb;
+                    sum += sm.pal[idx];
                 }
+                uint8_t *o = out + j * IMG + i;
+                o[0] = (uint8_t)((sum >> 2) & 0xffu); o[IMG * IMG] = (uint8_t)((sum >> 12) & 0xffu); o[2 * IMG * IMG] = (uint8_t)((sum >> 22) & 0xffu);
             }
-        }
-        if (quad < 3) {  // the window is cleared and repainted for the next quadrant
-            __syncthreads();
-            for (int k = tid; k < WINQ; k += THREADS) reinterpret_cast<uint4 *>(sm.win)[k] = make_uint4(0u, 0u, 0u, 0u);
-            __syncthreads();
         }
     }
 }

@@ -15,6 +15,7 @@
 #define __forceinline__ inline
 struct short2 { short x, y; };
 struct uint2 { unsigned x, y; };
+struct uchar4 { unsigned char x, y, z, w; };
 static inline short2 make_short2(short x, short y) { return short2{x, y}; }
 template <class A, class B> static inline auto min(A a, B b) -> decltype(a + b) { return a < b ? a : b; }
 template <class A, class B> static inline auto max(A a, B b) -> decltype(a + b) { return a > b ? a : b; }

@@ -62,7 +62,7 @@ def _oracle_images(sc, book, ids):
     return np.stack(out)
 
 
-def _lockstep_images(env, sc, n, steps, seed, check_every=3):
+def _lockstep_images(env, sc, n, steps, seed, check_every=3, redraw=12, keep=0.7):
     """Steps the CUDA env with persistent, drifting actions; the oracle renders from the CUDA env's own pose and
     substep counters (so this isolates the rasteriser), a rotating subset of envs each step."""
     book = io.TrajectoryBook(n)
@@ -76,9 +76,9 @@ def _lockstep_images(env, sc, n, steps, seed, check_every=3):
     live = np.ones(n, dtype=bool)
     compared = 0
     for k in range(steps):
-        if k % 12 == 11:
+        if k % redraw == redraw - 1:
             drift = rng.uniform(-1, 1, size=(n, 2))
-        act = np.clip(0.7 * drift + 0.3 * rng.uniform(-1, 1, size=(n, 2)), -1, 1)
+        act = np.clip(keep * drift + (1.0 - keep) * rng.uniform(-1, 1, size=(n, 2)), -1, 1)
         obs, _, done, _ = env.step(torch.as_tensor(act, device=env.device).contiguous())
         pose, sub, ret = _np(env.out["pose"]), _np(env.out["substeps"]), _np(env.out["retreated"])
         for i in range(n):
@@ -100,6 +100,55 @@ def test_render_matches_the_oracle_on_generated_scenes():
     compared, book = _lockstep_images(env, sc, n, 45, 5)
     assert compared >= 300
     assert max(len(t) for t in book.traj) > io.TRAJ_RENDER_LEN
+    env.close()
+
+
+def test_render_dynamic_layer_resolved_per_lattice_sample(monkeypatch):
+    """k_render keeps the vehicle and trajectory boxes in a screen window of shared memory; a trail too long for the
+    window is resolved per lattice sample instead.  HOPE_B200_RENDER_LATTICE=1 (read by hope_create) takes that path
+    for every image."""
+    monkeypatch.setenv("HOPE_B200_RENDER_LATTICE", "1")
+    n = 32
+    sc = generate_scenes(n, "mix", 33)
+    env = BatchedParkingEnv(n, scenes=sc, auto_reset=False, use_img_observation=True)
+    monkeypatch.delenv("HOPE_B200_RENDER_LATTICE")
+    compared, book = _lockstep_images(env, sc, n, 36, 6)
+    assert compared >= 150
+    assert max(len(t) for t in book.traj) > io.TRAJ_RENDER_LEN
+    env.close()
+
+
+def test_render_long_trails_at_full_speed():
+    """Full speed held for the whole run (forward for one half of the envs, backward for the other, a little steering):
+    trails of 20 boxes spanning more than 200 pixels on every heading, i.e. dynamic-layer windows near and over the
+    shared-memory capacity (the per-lattice-sample path is taken where the window does not fit)."""
+    n = 64
+    sc = generate_scenes(n, "mix", 35)
+    env = BatchedParkingEnv(n, scenes=sc, auto_reset=False, use_img_observation=True)
+    env.reset()
+    book = io.TrajectoryBook(n)
+    for i in range(n):
+        book.reset(i, sc["start"][i])
+    rng = np.random.default_rng(4)
+    act = np.stack([rng.uniform(-0.35, 0.35, size=n), np.where(np.arange(n) % 2 == 0, 1.0, -1.0)], axis=1)  # (steer, speed)
+    live = np.ones(n, dtype=bool)
+    compared, longest = 0, 0.0
+    for k in range(30):
+        obs, _, done, _ = env.step(torch.as_tensor(act, device=env.device).contiguous())
+        pose_k, sub, ret = _np(env.out["pose"]), _np(env.out["substeps"]), _np(env.out["retreated"])
+        for i in range(n):
+            if live[i]:
+                book.step(i, pose_k[i], sub[i], ret[i])
+                tail = np.asarray([p[:2] for p in book.traj[i][-io.TRAJ_RENDER_LEN:]])
+                longest = max(longest, float(np.abs(tail.max(axis=0) - tail.min(axis=0)).max()))
+        ids = [i for i in range(k % 2, n, 2) if live[i]]
+        if ids:
+            got, want = _np(obs["img"])[ids], _oracle_images(sc, book, ids)
+            assert np.array_equal(got, want), f"step {k}: (images, bytes) differing = {_mismatch(got, want)}"
+            compared += len(ids)
+        live &= _np(done) == 0
+    assert compared >= 300
+    assert longest * 12 > 180, longest  # K = 12 pixels per metre
     env.close()
 
 
