@@ -98,9 +98,10 @@ class BatchedParkingEnv(object):
         self.use_img = bool(use_img_observation)
         if self.use_img:
             if not refconfig.image_supported(self.config):
-                raise capi.HopeError("image observation: k_render is compiled for WIN 500x500, OBS 256x256, K 12, TRAJ_RENDER_LEN 20 "
+                raise capi.HopeError("image observation: k_render is compiled for WIN 500x500, OBS 256x256, K 12, TRAJ_RENDER_LEN <= 20 "
                                      "(car_parking_base.py:301-350); configs.py asks for another raster geometry")
             self.set_palette(refconfig.palette(self.config))
+            capi.check(self.lib.hope_set_render_traj(self.ctx, refconfig.traj_render_len(self.config)), self.ctx)
         self.default_stages = capi.STAGE_ALL | (capi.STAGE_IMAGE if self.use_img else 0)
         for name, ct, shape in capi.OUT_FIELDS:
             if name == "img" and not self.use_img:

@@ -80,6 +80,7 @@ def load_library(max_obs=16):
         "hope_last_cuda_error": (C.c_char_p, [vp]),
         "hope_upload_tables": (C.c_int, [vp] + [dp] * 7),
         "hope_set_palette": (C.c_int, [vp, vp]),
+        "hope_set_render_traj": (C.c_int, [vp, C.c_int]),
         "hope_expand_mask": (C.c_int, [vp, vp, i32]),
         "hope_expand_mask_portable": (C.c_int, [vp, vp, i32]),
         "hope_expand_lidar": (C.c_int, [vp, vp, vp, vp, vp, i32, i32]),

@@ -1,5 +1,5 @@
-// render.cuh — k_render: the image observation without ever materialising the reference's
-// 500 x 500 screen, its rotated copy or the 256 x 256 crop in HBM.  Included by hope_kernels.cu (namespace hope).
+// render.cuh — the image observation without ever materialising the reference's rotated screen copy or
+// the 256 x 256 crop; of the 500 x 500 screen only the part that is constant during an episode is kept (2 bits per pixel).  Included by hope_kernels.cu (namespace hope).
 //
 // Reference path (src/env/car_parking_base.py:301-350, src/env/observation_processor.py:6-23, env_wrapper.py:52-55):
 //   _render               paint obstacles, start outline, dest box, vehicle box, last <= 20 trajectory boxes on a
@@ -11,30 +11,31 @@
 // mean of 4 crop pixels, and each crop pixel is ONE screen pixel through two integer shifts and the 16.16
 // fixed-point rotation.
 //   k_render_camera (thread / env): the composed integer map crop pixel -> screen pixel (Camera, 96 B per env).
-//   k_render (CTA / env, 256 threads, ~44 KB of shared memory, 5 CTAs per SM; the four quadrants of the image go
-//   through the same window one after the other, set-up and span table are built once):
-//   1. set-up: the screen window the quadrant's 64 x 64 sample lattice can touch (<= 180 x 180 pixels) is kept as
-//      one byte per pixel in shared memory; one thread per shape turns its ring into integer screen vertices and a
-//      scan-conversion record (edges in draw_fillpoly's visiting order); the start-box outline (draw_line, Bresenham)
-//      becomes 5 segment records whose pixel run on any row has a closed form.  Every KIND of shape is prepared by a warp of
-//      its own (the branches run side by side), through ONE copy of the float64 set-up code;
-//   2. paint, order-free: _render's painter's order is the order of increasing colour index, so "the later shape wins" is a
-//      per-pixel MAXIMUM.  A window byte holds a thermometer code of the colour index (colour_code / traj_code below) and
-//      spans are OR-ed in with shared-memory atomics: OR of thermometer codes = maximum, whichever thread paints whichever
-//      (shape, row) pair first.  Every such pair is one work item — pygame's scan conversion restated literally per row —
-//      and the items are dealt round all 256 threads (static shapes: by a running row offset; vehicle + trajectory boxes:
-//      from a span table built once per image, 2a).  A byte has room for 8 thermometer levels and there are 25 colours: the
-//      20 trajectory colours share one level plus a 3-bit thermometer of their GROUP of 5; the gather finds the newest box
-//      of the newest group that covers the sample in the span table (at most 4 look-ups).
-//      (Round 1 let one thread OWN one window row and replay the painter's order on it: the rows through the image centre
-//      carry ~22 boxes, the others none, and half of all warp samples sat at the paint -> gather barrier; 6.5 ms per 65 536
-//      images against 4.9 ms now.  The first order-free build was SLOWER (11 ms): 16.7 k SASS instructions, a third of
-//      the stall samples "no instruction" — the L1.5 instruction cache holds 32 KB.  Out-of-line cold paths and the shared
-//      set-up code brought it to 4.0 k instructions.)
-//   3. gather: each thread resolves output pixels = 4 window bytes -> colour index -> palette -> (sum + 2) >> 2 and stores them
-//      as uint8 [3][64][64], a warp writing one 32-byte sector per channel (the reference's float64 image is this / 255).
-// HBM traffic per env-step: 12 288 B written + ~1.3 KB read (scene ring vertices, trajectory ring buffer; the other
-// three quadrants hit L2).
+//   k_render_static (CTA / env, returns at once unless the env's scene changed): obstacles, start outline and dest box do not
+//   change during an episode, so they are painted ONCE per (env, scene) into HBM as 2 bits per pixel (colour index 0..3), 128
+//   bytes per screen row, 64 000 bytes per env (4.2 GB for 65 536 envs).  Painting is order-free: _render's painter's order is
+//   the order of increasing colour index, so "the later shape wins" is a per-pixel MAXIMUM; a tile byte holds a thermometer code
+//   of the colour index and spans are OR-ed in with shared-memory atomics, every (shape, row) pair one work item dealt round
+//   the 256 threads (pygame's scan conversion restated literally per row; the start-box outline = 5 Bresenham segments whose
+//   pixel run on any row has a closed form).
+//   k_render (CTA / env, 256 threads, 73 KB of shared memory, 3 CTAs per SM), every step:
+//   1. set-up: the screen window the 128 x 128 sample lattice can touch (<= 360 x 360 pixels, rotated view); one thread per
+//      dynamic box (vehicle + the last <= 20 trajectory boxes) prepares its scan-conversion record;
+//   2. the window's rows of the cached static screen are fetched with cp.async.bulk (one copy per row, <= 112 B, completion
+//      counted by one mbarrier) and land under steps 3 and 4: 40 KB of shared memory hold them;
+//   3. span table: the run every dynamic box paints on each of its <= 64 screen rows, one (box, row) pair per thread and pass;
+//   4. dynamic layer: a window of one NIBBLE per screen pixel over the boxes' bounding box (cut to the view, 24 KB): a thread owns a
+//      window row and writes the boxes' runs on it old -> new, whole words between the ends.  15 codes for 21 boxes: trajectory
+//      box t carries 1 + t % 14, and the gather asks the span table whether the box 14 steps newer covers the pixel too.  A trail
+//      whose window exceeds the 24 KB (more than ~ 220 x 220 pixels inside the view) is resolved per lattice sample instead:
+//      newest box first, every thread tests ITS samples of the box's lattice rectangle against the span table;
+//   5. gather: a warp resolves 8 x 4 output pixels per round; an output pixel = 4 samples; a sample = the dynamic layer's box if any,
+//      else the 2-bit static pixel of the staged rows; palette sums in one packed word (10-bit lanes), rounded mean, uint8
+//      [3][64][64] (the reference's float64 image is this / 255).
+// HBM traffic per env-step: 12 288 B written + 20-41 KB of static rows read (mostly from L2 after the first step of an
+// episode: the 64 KB screen of an env is re-read every step) + ~1.3 KB of pose / trajectory.
+// History (profiles/r02_ncu_k_render_history.txt): round 1 painted the whole window per step with one thread per window row
+// (6.5 ms per 65 536 images); order-free painting of four quadrant windows 4.9 ms; this design 3.6 ms.
 #pragma once
 
 namespace render {
@@ -48,18 +49,12 @@ constexpr int THREADS = 256;
 constexpr int NDYN = 1 + TRAJ;    // vehicle box + trajectory boxes
 constexpr int DROWS = 64;         // screen rows a vehicle-sized box can span: its diagonal is 5.07 m * K = 60.9 pixels
 constexpr int NCOLOR = 5 + TRAJ;  // 0 background, 1 obstacle, 2 start outline, 3 dest, 4 vehicle, 5.. trajectory old -> new
-// What a window byte holds: a thermometer code of the colour index, so that OR = "the later painted shape wins".  Indices 1..4:
-// the low (index) bits set.  Trajectory boxes (20 colours, old -> new) set bits 0..4 plus a 3-bit thermometer of their GROUP
-// (TGROUP consecutive boxes): the OR keeps the newest group exactly, and the gather finds the newest box of that group
-// that covers the sample in the span table (<= TGROUP look-ups).
-constexpr int TGROUP = 5;
-static_assert((TRAJ + TGROUP - 1) / TGROUP - 1 <= 3, "group thermometer: 3 bits");
-constexpr unsigned CODE_DYN = 0x10u;    // bit 4: a trajectory box covers the pixel
-__host__ __device__ constexpr unsigned colour_code(int index) { return (1u << index) - 1u; }                                      // index 1..4
-__host__ __device__ constexpr unsigned traj_code(int i) { return 0x1fu | (((1u << (i / TGROUP)) - 1u) << 5); }                    // i = 0 oldest
+// What a tile byte of k_render_static holds: a thermometer code of the colour index (1..3: the low `index` bits set), so that
+// OR = "the later painted shape wins".
+__host__ __device__ constexpr unsigned colour_code(int index) { return (1u << index) - 1u; }
 static_assert(TRAJ <= 32 && MAXO + 2 <= THREADS && 33 <= THREADS - 2 - NCOLOR, "one thread per dynamic box; shape threads, palette threads and the camera thread are disjoint");
 
-struct Palette { uint32_t rg[NCOLOR], b[NCOLOR]; };  // R | G << 16 and B: 16-bit lanes so four samples add without carry
+struct Palette { uint32_t rg[NCOLOR], b[NCOLOR]; };  // R | G << 16 and B (k_render repacks them into 10-bit lanes)
 
 struct Camera {
     // screen pixel of crop pixel (u, v): capture coordinates xc = u + cx0, yc = v + cy0, then
@@ -68,7 +63,7 @@ struct Camera {
     int rx0, ry0;          // crop -> "rotate" surface offset (the 500 x 500 blit target)
     int nx, ny;            // capture size
     int a0, a1, a2, b0, b1, b2;
-    int wx0, wy0, wx1, wy1;  // screen window of one quadrant (inclusive), wx0 aligned to 4; filled in by k_render
+    int wx0, wy0, wx1, wy1;  // on-screen part of the sample lattice's bounding box (inclusive); filled in by k_render
     double kbx, kby;       // coord_transform_matrix offsets
     int ulo, uhi, vlo, vhi;  // crop pixels that land on the rotated screen copy at all (the rest reads as background)
 };
@@ -78,7 +73,7 @@ struct Edge { short ylo, yhi, xlo, dx; int dy; float rdy; };  // non-horizontal 
 
 struct Shape {   // one ring prepared for draw_fillpoly
     short miny, maxy, minx, maxx;
-    short color, ne, nh, outline;      // color: the byte code painted (colour_code / traj_code); outline = 1: the width-1 start box, 0: filled
+    short color, ne, nh, outline;      // color: the byte code painted (colour_code; unused for the dynamic boxes); outline = 1: the width-1 start box, 0: filled
     Edge e[4];                         // in the order draw_fillpoly visits them (decides floor / ceil)
     short hy[4], hxa[4], hxb[4];       // horizontal edges strictly between miny and maxy (incl. the closing zero-length edge)
 };
@@ -321,11 +316,19 @@ __device__ __noinline__ void paint_shape_row(const Smem &sm, const Shape &S, int
 
 #ifndef HOPE_RENDER_HOST_TEST  // tests/render_host_harness.cpp compiles the scan-conversion helpers above with g++
 
-// One thread per env: the camera of this step (see Camera).
-__global__ void __launch_bounds__(128) k_render_camera(int n, Pool pool, EnvState st, hope_params par, render::Camera *__restrict__ cams) {
+// One thread per env: the camera of this step (see Camera), and the env joins `repaint` (list, *repaint_n its length, zeroed before
+// the launch) when its scene changed since its static screen was painted (keys: pool slot + the slot's regeneration count).
+__global__ void __launch_bounds__(128) k_render_camera(int n, Pool pool, EnvState st, hope_params par, render::Camera *__restrict__ cams,
+                                                       const unsigned *__restrict__ episode, const uint2 *__restrict__ keys,
+                                                       int *__restrict__ repaint, int *__restrict__ repaint_n) {
     using namespace render;
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= n) return;
+    {
+        const int sid = st.scene[env];
+        const uint2 key = keys[env];
+        if (key.x != (unsigned)sid || key.y != (episode ? episode[sid] : 0u)) repaint[atomicAdd(repaint_n, 1)] = env;
+    }
     const double *meta = pool.meta + (size_t)st.scene[env] * META;
     const double x = st.pose[3 * env], y = st.pose[3 * env + 1], h = st.pose[3 * env + 2];
     const double ch = st.cs[2 * env], sh = st.cs[2 * env + 1];
@@ -384,23 +387,22 @@ __global__ void __launch_bounds__(128) k_render_camera(int n, Pool pool, EnvStat
     cams[env] = c;
 }
 
-// One CTA per env, every step; returns at once unless the env's scene changed since its static screen was painted (key = pool slot +
-// the slot's regeneration count).  Paints obstacles, start outline and dest box tile by tile (100 screen rows of thermometer bytes
+// A small grid walks the envs k_render_camera listed (none on most steps, all after a reset of the whole batch), one CTA per env
+// at a time.  Paints obstacles, start outline and dest box tile by tile (100 screen rows of thermometer bytes
 // in shared memory, every (shape, row) pair one work item, spans OR-ed in) and stores the tile as 2 bits per pixel.
 __global__ void __launch_bounds__(render::THREADS)
-k_render_static(int n, Pool pool, EnvState st, const unsigned *__restrict__ episode, const render::Camera *__restrict__ cams, hope_params par,
-                uint8_t *__restrict__ screen, uint2 *__restrict__ keys) {
+k_render_static(Pool pool, EnvState st, const unsigned *__restrict__ episode, const render::Camera *__restrict__ cams, hope_params par,
+                uint8_t *__restrict__ screen, uint2 *__restrict__ keys, const int *__restrict__ repaint, const int *__restrict__ repaint_n) {
     using namespace render;
-    const int env = blockIdx.x;
-    const int sid = st.scene[env];
-    const unsigned ep = episode ? episode[sid] : 0u;
-    {
-        const uint2 key = keys[env];
-        if (key.x == (unsigned)sid && key.y == ep) return;
-    }
     extern __shared__ __align__(16) unsigned char render_smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(render_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
+    const int nrepaint = *repaint_n;
+#pragma unroll 1
+    for (int item = blockIdx.x; item < nrepaint; item += gridDim.x) {   // (every pass ends with a block barrier: the tile loop's)
+    const int env = repaint[item];
+    const int sid = st.scene[env];
+    const unsigned ep = episode ? episode[sid] : 0u;
     const double *meta = pool.meta + (size_t)sid * META;
     const int nobs = pool.nobs[sid];
     {   // one thread per shape; start and dest in warps of their own next to the obstacles' (when those fit one warp)
@@ -489,6 +491,7 @@ k_render_static(int n, Pool pool, EnvState st, const unsigned *__restrict__ epis
         __syncthreads();
     }
     if (tid == 0) keys[env] = make_uint2((unsigned)sid, ep);
+    }
 }
 
 // One CTA per env.
@@ -502,10 +505,11 @@ k_render_static(int n, Pool pool, EnvState st, const unsigned *__restrict__ epis
 //      table and records the box's palette index where nothing newer did;
 //   5. gather: an output pixel = 4 samples; a sample = its dynamic index if any, else the 2-bit static pixel of the staged window;
 //      palette sums in one packed word, rounded mean, uint8 [3][64][64] with a warp writing whole 32-byte sectors.
-// traj: [N][20][4] ring buffer (x, y, cos h, sin h) of Vehicle.trajectory's tail, traj_n: [N] its length (see k_advance)
+// traj: [N][20][4] ring buffer (x, y, cos h, sin h) of Vehicle.trajectory's tail, traj_n: [N] its length (see k_advance);
+// traj_len <= TRAJ: how many of them are drawn, in the colours 5 + traj_len - ntraj .. of the palette (TRAJ_COLORS[-ntraj:])
 __global__ void __launch_bounds__(render::THREADS, 3)
 k_render(int n, EnvState st, const render::Camera *__restrict__ cams, hope_params par, render::Palette pal, const uint8_t *__restrict__ screen,
-         uint8_t *__restrict__ img, int force_lattice) {
+         uint8_t *__restrict__ img, int traj_len, int force_lattice) {
     using namespace render;
     extern __shared__ __align__(16) unsigned char render_smem_raw[];
     SmemDyn &sm = *reinterpret_cast<SmemDyn *>(render_smem_raw);
@@ -553,7 +557,7 @@ k_render(int n, EnvState st, const render::Camera *__restrict__ cams, hope_param
     }
     {
         const int tn = st.traj_n[env];
-        const int ntraj = tn > 1 ? min(tn, TRAJ) : 0;
+        const int ntraj = tn > 1 ? min(tn, traj_len) : 0;  // car_parking_base.py:315-316; traj_len = TRAJ_RENDER_LEN, 0 when RENDER_TRAJ is off
         if (tid == 0) sm.ndyn = 1 + ntraj;
         // dynamic box d: 0 = the vehicle (warp 1, lane 0), 1 + i = trajectory box i, old -> new (warp 0)
         int d = -1;
@@ -634,7 +638,7 @@ k_render(int n, EnvState st, const render::Camera *__restrict__ cams, hope_param
         if (lane == 0) {
             x0 = max(x0, cam.wx0); x1 = min(x1, cam.wx1); y0 = max(y0, cam.wy0); y1 = min(y1, cam.wy1);
             int dnw = 0, dnr = 0;
-            if (x0 <= x1 && y0 <= y1) { dnw = (x1 >> 3) - (x0 >> 3) + 1; dnr = y1 - y0 + 1; }
+            if (x0 <= x1 && y0 <= y1) { dnw = ((x1 >> 3) - (x0 >> 3) + 1) | 1; dnr = y1 - y0 + 1; }  // odd pitch: the row owners (consecutive rows) hit different banks
             const int lattice = dnw * dnr > DWORDS || (force_lattice && dnr > 0);
             sm.dx0 = x0 & ~7; sm.dy0 = y0; sm.dnw = lattice ? 0 : dnw; sm.dnr = lattice ? 0 : dnr; sm.lattice_mode = lattice;
         }
@@ -701,11 +705,11 @@ k_render(int n, EnvState st, const render::Camera *__restrict__ cams, hope_param
             const int y = wr + dy0, xend = 8 * dnw - 1;
             uint32_t *row = sm.dwin + wr * dnw;
 #pragma unroll 1
-            for (int d = 0; d < ndyn; ++d) {
+            for (int d = 0, code = (int)CODE_VEHICLE; d < ndyn; ++d, code = code >= CODE_MOD ? 1 : code + 1) {  // 15, then 1 + (d - 1) % 14
                 const short2 dr = sm.drange[d];
                 if (y < dr.x || y > dr.y) continue;
                 const short2 e = sm.dyn[d][y - dr.x];
-                const uint32_t fill = (d == 0 ? CODE_VEHICLE : (uint32_t)(1 + (d - 1) % CODE_MOD)) * 0x11111111u;
+                const uint32_t fill = (uint32_t)code * 0x11111111u;
                 if (e.x != DYN_DIRECT) {
                     const int na = max((int)e.x - dx0, 0), nb = min((int)e.y - dx0, xend);
                     if (na <= nb) {
@@ -738,7 +742,7 @@ k_render(int n, EnvState st, const render::Camera *__restrict__ cams, hope_param
             const uchar4 lb = sm.lbox[d];
             if (lb.x > lb.y) continue;
             const int miny = sm.drange[d].x;
-            const uint8_t pidx = (uint8_t)(d == 0 ? 4 : 5 + TRAJ - ntraj + d - 1);
+            const uint8_t pidx = (uint8_t)(d == 0 ? 4 : 5 + traj_len - ntraj + d - 1);
             const int acol = lb.x + ((lane - lb.x) & 31);
 #pragma unroll 1
             for (int b = lb.z + ((warp - lb.z) & 7); b <= lb.w; b += 8) {
@@ -759,7 +763,7 @@ k_render(int n, EnvState st, const render::Camera *__restrict__ cams, hope_param
     if (tid == THREADS - 1 && !sm.fast) {  // screen pixel (0, 0), rotate()'s background colour
         unsigned idx = probe_static & 3u;
         for (int d = 0; d < ndyn; ++d)
-            if (sm.shapes[d].miny <= 0 && sm.shapes[d].minx <= 0 && shape_covers(sm.shapes[d], 0, 0)) idx = d == 0 ? 4u : (unsigned)(5 + TRAJ - ntraj + d - 1);
+            if (sm.shapes[d].miny <= 0 && sm.shapes[d].minx <= 0 && shape_covers(sm.shapes[d], 0, 0)) idx = d == 0 ? 4u : (unsigned)(5 + traj_len - ntraj + d - 1);
         sm.probe = idx;
     }
     __syncthreads();
@@ -802,7 +806,7 @@ k_render(int n, EnvState st, const render::Camera *__restrict__ cams, hope_param
                                     if ((sx >= e.x && sx <= e.y) || (e.x == DYN_DIRECT && shape_covers(sm.shapes[d1], sx, sy))) d = d1;
                                 }
                             }
-                            idx = (unsigned)(5 + TRAJ - ntraj + d - 1);
+                            idx = (unsigned)(5 + traj_len - ntraj + d - 1);
                         }
                         out4 |= idx << (8 * k);
                     }
@@ -811,7 +815,7 @@ k_render(int n, EnvState st, const render::Camera *__restrict__ cams, hope_param
             return out4;
         };
         if (sm.fast) {
-#pragma unroll 1
+#pragma unroll 2
             for (int r = 0; r < IMG * IMG / THREADS; ++r) {
                 const int i = ((warp & 7) << 3) | il, j = (r << 2) | jl;
                 const int xc = 4 * i + 1 + cam.cx0, yc = 4 * j + 1 + cam.cy0;

@@ -127,7 +127,12 @@ def validate(c):
 
 def image_supported(c):
     """k_render bakes the raster geometry of car_parking_base.py:301-350 in: only the shipped values are available."""
-    return (int(c.WIN_W), int(c.WIN_H), int(c.OBS_W), int(c.OBS_H), int(c.K), int(c.TRAJ_RENDER_LEN)) == (500, 500, 256, 256, 12, 20)
+    return (int(c.WIN_W), int(c.WIN_H), int(c.OBS_W), int(c.OBS_H), int(c.K)) == (500, 500, 256, 256, 12) and 0 <= traj_render_len(c) <= 20
+
+
+def traj_render_len(c):
+    """how many trajectory boxes _render draws (car_parking_base.py:315-316): TRAJ_RENDER_LEN, none with RENDER_TRAJ off"""
+    return int(c.TRAJ_RENDER_LEN) if c.RENDER_TRAJ else 0
 
 
 def step_params(c):
@@ -145,7 +150,8 @@ def step_params(c):
 def palette(c):
     """(25, 3) uint8 colours in hope_set_palette order (configs.py:26-30, 80-88)"""
     traj = np.linspace(np.array(c.TRAJ_COLOR_LOW), np.array(c.TRAJ_COLOR_HIGH), int(c.TRAJ_RENDER_LEN), endpoint=True, dtype=np.uint8)
-    rows = [c.BG_COLOR, c.OBSTACLE_COLOR, c.START_COLOR, c.DEST_COLOR, c.COLOR_POOL[0]] + [tuple(t) for t in traj]
+    rows = [c.BG_COLOR, c.OBSTACLE_COLOR, c.START_COLOR, c.DEST_COLOR, c.COLOR_POOL[0]] + [tuple(t) for t in traj[:20]]
+    rows += [c.BG_COLOR] * (25 - len(rows))  # a shorter TRAJ_RENDER_LEN leaves the tail unused (hope_set_render_traj)
     return np.array([r[:3] for r in rows], dtype=np.uint8)
 
 

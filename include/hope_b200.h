@@ -141,6 +141,10 @@ int hope_upload_tables(hope_ctx *ctx, const double *h_ray_a, const double *h_ray
  * [5..24] TRAJ_COLORS[0..19].  A palette entry equal to BG_COLOR reads as black in the observation
  * (Obs_Processor.change_bg_color).  hope_create installs the reference's defaults. */
 int hope_set_palette(hope_ctx *ctx, const uint8_t *h_rgb);
+/* How many of the last trajectory boxes _render draws: configs.py:86 TRAJ_RENDER_LEN (0..20, default 20), 0 for configs.py:105
+   RENDER_TRAJ = False (car_parking_base.py:315-320).  Box i of the n drawn (old -> new) takes palette entry 5 + len - n + i,
+   i.e. the palette's trajectory colours are TRAJ_COLORS of that length in entries 5 .. 5 + len - 1. */
+int hope_set_render_traj(hope_ctx *ctx, int traj_render_len);
 
 /* Scene pool, HOST pointers: scenes [first, first+n) of the pool.
  *   start[n][3] dest[n][3] bounds[n][4]=(xmin,xmax,ymin,ymax) obs_xy[n][16][4][2] nverts[n][16]

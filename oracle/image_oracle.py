@@ -72,9 +72,16 @@ def downsample4(img):
     return ((s + 2) >> 2).astype(np.uint8)
 
 
-def render_screen(start, dest, bounds, obstacles, traj):
+def traj_colors(traj_render_len):
+    """configs.py:87-88 TRAJ_COLORS for another TRAJ_RENDER_LEN"""
+    return [tuple(int(v) for v in c[:3]) for c in
+            np.linspace(np.array((10, 10, 10, 255)), np.array((10, 10, 200, 255)), traj_render_len, endpoint=True, dtype=np.uint8)]
+
+
+def render_screen(start, dest, bounds, obstacles, traj, traj_render_len=TRAJ_RENDER_LEN):
     """_render: the 500 x 500 screen.  `obstacles`: list of open vertex lists; `traj`: list of (x, y, heading),
-    the last one being the current state."""
+    the last one being the current state.  traj_render_len: configs.py:86 TRAJ_RENDER_LEN, 0 = RENDER_TRAJ off
+    (car_parking_base.py:315)."""
     mat = screen_matrix(bounds)
     surf = sr.Surface((WIN_W, WIN_H))
     surf.fill(BG_COLOR)
@@ -84,10 +91,11 @@ def render_screen(start, dest, bounds, obstacles, traj):
     sr.polygon(surf, START_COLOR, to_screen(create_box(*start), mat), width=1)
     sr.polygon(surf, DEST_COLOR, to_screen(create_box(*dest), mat))
     sr.polygon(surf, VEHICLE_COLOR, to_screen(create_box(*traj[-1]), mat))
-    if len(traj) > 1:
-        n = min(len(traj), TRAJ_RENDER_LEN)
+    if traj_render_len > 0 and len(traj) > 1:
+        n = min(len(traj), traj_render_len)
+        colors = TRAJ_COLORS if traj_render_len == TRAJ_RENDER_LEN else traj_colors(traj_render_len)
         for i in range(n):
-            sr.polygon(surf, TRAJ_COLORS[-(n - i)], to_screen(create_box(*traj[-(n - i)]), mat))
+            sr.polygon(surf, colors[-(n - i)], to_screen(create_box(*traj[-(n - i)]), mat))
     return surf, mat
 
 
@@ -117,9 +125,9 @@ def process(raw):
     return np.ascontiguousarray(downsample4(img).transpose(2, 0, 1))
 
 
-def render_observation(start, dest, bounds, obstacles, traj):
+def render_observation(start, dest, bounds, obstacles, traj, traj_render_len=TRAJ_RENDER_LEN):
     """uint8 (3, 64, 64); the reference's float64 observation is this / 255.0."""
-    surf, mat = render_screen(start, dest, bounds, obstacles, traj)
+    surf, mat = render_screen(start, dest, bounds, obstacles, traj, traj_render_len)
     return process(crop_observation(surf, mat, traj[-1]))
 
 

@@ -54,11 +54,11 @@ def test_golden_images_through_cuda(golden_dir, level):
     env.close()
 
 
-def _oracle_images(sc, book, ids):
+def _oracle_images(sc, book, ids, traj_render_len=io.TRAJ_RENDER_LEN):
     out = []
     for i in ids:
         rings = io.scene_rings(sc["obs"][i], sc["nverts"][i])
-        out.append(io.render_observation(sc["start"][i], sc["dest"][i], sc["bounds"][i], rings, book.traj[i]))
+        out.append(io.render_observation(sc["start"][i], sc["dest"][i], sc["bounds"][i], rings, book.traj[i], traj_render_len))
     return np.stack(out)
 
 
@@ -149,6 +149,42 @@ def test_render_long_trails_at_full_speed():
         live &= _np(done) == 0
     assert compared >= 300
     assert longest * 12 > 180, longest  # K = 12 pixels per metre
+    env.close()
+
+
+@pytest.mark.parametrize("length, render_traj", [(7, True), (20, False), (1, True)])
+def test_trajectory_length_follows_configs(length, render_traj):
+    """configs.py:86 TRAJ_RENDER_LEN / :105 RENDER_TRAJ are run-time settings of k_render (hope_set_render_traj): a shorter trail
+    takes TRAJ_COLORS of that length, RENDER_TRAJ = False draws no trail at all (car_parking_base.py:315-320)."""
+    from hope_b200 import refconfig
+    cfg = refconfig.defaults()
+    cfg.TRAJ_RENDER_LEN, cfg.RENDER_TRAJ = length, render_traj
+    drawn = length if render_traj else 0
+    n = 24
+    sc = generate_scenes(n, "mix", 36)
+    env = BatchedParkingEnv(n, scenes=sc, auto_reset=False, use_img_observation=True, config=cfg)
+    book = io.TrajectoryBook(n)
+    obs = env.reset()
+    for i in range(n):
+        book.reset(i, sc["start"][i])
+    rng = np.random.default_rng(9)
+    drift = rng.uniform(-1, 1, size=(n, 2))
+    live = np.ones(n, dtype=bool)
+    compared = 0
+    for k in range(14):
+        act = np.clip(0.8 * drift + 0.2 * rng.uniform(-1, 1, size=(n, 2)), -1, 1)
+        obs, _, done, _ = env.step(torch.as_tensor(act, device=env.device).contiguous())
+        pose, sub, ret = _np(env.out["pose"]), _np(env.out["substeps"]), _np(env.out["retreated"])
+        for i in range(n):
+            if live[i]:
+                book.step(i, pose[i], sub[i], ret[i])
+        ids = [i for i in range(k % 2, n, 2) if live[i]]
+        if ids:
+            got, want = _np(obs["img"])[ids], _oracle_images(sc, book, ids, drawn)
+            assert np.array_equal(got, want), f"step {k}: (images, bytes) differing = {_mismatch(got, want)}"
+            compared += len(ids)
+        live &= _np(done) == 0
+    assert compared >= 80
     env.close()
 
 
