@@ -24,18 +24,19 @@
 //   2. the window's rows of the cached static screen are fetched with cp.async.bulk (one copy per row, <= 112 B, completion
 //      counted by one mbarrier) and land under steps 3 and 4: 40 KB of shared memory hold them;
 //   3. span table: the run every dynamic box paints on each of its <= 64 screen rows, one (box, row) pair per thread and pass;
-//   4. dynamic layer: a window of one NIBBLE per screen pixel over the boxes' bounding box (cut to the view, 24 KB): a thread owns a
-//      window row and writes the boxes' runs on it old -> new, whole words between the ends.  15 codes for 21 boxes: trajectory
-//      box t carries 1 + t % 14, and the gather asks the span table whether the box 14 steps newer covers the pixel too.  A trail
-//      whose window exceeds the 24 KB (more than ~ 220 x 220 pixels inside the view) is resolved per lattice sample instead:
-//      newest box first, every thread tests ITS samples of the box's lattice rectangle against the span table;
+//   4. dynamic layer: windows of one NIBBLE per screen pixel over the boxes' bounding box (cut to the view): a thread owns a window
+//      row and writes its boxes' runs on it old -> new, whole words between the ends.  The older and the newer half of the boxes
+//      have a window each (2 x 12 KB; the gather asks the newer one first): the two halves are painted side by side by the two
+//      half-warps, a row owner walks at most 11 boxes, and 11 codes fit the nibble.  A trail whose windows exceed their 12 KB (more
+//      than ~ 150 x 150 pixels per half inside the view) is resolved per lattice sample instead: newest box first, every thread
+//      tests ITS samples of the box's lattice rectangle against the span table;
 //   5. gather: a warp resolves 8 x 4 output pixels per round; an output pixel = 4 samples; a sample = the dynamic layer's box if any,
 //      else the 2-bit static pixel of the staged rows; palette sums in one packed word (10-bit lanes), rounded mean, uint8
 //      [3][64][64] (the reference's float64 image is this / 255).
 // HBM traffic per env-step: 12 288 B written + 20-41 KB of static rows read (mostly from L2 after the first step of an
 // episode: the 64 KB screen of an env is re-read every step) + ~1.3 KB of pose / trajectory.
 // History (profiles/r02_ncu_k_render_history.txt): round 1 painted the whole window per step with one thread per window row
-// (6.5 ms per 65 536 images); order-free painting of four quadrant windows 4.9 ms; this design 3.6 ms.
+// (6.5 ms per 65 536 images); order-free painting of four quadrant windows 4.9 ms; this design 3.2 ms.
 #pragma once
 
 namespace render {
@@ -105,8 +106,7 @@ struct Smem {                           // k_render_static
 constexpr int LAT = 2 * IMG;
 constexpr int WROWS = 360;              // screen rows the lattice can touch: 253 sqrt(2) (1 + 2^-15) + 2 <= 360
 constexpr int DWORDS = 6144;            // capacity of the dynamic layer's screen window, 8 pixels per word (e.g. 192 rows x 256 pixels)
-constexpr unsigned CODE_VEHICLE = 15u;  // nibble codes of the dynamic layer: 0 none, 1 + t % 14 trajectory box t (old -> new), 15 vehicle
-constexpr int CODE_MOD = 14;
+constexpr int DHALF = DWORDS / 2;        // the older and the newer half of the boxes are painted into windows of their own
 constexpr int WCHUNK = 7;               // 16-byte chunks (64 pixels) per staged row: 361 pixels straddle at most 7
 constexpr int WPITCH = WCHUNK * 16;
 
@@ -122,10 +122,11 @@ struct SmemDyn {                        // k_render
     uchar4 lbox[NDYN];                  // lattice columns [x, y] and rows [z, w] the box can cover (x > y: none)
     uint32_t pal[NCOLOR];               // R | G << 10 | B << 20: four samples add without carry
     short2 dyn[NDYN][DROWS];            // span of dynamic box d on screen row miny_d + r; x > y: nothing; x == DYN_DIRECT: evaluate
-    int dx0, dy0, dnw, dnr;             // dynamic layer as a screen window: rows [dy0, dy0 + dnr), pixels [dx0, dx0 + 8 dnw), dx0 % 8 == 0
-    int lattice_mode;                   // the window would not fit: the layer is resolved per lattice sample instead (didx)
+    // dynamic layer as two screen windows (0: boxes [0, dsplit), 1: boxes [dsplit, ndyn), each the bounding box of its boxes cut to
+    // the view): rows [dy0, dy0 + dnr), pixels [dx0, dx0 + 8 dnw), dx0 % 8 == 0, words dwin[g * DHALF ..); nibble = 1 + box - first box
+    int dx0[2], dy0[2], dnw[2], dnr[2];
     union {
-        alignas(16) uint32_t dwin[DWORDS];   // window mode: one nibble per screen pixel, the code of the newest box painted there
+        alignas(16) uint32_t dwin[DWORDS];   // window mode: one nibble per screen pixel and window, the code of the newest box painted there
         alignas(16) uint8_t didx[LAT][LAT];  // lattice mode: palette index of the newest dynamic box on the sample, 0: none
     };
     alignas(16) uint8_t swin[WROWS * WPITCH];  // the static screen rows, 2 bits per pixel
@@ -623,10 +624,13 @@ k_render(int n, EnvState st, const render::Camera *__restrict__ cams, hope_param
                          :: "r"(dst), "l"(src + (size_t)r * SCREEN_PITCH), "r"(bytes), "r"(bar) : "memory");
         }
     }
-    if (warp == 0) {  // the dynamic layer's window: bounding box of the boxes, cut to what the lattice can touch
+    const int dsplit = (ndyn + 1) >> 1;
+    static_assert(NDYN <= 30, "(NDYN + 1) / 2 codes per window fit a nibble");
+    if (warp < 2) {  // the windows of the dynamic layer, warp g for window g: bounding box of its boxes, cut to what the lattice can touch
         int x0 = 0x7fff, y0 = 0x7fff, x1 = -0x8000, y1 = -0x8000;
-        if (lane < ndyn) {
-            const Shape &S = sm.shapes[lane];
+        const int d = (warp ? dsplit : 0) + lane;
+        if (d < (warp ? ndyn : dsplit)) {
+            const Shape &S = sm.shapes[d];
             if (S.miny <= S.maxy) { x0 = S.minx; x1 = S.maxx; y0 = S.miny; y1 = S.maxy; }
         }
         static_assert(NDYN <= 32, "one lane per dynamic box");
@@ -639,8 +643,7 @@ k_render(int n, EnvState st, const render::Camera *__restrict__ cams, hope_param
             x0 = max(x0, cam.wx0); x1 = min(x1, cam.wx1); y0 = max(y0, cam.wy0); y1 = min(y1, cam.wy1);
             int dnw = 0, dnr = 0;
             if (x0 <= x1 && y0 <= y1) { dnw = ((x1 >> 3) - (x0 >> 3) + 1) | 1; dnr = y1 - y0 + 1; }  // odd pitch: the row owners (consecutive rows) hit different banks
-            const int lattice = dnw * dnr > DWORDS || (force_lattice && dnr > 0);
-            sm.dx0 = x0 & ~7; sm.dy0 = y0; sm.dnw = lattice ? 0 : dnw; sm.dnr = lattice ? 0 : dnr; sm.lattice_mode = lattice;
+            sm.dx0[warp] = x0 & ~7; sm.dy0[warp] = y0; sm.dnw[warp] = dnw; sm.dnr[warp] = dnr;
         }
     }
     // screen pixel (0, 0) of the static screen, for rotate()'s background colour: only read when a sample can leave the screen, and
@@ -692,24 +695,32 @@ k_render(int n, EnvState st, const render::Camera *__restrict__ cams, hope_param
     __syncthreads();
     const int a0 = cam.a0, a1 = cam.a1, a2 = cam.a2, b0 = cam.b0, b1 = cam.b1, b2 = cam.b2;
     // ---------------------------------------------------------------- 4. dynamic layer
-    const int dx0 = sm.dx0, dy0 = sm.dy0, dnw = sm.dnw, dnr = sm.dnr;
-    const bool lattice_mode = sm.lattice_mode != 0;
+    // a window that does not fit its half of dwin (a trail of more than ~ 150 x 150 pixels per half inside the view): lattice mode
+    const bool lattice_mode = sm.dnw[0] * sm.dnr[0] > DHALF || sm.dnw[1] * sm.dnr[1] > DHALF || (force_lattice && sm.dnr[0] + sm.dnr[1] > 0);
+    const int dxA = sm.dx0[0], dyA = sm.dy0[0], dwA = lattice_mode ? 0 : sm.dnw[0], drA = lattice_mode ? 0 : sm.dnr[0];
+    const int dxB = sm.dx0[1], dyB = sm.dy0[1], dwB = lattice_mode ? 0 : sm.dnw[1], drB = lattice_mode ? 0 : sm.dnr[1];
     if (!lattice_mode) {
-        // window mode: a thread owns a window row and paints the boxes' runs on it old -> new (the painter's order) as nibbles, whole
-        // words between the ends; rows are independent, so there is nothing to wait for.  (Measured on B200 before this: one pass
-        // per box with a block barrier, and rows dealt to warps modulo 8 with four lanes per row: 2.5 and 4.7 times the instructions.)
+        // window mode: a thread owns a window row and paints its window's boxes' runs on it old -> new (the painter's order) as
+        // nibbles, whole words between the ends; rows are independent, so there is nothing to wait for.  Lanes 0-15 of warp w own rows
+        // 16 w .. 16 w + 15 (+ 128, ...) of window 0, lanes 16-31 the same rows of window 1: the two halves of the boxes go side by
+        // side, and a thread walks (ndyn + 1) / 2 boxes at most.  (Measured on B200 before this: one pass per box with a block
+        // barrier; rows dealt to warps modulo 8 with four lanes per row; one window for all boxes, whose 21-box chain per row left
+        // the other warps waiting at the barrier for a quarter of the kernel.)
+        const int g = lane >> 4;
+        const int dx0 = g ? dxB : dxA, dy0 = g ? dyB : dyA, dnw = g ? dwB : dwA, dnr = g ? drB : drA;
+        const int dfirst = g ? dsplit : 0, dcount = g ? ndyn - dsplit : dsplit;
+        uint32_t *win = sm.dwin + g * DHALF;
 #pragma unroll 1
-        // Rows go to warps in blocks of 16 (lanes 0-15: rows 16 w .. 16 w + 15, lanes 16-31: the same + 128): a box touches
-        // few warps, a trail of 128 rows all eight.
-        for (int wr = ((lane >> 4) << 7) | (warp << 4) | (lane & 15); wr < dnr; wr += THREADS) {
+        for (int wr = (warp << 4) | (lane & 15); wr < dnr; wr += THREADS / 2) {
             const int y = wr + dy0, xend = 8 * dnw - 1;
-            uint32_t *row = sm.dwin + wr * dnw;
+            uint32_t *row = win + wr * dnw;
 #pragma unroll 1
-            for (int d = 0, code = (int)CODE_VEHICLE; d < ndyn; ++d, code = code >= CODE_MOD ? 1 : code + 1) {  // 15, then 1 + (d - 1) % 14
+            for (int k = 0; k < dcount; ++k) {
+                const int d = dfirst + k;
                 const short2 dr = sm.drange[d];
                 if (y < dr.x || y > dr.y) continue;
                 const short2 e = sm.dyn[d][y - dr.x];
-                const uint32_t fill = (uint32_t)code * 0x11111111u;
+                const uint32_t fill = (uint32_t)(k + 1) * 0x11111111u;
                 if (e.x != DYN_DIRECT) {
                     const int na = max((int)e.x - dx0, 0), nb = min((int)e.y - dx0, xend);
                     if (na <= nb) {
@@ -786,31 +797,31 @@ k_render(int n, EnvState st, const render::Camera *__restrict__ cams, hope_param
                 return (unsigned)*reinterpret_cast<const unsigned short *>(&sm.didx[2 * j_][2 * i_]) |
                        ((unsigned)*reinterpret_cast<const unsigned short *>(&sm.didx[2 * j_ + 1][2 * i_]) << 16);
             // the four samples lie within two pixels of the first
-            if ((unsigned)((fyb >> 16) - dy0 + 2) >= (unsigned)(dnr + 4) || (unsigned)((fxb >> 16) - dx0 + 2) >= (unsigned)(8 * dnw + 4)) return 0u;
+            const int sx0 = fxb >> 16, sy0 = fyb >> 16;
+            const bool nearA = (unsigned)(sy0 - dyA + 2) < (unsigned)(drA + 4) && (unsigned)(sx0 - dxA + 2) < (unsigned)(8 * dwA + 4);
+            const bool nearB = (unsigned)(sy0 - dyB + 2) < (unsigned)(drB + 4) && (unsigned)(sx0 - dxB + 2) < (unsigned)(8 * dwB + 4);
+            if (!nearA && !nearB) return 0u;
             unsigned out4 = 0u;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int fx = fxb + ((k & 1) ? a1 : 0) + ((k >> 1) ? a2 : 0), fy = fyb + ((k & 1) ? b1 : 0) + ((k >> 1) ? b2 : 0);
-                const int sx = fx >> 16, sy = fy >> 16, rx = sx - dx0, ry = sy - dy0;
-                if ((unsigned)ry < (unsigned)dnr && (unsigned)rx < (unsigned)(8 * dnw)) {
-                    const unsigned c = (sm.dwin[ry * dnw + (rx >> 3)] >> (4 * (rx & 7))) & 15u;
-                    if (c) {
-                        unsigned idx = 4u;
-                        if (c != CODE_VEHICLE) {
-                            int d = (int)c;  // trajectory box t = c - 1, unless the one CODE_MOD steps newer covers the pixel too
-                            if (d + CODE_MOD <= ntraj) {
-                                const int d1 = d + CODE_MOD;
-                                const unsigned r1 = (unsigned)(sy - sm.drange[d1].x);
-                                if (r1 < (unsigned)DROWS) {
-                                    const short2 e = sm.dyn[d1][r1];
-                                    if ((sx >= e.x && sx <= e.y) || (e.x == DYN_DIRECT && shape_covers(sm.shapes[d1], sx, sy))) d = d1;
-                                }
-                            }
-                            idx = (unsigned)(5 + traj_len - ntraj + d - 1);
-                        }
-                        out4 |= idx << (8 * k);
+                const int sx = fx >> 16, sy = fy >> 16;
+                int d = -1;  // the newer half's window first
+                {
+                    const int rx = sx - dxB, ry = sy - dyB;
+                    if ((unsigned)ry < (unsigned)drB && (unsigned)rx < (unsigned)(8 * dwB)) {
+                        const unsigned c = (sm.dwin[DHALF + ry * dwB + (rx >> 3)] >> (4 * (rx & 7))) & 15u;
+                        if (c) d = dsplit + (int)c - 1;
                     }
                 }
+                if (d < 0) {
+                    const int rx = sx - dxA, ry = sy - dyA;
+                    if ((unsigned)ry < (unsigned)drA && (unsigned)rx < (unsigned)(8 * dwA)) {
+                        const unsigned c = (sm.dwin[ry * dwA + (rx >> 3)] >> (4 * (rx & 7))) & 15u;
+                        if (c) d = (int)c - 1;
+                    }
+                }
+                if (d >= 0) out4 |= (d == 0 ? 4u : (unsigned)(5 + traj_len - ntraj + d - 1)) << (8 * k);
             }
             return out4;
         };
