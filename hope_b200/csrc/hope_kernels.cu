@@ -517,6 +517,7 @@ struct hope_ctx {
     render::Camera *d_cams = nullptr;
     uint8_t *d_screen = nullptr;      // [N][500][125]: the static part of every env's screen, 2 bits per pixel (k_render_static), allocated with the first image
     uint2 *d_screen_key = nullptr;
+    uint8_t *d_spanrec = nullptr;     // [N][render::SPANREC]: what each box of the trajectory ring buffer paints on its screen rows, with the pose it was computed from
     int *d_repaint = nullptr, *d_repaint_n = nullptr;  // [N] each: envs whose static screen is stale (k_render_camera -> k_render_static), per env range: list at [lo ..), its length at [lo]
     int render_traj_len = render::TRAJ;  // hope_set_render_traj: configs.py:86 TRAJ_RENDER_LEN (0: RENDER_TRAJ off)
     int render_force_lattice = 0;     // HOPE_B200_RENDER_LATTICE=1 (tests): k_render resolves the dynamic layer per lattice sample even when its window fits    // [N]: (pool slot, its regeneration count) the cached screen was painted for; all ones = none
@@ -804,7 +805,7 @@ int launch_range(hope_ctx *ctx, const double *d_action, const hope_out &out_all,
             CK(cudaMemsetAsync(repaint_n, 0, sizeof(int), so));
             k_render_camera<<<(n + 127) / 128, 128, 0, so>>>(n, pool, st, ctx->par, cams, ctx->d_episode, ctx->d_screen_key + lo, repaint, repaint_n);
             k_render_static<<<std::min(n, ctx->sm_count * 4), render::THREADS, sizeof(render::Smem), so>>>(pool, st, ctx->d_episode, cams, ctx->par, screen, ctx->d_screen_key + lo, repaint, repaint_n);
-            k_render<<<n, render::THREADS, sizeof(render::SmemDyn), so>>>(n, st, cams, ctx->par, ctx->palette, screen, out.img, ctx->render_traj_len, ctx->render_force_lattice);
+            k_render<<<n, render::THREADS, sizeof(render::SmemDyn), so>>>(n, st, cams, ctx->par, ctx->palette, screen, out.img, ctx->d_spanrec + (size_t)lo * render::SPANREC, ctx->render_traj_len, ctx->render_force_lattice);
             ctx->launches++;
             prof_mark(ctx, 6, so);
             ctx->launches++;
@@ -846,7 +847,7 @@ int launch_range(hope_ctx *ctx, const double *d_action, const hope_out &out_all,
         CK(cudaMemsetAsync(repaint_n, 0, sizeof(int), s));
         k_render_camera<<<(n + 127) / 128, 128, 0, s>>>(n, pool, st, ctx->par, cams, ctx->d_episode, ctx->d_screen_key + lo, repaint, repaint_n);
         k_render_static<<<std::min(n, ctx->sm_count * 4), render::THREADS, sizeof(render::Smem), s>>>(pool, st, ctx->d_episode, cams, ctx->par, screen, ctx->d_screen_key + lo, repaint, repaint_n);
-        k_render<<<n, render::THREADS, sizeof(render::SmemDyn), s>>>(n, st, cams, ctx->par, ctx->palette, screen, out.img, ctx->render_traj_len, ctx->render_force_lattice);
+        k_render<<<n, render::THREADS, sizeof(render::SmemDyn), s>>>(n, st, cams, ctx->par, ctx->palette, screen, out.img, ctx->d_spanrec + (size_t)lo * render::SPANREC, ctx->render_traj_len, ctx->render_force_lattice);
         prof_mark(ctx, 6, s);
         ctx->launches += 2;
     }
@@ -876,6 +877,8 @@ int ensure_screen(hope_ctx *ctx) {
     if (ctx->d_screen) return HOPE_OK;
     CK(cudaMalloc(&ctx->d_screen, (size_t)ctx->n * render::SCREEN_BYTES));
     CK(cudaMalloc(&ctx->d_screen_key, sizeof(uint2) * (size_t)ctx->n));
+    CK(cudaMalloc(&ctx->d_spanrec, (size_t)ctx->n * render::SPANREC));
+    CK(cudaMemset(ctx->d_spanrec, 0xff, (size_t)ctx->n * render::SPANREC));  // NaN poses: no record matches
     CK(cudaMalloc(&ctx->d_repaint, sizeof(int) * (size_t)ctx->n));
     CK(cudaMalloc(&ctx->d_repaint_n, sizeof(int) * (size_t)ctx->n));
     CK(cudaMemset(ctx->d_screen_key, 0xff, sizeof(uint2) * (size_t)ctx->n));
@@ -1092,7 +1095,7 @@ int hope_destroy(hope_ctx *ctx) {
     cudaSetDevice(ctx->device);
     void *ptrs[] = {ctx->d_obs, ctx->d_aabb, ctx->d_meta, ctx->d_nv, ctx->d_nobs, ctx->d_tab, ctx->d_pose, ctx->d_accum, ctx->d_t,
                     ctx->d_scene, ctx->d_pending, ctx->d_gate, ctx->d_counters, ctx->d_words, ctx->d_ntry, ctx->d_ncand, ctx->d_cs, ctx->d_item_base, ctx->d_items, ctx->d_item_bad, ctx->d_slots, ctx->d_n_items, ctx->d_plan_rem, ctx->d_plan_u8, ctx->d_regen_slots, ctx->d_regen_count, ctx->d_gen_status, ctx->d_episode,
-                    ctx->d_action, ctx->d_stage, ctx->d_stage_img, ctx->d_traj, ctx->d_traj_n, ctx->d_cams, ctx->d_screen, ctx->d_screen_key, ctx->d_repaint, ctx->d_repaint_n};
+                    ctx->d_action, ctx->d_stage, ctx->d_stage_img, ctx->d_traj, ctx->d_traj_n, ctx->d_cams, ctx->d_screen, ctx->d_screen_key, ctx->d_repaint, ctx->d_repaint_n, ctx->d_spanrec};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->host_graph) cudaGraphExecDestroy(ctx->host_graph);

@@ -106,6 +106,15 @@ struct Smem {                           // k_render_static
 constexpr int LAT = 2 * IMG;
 constexpr int WROWS = 360;              // screen rows the lattice can touch: 253 sqrt(2) (1 + 2^-15) + 2 <= 360
 constexpr int DWORDS = 6144;            // capacity of the dynamic layer's screen window, 8 pixels per word (e.g. 192 rows x 256 pixels)
+// A trajectory box is drawn for up to 20 steps at the same screen place (only the camera moves), so the run it paints on each of its
+// rows is computed once, the step it joins the trail, and kept in HBM beside the pose it belongs to (one record per env and slot of
+// the trajectory ring buffer); a later step takes the record iff pose and screen offsets are the ones it would compute from.
+// Per env: the 20 slots' runs (short2[64] each, 5 120 B: ONE bulk copy into the span table, requested before anything else),
+// then the 20 heads (x, y, cos h, sin h, kbx, kby as float64 + padding).
+constexpr int SPANREC_HEAD = 64;
+constexpr int SPANREC_RUNS = TRAJ * DROWS * 4;
+constexpr int SPANREC = SPANREC_RUNS + TRAJ * SPANREC_HEAD;   // per env
+static_assert(SPANREC % 16 == 0 && SPANREC_RUNS % 16 == 0, "bulk-copy source alignment");
 constexpr int DHALF = DWORDS / 2;        // the older and the newer half of the boxes are painted into windows of their own
 constexpr int WCHUNK = 7;               // 16-byte chunks (64 pixels) per staged row: 361 pixels straddle at most 7
 constexpr int WPITCH = WCHUNK * 16;
@@ -116,12 +125,15 @@ struct SmemDyn {                        // k_render
     int ndyn;
     uint32_t probe;                     // palette index of screen pixel (0, 0): rotate()'s background colour
     int wy0, nrows, cb0, nch;           // staged window: screen rows [wy0, wy0 + nrows), 16-byte chunks [cb0, cb0 + nch) of each
-    alignas(8) unsigned long long bar;  // mbarrier of the staging copies
+    alignas(8) unsigned long long bar;  // mbarrier of the static rows
+    alignas(8) unsigned long long bar2; // mbarrier of the span records
+    int slot0;                          // ring slot of trajectory box 1 (the oldest drawn)
     alignas(16) Shape shapes[NDYN];     // vehicle box (0), trajectory boxes old -> new (1 ..)
     short2 drange[NDYN];                // (miny, maxy) of dynamic box d
     uchar4 lbox[NDYN];                  // lattice columns [x, y] and rows [z, w] the box can cover (x > y: none)
     uint32_t pal[NCOLOR];               // R | G << 10 | B << 20: four samples add without carry
-    short2 dyn[NDYN][DROWS];            // span of dynamic box d on screen row miny_d + r; x > y: nothing; x == DYN_DIRECT: evaluate
+    uint8_t hit[NDYN + 3];              // the span record of the box's ring slot is valid
+    alignas(16) short2 dyn[NDYN][DROWS];  // [ring slot of the trajectory box (see dslot), TRAJ for the vehicle]: span of the box on screen row miny_d + r; x > y: nothing; x == DYN_DIRECT: evaluate
     // dynamic layer as two screen windows (0: boxes [0, dsplit), 1: boxes [dsplit, ndyn), each the bounding box of its boxes cut to
     // the view): rows [dy0, dy0 + dnr), pixels [dx0, dx0 + 8 dnw), dx0 % 8 == 0, words dwin[g * DHALF ..); nibble = 1 + box - first box
     int dx0[2], dy0[2], dnw[2], dnr[2];
@@ -510,14 +522,22 @@ k_render_static(Pool pool, EnvState st, const unsigned *__restrict__ episode, co
 // traj_len <= TRAJ: how many of them are drawn, in the colours 5 + traj_len - ntraj .. of the palette (TRAJ_COLORS[-ntraj:])
 __global__ void __launch_bounds__(render::THREADS, 3)
 k_render(int n, EnvState st, const render::Camera *__restrict__ cams, hope_params par, render::Palette pal, const uint8_t *__restrict__ screen,
-         uint8_t *__restrict__ img, int traj_len, int force_lattice) {
+         uint8_t *__restrict__ img, uint8_t *__restrict__ spanrec, int traj_len, int force_lattice) {
     using namespace render;
     extern __shared__ __align__(16) unsigned char render_smem_raw[];
     SmemDyn &sm = *reinterpret_cast<SmemDyn *>(render_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int env = blockIdx.x;
     const uint8_t *scr = screen + (size_t)env * SCREEN_BYTES;
-    const unsigned bar = (unsigned)__cvta_generic_to_shared(&sm.bar);
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&sm.bar), bar2 = (unsigned)__cvta_generic_to_shared(&sm.bar2);
+    uint8_t *const rec = spanrec + (size_t)env * SPANREC;
+    if (tid == 0) {  // the span records of all 20 ring slots, whatever they hold: they are validated when they are here
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar2) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar2), "r"(SPANREC_RUNS) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"((unsigned)__cvta_generic_to_shared(&sm.dyn[0][0])), "l"(rec), "r"(SPANREC_RUNS), "r"(bar2) : "memory");
+    }
     // ---------------------------------------------------------------- 1. set-up
     static_assert(offsetof(SmemDyn, dwin) % 16 == 0 && offsetof(SmemDyn, swin) % 16 == 0 && DWORDS % (4 * THREADS) == 0 && DWORDS * 4 >= LAT * LAT,
                   "cleared as uint4; bulk copy targets; didx fits");
@@ -559,10 +579,11 @@ k_render(int n, EnvState st, const render::Camera *__restrict__ cams, hope_param
     {
         const int tn = st.traj_n[env];
         const int ntraj = tn > 1 ? min(tn, traj_len) : 0;  // car_parking_base.py:315-316; traj_len = TRAJ_RENDER_LEN, 0 when RENDER_TRAJ is off
-        if (tid == 0) sm.ndyn = 1 + ntraj;
+        if (tid == 0) { sm.ndyn = 1 + ntraj; sm.slot0 = (tn - ntraj) % TRAJ; }
         // dynamic box d: 0 = the vehicle (warp 1, lane 0), 1 + i = trajectory box i, old -> new (warp 0)
         int d = -1;
         if (tid < ntraj) d = 1 + tid; else if (tid == 32) d = 0;
+        bool hit = false;
         if (d >= 0) {
             Shape &S = sm.shapes[d];
             double bx[4], by[4];
@@ -581,7 +602,12 @@ k_render(int n, EnvState st, const render::Camera *__restrict__ cams, hope_param
                 const double2 *p = reinterpret_cast<const double2 *>(st.traj) + ((size_t)env * TRAJ + (tn - back) % TRAJ) * 2;
                 const double2 xy = p[0], cs = p[1];
                 x = xy.x; y = xy.y; c = cs.x; sn = cs.y;
+                // the span record of this ring slot: valid iff it was computed from this very pose and these screen offsets
+                const double2 *h = reinterpret_cast<const double2 *>(rec + SPANREC_RUNS + ((tn - back) % TRAJ) * SPANREC_HEAD);
+                const double2 h0 = h[0], h1 = h[1], h2 = h[2];
+                hit = h0.x == x && h0.y == y && h1.x == c && h1.y == sn && h2.x == cam.kbx && h2.y == cam.kby;
             }
+            sm.hit[d] = hit ? 1 : 0;
             vehicle_box(x, y, c, sn, par.box_x, par.box_y, bx, by);
             ring_shape(S, cam, bx, by, 4, 0, 0);
             if (skip) { S.miny = 1; S.maxy = 0; }
@@ -610,6 +636,7 @@ k_render(int n, EnvState st, const render::Camera *__restrict__ cams, hope_param
             }
             sm.lbox[d] = lb;
         }
+
     }
     __syncthreads();
     const Camera &cam = sm.cam;
@@ -651,8 +678,17 @@ k_render(int n, EnvState st, const render::Camera *__restrict__ cams, hope_param
     unsigned probe_static = 0u;
     if (tid == THREADS - 1 && !sm.fast) probe_static = scr[0];
     // ---------------------------------------------------------------- 3. span table of the dynamic boxes
+    const int slot0 = sm.slot0;
+    // span-table row of dynamic box d: its slot of the trajectory ring buffer (the records arrive in ring order), TRAJ for the vehicle
+    auto dslot = [&](int d) -> int { const int s = slot0 + d - 1; return d == 0 ? TRAJ : (s >= TRAJ ? s - TRAJ : s); };
+    {   // the span records have landed (requested first thing): what is computed below overwrites the stale ones
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar2) : "memory");
+    }
     for (int idx = tid; idx < ndyn * DROWS; idx += THREADS) {
         const int d = idx / DROWS, r = idx - d * DROWS;
+        if (sm.hit[d]) continue;
         const Shape &S = sm.shapes[d];
         const int y = S.miny + r;
         short2 e = make_short2(1, 0);  // nothing on this row
@@ -690,7 +726,16 @@ k_render(int n, EnvState st, const render::Camera *__restrict__ cams, hope_param
                     }
             }
         }
-        sm.dyn[d][r] = e;
+        const int slot = dslot(d);
+        sm.dyn[slot][r] = e;
+        if (d > 0) {  // keep it for the steps to come
+            reinterpret_cast<short2 *>(rec)[slot * DROWS + r] = e;
+            if (r == 0) {
+                const double2 *p = reinterpret_cast<const double2 *>(st.traj) + ((size_t)env * TRAJ + slot) * 2;
+                double2 *h = reinterpret_cast<double2 *>(rec + SPANREC_RUNS + slot * SPANREC_HEAD);
+                h[0] = p[0]; h[1] = p[1]; h[2] = make_double2(cam.kbx, cam.kby);
+            }
+        }
     }
     __syncthreads();
     const int a0 = cam.a0, a1 = cam.a1, a2 = cam.a2, b0 = cam.b0, b1 = cam.b1, b2 = cam.b2;
@@ -719,7 +764,7 @@ k_render(int n, EnvState st, const render::Camera *__restrict__ cams, hope_param
                 const int d = dfirst + k;
                 const short2 dr = sm.drange[d];
                 if (y < dr.x || y > dr.y) continue;
-                const short2 e = sm.dyn[d][y - dr.x];
+                const short2 e = sm.dyn[dslot(d)][y - dr.x];
                 const uint32_t fill = (uint32_t)(k + 1) * 0x11111111u;
                 if (e.x != DYN_DIRECT) {
                     const int na = max((int)e.x - dx0, 0), nb = min((int)e.y - dx0, xend);
@@ -764,7 +809,7 @@ k_render(int n, EnvState st, const render::Camera *__restrict__ cams, hope_param
                     const int sx = (fxr + a1 * u) >> 16, sy = (fyr + b1 * u) >> 16;
                     const unsigned r = (unsigned)(sy - miny);
                     if (r < (unsigned)DROWS && sm.didx[b][a] == 0) {
-                        const short2 e = sm.dyn[d][r];
+                        const short2 e = sm.dyn[dslot(d)][r];
                         if ((sx >= e.x && sx <= e.y) || (e.x == DYN_DIRECT && shape_covers(sm.shapes[d], sx, sy))) sm.didx[b][a] = pidx;
                     }
                 }
@@ -778,7 +823,7 @@ k_render(int n, EnvState st, const render::Camera *__restrict__ cams, hope_param
         sm.probe = idx;
     }
     __syncthreads();
-    {   // the staged rows have landed
+    {   // the staged static rows have landed
         unsigned done = 0;
         while (!done)
             asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar) : "memory");
