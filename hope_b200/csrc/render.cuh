@@ -23,7 +23,11 @@
 //      dynamic box (vehicle + the last <= 20 trajectory boxes) prepares its scan-conversion record;
 //   2. the window's rows of the cached static screen are fetched with cp.async.bulk (one copy per row, <= 112 B, completion
 //      counted by one mbarrier) and land under steps 3 and 4: 40 KB of shared memory hold them;
-//   3. span table: the run every dynamic box paints on each of its <= 64 screen rows, one (box, row) pair per thread and pass;
+//   3. span table: the run every dynamic box paints on each of its <= 64 screen rows.  A trajectory box stays where it is for the
+//      20 steps it is drawn (only the camera moves), so its runs are computed ONCE, the step it joins the trail, and kept in HBM
+//      beside the pose they belong to (6.4 KB per env: one record per slot of the trajectory ring buffer).  All 20 records arrive
+//      by one 5 KB bulk copy requested before anything else; a record is used iff its pose and screen offsets are the ones this
+//      step would compute from, else the runs are computed (one (box, row) pair per thread and pass) and the record rewritten;
 //   4. dynamic layer: windows of one NIBBLE per screen pixel over the boxes' bounding box (cut to the view): a thread owns a window
 //      row and writes its boxes' runs on it old -> new, whole words between the ends.  The older and the newer half of the boxes
 //      have a window each (2 x 12 KB; the gather asks the newer one first): the two halves are painted side by side by the two
@@ -33,10 +37,10 @@
 //   5. gather: a warp resolves 8 x 4 output pixels per round; an output pixel = 4 samples; a sample = the dynamic layer's box if any,
 //      else the 2-bit static pixel of the staged rows; palette sums in one packed word (10-bit lanes), rounded mean, uint8
 //      [3][64][64] (the reference's float64 image is this / 255).
-// HBM traffic per env-step: 12 288 B written + 20-41 KB of static rows read (mostly from L2 after the first step of an
-// episode: the 64 KB screen of an env is re-read every step) + ~1.3 KB of pose / trajectory.
+// HBM traffic per env-step: 12 288 B written + 20-41 KB of static rows + 6.4 KB of span records read + ~1.3 KB of pose /
+// trajectory (measured: 48 KB read, 11.5 KB written per image).
 // History (profiles/r02_ncu_k_render_history.txt): round 1 painted the whole window per step with one thread per window row
-// (6.5 ms per 65 536 images); order-free painting of four quadrant windows 4.9 ms; this design 3.2 ms.
+// (6.5 ms per 65 536 images); order-free painting of four quadrant windows 4.9 ms; this design 2.9 ms.
 #pragma once
 
 namespace render {
