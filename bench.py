@@ -503,7 +503,7 @@ def main():
     if not args.no_secondary:
         K2, W2 = min(K, 16), 4
         secondary = {"cfg4": measure_rollout(env, rank, local_rank, world, dev, K2, W2),
-                     "cfg5": measure_sac(env, rank, local_rank, world, dev, K2, W2)}
+                     "cfg5": measure_sac(env, rank, local_rank, world, dev, 64, 16)}  # 8 updates in the timed region (0.2 s): one host hiccup in 16 steps had tripled the figure
         # cfg 4 as the reference ships it (USE_IMG: 4-modal actor, image observation rendered every step): the same scenes, a
         # second env with the image stage on
         env_img = BatchedParkingEnv(n, scenes=scenes, device=local_rank, auto_reset=True, use_img_observation=True)
