@@ -188,6 +188,45 @@ def test_trajectory_length_follows_configs(length, render_traj):
     env.close()
 
 
+@pytest.mark.parametrize("regenerate", [False, True])
+def test_static_screen_follows_auto_reset_and_regeneration(regenerate):
+    """The static part of the screen is cached per env and keyed by (pool slot, regeneration count of the slot): an env that
+    auto-resets onto the next pool scene, or whose slot is regenerated on the device, must get a fresh screen (and its
+    trajectory records must not survive the reset)."""
+    n = 96
+    if regenerate:
+        env = BatchedParkingEnv(n, pool_size=n, level="Normal", seed=5, auto_reset=True, device_scenes=True, use_img_observation=True)
+    else:
+        pool = generate_scenes(2 * n, "Normal", 11)
+        env = BatchedParkingEnv(n, scenes=pool, auto_reset=True, use_img_observation=True)
+    env.reset()
+    pool = env.get_scene_pool()
+    book = io.TrajectoryBook(n)
+    sid = env.get_state()["scene_id"]
+    for i in range(n):
+        book.reset(i, pool["start"][sid[i]])
+    act = torch.zeros((n, 2), dtype=torch.float64, device=env.device); act[:, 1] = 1.0  # straight ahead until something ends the episode
+    act[:, 0] = torch.linspace(-0.5, 0.5, n, dtype=torch.float64, device=env.device)
+    resets, compared = 0, 0
+    for k in range(40):
+        obs, _, _, _ = env.step(act)
+        pose, sub, ret, was = (_np(env.out[key]) for key in ("pose", "substeps", "retreated", "was_reset"))
+        if was.any():
+            pool, sid = env.get_scene_pool(), env.get_state()["scene_id"]
+        for i in range(n):
+            if was[i]:
+                book.reset(i, pose[i]); resets += 1
+            else:
+                book.step(i, pose[i], sub[i], ret[i])
+        ids = [i for i in range(n) if was[i]][:6] + list(range(k % 8, n, 8))
+        scenes = {key: pool[key][sid] for key in ("start", "dest", "bounds", "obs", "nverts")}
+        got, want = _np(obs["img"])[ids], _oracle_images(scenes, book, ids)
+        assert np.array_equal(got, want), f"step {k}: (images, bytes) differing = {_mismatch(got, want)}"
+        compared += len(ids)
+    assert resets >= n // 2 and compared >= 400
+    env.close()
+
+
 def test_quarter_turn_headings_take_the_rotate90_path():
     n = 8
     sc = generate_scenes(n, "Normal", 77)
