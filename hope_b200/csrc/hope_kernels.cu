@@ -520,7 +520,8 @@ struct hope_ctx {
     uint8_t *d_spanrec = nullptr;     // [N][render::SPANREC]: what each box of the trajectory ring buffer paints on its screen rows, with the pose it was computed from
     int *d_repaint = nullptr, *d_repaint_n = nullptr;  // [N] each: envs whose static screen is stale (k_render_camera -> k_render_static), per env range: list at [lo ..), its length at [lo]
     int render_traj_len = render::TRAJ;  // hope_set_render_traj: configs.py:86 TRAJ_RENDER_LEN (0: RENDER_TRAJ off)
-    int render_force_lattice = 0;     // HOPE_B200_RENDER_LATTICE=1 (tests): k_render resolves the dynamic layer per lattice sample even when its window fits    // [N]: (pool slot, its regeneration count) the cached screen was painted for; all ones = none
+    int render_force_lattice = 0;
+    size_t render_pad = 0;            // HOPE_B200_RENDER_PAD_KB: extra dynamic shared memory per k_render CTA (fewer resident CTAs, room for the step kernels beside them)     // HOPE_B200_RENDER_LATTICE=1 (tests): k_render resolves the dynamic layer per lattice sample even when its window fits    // [N]: (pool slot, its regeneration count) the cached screen was painted for; all ones = none
     double *d_plan_rem = nullptr;
     uint8_t *d_plan_u8 = nullptr;  // types[N][5] | big[N] | n[N] | seg[N] | active[N]
     int sm_count = 148, walk_blocks = 148 * 4, check_blocks = 148 * 4, host_check_blocks = 148 * 4;
@@ -805,7 +806,7 @@ int launch_range(hope_ctx *ctx, const double *d_action, const hope_out &out_all,
             CK(cudaMemsetAsync(repaint_n, 0, sizeof(int), so));
             k_render_camera<<<(n + 127) / 128, 128, 0, so>>>(n, pool, st, ctx->par, cams, ctx->d_episode, ctx->d_screen_key + lo, repaint, repaint_n);
             k_render_static<<<std::min(n, ctx->sm_count * 4), render::THREADS, sizeof(render::Smem), so>>>(pool, st, ctx->d_episode, cams, ctx->par, screen, ctx->d_screen_key + lo, repaint, repaint_n);
-            k_render<<<n, render::THREADS, sizeof(render::SmemDyn), so>>>(n, st, cams, ctx->par, ctx->palette, screen, out.img, ctx->d_spanrec + (size_t)lo * render::SPANREC, ctx->render_traj_len, ctx->render_force_lattice);
+            k_render<<<n, render::THREADS, sizeof(render::SmemDyn) + ctx->render_pad, so>>>(n, st, cams, ctx->par, ctx->palette, screen, out.img, ctx->d_spanrec + (size_t)lo * render::SPANREC, ctx->render_traj_len, ctx->render_force_lattice);
             ctx->launches++;
             prof_mark(ctx, 6, so);
             ctx->launches++;
@@ -847,7 +848,7 @@ int launch_range(hope_ctx *ctx, const double *d_action, const hope_out &out_all,
         CK(cudaMemsetAsync(repaint_n, 0, sizeof(int), s));
         k_render_camera<<<(n + 127) / 128, 128, 0, s>>>(n, pool, st, ctx->par, cams, ctx->d_episode, ctx->d_screen_key + lo, repaint, repaint_n);
         k_render_static<<<std::min(n, ctx->sm_count * 4), render::THREADS, sizeof(render::Smem), s>>>(pool, st, ctx->d_episode, cams, ctx->par, screen, ctx->d_screen_key + lo, repaint, repaint_n);
-        k_render<<<n, render::THREADS, sizeof(render::SmemDyn), s>>>(n, st, cams, ctx->par, ctx->palette, screen, out.img, ctx->d_spanrec + (size_t)lo * render::SPANREC, ctx->render_traj_len, ctx->render_force_lattice);
+        k_render<<<n, render::THREADS, sizeof(render::SmemDyn) + ctx->render_pad, s>>>(n, st, cams, ctx->par, ctx->palette, screen, out.img, ctx->d_spanrec + (size_t)lo * render::SPANREC, ctx->render_traj_len, ctx->render_force_lattice);
         prof_mark(ctx, 6, s);
         ctx->launches += 2;
     }
@@ -1066,11 +1067,12 @@ int hope_create(hope_ctx **out, int device, int n_envs, int pool_size, const hop
     if (const char *e = getenv("HOPE_B200_HOST_SPLIT")) ctx->host_split = e;
     if (const char *e = getenv("HOPE_B200_HOST_DEBUG")) ctx->host_debug = atoi(e);
     if (const char *e = getenv("HOPE_B200_RENDER_LATTICE")) ctx->render_force_lattice = atoi(e) != 0;
+    if (const char *e = getenv("HOPE_B200_RENDER_PAD_KB")) { int v = atoi(e); if (v > 0 && v <= 150) ctx->render_pad = (size_t)v * 1024; }
     if (const char *e = getenv("HOPE_B200_HOST_RS_AFTER")) ctx->host_rs_after_observe = atoi(e) != 0;
     if (const char *e = getenv("HOPE_B200_HOST_CHUNKS")) { int v = atoi(e); if (v >= 1 && v <= 64) ctx->host_chunks = v; }
     CK(cudaFuncSetAttribute(k_observe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((OBS_THREADS / 32) * sizeof(ObserveSmem))));
     CK(cudaFuncSetAttribute(k_render_static, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(render::Smem)));
-    CK(cudaFuncSetAttribute(k_render, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(render::SmemDyn)));
+    CK(cudaFuncSetAttribute(k_render, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(render::SmemDyn) + ctx->render_pad)));
     {   // a vehicle-sized box covers at most diagonal * K + 2 screen rows after truncation
         double diag = 0.0;
         for (int a = 0; a < 4; ++a)

@@ -108,8 +108,11 @@ struct Smem {                           // k_render_static
 // k_render's sample lattice: cv2's 4x INTER_LINEAR reads crop pixels 4i+1, 4i+2 of either axis = 128 x 128 samples,
 // lattice index a <-> crop pixel 2a + 1 - (a & 1)
 constexpr int LAT = 2 * IMG;
-constexpr int WROWS = 360;              // screen rows the lattice can touch: 253 sqrt(2) (1 + 2^-15) + 2 <= 360
-constexpr int DWORDS = 6144;            // capacity of the dynamic layer's screen window, 8 pixels per word (e.g. 192 rows x 256 pixels)
+// The static rows are staged per HALF of the image (output rows 0-31, then 32-63, through the same buffer): half the lattice touches
+// at most 253 |sin| + 125 |cos| + 2 rows of 253 |cos| + 125 |sin| + 2 pixels, i.e. rows x (16-byte chunks per row) x 16 <= 26 688 bytes
+// over all rotations (against 40 320 for the whole lattice) -- what lets a fourth CTA live on the SM.
+constexpr int SWIN_BYTES = 26688;
+constexpr int DWORDS = 5120;            // capacity of the dynamic layer's screen windows, 8 pixels per word
 // A trajectory box is drawn for up to 20 steps at the same screen place (only the camera moves), so the run it paints on each of its
 // rows is computed once, the step it joins the trail, and kept in HBM beside the pose it belongs to (one record per env and slot of
 // the trajectory ring buffer); a later step takes the record iff pose and screen offsets are the ones it would compute from.
@@ -120,15 +123,13 @@ constexpr int SPANREC_RUNS = TRAJ * DROWS * 4;
 constexpr int SPANREC = SPANREC_RUNS + TRAJ * SPANREC_HEAD;   // per env
 static_assert(SPANREC % 16 == 0 && SPANREC_RUNS % 16 == 0, "bulk-copy source alignment");
 constexpr int DHALF = DWORDS / 2;        // the older and the newer half of the boxes are painted into windows of their own
-constexpr int WCHUNK = 7;               // 16-byte chunks (64 pixels) per staged row: 361 pixels straddle at most 7
-constexpr int WPITCH = WCHUNK * 16;
 
 struct SmemDyn {                        // k_render
     Camera cam;
     int fast;                           // every sample of the image maps inside the screen: no per-sample checks
     int ndyn;
     uint32_t probe;                     // palette index of screen pixel (0, 0): rotate()'s background colour
-    int wy0, nrows, cb0, nch;           // staged window: screen rows [wy0, wy0 + nrows), 16-byte chunks [cb0, cb0 + nch) of each
+    int wy0[2], nrows[2], cb0[2], nch[2];  // staged window of image half h: screen rows [wy0, wy0 + nrows), 16-byte chunks [cb0, cb0 + nch) of each
     alignas(8) unsigned long long bar;  // mbarrier of the static rows
     alignas(8) unsigned long long bar2; // mbarrier of the span records
     int slot0;                          // ring slot of trajectory box 1 (the oldest drawn)
@@ -145,7 +146,7 @@ struct SmemDyn {                        // k_render
         alignas(16) uint32_t dwin[DWORDS];   // window mode: one nibble per screen pixel and window, the code of the newest box painted there
         alignas(16) uint8_t didx[LAT][LAT];  // lattice mode: palette index of the newest dynamic box on the sample, 0: none
     };
-    alignas(16) uint8_t swin[WROWS * WPITCH];  // the static screen rows, 2 bits per pixel
+    alignas(16) uint8_t swin[SWIN_BYTES];  // the static screen rows of one image half, 2 bits per pixel, pitch 16 nch
 };
 
 // _coord_transform + pygame's (int) conversion of one world point
@@ -524,7 +525,7 @@ k_render_static(Pool pool, EnvState st, const unsigned *__restrict__ episode, co
 //      palette sums in one packed word, rounded mean, uint8 [3][64][64] with a warp writing whole 32-byte sectors.
 // traj: [N][20][4] ring buffer (x, y, cos h, sin h) of Vehicle.trajectory's tail, traj_n: [N] its length (see k_advance);
 // traj_len <= TRAJ: how many of them are drawn, in the colours 5 + traj_len - ntraj .. of the palette (TRAJ_COLORS[-ntraj:])
-__global__ void __launch_bounds__(render::THREADS, 3)
+__global__ void __launch_bounds__(render::THREADS, 4)
 k_render(int n, EnvState st, const render::Camera *__restrict__ cams, hope_params par, render::Palette pal, const uint8_t *__restrict__ screen,
          uint8_t *__restrict__ img, uint8_t *__restrict__ spanrec, int traj_len, int force_lattice) {
     using namespace render;
@@ -545,7 +546,7 @@ k_render(int n, EnvState st, const render::Camera *__restrict__ cams, hope_param
     // ---------------------------------------------------------------- 1. set-up
     static_assert(offsetof(SmemDyn, dwin) % 16 == 0 && offsetof(SmemDyn, swin) % 16 == 0 && DWORDS % (4 * THREADS) == 0 && DWORDS * 4 >= LAT * LAT,
                   "cleared as uint4; bulk copy targets; didx fits");
-    static_assert(sizeof(SmemDyn) <= 74 * 1024, "3 CTAs per SM (227 KB, 1 KB reserved per CTA)");
+    static_assert(4 * (sizeof(SmemDyn) + 1024) <= 227 * 1024, "4 CTAs per SM (227 KB, 1 KB reserved per CTA)");
 #pragma unroll
     for (int k = 0; k < DWORDS / (4 * THREADS); ++k) reinterpret_cast<uint4 *>(sm.dwin)[tid + k * THREADS] = make_uint4(0u, 0u, 0u, 0u);
     if (tid == THREADS - 2) {
@@ -563,18 +564,28 @@ k_render(int n, EnvState st, const render::Camera *__restrict__ cams, hope_param
             fx0 = min(fx0, fx); fx1 = max(fx1, fx); fy0 = min(fy0, fy); fy1 = max(fy1, fy);
         }
         sm.fast = (1 >= c.ulo && OBS - 2 <= c.uhi && 1 >= c.vlo && OBS - 2 <= c.vhi && fx0 >= 0 && fy0 >= 0 && fx1 <= fmax_ && fy1 <= fmax_) ? 1 : 0;
-        // staged window: the on-screen part of the lattice's bounding box, whole 16-byte chunks (64 pixels) per row
         const int wx0 = max(fx0 >> 16, 0), wx1 = min(fx1 >> 16, WIN - 1), wy0 = max(fy0 >> 16, 0), wy1 = min(fy1 >> 16, WIN - 1);
-        int nrows = 0, nch = 0, cb0 = 0;
-        if (wx0 <= wx1 && wy0 <= wy1) {
-            nrows = min(wy1 - wy0 + 1, WROWS);
-            cb0 = wx0 >> 6; nch = min((wx1 >> 6) - cb0 + 1, WCHUNK);
-        }
-        sm.wy0 = wy0; sm.nrows = nrows; sm.cb0 = cb0; sm.nch = nch;
         sm.cam.wx0 = wx0; sm.cam.wy0 = wy0; sm.cam.wx1 = wx1; sm.cam.wy1 = wy1;  // on-screen part of the lattice's bounding box (empty: wx0 > wx1 or wy0 > wy1)
+        // staged windows: the on-screen part of the bounding box of either half of the lattice (v = 1 .. 126 and 129 .. 254),
+        // whole 16-byte chunks (64 pixels) per row
+        for (int h = 0; h < 2; ++h) {
+            int gx0 = 0x7fffffff, gx1 = -0x7fffffff - 1, gy0 = 0x7fffffff, gy1 = -0x7fffffff - 1;
+            for (int k = 0; k < 4; ++k) {
+                const int xc = ((k & 1) ? OBS - 2 : 1) + c.cx0, yc = ((k & 2) ? OBS / 2 - 2 : 1) + h * (OBS / 2) + c.cy0;
+                const int fx = c.a0 + c.a1 * xc + c.a2 * yc, fy = c.b0 + c.b1 * xc + c.b2 * yc;
+                gx0 = min(gx0, fx); gx1 = max(gx1, fx); gy0 = min(gy0, fy); gy1 = max(gy1, fy);
+            }
+            const int hx0 = max(gx0 >> 16, 0), hx1 = min(gx1 >> 16, WIN - 1), hy0 = max(gy0 >> 16, 0), hy1 = min(gy1 >> 16, WIN - 1);
+            int nrows = 0, nch = 0, cb0 = 0;
+            if (hx0 <= hx1 && hy0 <= hy1) {
+                cb0 = hx0 >> 6; nch = (hx1 >> 6) - cb0 + 1;
+                nrows = min(hy1 - hy0 + 1, SWIN_BYTES / (16 * nch));  // (never the bound: see SWIN_BYTES)
+            }
+            sm.wy0[h] = hy0; sm.nrows[h] = nrows; sm.cb0[h] = cb0; sm.nch[h] = nch;
+        }
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(nrows * nch * 16) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(sm.nrows[0] * sm.nch[0] * 16) : "memory");
     }
     if (tid >= THREADS - 2 - NCOLOR && tid < THREADS - 2) {
         const int k = tid - (THREADS - 2 - NCOLOR);
@@ -646,15 +657,22 @@ k_render(int n, EnvState st, const render::Camera *__restrict__ cams, hope_param
     const Camera &cam = sm.cam;
     const int ndyn = sm.ndyn, ntraj = ndyn - 1;
     // ---------------------------------------------------------------- 2. request the static rows of the window
-    {
-        const int nrows = sm.nrows, bytes = sm.nch * 16;
-        const uint8_t *src = scr + (size_t)sm.wy0 * SCREEN_PITCH + sm.cb0 * 16;
+    // every thread that reads what a bulk copy wrote watches the mbarrier phase itself
+    auto wait_phase = [&](unsigned b, int parity) {
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(b), "r"(parity) : "memory");
+    };
+    auto stage_rows = [&](int h) {
+        const int nrows = sm.nrows[h], bytes = sm.nch[h] * 16;
+        const uint8_t *src = scr + (size_t)sm.wy0[h] * SCREEN_PITCH + sm.cb0[h] * 16;
         for (int r = tid; r < nrows; r += THREADS) {
-            const unsigned dst = (unsigned)__cvta_generic_to_shared(&sm.swin[r * WPITCH]);
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(&sm.swin[r * bytes]);
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          :: "r"(dst), "l"(src + (size_t)r * SCREEN_PITCH), "r"(bytes), "r"(bar) : "memory");
         }
-    }
+    };
+    stage_rows(0);
     const int dsplit = (ndyn + 1) >> 1;
     static_assert(NDYN <= 30, "(NDYN + 1) / 2 codes per window fit a nibble");
     if (warp < 2) {  // the windows of the dynamic layer, warp g for window g: bounding box of its boxes, cut to what the lattice can touch
@@ -685,11 +703,7 @@ k_render(int n, EnvState st, const render::Camera *__restrict__ cams, hope_param
     const int slot0 = sm.slot0;
     // span-table row of dynamic box d: its slot of the trajectory ring buffer (the records arrive in ring order), TRAJ for the vehicle
     auto dslot = [&](int d) -> int { const int s = slot0 + d - 1; return d == 0 ? TRAJ : (s >= TRAJ ? s - TRAJ : s); };
-    {   // the span records have landed (requested first thing): what is computed below overwrites the stale ones
-        unsigned done = 0;
-        while (!done)
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar2) : "memory");
-    }
+    wait_phase(bar2, 0);  // the span records have landed (requested first thing): what is computed below overwrites the stale ones
     for (int idx = tid; idx < ndyn * DROWS; idx += THREADS) {
         const int d = idx / DROWS, r = idx - d * DROWS;
         if (sm.hit[d]) continue;
@@ -827,18 +841,13 @@ k_render(int n, EnvState st, const render::Camera *__restrict__ cams, hope_param
         sm.probe = idx;
     }
     __syncthreads();
-    {   // the staged static rows have landed
-        unsigned done = 0;
-        while (!done)
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar) : "memory");
-    }
-    // ---------------------------------------------------------------- 5. gather 64 x 64 x (2 x 2 samples)
+    wait_phase(bar, 0);  // the static rows of the first half have landed
+    // ---------------------------------------------------------------- 5. gather 64 x 64 x (2 x 2 samples), one half of the image at a time
     {
         // a warp resolves a tile of 8 x 4 output pixels per round (16 rounds): a compact patch of the screen, so that few warps
         // meet the dynamic layer's window; its stores are 4 x 8 bytes per channel and merge with the neighbour tiles' in L2
         const int il = lane & 7, jl = lane >> 3;
         uint8_t *out = img + (size_t)env * 3 * IMG * IMG;
-        const int woff = sm.wy0 * WPITCH + sm.cb0 * 16;  // static pixel (sx, sy): 2 bits of swin[sy * WPITCH + (sx >> 2) - woff]
         const uint32_t round2 = 2u | (2u << 10) | (2u << 20);  // (a + b + c + d + 2) >> 2 per 10-bit lane
         // palette indices of the dynamic layer on the four samples of output pixel (i, j), one per byte, 0: none
         auto dyn_of = [&](int i_, int j_, int fxb, int fyb) -> unsigned {
@@ -874,9 +883,21 @@ k_render(int n, EnvState st, const render::Camera *__restrict__ cams, hope_param
             }
             return out4;
         };
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+        if (half) {  // the other half's rows through the same buffer, once everybody is done with the first
+            __syncthreads();
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (tid == THREADS - 2) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(sm.nrows[1] * sm.nch[1] * 16) : "memory");
+            stage_rows(1);
+            wait_phase(bar, 1);
+        }
+        const int wpitch = sm.nch[half] * 16;
+        const int woff = sm.wy0[half] * wpitch + sm.cb0[half] * 16;  // static pixel (sx, sy): 2 bits of swin[sy * wpitch + (sx >> 2) - woff]
+        const int r0 = half * (IMG * IMG / THREADS / 2), r1 = r0 + IMG * IMG / THREADS / 2;
         if (sm.fast) {
 #pragma unroll 2
-            for (int r = 0; r < IMG * IMG / THREADS; ++r) {
+            for (int r = r0; r < r1; ++r) {
                 const int i = ((warp & 7) << 3) | il, j = (r << 2) | jl;
                 const int xc = 4 * i + 1 + cam.cx0, yc = 4 * j + 1 + cam.cy0;
                 const int fxb = a0 + a1 * xc + a2 * yc, fyb = b0 + b1 * xc + b2 * yc;
@@ -886,7 +907,7 @@ k_render(int n, EnvState st, const render::Camera *__restrict__ cams, hope_param
                 for (int k = 0; k < 4; ++k) {
                     const int fx = fxb + ((k & 1) ? a1 : 0) + ((k >> 1) ? a2 : 0), fy = fyb + ((k & 1) ? b1 : 0) + ((k >> 1) ? b2 : 0);
                     const int sx = fx >> 16, sy = fy >> 16;
-                    st4[k] = ((unsigned)sm.swin[sy * WPITCH + (sx >> 2) - woff] >> (2 * (sx & 3))) & 3u;
+                    st4[k] = ((unsigned)sm.swin[sy * wpitch + (sx >> 2) - woff] >> (2 * (sx & 3))) & 3u;
                 }
                 uint32_t sum = round2;
 #pragma unroll
@@ -902,7 +923,7 @@ k_render(int n, EnvState st, const render::Camera *__restrict__ cams, hope_param
             const unsigned xmaxv = (WIN << 16) - 1;
             const int ulo = cam.ulo, uhi = cam.uhi, vlo = cam.vlo, vhi = cam.vhi;
 #pragma unroll 1
-            for (int r = 0; r < IMG * IMG / THREADS; ++r) {
+            for (int r = r0; r < r1; ++r) {
                 const int i = ((warp & 7) << 3) | il, j = (r << 2) | jl;
                 const int ub = 4 * i + 1, xc = ub + cam.cx0;
                 const int vb = 4 * j + 1, yc = vb + cam.cy0;
@@ -920,7 +941,7 @@ k_render(int n, EnvState st, const render::Camera *__restrict__ cams, hope_param
                             idx = (dyn4 >> (8 * k)) & 0xffu;
                             if (idx == 0u) {
                                 const int sx = fx >> 16, sy = fy >> 16;
-                                idx = ((unsigned)sm.swin[sy * WPITCH + (sx >> 2) - woff] >> (2 * (sx & 3))) & 3u;
+                                idx = ((unsigned)sm.swin[sy * wpitch + (sx >> 2) - woff] >> (2 * (sx & 3))) & 3u;
                             }
                         }
                     }
@@ -930,6 +951,7 @@ k_render(int n, EnvState st, const render::Camera *__restrict__ cams, hope_param
                 o[0] = (uint8_t)((sum >> 2) & 0xffu); o[IMG * IMG] = (uint8_t)((sum >> 12) & 0xffu); o[2 * IMG * IMG] = (uint8_t)((sum >> 22) & 0xffu);
             }
         }
+        }  // half
     }
 }
 
