@@ -18,11 +18,13 @@
 //   of the colour index and spans are OR-ed in with shared-memory atomics, every (shape, row) pair one work item dealt round
 //   the 256 threads (pygame's scan conversion restated literally per row; the start-box outline = 5 Bresenham segments whose
 //   pixel run on any row has a closed form).
-//   k_render (CTA / env, 256 threads, 73 KB of shared memory, 3 CTAs per SM), every step:
+//   k_render (CTA / env, 256 threads, 54 KB of shared memory, 4 CTAs per SM), every step:
 //   1. set-up: the screen window the 128 x 128 sample lattice can touch (<= 360 x 360 pixels, rotated view); one thread per
 //      dynamic box (vehicle + the last <= 20 trajectory boxes) prepares its scan-conversion record;
-//   2. the window's rows of the cached static screen are fetched with cp.async.bulk (one copy per row, <= 112 B, completion
-//      counted by one mbarrier) and land under steps 3 and 4: 40 KB of shared memory hold them;
+//   2. the window's rows of the cached static screen are fetched with cp.async.bulk (one copy per row, <= 96 B, completion
+//      counted by one mbarrier) and land under steps 3 and 4.  They go through a 26.7 KB buffer one HALF of the image at a time
+//      (the rows of output rows 32-63 are requested when the gather of rows 0-31 is done): the whole view would take 40 KB in the
+//      worst rotation, and the difference is a fourth resident CTA per SM;
 //   3. span table: the run every dynamic box paints on each of its <= 64 screen rows.  A trajectory box stays where it is for the
 //      20 steps it is drawn (only the camera moves), so its runs are computed ONCE, the step it joins the trail, and kept in HBM
 //      beside the pose they belong to (6.4 KB per env: one record per slot of the trajectory ring buffer).  All 20 records arrive
@@ -32,7 +34,7 @@
 //      row and writes its boxes' runs on it old -> new, whole words between the ends.  The older and the newer half of the boxes
 //      have a window each (2 x 12 KB; the gather asks the newer one first): the two halves are painted side by side by the two
 //      half-warps, a row owner walks at most 11 boxes, and 11 codes fit the nibble.  A trail whose windows exceed their 12 KB (more
-//      than ~ 150 x 150 pixels per half inside the view) is resolved per lattice sample instead: newest box first, every thread
+//      than ~ 140 x 140 pixels per half inside the view) is resolved per lattice sample instead: newest box first, every thread
 //      tests ITS samples of the box's lattice rectangle against the span table;
 //   5. gather: a warp resolves 8 x 4 output pixels per round; an output pixel = 4 samples; a sample = the dynamic layer's box if any,
 //      else the 2-bit static pixel of the staged rows; palette sums in one packed word (10-bit lanes), rounded mean, uint8
@@ -40,7 +42,7 @@
 // HBM traffic per env-step: 12 288 B written + 20-41 KB of static rows + 6.4 KB of span records read + ~1.3 KB of pose /
 // trajectory (measured: 48 KB read, 11.5 KB written per image).
 // History (profiles/r02_ncu_k_render_history.txt): round 1 painted the whole window per step with one thread per window row
-// (6.5 ms per 65 536 images); order-free painting of four quadrant windows 4.9 ms; this design 2.9 ms.
+// (6.5 ms per 65 536 images); order-free painting of four quadrant windows 4.9 ms; this design 2.7 ms.
 #pragma once
 
 namespace render {
