@@ -247,3 +247,24 @@ def test_dlp_reader_refuses_foreign_pickles(tmp_path):
     p.write_bytes(pickle.dumps([(eval, ("1+1",))]))
     with pytest.raises(pickle.UnpicklingError, match="refusing"):
         dlp.read_dlp(str(p))
+
+
+def test_trajectory_rendering_settings_follow_configs():
+    """configs.py:86 TRAJ_RENDER_LEN and :105 RENDER_TRAJ reach k_render as a run-time length (hope_set_render_traj); the palette
+    keeps its 25 rows, the trajectory colours of a shorter trail in rows 5 .. 5 + len - 1 (configs.py:87-88 TRAJ_COLORS)."""
+    from hope_b200 import refconfig
+    c = refconfig.defaults()
+    assert refconfig.traj_render_len(c) == 20 and refconfig.image_supported(c)
+    pal20 = refconfig.palette(c)
+    assert pal20.shape == (25, 3) and tuple(pal20[5]) == (10, 10, 10) and tuple(pal20[24]) == (10, 10, 200)
+    c.TRAJ_RENDER_LEN = 7
+    pal7 = refconfig.palette(c)
+    want = np.linspace(np.array(c.TRAJ_COLOR_LOW), np.array(c.TRAJ_COLOR_HIGH), 7, endpoint=True, dtype=np.uint8)[:, :3]
+    assert refconfig.traj_render_len(c) == 7 and refconfig.image_supported(c)
+    assert pal7.shape == (25, 3) and np.array_equal(pal7[5:12], want) and np.array_equal(pal7[:5], pal20[:5])
+    c.RENDER_TRAJ = False
+    assert refconfig.traj_render_len(c) == 0 and refconfig.image_supported(c)
+    c.RENDER_TRAJ, c.TRAJ_RENDER_LEN = True, 21
+    assert not refconfig.image_supported(c)   # the trajectory ring buffer of k_advance holds 20 poses
+    c.TRAJ_RENDER_LEN, c.K = 20, 10
+    assert not refconfig.image_supported(c)   # the raster geometry itself stays compile-time
