@@ -193,9 +193,18 @@ def record_episodes(mods, level, n_episodes, seed, steps_per_episode=200, follow
     return out
 
 
-def record_images(mods, level, n_episodes, seed, steps_per_episode=40):
-    """Image observation of the unmodified reference (car_parking_base.py:301-350, observation_processor.py)."""
+def record_images(mods, level, n_episodes, seed, steps_per_episode=40, traj_render_len=None, render_traj=True):
+    """Image observation of the unmodified reference (car_parking_base.py:301-350, observation_processor.py).
+    traj_render_len / render_traj: configs.py:86-88 TRAJ_RENDER_LEN (with the TRAJ_COLORS it implies) and :105 RENDER_TRAJ are read
+    by CarParking._render as module globals of car_parking_base (star-imported from configs): setting them there is what editing
+    configs.py does, without touching a reference file."""
     cpb, wrap, vehicle, rs, pmn, configs = mods
+    saved = (cpb.TRAJ_RENDER_LEN, cpb.TRAJ_COLORS, cpb.RENDER_TRAJ)
+    if traj_render_len is not None:
+        cpb.TRAJ_RENDER_LEN = int(traj_render_len)
+        cpb.TRAJ_COLORS = list(map(tuple, np.linspace(np.array(configs.TRAJ_COLOR_LOW), np.array(configs.TRAJ_COLOR_HIGH),
+                                                      int(traj_render_len), endpoint=True, dtype=np.uint8)))  # configs.py:87-88
+    cpb.RENDER_TRAJ = bool(render_traj)
     raw = cpb.CarParking(render_mode="rgb_array", fps=100, verbose=False,
                          use_lidar_observation=True, use_img_observation=True, use_action_mask=True)
     env = wrap.CarParkingWrapper(raw)
@@ -244,6 +253,7 @@ def record_images(mods, level, n_episodes, seed, steps_per_episode=40):
             rec["done"].append(done)
             if done:
                 break
+    cpb.TRAJ_RENDER_LEN, cpb.TRAJ_COLORS, cpb.RENDER_TRAJ = saved
     out = {k: np.asarray(v) for k, v in rec.items()}
     out.update({"scene_" + k: np.asarray(v) for k, v in scn.items()})
     return out
@@ -327,7 +337,7 @@ def main():
     ap.add_argument("--episodes", type=int, default=3)
     ap.add_argument("--scenes", type=int, default=96)
     ap.add_argument("--follow-episodes", type=int, default=12)
-    ap.add_argument("--only", default=None, help="'rs', 'tables', 'images' or 'collide': regenerate just that fixture")
+    ap.add_argument("--only", default=None, help="'rs', 'tables', 'images', 'trajcfg' or 'collide': regenerate just that fixture")
     ap.add_argument("--image-episodes", type=int, default=4)
     args = ap.parse_args()
     out = os.path.abspath(args.out)
@@ -342,6 +352,13 @@ def main():
             im = record_images(mods, level, args.image_episodes, 777)
             np.savez_compressed(os.path.join(out, f"images_{level}.npz"), **im)
             print(level, "image steps", len(im["traj_len"]), "max traj", int(im["traj_len"].max()))
+    if args.only in (None, "trajcfg"):
+        # the image observation under other trajectory settings (what hope_set_render_traj mirrors)
+        for tag, kw in (("len7", dict(traj_render_len=7)), ("off", dict(render_traj=False))):
+            im = record_images(mods, "Normal", 2, 4242, steps_per_episode=30, **kw)
+            im["traj_render_len"] = np.int32(kw.get("traj_render_len", 20) if kw.get("render_traj", True) else 0)
+            np.savez_compressed(os.path.join(out, f"images_traj_{tag}.npz"), **im)
+            print("trajectory settings", tag, "image steps", len(im["traj_len"]), "max traj", int(im["traj_len"].max()))
     if args.only in (None, "collide"):
         parts = [record_episodes(mods, level, 25, 9000 + 100 * k, env_collide=True) for k, level in enumerate(("Normal", "Complex", "Extrem"))]
         merged = {}

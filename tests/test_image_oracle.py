@@ -40,6 +40,35 @@ def test_golden_images_replay_bit_exact(golden_dir, level):
     assert g["traj_len"].max() > io.TRAJ_RENDER_LEN  # the 20-box window is exercised
 
 
+@pytest.mark.parametrize("tag", ["len7", "off"])
+def test_golden_images_under_other_trajectory_settings(golden_dir, tag):
+    """configs.py:86 TRAJ_RENDER_LEN = 7 and :105 RENDER_TRAJ = False, recorded from the unmodified reference
+    (oracle/make_golden.py --only trajcfg): pins the oracle's traj_render_len parameter, against which the GPU tests
+    check hope_set_render_traj."""
+    g = dict(np.load(os.path.join(golden_dir, f"images_traj_{tag}.npz")))
+    length = int(g["traj_render_len"])
+    assert length == {"len7": 7, "off": 0}[tag]
+    n_ep = len(g["scene_start"])
+    book = io.TrajectoryBook(n_ep)
+    last_ep, checked, differs = -1, 0, 0
+    for k in range(len(g["ep"])):
+        ep = int(g["ep"][k])
+        rings = io.scene_rings(g["scene_obs"][ep], g["scene_nverts"][ep])
+        scene = (g["scene_start"][ep], g["scene_dest"][ep], g["scene_bounds"][ep], rings)
+        if ep != last_ep:
+            book.reset(ep, g["scene_start"][ep])
+            assert np.array_equal(io.render_observation(*scene, book.traj[ep], length), g["scene_reset_img"][ep])
+            last_ep = ep
+        book.step(ep, g["pose"][k], g["substeps"][k], g["retreated"][k])
+        assert len(book.traj[ep]) == int(g["traj_len"][k])
+        if k % 2 == 0:
+            assert np.array_equal(io.render_observation(*scene, book.traj[ep], length), g["img"][k]), f"step {k}"
+            checked += 1
+            if k % 10 == 0 and len(book.traj[ep]) > 8:  # the setting matters: the default trail paints other bytes
+                differs += not np.array_equal(io.render_observation(*scene, book.traj[ep]), g["img"][k])
+    assert checked >= 25 and g["traj_len"].max() > 20 and differs > 0
+
+
 def test_downsample_equals_cv2_resize():
     cv2 = pytest.importorskip("cv2")
     rng = np.random.default_rng(5)
