@@ -888,10 +888,12 @@ k_render(int n, EnvState st, const render::Camera *__restrict__ cams, hope_param
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
         if (half) {  // the other half's rows through the same buffer, once everybody is done with the first
-            // (this thread has seen phase 0 complete: the arrival opens phase 1, and it is posted before any copy of that phase)
-            if (tid == THREADS - 2) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(sm.nrows[1] * sm.nch[1] * 16) : "memory");
+            // The arrival that opens phase 1 comes AFTER the block barrier: every thread has left its phase-0 wait by then (an empty
+            // second window completes phase 1 at once, and a thread still polling parity 0 would then wait for phase 2 for ever).
+            // Copies of other threads may complete before it is posted: the transaction count may go negative in between.
             __syncthreads();
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (tid == THREADS - 2) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(sm.nrows[1] * sm.nch[1] * 16) : "memory");
             stage_rows(1);
             wait_phase(bar, 1);
         }
